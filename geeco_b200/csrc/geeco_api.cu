@@ -1,0 +1,729 @@
+// C-ABI entry points, context / workspace planning and step orchestration.
+// Public contract and reference citations: include/geeco_b200.h.
+#include "common.cuh"
+#include "tail.cuh"
+#include "plan.cuh"
+#include "../../include/geeco_b200.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// error string + launch counter
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static long long g_launches = 0;
+
+void geeco_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void geeco_count_launch(int n) { g_launches += n; }
+
+extern "C" const char* geeco_last_error(void) { return g_err; }
+extern "C" int geeco_version(void) { return 100; }
+extern "C" int64_t geeco_launch_count(int32_t reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// fp32 emulation of graph.py:17-28 (every operand is a float32 tensor in the reference graph)
+static float harmonic_f32(int t) {
+  volatile float acc = 0.f;
+  for (int i = 1; i <= t; ++i) acc = acc + 1.0f / (float)i;
+  return acc;
+}
+extern "C" int geeco_alpha_table(int32_t K, float* out) {
+  if (K < 1 || !out) { geeco_set_error("alpha_table: bad arguments"); return GEECO_ERR_INVALID; }
+  const float T = (float)K, HT = harmonic_f32(K);
+  for (int t = 1; t <= K; ++t) {
+    volatile float lhs = 2.0f * ((T - (float)t) + 1.0f);
+    volatile float diff = HT - harmonic_f32(t - 1);
+    volatile float rhs = (T + 1.0f) * diff;
+    out[t - 1] = lhs - rhs;
+  }
+  return GEECO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry builders
+// ------------------------------------------------------------------------------------------
+static void same_pad(int in, int k, int s, int* out, int* before) {
+  *out = (in + s - 1) / s;
+  int total = (*out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  *before = total / 2;
+}
+
+GatherGeom conv_fwd_geom(int H, int W, int Cs, int Cw, int Cout, int stride, int imgs_per_group) {
+  GatherGeom g;
+  memset(&g, 0, sizeof(g));
+  int Ho, Wo, pt, pl;
+  same_pad(H, 3, stride, &Ho, &pt);
+  same_pad(W, 3, stride, &Wo, &pl);
+  g.Hs = H; g.Ws = W; g.Cs = Cs; g.Hm = Ho; g.Wm = Wo; g.sy = stride; g.sx = stride;
+  g.ntaps = 9;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int t = ky * 3 + kx;
+      g.dy[t] = ky - pt; g.dx[t] = kx - pl; g.wbase[t] = t * Cw;
+    }
+  g.Cw = Cw; g.ldb = Cout; g.transB = 0; g.Nn = Cout;
+  g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1; g.dy0 = 0; g.dx0 = 0;
+  g.imgs_per_group = imgs_per_group;
+  g.b_group_stride = 9ll * Cw * Cout;
+  g.bias_group_stride = Cout;
+  return g;
+}
+
+// data-gradient geometry of input-pixel class (py, px); returns false when the class has no pixels/taps
+bool conv_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, GatherGeom* out) {
+  GatherGeom g;
+  memset(&g, 0, sizeof(g));
+  int Ho, Wo, pt, pl;
+  same_pad(H, 3, stride, &Ho, &pt);
+  same_pad(W, 3, stride, &Wo, &pl);
+  g.Hs = Ho; g.Ws = Wo; g.Cs = Cout;
+  g.Hm = (H - py + stride - 1) / stride; g.Wm = (W - px + stride - 1) / stride;
+  if (g.Hm <= 0 || g.Wm <= 0) return false;
+  g.sy = 1; g.sx = 1;
+  int nt = 0;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ny = py + pt - ky;
+    if (((ny % stride) + stride) % stride) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int nx = px + pl - kx;
+      if (((nx % stride) + stride) % stride) continue;
+      // floor division (ny may be negative)
+      g.dy[nt] = (ny >= 0) ? ny / stride : -((-ny + stride - 1) / stride);
+      g.dx[nt] = (nx >= 0) ? nx / stride : -((-nx + stride - 1) / stride);
+      g.wbase[nt] = (ky * 3 + kx) * Cin * Cout;
+      ++nt;
+    }
+  }
+  if (!nt) return false;
+  g.ntaps = nt;
+  g.Cw = Cout; g.ldb = Cout; g.transB = 1; g.Nn = Cin;
+  g.Hd = H; g.Wd = W; g.dsy = stride; g.dsx = stride; g.dy0 = py; g.dx0 = px;
+  g.imgs_per_group = imgs_per_group;
+  g.b_group_stride = 9ll * Cin * Cout;
+  g.bias_group_stride = 0;
+  *out = g;
+  return true;
+}
+
+GatherGeom dense_geom(int rows, int K, int Nn, int ldb, int transB) {
+  GatherGeom g;
+  memset(&g, 0, sizeof(g));
+  g.Hs = 1; g.Ws = 1; g.Cs = K; g.Hm = 1; g.Wm = 1; g.sy = 1; g.sx = 1; g.ntaps = 1;
+  g.Cw = K; g.ldb = ldb; g.transB = transB; g.Nn = Nn;
+  g.Hd = 1; g.Wd = 1; g.dsy = 1; g.dsx = 1;
+  g.imgs_per_group = rows;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static const char* kEncScopes[3] = {"GoalVMC/ConvEncoder", "GoalVMC/DynBuffEncoder", "GoalVMC/DynDiffEncoder"};
+static const int kEncChannels[7] = {32, 48, 64, 128, 192, 256, 256};   // graph.py:76-110
+static const int kEncStrides[8] = {1, 2, 2, 2, 2, 2, 2, 2};            // graph.py:78-113
+
+struct Carver {
+  char* base; size_t off;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~(size_t)255;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+static int add_param(geeco_ctx* c, const std::string& name, std::initializer_list<int64_t> shape) {
+  geeco_param_desc d;
+  memset(&d, 0, sizeof(d));
+  snprintf(d.name, sizeof(d.name), "%s", name.c_str());
+  d.ndim = (int)shape.size();
+  d.numel = 1;
+  int i = 0;
+  for (auto s : shape) { d.shape[i++] = s; d.numel *= s; }
+  c->arena_floats = (c->arena_floats + 3) & ~3ll;
+  d.offset = c->arena_floats;
+  c->arena_floats += d.numel;
+  c->params.push_back(d);
+  return (int)c->params.size() - 1;
+}
+
+static int validate(const geeco_config* cfg) {
+  if (!cfg) { geeco_set_error("config is NULL"); return GEECO_ERR_INVALID; }
+  if (cfg->img_channels != 3 && cfg->img_channels != 4) {
+    geeco_set_error("Unsupported number of channels for input frame: %d!", cfg->img_channels);   // estimator.py:173-175
+    return GEECO_ERR_INVALID;
+  }
+  if (cfg->img_height != 256 || cfg->img_width != 256) {
+    // graph.py:139,163,188 hard-code the 2x2 tiling of the joint state: 8 layers, 7 stride-2 -> 256 px only
+    geeco_set_error("the e2evmc graph is only defined for 256x256 inputs (2x2 conv8 map); got %dx%d",
+                    cfg->img_height, cfg->img_width);
+    return GEECO_ERR_INVALID;
+  }
+  if (cfg->window_size < 2 || cfg->window_size > 8) { geeco_set_error("window_size %d outside [2,8]", cfg->window_size); return GEECO_ERR_INVALID; }
+  if (cfg->batch_size < 1 || cfg->batch_size > 21845) { geeco_set_error("batch_size %d outside [1,21845]", cfg->batch_size); return GEECO_ERR_INVALID; }
+  if (cfg->dim_s_obs % 4 || cfg->dim_s_dyn % 4 || cfg->dim_s_diff % 4 || cfg->dim_h_lstm % 4 || cfg->dim_s_obs < 4 ||
+      cfg->dim_s_dyn < 4 || cfg->dim_s_diff < 4 || cfg->dim_h_lstm < 4 || cfg->dim_h_fc < 1) {
+    geeco_set_error("dim_s_obs/dim_s_dyn/dim_s_diff/dim_h_lstm must be positive multiples of 4");
+    return GEECO_ERR_INVALID;
+  }
+  if ((4 * (cfg->dim_s_obs + cfg->dim_s_dyn + cfg->dim_jnt_state + cfg->dim_s_diff)) % 4) return GEECO_ERR_INVALID;
+  if (cfg->num_grp_states < 1 || cfg->num_grp_states > 6) { geeco_set_error("num_grp_states %d outside [1,6]", cfg->num_grp_states); return GEECO_ERR_INVALID; }
+  if (cfg->dim_jnt_state < 1) { geeco_set_error("dim_jnt_state must be positive"); return GEECO_ERR_INVALID; }
+  if (cfg->precision != GEECO_FP32 && cfg->precision != GEECO_BF16) { geeco_set_error("unknown precision %d", cfg->precision); return GEECO_ERR_INVALID; }
+  return GEECO_OK;
+}
+
+// builds layer table, parameter table and (when base != NULL) the workspace pointers
+static int plan(geeco_ctx* c, char* ws_base) {
+  const geeco_config& cfg = c->cfg;
+  const int N = cfg.batch_size;
+  c->params.clear();
+  c->arena_floats = 0;
+  const bool bf16 = cfg.precision == GEECO_BF16;
+  c->CP = bf16 ? 8 : 4;
+  // ---- layer geometry
+  const int dims8[3] = {cfg.dim_s_obs, cfg.dim_s_dyn, cfg.dim_s_diff};
+  c->uniform8 = (dims8[0] == dims8[1] && dims8[1] == dims8[2]);
+  int H = cfg.img_height, Cin_real = cfg.img_channels, Cin_pad = c->CP;
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    L.Hin = H; L.stride = kEncStrides[l]; L.Hout = (H + L.stride - 1) / L.stride;
+    L.Cin_real = Cin_real; L.Cin_pad = Cin_pad;
+    for (int e = 0; e < 3; ++e) L.Cout[e] = l < 7 ? kEncChannels[l] : dims8[e];
+    L.grouped = l < 7 || c->uniform8;
+    H = L.Hout; Cin_real = L.Cout[0]; Cin_pad = L.Cout[0];
+  }
+  // ---- parameters, arena order = gradient-bucket order (late layers first)
+  const int xdim = 4 * (cfg.dim_s_obs + cfg.dim_s_dyn + cfg.dim_jnt_state + cfg.dim_s_diff);
+  const int Hl = cfg.dim_h_lstm, Fc = cfg.dim_h_fc, G = cfg.num_grp_states;
+  c->xdim = xdim;
+  const std::string dsc = "GoalVMC/LSTMDecoder/";
+  c->p_lstm_w = add_param(c, dsc + "lstm_cell/kernel", {xdim + Hl, 4 * Hl});
+  c->p_lstm_b = add_param(c, dsc + "lstm_cell/bias", {4 * Hl});
+  c->p_fc1_w = add_param(c, dsc + "fc1/kernel", {Hl, Fc});
+  c->p_fc1_b = add_param(c, dsc + "fc1/bias", {Fc});
+  c->p_head_w[0] = add_param(c, dsc + "pred_cmd_ee/kernel", {Fc, 3});
+  c->p_head_b[0] = add_param(c, dsc + "pred_cmd_ee/bias", {3});
+  c->p_head_w[1] = add_param(c, dsc + "logits_cmd_grp/kernel", {Fc, G});
+  c->p_head_b[1] = add_param(c, dsc + "logits_cmd_grp/bias", {G});
+  c->p_head_w[2] = add_param(c, dsc + "pred_aux_ee/kernel", {Fc, 3});
+  c->p_head_b[2] = add_param(c, dsc + "pred_aux_ee/bias", {3});
+  c->p_head_w[3] = add_param(c, dsc + "pred_aux_obj/kernel", {Fc, 3});
+  c->p_head_b[3] = add_param(c, dsc + "pred_aux_obj/bias", {3});
+  for (int l = 7; l >= 0; --l) {
+    LayerPlan& L = c->layers[l];
+    char nm[128];
+    for (int e = 0; e < 3; ++e) {
+      snprintf(nm, sizeof(nm), "%s/conv%d/kernel", kEncScopes[e], l + 1);
+      L.p_w[e] = add_param(c, nm, {3, 3, L.Cin_real, L.Cout[e]});
+    }
+    for (int e = 0; e < 3; ++e) {
+      snprintf(nm, sizeof(nm), "%s/conv%d/bias", kEncScopes[e], l + 1);
+      L.p_b[e] = add_param(c, nm, {L.Cout[e]});
+    }
+    if (l == 4) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[0] = c->arena_floats; }
+    if (l == 2) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[1] = c->arena_floats; }
+  }
+  c->arena_floats = (c->arena_floats + 3) & ~3ll;
+  c->bucket_end[2] = c->arena_floats;
+
+  // ---- workspace
+  Carver cv{ws_base, 0};
+  const size_t esz = bf16 ? 2 : 4;
+  const long long HW = (long long)cfg.img_height * cfg.img_width;
+  c->x0 = cv.take((size_t)3 * N * HW * c->CP * esz);
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    long long off = 0;
+    for (int e = 0; e < 3; ++e) { L.act_off[e] = off; off += (long long)N * L.Hout * L.Hout * L.Cout[e]; }
+    L.act_elems = off;
+    L.y = cv.take((size_t)off * esz);
+    L.g = cfg.training ? cv.take((size_t)off * esz) : nullptr;
+  }
+  c->NH = 9 + G;
+  c->state = (float*)cv.take(sizeof(float) * N * (xdim + Hl));
+  c->gates = (float*)cv.take(sizeof(float) * N * 4 * Hl);
+  c->c_cur = (float*)cv.take(sizeof(float) * N * Hl);
+  c->m_cur = (float*)cv.take(sizeof(float) * N * Hl);
+  c->state_out = (float*)cv.take(sizeof(float) * N * 2 * Hl);
+  c->c_carry = (float*)cv.take(sizeof(float) * N * Hl);
+  c->m_carry = (float*)cv.take(sizeof(float) * N * Hl);
+  c->fc1 = (float*)cv.take(sizeof(float) * N * Fc);
+  c->heads = (float*)cv.take(sizeof(float) * N * c->NH);
+  c->loss_parts = (float*)cv.take(sizeof(float) * N * 5);
+  c->dheads = (float*)cv.take(sizeof(float) * N * c->NH);
+  c->losses = (float*)cv.take(sizeof(float) * 8);
+  c->sc = (float*)cv.take(sizeof(float) * 8);
+  // fp32 staging of the first / last conv maps for the tail (bf16 mode converts conv8 output)
+  c->y8_f32 = bf16 ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
+  c->g8_f32 = (bf16 && cfg.training) ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
+  if (cfg.training) {
+    c->dfc1 = (float*)cv.take(sizeof(float) * N * Fc);
+    c->dgates = (float*)cv.take(sizeof(float) * N * 4 * Hl);
+    c->dstate = (float*)cv.take(sizeof(float) * N * (xdim + Hl));
+    // split-K partial buffer: worst case over all TN launches
+    long long cap = 0;
+    for (int l = 0; l < 8; ++l) {
+      LayerPlan& L = c->layers[l];
+      const int groups = L.grouped ? 3 : 1;
+      for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
+        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
+        long long need = gemm_tn_partial_floats(g, groups);
+        if (need > cap) cap = need;
+      }
+    }
+    {
+      GatherGeom g = dense_geom(N, xdim + Hl, 4 * Hl, 4 * Hl, 0);
+      long long need = gemm_tn_partial_floats(g, 1);
+      if (need > cap) cap = need;
+    }
+    c->partial_cap = cap;
+    c->partial = (float*)cv.take(sizeof(float) * cap);
+  }
+  if (bf16) {
+    int rc = plan_bf16(c, &cv.off, ws_base);
+    if (rc) return rc;
+  }
+  c->workspace_bytes = (cv.off + 255) & ~(size_t)255;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_query_sizes(const geeco_config* cfg, geeco_sizes* out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) { geeco_set_error("out is NULL"); return GEECO_ERR_INVALID; }
+  geeco_ctx tmp;
+  tmp.cfg = *cfg;
+  rc = plan(&tmp, nullptr);
+  if (rc) return rc;
+  out->arena_floats = tmp.arena_floats;
+  out->workspace_bytes = (int64_t)tmp.workspace_bytes;
+  out->num_params = (int32_t)tmp.params.size();
+  out->num_buckets = 3;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_create(const geeco_config* cfg, geeco_ctx** out) {
+  int rc = validate(cfg);
+  if (rc) return rc;
+  if (!out) { geeco_set_error("out is NULL"); return GEECO_ERR_INVALID; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    geeco_set_error("no CUDA device: geeco_b200 has no CPU fallback");
+    return GEECO_ERR_CUDA;
+  }
+  geeco_ctx* c = new geeco_ctx();
+  c->cfg = *cfg;
+  rc = plan(c, nullptr);
+  if (rc) { delete c; return rc; }
+  geeco_alpha_table(cfg->window_size, c->alpha);
+  *out = c;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_destroy(geeco_ctx* ctx) {
+  delete ctx;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_bind(geeco_ctx* c, float* theta, float* grad, float* m, float* v, void* workspace,
+                          int64_t workspace_bytes) {
+  if (!c || !theta || !workspace) { geeco_set_error("bind: NULL argument"); return GEECO_ERR_INVALID; }
+  if (c->cfg.training && (!grad || !m || !v)) { geeco_set_error("bind: training context needs grad/m/v arenas"); return GEECO_ERR_INVALID; }
+  if ((size_t)workspace_bytes < c->workspace_bytes) {
+    geeco_set_error("bind: workspace of %lld bytes < required %zu", (long long)workspace_bytes, c->workspace_bytes);
+    return GEECO_ERR_WORKSPACE;
+  }
+  if (((uintptr_t)workspace & 255) || ((uintptr_t)theta & 15) || ((uintptr_t)grad & 15) || ((uintptr_t)m & 15) || ((uintptr_t)v & 15)) {
+    geeco_set_error("bind: workspace must be 256-byte aligned, arenas 16-byte aligned");
+    return GEECO_ERR_INVALID;
+  }
+  c->theta = theta; c->grad = grad; c->m = m; c->v = v;
+  int rc = plan(c, (char*)workspace);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemset(c->sc, 0, sizeof(float) * 8));
+  CUDA_TRY(cudaMemset(c->c_carry, 0, sizeof(float) * c->cfg.batch_size * c->cfg.dim_h_lstm));
+  CUDA_TRY(cudaMemset(c->m_carry, 0, sizeof(float) * c->cfg.batch_size * c->cfg.dim_h_lstm));
+  c->bound = true;
+  c->weights_dirty = true;
+  c->fwd_done = false;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_param_info(const geeco_ctx* c, int32_t index, geeco_param_desc* out) {
+  if (!c || !out || index < 0 || index >= (int)c->params.size()) { geeco_set_error("param_info: bad index %d", index); return GEECO_ERR_INVALID; }
+  *out = c->params[index];
+  return GEECO_OK;
+}
+
+extern "C" int geeco_grad_bucket(const geeco_ctx* c, int32_t b, int64_t* offset, int64_t* numel) {
+  if (!c || b < 0 || b > 2 || !offset || !numel) { geeco_set_error("grad_bucket: bad arguments"); return GEECO_ERR_INVALID; }
+  const long long lo = b == 0 ? 0 : c->bucket_end[b - 1];
+  *offset = lo; *numel = c->bucket_end[b] - lo;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_params_changed(geeco_ctx* c, void* stream) {
+  if (!c || !c->bound) { geeco_set_error("params_changed: context not bound"); return GEECO_ERR_STATE; }
+  c->weights_dirty = true;
+  (void)stream;
+  return GEECO_OK;
+}
+
+extern "C" int geeco_set_step(geeco_ctx* c, int64_t t, void* stream) {
+  if (!c || !c->bound) { geeco_set_error("set_step: context not bound"); return GEECO_ERR_STATE; }
+  c->host_sc[0] = (float)t; c->host_sc[1] = 0.f; c->host_sc[2] = 0.f; c->host_sc[3] = 0.f;
+  CUDA_TRY(cudaMemcpyAsync(c->sc, c->host_sc, 4 * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return GEECO_OK;
+}
+
+extern "C" int geeco_set_lstm_state(geeco_ctx* c, const float* state_cm, void* stream) {
+  if (!c || !c->bound) { geeco_set_error("set_lstm_state: context not bound"); return GEECO_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = c->cfg.batch_size, Hl = c->cfg.dim_h_lstm;
+  if (!state_cm) {
+    CUDA_TRY(cudaMemsetAsync(c->c_carry, 0, sizeof(float) * N * Hl, st));
+    CUDA_TRY(cudaMemsetAsync(c->m_carry, 0, sizeof(float) * N * Hl, st));
+  } else {
+    CUDA_TRY(cudaMemcpy2DAsync(c->c_carry, sizeof(float) * Hl, state_cm, sizeof(float) * 2 * Hl, sizeof(float) * Hl, N, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpy2DAsync(c->m_carry, sizeof(float) * Hl, state_cm + Hl, sizeof(float) * 2 * Hl, sizeof(float) * Hl, N, cudaMemcpyDeviceToDevice, st));
+  }
+  return GEECO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// functional ops
+// ------------------------------------------------------------------------------------------
+extern "C" int geeco_dynimg(const float* in, float* out, int32_t N, int32_t K, int32_t H, int32_t W, int32_t C,
+                            const float* alpha, int32_t cluster, float* scratch, void* stream) {
+  if (!in || !out) { geeco_set_error("dynimg: NULL tensor"); return GEECO_ERR_INVALID; }
+  if (K < 2 || K > 16) { geeco_set_error("dynimg: window size K=%d outside [2,16]", K); return GEECO_ERR_INVALID; }
+  float tab[16];
+  if (!alpha) { geeco_alpha_table(K, tab); alpha = tab; }
+  const long long HWC = (long long)H * W * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cluster >= 0) {
+    int rc = launch_dynimg(in, out, N, K, HWC, alpha, cluster, st);
+    if (rc != GEECO_ERR_WORKSPACE) return rc;
+  }
+  if (!scratch) { geeco_set_error("dynimg: two-pass path needs a scratch buffer of 2*N floats"); return GEECO_ERR_INVALID; }
+  return launch_dynimg_twopass(in, out, scratch, N, K, HWC, alpha, st);
+}
+
+extern "C" int geeco_conv2d_same(const float* x, const float* w, const float* b, float* y, int32_t N, int32_t H,
+                                 int32_t W, int32_t Cin, int32_t Cout, int32_t stride, int32_t relu, void* stream) {
+  if (!x || !w || !y) { geeco_set_error("conv2d: NULL tensor"); return GEECO_ERR_INVALID; }
+  GatherGeom g = conv_fwd_geom(H, W, Cin, Cin, Cout, stride, N);
+  if (H != W) { int Wo, pl; same_pad(W, 3, stride, &Wo, &pl); g.Ws = W; g.Wm = Wo; g.Wd = Wo; }
+  return launch_gemm_nn_f32(g, x, w, b, nullptr, y, 1, b ? (relu ? EPI_BIAS_RELU : EPI_BIAS) : EPI_STORE,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int64_t geeco_conv2d_bwd_scratch_floats(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                                   int32_t stride) {
+  GatherGeom g = conv_fwd_geom(H, W, Cin, Cin, Cout, stride, N);
+  return gemm_tn_partial_floats(g, 1);
+}
+
+extern "C" int geeco_conv2d_same_bwd(const float* x, const float* w, const float* dy_pre, const float* relu_mask_x,
+                                     float* dw, float* db, float* dx, float* scratch, int64_t scratch_floats,
+                                     int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t stride,
+                                     void* stream) {
+  if (H != W) { geeco_set_error("conv2d_bwd: square inputs only"); return GEECO_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dw) {
+    GatherGeom g = conv_fwd_geom(H, W, Cin, Cin, Cout, stride, N);
+    int rc = launch_gemm_tn_f32(g, x, dy_pre, dw, db, scratch, scratch_floats, 1, 0, 0, st);
+    if (rc) return rc;
+  }
+  if (dx) {
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px) {
+        GatherGeom g;
+        if (!conv_dgrad_geom(H, W, Cin, Cout, stride, py, px, N, &g)) continue;
+        int rc = launch_gemm_nn_f32(g, dy_pre, w, nullptr, relu_mask_x, dx, 1, relu_mask_x ? EPI_MASK : EPI_STORE, st);
+        if (rc) return rc;
+      }
+  }
+  return GEECO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// model step (fp32 path here; bf16 path in step_bf16.cu)
+// ------------------------------------------------------------------------------------------
+static inline float* P(geeco_ctx* c, int idx) { return c->theta + c->params[idx].offset; }
+static inline float* GR(geeco_ctx* c, int idx) { return c->grad + c->params[idx].offset; }
+
+static TailDims tail_dims(const geeco_ctx* c) {
+  TailDims d;
+  d.N = c->cfg.batch_size; d.K = c->cfg.window_size; d.J = c->cfg.dim_jnt_state;
+  d.D_obs = c->cfg.dim_s_obs; d.D_dyn = c->cfg.dim_s_dyn; d.D_diff = c->cfg.dim_s_diff;
+  d.Hl = c->cfg.dim_h_lstm; d.Fc = c->cfg.dim_h_fc; d.G = c->cfg.num_grp_states;
+  d.lambda_aux = c->cfg.lambda_aux;
+  return d;
+}
+static TailParams tail_params(geeco_ctx* c) {
+  TailParams p;
+  p.w_fc1 = P(c, c->p_fc1_w); p.b_fc1 = P(c, c->p_fc1_b);
+  p.w_cmd_ee = P(c, c->p_head_w[0]); p.b_cmd_ee = P(c, c->p_head_b[0]);
+  p.w_grp = P(c, c->p_head_w[1]); p.b_grp = P(c, c->p_head_b[1]);
+  p.w_aux_ee = P(c, c->p_head_w[2]); p.b_aux_ee = P(c, c->p_head_b[2]);
+  p.w_aux_obj = P(c, c->p_head_w[3]); p.b_aux_obj = P(c, c->p_head_b[3]);
+  return p;
+}
+static TailGrads tail_grads(geeco_ctx* c) {
+  TailGrads p;
+  p.w_fc1 = GR(c, c->p_fc1_w); p.b_fc1 = GR(c, c->p_fc1_b);
+  p.w_cmd_ee = GR(c, c->p_head_w[0]); p.b_cmd_ee = GR(c, c->p_head_b[0]);
+  p.w_grp = GR(c, c->p_head_w[1]); p.b_grp = GR(c, c->p_head_b[1]);
+  p.w_aux_ee = GR(c, c->p_head_w[2]); p.b_aux_ee = GR(c, c->p_head_b[2]);
+  p.w_aux_obj = GR(c, c->p_head_w[3]); p.b_aux_obj = GR(c, c->p_head_b[3]);
+  return p;
+}
+
+static int check_batch(const geeco_ctx* c, const geeco_batch* b, bool need_labels) {
+  if (!c || !c->bound) { geeco_set_error("context not bound (call geeco_bind first)"); return GEECO_ERR_STATE; }
+  if (!b || !b->rgb || !b->target_rgb || !b->jnt_state) { geeco_set_error("batch: rgb / target_rgb / jnt_state must be given"); return GEECO_ERR_INVALID; }
+  if (need_labels && (!b->cmd || !b->ee_state || !b->obj_state)) { geeco_set_error("batch: cmd / ee_state / obj_state needed for the losses"); return GEECO_ERR_INVALID; }
+  return GEECO_OK;
+}
+
+// conv stack forward, fp32
+static int encoders_fwd_f32(geeco_ctx* c, cudaStream_t st) {
+  const int N = c->cfg.batch_size;
+  const float* src = (const float*)c->x0;
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    if (L.grouped) {
+      GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[0], L.stride, N);
+      g.b_group_stride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
+      g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+      int rc = launch_gemm_nn_f32(g, src, P(c, L.p_w[0]), P(c, L.p_b[0]), nullptr, (float*)L.y, 3, EPI_BIAS_RELU, st);
+      if (rc) return rc;
+    } else {
+      for (int e = 0; e < 3; ++e) {
+        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
+        const float* s = src + (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+        int rc = launch_gemm_nn_f32(g, s, P(c, L.p_w[e]), P(c, L.p_b[e]), nullptr, (float*)L.y + L.act_off[e], 1, EPI_BIAS_RELU, st);
+        if (rc) return rc;
+      }
+    }
+    src = (const float*)L.y;
+  }
+  return GEECO_OK;
+}
+
+static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, const float* y8, bool with_loss,
+                        cudaStream_t st) {
+  const geeco_config& cfg = c->cfg;
+  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm;
+  TailDims d = tail_dims(c);
+  LayerPlan& L8 = c->layers[7];
+  const bool carry = cfg.carry_state != 0;
+  int rc = launch_build_state(d, y8 + L8.act_off[0], y8 + L8.act_off[1], y8 + L8.act_off[2], b->jnt_state,
+                              carry ? c->m_carry : nullptr, c->state, st);
+  if (rc) return rc;
+  GatherGeom g = dense_geom(N, c->xdim + Hl, 4 * Hl, 4 * Hl, 0);
+  rc = launch_gemm_nn_f32(g, c->state, P(c, c->p_lstm_w), P(c, c->p_lstm_b), nullptr, c->gates, 1, EPI_BIAS, st);
+  if (rc) return rc;
+  rc = launch_lstm_cell(N, Hl, c->gates, carry ? c->c_carry : nullptr, c->c_cur, c->m_cur, c->state_out, st);
+  if (rc) return rc;
+  if (with_loss && cfg.l2_regularizer > 0.f) {
+    rc = launch_l2_term(c->theta, c->arena_floats, cfg.l2_regularizer, c->sc, st);
+    if (rc) return rc;
+  }
+  rc = launch_tail_fwd(d, tail_params(c), c->m_cur, c->fc1, c->heads, b->cmd, b->ee_state, b->obj_state, c->loss_parts,
+                       c->dheads, with_loss ? 1 : 0, st);
+  if (rc) return rc;
+  if (with_loss) {
+    rc = launch_loss_reduce(d, c->loss_parts, cfg.l2_regularizer > 0.f ? c->sc + 2 : nullptr, c->losses, st);
+    if (rc) return rc;
+  }
+  if (out) {
+    if (out->heads) CUDA_TRY(cudaMemcpyAsync(out->heads, c->heads, sizeof(float) * N * c->NH, cudaMemcpyDeviceToDevice, st));
+    if (out->fc1) CUDA_TRY(cudaMemcpyAsync(out->fc1, c->fc1, sizeof(float) * N * cfg.dim_h_fc, cudaMemcpyDeviceToDevice, st));
+    if (out->lstm_state) CUDA_TRY(cudaMemcpyAsync(out->lstm_state, c->state_out, sizeof(float) * N * 2 * Hl, cudaMemcpyDeviceToDevice, st));
+    if (out->losses && with_loss) CUDA_TRY(cudaMemcpyAsync(out->losses, c->losses, sizeof(float) * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  return GEECO_OK;
+}
+
+static int carry_update(geeco_ctx* c, cudaStream_t st) {
+  if (!c->cfg.carry_state) return GEECO_OK;
+  const size_t bytes = sizeof(float) * c->cfg.batch_size * c->cfg.dim_h_lstm;
+  CUDA_TRY(cudaMemcpyAsync(c->c_carry, c->c_cur, bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->m_carry, c->m_cur, bytes, cudaMemcpyDeviceToDevice, st));
+  return GEECO_OK;
+}
+
+static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, bool with_loss, cudaStream_t st) {
+  const geeco_config& cfg = c->cfg;
+  const bool bf16 = cfg.precision == GEECO_BF16;
+  int rc = launch_preprocess_geecof(b->rgb, b->target_rgb, c->x0, bf16 ? 1 : 0, c->CP, out ? out->dynbuff : nullptr,
+                                    out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
+                                    cfg.img_width, cfg.img_channels, c->alpha, 0, st);
+  if (rc) return rc;
+  const float* y8;
+  if (bf16) {
+    rc = encoders_fwd_bf16(c, st);
+    if (rc) return rc;
+    y8 = c->y8_f32;
+  } else {
+    rc = encoders_fwd_f32(c, st);
+    if (rc) return rc;
+    y8 = (const float*)c->layers[7].y;
+  }
+  return tail_forward(c, b, out, y8, with_loss, st);
+}
+
+extern "C" int geeco_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, void* stream) {
+  const bool with_loss = b && b->cmd && out && out->losses;
+  int rc = check_batch(c, b, with_loss);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = forward_impl(c, b, out, with_loss, st);
+  if (rc) return rc;
+  return carry_update(c, st);
+}
+
+extern "C" int geeco_step_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, void* stream) {
+  int rc = check_batch(c, b, true);
+  if (rc) return rc;
+  if (!c->cfg.training) { geeco_set_error("context was created with training = 0"); return GEECO_ERR_STATE; }
+  rc = forward_impl(c, b, out, true, (cudaStream_t)stream);
+  if (rc) return rc;
+  c->fwd_done = true;
+  return GEECO_OK;
+}
+
+static int conv_layer_bwd_f32(geeco_ctx* c, int l, cudaStream_t st) {
+  const int N = c->cfg.batch_size;
+  LayerPlan& L = c->layers[l];
+  const float* xin = l == 0 ? (const float*)c->x0 : (const float*)c->layers[l - 1].y;
+  const int ngroups = L.grouped ? 3 : 1;
+  for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
+    const long long in_off = L.grouped ? 0 : (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+    const float* gy = (const float*)L.g + (L.grouped ? 0 : L.act_off[e]);
+    GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
+    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
+    const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+    int rc = launch_gemm_tn_f32(g, xin + in_off, gy, GR(c, L.p_w[e]), GR(c, L.p_b[e]), c->partial, c->partial_cap,
+                                ngroups, wstride, bstride, st);
+    if (rc) return rc;
+    if (l == 0) continue;
+    for (int py = 0; py < L.stride; ++py)
+      for (int px = 0; px < L.stride; ++px) {
+        GatherGeom dg;
+        if (!conv_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, py, px, N, &dg)) continue;
+        dg.b_group_stride = wstride;
+        rc = launch_gemm_nn_f32(dg, gy, P(c, L.p_w[e]), nullptr, xin + in_off, (float*)c->layers[l - 1].g + in_off,
+                                ngroups, EPI_MASK, st);
+        if (rc) return rc;
+      }
+  }
+  return GEECO_OK;
+}
+
+extern "C" int geeco_step_backward(geeco_ctx* c, int32_t bucket, void* stream) {
+  if (!c || !c->bound || !c->fwd_done) { geeco_set_error("step_backward: call geeco_step_forward first"); return GEECO_ERR_STATE; }
+  if (bucket < 0 || bucket > 2) { geeco_set_error("step_backward: bucket %d outside [0,2]", bucket); return GEECO_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const geeco_config& cfg = c->cfg;
+  const bool bf16 = cfg.precision == GEECO_BF16;
+  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm;
+  int rc;
+  if (bucket == 0) {
+    TailDims d = tail_dims(c);
+    const bool carry = cfg.carry_state != 0;
+    rc = launch_tail_bwd(d, tail_params(c), tail_grads(c), c->m_cur, c->fc1, c->dheads, c->gates,
+                         carry ? c->c_carry : nullptr, c->dfc1, c->dgates, st);
+    if (rc) return rc;
+    GatherGeom gw = dense_geom(N, c->xdim + Hl, 4 * Hl, 4 * Hl, 0);
+    rc = launch_gemm_tn_f32(gw, c->state, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), c->partial, c->partial_cap, 1, 0, 0, st);
+    if (rc) return rc;
+    GatherGeom gx = dense_geom(N, 4 * Hl, c->xdim, 4 * Hl, 1);
+    rc = launch_gemm_nn_f32(gx, c->dgates, P(c, c->p_lstm_w), nullptr, nullptr, c->dstate, 1, EPI_STORE, st);
+    if (rc) return rc;
+    LayerPlan& L8 = c->layers[7];
+    const float* y8 = bf16 ? c->y8_f32 : (const float*)L8.y;
+    float* g8 = bf16 ? c->g8_f32 : (float*)L8.g;
+    rc = launch_scatter_dstate(d, c->dstate, c->xdim, y8 + L8.act_off[0], y8 + L8.act_off[1], y8 + L8.act_off[2],
+                               g8 + L8.act_off[0], g8 + L8.act_off[1], g8 + L8.act_off[2], st);
+    if (rc) return rc;
+  }
+  const int lhi = bucket == 0 ? 7 : (bucket == 1 ? 3 : 1);
+  const int llo = bucket == 0 ? 4 : (bucket == 1 ? 2 : 0);
+  if (bf16) return encoders_bwd_bf16(c, lhi, llo, st);
+  for (int l = lhi; l >= llo; --l) {
+    rc = conv_layer_bwd_f32(c, l, st);
+    if (rc) return rc;
+  }
+  return GEECO_OK;
+}
+
+extern "C" int geeco_step_update(geeco_ctx* c, float grad_scale, void* stream) {
+  if (!c || !c->bound || !c->fwd_done) { geeco_set_error("step_update: call geeco_step_forward/backward first"); return GEECO_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const geeco_config& cfg = c->cfg;
+  int rc = launch_adam(c->theta, c->grad, c->m, c->v, c->arena_floats, c->sc, cfg.lr, cfg.adam_beta1, cfg.adam_beta2,
+                       cfg.adam_eps, grad_scale, cfg.l2_regularizer, st);
+  if (rc) return rc;
+  c->weights_dirty = true;
+  c->fwd_done = false;
+  return carry_update(c, st);
+}
+
+extern "C" int geeco_train_step(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, float grad_scale,
+                                void* stream) {
+  int rc = geeco_step_forward(c, b, out, stream);
+  if (rc) return rc;
+  for (int bucket = 0; bucket < 3; ++bucket) {
+    rc = geeco_step_backward(c, bucket, stream);
+    if (rc) return rc;
+  }
+  return geeco_step_update(c, grad_scale, stream);
+}
+
+extern "C" int geeco_debug_buffer(const geeco_ctx* c, const char* name, void** ptr, int64_t* numel, int32_t* dtype) {
+  if (!c || !c->bound || !name || !ptr || !numel || !dtype) { geeco_set_error("debug_buffer: bad arguments"); return GEECO_ERR_INVALID; }
+  const geeco_config& cfg = c->cfg;
+  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm;
+  const int act_dt = cfg.precision == GEECO_BF16 ? 1 : 0;
+  *dtype = 0;
+  std::string s(name);
+  if (s == "x0") { *ptr = c->x0; *numel = 3ll * N * cfg.img_height * cfg.img_width * c->CP; *dtype = act_dt; return GEECO_OK; }
+  if (s.size() == 2 && (s[0] == 'y' || s[0] == 'g') && s[1] >= '1' && s[1] <= '8') {
+    const LayerPlan& L = c->layers[s[1] - '1'];
+    *ptr = s[0] == 'y' ? L.y : L.g; *numel = L.act_elems; *dtype = act_dt;
+    if (!*ptr) { geeco_set_error("debug_buffer: %s not allocated", name); return GEECO_ERR_INVALID; }
+    return GEECO_OK;
+  }
+  struct { const char* n; float* p; long long cnt; } tab[] = {
+      {"state", c->state, (long long)N * (c->xdim + Hl)}, {"gates", c->gates, (long long)N * 4 * Hl},
+      {"c", c->c_cur, (long long)N * Hl}, {"m", c->m_cur, (long long)N * Hl}, {"fc1", c->fc1, (long long)N * cfg.dim_h_fc},
+      {"heads", c->heads, (long long)N * c->NH}, {"dheads", c->dheads, (long long)N * c->NH},
+      {"dfc1", c->dfc1, (long long)N * cfg.dim_h_fc}, {"dgates", c->dgates, (long long)N * 4 * Hl},
+      {"dstate", c->dstate, (long long)N * c->xdim}, {"losses", c->losses, 8}, {"sc", c->sc, 8},
+      {"y8_f32", c->y8_f32, c->layers[7].act_elems}, {"g8_f32", c->g8_f32, c->layers[7].act_elems}};
+  for (auto& t : tab)
+    if (s == t.n) {
+      if (!t.p) { geeco_set_error("debug_buffer: %s not allocated", name); return GEECO_ERR_INVALID; }
+      *ptr = t.p; *numel = t.cnt; return GEECO_OK;
+    }
+  geeco_set_error("debug_buffer: unknown buffer '%s'", name);
+  return GEECO_ERR_INVALID;
+}

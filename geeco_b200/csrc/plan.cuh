@@ -1,0 +1,54 @@
+// Context layout shared by geeco_api.cu and the bf16 step (step_bf16.cu).
+#pragma once
+#include "common.cuh"
+#include "../../include/geeco_b200.h"
+#include <vector>
+
+struct LayerPlan {
+  int Hin, Hout, stride;
+  int Cin_real, Cin_pad;
+  int Cout[3];
+  bool grouped;               // the three encoders share shapes -> one grouped launch
+  int p_w[3], p_b[3];         // parameter-table indices
+  long long act_off[3];       // element offset of encoder e inside y / g
+  long long act_elems;
+  void* y;                    // post-ReLU output  [3][N][Hout][Hout][Cout]
+  void* g;                    // dL/d(pre-activation), same layout (training only)
+  // bf16 mode: packed weight copies (see step_bf16.cu)
+  void* w_fwd;                // [3][Cout][Kpad]  bf16, K-major
+  void* w_dgrad;              // [3][9][Cin][Cout] bf16 (tap-major, Cout contiguous)
+  int Kpad;
+};
+
+struct geeco_ctx {
+  geeco_config cfg;
+  std::vector<geeco_param_desc> params;
+  long long arena_floats = 0;
+  long long bucket_end[3] = {0, 0, 0};
+  size_t workspace_bytes = 0;
+  bool bound = false, weights_dirty = true, fwd_done = false, uniform8 = true;
+  int CP = 4, NH = 12, xdim = 0;
+  float alpha[16];
+  float host_sc[8];
+  LayerPlan layers[8];
+  int p_lstm_w, p_lstm_b, p_fc1_w, p_fc1_b, p_head_w[4], p_head_b[4];
+  float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
+  void* x0 = nullptr;
+  float *state, *gates, *c_cur, *m_cur, *state_out, *c_carry, *m_carry, *fc1, *heads, *loss_parts, *dheads, *losses, *sc;
+  float *y8_f32 = nullptr, *g8_f32 = nullptr;
+  float *dfc1 = nullptr, *dgates = nullptr, *dstate = nullptr, *partial = nullptr;
+  long long partial_cap = 0;
+  // bf16 extras
+  void* bf16_ws = nullptr;
+};
+
+GatherGeom conv_fwd_geom(int H, int W, int Cs, int Cw, int Cout, int stride, int imgs_per_group);
+bool conv_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, GatherGeom* out);
+GatherGeom dense_geom(int rows, int K, int Nn, int ldb, int transB);
+long long gemm_tn_partial_floats(const GatherGeom& g, int groups);
+void geeco_count_launch(int n);
+
+// step_bf16.cu
+int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base);
+int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st);
+int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st);

@@ -1,0 +1,408 @@
+// Rank pooling (dynamic image / dynamic difference) for sm_100a.
+//
+// Reference: src/models/e2evmc/graph.py:17-55 (`_H`, `_alpha`, `dynimg`) and :392-401 (the two
+// call sites of GEECO-F: the K-frame buffer and the [current, target] pair).
+//
+//   d   = sum_k alpha_k * x_k                       (products rounded, then summed in k order)
+//   out = (d - min_hwc d) / (max_hwc d - min_hwc d + 1e-6)      per sample
+//
+// The op is pure HBM streaming with one per-sample reduction in the middle.  To read the K-frame
+// buffer ONCE and write the normalised image ONCE, a thread-block CLUSTER owns one sample: every
+// CTA keeps its slice of the un-normalised d in shared memory, CTAs exchange (min, max) through
+// distributed shared memory, and the normalised slice is written from shared memory.  Loads are
+// 128-bit, read-only, no-L1-allocate; K is a template parameter so all K loads of a position are
+// in flight together.
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <float.h>
+
+namespace cg = cooperative_groups;
+
+struct AlphaTab { float a[16]; };
+
+static constexpr int RP_THREADS = 512;
+static constexpr int RP_MAX_CLUSTER = 16;
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ float4 f4_scale(float a, const float4& v) {
+  return make_float4(__fmul_rn(a, v.x), __fmul_rn(a, v.y), __fmul_rn(a, v.z), __fmul_rn(a, v.w));
+}
+__device__ __forceinline__ float4 f4_axpy(const float4& acc, float a, const float4& v) {
+  return make_float4(__fadd_rn(acc.x, __fmul_rn(a, v.x)), __fadd_rn(acc.y, __fmul_rn(a, v.y)),
+                     __fadd_rn(acc.z, __fmul_rn(a, v.z)), __fadd_rn(acc.w, __fmul_rn(a, v.w)));
+}
+__device__ __forceinline__ void f4_minmax(const float4& v, float& mn, float& mx) {
+  mn = fminf(mn, fminf(fminf(v.x, v.y), fminf(v.z, v.w)));
+  mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+}
+__device__ __forceinline__ float4 f4_norm(const float4& d, float mn, float rng) {
+  return make_float4(__fdiv_rn(d.x - mn, rng), __fdiv_rn(d.y - mn, rng), __fdiv_rn(d.z - mn, rng),
+                     __fdiv_rn(d.w - mn, rng));
+}
+
+// Block-wide then cluster-wide (min, max).  `s_red` holds 2*32 floats, `s_mm` 2*RP_MAX_CLUSTER per pair.
+__device__ __forceinline__ void cluster_minmax(float& mn, float& mx, float* s_red, float* s_mm, int pair,
+                                               int npairs) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { s_red[warp * 2] = mn; s_red[warp * 2 + 1] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    mn = lane < nwarps ? s_red[lane * 2] : FLT_MAX;
+    mx = lane < nwarps ? s_red[lane * 2 + 1] : -FLT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    const unsigned cl = cluster.num_blocks(), me = cluster.block_rank();
+    // lane r publishes this CTA's pair into CTA r's shared memory (DSMEM store)
+    if ((unsigned)lane < cl) {
+      float* remote = cluster.map_shared_rank(s_mm, lane);
+      remote[(pair * RP_MAX_CLUSTER + me) * 2] = mn;
+      remote[(pair * RP_MAX_CLUSTER + me) * 2 + 1] = mx;
+    }
+  }
+  __syncthreads();
+  if (pair == npairs - 1) cluster.sync();   // release/acquire: all CTAs' pairs are visible after this
+}
+__device__ __forceinline__ void cluster_minmax_read(float& mn, float& mx, const float* s_mm, int pair) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cl = cluster.num_blocks();
+  mn = FLT_MAX; mx = -FLT_MAX;
+  for (unsigned r = 0; r < cl; ++r) {
+    mn = fminf(mn, s_mm[(pair * RP_MAX_CLUSTER + r) * 2]);
+    mx = fmaxf(mx, s_mm[(pair * RP_MAX_CLUSTER + r) * 2 + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic dynimg: in [N,K,HWC] f32 -> out [N,HWC] f32 ; grid = (cluster, N), cluster dims (CL,1,1)
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(RP_THREADS) dynimg_cluster_kernel(const float* __restrict__ in,
+                                                                    float* __restrict__ out, long long total4,
+                                                                    long long per4, AlphaTab al) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_red[64];
+  __shared__ float s_mm[2 * RP_MAX_CLUSTER];
+  float4* sd = reinterpret_cast<float4*>(smem_raw);
+  const long long n = blockIdx.y;
+  const long long lo = (long long)blockIdx.x * per4;
+  long long hi = lo + per4; if (hi > total4) hi = total4;
+  const float4* base = reinterpret_cast<const float4*>(in) + n * K * total4;
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  constexpr int U = (K >= 8) ? 1 : (K >= 4 ? 2 : 4);
+  for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += (long long)U * RP_THREADS) {
+    float4 v[U][K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + (long long)u * RP_THREADS;
+      if (i < hi) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[u][k] = ldg_stream(base + k * total4 + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + (long long)u * RP_THREADS;
+      if (i < hi) {
+        float4 acc = f4_scale(al.a[0], v[u][0]);
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[u][k]);
+        sd[i - lo] = acc;
+        f4_minmax(acc, mn, mx);
+      }
+    }
+  }
+  cluster_minmax(mn, mx, s_red, s_mm, 0, 1);
+  cluster_minmax_read(mn, mx, s_mm, 0);
+  const float rng = __fadd_rn(__fsub_rn(mx, mn), 1e-6f);
+  float4* o = reinterpret_cast<float4*>(out) + n * total4;
+  for (long long i = lo + threadIdx.x; i < hi; i += RP_THREADS) stg_stream(o + i, f4_norm(sd[i - lo], mn, rng));
+}
+
+// two-pass fallback (samples too large for a 16-CTA cluster's shared memory)
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void minmax_init_kernel(int* mm, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { mm[2 * i] = f2ord(FLT_MAX); mm[2 * i + 1] = f2ord(-FLT_MAX); }
+}
+template <int K>
+__global__ void __launch_bounds__(256) dynimg_pass1_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int* __restrict__ mm, long long total4, AlphaTab al) {
+  const long long n = blockIdx.y;
+  const float4* base = reinterpret_cast<const float4*>(in) + n * K * total4;
+  float4* o = reinterpret_cast<float4*>(out) + n * total4;
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = ldg_stream(base + k * total4 + i);
+    float4 acc = f4_scale(al.a[0], v[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[k]);
+    o[i] = acc;
+    f4_minmax(acc, mn, mx);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm + 2 * n, f2ord(mn)); atomicMax(mm + 2 * n + 1, f2ord(mx)); }
+}
+__global__ void __launch_bounds__(256) dynimg_pass2_kernel(float* __restrict__ out, const int* __restrict__ mm,
+                                                           long long total4) {
+  const long long n = blockIdx.y;
+  const float mn = ord2f(mm[2 * n]), mx = ord2f(mm[2 * n + 1]);
+  const float rng = __fadd_rn(__fsub_rn(mx, mn), 1e-6f);
+  float4* o = reinterpret_cast<float4*>(out) + n * total4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x)
+    o[i] = f4_norm(o[i], mn, rng);
+}
+
+// ---------------------------------------------------------------------------------------
+// fused GEECO-F pre-process (graph.py:387-401): one pass over the K-frame buffer + target frame
+//   enc 0: current frame (= frame K-1)             -> x0[0][n]  (channel-padded, OutT)
+//   enc 1: dynimg(buffer)                          -> x0[1][n]
+//   enc 2: dynimg([current, target])  (alpha -1/2, 1/2)  -> x0[2][n]
+// optional fp32 un-padded copies of enc 1 / enc 2 for the 'dynbuff' / 'dyndiff' endpoints.
+// Work unit = 4 pixels = C float4 loads per frame.
+// ---------------------------------------------------------------------------------------
+template <typename OutT, int CP> struct PixPack;
+template <> struct PixPack<float, 4> {
+  static __device__ __forceinline__ void store(float* dst, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+  }
+};
+template <> struct PixPack<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(dst) = u;
+  }
+};
+template <> struct PixPack<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* dst, float a, float b, float c, float d) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint4 u; u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1); u.z = 0u; u.w = 0u;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+};
+
+// values e[0..4*C) of 4 consecutive pixels -> padded pixels (channels >= C are zero)
+template <typename OutT, int CP, int C>
+__device__ __forceinline__ void store_unit(OutT* dst, const float* e) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    PixPack<OutT, CP>::store(dst + p * CP, e[p * C], e[p * C + 1], e[p * C + 2], C == 4 ? e[p * C + (C - 1)] : 0.f);
+}
+
+template <typename OutT, int CP, int C, int K>
+__global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
+    const float* __restrict__ rgb, const float* __restrict__ tgt, OutT* __restrict__ x0,
+    float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
+    AlphaTab al) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float s_red[64];
+  __shared__ float s_mm[2 * 2 * RP_MAX_CLUSTER];
+  // smem: [2][per_units][C] float4
+  float4* sd0 = reinterpret_cast<float4*>(smem_raw);
+  float4* sd1 = sd0 + per_units * C;
+  const long long n = blockIdx.y;
+  const long long lo = (long long)blockIdx.x * per_units;
+  long long hi = lo + per_units; if (hi > units) hi = units;
+  const long long img4 = units * C;                       // float4 per image
+  const float4* fbase = reinterpret_cast<const float4*>(rgb) + n * K * img4;
+  const float4* tbase = reinterpret_cast<const float4*>(tgt) + n * img4;
+  const long long img_out = units * 4 * CP;               // OutT elements per padded image
+  OutT* x_cur = x0 + n * img_out;
+  OutT* x_dyn = x0 + ((long long)N + n) * img_out;
+  OutT* x_dif = x0 + (2ll * N + n) * img_out;
+  float mn0 = FLT_MAX, mx0 = -FLT_MAX, mn1 = FLT_MAX, mx1 = -FLT_MAX;
+  for (long long u = lo + threadIdx.x; u < hi; u += RP_THREADS) {
+    float4 v[K][C], t[C];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < C; ++j) v[k][j] = ldg_stream(fbase + k * img4 + u * C + j);
+#pragma unroll
+    for (int j = 0; j < C; ++j) t[j] = ldg_stream(tbase + u * C + j);
+    float cur[4 * C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      float4 acc = f4_scale(al.a[0], v[0][j]);
+#pragma unroll
+      for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[k][j]);
+      const float4 c4 = v[K - 1][j];
+      float4 dd = f4_axpy(f4_scale(-0.5f, c4), 0.5f, t[j]);
+      sd0[(u - lo) * C + j] = acc;
+      sd1[(u - lo) * C + j] = dd;
+      f4_minmax(acc, mn0, mx0);
+      f4_minmax(dd, mn1, mx1);
+      cur[j * 4] = c4.x; cur[j * 4 + 1] = c4.y; cur[j * 4 + 2] = c4.z; cur[j * 4 + 3] = c4.w;
+    }
+    store_unit<OutT, CP, C>(x_cur + u * 4 * CP, cur);
+  }
+  cluster_minmax(mn0, mx0, s_red, s_mm, 0, 2);
+  cluster_minmax(mn1, mx1, s_red, s_mm, 1, 2);
+  cluster_minmax_read(mn0, mx0, s_mm, 0);
+  cluster_minmax_read(mn1, mx1, s_mm, 1);
+  const float rng0 = __fadd_rn(__fsub_rn(mx0, mn0), 1e-6f), rng1 = __fadd_rn(__fsub_rn(mx1, mn1), 1e-6f);
+  float4* o0 = dynbuff_f32 ? reinterpret_cast<float4*>(dynbuff_f32) + n * img4 : nullptr;
+  float4* o1 = dyndiff_f32 ? reinterpret_cast<float4*>(dyndiff_f32) + n * img4 : nullptr;
+  for (long long u = lo + threadIdx.x; u < hi; u += RP_THREADS) {
+    float e0[4 * C], e1[4 * C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
+      const float4 b = f4_norm(sd1[(u - lo) * C + j], mn1, rng1);
+      e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
+      e1[j * 4] = b.x; e1[j * 4 + 1] = b.y; e1[j * 4 + 2] = b.z; e1[j * 4 + 3] = b.w;
+      if (o0) stg_stream(o0 + u * C + j, a);
+      if (o1) stg_stream(o1 + u * C + j, b);
+    }
+    store_unit<OutT, CP, C>(x_dyn + u * 4 * CP, e0);
+    store_unit<OutT, CP, C>(x_dif + u * 4 * CP, e1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int pick_cluster(long long bytes_per_sample, int hint) {
+  if (hint > 0) return hint;
+  int cl = 1;
+  while (cl < RP_MAX_CLUSTER && bytes_per_sample / cl > 100 * 1024) cl *= 2;
+  return cl;
+}
+
+template <typename KernelT>
+static int launch_clustered(KernelT kernel, dim3 grid, int cl, size_t smem, cudaStream_t st, void** args) {
+  CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cl > 8) CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(RP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
+  geeco_count_launch(1);
+  return GEECO_OK;
+}
+
+#define RP_SWITCH_K(K, STMT)                                                                     \
+  switch (K) {                                                                                   \
+    case 2: { constexpr int KK = 2; STMT; } break;   case 3: { constexpr int KK = 3; STMT; } break;   \
+    case 4: { constexpr int KK = 4; STMT; } break;   case 5: { constexpr int KK = 5; STMT; } break;   \
+    case 6: { constexpr int KK = 6; STMT; } break;   case 7: { constexpr int KK = 7; STMT; } break;   \
+    case 8: { constexpr int KK = 8; STMT; } break;   case 9: { constexpr int KK = 9; STMT; } break;   \
+    case 10: { constexpr int KK = 10; STMT; } break; case 11: { constexpr int KK = 11; STMT; } break; \
+    case 12: { constexpr int KK = 12; STMT; } break; case 13: { constexpr int KK = 13; STMT; } break; \
+    case 14: { constexpr int KK = 14; STMT; } break; case 15: { constexpr int KK = 15; STMT; } break; \
+    case 16: { constexpr int KK = 16; STMT; } break;                                              \
+    default: geeco_set_error("dynimg: window size K=%d outside [2,16]", K); return GEECO_ERR_INVALID; \
+  }
+
+#define RP_SWITCH_K_LO(K, STMT)                                                                  \
+  switch (K) {                                                                                   \
+    case 2: { constexpr int KK = 2; STMT; } break;   case 3: { constexpr int KK = 3; STMT; } break;   \
+    case 4: { constexpr int KK = 4; STMT; } break;   case 5: { constexpr int KK = 5; STMT; } break;   \
+    case 6: { constexpr int KK = 6; STMT; } break;   case 7: { constexpr int KK = 7; STMT; } break;   \
+    case 8: { constexpr int KK = 8; STMT; } break;                                                \
+    default: geeco_set_error("preprocess: window size K=%d outside [2,8]", K); return GEECO_ERR_INVALID; \
+  }
+
+static const size_t RP_SMEM_CAP = 200 * 1024;
+
+int launch_dynimg(const float* in, float* out, int N, int K, long long HWC, const float* alpha_host,
+                  int cluster_hint, cudaStream_t st) {
+  if (HWC % 4) { geeco_set_error("dynimg: H*W*C=%lld must be a multiple of 4", HWC); return GEECO_ERR_INVALID; }
+  if (N <= 0) return GEECO_OK;
+  if (N > 65535) { geeco_set_error("dynimg: N=%d > 65535", N); return GEECO_ERR_INVALID; }
+  AlphaTab al = {};
+  for (int k = 0; k < K && k < 16; ++k) al.a[k] = alpha_host[k];
+  long long total4 = HWC / 4;
+  int cl = pick_cluster(HWC * 4, cluster_hint);
+  long long per4 = (total4 + cl - 1) / cl;
+  size_t smem = (size_t)per4 * 16;
+  if (smem > RP_SMEM_CAP) return GEECO_ERR_WORKSPACE;   // caller falls back to the two-pass path
+  void* args[] = {(void*)&in, (void*)&out, (void*)&total4, (void*)&per4, (void*)&al};
+  RP_SWITCH_K(K, return launch_clustered(dynimg_cluster_kernel<KK>, dim3(cl, N), cl, smem, st, args));
+  return GEECO_OK;
+}
+
+int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, int N, int K, long long HWC,
+                          const float* alpha_host, cudaStream_t st) {
+  if (HWC % 4) { geeco_set_error("dynimg: H*W*C=%lld must be a multiple of 4", HWC); return GEECO_ERR_INVALID; }
+  if (N <= 0) return GEECO_OK;
+  AlphaTab al = {};
+  for (int k = 0; k < K && k < 16; ++k) al.a[k] = alpha_host[k];
+  long long total4 = HWC / 4;
+  int* mm = reinterpret_cast<int*>(minmax_scratch);
+  minmax_init_kernel<<<ceil_div(N, 256), 256, 0, st>>>(mm, N);
+  int bps = (int)((total4 + 256 * 8 - 1) / (256 * 8)); if (bps < 1) bps = 1; if (bps > 1024) bps = 1024;
+  dim3 grid(bps, N);
+  RP_SWITCH_K(K, (dynimg_pass1_kernel<KK><<<grid, 256, 0, st>>>(in, out, mm, total4, al)));
+  dynimg_pass2_kernel<<<grid, 256, 0, st>>>(out, mm, total4);
+  geeco_count_launch(3);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+template <typename OutT, int CP, int C>
+static int launch_pre_t(const float* rgb, const float* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
+                        const AlphaTab& al_in, int cluster_hint, cudaStream_t st) {
+  long long units = (long long)H * W / 4;
+  int cl = pick_cluster(2ll * H * W * C * 4, cluster_hint);
+  long long per_units = (units + cl - 1) / cl;
+  size_t smem = (size_t)per_units * C * 16 * 2;
+  if (smem > RP_SMEM_CAP) {
+    geeco_set_error("preprocess: %dx%dx%d needs %zu B of shared memory per CTA at cluster %d", H, W, C, smem, cl);
+    return GEECO_ERR_INVALID;
+  }
+  OutT* x = reinterpret_cast<OutT*>(x0);
+  AlphaTab al = al_in;
+  void* args[] = {(void*)&rgb, (void*)&tgt, (void*)&x, (void*)&db, (void*)&dd, (void*)&N, (void*)&units,
+                  (void*)&per_units, (void*)&al};
+  RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
+  return GEECO_OK;
+}
+
+int launch_preprocess_geecof(const float* rgb, const float* tgt, void* x0, int out_bf16, int CP, float* dynbuff_f32,
+                             float* dyndiff_f32, int N, int K, int H, int W, int C, const float* alpha_host,
+                             int cluster_hint, cudaStream_t st) {
+  if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
+  if (N <= 0) return GEECO_OK;
+  if (N > 65535) { geeco_set_error("preprocess: N=%d > 65535", N); return GEECO_ERR_INVALID; }
+  if (K > 8) { geeco_set_error("preprocess: fused path supports window_size <= 8 (got %d)", K); return GEECO_ERR_INVALID; }
+  AlphaTab al = {};
+  for (int k = 0; k < K; ++k) al.a[k] = alpha_host[k];
+#define PRE_CASE(T, cp, c) return launch_pre_t<T, cp, c>(rgb, tgt, x0, dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, st)
+  if (!out_bf16 && CP == 4 && C == 3) PRE_CASE(float, 4, 3);
+  if (!out_bf16 && CP == 4 && C == 4) PRE_CASE(float, 4, 4);
+  if (out_bf16 && CP == 8 && C == 3) PRE_CASE(__nv_bfloat16, 8, 3);
+  if (out_bf16 && CP == 8 && C == 4) PRE_CASE(__nv_bfloat16, 8, 4);
+  if (out_bf16 && CP == 4 && C == 3) PRE_CASE(__nv_bfloat16, 4, 3);
+  if (out_bf16 && CP == 4 && C == 4) PRE_CASE(__nv_bfloat16, 4, 4);
+#undef PRE_CASE
+  geeco_set_error("preprocess: unsupported (bf16=%d, CP=%d, C=%d)", out_bf16, CP, C);
+  return GEECO_ERR_INVALID;
+}

@@ -1,0 +1,89 @@
+"""Synthetic (features, labels) batches in the layout the reference's input pipeline emits.
+
+The reference's `pickplace_input_fn_v4` (src/data/geeco_gym.py:401-474) is a tf.data
+pipeline over zlib TFRecords; datasets are not available offline and the pipeline itself is
+outside the hot path, but its *layout and index contract* is the
+input boundary of the train step:
+
+  features: step [N,K] i64, rgb [N,K,H,W,3] f32 in [0,1] (stored uint8/255, geeco_gym.py:310),
+            jnt_state [N,K,7], ee_state [N,K,7], obj_state [N,K,7], target_rgb [N,H,W,3]
+  labels:   cmd [N,4] = cmd of the last frame of the window (geeco_gym.py:394)
+
+Index contract (geeco_gym.py:598-631): episode length L, S = L-1 usable frames, window w in
+[0, S-K] covers frames w..w+K-1, target = frame L-1, stream position g = e*(S-K+1) + w, batches
+are consecutive slices of the stream (no window-level shuffle, :447-448).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+EPISODE_LENGTH = 100   # src/geeco_gym/pickplace.py:157
+
+
+def num_windows(episode_length: int, window_size: int) -> int:
+  """_window_v3 (geeco_gym.py:617-618): (L-1) - K + 1."""
+  return episode_length - 1 - window_size + 1
+
+
+def window_frame_indices(episode_length: int, window_size: int) -> np.ndarray:
+  """int64 [num_windows, K]: frame indices of every sliding window of one episode."""
+  nw = num_windows(episode_length, window_size)
+  return np.arange(nw, dtype=np.int64).reshape(nw, 1) + np.arange(window_size, dtype=np.int64).reshape(1, -1)
+
+
+def locate(g: int, episode_length: int, window_size: int):
+  """Stream position -> (episode, window, cur_frame, target_frame)."""
+  e, w = divmod(int(g), num_windows(episode_length, window_size))
+  return e, w, w + window_size - 1, episode_length - 1
+
+
+def rank_slice(batch_index: int, global_batch: int, rank: int, world: int):
+  """Contiguous share of global batch `batch_index` owned by `rank`:
+  stream positions [b*G + r*G/n, b*G + (r+1)*G/n)."""
+  if global_batch % world:
+    raise ValueError("global batch %d not divisible by world size %d" % (global_batch, world))
+  per = global_batch // world
+  lo = batch_index * global_batch + rank * per
+  return lo, lo + per
+
+
+def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0, first_stream_pos=0,
+                    structured=True, episode_length=EPISODE_LENGTH):
+  """One (features, labels) tuple of numpy arrays, seeded, uint8-quantised pixels.
+
+  structured=True gives every window temporal structure (frame k = base image rolled by k
+  pixels plus fresh noise) so K-frame buffers are never static -- the dynimg min/max
+  normalisation is ill-conditioned on identical frames.
+  """
+  rng = np.random.default_rng(seed)
+  K = window_size
+  if structured:
+    base = rng.integers(0, 256, size=(n, height, width, channels))
+    frames = []
+    for k in range(K):
+      noise = rng.integers(-24, 25, size=(n, height, width, channels))
+      frames.append(np.clip(np.roll(base, shift=(k, 2 * k), axis=(1, 2)) + noise, 0, 255))
+    rgb = np.stack(frames, axis=1)
+  else:
+    rgb = rng.integers(0, 256, size=(n, K, height, width, channels))
+  rgb = (rgb / 255.0).astype(np.float32)
+  tgt = (rng.integers(0, 256, size=(n, height, width, channels)) / 255.0).astype(np.float32)
+  jnt = rng.uniform(-np.pi, np.pi, size=(n, K, 7)).astype(np.float32)
+  ee = np.zeros((n, K, 7), dtype=np.float32)
+  ee[..., :3] = np.array([1.34, 0.75, 0.55], dtype=np.float32) + rng.uniform(-0.15, 0.15, size=(n, K, 3))
+  ee[..., 3:] = np.array([1.0, 0.0, 1.0, 0.0], dtype=np.float32)
+  obj = np.zeros((n, K, 7), dtype=np.float32)
+  obj[..., 0] = rng.uniform(1.075, 1.425, size=(n, K))
+  obj[..., 1] = rng.uniform(0.35, 1.15, size=(n, K))
+  obj[..., 2] = 0.307
+  obj[..., 3] = 1.0
+  step = np.empty((n, K), dtype=np.int64)
+  for i in range(n):
+    _, w, _, _ = locate(first_stream_pos + i, episode_length, K)
+    step[i] = w + np.arange(K)
+  cmd = np.empty((n, 4), dtype=np.float32)
+  cmd[:, :3] = rng.uniform(-2.0, 2.0, size=(n, 3))
+  cmd[:, 3] = rng.integers(-1, 2, size=n)
+  features = {'step': step, 'rgb': rgb, 'jnt_state': jnt, 'ee_state': ee, 'obj_state': obj, 'target_rgb': tgt}
+  labels = {'cmd': cmd}
+  return features, labels

@@ -1,0 +1,318 @@
+"""Engine: owns the device memory of one model replica and drives the C-ABI.
+
+PyTorch is used for plumbing only (device allocations, streams, pinned host buffers,
+torch.distributed for the gradient all-reduce); every arithmetic op of the hot path runs in
+libgeeco_b200.so.  One Engine == one `tf.Session` worth of state in the reference: parameters
+(TF variable names / layouts), Adam slots, global step, LSTM memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .params import E2EVMCConfig
+
+LOSS_KEYS = ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss_reg', 'loss')
+_FEATURE_KEYS = ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state')
+
+
+def _check_switches(cfg: E2EVMCConfig):
+  """Same ValueErrors as graph.py:250-252,357-359,408-410 for unknown values; the switch values that
+  exist in the reference but are not yet on the CUDA path raise NotImplementedError."""
+  if cfg.control_mode not in ('cartesian', 'velocity'):
+    raise ValueError("Unknown control mode '%s'" % (cfg.control_mode,))
+  if cfg.proc_tgt not in ('constant', 'residual', 'dyndiff'):
+    raise ValueError("Unknown processing mode for target image: %s!" % (cfg.proc_tgt,))
+  if cfg.proc_obs not in ('sequence', 'dynimg'):
+    raise ValueError("Unknown processing mode for frame buffer: %s!" % (cfg.proc_obs,))
+  if cfg.img_channels not in (3, 4):
+    raise ValueError("Unsupported number of channels for input frame: %d!" % cfg.img_channels)
+  if (cfg.proc_obs, cfg.proc_tgt, cfg.control_mode) != ('dynimg', 'dyndiff', 'cartesian'):
+    raise NotImplementedError(
+        "geeco_b200 currently runs the GEECO-F wiring (--proc_obs dynimg --proc_tgt dyndiff "
+        "--control_mode cartesian); got proc_obs=%s proc_tgt=%s control_mode=%s"
+        % (cfg.proc_obs, cfg.proc_tgt, cfg.control_mode))
+
+
+class Engine(object):
+  """One replica of the goal-conditioned controller on one GPU."""
+
+  def __init__(self, cfg: E2EVMCConfig, batch_size=None, precision='fp32', training=True, carry_state=False,
+               device=None):
+    _check_switches(cfg)
+    if not torch.cuda.is_available():
+      raise RuntimeError("geeco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    self.lib = _lib.load()
+    self.cfg = cfg
+    self.N = int(batch_size if batch_size is not None else cfg.batch_size)
+    self.precision = precision
+    self.training = bool(training)
+    self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    torch.cuda.set_device(self.device)
+    c = _lib.GeecoConfig()
+    for k in ('img_height', 'img_width', 'img_channels', 'dim_jnt_state', 'window_size', 'dim_s_obs', 'dim_s_dyn',
+              'dim_s_diff', 'dim_h_lstm', 'dim_h_fc', 'num_grp_states'):
+      setattr(c, k, int(getattr(cfg, k)))
+    c.batch_size = self.N
+    c.precision = {'fp32': _lib.GEECO_FP32, 'bf16': _lib.GEECO_BF16}[precision]
+    c.carry_state = 1 if carry_state else 0
+    c.training = 1 if training else 0
+    c.lr, c.lambda_aux, c.l2_regularizer = float(cfg.lr), float(cfg.lambda_aux), float(cfg.l2_regularizer)
+    c.adam_beta1, c.adam_beta2, c.adam_eps = 0.9, 0.999, 1e-8
+    self._c = c
+    sizes = _lib.GeecoSizes()
+    _lib.check(self.lib.geeco_query_sizes(C.byref(c), C.byref(sizes)))
+    self.sizes = sizes
+    n = int(sizes.arena_floats)
+    self.theta = torch.zeros(n, dtype=torch.float32, device=self.device)
+    self.grad = torch.zeros(n, dtype=torch.float32, device=self.device) if training else None
+    self.adam_m = torch.zeros(n, dtype=torch.float32, device=self.device) if training else None
+    self.adam_v = torch.zeros(n, dtype=torch.float32, device=self.device) if training else None
+    self.workspace = torch.zeros(int(sizes.workspace_bytes) + 256, dtype=torch.uint8, device=self.device)
+    ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+    ctx = C.c_void_p()
+    _lib.check(self.lib.geeco_create(C.byref(c), C.byref(ctx)))
+    self._ctx = ctx
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(self.lib.geeco_bind(ctx, ptr(self.theta), ptr(self.grad), ptr(self.adam_m), ptr(self.adam_v),
+                                   C.c_void_p(ws_ptr), int(sizes.workspace_bytes)))
+    # named views (TF variable names, TF layouts)
+    self.param_table = OrderedDict()
+    for i in range(sizes.num_params):
+      d = _lib.GeecoParamDesc()
+      _lib.check(self.lib.geeco_param_info(ctx, i, C.byref(d)))
+      shape = tuple(int(d.shape[j]) for j in range(d.ndim))
+      self.param_table[d.name.decode()] = (int(d.offset), int(d.numel), shape)
+    self.buckets = []
+    for b in range(sizes.num_buckets):
+      off, cnt = C.c_int64(), C.c_int64()
+      _lib.check(self.lib.geeco_grad_bucket(ctx, b, C.byref(off), C.byref(cnt)))
+      self.buckets.append((int(off.value), int(cnt.value)))
+    self.global_step = 0
+    self.NH = 9 + cfg.num_grp_states
+    # persistent device inputs/outputs + pinned host staging (allocated lazily)
+    self._dev_in, self._pin_in = {}, {}
+    self.out_heads = torch.zeros(self.N, self.NH, dtype=torch.float32, device=self.device)
+    self.out_fc1 = torch.zeros(self.N, cfg.dim_h_fc, dtype=torch.float32, device=self.device)
+    self.out_state = torch.zeros(self.N, 2 * cfg.dim_h_lstm, dtype=torch.float32, device=self.device)
+    self.out_losses = torch.zeros(8, dtype=torch.float32, device=self.device)
+    self._out_dyn = None
+
+  # ------------------------------------------------------------------ lifecycle
+  def close(self):
+    if getattr(self, '_ctx', None) is not None:
+      self.lib.geeco_destroy(self._ctx)
+      self._ctx = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def _stream(self):
+    return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  # ------------------------------------------------------------------ parameters
+  def view(self, name, arena=None):
+    off, cnt, shape = self.param_table[name]
+    arena = self.theta if arena is None else arena
+    return arena[off:off + cnt].view(shape)
+
+  def param_names(self):
+    return list(self.param_table.keys())
+
+  def count_parameters(self):
+    """What utils.count_parameters (src/models/e2evmc/utils.py:10-14) prints."""
+    return int(sum(cnt for _, cnt, _ in self.param_table.values()))
+
+  def init_params(self, seed=0):
+    """glorot_uniform kernels, zero biases: the TF defaults of tf.layers.conv2d / dense / LSTMCell."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(int(seed))
+    self.theta.zero_()
+    for name, (off, cnt, shape) in self.param_table.items():
+      if not name.endswith('/kernel'):
+        continue
+      if len(shape) == 4:
+        rf = shape[0] * shape[1]
+        fan_in, fan_out = rf * shape[2], rf * shape[3]
+      else:
+        fan_in, fan_out = shape[0], shape[1]
+      lim = math.sqrt(6.0 / (fan_in + fan_out))
+      w = (torch.rand(cnt, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * lim
+      self.theta[off:off + cnt].copy_(w)
+    self.params_changed()
+
+  def set_params(self, named: dict):
+    for name, arr in named.items():
+      if name.endswith('lstm_memory'):
+        continue
+      t = torch.as_tensor(np.asarray(arr, dtype=np.float32)) if not torch.is_tensor(arr) else arr.detach().float()
+      v = self.view(name)
+      if tuple(t.shape) != tuple(v.shape):
+        raise ValueError("shape mismatch for %s: %s vs %s" % (name, tuple(t.shape), tuple(v.shape)))
+      v.copy_(t.to(self.device))
+    self.params_changed()
+
+  def get_params(self, arena=None):
+    return OrderedDict((n, self.view(n, arena).detach().cpu().numpy().copy()) for n in self.param_table)
+
+  def get_grads(self):
+    return self.get_params(self.grad)
+
+  def params_changed(self):
+    _lib.check(self.lib.geeco_params_changed(self._ctx, self._stream()))
+
+  def set_global_step(self, t):
+    self.global_step = int(t)
+    _lib.check(self.lib.geeco_set_step(self._ctx, int(t), self._stream()))
+
+  def state_dict(self):
+    sd = {'global_step': self.global_step, 'theta': self.theta.detach().cpu().numpy()}
+    if self.training:
+      sd['adam_m'] = self.adam_m.detach().cpu().numpy()
+      sd['adam_v'] = self.adam_v.detach().cpu().numpy()
+    return sd
+
+  # ------------------------------------------------------------------ inputs
+  def _shapes(self):
+    cfg, N, K = self.cfg, self.N, self.cfg.window_size
+    H, W, Cc = cfg.img_height, cfg.img_width, cfg.img_channels
+    return {'rgb': (N, K, H, W, Cc), 'target_rgb': (N, H, W, Cc), 'jnt_state': (N, K, cfg.dim_jnt_state),
+            'ee_state': (N, K, 7), 'obj_state': (N, K, 7), 'cmd': (N, 4)}
+
+  def _to_device(self, key, value):
+    """Accepts a float32 CUDA tensor (used in place) or a host array (staged through pinned memory)."""
+    shape = self._shapes()[key]
+    if torch.is_tensor(value) and value.is_cuda:
+      if tuple(value.shape) != shape:
+        raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(value.shape)))
+      return value.contiguous().float()
+    arr = value if torch.is_tensor(value) else torch.from_numpy(np.ascontiguousarray(value))
+    if tuple(arr.shape) != shape:
+      raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(arr.shape)))
+    if key not in self._dev_in:
+      self._dev_in[key] = torch.empty(shape, dtype=torch.float32, device=self.device)
+      self._pin_in[key] = torch.empty(shape, dtype=torch.float32).pin_memory()
+    self._pin_in[key].copy_(arr)
+    self._dev_in[key].copy_(self._pin_in[key], non_blocking=True)
+    return self._dev_in[key]
+
+  def h2d_bytes(self, with_labels=True):
+    keys = list(_FEATURE_KEYS) + (['cmd'] if with_labels else [])
+    if not with_labels:
+      keys = ['rgb', 'target_rgb', 'jnt_state']
+    return int(sum(4 * int(np.prod(self._shapes()[k])) for k in keys))
+
+  def _batch(self, features, labels):
+    b = _lib.GeecoBatch()
+    keep = []
+    for k in ('rgb', 'target_rgb', 'jnt_state'):
+      t = self._to_device(k, features[k])
+      keep.append(t)
+      setattr(b, k, t.data_ptr())
+    if labels is not None:
+      for k in ('ee_state', 'obj_state'):
+        t = self._to_device(k, features[k])
+        keep.append(t)
+        setattr(b, k, t.data_ptr())
+      t = self._to_device('cmd', labels['cmd'])
+      keep.append(t)
+      b.cmd = t.data_ptr()
+    return b, keep
+
+  def _outputs(self, want_dyn=False, want_losses=True):
+    o = _lib.GeecoOutputs()
+    o.heads, o.fc1, o.lstm_state = self.out_heads.data_ptr(), self.out_fc1.data_ptr(), self.out_state.data_ptr()
+    if want_losses:
+      o.losses = self.out_losses.data_ptr()
+    if want_dyn:
+      if self._out_dyn is None:
+        cfg = self.cfg
+        shp = (self.N, cfg.img_height, cfg.img_width, cfg.img_channels)
+        self._out_dyn = (torch.zeros(shp, dtype=torch.float32, device=self.device),
+                         torch.zeros(shp, dtype=torch.float32, device=self.device))
+      o.dynbuff, o.dyndiff = self._out_dyn[0].data_ptr(), self._out_dyn[1].data_ptr()
+    return o
+
+  # ------------------------------------------------------------------ steps
+  def forward(self, features, labels=None, want_dyn=False):
+    """goal_e2evmc forward (+ losses when labels are given).  Returns a dict of DEVICE tensors
+    (views of persistent output buffers, overwritten by the next call)."""
+    b, keep = self._batch(features, labels)
+    o = self._outputs(want_dyn=want_dyn, want_losses=labels is not None)
+    _lib.check(self.lib.geeco_forward(self._ctx, C.byref(b), C.byref(o), self._stream()))
+    return self._endpoints(want_dyn, labels is not None)
+
+  def _endpoints(self, want_dyn, with_losses):
+    G = self.cfg.num_grp_states
+    h = self.out_heads
+    ep = OrderedDict()
+    ep['pred_cmd_ee'] = h[:, 0:3]
+    ep['logits_cmd_grp'] = h[:, 3:3 + G]
+    ep['pred_aux_ee'] = h[:, 3 + G:6 + G]
+    ep['pred_aux_obj'] = h[:, 6 + G:9 + G]
+    ep['fc1'] = self.out_fc1
+    ep['lstm_state'] = self.out_state
+    if want_dyn:
+      ep['dynbuff'], ep['dyndiff'] = self._out_dyn
+    if with_losses:
+      ep['losses'] = self.out_losses
+    return ep
+
+  def train_step(self, features, labels, grad_scale=1.0):
+    """One model_fn(TRAIN) step (estimator.py:144-244).  Returns the device tensor of 8 floats:
+    loss_cmd_ee, loss_cmd_grp, loss_pos_ee, loss_pos_obj, loss_reg, loss, #correct, N."""
+    b, keep = self._batch(features, labels)
+    o = self._outputs()
+    _lib.check(self.lib.geeco_train_step(self._ctx, C.byref(b), C.byref(o), float(grad_scale), self._stream()))
+    self.global_step += 1
+    return self.out_losses
+
+  def step_forward(self, features, labels):
+    b, keep = self._batch(features, labels)
+    o = self._outputs()
+    _lib.check(self.lib.geeco_step_forward(self._ctx, C.byref(b), C.byref(o), self._stream()))
+    return self.out_losses
+
+  def step_backward(self, bucket):
+    _lib.check(self.lib.geeco_step_backward(self._ctx, int(bucket), self._stream()))
+    off, cnt = self.buckets[bucket]
+    return self.grad[off:off + cnt]
+
+  def step_update(self, grad_scale=1.0):
+    _lib.check(self.lib.geeco_step_update(self._ctx, float(grad_scale), self._stream()))
+    self.global_step += 1
+
+  def set_lstm_state(self, state_cm=None):
+    p = C.c_void_p(state_cm.data_ptr()) if state_cm is not None else None
+    _lib.check(self.lib.geeco_set_lstm_state(self._ctx, p, self._stream()))
+
+  def losses_dict(self, losses=None):
+    v = (self.out_losses if losses is None else losses).detach().cpu().numpy()
+    return OrderedDict(zip(LOSS_KEYS, [float(x) for x in v[:6]]))
+
+  # ------------------------------------------------------------------ debugging
+  def debug_buffer(self, name):
+    ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int32()
+    _lib.check(self.lib.geeco_debug_buffer(self._ctx, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(dt)))
+    return wrap_device_pointer(ptr.value, int(cnt.value), torch.bfloat16 if dt.value == 1 else torch.float32,
+                               self.device)
+
+
+class _CudaArray(object):
+  def __init__(self, ptr, nbytes):
+    self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 3}
+
+
+def wrap_device_pointer(ptr, count, dtype, device):
+  """torch view (no copy) of `count` elements of `dtype` at device address `ptr`."""
+  esz = torch.empty(0, dtype=dtype).element_size()
+  raw = torch.as_tensor(_CudaArray(ptr, count * esz), device=device)
+  return raw.view(dtype)

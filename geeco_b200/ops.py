@@ -1,0 +1,74 @@
+"""Functional ops of the e2evmc graph on CUDA tensors (thin wrappers over the C-ABI).
+
+Counterparts of the variable-free / single-layer graph functions of the reference
+(src/models/e2evmc/graph.py): `dynimg` (:30-55) and one `tf.layers.conv2d` of `conv_encoder`
+(:76-115) with its gradients.  Used by the parity tests and by the rank-pooling sweep in bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+  return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _req(t, name):
+  if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+    raise ValueError("%s must be a contiguous float32 CUDA tensor" % name)
+  return t
+
+
+def dynimg(rgb_frames, alpha=None, cluster=0, out=None):
+  """graph.py:30-55.  rgb_frames [N,K,H,W,C] float32 CUDA in [0,1] -> [N,H,W,C].
+  cluster: 0 = automatic cluster size, >0 = forced cluster size, -1 = two-pass kernels."""
+  lib = _lib.load()
+  x = _req(rgb_frames, 'rgb_frames')
+  if x.dim() != 5:
+    raise ValueError("rgb_frames must be [N,K,H,W,C]")
+  N, K, H, W, Cc = x.shape
+  if out is None:
+    out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=x.device)
+  a = None
+  if alpha is not None:
+    a = (C.c_float * K)(*[float(v) for v in np.asarray(alpha, dtype=np.float32)])
+  scratch = torch.empty(2 * max(N, 1), dtype=torch.float32, device=x.device)
+  _lib.check(lib.geeco_dynimg(_p(x), _p(out), N, K, H, W, Cc, a, int(cluster), _p(scratch), _stream(x)))
+  return out
+
+
+def conv2d_same(x, w, b=None, stride=1, relu=True):
+  """tf.layers.conv2d(kernel_size=3, padding='SAME') on NHWC / HWIO tensors (fp32 kernels)."""
+  lib = _lib.load()
+  x, w = _req(x, 'x'), _req(w, 'w')
+  N, H, W, Cin = x.shape
+  Cout = w.shape[3]
+  Ho, Wo = -(-H // stride), -(-W // stride)
+  y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+  _lib.check(lib.geeco_conv2d_same(_p(x), _p(w), _p(b), _p(y), N, H, W, Cin, Cout, stride, 1 if relu else 0, _stream(x)))
+  return y
+
+
+def conv2d_same_bwd(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True):
+  """Gradients of conv2d_same given dL/d(pre-activation).  Returns (dw, db, dx)."""
+  lib = _lib.load()
+  x, w, dy_pre = _req(x, 'x'), _req(w, 'w'), _req(dy_pre, 'dy_pre')
+  N, H, W, Cin = x.shape
+  Cout = w.shape[3]
+  dw = torch.empty_like(w)
+  db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+  dx = torch.zeros_like(x) if need_dx else None
+  n = int(lib.geeco_conv2d_bwd_scratch_floats(N, H, W, Cin, Cout, stride))
+  scratch = torch.empty(n, dtype=torch.float32, device=x.device)
+  _lib.check(lib.geeco_conv2d_same_bwd(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx), _p(scratch),
+                                       n, N, H, W, Cin, Cout, stride, _stream(x)))
+  return dw, db, dx

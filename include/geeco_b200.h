@@ -1,0 +1,162 @@
+/* geeco_b200 -- C-ABI of the B200-native GEECO e2evmc hot path.
+ *
+ * The reference (ogroth/geeco) is pure Python on TensorFlow 1.15 and has NO native interface; the
+ * boundary this library replaces is the set of TF graph functions and wrappers listed below.  Each
+ * entry point cites the reference code it stands in for (paths relative to the reference root).
+ * The Python host (geeco_b200/*.py) binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status (GEECO_OK == 0); geeco_last_error() gives the message of
+ *     the last failure on the calling thread.  No C++ exceptions cross this boundary.
+ *   - all tensor pointers are CALLER-OWNED DEVICE memory (e.g. torch tensors' data_ptr()),
+ *     contiguous, float32 unless stated; layouts are TensorFlow's: activations NHWC, conv kernels
+ *     HWIO, dense kernels [in,out], LSTM kernel [in+h,4h] (gates i,j,f,o), LSTM state [c | m].
+ *   - the library never allocates device memory: parameters / gradients / Adam moments live in four
+ *     caller-provided flat float arenas, activations in one caller-provided workspace
+ *     (sizes from geeco_query_sizes).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - a context is not thread-safe (the reference drives its session from one Python thread).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef GEECO_B200_H_
+#define GEECO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GEECO_OK 0
+#define GEECO_ERR_INVALID 1   /* -> ValueError  (graph.py:250-252,357-359,382-384,408-410; estimator.py:173-175) */
+#define GEECO_ERR_CUDA 2      /* -> RuntimeError */
+#define GEECO_ERR_WORKSPACE 3 /* -> RuntimeError */
+#define GEECO_ERR_STATE 4     /* -> RuntimeError */
+
+#define GEECO_FP32 0          /* fp32 storage + fp32 CUDA-core math (parity mode, <= 1e-4 rel) */
+#define GEECO_BF16 1          /* bf16 activations/weights on tcgen05 tensor cores, fp32 accumulate + master weights */
+
+typedef struct geeco_ctx geeco_ctx;
+
+/* Subset of E2EVMCConfig (src/models/e2evmc/params.py:7-28) that shapes the GEECO-F graph
+ * (goal_condition=target, proc_obs=dynimg, proc_tgt=dyndiff, control_mode=cartesian), plus
+ * the execution switches of this library. */
+typedef struct geeco_config {
+  int32_t img_height, img_width, img_channels;
+  int32_t dim_jnt_state, window_size;
+  int32_t dim_s_obs, dim_s_dyn, dim_s_diff, dim_h_lstm, dim_h_fc, num_grp_states;
+  int32_t batch_size;     /* rows per call on this device (lstm_memory shape, graph.py:212,218) */
+  int32_t precision;      /* GEECO_FP32 | GEECO_BF16 */
+  int32_t carry_state;    /* 0: zero LSTM state at every call, as the reference executes (dead assign,
+                             graph.py:226); 1: carry [c|m] across calls (the intended semantics) */
+  int32_t training;       /* 1: reserve backward + optimizer workspace */
+  int32_t reserved0;
+  float lr, lambda_aux, l2_regularizer;          /* params.py:24-27 */
+  float adam_beta1, adam_beta2, adam_eps;        /* tf.train.AdamOptimizer defaults 0.9 / 0.999 / 1e-8 */
+} geeco_config;
+
+typedef struct geeco_sizes {
+  int64_t arena_floats;     /* length of each of the theta / grad / m / v arenas */
+  int64_t workspace_bytes;
+  int32_t num_params;       /* number of named variables */
+  int32_t num_buckets;      /* gradient buckets for overlapped all-reduce */
+} geeco_sizes;
+
+/* One trainable variable, named as TensorFlow names it (graph.py:73,214,342; predictor.py:87). */
+typedef struct geeco_param_desc {
+  char name[96];
+  int64_t offset;           /* in floats, into each arena */
+  int64_t numel;
+  int32_t ndim;
+  int32_t reserved0;
+  int64_t shape[4];
+} geeco_param_desc;
+
+/* Input features/labels of one step; layout of `_prepare_v4` (src/data/geeco_gym.py:373-399). */
+typedef struct geeco_batch {
+  const float* rgb;         /* [N,K,H,W,C] in [0,1]      features['rgb'] (+depth as 4th channel for rgbd) */
+  const float* target_rgb;  /* [N,H,W,C]                 features['target_rgb'] */
+  const float* jnt_state;   /* [N,K,J]                   features['jnt_state'] */
+  const float* ee_state;    /* [N,K,7] or NULL           features['ee_state']   (losses only) */
+  const float* obj_state;   /* [N,K,7] or NULL           features['obj_state']  (losses only) */
+  const float* cmd;         /* [N,4]   or NULL           labels['cmd']          (losses only) */
+} geeco_batch;
+
+/* Optional outputs (NULL = not wanted).  heads = [pred_cmd_ee 0:3 | logits_cmd_grp 3:3+G |
+ * pred_aux_ee | pred_aux_obj] (graph.py:233-259). */
+typedef struct geeco_outputs {
+  float* heads;             /* [N, 9+G] */
+  float* fc1;               /* [N, dim_h_fc]             endpoints['fc1'] */
+  float* dynbuff;           /* [N,H,W,C]                 endpoints['dynbuff']  (graph.py:393) */
+  float* dyndiff;           /* [N,H,W,C]                 endpoints['dyndiff']  (graph.py:401) */
+  float* lstm_state;        /* [N, 2*dim_h_lstm]         [c | m] after the step */
+  float* losses;            /* [8]: loss_cmd_ee, loss_cmd_grp, loss_pos_ee, loss_pos_obj, loss_reg, loss,
+                                    #correct gripper classes, N   (estimator.py:218-239,246-254) */
+} geeco_outputs;
+
+const char* geeco_last_error(void);
+int geeco_version(void);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int geeco_query_sizes(const geeco_config* cfg, geeco_sizes* out);
+int geeco_create(const geeco_config* cfg, geeco_ctx** out);
+int geeco_destroy(geeco_ctx* ctx);
+/* grad/m/v may be NULL when cfg.training == 0 */
+int geeco_bind(geeco_ctx* ctx, float* theta, float* grad, float* m, float* v, void* workspace,
+               int64_t workspace_bytes);
+int geeco_param_info(const geeco_ctx* ctx, int32_t index, geeco_param_desc* out);
+/* gradient bucket `b` covers arena floats [offset, offset+numel); bucket b is complete after
+ * geeco_step_backward(ctx, b, ...) returns (work enqueued on the stream). */
+int geeco_grad_bucket(const geeco_ctx* ctx, int32_t bucket, int64_t* offset, int64_t* numel);
+/* call after writing theta from the host side (refreshes derived bf16 weight copies) */
+int geeco_params_changed(geeco_ctx* ctx, void* stream);
+/* Adam step counter t (global_step of the reference's checkpoints) */
+int geeco_set_step(geeco_ctx* ctx, int64_t t, void* stream);
+/* LSTM carry state [N, 2*dim_h_lstm]; only meaningful with carry_state = 1 */
+int geeco_set_lstm_state(geeco_ctx* ctx, const float* state_cm, void* stream);
+
+/* ---- functional ops (parity-testable pieces of graph.py) ------------------------------------ */
+/* dynimg(rgb_frames) graph.py:30-55.  in [N,K,H,W,C] -> out [N,H,W,C].  alpha (host, K floats) may be
+ * NULL -> the fp32 coefficients of graph.py:17-28.  cluster = 0 picks the cluster size automatically;
+ * -1 forces the two-pass path (scratch: 2*N floats of device memory, may be NULL otherwise). */
+int geeco_dynimg(const float* in, float* out, int32_t N, int32_t K, int32_t H, int32_t W, int32_t C,
+                 const float* alpha, int32_t cluster, float* scratch, void* stream);
+int geeco_alpha_table(int32_t K, float* out_host);
+/* tf.layers.conv2d(3x3, SAME, stride, bias, optional ReLU) graph.py:76-115.  x [N,H,W,Cin] with Cin % 4 == 0,
+ * w HWIO [3,3,Cin,Cout], y [N,ceil(H/s),ceil(W/s),Cout].  fp32 path. */
+int geeco_conv2d_same(const float* x, const float* w, const float* b, float* y, int32_t N, int32_t H,
+                      int32_t W, int32_t Cin, int32_t Cout, int32_t stride, int32_t relu, void* stream);
+/* gradients of the above given dy_pre = dL/d(pre-activation) [N,Ho,Wo,Cout]:
+ * dw [3,3,Cin,Cout], db [Cout], dx [N,H,W,Cin] (NULL = skip; relu_mask_x: if non-NULL, dx is multiplied by
+ * (relu_mask_x > 0) i.e. the result is the pre-activation gradient of the producing layer).
+ * scratch: at least geeco_conv2d_bwd_scratch_floats(...) floats. */
+int64_t geeco_conv2d_bwd_scratch_floats(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t stride);
+int geeco_conv2d_same_bwd(const float* x, const float* w, const float* dy_pre, const float* relu_mask_x, float* dw,
+                          float* db, float* dx, float* scratch, int64_t scratch_floats, int32_t N, int32_t H,
+                          int32_t W, int32_t Cin, int32_t Cout, int32_t stride, void* stream);
+
+/* ---- model step ------------------------------------------------------------------------------ */
+/* goal_e2evmc forward (graph.py:321-416) [+ losses when batch->cmd and out->losses are given];
+ * the predictor hook (predictor.py:148-190) and EVAL mode (estimator.py:246-258) use this. */
+int geeco_forward(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outputs* out, void* stream);
+/* model_fn in TRAIN mode (estimator.py:144-244): forward, losses, backward, Adam.
+ * grad_scale multiplies the gradients inside the optimizer (1/world_size after a summing all-reduce). */
+int geeco_train_step(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outputs* out, float grad_scale,
+                     void* stream);
+/* the same step in phases, so the host can all-reduce gradient buckets between them */
+int geeco_step_forward(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outputs* out, void* stream);
+int geeco_step_backward(geeco_ctx* ctx, int32_t bucket, void* stream);
+int geeco_step_update(geeco_ctx* ctx, float grad_scale, void* stream);
+
+/* ---- introspection for tests / profiling ------------------------------------------------------ */
+/* internal activation buffers by name ("x0", "y1".."y8", "g1".."g8", "state", "gates", "dstate", ...);
+ * dtype: 0 = f32, 1 = bf16 */
+int geeco_debug_buffer(const geeco_ctx* ctx, const char* name, void** ptr, int64_t* numel, int32_t* dtype);
+/* number of kernel launches enqueued by this library since the last call with reset != 0 */
+int64_t geeco_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEECO_B200_H_ */
