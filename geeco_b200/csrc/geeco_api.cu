@@ -410,7 +410,8 @@ extern "C" int geeco_set_lstm_state(geeco_ctx* c, const float* state_cm, void* s
 // ------------------------------------------------------------------------------------------
 extern "C" int geeco_dynimg(const float* in, float* out, int32_t N, int32_t K, int32_t H, int32_t W, int32_t C,
                             const float* alpha, int32_t cluster, float* scratch, void* stream) {
-  if (!in || !out) { geeco_set_error("dynimg: NULL tensor"); return GEECO_ERR_INVALID; }
+  if (N == 0) return GEECO_OK;
+  if (!in || !out || N < 0) { geeco_set_error("dynimg: NULL tensor"); return GEECO_ERR_INVALID; }
   if (K < 2 || K > 16) { geeco_set_error("dynimg: window size K=%d outside [2,16]", K); return GEECO_ERR_INVALID; }
   float tab[16];
   if (!alpha) { geeco_alpha_table(K, tab); alpha = tab; }

@@ -199,6 +199,10 @@ class Engine(object):
       raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(arr.shape)))
     if key not in self._dev_in:
       self._dev_in[key] = torch.empty(shape, dtype=torch.float32, device=self.device)
+    if arr.dtype == torch.float32 and arr.is_pinned():
+      self._dev_in[key].copy_(arr, non_blocking=True)       # caller-pinned: straight H2D
+      return self._dev_in[key]
+    if key not in self._pin_in:
       self._pin_in[key] = torch.empty(shape, dtype=torch.float32).pin_memory()
     self._pin_in[key].copy_(arr)
     self._dev_in[key].copy_(self._pin_in[key], non_blocking=True)
