@@ -41,6 +41,7 @@ def parse_args():
   ap.add_argument('--cpu-batch', type=int, default=4, help='windows per step of the CPU baseline sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-kernels', action='store_true', help='skip the isolated kernel roofline timings')
   return ap.parse_args()
 
 
@@ -272,7 +273,7 @@ def run_ours(args):
            'api': 'geeco_b200.engine.Engine.train_step(host pinned features, labels) -> losses.cpu()'}
 
   peaks = load_peaks()
-  roofline, extra = kernel_rooflines(eng, dev, peaks, args) if rank == 0 else (None, None)
+  roofline, extra = kernel_rooflines(eng, dev, peaks, args) if (rank == 0 and not args.no_kernels) else (None, None)
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     cpu_baseline = time_cpu_reference(args.cpu_batch, 5, 2)

@@ -1,0 +1,48 @@
+// bf16 tensor-core (tcgen05) gather-GEMM kernels: declarations shared with step_bf16.cu / geeco_api.cu
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+// Geometry of one tensor-core gather GEMM (bf16 NHWC source, implicit im2col).
+struct TcGeom {
+  int Hs, Ws, Cs;             // source tensor [imgs, Hs, Ws, Cs] (bf16), Cs % 8 == 0
+  int Hm, Wm;                 // GEMM-row pixel grid per image
+  int sy, sx;
+  int ntaps;
+  int dy[GEECO_MAX_TAPS], dx[GEECO_MAX_TAPS];
+  int Ktot, Kpad;             // ntaps*Cs and its round-up to 64
+  int Nn;                     // GEMM N (multiple of 16, <= 256)
+  int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
+  int dsy, dsx, dy0, dx0;
+  int imgs_per_group, groups;
+  int b_rows_per_group;       // rows of the packed weight matrix per group (tensor-map row offset)
+  long long bias_group_stride;
+};
+
+enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3 };
+
+struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packed tap
+
+// fwd / dgrad: dst = epi(A(src) x Wp^T)
+int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
+                 const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
+                 cudaStream_t st);
+// wgrad: dW[(tap,ci)][co] (+ optional bias gradient) from im2col(src)^T x G, deterministic split reduction.
+//   g describes the FORWARD geometry (rows = output pixels); G is [imgs, Hm, Wm, Cout] bf16.
+//   Cw = channels per tap present in the weight tensor (Cin_real); dW fp32 [ntaps*Cw, Cout] per group.
+long long tc_wgrad_partial_floats(const TcGeom& g, int Cout);
+int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
+                    float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
+                    long long dbias_group_stride, cudaStream_t st);
+// packed bf16 weights.  mode 0 (fwd): out[g][n][t*Cs + ch] = W[g][tap_t][ch][n] ; rows = Nn
+//                       mode 1 (dgrad): out[g][ci][t*Cout + co] = W[g][tap_t][ci][co] ; rows = Cin
+int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
+                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, cudaStream_t st);
+int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
+int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
+// 2-D tensor map over a packed weight matrix [rows_total][Kpad] bf16, box = 64 x box_rows, SWIZZLE_128B
+int make_weight_tensor_map(CUtensorMap* map, const void* base, long long rows_total, int Kpad, int box_rows);
+
+TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_group, int groups);
+bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, int groups,
+                   TcGeom* out, int* taps_out);

@@ -308,6 +308,7 @@ extern "C" int geeco_query_sizes(const geeco_config* cfg, geeco_sizes* out) {
   geeco_ctx tmp;
   tmp.cfg = *cfg;
   rc = plan(&tmp, nullptr);
+  free_bf16(&tmp);
   if (rc) return rc;
   out->arena_floats = tmp.arena_floats;
   out->workspace_bytes = (int64_t)tmp.workspace_bytes;
@@ -335,6 +336,7 @@ extern "C" int geeco_create(const geeco_config* cfg, geeco_ctx** out) {
 }
 
 extern "C" int geeco_destroy(geeco_ctx* ctx) {
+  if (ctx) free_bf16(ctx);
   delete ctx;
   return GEECO_OK;
 }

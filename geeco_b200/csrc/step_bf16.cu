@@ -1,8 +1,302 @@
-// bf16 / tcgen05 path of the conv encoders (placeholder until conv_tc.cu lands).
+// bf16 / tcgen05 path of the three conv encoders inside the model step, plus the stand-alone
+// bf16 conv ops exported for parity tests and kernel benchmarks.
+// Reference: conv_encoder, src/models/e2evmc/graph.py:61-117 (three scopes, :390-402).
 #include "plan.cuh"
-int plan_bf16(geeco_ctx*, size_t*, char*) {
-  geeco_set_error("precision GEECO_BF16 is not available in this build");
-  return GEECO_ERR_INVALID;
+#include "conv_tc.cuh"
+
+#include <string.h>
+
+struct Bf16Layer {
+  TcGeom fwd;                          // forward geometry (also the wgrad geometry)
+  __nv_bfloat16* w_fwd[3];             // packed [Cout][Kpad] per encoder (contiguous when grouped)
+  CUtensorMap fwd_map[3];
+  int n_classes;
+  TcGeom dg[4];
+  int dg_taps[4][9];
+  __nv_bfloat16* w_dg[4][3];
+  CUtensorMap dg_map[4][3];
+};
+
+struct Bf16Plan {
+  Bf16Layer L[8];
+  float* partial;
+  long long partial_cap;
+};
+
+static void* carve(size_t* off, char* base, size_t bytes) {
+  *off = (*off + 255) & ~(size_t)255;
+  void* p = base ? base + *off : nullptr;
+  *off += bytes;
+  return p;
 }
-int encoders_fwd_bf16(geeco_ctx*, cudaStream_t) { geeco_set_error("bf16 path not built"); return GEECO_ERR_INVALID; }
-int encoders_bwd_bf16(geeco_ctx*, int, int, cudaStream_t) { geeco_set_error("bf16 path not built"); return GEECO_ERR_INVALID; }
+
+int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
+  if (!c->bf16_ws) c->bf16_ws = new Bf16Plan();
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  const int N = c->cfg.batch_size;
+  long long cap = 0;
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    const int groups = L.grouped ? 3 : 1;
+    B.fwd = tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L.stride, N, groups);
+    B.n_classes = 0;
+    if (l > 0) {
+      for (int py = 0; py < L.stride; ++py)
+        for (int px = 0; px < L.stride; ++px) {
+          TcGeom dg;
+          int taps[9];
+          if (!tc_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[0], L.stride, py, px, N, groups, &dg, taps)) continue;
+          const int ci = B.n_classes++;
+          B.dg[ci] = dg;
+          memcpy(B.dg_taps[ci], taps, sizeof(taps));
+          for (int e = 0; e < 3; ++e) B.w_dg[ci][e] = nullptr;
+        }
+    }
+    for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
+      TcGeom g = B.fwd;
+      const long long need = tc_wgrad_partial_floats(g, L.Cout[e]);
+      if (need > cap) cap = need;
+    }
+  }
+  // contiguous packed-weight storage per layer: [enc][rows][Kpad]
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    size_t tot = 0;
+    for (int e = 0; e < 3; ++e) tot += (size_t)L.Cout[e] * B.fwd.Kpad;
+    __nv_bfloat16* base = (__nv_bfloat16*)carve(ws_off, ws_base, tot * 2);
+    size_t o = 0;
+    for (int e = 0; e < 3; ++e) { B.w_fwd[e] = base ? base + o : nullptr; o += (size_t)L.Cout[e] * B.fwd.Kpad; }
+    for (int ci = 0; ci < B.n_classes; ++ci) {
+      size_t t2 = 0;
+      for (int e = 0; e < 3; ++e) t2 += (size_t)L.Cin_real * ((B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64);
+      __nv_bfloat16* b2 = (__nv_bfloat16*)carve(ws_off, ws_base, t2 * 2);
+      size_t o2 = 0;
+      for (int e = 0; e < 3; ++e) {
+        B.w_dg[ci][e] = b2 ? b2 + o2 : nullptr;
+        o2 += (size_t)L.Cin_real * ((B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64);
+      }
+    }
+  }
+  bp->partial_cap = cap;
+  bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
+  if (!ws_base) return GEECO_OK;
+  // tensor maps (need the real addresses)
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    if (L.grouped) {
+      int rc = make_weight_tensor_map(&B.fwd_map[0], B.w_fwd[0], 3ll * L.Cout[0], B.fwd.Kpad, L.Cout[0]);
+      if (rc) return rc;
+      for (int ci = 0; ci < B.n_classes; ++ci) {
+        rc = make_weight_tensor_map(&B.dg_map[ci][0], B.w_dg[ci][0], 3ll * L.Cin_real, B.dg[ci].Kpad, L.Cin_real);
+        if (rc) return rc;
+      }
+    } else {
+      for (int e = 0; e < 3; ++e) {
+        int rc = make_weight_tensor_map(&B.fwd_map[e], B.w_fwd[e], L.Cout[e], B.fwd.Kpad, L.Cout[e]);
+        if (rc) return rc;
+        for (int ci = 0; ci < B.n_classes; ++ci) {
+          const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
+          rc = make_weight_tensor_map(&B.dg_map[ci][e], B.w_dg[ci][e], L.Cin_real, Kp, L.Cin_real);
+          if (rc) return rc;
+        }
+      }
+    }
+  }
+  return GEECO_OK;
+}
+
+void free_bf16(geeco_ctx* c) {
+  if (c->bf16_ws) { delete (Bf16Plan*)c->bf16_ws; c->bf16_ws = nullptr; }
+}
+
+static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+
+static int repack_weights(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
+    const int ne = L.grouped ? 1 : 3;
+    for (int e = 0; e < ne; ++e) {
+      const int groups = L.grouped ? 3 : 1;
+      const float* W = c->theta + c->params[L.p_w[e]].offset;
+      int rc = launch_pack_weights(W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps,
+                                   L.Cout[e], B.fwd.Kpad, st);
+      if (rc) return rc;
+      for (int ci = 0; ci < B.n_classes; ++ci) {
+        const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
+        rc = launch_pack_weights(W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps,
+                                 B.dg_taps[ci], L.Cin_real, Kp, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  c->weights_dirty = false;
+  return GEECO_OK;
+}
+
+int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
+  if (c->weights_dirty) {
+    int rc = repack_weights(c, st);
+    if (rc) return rc;
+  }
+  const int N = c->cfg.batch_size;
+  const __nv_bfloat16* src = (const __nv_bfloat16*)c->x0;
+  for (int l = 0; l < 8; ++l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    if (L.grouped) {
+      TcGeom g = B.fwd;
+      g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+      int rc = launch_tc_nn(g, &B.fwd_map[0], src, c->theta + c->params[L.p_b[0]].offset, nullptr,
+                            (__nv_bfloat16*)L.y, l == 7 ? c->y8_f32 : nullptr, TC_EPI_BIAS_RELU, 0, st);
+      if (rc) return rc;
+    } else {
+      for (int e = 0; e < 3; ++e) {
+        TcGeom g = tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[e], L.stride, N, 1);
+        const __nv_bfloat16* s = src + (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+        int rc = launch_tc_nn(g, &B.fwd_map[e], s, c->theta + c->params[L.p_b[e]].offset, nullptr,
+                              (__nv_bfloat16*)L.y + L.act_off[e], l == 7 ? c->y8_f32 + L.act_off[e] : nullptr,
+                              TC_EPI_BIAS_RELU, 0, st);
+        if (rc) return rc;
+      }
+    }
+    src = (const __nv_bfloat16*)L.y;
+  }
+  return GEECO_OK;
+}
+
+int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
+  const int N = c->cfg.batch_size;
+  if (lhi == 7) {
+    int rc = launch_f32_to_bf16(c->g8_f32, (__nv_bfloat16*)c->layers[7].g, c->layers[7].act_elems, st);
+    if (rc) return rc;
+  }
+  for (int l = lhi; l >= llo; --l) {
+    LayerPlan& L = c->layers[l];
+    Bf16Layer& B = bp->L[l];
+    const __nv_bfloat16* xin = l == 0 ? (const __nv_bfloat16*)c->x0 : (const __nv_bfloat16*)c->layers[l - 1].y;
+    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
+    const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+    const int ne = L.grouped ? 1 : 3;
+    for (int e = 0; e < ne; ++e) {
+      const int groups = L.grouped ? 3 : 1;
+      const long long in_off = L.grouped ? 0 : (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+      const __nv_bfloat16* gy = (const __nv_bfloat16*)L.g + (L.grouped ? 0 : L.act_off[e]);
+      TcGeom g = L.grouped ? B.fwd : tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[e], L.stride, N, 1);
+      int rc = launch_tc_wgrad(g, L.Cout[e], L.Cin_real, xin + in_off, gy, c->grad + c->params[L.p_w[e]].offset,
+                               c->grad + c->params[L.p_b[e]].offset, bp->partial, bp->partial_cap, wstride, bstride, st);
+      if (rc) return rc;
+      if (l == 0) continue;
+      for (int ci = 0; ci < B.n_classes; ++ci) {
+        TcGeom dg = B.dg[ci];
+        if (!L.grouped) {
+          int taps[9];
+          tc_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, dg.dy0, dg.dx0, N, 1, &dg, taps);
+        }
+        (void)groups;
+        rc = launch_tc_nn(dg, &B.dg_map[ci][e], gy, nullptr, xin + in_off, (__nv_bfloat16*)c->layers[l - 1].g + in_off,
+                          nullptr, TC_EPI_MASK, 0, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return GEECO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone bf16 conv ops (C-ABI, see include/geeco_b200.h)
+// ------------------------------------------------------------------------------------------------
+static size_t conv_bf16_scratch(int N, int H, int W, int Cin, int Cout, int stride, size_t* o_fwd, size_t o_dg[4],
+                                size_t* o_part, long long* part_floats) {
+  size_t off = 0;
+  TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
+  auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; size_t r = off; off += bytes; return r; };
+  *o_fwd = take((size_t)Cout * g.Kpad * 2);
+  int ci = 0;
+  for (int py = 0; py < stride; ++py)
+    for (int px = 0; px < stride; ++px) {
+      TcGeom dg; int taps[9];
+      if (!tc_dgrad_geom(H, W, Cin, Cout, stride, py, px, N, 1, &dg, taps)) continue;
+      o_dg[ci++] = take((size_t)Cin * dg.Kpad * 2);
+    }
+  *part_floats = tc_wgrad_partial_floats(g, Cout);
+  *o_part = take((size_t)*part_floats * 4);
+  return off + 256;
+}
+
+extern "C" int64_t geeco_conv2d_bf16_scratch_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout,
+                                                   int32_t stride) {
+  size_t a, b[4], p; long long pf;
+  return (int64_t)conv_bf16_scratch(N, H, W, Cin, Cout, stride, &a, b, &p, &pf);
+}
+
+extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float* b, void* y, float* y_f32,
+                                      void* scratch, int64_t scratch_bytes, int32_t N, int32_t H, int32_t W,
+                                      int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride, int32_t relu, void* stream) {
+  if (!x || !w || !scratch || (!y && !y_f32)) { geeco_set_error("conv2d_bf16: NULL tensor"); return GEECO_ERR_INVALID; }
+  if (H != W) { geeco_set_error("conv2d_bf16: square inputs only"); return GEECO_ERR_INVALID; }
+  size_t o_fwd, o_dg[4], o_part; long long pf;
+  if ((int64_t)conv_bf16_scratch(N, H, W, Cin, Cout, stride, &o_fwd, o_dg, &o_part, &pf) > scratch_bytes) {
+    geeco_set_error("conv2d_bf16: scratch too small"); return GEECO_ERR_WORKSPACE;
+  }
+  char* base = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  cudaStream_t st = (cudaStream_t)stream;
+  TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
+  __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_fwd);
+  int rc = launch_pack_weights(w, wp, 0, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, st);
+  if (rc) return rc;
+  CUtensorMap map;
+  rc = make_weight_tensor_map(&map, wp, Cout, g.Kpad, Cout);
+  if (rc) return rc;
+  return launch_tc_nn(g, &map, (const __nv_bfloat16*)x, b, nullptr, (__nv_bfloat16*)y, y_f32,
+                      b ? (relu ? TC_EPI_BIAS_RELU : TC_EPI_BIAS) : TC_EPI_STORE, 0, st);
+}
+
+extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x,
+                                          float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes,
+                                          int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cw, int32_t Cout,
+                                          int32_t stride, void* stream) {
+  if (!x || !w || !dy_pre || !scratch) { geeco_set_error("conv2d_bwd_bf16: NULL tensor"); return GEECO_ERR_INVALID; }
+  if (H != W) { geeco_set_error("conv2d_bwd_bf16: square inputs only"); return GEECO_ERR_INVALID; }
+  size_t o_fwd, o_dg[4], o_part; long long pf;
+  if ((int64_t)conv_bf16_scratch(N, H, W, Cin, Cout, stride, &o_fwd, o_dg, &o_part, &pf) > scratch_bytes) {
+    geeco_set_error("conv2d_bwd_bf16: scratch too small"); return GEECO_ERR_WORKSPACE;
+  }
+  char* base = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+  cudaStream_t st = (cudaStream_t)stream;
+  TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
+  int rc;
+  if (dw) {
+    rc = launch_tc_wgrad(g, Cout, Cw, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_pre, dw, db,
+                         (float*)(base + o_part), pf, 0, 0, st);
+    if (rc) return rc;
+  }
+  if (dx) {
+    if (Cw != Cin) { geeco_set_error("conv2d_bwd_bf16: dx needs Cw == Cin"); return GEECO_ERR_INVALID; }
+    int ci = 0;
+    for (int py = 0; py < stride; ++py)
+      for (int px = 0; px < stride; ++px) {
+        TcGeom dg; int taps[9];
+        if (!tc_dgrad_geom(H, W, Cin, Cout, stride, py, px, N, 1, &dg, taps)) continue;
+        __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_dg[ci++]);
+        rc = launch_pack_weights(w, wp, 1, 1, 0, Cin, Cout, Cout, dg.ntaps, taps, Cin, dg.Kpad, st);
+        if (rc) return rc;
+        CUtensorMap map;
+        rc = make_weight_tensor_map(&map, wp, Cin, dg.Kpad, Cin);
+        if (rc) return rc;
+        rc = launch_tc_nn(dg, &map, (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
+                          (__nv_bfloat16*)dx, nullptr, relu_mask_x ? TC_EPI_MASK : TC_EPI_STORE, 0, st);
+        if (rc) return rc;
+      }
+  }
+  return GEECO_OK;
+}

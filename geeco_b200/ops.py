@@ -72,3 +72,41 @@ def conv2d_same_bwd(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True):
   _lib.check(lib.geeco_conv2d_same_bwd(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx), _p(scratch),
                                        n, N, H, W, Cin, Cout, stride, _stream(x)))
   return dw, db, dx
+
+
+def _req_bf16(t, name):
+  if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+    raise ValueError("%s must be a contiguous bfloat16 CUDA tensor" % name)
+  return t
+
+
+def conv2d_same_bf16(x, w, b=None, stride=1, relu=True, want_f32=False):
+  """Tensor-core (tcgen05) conv: x bf16 [N,H,W,Cin] (Cin % 8 == 0), w fp32 HWIO [3,3,Cw,Cout] with Cw <= Cin."""
+  lib = _lib.load()
+  x, w = _req_bf16(x, 'x'), _req(w, 'w')
+  N, H, W, Cin = x.shape
+  Cw, Cout = w.shape[2], w.shape[3]
+  Ho, Wo = -(-H // stride), -(-W // stride)
+  y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+  y32 = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=x.device) if want_f32 else None
+  n = int(lib.geeco_conv2d_bf16_scratch_bytes(N, H, W, Cin, Cout, stride))
+  scratch = torch.empty(n, dtype=torch.uint8, device=x.device)
+  _lib.check(lib.geeco_conv2d_same_bf16(_p(x), _p(w), _p(b), _p(y), _p(y32), _p(scratch), n, N, H, W, Cin, Cw, Cout,
+                                        stride, 1 if relu else 0, _stream(x)))
+  return (y, y32) if want_f32 else y
+
+
+def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True):
+  """Tensor-core gradients of conv2d_same_bf16: returns (dw fp32, db fp32, dx bf16)."""
+  lib = _lib.load()
+  x, w, dy_pre = _req_bf16(x, 'x'), _req(w, 'w'), _req_bf16(dy_pre, 'dy_pre')
+  N, H, W, Cin = x.shape
+  Cw, Cout = w.shape[2], w.shape[3]
+  dw = torch.empty_like(w)
+  db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+  dx = torch.zeros_like(x) if need_dx else None
+  n = int(lib.geeco_conv2d_bf16_scratch_bytes(N, H, W, Cin, Cout, stride))
+  scratch = torch.empty(n, dtype=torch.uint8, device=x.device)
+  _lib.check(lib.geeco_conv2d_same_bwd_bf16(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx),
+                                            _p(scratch), n, N, H, W, Cin, Cw, Cout, stride, _stream(x)))
+  return dw, db, dx

@@ -136,6 +136,17 @@ int geeco_conv2d_same_bwd(const float* x, const float* w, const float* dy_pre, c
                           float* db, float* dx, float* scratch, int64_t scratch_floats, int32_t N, int32_t H,
                           int32_t W, int32_t Cin, int32_t Cout, int32_t stride, void* stream);
 
+/* bf16 tensor-core (tcgen05) versions of the two ops above.  x / y / dy_pre / relu_mask_x / dx are bf16 NHWC,
+ * Cin % 8 == 0, Cout % 16 == 0, Cout <= 256; w, b, dw, db stay fp32 in TF layout with Cw <= Cin real input
+ * channels (w is [3,3,Cw,Cout]; x channels >= Cw must be zero).  y_f32 (optional) receives an fp32 copy. */
+int64_t geeco_conv2d_bf16_scratch_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t stride);
+int geeco_conv2d_same_bf16(const void* x, const float* w, const float* b, void* y, float* y_f32, void* scratch,
+                           int64_t scratch_bytes, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cw,
+                           int32_t Cout, int32_t stride, int32_t relu, void* stream);
+int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x, float* dw,
+                               float* db, void* dx, void* scratch, int64_t scratch_bytes, int32_t N, int32_t H,
+                               int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride, void* stream);
+
 /* ---- model step ------------------------------------------------------------------------------ */
 /* goal_e2evmc forward (graph.py:321-416) [+ losses when batch->cmd and out->losses are given];
  * the predictor hook (predictor.py:148-190) and EVAL mode (estimator.py:246-258) use this. */

@@ -1,0 +1,63 @@
+"""GPU parity of the tcgen05 (bf16) conv kernels against the CPU oracle evaluated on the same
+bf16-rounded operands: the fp32 copy of the output must agree to fp32-accumulation accuracy, the bf16
+output to bf16 rounding (2^-9 relative)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geeco_oracle as O
+from tests.util import rel_l2, rel_max
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+CASES = [
+    # N, H, Cin(storage), Cw(real), Cout, stride
+    (2, 16, 8, 3, 32, 1),        # conv1-like: channel-padded input, K 72 -> 128
+    (2, 16, 32, 32, 48, 2),      # conv2-like: K 288 -> 320
+    (3, 8, 48, 48, 64, 2),       # conv3-like: K 432 -> 448
+    (2, 8, 64, 64, 128, 2),
+    (5, 4, 128, 128, 192, 2),    # M = 20 rows: one partial tile
+    (2, 4, 256, 256, 256, 2),    # N = 256: full TMEM double buffer
+    (1, 64, 8, 4, 32, 1),        # 4096 rows: 32 tiles, rgbd-like
+    (3, 32, 32, 32, 48, 2),      # 768 rows: multi-tile persistent loop
+    (40, 2, 256, 256, 256, 2),   # conv8-like at batch 40
+]
+
+
+def _bf(x):
+  return torch.from_numpy(x).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv2d_bf16_fwd_bwd_matches_oracle(cuda_device, case):
+  from geeco_b200 import ops
+  N, H, Cin, Cw, Cout, stride = case
+  rng = np.random.default_rng(sum(case))
+  x = rng.uniform(0, 1, size=(N, H, H, Cin)).astype(np.float32)
+  x[..., Cw:] = 0.0
+  w = rng.uniform(-0.2, 0.2, size=(3, 3, Cw, Cout)).astype(np.float32)
+  b = rng.uniform(-0.1, 0.1, size=(Cout,)).astype(np.float32)
+  xb, wb = _bf(x), _bf(w)
+  xt = xb[..., :Cw].double().requires_grad_(True)
+  wt = wb.double().requires_grad_(True)
+  bt = torch.from_numpy(b).double().requires_grad_(True)
+  y_ref = O.conv2d_same(xt, wt, bt, stride, relu=True)
+  up = _bf(rng.uniform(-1, 1, size=tuple(y_ref.shape)).astype(np.float32))
+  dy_pre_ref = up.double() * (y_ref.detach() > 0)
+  y_ref.backward(dy_pre_ref)      # d/dy of relu output: equivalent to feeding dy_pre into the pre-activation
+  xd = xb.to(cuda_device)
+  wd = wb.float().to(cuda_device)
+  bd = torch.from_numpy(b).to(cuda_device)
+  y, y32 = ops.conv2d_same_bf16(xd, wd, bd, stride=stride, relu=True, want_f32=True)
+  torch.cuda.synchronize()
+  assert rel_max(y32.cpu().numpy(), y_ref.detach().numpy()) <= 2e-5, 'fwd f32'
+  assert rel_max(y.float().cpu().numpy(), y_ref.detach().numpy()) <= 5e-3, 'fwd bf16'
+  dyb = _bf(dy_pre_ref.float().numpy()).to(cuda_device).contiguous()
+  mask = xd if Cw == Cin else None
+  dw, db, dx = ops.conv2d_same_bwd_bf16(xd, wd, dyb, stride=stride, relu_mask_x=mask, need_dx=(Cw == Cin))
+  torch.cuda.synchronize()
+  assert rel_max(dw.cpu().numpy(), wt.grad.numpy()) <= 2e-5, 'dw'
+  assert rel_max(db.cpu().numpy(), bt.grad.numpy()) <= 2e-5, 'db'
+  if Cw == Cin:
+    ref_dx = xt.grad.numpy() * (xb.double().numpy() > 0)
+    assert rel_max(dx.float().cpu().numpy(), ref_dx) <= 5e-3, 'dx'
