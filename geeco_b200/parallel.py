@@ -1,0 +1,56 @@
+"""Data-parallel plumbing (one process per GPU, torch.distributed / NCCL over NVLink).
+
+The reference has no distributed path at all; the hot path shards by batch with ONE
+exchange step: a summing all-reduce of the flat gradient arena, issued bucket by bucket (late layers
+first) while the remaining backward kernels run, and divided by the world size inside the fused
+Adam kernel.  Every loss is a batch mean and nothing else couples samples, so with equal per-rank
+batches the result equals the global-batch gradient exactly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .data import rank_slice  # noqa: F401  (re-exported: the stream partition of SURVEY 8e)
+
+
+def world_info():
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_rank(), dist.get_world_size()
+  return 0, 1
+
+
+def allreduce_bucket(flat_grad: torch.Tensor, bucket, async_op=True):
+  """Summing all-reduce of arena floats [offset, offset+numel).  Returns the work handle (or None)."""
+  off, cnt = bucket
+  if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    return None
+  return dist.all_reduce(flat_grad[off:off + cnt], op=dist.ReduceOp.SUM, async_op=async_op)
+
+
+def data_parallel_step(engine, features, labels):
+  """forward -> [backward bucket b ; all-reduce bucket b (async)]* -> wait -> Adam with 1/world."""
+  rank, world = world_info()
+  if world == 1:
+    return engine.train_step(features, labels)
+  engine.step_forward(features, labels)
+  works = []
+  for b in range(len(engine.buckets)):
+    engine.step_backward(b)
+    works.append(allreduce_bucket(engine.grad, engine.buckets[b], async_op=True))
+  for w in works:
+    if w is not None:
+      w.wait()
+  engine.step_update(1.0 / world)
+  return engine.out_losses
+
+
+def broadcast_parameters(engine, src=0):
+  """All replicas start from rank `src`'s parameters (and Adam slots)."""
+  rank, world = world_info()
+  if world == 1:
+    return
+  for t in (engine.theta, engine.adam_m, engine.adam_v):
+    if t is not None:
+      dist.broadcast(t, src=src)
+  engine.params_changed()

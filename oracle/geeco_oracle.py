@@ -138,14 +138,55 @@ def conv2d_same(x_nhwc: torch.Tensor, w_hwio: torch.Tensor, b: torch.Tensor, str
   return y.permute(0, 2, 3, 1)
 
 
-def conv_encoder(x_nhwc, params, scope, return_all=False):
-  """graph.py:61-117; `scope` e.g. 'GoalVMC/ConvEncoder'."""
+class _RoundBF16(torch.autograd.Function):
+  """forward: round to bfloat16 (value kept in the working dtype); backward: identity."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g
+
+
+class _GradRoundBF16(torch.autograd.Function):
+  """forward: identity; backward: round the incoming gradient to bfloat16."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.view_as(x)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).to(g.dtype)
+
+
+def round_bf16(x):
+  return _RoundBF16.apply(x)
+
+
+def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False):
+  """graph.py:61-117; `scope` e.g. 'GoalVMC/ConvEncoder'.
+
+  emulate_bf16=True restates the SAME graph with the storage roundings of the library's bf16 mode
+  (DESIGN.md "bf16 policy"): encoder input, conv kernels, every post-ReLU activation except conv8's
+  and every pre-activation gradient are rounded to bfloat16; accumulation, biases, master weights and
+  everything after conv8 stay in the working dtype.  It exists because ReLU-mask flips make the bf16
+  gradients differ from the fp32 graph's by O(sqrt(eps)), which says nothing about kernel correctness."""
   acts = []
-  net = x_nhwc
+  net = round_bf16(x_nhwc) if emulate_bf16 else x_nhwc
   for li in range(8):
     w = params['%s/conv%d/kernel' % (scope, li + 1)]
     b = params['%s/conv%d/bias' % (scope, li + 1)]
-    net = conv2d_same(net, w, b, ENCODER_STRIDES[li], relu=True)
+    if emulate_bf16:
+      z = conv2d_same(net, round_bf16(w), b, ENCODER_STRIDES[li], relu=False)
+      z = _GradRoundBF16.apply(z)
+      net = torch.relu(z)
+      if li < 7:
+        net = round_bf16(net)
+    else:
+      net = conv2d_same(net, w, b, ENCODER_STRIDES[li], relu=True)
     acts.append(net)
   return (net, acts) if return_all else net
 
@@ -219,7 +260,7 @@ def lstm_decoder(feat_list, params, cfg, scope='GoalVMC/LSTMDecoder', init_state
 # model fns (graph.py:268-416)
 # --------------------------------------------------------------------------
 def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC', init_state=None,
-                alpha=None):
+                alpha=None, emulate_bf16=False):
   """graph.py:321-416.  rgb_frames [N,K,H,W,C], jnt_states [N,K,7], tgt_frame [N,H,W,C]."""
   ep = OrderedDict()
   K = cfg['window_size']
@@ -246,14 +287,15 @@ def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC',
       feat_list.append(state)
   elif proc_obs == 'dynimg':
     cur, jnt = frames[-1], jnts[-1]
-    feat, acts = conv_encoder(cur, params, scope + '/ConvEncoder', return_all=True)
+    eb = emulate_bf16
+    feat, acts = conv_encoder(cur, params, scope + '/ConvEncoder', return_all=True, emulate_bf16=eb)
     ep['obs_acts'] = acts
     dyn_buff = dynimg(rgb_frames, alpha)
     ep['dynbuff'] = dyn_buff
-    dyn_feat = conv_encoder(dyn_buff, params, scope + '/DynBuffEncoder')
+    dyn_feat = conv_encoder(dyn_buff, params, scope + '/DynBuffEncoder', emulate_bf16=eb)
     dd = dyndiff(cur, tgt_frame)
     ep['dyndiff'] = dd
-    tgt_feat = conv_encoder(dd, params, scope + '/DynDiffEncoder')
+    tgt_feat = conv_encoder(dd, params, scope + '/DynDiffEncoder', emulate_bf16=eb)
     ep['conv8_obs'], ep['conv8_dyn'], ep['conv8_diff'] = feat, dyn_feat, tgt_feat
     feat_list.append(representation_concatenation_v2(feat, dyn_feat, jnt, tgt_feat))
   else:
@@ -439,23 +481,23 @@ def _to(x, dtype):
   return torch.as_tensor(np.asarray(x)).to(dtype) if not torch.is_tensor(x) else x.to(dtype)
 
 
-def forward_losses(params, features, labels, cfg, init_state=None):
+def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=False):
   dt = next(iter(params.values())).dtype
   rgb = _to(features['rgb'], dt)
   tgt = _to(features['target_rgb'], dt)
   jnt = _to(features['jnt_state'], dt)
   f2 = {'ee_state': _to(features['ee_state'], dt), 'obj_state': _to(features['obj_state'], dt)}
   l2 = {'cmd': _to(labels['cmd'], dt)}
-  net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state)
+  net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16)
   losses = losses_cartesian(ep, f2, l2, params, cfg)
   return losses, ep
 
 
-def train_step(params, opt_state, features, labels, cfg, retain=()):
+def train_step(params, opt_state, features, labels, cfg, retain=(), emulate_bf16=False):
   """model_fn in TRAIN mode: forward, losses, gradients, one Adam update (in place).
   Returns (losses, grads, endpoints)."""
   leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
-  losses, ep = forward_losses(leaves, features, labels, cfg)
+  losses, ep = forward_losses(leaves, features, labels, cfg, emulate_bf16=emulate_bf16)
   for k in retain:
     ep[k].retain_grad()
   losses['loss'].backward()

@@ -1,0 +1,193 @@
+"""CPU-only tests of the host side: config record, input index contract, C-ABI surface, gloo path."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_config_record_matches_reference_defaults(tmp_path):
+  from geeco_b200 import (E2E_VMC_DEFAULT_CONFIG, E2E_VMC_DEFAULT_PARAM_DICT, create_e2evmc_config,
+                          load_model_config, save_model_config)
+  # params.py:7-28 of the reference
+  expect = dict(img_height=256, img_width=256, img_channels=3, dim_jnt_state=7, dim_grp_command=2,
+                control_mode='cartesian', num_grp_states=3, dim_action=4, proc_obs='sequence', proc_tgt='constant',
+                dim_s_obs=256, dim_s_dyn=256, dim_s_diff=256, dim_h_lstm=128, dim_h_fc=128, window_size=4,
+                l2_regularizer=0.0, lambda_aux=1.0, batch_size=32, lr=1e-4)
+  assert E2E_VMC_DEFAULT_PARAM_DICT == expect
+  assert list(E2E_VMC_DEFAULT_CONFIG._fields) == list(expect.keys())
+  cfg = create_e2evmc_config({'proc_obs': 'dynimg', 'unknown_key': 1, 'lr': 3e-4})
+  assert cfg.proc_obs == 'dynimg' and cfg.lr == 3e-4 and not hasattr(cfg, 'unknown_key')
+  with pytest.raises(AttributeError):
+    cfg.lr = 1.0
+  save_model_config(cfg._asdict(), str(tmp_path), 'e2evmc_config')
+  with open(os.path.join(str(tmp_path), 'e2evmc_config.json')) as fp:
+    txt = fp.read()
+  assert txt.startswith('{\n  "batch_size": 32')          # indent=2, sort_keys=True
+  assert create_e2evmc_config(load_model_config(str(tmp_path), 'e2evmc_config')) == cfg
+
+
+def _literal_windows(L, K):
+  """Literal transcription of _preprocess_targets_v3 + _window_v3 on frame indices."""
+  seq = list(range(L))[:-1]                 # drop last frame
+  S = L - 1
+  return [seq[i:i + K] for i in range(S - K + 1)]
+
+
+def test_window_index_contract_property():
+  from hypothesis import given, settings, strategies as st
+  from geeco_b200 import data as D
+  from oracle import geeco_oracle as O
+
+  @settings(max_examples=200, deadline=None)
+  @given(st.integers(min_value=3, max_value=300), st.integers(min_value=1, max_value=16), st.integers(0, 10 ** 6))
+  def prop(L, K, g):
+    if K > L - 1:
+      return
+    lit = _literal_windows(L, K)
+    idx = D.window_frame_indices(L, K)
+    assert idx.dtype == np.int64 and idx.tolist() == lit
+    assert np.array_equal(idx, O.window_indices(L, K))
+    nw = D.num_windows(L, K)
+    assert nw == len(lit) == L - K
+    e, w, cur, tgt = D.locate(g, L, K)
+    assert e * nw + w == g and 0 <= w < nw
+    assert cur == lit[w][-1] and tgt == L - 1
+    assert O.stream_index(g, L, K)[:4] == (e, w, cur, tgt)
+  prop()
+  assert D.num_windows(100, 4) == 96           # 3 batches of 32 per episode
+
+
+def test_rank_slices_partition_the_global_batch():
+  from geeco_b200.data import rank_slice
+  for world in (1, 2, 4, 8):
+    seen = []
+    for r in range(world):
+      lo, hi = rank_slice(3, 512, r, world)
+      seen.extend(range(lo, hi))
+    assert seen == list(range(3 * 512, 4 * 512))
+  with pytest.raises(ValueError):
+    rank_slice(0, 510, 0, 4)
+
+
+def test_synthetic_batch_layout():
+  from geeco_b200.data import synthetic_batch
+  f, l = synthetic_batch(3, seed=0, first_stream_pos=94)
+  assert f['rgb'].shape == (3, 4, 256, 256, 3) and f['rgb'].dtype == np.float32
+  assert f['target_rgb'].shape == (3, 256, 256, 3)
+  assert f['jnt_state'].shape == (3, 4, 7) and f['ee_state'].shape == (3, 4, 7) and f['obj_state'].shape == (3, 4, 7)
+  assert f['step'].dtype == np.int64 and f['step'].tolist() == [[94, 95, 96, 97], [95, 96, 97, 98], [0, 1, 2, 3]]
+  assert l['cmd'].shape == (3, 4) and set(np.unique(l['cmd'][:, 3])).issubset({-1.0, 0.0, 1.0})
+  q = f['rgb'] * 255.0
+  assert np.abs(q - np.rint(q)).max() < 1e-4 and f['rgb'].min() >= 0 and f['rgb'].max() <= 1
+  assert not np.array_equal(f['rgb'][:, 0], f['rgb'][:, 1])      # never a static buffer
+  f2, _ = synthetic_batch(3, seed=0, first_stream_pos=94)
+  assert np.array_equal(f['rgb'], f2['rgb'])
+
+
+def _header_functions():
+  with open(os.path.join(ROOT, 'include', 'geeco_b200.h')) as fp:
+    src = fp.read()
+  src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+  return sorted(set(re.findall(r'\b(geeco_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+  import ctypes
+  from geeco_b200 import _lib
+  from geeco_b200.build import build_library
+  build_library()
+  names = _header_functions()
+  assert len(names) >= 20
+  assert sorted(_lib.SYMBOLS.keys()) == names, set(names) ^ set(_lib.SYMBOLS.keys())
+  lib = _lib.load()
+  raw = ctypes.CDLL(_lib.LIB_PATH)
+  for n in names:
+    assert getattr(raw, n) is not None
+  assert lib.geeco_version() >= 100
+  # host-only entry points work without a GPU
+  a = _lib.alpha_table(4)
+  assert np.allclose(a, [-2.416668, 0.58333254, 1.0833325, 0.7499994], atol=2e-7)
+  from oracle import geeco_oracle as O
+  for K in range(2, 17):
+    assert np.array_equal(_lib.alpha_table(K), O.alpha_table_f32(K)), K
+  c = _lib.GeecoConfig()
+  for k, v in dict(img_height=256, img_width=256, img_channels=3, dim_jnt_state=7, window_size=4, dim_s_obs=256,
+                   dim_s_dyn=256, dim_s_diff=256, dim_h_lstm=128, dim_h_fc=128, num_grp_states=3, batch_size=64,
+                   precision=1, training=1).items():
+    setattr(c, k, v)
+  s = _lib.GeecoSizes()
+  _lib.check(lib.geeco_query_sizes(ctypes.byref(c), ctypes.byref(s)))
+  assert s.num_params == 60 and s.num_buckets == 3 and 7552796 <= s.arena_floats < 7552796 + 4 * 60
+  assert s.workspace_bytes > 2 ** 30
+  c.img_channels = 5
+  with pytest.raises(ValueError):
+    _lib.check(lib.geeco_query_sizes(ctypes.byref(c), ctypes.byref(s)))
+
+
+def test_product_fails_loudly_without_gpu():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("GPU present")
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.engine import Engine
+  with pytest.raises(RuntimeError):
+    Engine(create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff')), batch_size=1)
+
+
+def test_product_never_imports_the_oracle():
+  for dirpath, _, files in os.walk(os.path.join(ROOT, 'geeco_b200')):
+    for fn in files:
+      if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+        with open(os.path.join(dirpath, fn)) as fp:
+          txt = fp.read()
+        assert 'import oracle' not in txt and 'from oracle' not in txt, fn
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import torch, torch.distributed as dist
+from geeco_b200 import parallel
+from geeco_b200.data import rank_slice
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+class FakeEngine:
+  def __init__(self):
+    self.grad = torch.zeros(10); self.buckets = [(0, 4), (4, 4), (8, 2)]; self.theta = torch.zeros(10)
+    self.adam_m = None; self.adam_v = None; self.log = []; self.out_losses = torch.zeros(8)
+  def step_forward(self, f, l): self.log.append('fwd')
+  def step_backward(self, b):
+    off, cnt = self.buckets[b]; self.grad[off:off + cnt] = float(rank + 1) * (b + 1); self.log.append('bwd%%d' %% b)
+  def step_update(self, scale): self.theta -= self.grad * scale; self.log.append('upd')
+  def params_changed(self): pass
+e = FakeEngine()
+parallel.data_parallel_step(e, None, None)
+exp = torch.tensor([1.5] * 4 + [3.0] * 4 + [4.5] * 2)      # mean over ranks of (rank+1)*(b+1)
+assert torch.allclose(-e.theta, exp), e.theta
+assert e.log == ['fwd', 'bwd0', 'bwd1', 'bwd2', 'upd']
+e.theta = torch.full((10,), float(rank))
+parallel.broadcast_parameters(e, src=0)
+assert float(e.theta.abs().max()) == 0.0
+lo, hi = rank_slice(0, 8, rank, world)
+assert (lo, hi) == (rank * 4, rank * 4 + 4)
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+@pytest.mark.timeout(180)
+def test_data_parallel_step_world_size_2_gloo(tmp_path):
+  script = os.path.join(str(tmp_path), 'worker.py')
+  with open(script, 'w') as fp:
+    fp.write(_GLOO_WORKER % {'root': ROOT})
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
+         '127.0.0.1', '--master-port', '29541', script]
+  r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=170)
+  assert r.returncode == 0, r.stdout[-3000:]
+  assert 'ok 0' in r.stdout and 'ok 1' in r.stdout
