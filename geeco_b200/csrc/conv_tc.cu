@@ -5,17 +5,23 @@
 //
 // tc_nn_kernel   (forward, data-gradient):  D[m][n] = sum_k A[m][k] * Wp[n][k]
 //   A  : implicit im2col rows (one output pixel each), gathered from the NHWC bf16 activation with
-//        16-byte cp.async into a 128x64 K-major SWIZZLE_128B shared-memory tile (zero-fill = padding)
+//        cp.async (16-byte pieces; 8-byte pieces for the 4-channel network input) into a 128x64
+//        K-major SWIZZLE_128B shared-memory tile; zero-fill = SAME padding / out-of-range rows
 //   Wp : pre-packed bf16 weights [N][Kpad], streamed by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B)
 //   D  : fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
 //        tile i+1; epilogue = tcgen05.ld -> bias+ReLU (fwd) or ReLU-mask (dgrad) -> bf16 NHWC store
-//   Persistent CTAs, warp roles: 0-3 gather producers, 4-7 epilogue, 8 MMA issuer (+TMEM alloc), 9 TMA.
+//   Persistent CTAs; warp roles: 0-7 gather producers, 8-11 epilogue, 12 MMA issuer (+TMEM alloc), 13 TMA.
 //
 // tc_wgrad_kernel (weight gradient):  dW^T[co][(tap,ci)] = sum_pixels G[p][co] * im2col[p][(tap,ci)]
 //   both operands are gathered as MN-major SWIZZLE_128B tiles (64 pixels x 64 values per sub-tile);
 //   M = 128 output channels, N <= 256 reduction-index values per CTA, split over pixel ranges with a
 //   deterministic second-stage reduction; the bias gradient rides along as a column of ones when the
 //   reduction index has padding to spare.
+//
+// Producer cost matters as much as the MMAs here (conv1-conv3 are HBM/L2-bound): row
+// decoding uses shifts (all map sizes are powers of two), source pointers and per-tap validity masks
+// are computed once per tile, and pieces that are padding for the whole launch are never written
+// (shared memory is zeroed once).
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
@@ -27,129 +33,167 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-constexpr int LOOKAHEAD = 2;
-constexpr int NN_THREADS = 320;
-constexpr int WG_THREADS = 288;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int PROD_THREADS = 256;
+constexpr int NN_THREADS = PROD_THREADS + 128 + 64;   // 448
+constexpr int WG_THREADS = PROD_THREADS + 128 + 32;   // 416
+constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
+constexpr int SUB = 64 * 128;                         // one 64-row x 128-byte sub-tile
 
-struct RowDec {
-  int pix;      // (group*ipg + img) * Hs * Ws
-  int ys, xs;   // y*sy, x*sx  (ys = -(1<<20) marks an invalid row -> every tap is out of bounds)
-};
+__device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+template <int PIECE>
+__device__ __forceinline__ void cp_piece(uint32_t dst_smem, const void* src, bool ok) {
+  if (PIECE == 8) cp_async16(dst_smem, src, ok ? 16u : 0u);
+  else cp_async8(dst_smem, src, ok ? 8u : 0u);
+}
 
-__device__ __forceinline__ RowDec decode_row_tc(const TcGeom& g, int group, long long m, long long Mg) {
-  RowDec r;
-  if (m < Mg) {
-    const int hw = g.Hm * g.Wm;
-    const int img = (int)(m / hw);
-    const int rem = (int)(m - (long long)img * hw);
-    const int y = rem / g.Wm, x = rem - y * g.Wm;
-    r.pix = (group * g.imgs_per_group + img) * g.Hs * g.Ws;
-    r.ys = y * g.sy; r.xs = x * g.sx;
+// (img, y, x) of GEMM row m of a group; shifts when the map sizes are powers of two
+__device__ __forceinline__ void decode_pixel(const TcGeom& g, uint32_t m, int& img, int& y, int& x) {
+  if (g.hw_shift >= 0) {
+    img = (int)(m >> g.hw_shift);
+    const uint32_t rem = m & ((1u << g.hw_shift) - 1u);
+    y = (int)(rem >> g.w_shift);
+    x = (int)(rem & ((1u << g.w_shift) - 1u));
   } else {
-    r.pix = 0; r.ys = -(1 << 20); r.xs = 0;
+    const uint32_t hw = (uint32_t)(g.Hm * g.Wm);
+    img = (int)(m / hw);
+    const uint32_t rem = m - (uint32_t)img * hw;
+    y = (int)(rem / (uint32_t)g.Wm);
+    x = (int)(rem - (uint32_t)y * (uint32_t)g.Wm);
   }
-  return r;
+}
+__device__ __forceinline__ void split_k(const TcGeom& g, int k, int& tap, int& ch) {
+  if (g.cs_shift >= 0) { tap = k >> g.cs_shift; ch = k & (g.Cs - 1); }
+  else { tap = k / g.Cs; ch = k - tap * g.Cs; }
+}
+// bit t set <=> tap t of source pixel (ys+dy[t], xs+dx[t]) lies inside the image
+__device__ __forceinline__ uint32_t tap_mask(const TcGeom& g, int ys, int xs) {
+  uint32_t mk = 0;
+#pragma unroll
+  for (int t = 0; t < GEECO_MAX_TAPS; ++t) {
+    if (t < g.ntaps) {
+      const int iy = ys + g.dy[t], ix = xs + g.dx[t];
+      if ((unsigned)iy < (unsigned)g.Hs && (unsigned)ix < (unsigned)g.Ws) mk |= 1u << t;
+    }
+  }
+  return mk;
+}
+
+__device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
+  for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward / data-gradient kernel
+// forward / data-gradient kernel.  PIECE = bf16 elements per cp.async (8 -> 16 B, 4 -> 8 B)
 // ------------------------------------------------------------------------------------------------
+template <int PIECE>
 __global__ void __launch_bounds__(NN_THREADS, 1)
 tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
-             int total_tiles, int tmem_cols) {
+             int total_tiles, int tmem_cols, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
   const int b_stage_bytes = BN * BK * 2;
   uint8_t* a_base = smem;
-  uint8_t* b_base = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + STAGES * b_stage_bytes);
+  uint8_t* b_base = smem + stages * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + stages * b_stage_bytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128 + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS + 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
-  if (warp == 9 && lane == 0) tma_prefetch_desc(&wmap);
+  if (g.Kpad > g.Ktot) {          // padding columns are never written by the producers
+    zero_smem(a_base, stages * A_STAGE_BYTES);
+    fence_proxy_async();
+  }
+  if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+  if (warp == 13 && lane == 0) tma_prefetch_desc(&wmap);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
   const int nkb = g.Kpad / BK;
-  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  const uint32_t Mg = (uint32_t)g.imgs_per_group * (uint32_t)(g.Hm * g.Wm);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== A producers: implicit-im2col gather =====================
-    const int chunk = lane & 7, rsub = lane >> 3;
+    constexpr int PPR = BK / PIECE;                 // pieces per 128-byte row
+    constexpr int ROWS_PER_PASS = PROD_THREADS / PPR;
+    constexpr int PASSES = BM / ROWS_PER_PASS;
+    const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
+    const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int group = tile / tiles_per_group;
-      const long long m0 = (long long)(tile - group * tiles_per_group) * BM;
-      RowDec rd[8];
+      const uint32_t m0 = (uint32_t)(tile - group * tiles_per_group) * BM;
+      // per row: pointer to source pixel (ys, xs) and the coordinates themselves; an out-of-range row
+      // gets ys = 1<<20 so that every tap fails the bounds test and zero-fills
+      const __nv_bfloat16* rptr[PASSES];
+      int rys[PASSES], rxs[PASSES];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rd[i] = decode_row_tc(g, group, m0 + warp * 32 + i * 4 + rsub, Mg);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-        const int k = kb * BK + chunk * 8;
-        const bool kvalid = k < g.Ktot;
-        const int tap = kvalid ? k / g.Cs : 0;
-        const int ch = k - tap * g.Cs;
-        const int dyt = g.dy[tap], dxt = g.dx[tap];
-        const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = warp * 32 + i * 4 + rsub;
-          const int iy = rd[i].ys + dyt, ix = rd[i].xs + dxt;
-          const bool ok = kvalid && (unsigned)iy < (unsigned)g.Hs && (unsigned)ix < (unsigned)g.Ws;
-          const __nv_bfloat16* p = ok ? src + ((long long)(rd[i].pix + iy * g.Ws + ix) * g.Cs + ch) : src;
-          cp_async16(a_s + row * 128 + ((chunk ^ (row & 7)) << 4), p, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (it >= LOOKAHEAD) {
-          cp_async_wait<LOOKAHEAD>();
-          fence_proxy_async();
-          mbar_arrive(&full[(it - LOOKAHEAD) % STAGES]);
+      for (int i = 0; i < PASSES; ++i) {
+        const uint32_t m = m0 + i * ROWS_PER_PASS + rsub;
+        rptr[i] = src; rys[i] = 1 << 20; rxs[i] = 0;
+        if (m < Mg) {
+          int img, y, x;
+          decode_pixel(g, m, img, y, x);
+          rys[i] = y * g.sy; rxs[i] = x * g.sx;
+          rptr[i] = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + rys[i]) * g.Ws + rxs[i]) * g.Cs;
         }
       }
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % stages;
+        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int k = kb * BK + piece * PIECE;
+        if (k < g.Ktot) {
+          int tap, ch;
+          split_k(g, k, tap, ch);
+          const int dyt = g.dy[tap], dxt = g.dx[tap];
+          const int toff = (dyt * g.Ws + dxt) * g.Cs + ch;
+          const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < PASSES; ++i) {
+            const int row = i * ROWS_PER_PASS + rsub;
+            const bool ok = (unsigned)(rys[i] + dyt) < (unsigned)g.Hs && (unsigned)(rxs[i] + dxt) < (unsigned)g.Ws;
+            const uint32_t d = a_s + row * 128 + ((((pbyte >> 4) ^ (uint32_t)(row & 7))) << 4) + (pbyte & 15u);
+            cp_piece<PIECE>(d, ok ? (const void*)(rptr[i] + toff) : (const void*)src, ok);
+          }
+        }
+        // asynchronous arrival: fires when this thread's copies have landed; the producer never waits
+        cp_async_mbar_arrive_noinc(&full[s]);
+      }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    const uint32_t first = it >= LOOKAHEAD ? it - LOOKAHEAD : 0;
-    for (uint32_t j = first; j < it; ++j) mbar_arrive(&full[j % STAGES]);
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int hw = g.Hm * g.Wm;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const int group = tile / tiles_per_group;
-      const long long m = (long long)(tile - group * tiles_per_group) * BM + row;
+      const uint32_t m = (uint32_t)(tile - group * tiles_per_group) * BM + row;
       const int buf = tl & 1;
-      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
-      tc_fence_after();
       const bool valid = m < Mg;
       long long off = 0;
       if (valid) {
-        const int img = (int)(m / hw);
-        const int rem = (int)(m - (long long)img * hw);
-        const int y = rem / g.Wm, x = rem - y * g.Wm;
+        int img, y, x;
+        decode_pixel(g, m, img, y, x);
         off = ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + g.dy0)) * g.Wd + (x * g.dsx + g.dx0)) * g.Nn;
       }
       const float* bias = bias_all ? bias_all + (long long)group * g.bias_group_stride : nullptr;
+      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t v[16];
@@ -159,12 +203,17 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (epi == TC_EPI_BIAS_RELU) {
+          if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i] + __ldg(bias + c0 + i), 0.f);
-          } else if (epi == TC_EPI_BIAS) {
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = __ldg(b4 + i);
+              f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+            }
+            if (epi == TC_EPI_BIAS_RELU) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += __ldg(bias + c0 + i);
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
           } else if (epi == TC_EPI_MASK) {
             const uint4 m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
             const uint4 m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
@@ -196,7 +245,7 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
@@ -207,8 +256,8 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(buf * BN);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+          const int s = it % stages;
+          mbar_wait(&full[s], (it / stages) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(a_base + s * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(b_base + s * b_stage_bytes);
@@ -228,8 +277,8 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int group = tile / tiles_per_group;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          const int s = it % stages;
+          mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
           tma_load_2d(smem_u32(b_base + s * b_stage_bytes), &wmap, &full[s], kb * BK, group * g.b_rows_per_group);
         }
@@ -238,111 +287,134 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (warp == 12) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
 // weight-gradient kernel
 //   grid.x = mtile * n_chunks + nchunk ; grid.y = split ; grid.z = group
 // ------------------------------------------------------------------------------------------------
+template <int PIECE>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
-                int ones_col, int tmem_cols) {
+                int ones_col, int tmem_cols, int stages, int gsub, int nsub_max) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mtile = blockIdx.x / n_chunks, nchunk = blockIdx.x - mtile * n_chunks;
   const int split = blockIdx.y, group = blockIdx.z, groups = gridDim.z;
   int nsub = (g.Kpad - nchunk * 256) / 64;
   if (nsub > 4) nsub = 4;
-  constexpr int SUB = 64 * 128;                     // one 64-pixel x 128-byte sub-tile
-  const int stage_bytes = (2 + 4) * SUB;            // G: 2 sub-tiles, im2col: up to 4
+  // stage = [2 G sub-tiles][nsub_max im2col sub-tiles]; the MMA always reads both G sub-tiles (M = 128)
+  const int stage_bytes = (2 + nsub_max) * SUB;
   uint8_t* st_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+  zero_smem(st_base, stages * stage_bytes);       // pieces that are padding for this CTA are never written
+  fence_proxy_async();
+  if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  const uint32_t Mg = (uint32_t)g.imgs_per_group * (uint32_t)(g.Hm * g.Wm);
   const int kb_lo = split * kb_per_split;
   int kb_hi = kb_lo + kb_per_split;
   if (kb_hi > total_kb) kb_hi = total_kb;
   const int nkb = kb_hi - kb_lo;
 
-  if (warp < 4) {
-    const int chunk = lane & 7, rsub = lane >> 3;
-    // per-thread constants of the im2col columns it copies
-    int kv[4], kdy[4], kdx[4], kch[4];
+  if (warp < 8) {
+    // ---- G tile mapping: 16-byte chunks, 32 rows per pass
+    const int g_chunk = threadIdx.x & 7, g_rsub = threadIdx.x >> 3;
+    bool g_ok[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) g_ok[j] = j < gsub && (mtile * 128 + j * 64 + g_chunk * 8) < Cout;
+    const long long g_col = (long long)mtile * 128 + g_chunk * 8;
+    // ---- im2col mapping
+    constexpr int PPR = 64 / PIECE;
+    constexpr int ROWS_PER_PASS = PROD_THREADS / PPR;
+    constexpr int PASSES = 64 / ROWS_PER_PASS;
+    const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
+    const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
+    int kind[4], kdy[4], kdx[4], ktoff[4];      // 0 = padding (skip), 1 = gather, 2 = ones column
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = nchunk * 256 + j * 64 + chunk * 8;
-      kv[j] = (j < nsub && k < g.Ktot) ? 1 : 0;
-      if (j < nsub && k == ones_col) kv[j] = 2;
-      const int tap = kv[j] == 1 ? k / g.Cs : 0;
-      kch[j] = k - tap * g.Cs;
-      kdy[j] = g.dy[tap]; kdx[j] = g.dx[tap];
+      const int k = nchunk * 256 + j * 64 + piece * PIECE;
+      kind[j] = 0; kdy[j] = 0; kdx[j] = 0; ktoff[j] = 0;
+      if (j < nsub) {
+        if (k < g.Ktot) {
+          int tap, ch;
+          split_k(g, k, tap, ch);
+          kind[j] = 1; kdy[j] = g.dy[tap]; kdx[j] = g.dx[tap];
+          ktoff[j] = (g.dy[tap] * g.Ws + g.dx[tap]) * g.Cs + ch;
+        } else if (k == ones_col) {
+          kind[j] = 2;
+        }
+      }
     }
     const long long grow = (long long)group * Mg;
     for (int it = 0; it < nkb; ++it) {
-      const int s = it % STAGES;
-      mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+      const int s = it % stages;
+      mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
       const uint32_t sb = smem_u32(st_base + s * stage_bytes);
+      const uint32_t mb = (uint32_t)(kb_lo + it) * 64;
+      // G tile: rows = pixels, up to 128 output channels of this M tile
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp * 16 + i * 4 + rsub;
-        const long long m = (long long)(kb_lo + it) * 64 + r;
-        const RowDec rd = decode_row_tc(g, group, m, Mg);
+      for (int i = 0; i < 2; ++i) {
+        const int r = i * 32 + g_rsub;
+        const uint32_t m = mb + r;
         const bool rvalid = m < Mg;
-        const uint32_t roff = r * 128 + ((chunk ^ (r & 7)) << 4);
-        // G tile: rows = pixels, 128 output channels of this M tile
+        const uint32_t roff = r * 128 + ((g_chunk ^ (r & 7)) << 4);
+        const __nv_bfloat16* gp = G + ((grow + m) * Cout + g_col);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = mtile * 128 + j * 64 + chunk * 8;
-          const bool ok = rvalid && c < Cout;
-          const __nv_bfloat16* p = ok ? G + ((grow + m) * Cout + c) : G;
-          cp_async16(sb + j * SUB + roff, p, ok ? 16u : 0u);
+        for (int j = 0; j < 2; ++j)
+          if (g_ok[j]) cp_async16(sb + j * SUB + roff, rvalid ? (const void*)(gp + j * 64) : (const void*)G, rvalid ? 16u : 0u);
+      }
+      // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) {
+        const int r = i * ROWS_PER_PASS + rsub;
+        const uint32_t m = mb + r;
+        const bool rvalid = m < Mg;
+        int ys = 1 << 20, xs = 0;          // out-of-range row: every tap fails the bounds test
+        const __nv_bfloat16* rp = src;
+        if (rvalid) {
+          int img, y, x;
+          decode_pixel(g, m, img, y, x);
+          ys = y * g.sy; xs = x * g.sx;
+          rp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + ys) * g.Ws + xs) * g.Cs;
         }
-        // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
+        const uint32_t roff = r * 128 + ((((pbyte >> 4) ^ (uint32_t)(r & 7))) << 4) + (pbyte & 15u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j >= nsub) break;
+          if (kind[j] == 0) continue;
           const uint32_t d = sb + (2 + j) * SUB + roff;
-          if (kv[j] == 2) {
-            // bias-gradient column: 1.0 in the first padding column of valid pixels
-            const uint32_t one = rvalid ? 0x00003f80u : 0u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+          if (kind[j] == 1) {
+            const bool ok = (unsigned)(ys + kdy[j]) < (unsigned)g.Hs && (unsigned)(xs + kdx[j]) < (unsigned)g.Ws;
+            cp_piece<PIECE>(d, ok ? (const void*)(rp + ktoff[j]) : (const void*)src, ok);
           } else {
-            const int iy = rd.ys + kdy[j], ix = rd.xs + kdx[j];
-            const bool ok = kv[j] == 1 && (unsigned)iy < (unsigned)g.Hs && (unsigned)ix < (unsigned)g.Ws;
-            const __nv_bfloat16* p = ok ? src + ((long long)(rd.pix + iy * g.Ws + ix) * g.Cs + kch[j]) : src;
-            cp_async16(d, p, ok ? 16u : 0u);
+            // bias-gradient column: 1.0 (bf16 0x3f80) in the first padding column of valid pixels
+            const uint32_t one = rvalid ? 0x00003f80u : 0u;
+            if (PIECE == 8) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+            else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+            fence_proxy_async();     // generic-proxy store -> visible to the tensor core's async-proxy reads
           }
         }
       }
-      cp_async_commit();
-      if (it >= LOOKAHEAD) {
-        cp_async_wait<LOOKAHEAD>();
-        fence_proxy_async();
-        mbar_arrive(&full[(it - LOOKAHEAD) % STAGES]);
-      }
+      cp_async_mbar_arrive_noinc(&full[s]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = nkb >= LOOKAHEAD ? nkb - LOOKAHEAD : 0; j < nkb; ++j) mbar_arrive(&full[j % STAGES]);
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int co = mtile * 128 + row;
@@ -365,8 +437,8 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(128, nsub * 64, 1, 1);
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full[s], (it / STAGES) & 1);
+        const int s = it % stages;
+        mbar_wait(&full[s], (it / stages) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(st_base + s * stage_bytes);
         const uint32_t b_addr = a_addr + 2 * SUB;
@@ -381,7 +453,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (warp == 12) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // dW[g][(tap*Cw + ch)][co] = sum_splits partial[s][g][co][tap*Cs + ch] ; bias from the ones column
@@ -414,18 +486,38 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
-// column sums of a bf16 [rows][C] matrix per group (bias gradient when no padding column exists);
-// stage 1: grid (chunks, groups) -> part[g][chunk][C]; stage 2 reduces chunks in order.
-__global__ void colsum_bf16_stage1(const __nv_bfloat16* __restrict__ G, float* __restrict__ part, long long rows_per_group,
-                                   int C, int chunks) {
+// column sums of a bf16 [rows][C] matrix per group (bias gradient when no padding column exists).
+// stage 1: grid (chunks, groups), 16-byte loads, fixed-order in-block reduction -> part[g][chunk][C];
+// stage 2 adds the chunks in order.  C % 8 == 0, C <= 256.
+__global__ void __launch_bounds__(256) colsum_bf16_stage1(const __nv_bfloat16* __restrict__ G, float* __restrict__ part,
+                                                          long long rows_per_group, int C, int chunks) {
+  __shared__ float red[8][264];
   const int grp = blockIdx.y, chunk = blockIdx.x;
+  const int cg = C >> 3;                       // 16-byte column groups
+  int rp = 256 / cg; if (rp > 8) rp = 8;       // rows handled in parallel
+  const int rl = threadIdx.x / cg, c8 = threadIdx.x - rl * cg;
   const long long per = (rows_per_group + chunks - 1) / chunks;
-  const long long lo = chunk * per;
+  const long long lo = (long long)chunk * per;
   long long hi = lo + per; if (hi > rows_per_group) hi = rows_per_group;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rl < rp) {
+    const __nv_bfloat16* base = G + ((long long)grp * rows_per_group) * C + c8 * 8;
+    for (long long r = lo + rl; r < hi; r += rp) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[2 * i] += __uint_as_float(w[i] << 16);
+        a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][c8 * 8 + i] = a[i];
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
-    const __nv_bfloat16* p = G + ((long long)grp * rows_per_group) * C + c;
-    for (long long r = lo; r < hi; ++r) s += __bfloat162float(p[r * C]);
+    for (int r = 0; r < rp; ++r) s += red[r][c];
     part[((long long)grp * chunks + chunk) * C + c] = s;
   }
 }
@@ -479,6 +571,23 @@ int num_sms() {
   }
   return g_num_sms;
 }
+
+int ilog2_exact(int v) {
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+void finish_geom(TcGeom* g) {
+  const int ws = ilog2_exact(g->Wm), hs = ilog2_exact(g->Hm);
+  g->w_shift = ws;
+  g->hw_shift = (ws >= 0 && hs >= 0) ? ws + hs : -1;
+  if (g->hw_shift < 0) g->w_shift = -1;
+  g->cs_shift = ilog2_exact(g->Cs);
+}
+
+constexpr size_t SMEM_BUDGET = 227 * 1024;
 
 }  // namespace
 
@@ -534,6 +643,7 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   g.Ktot = 9 * Cs; g.Kpad = (g.Ktot + 63) / 64 * 64;
   g.Nn = Cout; g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
+  finish_geom(&g);
   return g;
 }
 
@@ -566,6 +676,7 @@ bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, 
   g.Ktot = nt * Cout; g.Kpad = (g.Ktot + 63) / 64 * 64;
   g.Nn = Cin; g.Hd = H; g.Wd = W; g.dsy = stride; g.dsx = stride; g.dy0 = py; g.dx0 = px;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cin; g.bias_group_stride = 0;
+  finish_geom(&g);
   *out = g;
   return true;
 }
@@ -576,39 +687,53 @@ static int next_pow2_cols(int c) {
   return p;
 }
 
+static int check_geom(const TcGeom& g, const char* who) {
+  if ((g.Cs % 8) && g.Cs != 4) { geeco_set_error("%s: Cs=%d must be 4 or a multiple of 8", who, g.Cs); return GEECO_ERR_INVALID; }
+  if (g.Kpad % 64) { geeco_set_error("%s: Kpad=%d must be a multiple of 64", who, g.Kpad); return GEECO_ERR_INVALID; }
+  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  if (Mg >= (1ll << 31) || (long long)g.imgs_per_group * g.groups * g.Hs * g.Ws >= (1ll << 31)) {
+    geeco_set_error("%s: tensor has too many pixels for 32-bit indexing", who);
+    return GEECO_ERR_INVALID;
+  }
+  return GEECO_OK;
+}
+
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
                  cudaStream_t st) {
-  if (g.Nn % 16 || g.Nn < 16 || g.Nn > 256 || g.Cs % 8 || g.Kpad % 64) {
-    geeco_set_error("tc_nn: unsupported shape N=%d Cs=%d Kpad=%d", g.Nn, g.Cs, g.Kpad);
-    return GEECO_ERR_INVALID;
-  }
+  if (g.Nn % 16 || g.Nn < 16 || g.Nn > 256) { geeco_set_error("tc_nn: unsupported N=%d", g.Nn); return GEECO_ERR_INVALID; }
+  int rc = check_geom(g, "tc_nn");
+  if (rc) return rc;
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
-  if ((long long)g.imgs_per_group * g.groups * g.Hs * g.Ws >= (1ll << 31)) {
-    geeco_set_error("tc_nn: source tensor has too many pixels for 32-bit indexing");
-    return GEECO_ERR_INVALID;
-  }
   const int tiles_per_group = ceil_div(Mg, BM);
   const int total_tiles = tiles_per_group * g.groups;
-  const size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + g.Nn * BK * 2) + 256;
+  const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;
   const int tmem_cols = next_pow2_cols(2 * g.Nn);
-  int per_sm = (int)(227 * 1024 / smem);
-  if (per_sm > 2) per_sm = 2;
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm * tmem_cols > 512) per_sm = 1;
+  // small-N layers are latency/bandwidth-bound: two CTAs per SM with 4 stages; wide layers: one CTA, deeper ring
+  int per_sm = (tmem_cols <= 256 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - 512) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 3) { geeco_set_error("tc_nn: stage of %d bytes does not fit 3 times", stage_bytes); return GEECO_ERR_INVALID; }
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
   int ctas = num_sms() * per_sm;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > total_tiles) ctas = total_tiles;
-  CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_nn_kernel<<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group, total_tiles,
-                                               tmem_cols);
+  if (g.Cs == 4) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
+                                                    total_tiles, tmem_cols, stages);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
+                                                    total_tiles, tmem_cols, stages);
+  }
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
 
-struct WgradPlan { int m_tiles, n_chunks, splits, kb_per_split, total_kb, Mrows_pad, ones_col; };
+struct WgradPlan { int m_tiles, n_chunks, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, nsub_max, stages, per_sm; };
 
 static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   WgradPlan p;
@@ -616,8 +741,14 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   p.m_tiles = (Cout + 127) / 128;
   p.n_chunks = (g.Kpad + 255) / 256;
   p.total_kb = (int)((Mg + 63) / 64);
+  p.gsub = Cout > 64 ? 2 : 1;
+  p.nsub_max = g.Kpad >= 256 ? 4 : g.Kpad / 64;
+  const int stage_bytes = (2 + p.nsub_max) * SUB;
+  p.per_sm = (2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  p.stages = (int)((SMEM_BUDGET / p.per_sm - 1024 - 512) / stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int base = p.m_tiles * p.n_chunks * g.groups;
-  int want = (num_sms() + base - 1) / base;
+  int want = (num_sms() * p.per_sm + base - 1) / base;
   if (want < 1) want = 1;
   if (want > p.total_kb) want = p.total_kb;
   p.kb_per_split = (p.total_kb + want - 1) / want;
@@ -630,17 +761,16 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
 long long tc_wgrad_partial_floats(const TcGeom& g, int Cout) {
   WgradPlan p = wgrad_plan(g, Cout);
   long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
-  long long colsum_part = (long long)g.groups * 64 * Cout;
+  long long colsum_part = (long long)g.groups * 296 * Cout;
   return main_part + colsum_part + 64;
 }
 
 int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
                     float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
                     long long dbias_group_stride, cudaStream_t st) {
-  if (g.Cs % 8 || Cout % 8 || g.Kpad % 64) {
-    geeco_set_error("tc_wgrad: unsupported shape Cs=%d Cout=%d Kpad=%d", g.Cs, Cout, g.Kpad);
-    return GEECO_ERR_INVALID;
-  }
+  if (Cout % 8 || Cout > 256 * 8) { geeco_set_error("tc_wgrad: unsupported Cout=%d", Cout); return GEECO_ERR_INVALID; }
+  int rc = check_geom(g, "tc_wgrad");
+  if (rc) return rc;
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
   WgradPlan p = wgrad_plan(g, Cout);
@@ -649,19 +779,28 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
     geeco_set_error("tc_wgrad: partial buffer too small (%lld floats needed, %lld given)", tc_wgrad_partial_floats(g, Cout), partial_cap);
     return GEECO_ERR_WORKSPACE;
   }
-  const size_t smem = 1024 + (size_t)STAGES * 6 * 64 * 128 + 256;
-  CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.stages < 3) { geeco_set_error("tc_wgrad: stage does not fit 3 times"); return GEECO_ERR_INVALID; }
+  const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_max) * SUB + 512;
+  const int ones = dbias ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
-  tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
-                                                  p.Mrows_pad, dbias ? p.ones_col : -1, 256);
+  if (g.Cs == 4) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<4><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
+                                                       p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgrad_kernel<8><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
+                                                       p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);
+  }
   const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
   int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
   wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
-                                          g.Ktot, dbias ? p.ones_col : -1, dw_group_stride, dbias_group_stride);
+                                          g.Ktot, ones, dw_group_stride, dbias_group_stride);
   geeco_count_launch(2);
   if (dbias && p.ones_col < 0) {
+    if (Cout > 256) { geeco_set_error("tc_wgrad: bias gradient needs Cout <= 256"); return GEECO_ERR_INVALID; }
     float* part = partial + main_part;
-    const int chunks = Mg >= 64 * 8 ? 64 : 1;
+    int chunks = (int)(Mg / 256); if (chunks > 296 / g.groups) chunks = 296 / g.groups; if (chunks < 1) chunks = 1;
     colsum_bf16_stage1<<<dim3(chunks, g.groups), 256, 0, st>>>(G, part, Mg, Cout, chunks);
     colsum_stage2<<<g.groups, 256, 0, st>>>(part, dbias, Cout, chunks, dbias_group_stride);
     geeco_count_launch(2);

@@ -5,7 +5,8 @@
 
 // Geometry of one tensor-core gather GEMM (bf16 NHWC source, implicit im2col).
 struct TcGeom {
-  int Hs, Ws, Cs;             // source tensor [imgs, Hs, Ws, Cs] (bf16), Cs % 8 == 0
+  int hw_shift, w_shift, cs_shift;   // log2(Hm*Wm), log2(Wm), log2(Cs) when powers of two, else -1
+  int Hs, Ws, Cs;             // source tensor [imgs, Hs, Ws, Cs] (bf16), Cs == 4 or Cs % 8 == 0
   int Hm, Wm;                 // GEMM-row pixel grid per image
   int sy, sx;
   int ntaps;

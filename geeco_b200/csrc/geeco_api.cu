@@ -183,6 +183,11 @@ static int validate(const geeco_config* cfg) {
   if (cfg->num_grp_states < 1 || cfg->num_grp_states > 6) { geeco_set_error("num_grp_states %d outside [1,6]", cfg->num_grp_states); return GEECO_ERR_INVALID; }
   if (cfg->dim_jnt_state < 1) { geeco_set_error("dim_jnt_state must be positive"); return GEECO_ERR_INVALID; }
   if (cfg->precision != GEECO_FP32 && cfg->precision != GEECO_BF16) { geeco_set_error("unknown precision %d", cfg->precision); return GEECO_ERR_INVALID; }
+  if (cfg->precision == GEECO_BF16 && (cfg->dim_s_obs % 16 || cfg->dim_s_dyn % 16 || cfg->dim_s_diff % 16 ||
+                                        cfg->dim_s_obs > 256 || cfg->dim_s_dyn > 256 || cfg->dim_s_diff > 256)) {
+    geeco_set_error("bf16 mode: dim_s_obs/dim_s_dyn/dim_s_diff must be multiples of 16 and <= 256");
+    return GEECO_ERR_INVALID;
+  }
   return GEECO_OK;
 }
 
@@ -193,7 +198,7 @@ static int plan(geeco_ctx* c, char* ws_base) {
   c->params.clear();
   c->arena_floats = 0;
   const bool bf16 = cfg.precision == GEECO_BF16;
-  c->CP = bf16 ? 8 : 4;
+  c->CP = 4;   // network input is channel-padded 3 -> 4 (fp32: 16 B / pixel, bf16: 8 B / pixel)
   // ---- layer geometry
   const int dims8[3] = {cfg.dim_s_obs, cfg.dim_s_dyn, cfg.dim_s_diff};
   c->uniform8 = (dims8[0] == dims8[1] && dims8[1] == dims8[2]);
@@ -267,6 +272,7 @@ static int plan(geeco_ctx* c, char* ws_base) {
   c->dheads = (float*)cv.take(sizeof(float) * N * c->NH);
   c->losses = (float*)cv.take(sizeof(float) * 8);
   c->sc = (float*)cv.take(sizeof(float) * 8);
+  c->gates_partial = (float*)cv.take(sizeof(float) * lstm_gates_partial_floats(N, xdim + Hl, 4 * Hl));
   // fp32 staging of the first / last conv maps for the tail (bf16 mode converts conv8 output)
   c->y8_f32 = bf16 ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
   c->g8_f32 = (bf16 && cfg.training) ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
@@ -540,8 +546,9 @@ static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
   int rc = launch_build_state(d, y8 + L8.act_off[0], y8 + L8.act_off[1], y8 + L8.act_off[2], b->jnt_state,
                               carry ? c->m_carry : nullptr, c->state, st);
   if (rc) return rc;
-  GatherGeom g = dense_geom(N, c->xdim + Hl, 4 * Hl, 4 * Hl, 0);
-  rc = launch_gemm_nn_f32(g, c->state, P(c, c->p_lstm_w), P(c, c->p_lstm_b), nullptr, c->gates, 1, EPI_BIAS, st);
+  // in the reference-faithful mode m_prev == 0, so the h-rows of the kernel contribute nothing: K = xdim
+  rc = launch_lstm_gates(c->state, c->xdim + Hl, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, N,
+                         carry ? c->xdim + Hl : c->xdim, 4 * Hl, st);
   if (rc) return rc;
   rc = launch_lstm_cell(N, Hl, c->gates, carry ? c->c_carry : nullptr, c->c_cur, c->m_cur, c->state_out, st);
   if (rc) return rc;

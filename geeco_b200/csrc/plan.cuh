@@ -35,7 +35,7 @@ struct geeco_ctx {
   float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
   void* x0 = nullptr;
   float *state, *gates, *c_cur, *m_cur, *state_out, *c_carry, *m_carry, *fc1, *heads, *loss_parts, *dheads, *losses, *sc;
-  float *y8_f32 = nullptr, *g8_f32 = nullptr;
+  float *y8_f32 = nullptr, *g8_f32 = nullptr, *gates_partial = nullptr;
   float *dfc1 = nullptr, *dgates = nullptr, *dstate = nullptr, *partial = nullptr;
   long long partial_cap = 0;
   // bf16 extras

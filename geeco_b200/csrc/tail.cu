@@ -366,3 +366,79 @@ int launch_l2_term(const float* theta, long long n, float l2, float* sc, cudaStr
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// LSTM gate GEMM  gates[N, 4h] = [x, m_prev][N, K] @ kernel[K, 4h] + bias   (graph.py:224)
+// M = batch is tiny, K = 3228 is long: split K across CTAs (each streams 32 kernel rows once),
+// fixed-order reduction of the partials adds the bias.  fp32 CUDA cores; 0.2 GFLOP.
+// ---------------------------------------------------------------------------------------
+constexpr int GK_SLICE = 32;
+template <int CPT>
+__global__ void __launch_bounds__(256) gates_splitk_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                           float* __restrict__ partial, int N, int K, int ldx,
+                                                           int Ncols) {
+  __shared__ float xs[32][GK_SLICE + 1];
+  const int k0 = blockIdx.x * GK_SLICE, n0 = blockIdx.y * 32;
+  for (int e = threadIdx.x; e < 32 * GK_SLICE; e += 256) {
+    const int n = e / GK_SLICE, k = e - n * GK_SLICE;
+    xs[n][k] = (n0 + n < N && k0 + k < K) ? x[(long long)(n0 + n) * ldx + k0 + k] : 0.f;
+  }
+  __syncthreads();
+  float acc[32][CPT];
+#pragma unroll
+  for (int n = 0; n < 32; ++n)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[n][c] = 0.f;
+  const int kend = (K - k0) < GK_SLICE ? (K - k0) : GK_SLICE;
+  for (int kk = 0; kk < kend; ++kk) {
+    float w[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = threadIdx.x + c * 256;
+      w[c] = col < Ncols ? __ldg(W + (long long)(k0 + kk) * Ncols + col) : 0.f;
+    }
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float a = xs[n][kk];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) acc[n][c] = fmaf(a, w[c], acc[n][c]);
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {
+    if (n0 + n >= N) break;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = threadIdx.x + c * 256;
+      if (col < Ncols) partial[((long long)blockIdx.x * N + n0 + n) * Ncols + col] = acc[n][c];
+    }
+  }
+}
+__global__ void gates_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
+                                    float* __restrict__ gates, int slices, int N, int Ncols) {
+  const long long total = (long long)N * Ncols;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float s = bias ? bias[i % Ncols] : 0.f;
+  for (int k = 0; k < slices; ++k) s += partial[(long long)k * total + i];
+  gates[i] = s;
+}
+
+long long lstm_gates_partial_floats(int N, int K, int Ncols) {
+  return (long long)((K + GK_SLICE - 1) / GK_SLICE) * N * Ncols;
+}
+int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias, float* gates, float* partial, int N,
+                      int K, int Ncols, cudaStream_t st) {
+  if (Ncols > 1024) { geeco_set_error("lstm gates: 4*dim_h_lstm = %d > 1024 not supported", Ncols); return GEECO_ERR_INVALID; }
+  const int slices = (K + GK_SLICE - 1) / GK_SLICE;
+  dim3 grid(slices, (N + 31) / 32);
+  const int cpt = (Ncols + 255) / 256;
+  if (cpt == 1) gates_splitk_kernel<1><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
+  else if (cpt == 2) gates_splitk_kernel<2><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
+  else if (cpt == 3) gates_splitk_kernel<3><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
+  else gates_splitk_kernel<4><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
+  gates_reduce_kernel<<<ceil_div((long long)N * Ncols, 256), 256, 0, st>>>(partial, bias, gates, slices, N, Ncols);
+  geeco_count_launch(2);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}

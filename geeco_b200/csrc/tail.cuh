@@ -29,3 +29,6 @@ int launch_tail_bwd(const TailDims& d, const TailParams& p, const TailGrads& g, 
 int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, float* sc, double lr, double b1,
                 double b2, double eps, float gscale, float l2, cudaStream_t st);
 int launch_l2_term(const float* theta, long long n, float l2, float* sc, cudaStream_t st);
+long long lstm_gates_partial_floats(int N, int K, int Ncols);
+int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias, float* gates, float* partial, int N,
+                      int K, int Ncols, cudaStream_t st);

