@@ -135,6 +135,35 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
     const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
     uint32_t it = 0;
+    if (PIECE == 4 && g.rowwin) {
+      // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
+      // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int group = tile / tiles_per_group;
+        const uint32_t m0 = (uint32_t)(tile - group * tiles_per_group) * BM;
+        int img, y, x0;
+        decode_pixel(g, m0, img, y, x0);
+        const int s = it % stages;
+        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
+        const __nv_bfloat16* imgbase = src + (long long)((group * g.imgs_per_group + img) * g.Hs) * g.Ws * 4;
+        for (int p = threadIdx.x; p < 3 * BM; p += PROD_THREADS) {
+          const int row = p & (BM - 1), ky = p >> 7;
+          const int iy = y + g.dy[ky * 3];
+          const int xl = x0 + row + g.dx[0];
+          const bool rowok = (m0 + row) < Mg && (unsigned)iy < (unsigned)g.Hs;
+          const __nv_bfloat16* sp = imgbase + ((long long)iy * g.Ws + xl) * 4;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const bool ok = rowok && (unsigned)(xl + kx) < (unsigned)g.Ws;
+            const uint32_t byte = (uint32_t)(ky * 24 + kx * 8);
+            const uint32_t d = a_s + row * 128 + (((byte >> 4) ^ (uint32_t)(row & 7)) << 4) + (byte & 15u);
+            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
+          }
+        }
+        cp_async_mbar_arrive_noinc(&full[s]);
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int group = tile / tiles_per_group;
       const uint32_t m0 = (uint32_t)(tile - group * tiles_per_group) * BM;
@@ -381,6 +410,33 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
         for (int j = 0; j < 2; ++j)
           if (g_ok[j]) cp_async16(sb + j * SUB + roff, rvalid ? (const void*)(gp + j * 64) : (const void*)G, rvalid ? 16u : 0u);
       }
+      if (PIECE == 4 && g.rowwin) {
+        // conv1 fast path: 64 consecutive pixels of one image row; threads 0..191 copy one (row, ky) window
+        // of 24 contiguous bytes, threads 192..255 write the bias-gradient ones column (k = 36)
+        int img, y, x0;
+        decode_pixel(g, mb, img, y, x0);
+        const int p = threadIdx.x;
+        if (p < 192) {
+          const int row = p & 63, ky = p >> 6;
+          const int iy = y + g.dy[ky * 3];
+          const int xl = x0 + row + g.dx[0];
+          const bool rowok = (mb + row) < Mg && (unsigned)iy < (unsigned)g.Hs;
+          const __nv_bfloat16* sp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + iy) * g.Ws + xl) * 4;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const bool ok = rowok && (unsigned)(xl + kx) < (unsigned)g.Ws;
+            const uint32_t byte = (uint32_t)(ky * 24 + kx * 8);
+            const uint32_t d = sb + 2 * SUB + row * 128 + (((byte >> 4) ^ (uint32_t)(row & 7)) << 4) + (byte & 15u);
+            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
+          }
+        } else if (ones_col == 36) {
+          const int row = p - 192;
+          const uint32_t one = (mb + row) < Mg ? 0x00003f80u : 0u;
+          const uint32_t d = sb + 2 * SUB + row * 128 + (((72u >> 4) ^ (uint32_t)(row & 7)) << 4) + (72u & 15u);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+          fence_proxy_async();
+        }
+      } else
       // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
 #pragma unroll
       for (int i = 0; i < PASSES; ++i) {
@@ -587,7 +643,9 @@ void finish_geom(TcGeom* g) {
   g->cs_shift = ilog2_exact(g->Cs);
 }
 
-constexpr size_t SMEM_BUDGET = 227 * 1024;
+// dynamic shared memory per SM we plan with: 227 KB is the per-CTA maximum; two co-resident CTAs each
+// also pay 1 KB of system-reserved shared memory out of the 228 KB, so plan with 222 KB in total
+constexpr size_t SMEM_BUDGET = 222 * 1024;
 
 }  // namespace
 
@@ -644,6 +702,7 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   g.Nn = Cout; g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
+  g.rowwin = (Cs == 4 && stride == 1 && Wo % 128 == 0 && g.hw_shift >= 0) ? 1 : 0;
   return g;
 }
 
@@ -720,10 +779,12 @@ int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* 
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > total_tiles) ctas = total_tiles;
   if (g.Cs == 4) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
                                                     total_tiles, tmem_cols, stages);
   } else {
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
                                                     total_tiles, tmem_cols, stages);
@@ -784,10 +845,12 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
   const int ones = dbias ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
   if (g.Cs == 4) {
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<4><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
                                                        p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);
   } else {
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<8><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
                                                        p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);

@@ -5,6 +5,7 @@
 
 // Geometry of one tensor-core gather GEMM (bf16 NHWC source, implicit im2col).
 struct TcGeom {
+  int rowwin;                 // 1: 4-channel stride-1 3x3 forward geometry with Wm % 128 == 0 (conv1 fast producers)
   int hw_shift, w_shift, cs_shift;   // log2(Hm*Wm), log2(Wm), log2(Cs) when powers of two, else -1
   int Hs, Ws, Cs;             // source tensor [imgs, Hs, Ws, Cs] (bf16), Cs == 4 or Cs % 8 == 0
   int Hm, Wm;                 // GEMM-row pixel grid per image
