@@ -1,0 +1,1 @@
+from geeco_b200.predictor import GoalE2EVMCPredictor, BatchedGoalPredictor, TOL_FRAME_RANGE  # noqa: F401

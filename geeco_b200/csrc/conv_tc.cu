@@ -36,7 +36,8 @@ constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int PROD_THREADS = 256;
 constexpr int NN_THREADS = PROD_THREADS + 128 + 64;   // 448
-constexpr int WG_THREADS = PROD_THREADS + 128 + 32;   // 416
+constexpr int WG_PROD_THREADS = 512;
+constexpr int WG_THREADS = WG_PROD_THREADS + 128 + 32;   // 672
 constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
 constexpr int SUB = 64 * 128;                         // one 64-row x 128-byte sub-tile
 
@@ -327,15 +328,16 @@ template <int PIECE>
 __global__ void __launch_bounds__(WG_THREADS, 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
-                int ones_col, int tmem_cols, int stages, int gsub, int nsub_max) {
+                int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mtile = blockIdx.x / n_chunks, nchunk = blockIdx.x - mtile * n_chunks;
   const int split = blockIdx.y, group = blockIdx.z, groups = gridDim.z;
-  int nsub = (g.Kpad - nchunk * 256) / 64;
-  if (nsub > 4) nsub = 4;
-  // stage = [2 G sub-tiles][nsub_max im2col sub-tiles]; the MMA always reads both G sub-tiles (M = 128)
-  const int stage_bytes = (2 + nsub_max) * SUB;
+  const int col0 = nchunk * nsub_chunk * 64;          // first reduction-index column of this CTA
+  int nsub = (g.Kpad - col0) / 64;
+  if (nsub > nsub_chunk) nsub = nsub_chunk;
+  // stage = [2 G sub-tiles][nsub_chunk im2col sub-tiles]; the MMA always reads both G sub-tiles (M = 128)
+  const int stage_bytes = (2 + nsub_chunk) * SUB;
   uint8_t* st_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
   uint64_t* full = bars;
@@ -344,14 +346,15 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int EPI_WARP0 = WG_PROD_THREADS / 32, MMA_WARP = EPI_WARP0 + 4;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], WG_PROD_THREADS); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
   zero_smem(st_base, stages * stage_bytes);       // pieces that are padding for this CTA are never written
   fence_proxy_async();
-  if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+  if (warp == MMA_WARP) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -363,23 +366,23 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   if (kb_hi > total_kb) kb_hi = total_kb;
   const int nkb = kb_hi - kb_lo;
 
-  if (warp < 8) {
-    // ---- G tile mapping: 16-byte chunks, 32 rows per pass
-    const int g_chunk = threadIdx.x & 7, g_rsub = threadIdx.x >> 3;
+  if (warp < EPI_WARP0) {
+    // ---- G tile mapping: 16-byte chunks, 64 rows in one pass
+    const int g_chunk = threadIdx.x & 7, g_row = threadIdx.x >> 3;
     bool g_ok[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) g_ok[j] = j < gsub && (mtile * 128 + j * 64 + g_chunk * 8) < Cout;
     const long long g_col = (long long)mtile * 128 + g_chunk * 8;
     // ---- im2col mapping
     constexpr int PPR = 64 / PIECE;
-    constexpr int ROWS_PER_PASS = PROD_THREADS / PPR;
+    constexpr int ROWS_PER_PASS = WG_PROD_THREADS / PPR;
     constexpr int PASSES = 64 / ROWS_PER_PASS;
     const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
-    int kind[4], kdy[4], kdx[4], ktoff[4];      // 0 = padding (skip), 1 = gather, 2 = ones column
+    int kind[8], kdy[8], kdx[8], ktoff[8];      // 0 = padding (skip), 1 = gather, 2 = ones column
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = nchunk * 256 + j * 64 + piece * PIECE;
+    for (int j = 0; j < 8; ++j) {
+      const int k = col0 + j * 64 + piece * PIECE;
       kind[j] = 0; kdy[j] = 0; kdx[j] = 0; ktoff[j] = 0;
       if (j < nsub) {
         if (k < g.Ktot) {
@@ -399,12 +402,10 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
       const uint32_t sb = smem_u32(st_base + s * stage_bytes);
       const uint32_t mb = (uint32_t)(kb_lo + it) * 64;
       // G tile: rows = pixels, up to 128 output channels of this M tile
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = i * 32 + g_rsub;
-        const uint32_t m = mb + r;
+      {
+        const uint32_t m = mb + g_row;
         const bool rvalid = m < Mg;
-        const uint32_t roff = r * 128 + ((g_chunk ^ (r & 7)) << 4);
+        const uint32_t roff = g_row * 128 + ((g_chunk ^ (g_row & 7)) << 4);
         const __nv_bfloat16* gp = G + ((grow + m) * Cout + g_col);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
@@ -429,54 +430,55 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
             const uint32_t d = sb + 2 * SUB + row * 128 + (((byte >> 4) ^ (uint32_t)(row & 7)) << 4) + (byte & 15u);
             cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
           }
-        } else if (ones_col == 36) {
+        } else if (p < 256 && ones_col == 36) {
           const int row = p - 192;
           const uint32_t one = (mb + row) < Mg ? 0x00003f80u : 0u;
           const uint32_t d = sb + 2 * SUB + row * 128 + (((72u >> 4) ^ (uint32_t)(row & 7)) << 4) + (72u & 15u);
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
           fence_proxy_async();
         }
-      } else
-      // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
+      } else {
+        // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
 #pragma unroll
-      for (int i = 0; i < PASSES; ++i) {
-        const int r = i * ROWS_PER_PASS + rsub;
-        const uint32_t m = mb + r;
-        const bool rvalid = m < Mg;
-        int ys = 1 << 20, xs = 0;          // out-of-range row: every tap fails the bounds test
-        const __nv_bfloat16* rp = src;
-        if (rvalid) {
-          int img, y, x;
-          decode_pixel(g, m, img, y, x);
-          ys = y * g.sy; xs = x * g.sx;
-          rp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + ys) * g.Ws + xs) * g.Cs;
-        }
-        const uint32_t roff = r * 128 + ((((pbyte >> 4) ^ (uint32_t)(r & 7))) << 4) + (pbyte & 15u);
+        for (int i = 0; i < PASSES; ++i) {
+          const int r = i * ROWS_PER_PASS + rsub;
+          const uint32_t m = mb + r;
+          const bool rvalid = m < Mg;
+          int ys = 1 << 20, xs = 0;          // out-of-range row: every tap fails the bounds test
+          const __nv_bfloat16* rp = src;
+          if (rvalid) {
+            int img, y, x;
+            decode_pixel(g, m, img, y, x);
+            ys = y * g.sy; xs = x * g.sx;
+            rp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + ys) * g.Ws + xs) * g.Cs;
+          }
+          const uint32_t roff = r * 128 + ((((pbyte >> 4) ^ (uint32_t)(r & 7))) << 4) + (pbyte & 15u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (kind[j] == 0) continue;
-          const uint32_t d = sb + (2 + j) * SUB + roff;
-          if (kind[j] == 1) {
-            const bool ok = (unsigned)(ys + kdy[j]) < (unsigned)g.Hs && (unsigned)(xs + kdx[j]) < (unsigned)g.Ws;
-            cp_piece<PIECE>(d, ok ? (const void*)(rp + ktoff[j]) : (const void*)src, ok);
-          } else {
-            // bias-gradient column: 1.0 (bf16 0x3f80) in the first padding column of valid pixels
-            const uint32_t one = rvalid ? 0x00003f80u : 0u;
-            if (PIECE == 8) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
-            else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
-            fence_proxy_async();     // generic-proxy store -> visible to the tensor core's async-proxy reads
+          for (int j = 0; j < 8; ++j) {
+            if (kind[j] == 0) continue;
+            const uint32_t d = sb + (2 + j) * SUB + roff;
+            if (kind[j] == 1) {
+              const bool ok = (unsigned)(ys + kdy[j]) < (unsigned)g.Hs && (unsigned)(xs + kdx[j]) < (unsigned)g.Ws;
+              cp_piece<PIECE>(d, ok ? (const void*)(rp + ktoff[j]) : (const void*)src, ok);
+            } else {
+              // bias-gradient column: 1.0 (bf16 0x3f80) in the first padding column of valid pixels
+              const uint32_t one = rvalid ? 0x00003f80u : 0u;
+              if (PIECE == 8) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+              else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
+              fence_proxy_async();     // generic-proxy store -> visible to the tensor core's async-proxy reads
+            }
           }
         }
       }
       cp_async_mbar_arrive_noinc(&full[s]);
     }
-  } else if (warp < 12) {
+  } else if (warp < MMA_WARP) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int co = mtile * 128 + row;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    float* P = partial + (((long long)split * groups + group) * Mrows_pad + co) * g.Kpad + nchunk * 256;
+    float* P = partial + (((long long)split * groups + group) * Mrows_pad + co) * g.Kpad + col0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int c0 = 0; c0 < nsub * 64; c0 += 16) {
       uint32_t v[16];
@@ -491,7 +493,10 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     }
   } else {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, nsub * 64, 1, 1);
+      // N <= 256 per instruction: up to two MMAs per 16-pixel step (columns [0,256) and [256, nsub*64))
+      const int n_lo = nsub > 4 ? 256 : nsub * 64, n_hi = nsub > 4 ? (nsub - 4) * 64 : 0;
+      const uint32_t idesc_lo = make_idesc_bf16(128, n_lo, 1, 1);
+      const uint32_t idesc_hi = make_idesc_bf16(128, n_hi > 0 ? n_hi : 64, 1, 1);
       for (int it = 0; it < nkb; ++it) {
         const int s = it % stages;
         mbar_wait(&full[s], (it / stages) & 1);
@@ -499,9 +504,12 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
         const uint32_t a_addr = smem_u32(st_base + s * stage_bytes);
         const uint32_t b_addr = a_addr + 2 * SUB;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)   // 4 x 16 pixels
-          tc_mma(tmem_base, make_desc_sw128(a_addr + j * 2048, SUB, 1024), make_desc_sw128(b_addr + j * 2048, SUB, 1024),
-                 idesc, (it | j) != 0 ? 1u : 0u);
+        for (int j = 0; j < 4; ++j) {   // 4 x 16 pixels
+          const uint64_t ad = make_desc_sw128(a_addr + j * 2048, SUB, 1024);
+          tc_mma(tmem_base, ad, make_desc_sw128(b_addr + j * 2048, SUB, 1024), idesc_lo, (it | j) != 0 ? 1u : 0u);
+          if (n_hi > 0)
+            tc_mma(tmem_base + 256, ad, make_desc_sw128(b_addr + 4 * SUB + j * 2048, SUB, 1024), idesc_hi, (it | j) != 0 ? 1u : 0u);
+        }
         tc_commit(&empty[s]);
       }
       tc_commit(tmem_full);
@@ -509,7 +517,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  if (warp == MMA_WARP) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // dW[g][(tap*Cw + ch)][co] = sum_splits partial[s][g][co][tap*Cs + ch] ; bias from the ones column
@@ -794,22 +802,26 @@ int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* 
   return GEECO_OK;
 }
 
-struct WgradPlan { int m_tiles, n_chunks, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, nsub_max, stages, per_sm; };
+struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols; };
 
 static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   WgradPlan p;
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   p.m_tiles = (Cout + 127) / 128;
-  p.n_chunks = (g.Kpad + 255) / 256;
+  const int total_sub = g.Kpad / 64;
+  // up to 8 sub-tiles (N = 512 TMEM columns) per CTA; the ring must hold at least 3 stages
+  int cap = 8;
+  while (cap > 1 && 3 * (2 + cap) * SUB + 1536 > (int)SMEM_BUDGET) --cap;
+  p.n_chunks = (total_sub + cap - 1) / cap;
+  p.nsub_chunk = (total_sub + p.n_chunks - 1) / p.n_chunks;
   p.total_kb = (int)((Mg + 63) / 64);
   p.gsub = Cout > 64 ? 2 : 1;
-  p.nsub_max = g.Kpad >= 256 ? 4 : g.Kpad / 64;
-  const int stage_bytes = (2 + p.nsub_max) * SUB;
-  p.per_sm = (2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
-  p.stages = (int)((SMEM_BUDGET / p.per_sm - 1024 - 512) / stage_bytes);
+  const int stage_bytes = (2 + p.nsub_chunk) * SUB;
+  p.stages = (int)((SMEM_BUDGET - 1024 - 512) / stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.tmem_cols = p.nsub_chunk > 4 ? 512 : (p.nsub_chunk > 2 ? 256 : 128);
   const int base = p.m_tiles * p.n_chunks * g.groups;
-  int want = (num_sms() * p.per_sm + base - 1) / base;
+  int want = (num_sms() + base - 1) / base;
   if (want < 1) want = 1;
   if (want > p.total_kb) want = p.total_kb;
   p.kb_per_split = (p.total_kb + want - 1) / want;
@@ -841,19 +853,19 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
     return GEECO_ERR_WORKSPACE;
   }
   if (p.stages < 3) { geeco_set_error("tc_wgrad: stage does not fit 3 times"); return GEECO_ERR_INVALID; }
-  const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_max) * SUB + 512;
+  const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_chunk) * SUB + 512;
   const int ones = dbias ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
   if (g.Cs == 4) {
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<4><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
-                                                       p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);
+                                                       p.Mrows_pad, ones, p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_wgrad_kernel<8><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
-                                                       p.Mrows_pad, ones, 256, p.stages, p.gsub, p.nsub_max);
+                                                       p.Mrows_pad, ones, p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);
   }
   const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
   int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;

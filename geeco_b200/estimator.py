@@ -1,0 +1,229 @@
+"""Training / evaluation entry with the shape of the reference's tf.estimator usage.
+
+Reference: `goal_e2evmc_model_fn(features, labels, mode, params)` (src/models/e2evmc/estimator.py:144-279)
+wrapped in `tf.estimator.Estimator(model_fn, model_dir, config, params)` and driven by
+`estimator.train(input_fn)` / `estimator.evaluate(input_fn)` (scripts/train_e2evmc.py:254-291).
+
+Here an `Estimator` owns one `Engine` (the CUDA context); `input_fn()` returns an iterable of
+`(features, labels)` dicts in the layout of `_prepare_v4` (src/data/geeco_gym.py:373-399).  The TF
+mechanics that the caller can observe are kept:
+  * `train()` restores the latest checkpoint of `model_dir`, runs ONE pass over the input, writes
+    `model.ckpt-<global_step>` files plus the `checkpoint` header, keeps `keep_checkpoint_max` of them;
+  * `evaluate()` returns {'loss' (mean of per-batch losses), 'cmd_ee','pos_ee','pos_obj' (streaming MSE),
+    'cmd_grp' (accuracy), 'global_step'} (estimator.py:246-258);
+  * checkpoints store variables under their TF names (GoalVMC/.../kernel, .../kernel/Adam, ...).
+"""
+from __future__ import annotations
+
+import collections
+import os
+import re
+
+import numpy as np
+
+from . import parallel
+from .params import E2EVMCConfig
+
+
+class ModeKeys(object):
+  TRAIN, EVAL, PREDICT = 'train', 'eval', 'infer'
+
+
+RunConfig = collections.namedtuple('RunConfig', ['save_checkpoints_steps', 'keep_checkpoint_max'])
+RunConfig.__new__.__defaults__ = (10000, 2)
+
+EstimatorSpec = collections.namedtuple('EstimatorSpec', ['mode', 'loss', 'train_op', 'eval_metric_ops', 'predictions',
+                                                         'endpoints'])
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoints (TF-named variables in .npz; the `checkpoint` header file of tf.train.Saver)
+# ------------------------------------------------------------------------------------------------
+def latest_checkpoint(model_dir):
+  """Counterpart of tf.train.latest_checkpoint: path prefix `<model_dir>/model.ckpt-<step>` or None."""
+  header = os.path.join(model_dir, 'checkpoint')
+  if not os.path.exists(header):
+    return None
+  with open(header) as fp:
+    m = re.search(r'model_checkpoint_path:\s*"([^"]+)"', fp.read())
+  if not m:
+    return None
+  prefix = os.path.join(model_dir, os.path.basename(m.group(1)))
+  return prefix if os.path.exists(prefix + '.npz') else None
+
+
+def save_checkpoint(engine, model_dir, keep_max=2):
+  step = int(engine.global_step)
+  name = 'model.ckpt-%d' % step
+  arrays = {'global_step': np.array(step, dtype=np.int64)}
+  for n in engine.param_names():
+    arrays[n] = engine.view(n).detach().cpu().numpy()
+    if engine.training:
+      arrays[n + '/Adam'] = engine.view(n, engine.adam_m).detach().cpu().numpy()
+      arrays[n + '/Adam_1'] = engine.view(n, engine.adam_v).detach().cpu().numpy()
+  arrays['beta1_power'] = np.array(0.9 ** step, dtype=np.float32)
+  arrays['beta2_power'] = np.array(0.999 ** step, dtype=np.float32)
+  # the reference saves the (never written, all-zero) lstm_memory variable as well (graph.py:219,226)
+  arrays['GoalVMC/LSTMDecoder/lstm_memory'] = np.zeros((engine.N, 2 * engine.cfg.dim_h_lstm), dtype=np.float32)
+  os.makedirs(model_dir, exist_ok=True)
+  np.savez(os.path.join(model_dir, name + '.npz'), **arrays)
+  existing = sorted((int(re.search(r'model\.ckpt-(\d+)\.npz$', f).group(1)) for f in os.listdir(model_dir)
+                     if re.search(r'model\.ckpt-(\d+)\.npz$', f)))
+  if keep_max > 0:
+    for old in existing[:-keep_max]:
+      os.remove(os.path.join(model_dir, 'model.ckpt-%d.npz' % old))
+    existing = existing[-keep_max:]
+  with open(os.path.join(model_dir, 'checkpoint'), 'w') as fp:
+    fp.write('model_checkpoint_path: "%s"\n' % name)
+    for s in existing:
+      fp.write('all_model_checkpoint_paths: "model.ckpt-%d"\n' % s)
+  return os.path.join(model_dir, name)
+
+
+def restore_checkpoint(engine, prefix):
+  """Restores every variable except lstm_memory (predictor.py:87) and, when present, the Adam slots."""
+  with np.load(prefix + '.npz') as data:
+    engine.set_params({n: data[n] for n in engine.param_names()})
+    if engine.training and all((n + '/Adam') in data for n in engine.param_names()):
+      import torch
+      for n in engine.param_names():
+        engine.view(n, engine.adam_m).copy_(torch.from_numpy(data[n + '/Adam']))
+        engine.view(n, engine.adam_v).copy_(torch.from_numpy(data[n + '/Adam_1']))
+    engine.set_global_step(int(data['global_step']))
+  return engine.global_step
+
+
+# ------------------------------------------------------------------------------------------------
+# model_fn
+# ------------------------------------------------------------------------------------------------
+_ENGINES = {}
+
+
+def _engine_for(config: E2EVMCConfig, batch, precision, training):
+  from .engine import Engine
+  key = (tuple(config), int(batch), precision, bool(training))
+  if key not in _ENGINES:
+    _ENGINES[key] = Engine(config, batch_size=batch, precision=precision, training=training)
+    _ENGINES[key].init_params(seed=0)
+  return _ENGINES[key]
+
+
+def predictions_from_endpoints(ep):
+  """estimator.py:183-189 (cartesian control)."""
+  return {'cmd_ee': ep['pred_cmd_ee'], 'logits_cmd_grp': ep['logits_cmd_grp'], 'pos_ee': ep['pred_aux_ee'],
+          'pos_obj': ep['pred_aux_obj']}
+
+
+def goal_e2evmc_model_fn(features, labels, mode, params):
+  """Eager counterpart of estimator.py:144-279.  `params`: {'e2evmc_config', 'log_steps', 'debug'} plus the
+  optional execution keys 'precision' ('bf16' | 'fp32') and 'engine' (reuse an existing Engine)."""
+  config = params['e2evmc_config']
+  if config.img_channels not in (3, 4):
+    raise ValueError("Unsupported number of channels for input frame: %d!" % config.img_channels)
+  if mode not in (ModeKeys.TRAIN, ModeKeys.EVAL, ModeKeys.PREDICT):
+    raise RuntimeError("Unknown estimator mode: %s" % (mode,))
+  batch = int(np.shape(features['rgb'])[0])
+  eng = params.get('engine') or _engine_for(config, batch, params.get('precision', 'bf16'), mode == ModeKeys.TRAIN)
+  if mode == ModeKeys.PREDICT:
+    ep = eng.forward(features, None)
+    return EstimatorSpec(mode, None, None, None, {k: v.detach().cpu().numpy() for k, v in
+                                                   predictions_from_endpoints(ep).items()}, ep)
+  if mode == ModeKeys.TRAIN:
+    losses = parallel.data_parallel_step(eng, features, labels)
+    return EstimatorSpec(mode, losses, 'adam', None, None, None)
+  ep = eng.forward(features, labels)
+  return EstimatorSpec(mode, ep['losses'], None, ep['losses'], None, ep)
+
+
+class Estimator(object):
+  """`tf.estimator.Estimator`-shaped driver of one Engine."""
+
+  def __init__(self, model_fn, model_dir, config=None, params=None, precision='bf16', batch_size=None):
+    self._model_fn = model_fn
+    self.model_dir = model_dir
+    self.config = config or RunConfig()
+    self.params = dict(params or {})
+    self.precision = precision
+    self._cfg = self.params['e2evmc_config']
+    self._batch = int(batch_size or self._cfg.batch_size)
+    self._engine = None
+    self.last_train_losses = []
+    os.makedirs(model_dir, exist_ok=True)
+
+  @property
+  def engine(self):
+    if self._engine is None:
+      from .engine import Engine
+      self._engine = Engine(self._cfg, batch_size=self._batch, precision=self.precision, training=True)
+      self._engine.init_params(seed=int(self.params.get('seed', 0)))
+      parallel.broadcast_parameters(self._engine)
+      ckpt = latest_checkpoint(self.model_dir)
+      if ckpt:
+        restore_checkpoint(self._engine, ckpt)
+    return self._engine
+
+  def _check_batch(self, features):
+    n = int(np.shape(features['rgb'])[0])
+    if n != self._batch:
+      # lstm_memory is created with the static shape [batch_size, 2*dim_h_lstm] (graph.py:212,218): every
+      # batch the reference sees has exactly batch_size rows
+      raise ValueError("batch of %d rows but the model was built for batch_size=%d" % (n, self._batch))
+
+  def train(self, input_fn, steps=None):
+    eng = self.engine
+    rank, _ = parallel.world_info()
+    p = dict(self.params, engine=eng)
+    done, self.last_train_losses = 0, []
+    log_steps = int(self.params.get('log_steps', 1000) or 1000)
+    for features, labels in input_fn():
+      self._check_batch(features)
+      spec = self._model_fn(features, labels, ModeKeys.TRAIN, p)
+      done += 1
+      if eng.global_step % log_steps == 0 or done == 1:
+        self.last_train_losses.append((eng.global_step, eng.losses_dict(spec.loss)))
+        if rank == 0 and self.params.get('debug'):
+          print('step %d: %s' % self.last_train_losses[-1])
+      if rank == 0 and self.config.save_checkpoints_steps and eng.global_step % self.config.save_checkpoints_steps == 0:
+        save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
+      if steps is not None and done >= steps:
+        break
+    if rank == 0:
+      save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
+    return self
+
+  def evaluate(self, input_fn, steps=None):
+    eng = self.engine
+    p = dict(self.params, engine=eng)
+    loss_sum, nb = 0.0, 0
+    se = {'cmd_ee': 0.0, 'pos_ee': 0.0, 'pos_obj': 0.0}
+    cnt, correct, rows = 0, 0.0, 0
+    for features, labels in input_fn():
+      self._check_batch(features)
+      spec = self._model_fn(features, labels, ModeKeys.EVAL, p)
+      v = spec.loss.detach().cpu().numpy().astype(np.float64)
+      n = int(v[7])
+      loss_sum += v[5]; nb += 1
+      # v[0], v[2], v[3] are per-batch MSEs (mean over n*3): recover the sums for the streaming metric
+      se['cmd_ee'] += v[0] * n * 3; se['pos_ee'] += v[2] * n * 3; se['pos_obj'] += v[3] * n * 3
+      cnt += n * 3; correct += v[6]; rows += n
+      if steps is not None and nb >= steps:
+        break
+    if nb == 0:
+      raise ValueError("evaluate(): input_fn yielded no batches")
+    out = {k: se[k] / cnt for k in se}
+    out.update({'loss': loss_sum / nb, 'cmd_grp': correct / rows, 'global_step': eng.global_step})
+    return out
+
+  def predict(self, input_fn):
+    eng = self.engine
+    p = dict(self.params, engine=eng)
+    for features in input_fn():
+      if isinstance(features, tuple):
+        features = features[0]
+      spec = self._model_fn(features, None, ModeKeys.PREDICT, p)
+      n = spec.predictions['cmd_ee'].shape[0]
+      for i in range(n):
+        yield {k: v[i] for k, v in spec.predictions.items()}
+
+  def latest_checkpoint(self):
+    return latest_checkpoint(self.model_dir)

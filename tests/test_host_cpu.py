@@ -191,3 +191,84 @@ def test_data_parallel_step_world_size_2_gloo(tmp_path):
   r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=170)
   assert r.returncode == 0, r.stdout[-3000:]
   assert 'ok 0' in r.stdout and 'ok 1' in r.stdout
+
+
+# reference scripts/train_e2evmc.py:22-124 -- (flag, type, default)
+_REFERENCE_FLAGS = [
+    ('dataset_dir', str, '../data/gym-pick-pad2-cube2-v4'), ('split_name', str, 'default'),
+    ('model_dir', str, '../tmp/models/geeco-f'), ('observation_format', str, 'rgb'), ('control_mode', str, 'cartesian'),
+    ('goal_condition', str, 'none'), ('window_size', int, 4), ('dim_h_lstm', int, 128), ('dim_h_fc', int, 128),
+    ('dim_s_obs', int, 256), ('dim_s_dyn', int, 256), ('dim_s_diff', int, 256), ('proc_obs', str, 'sequence'),
+    ('proc_tgt', str, 'constant'), ('l2_regularizer', float, 0.0), ('lambda_aux', float, 1.0),
+    ('data_encoding', str, 'v4'), ('lr', float, 1e-4), ('train_epochs', int, 10), ('ckpt_steps', int, 10000),
+    ('num_last_ckpt', int, 2), ('num_best_ckpt', int, 5), ('batch_size', int, 32), ('memcap', float, 0.8),
+    ('num_threads', int, 4), ('prefetch_size', int, 4), ('shuffle_buffer', int, 64), ('log_steps', int, 1000),
+    ('debug', bool, False), ('initial_eval', bool, False)]
+
+
+def _train_module():
+  import importlib
+  sys.path.insert(0, os.path.join(ROOT, 'scripts'))
+  return importlib.import_module('train_e2evmc')
+
+
+def test_train_cli_accepts_the_reference_flags():
+  m = _train_module()
+  d = vars(m.ARGPARSER.parse_args([]))
+  for name, typ, default in _REFERENCE_FLAGS:
+    assert name in d, name
+    assert d[name] == default and isinstance(d[name], typ), (name, d[name])
+  a = m.ARGPARSER.parse_args(['--observation_format', 'rgb', '--goal_condition', 'target', '--proc_obs', 'dynimg',
+                              '--proc_tgt', 'dyndiff', '--batch_size', '64', '--debug'])
+  assert (a.observation_format, a.goal_condition, a.proc_obs, a.proc_tgt, a.batch_size, a.debug) == \
+      ('rgb', 'target', 'dynimg', 'dyndiff', 64, True)
+  with pytest.raises(NotImplementedError):
+    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'target', '--dataset_dir', '/nonexistent']))
+
+
+def test_snapshot_export_protocol(tmp_path):
+  m = _train_module()
+  from geeco_b200.estimator import latest_checkpoint
+  md = str(tmp_path)
+  with open(os.path.join(md, '20260101_000000000-runcmd.json'), 'w') as fp:
+    fp.write('{}')
+  with open(os.path.join(md, 'e2evmc_config.json'), 'w') as fp:
+    fp.write('{}')
+  losses = [0.5, 0.3, 0.9, 0.1]
+  for i, loss in enumerate(losses):
+    step = 10 * (i + 1)
+    np.savez(os.path.join(md, 'model.ckpt-%d.npz' % step), global_step=np.array(step))
+    with open(os.path.join(md, 'checkpoint'), 'w') as fp:
+      fp.write('model_checkpoint_path: "model.ckpt-%d"\n' % step)
+    assert latest_checkpoint(md).endswith('model.ckpt-%d' % step)
+    m.export_snapshot(md, {'loss': loss}, num_best_ckpt=3)
+  with open(os.path.join(md, 'snapshots', 'snapshot_index.json')) as fp:
+    idx = json.load(fp)
+  assert sorted(v['loss'] for v in idx.values()) == [0.1, 0.3, 0.5]          # the worst (0.9) was evicted
+  assert not os.path.exists(os.path.join(md, 'snapshots', 'model.ckpt-30'))
+  snap = os.path.join(md, 'snapshots', 'model.ckpt-40')
+  assert sorted(os.listdir(snap)) == ['20260101_000000000-runcmd.json', 'checkpoint', 'e2evmc_config.json',
+                                      'model.ckpt-40.npz']
+  with open(os.path.join(snap, 'checkpoint')) as fp:
+    assert fp.read() == 'model_checkpoint_path: "model.ckpt-40"\n'
+
+
+def test_run_command_file(tmp_path):
+  m = _train_module()
+  from geeco_b200.runscript import save_run_command
+  p = save_run_command(m.ARGPARSER, str(tmp_path), ['--lr', '0.5', '--bogus', '1'])
+  assert re.match(r'\d{8}_\d{9}-runcmd\.json$', os.path.basename(p))
+  with open(p) as fp:
+    d = json.load(fp)
+  assert d['parsed_args']['lr'] == 0.5 and d['unparsed_args'] == ['--bogus', '1']
+
+
+def test_compat_import_paths():
+  code = ("import sys; sys.path.insert(0, %r); "
+          "from models.e2evmc.predictor import GoalE2EVMCPredictor; "
+          "from models.e2evmc.estimator import goal_e2evmc_model_fn; "
+          "from models.e2evmc.params import create_e2evmc_config; "
+          "from models.e2evmc.utils import load_model_config; "
+          "from utils.runscript import save_run_command; print('ok')") % os.path.join(ROOT, 'compat')
+  r = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert r.returncode == 0 and 'ok' in r.stdout, r.stdout
