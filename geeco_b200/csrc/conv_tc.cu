@@ -91,10 +91,10 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 // ------------------------------------------------------------------------------------------------
 template <int PIECE>
 __global__ void __launch_bounds__(NN_THREADS, 1)
-tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __nv_bfloat16* __restrict__ src,
+tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
-             int total_tiles, int tmem_cols, int stages) {
+             int tiles_flat, int tmem_cols, int stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -114,19 +114,23 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
   }
-  if (g.Kpad > g.Ktot) {          // padding columns are never written by the producers
-    zero_smem(a_base, stages * A_STAGE_BYTES);
-    fence_proxy_async();
-  }
+  // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
+  // they hold later is finite data (multiplied by zero weights)
+  zero_smem(a_base, stages * A_STAGE_BYTES);
+  fence_proxy_async();
   if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
-  if (warp == 13 && lane == 0) tma_prefetch_desc(&wmap);
+  if (warp == 13 && lane == 0) {
+    for (int c = 0; c < cl.ncls; ++c) tma_prefetch_desc(&maps.m[c]);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int nkb = g.Kpad / BK;
   const uint32_t Mg = (uint32_t)g.imgs_per_group * (uint32_t)(g.Hm * g.Wm);
+  const int ncls = cl.ncls;
+  // work item j of this CTA: flat tile (j / ncls) * gridDim.x + blockIdx.x, class j % ncls  -> the classes
+  // of one tile run back to back (their source rows and destination lines are shared)
 
   if (warp < 8) {
     // ===================== A producers: implicit-im2col gather =====================
@@ -139,9 +143,10 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
     if (PIECE == 4 && g.rowwin) {
       // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
       // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int group = tile / tiles_per_group;
-        const uint32_t m0 = (uint32_t)(tile - group * tiles_per_group) * BM;
+      const TcCls& k0 = cl.c[0];
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x, ++it) {
+        const int group = flat / tiles_per_group;
+        const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
         int img, y, x0;
         decode_pixel(g, m0, img, y, x0);
         const int s = it % stages;
@@ -150,8 +155,8 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
         const __nv_bfloat16* imgbase = src + (long long)((group * g.imgs_per_group + img) * g.Hs) * g.Ws * 4;
         for (int p = threadIdx.x; p < 3 * BM; p += PROD_THREADS) {
           const int row = p & (BM - 1), ky = p >> 7;
-          const int iy = y + g.dy[ky * 3];
-          const int xl = x0 + row + g.dx[0];
+          const int iy = y + k0.dy[ky * 3];
+          const int xl = x0 + row + k0.dx[0];
           const bool rowok = (m0 + row) < Mg && (unsigned)iy < (unsigned)g.Hs;
           const __nv_bfloat16* sp = imgbase + ((long long)iy * g.Ws + xl) * 4;
 #pragma unroll
@@ -164,45 +169,50 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
         }
         cp_async_mbar_arrive_noinc(&full[s]);
       }
-    } else
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int group = tile / tiles_per_group;
-      const uint32_t m0 = (uint32_t)(tile - group * tiles_per_group) * BM;
-      // per row: pointer to source pixel (ys, xs) and the coordinates themselves; an out-of-range row
-      // gets ys = 1<<20 so that every tap fails the bounds test and zero-fills
-      const __nv_bfloat16* rptr[PASSES];
-      int rys[PASSES], rxs[PASSES];
+    } else {
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+        const int group = flat / tiles_per_group;
+        const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+        // per row: pointer to source pixel (ys, xs) and the coordinates themselves; an out-of-range row
+        // gets ys = 1<<20 so that every tap fails the bounds test and zero-fills
+        const __nv_bfloat16* rptr[PASSES];
+        int rys[PASSES], rxs[PASSES];
 #pragma unroll
-      for (int i = 0; i < PASSES; ++i) {
-        const uint32_t m = m0 + i * ROWS_PER_PASS + rsub;
-        rptr[i] = src; rys[i] = 1 << 20; rxs[i] = 0;
-        if (m < Mg) {
-          int img, y, x;
-          decode_pixel(g, m, img, y, x);
-          rys[i] = y * g.sy; rxs[i] = x * g.sx;
-          rptr[i] = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + rys[i]) * g.Ws + rxs[i]) * g.Cs;
-        }
-      }
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % stages;
-        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
-        const int k = kb * BK + piece * PIECE;
-        if (k < g.Ktot) {
-          int tap, ch;
-          split_k(g, k, tap, ch);
-          const int dyt = g.dy[tap], dxt = g.dx[tap];
-          const int toff = (dyt * g.Ws + dxt) * g.Cs + ch;
-          const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
-#pragma unroll
-          for (int i = 0; i < PASSES; ++i) {
-            const int row = i * ROWS_PER_PASS + rsub;
-            const bool ok = (unsigned)(rys[i] + dyt) < (unsigned)g.Hs && (unsigned)(rxs[i] + dxt) < (unsigned)g.Ws;
-            const uint32_t d = a_s + row * 128 + ((((pbyte >> 4) ^ (uint32_t)(row & 7))) << 4) + (pbyte & 15u);
-            cp_piece<PIECE>(d, ok ? (const void*)(rptr[i] + toff) : (const void*)src, ok);
+        for (int i = 0; i < PASSES; ++i) {
+          const uint32_t m = m0 + i * ROWS_PER_PASS + rsub;
+          rptr[i] = src; rys[i] = 1 << 20; rxs[i] = 0;
+          if (m < Mg) {
+            int img, y, x;
+            decode_pixel(g, m, img, y, x);
+            rys[i] = y * g.sy; rxs[i] = x * g.sx;
+            rptr[i] = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + rys[i]) * g.Ws + rxs[i]) * g.Cs;
           }
         }
-        // asynchronous arrival: fires when this thread's copies have landed; the producer never waits
-        cp_async_mbar_arrive_noinc(&full[s]);
+        for (int c = 0; c < ncls; ++c) {
+          const TcCls& kc = cl.c[c];
+          const int nkb = kc.Kpad / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % stages;
+            mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+            const int k = kb * BK + piece * PIECE;
+            if (k < kc.Ktot) {
+              int tap, ch;
+              split_k(g, k, tap, ch);
+              const int dyt = kc.dy[tap], dxt = kc.dx[tap];
+              const int toff = (dyt * g.Ws + dxt) * g.Cs + ch;
+              const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
+#pragma unroll
+              for (int i = 0; i < PASSES; ++i) {
+                const int row = i * ROWS_PER_PASS + rsub;
+                const bool ok = (unsigned)(rys[i] + dyt) < (unsigned)g.Hs && (unsigned)(rxs[i] + dxt) < (unsigned)g.Ws;
+                const uint32_t d = a_s + row * 128 + ((((pbyte >> 4) ^ (uint32_t)(row & 7))) << 4) + (pbyte & 15u);
+                cp_piece<PIECE>(d, ok ? (const void*)(rptr[i] + toff) : (const void*)src, ok);
+              }
+            }
+            // asynchronous arrival: fires when this thread's copies have landed; the producer never waits
+            cp_async_mbar_arrive_noinc(&full[s]);
+          }
+        }
       }
     }
   } else if (warp < 12) {
@@ -210,107 +220,114 @@ tc_nn_kernel(const TcGeom g, const __grid_constant__ CUtensorMap wmap, const __n
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const int group = tile / tiles_per_group;
-      const uint32_t m = (uint32_t)(tile - group * tiles_per_group) * BM + row;
-      const int buf = tl & 1;
+    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+      const int group = flat / tiles_per_group;
+      const uint32_t m = (uint32_t)(flat - group * tiles_per_group) * BM + row;
       const bool valid = m < Mg;
-      long long off = 0;
-      if (valid) {
-        int img, y, x;
-        decode_pixel(g, m, img, y, x);
-        off = ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + g.dy0)) * g.Wd + (x * g.dsx + g.dx0)) * g.Nn;
-      }
+      int img = 0, y = 0, x = 0;
+      if (valid) decode_pixel(g, m, img, y, x);
       const float* bias = bias_all ? bias_all + (long long)group * g.bias_group_stride : nullptr;
-      mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
+      for (int c = 0; c < ncls; ++c, ++tl) {
+        const TcCls& kc = cl.c[c];
+        const int buf = tl & 1;
+        const long long off =
+            ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + kc.dy0)) * g.Wd + (x * g.dsx + kc.dx0)) * g.Nn;
+        mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 bb = __ldg(b4 + i);
-              f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = __ldg(b4 + i);
+                f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+              }
+              if (epi == TC_EPI_BIAS_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+            } else if (epi == TC_EPI_MASK) {
+              const uint4 m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
+              const uint4 m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
+              const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                // post-ReLU activations are >= 0: "y > 0" == magnitude bits non-zero and sign clear
+                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) f[2 * i] = 0.f;
+                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) f[2 * i + 1] = 0.f;
+              }
             }
-            if (epi == TC_EPI_BIAS_RELU) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            if (dst) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
+              o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+              o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
+              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+              *reinterpret_cast<uint4*>(dst + off + c0) = o0;
+              *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
             }
-          } else if (epi == TC_EPI_MASK) {
-            const uint4 m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
-            const uint4 m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
-            const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+            if (dst_f32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              // post-ReLU activations are >= 0: "y > 0" == magnitude bits non-zero and sign clear
-              const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-              if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) f[2 * i] = 0.f;
-              if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) f[2 * i + 1] = 0.f;
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             }
-          }
-          if (dst) {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-            o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-            o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            *reinterpret_cast<uint4*>(dst + off + c0) = o0;
-            *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
-          }
-          if (dst_f32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           }
         }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty[buf]);
     }
   } else if (warp == 12) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
       uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const int buf = tl & 1;
-        mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          mbar_wait(&full[s], (it / stages) & 1);
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+        for (int c = 0; c < ncls; ++c, ++tl) {
+          const int nkb = cl.c[c].Kpad / BK;
+          const int buf = tl & 1;
+          mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + s * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(b_base + s * b_stage_bytes);
+          const uint32_t d = tmem_base + (uint32_t)(buf * BN);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % stages;
+            mbar_wait(&full[s], (it / stages) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(a_base + s * A_STAGE_BYTES);
+            const uint32_t b_addr = smem_u32(b_base + s * b_stage_bytes);
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j)
-            tc_mma(d, make_desc_sw128(a_addr + j * 32, 16, 1024), make_desc_sw128(b_addr + j * 32, 16, 1024), idesc,
-                   (kb | j) != 0 ? 1u : 0u);
-          tc_commit(&empty[s]);
+            for (int j = 0; j < BK / 16; ++j)
+              tc_mma(d, make_desc_sw128(a_addr + j * 32, 16, 1024), make_desc_sw128(b_addr + j * 32, 16, 1024), idesc,
+                     (kb | j) != 0 ? 1u : 0u);
+            tc_commit(&empty[s]);
+          }
+          tc_commit(&tmem_full[buf]);
         }
-        tc_commit(&tmem_full[buf]);
       }
     }
   } else {
     // ===================== weight tiles by TMA (one thread) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int group = tile / tiles_per_group;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % stages;
-          mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
-          tma_load_2d(smem_u32(b_base + s * b_stage_bytes), &wmap, &full[s], kb * BK, group * g.b_rows_per_group);
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+        const int group = flat / tiles_per_group;
+        for (int c = 0; c < ncls; ++c) {
+          const int nkb = cl.c[c].Kpad / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % stages;
+            mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
+            tma_load_2d(smem_u32(b_base + s * b_stage_bytes), &maps.m[c], &full[s], kb * BK, group * g.b_rows_per_group);
+          }
         }
       }
     }
@@ -765,19 +782,41 @@ static int check_geom(const TcGeom& g, const char* who) {
   return GEECO_OK;
 }
 
-int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
-                 const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
-                 cudaStream_t st) {
+static void fill_class(TcCls* c, const TcGeom& g) {
+  c->ntaps = g.ntaps; c->Ktot = g.Ktot; c->Kpad = g.Kpad; c->dy0 = g.dy0; c->dx0 = g.dx0;
+  for (int t = 0; t < GEECO_MAX_TAPS; ++t) { c->dy[t] = g.dy[t]; c->dx[t] = g.dx[t]; }
+}
+
+// ncls geometries that differ only in taps / K extent / destination offset (the parity classes of a
+// strided data-gradient) run as ONE launch; ncls == 1 is the plain forward / single-class case
+int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
+                       const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
+                       int max_ctas, cudaStream_t st) {
+  if (ncls < 1 || ncls > 4) { geeco_set_error("tc_nn: ncls=%d outside [1,4]", ncls); return GEECO_ERR_INVALID; }
+  const TcGeom& g = gs[0];
   if (g.Nn % 16 || g.Nn < 16 || g.Nn > 256) { geeco_set_error("tc_nn: unsupported N=%d", g.Nn); return GEECO_ERR_INVALID; }
-  int rc = check_geom(g, "tc_nn");
-  if (rc) return rc;
+  TcClasses cl;
+  memset(&cl, 0, sizeof(cl));
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  cl.ncls = ncls;
+  for (int c = 0; c < ncls; ++c) {
+    int rc = check_geom(gs[c], "tc_nn");
+    if (rc) return rc;
+    if (gs[c].Hm != g.Hm || gs[c].Wm != g.Wm || gs[c].Nn != g.Nn || gs[c].Cs != g.Cs || gs[c].Hs != g.Hs || gs[c].Ws != g.Ws) {
+      geeco_set_error("tc_nn: classes of one launch must share the row grid, source and N");
+      return GEECO_ERR_INVALID;
+    }
+    fill_class(&cl.c[c], gs[c]);
+    maps.m[c] = *wmaps[c];
+  }
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
   const int tiles_per_group = ceil_div(Mg, BM);
-  const int total_tiles = tiles_per_group * g.groups;
+  const int tiles_flat = tiles_per_group * g.groups;
   const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;
   const int tmem_cols = next_pow2_cols(2 * g.Nn);
-  // small-N layers are latency/bandwidth-bound: two CTAs per SM with 4 stages; wide layers: one CTA, deeper ring
+  // small-N layers are latency/bandwidth-bound: two CTAs per SM; wide layers: one CTA, deeper ring
   int per_sm = (tmem_cols <= 256 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
   int stages = (int)((SMEM_BUDGET / per_sm - 1024 - 512) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -785,21 +824,28 @@ int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* 
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
   int ctas = num_sms() * per_sm;
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
-  if (ctas > total_tiles) ctas = total_tiles;
+  if (ctas > tiles_flat) ctas = tiles_flat;
   if (g.Cs == 4) {
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    total_tiles, tmem_cols, stages);
+    tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
+                                                    tiles_flat, tmem_cols, stages);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, *wmap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    total_tiles, tmem_cols, stages);
+    tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
+                                                    tiles_flat, tmem_cols, stages);
   }
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
+}
+
+int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
+                 const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
+                 cudaStream_t st) {
+  const CUtensorMap* maps[1] = {wmap};
+  return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st);
 }
 
 struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols; };

@@ -21,6 +21,11 @@ struct TcGeom {
   long long bias_group_stride;
 };
 
+// per-class part of a geometry (taps, K extent, destination offset) and the weight maps of a multi-class launch
+struct TcCls { int ntaps; int dy[GEECO_MAX_TAPS], dx[GEECO_MAX_TAPS]; int Ktot, Kpad, dy0, dx0; };
+struct TcClasses { int ncls; TcCls c[4]; };
+struct TcMaps { CUtensorMap m[4]; };
+
 enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3 };
 
 struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packed tap
@@ -29,6 +34,9 @@ struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packe
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
                  cudaStream_t st);
+int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
+                       const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
+                       int max_ctas, cudaStream_t st);
 // wgrad: dW[(tap,ci)][co] (+ optional bias gradient) from im2col(src)^T x G, deterministic split reduction.
 //   g describes the FORWARD geometry (rows = output pixels); G is [imgs, Hm, Wm, Cout] bf16.
 //   Cw = channels per tap present in the weight tensor (Cin_real); dW fp32 [ntaps*Cw, Cout] per group.

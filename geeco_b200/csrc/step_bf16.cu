@@ -196,15 +196,20 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
                                c->grad + c->params[L.p_b[e]].offset, bp->partial, bp->partial_cap, wstride, bstride, st);
       if (rc) return rc;
       if (l == 0) continue;
-      for (int ci = 0; ci < B.n_classes; ++ci) {
-        TcGeom dg = B.dg[ci];
-        if (!L.grouped) {
-          int taps[9];
-          tc_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, dg.dy0, dg.dx0, N, 1, &dg, taps);
+      {
+        TcGeom dgs[4];
+        const CUtensorMap* dmaps[4];
+        for (int ci = 0; ci < B.n_classes; ++ci) {
+          dgs[ci] = B.dg[ci];
+          if (!L.grouped) {
+            int taps[9];
+            tc_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, B.dg[ci].dy0, B.dg[ci].dx0, N, 1, &dgs[ci], taps);
+          }
+          dmaps[ci] = &B.dg_map[ci][e];
         }
         (void)groups;
-        rc = launch_tc_nn(dg, &B.dg_map[ci][e], gy, nullptr, xin + in_off, (__nv_bfloat16*)c->layers[l - 1].g + in_off,
-                          nullptr, TC_EPI_MASK, 0, st);
+        rc = launch_tc_nn_multi(dgs, dmaps, B.n_classes, gy, nullptr, xin + in_off,
+                                (__nv_bfloat16*)c->layers[l - 1].g + in_off, nullptr, TC_EPI_MASK, 0, st);
         if (rc) return rc;
       }
     }
@@ -283,20 +288,34 @@ extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const v
   if (dx) {
     if (Cw != Cin) { geeco_set_error("conv2d_bwd_bf16: dx needs Cw == Cin"); return GEECO_ERR_INVALID; }
     int ci = 0;
+    TcGeom dgs[4];
+    CUtensorMap dm[4];
+    const CUtensorMap* dmaps[4];
     for (int py = 0; py < stride; ++py)
       for (int px = 0; px < stride; ++px) {
         TcGeom dg; int taps[9];
         if (!tc_dgrad_geom(H, W, Cin, Cout, stride, py, px, N, 1, &dg, taps)) continue;
-        __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_dg[ci++]);
+        __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_dg[ci]);
         rc = launch_pack_weights(w, wp, 1, 1, 0, Cin, Cout, Cout, dg.ntaps, taps, Cin, dg.Kpad, st);
         if (rc) return rc;
-        CUtensorMap map;
-        rc = make_weight_tensor_map(&map, wp, Cin, dg.Kpad, Cin);
+        rc = make_weight_tensor_map(&dm[ci], wp, Cin, dg.Kpad, Cin);
         if (rc) return rc;
-        rc = launch_tc_nn(dg, &map, (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
+        dgs[ci] = dg; dmaps[ci] = &dm[ci];
+        ++ci;
+      }
+    bool same_grid = true;
+    for (int i = 1; i < ci; ++i) same_grid = same_grid && dgs[i].Hm == dgs[0].Hm && dgs[i].Wm == dgs[0].Wm;
+    if (same_grid) {
+      rc = launch_tc_nn_multi(dgs, dmaps, ci, (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
+                              (__nv_bfloat16*)dx, nullptr, relu_mask_x ? TC_EPI_MASK : TC_EPI_STORE, 0, st);
+      if (rc) return rc;
+    } else {
+      for (int i = 0; i < ci; ++i) {
+        rc = launch_tc_nn(dgs[i], dmaps[i], (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
                           (__nv_bfloat16*)dx, nullptr, relu_mask_x ? TC_EPI_MASK : TC_EPI_STORE, 0, st);
         if (rc) return rc;
       }
+    }
   }
   return GEECO_OK;
 }
