@@ -25,6 +25,7 @@
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 using namespace tc;
@@ -35,6 +36,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int PROD_THREADS = 256;
+constexpr int LOOKAHEAD = 2;                          // cp.async groups in flight per producer thread before it signals
 constexpr int NN_THREADS = PROD_THREADS + 128 + 64;   // 448
 constexpr int WG_PROD_THREADS = 512;
 constexpr int WG_THREADS = WG_PROD_THREADS + 128 + 32;   // 672
@@ -82,6 +84,24 @@ __device__ __forceinline__ uint32_t tap_mask(const TcGeom& g, int ys, int xs) {
   return mk;
 }
 
+// One mbarrier arrival per producer WARP (per-thread arrivals on one mbarrier serialise in the shared-memory
+// atomic unit): each thread commits its copies of k-block `it` as a cp.async group, waits until the group of
+// k-block it-LOOKAHEAD has landed, the warp converges and lane 0 arrives on that older stage.
+__device__ __forceinline__ void producer_signal(uint64_t* full, uint32_t it, int stages, int lane) {
+  cp_async_commit();
+  if (it >= LOOKAHEAD) {
+    cp_async_wait<LOOKAHEAD>();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[(it - LOOKAHEAD) % stages]);
+  }
+}
+__device__ __forceinline__ void producer_drain(uint64_t* full, uint32_t it, int stages, int lane) {
+  cp_async_wait<0>();
+  __syncwarp();
+  if (lane == 0)
+    for (uint32_t j = it >= LOOKAHEAD ? it - LOOKAHEAD : 0; j < it; ++j) mbar_arrive(&full[j % stages]);
+}
+
 __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
   for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
 }
@@ -90,11 +110,11 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 // forward / data-gradient kernel.  PIECE = bf16 elements per cp.async (8 -> 16 B, 4 -> 8 B)
 // ------------------------------------------------------------------------------------------------
 template <int PIECE>
-__global__ void __launch_bounds__(NN_THREADS, 1)
+__global__ void __launch_bounds__(NN_THREADS, 2)
 tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
-             int tiles_flat, int tmem_cols, int stages) {
+             int tiles_flat, int tmem_cols, int stages, int nbuf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -105,13 +125,13 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tmem_full = bars + 2 * MAX_STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS + 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
   }
   // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
@@ -143,29 +163,48 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     if (PIECE == 4 && g.rowwin) {
       // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
       // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
+      // everything that does not depend on the tile is hoisted: thread t owns row (t & 127) for ky = t >> 7
+      // (0 or 1) and, if t < 128, also ky = 2; the three destination byte offsets per (row, ky) are constants
       const TcCls& k0 = cl.c[0];
+      const int row = threadIdx.x & (BM - 1);
+      const int kyA = threadIdx.x >> 7;
+      const bool hasB = threadIdx.x < BM;
+      uint32_t dA[3], dB[3];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t ba = (uint32_t)(kyA * 24 + kx * 8), bb = (uint32_t)(2 * 24 + kx * 8);
+        dA[kx] = row * 128 + (((ba >> 4) ^ (uint32_t)(row & 7)) << 4) + (ba & 15u);
+        dB[kx] = row * 128 + (((bb >> 4) ^ (uint32_t)(row & 7)) << 4) + (bb & 15u);
+      }
+      const int dyA = k0.dy[kyA * 3], dyB = k0.dy[6], dx0 = k0.dx[0];
+      const int Hs = g.Hs, Ws = g.Ws, ipg = g.imgs_per_group, hw_shift = g.hw_shift, w_shift = g.w_shift;
+      const long long offA = ((long long)dyA * Ws + row + dx0) * 4, offB = ((long long)dyB * Ws + row + dx0) * 4;
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x, ++it) {
         const int group = flat / tiles_per_group;
         const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
-        int img, y, x0;
-        decode_pixel(g, m0, img, y, x0);
+        const int img = (int)(m0 >> hw_shift);
+        const uint32_t rem = m0 & ((1u << hw_shift) - 1u);
+        const int y = (int)(rem >> w_shift), x0 = (int)(rem & ((1u << w_shift) - 1u));
         const int s = it % stages;
         mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
         const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
-        const __nv_bfloat16* imgbase = src + (long long)((group * g.imgs_per_group + img) * g.Hs) * g.Ws * 4;
-        for (int p = threadIdx.x; p < 3 * BM; p += PROD_THREADS) {
-          const int row = p & (BM - 1), ky = p >> 7;
-          const int iy = y + k0.dy[ky * 3];
-          const int xl = x0 + row + k0.dx[0];
-          const bool rowok = (m0 + row) < Mg && (unsigned)iy < (unsigned)g.Hs;
-          const __nv_bfloat16* sp = imgbase + ((long long)iy * g.Ws + xl) * 4;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const bool ok = rowok && (unsigned)(xl + kx) < (unsigned)g.Ws;
-            const uint32_t byte = (uint32_t)(ky * 24 + kx * 8);
-            const uint32_t d = a_s + row * 128 + (((byte >> 4) ^ (uint32_t)(row & 7)) << 4) + (byte & 15u);
-            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
-          }
+        // pointer to pixel (y, x0) of the image; every copy is this plus a per-thread constant
+        const __nv_bfloat16* pix = src + ((long long)((group * ipg + img) * Hs + y) * Ws + x0) * 4;
+        const int xl = x0 + row + dx0;                       // leftmost source column of this row's window
+        const bool in0 = xl >= 0, in2 = xl + 2 < Ws;         // kx = 1 is always inside (Ws >= 2)
+        {
+          const bool okr = (unsigned)(y + dyA) < (unsigned)Hs;
+          const __nv_bfloat16* sp = pix + offA;
+          cp_async8(a_s + dA[0], (okr && in0) ? (const void*)sp : (const void*)src, (okr && in0) ? 8u : 0u);
+          cp_async8(a_s + dA[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
+          cp_async8(a_s + dA[2], (okr && in2) ? (const void*)(sp + 8) : (const void*)src, (okr && in2) ? 8u : 0u);
+        }
+        if (hasB) {
+          const bool okr = (unsigned)(y + dyB) < (unsigned)Hs;
+          const __nv_bfloat16* sp = pix + offB;
+          cp_async8(a_s + dB[0], (okr && in0) ? (const void*)sp : (const void*)src, (okr && in0) ? 8u : 0u);
+          cp_async8(a_s + dB[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
+          cp_async8(a_s + dB[2], (okr && in2) ? (const void*)(sp + 8) : (const void*)src, (okr && in2) ? 8u : 0u);
         }
         cp_async_mbar_arrive_noinc(&full[s]);
       }
@@ -229,10 +268,10 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
       const float* bias = bias_all ? bias_all + (long long)group * g.bias_group_stride : nullptr;
       for (int c = 0; c < ncls; ++c, ++tl) {
         const TcCls& kc = cl.c[c];
-        const int buf = tl & 1;
+        const int buf = tl % nbuf;
         const long long off =
             ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + kc.dy0)) * g.Wd + (x * g.dsx + kc.dx0)) * g.Nn;
-        mbar_wait(&tmem_full[buf], (tl >> 1) & 1);
+        mbar_wait(&tmem_full[buf], (tl / nbuf) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
         for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -294,8 +333,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
         for (int c = 0; c < ncls; ++c, ++tl) {
           const int nkb = cl.c[c].Kpad / BK;
-          const int buf = tl & 1;
-          mbar_wait(&tmem_empty[buf], ((tl >> 1) & 1) ^ 1);
+          const int buf = tl % nbuf;
+          mbar_wait(&tmem_empty[buf], ((tl / nbuf) & 1) ^ 1);
           tc_fence_after();
           const uint32_t d = tmem_base + (uint32_t)(buf * BN);
           for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -370,6 +409,18 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     fence_barrier_init();
   }
   zero_smem(st_base, stages * stage_bytes);       // pieces that are padding for this CTA are never written
+  __syncthreads();
+  // bias gradient = sum_p G[p][co] * 1: the first padding column holds 1.0 (bf16 0x3f80) for EVERY row of EVERY
+  // stage, written once; rows past the end of the tensor contribute nothing because their G rows are zero-filled
+  if (ones_col >= col0 && ones_col < col0 + nsub * 64) {
+    const int oc = ones_col - col0, oj = oc >> 6;
+    const uint32_t obyte = (uint32_t)(oc & 63) * 2;
+    for (int i = threadIdx.x; i < stages * 64; i += blockDim.x) {
+      const int s = i >> 6, r = i & 63;
+      uint8_t* p = st_base + s * stage_bytes + (2 + oj) * SUB + r * 128 + ((((obyte >> 4) ^ (uint32_t)(r & 7))) << 4) + (obyte & 15u);
+      *reinterpret_cast<uint16_t*>(p) = 0x3f80;
+    }
+  }
   fence_proxy_async();
   if (warp == MMA_WARP) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   tc_fence_before();
@@ -396,7 +447,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     constexpr int PASSES = 64 / ROWS_PER_PASS;
     const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
-    int kind[8], kdy[8], kdx[8], ktoff[8];      // 0 = padding (skip), 1 = gather, 2 = ones column
+    int kind[8], kdy[8], kdx[8], ktoff[8];      // kind 0 = padding / ones column (never written), 1 = gather
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = col0 + j * 64 + piece * PIECE;
@@ -407,10 +458,18 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
           split_k(g, k, tap, ch);
           kind[j] = 1; kdy[j] = g.dy[tap]; kdx[j] = g.dx[tap];
           ktoff[j] = (g.dy[tap] * g.Ws + g.dx[tap]) * g.Cs + ch;
-        } else if (k == ones_col) {
-          kind[j] = 2;
         }
       }
+    }
+    // conv1 fast path constants (thread t < 192: row = t & 63, ky = t >> 6)
+    const int rw_row = threadIdx.x & 63, rw_ky = (threadIdx.x >> 6) % 3;
+    const int rw_dy = g.dy[rw_ky * 3], rw_dx0 = g.dx[0];
+    const long long rw_off = ((long long)rw_dy * g.Ws + rw_row + rw_dx0) * 4;
+    uint32_t rw_d[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const uint32_t bb = (uint32_t)(rw_ky * 24 + kx * 8);
+      rw_d[kx] = rw_row * 128 + (((bb >> 4) ^ (uint32_t)(rw_row & 7)) << 4) + (bb & 15u);
     }
     const long long grow = (long long)group * Mg;
     for (int it = 0; it < nkb; ++it) {
@@ -429,30 +488,20 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
           if (g_ok[j]) cp_async16(sb + j * SUB + roff, rvalid ? (const void*)(gp + j * 64) : (const void*)G, rvalid ? 16u : 0u);
       }
       if (PIECE == 4 && g.rowwin) {
-        // conv1 fast path: 64 consecutive pixels of one image row; threads 0..191 copy one (row, ky) window
-        // of 24 contiguous bytes, threads 192..255 write the bias-gradient ones column (k = 36)
-        int img, y, x0;
-        decode_pixel(g, mb, img, y, x0);
-        const int p = threadIdx.x;
-        if (p < 192) {
-          const int row = p & 63, ky = p >> 6;
-          const int iy = y + g.dy[ky * 3];
-          const int xl = x0 + row + g.dx[0];
-          const bool rowok = (mb + row) < Mg && (unsigned)iy < (unsigned)g.Hs;
-          const __nv_bfloat16* sp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + iy) * g.Ws + xl) * 4;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const bool ok = rowok && (unsigned)(xl + kx) < (unsigned)g.Ws;
-            const uint32_t byte = (uint32_t)(ky * 24 + kx * 8);
-            const uint32_t d = sb + 2 * SUB + row * 128 + (((byte >> 4) ^ (uint32_t)(row & 7)) << 4) + (byte & 15u);
-            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
-          }
-        } else if (p < 256 && ones_col == 36) {
-          const int row = p - 192;
-          const uint32_t one = (mb + row) < Mg ? 0x00003f80u : 0u;
-          const uint32_t d = sb + 2 * SUB + row * 128 + (((72u >> 4) ^ (uint32_t)(row & 7)) << 4) + (72u & 15u);
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
-          fence_proxy_async();
+        // conv1 fast path: 64 consecutive pixels of one image row; threads 0..191 copy one (row, ky) window of
+        // 24 contiguous bytes (all tile-invariant quantities were hoisted into rw_*)
+        if (threadIdx.x < 192) {
+          const int img = (int)(mb >> g.hw_shift);
+          const uint32_t rem = mb & ((1u << g.hw_shift) - 1u);
+          const int y = (int)(rem >> g.w_shift), x0 = (int)(rem & ((1u << g.w_shift) - 1u));
+          const __nv_bfloat16* sp = src + ((long long)((group * g.imgs_per_group + img) * g.Hs + y) * g.Ws + x0) * 4 + rw_off;
+          const int xl = x0 + rw_row + rw_dx0;
+          const bool okr = mb + rw_row < Mg && (unsigned)(y + rw_dy) < (unsigned)g.Hs;
+          const bool ok0 = okr && xl >= 0, ok2 = okr && xl + 2 < g.Ws;
+          const uint32_t base = sb + 2 * SUB;
+          cp_async8(base + rw_d[0], ok0 ? (const void*)sp : (const void*)src, ok0 ? 8u : 0u);
+          cp_async8(base + rw_d[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
+          cp_async8(base + rw_d[2], ok2 ? (const void*)(sp + 8) : (const void*)src, ok2 ? 8u : 0u);
         }
       } else {
         // im2col tile: rows = pixels, 64 reduction-index values per sub-tile
@@ -474,16 +523,8 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
           for (int j = 0; j < 8; ++j) {
             if (kind[j] == 0) continue;
             const uint32_t d = sb + (2 + j) * SUB + roff;
-            if (kind[j] == 1) {
-              const bool ok = (unsigned)(ys + kdy[j]) < (unsigned)g.Hs && (unsigned)(xs + kdx[j]) < (unsigned)g.Ws;
-              cp_piece<PIECE>(d, ok ? (const void*)(rp + ktoff[j]) : (const void*)src, ok);
-            } else {
-              // bias-gradient column: 1.0 (bf16 0x3f80) in the first padding column of valid pixels
-              const uint32_t one = rvalid ? 0x00003f80u : 0u;
-              if (PIECE == 8) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %2, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
-              else asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(d), "r"(one), "r"(0u) : "memory");
-              fence_proxy_async();     // generic-proxy store -> visible to the tensor core's async-proxy reads
-            }
+            const bool ok = (unsigned)(ys + kdy[j]) < (unsigned)g.Hs && (unsigned)(xs + kdx[j]) < (unsigned)g.Ws;
+            cp_piece<PIECE>(d, ok ? (const void*)(rp + ktoff[j]) : (const void*)src, ok);
           }
         }
       }
@@ -815,26 +856,34 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   const int tiles_per_group = ceil_div(Mg, BM);
   const int tiles_flat = tiles_per_group * g.groups;
   const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;
-  const int tmem_cols = next_pow2_cols(2 * g.Nn);
   // small-N layers are latency/bandwidth-bound: two CTAs per SM; wide layers: one CTA, deeper ring
-  int per_sm = (tmem_cols <= 256 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  int per_sm = (g.Nn <= 64 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  // accumulator ring in TMEM: as many buffers (power of two, <= 8) as fit this CTA's share of the 512 columns
+  int nbuf = 2;
+  while (nbuf < 8 && 2 * nbuf * g.Nn <= 512 / per_sm) nbuf *= 2;
+  // tuning overrides for experiments (tools/prof_conv.py): GEECO_TC_PERSM / GEECO_TC_NBUF / GEECO_TC_STAGES
+  if (const char* e = getenv("GEECO_TC_PERSM")) { const int v = atoi(e); if (v == 1 || v == 2) per_sm = v; }
+  if (const char* e = getenv("GEECO_TC_NBUF")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v * g.Nn <= 512 / per_sm) nbuf = v; }
+  const int tmem_cols = next_pow2_cols(nbuf * g.Nn);
   int stages = (int)((SMEM_BUDGET / per_sm - 1024 - 512) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (const char* e = getenv("GEECO_TC_STAGES")) { const int v = atoi(e); if (v >= 3 && v <= stages) stages = v; }
   if (stages < 3) { geeco_set_error("tc_nn: stage of %d bytes does not fit 3 times", stage_bytes); return GEECO_ERR_INVALID; }
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
   int ctas = num_sms() * per_sm;
+  if (const char* e = getenv("GEECO_TC_CTAS")) { const int v = atoi(e); if (v > 0) ctas = v; }
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > tiles_flat) ctas = tiles_flat;
   if (g.Cs == 4) {
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    tiles_flat, tmem_cols, stages);
+                                                    tiles_flat, tmem_cols, stages, nbuf);
   } else {
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    tiles_flat, tmem_cols, stages);
+                                                    tiles_flat, tmem_cols, stages, nbuf);
   }
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());

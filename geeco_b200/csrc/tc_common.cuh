@@ -24,8 +24,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.
-// try_wait suspends the thread in hardware for up to the hinted time, so the loop body runs rarely;
-// the iteration cap (tens of seconds) only exists to turn a protocol bug into a trap.
+// try_wait suspends the thread in hardware for a short implementation-defined time (an explicit suspend-time
+// hint compiles to a timed NANOSLEEP and delays wake-ups: measured slower); the clock check, amortised over
+// 2048 polls, only exists to turn a protocol bug into a trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -33,10 +34,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 1;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(200000u)
+        : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
     if ((spin & 2047u) == 0) {           // clock check amortised over 2048 polls
