@@ -3,10 +3,19 @@
 
   python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU under torchrun for N>1)
   python bench.py --impl reference ...                      the CPU restatement of the reference graph
+  python bench.py --extras                                  + BASELINE configs 4 (batched policy steps) and 5
+                                                             (rank-pooling sweep), written to profiles/
 
 Prints ONE JSON line on rank 0.  A "step" is one full train step (rank pooling -> 3 conv encoders ->
 LSTM cell -> heads -> losses -> backward -> Adam) on a synthetic batch of 64 windows per GPU
 (BASELINE config 2; weak scaling for N>1 with an NCCL gradient all-reduce overlapped with backward).
+
+  value     device-resident inputs (3 rotating batches, 252 MB of frames each: larger than the 126 MB L2)
+  e2e       the same metric through the public training entry `Estimator.train(input_fn)` with HOST (pinned)
+            batches: every step uploads its 252 MB batch (overlapped with the previous step on a copy stream)
+            and reads the step's losses back to the host
+  roofline  the kernel with the largest share of the step, timed alone with CUDA events (L2 flushed between
+            repetitions) against the measured HBM copy bandwidth; `kernels` holds the other hot kernels
 """
 from __future__ import annotations
 
@@ -15,6 +24,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -42,6 +52,7 @@ def parse_args():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-kernels', action='store_true', help='skip the isolated kernel roofline timings')
+  ap.add_argument('--extras', action='store_true', help='also run BASELINE configs 4 and 5 (1 GPU)')
   return ap.parse_args()
 
 
@@ -53,6 +64,15 @@ def load_peaks():
     return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d['bf16_tflops_sustained'],
             'source': 'measured'}
   return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+def load_traffic():
+  """DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_traffic.json)."""
+  path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+  if os.path.exists(path):
+    with open(path) as fp:
+      return json.load(fp)
+  return {}
 
 
 class ClockSampler(object):
@@ -67,28 +87,31 @@ class ClockSampler(object):
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                    '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                    '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
+      time.sleep(0.3)      # let the sampler come up before the timed region starts
     except Exception:
       self.proc = None
 
   def _read(self):
     for line in self.proc.stdout:
-      self.rows.append(line.strip())
+      self.rows.append((time.time(), line.strip()))
 
-  def stop(self):
+  def stop(self, t0=None, t1=None):
     if self.proc is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-    time.sleep(0.15)
+    time.sleep(0.12)
     self.proc.terminate()
     try:
       self.proc.wait(timeout=2)
     except Exception:
       self.proc.kill()
     sm, mx, reasons, pw = [], [], set(), []
-    for r in self.rows:
+    for ts, r in self.rows:
+      if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.1):
+        continue
       f = [x.strip() for x in r.split(',')]
       if len(f) < 9:
         continue
@@ -165,9 +188,10 @@ def run_reference(args):
 def run_ours(args):
   import torch
   import torch.distributed as dist
-  from geeco_b200 import create_e2evmc_config, _lib
+  from geeco_b200 import create_e2evmc_config, _lib, parallel
   from geeco_b200.data import synthetic_batch
   from geeco_b200.engine import Engine
+  from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -183,9 +207,10 @@ def run_ours(args):
   cfg = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff', batch_size=N))
   eng = Engine(cfg, batch_size=N, precision=args.precision, training=True, device=dev)
   eng.init_params(seed=0)
+  parallel.broadcast_parameters(eng)
   lib = _lib.load()
 
-  # >= 3 distinct device-resident batches (3 x 252 MB of frames >> 126 MB L2), rotated every step
+  # >= 3 distinct batches (3 x 252 MB of frames >> 126 MB L2), rotated every step
   NB = 3
   host_batches, dev_batches = [], []
   for i in range(NB):
@@ -197,17 +222,7 @@ def run_ours(args):
 
   def step_dev(i):
     b = dev_batches[i % NB]
-    if world == 1:
-      return eng.train_step(b, b)
-    eng.step_forward(b, b)
-    works = []
-    for bk in range(len(eng.buckets)):
-      g = eng.step_backward(bk)
-      works.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, async_op=True))
-    for w in works:
-      w.wait()
-    eng.step_update(1.0 / world)
-    return eng.out_losses
+    return parallel.data_parallel_step(eng, b, b)
 
   def barrier():
     torch.cuda.synchronize()
@@ -223,13 +238,15 @@ def run_ours(args):
     sampler.start()
   lib.geeco_launch_count(1)
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_wall0 = time.time()
   ev0.record()
   for i in range(args.steps):
     step_dev(i)
   ev1.record()
   barrier()
+  t_wall1 = time.time()
   launches = int(lib.geeco_launch_count(1))
-  clocks = sampler.stop() if rank == 0 else None
+  clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
   ms = ev0.elapsed_time(ev1)
   t = torch.tensor([ms], dtype=torch.float64, device=dev)
   if world > 1:
@@ -238,31 +255,23 @@ def run_ours(args):
   final_loss = float(eng.out_losses[5].item())
   value = world * N * args.steps / (ms * 1e-3)
 
-  # ---- end-to-end through the public API with HOST (pinned) inputs, loss read back every step
+  # ---- end to end through the public training entry: Estimator.train(input_fn) over HOST batches
   e2e = None
   if not args.no_e2e:
-    def step_host(i):
-      hb = host_batches[i % NB]
-      if world == 1:
-        losses = eng.train_step(hb, hb)
-      else:
-        eng.step_forward(hb, hb)
-        works = []
-        for bk in range(len(eng.buckets)):
-          works.append(dist.all_reduce(eng.step_backward(bk), op=dist.ReduceOp.SUM, async_op=True))
-        for w in works:
-          w.wait()
-        eng.step_update(1.0 / world)
-        losses = eng.out_losses
-      return losses.cpu()      # device -> host read of the step's result (32 bytes)
-    for i in range(max(1, min(args.warmup, 3))):
-      step_host(i)
+    n_e2e = max(3, min(args.steps, 12))
+    mdir = tempfile.mkdtemp(prefix='geeco_bench_')
+    est = Estimator(goal_e2evmc_model_fn, mdir, RunConfig(save_checkpoints_steps=0, keep_checkpoint_max=1),
+                    {'e2evmc_config': cfg, 'log_steps': 1, 'debug': False, 'save_final_checkpoint': False},
+                    precision=args.precision, batch_size=N)
+    est._engine = eng                      # same replica; Estimator drives it through model_fn
+
+    def host_input(n):
+      return lambda: ((host_batches[i % NB], host_batches[i % NB]) for i in range(n))
+    est.train(host_input(2), steps=2)      # warm-up (allocates staging buffers)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_e2e = max(3, min(args.steps, 10))
     e0.record()
-    for i in range(n_e2e):
-      step_host(i)
+    est.train(host_input(n_e2e), steps=n_e2e)          # log_steps=1: losses are read back to the host every step
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -270,13 +279,14 @@ def run_ours(args):
       dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e = {'value': world * N * n_e2e / (float(t2.item()) * 1e-3), 'unit': UNIT,
            'h2d_bytes_per_step': eng.h2d_bytes(True), 'd2h_bytes_per_step': 32, 'steps': n_e2e,
-           'api': 'geeco_b200.engine.Engine.train_step(host pinned features, labels) -> losses.cpu()'}
+           'api': 'geeco_b200.estimator.Estimator.train(input_fn over pinned host batches), log_steps=1'}
 
   peaks = load_peaks()
   roofline, extra = kernel_rooflines(eng, dev, peaks, args) if (rank == 0 and not args.no_kernels) else (None, None)
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     cpu_baseline = time_cpu_reference(args.cpu_batch, 5, 2)
+  extras = run_extras(eng, dev, peaks, args) if (args.extras and rank == 0 and world == 1) else None
 
   if rank == 0:
     line = {
@@ -291,71 +301,139 @@ def run_ours(args):
         'step_tflops': value * FLOP_PER_SAMPLE_TRAIN / 1e12,
         'final_loss': final_loss,
         'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roofline, 'kernels': extra,
-        'cpu_baseline': cpu_baseline, 'peaks': peaks,
+        'cpu_baseline': cpu_baseline, 'peaks': peaks, 'extras': extras,
     }
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
 
 
+def _timed(dev, fn, reps=5, flush=None):
+  import torch
+  fn(); torch.cuda.synchronize()
+  ts = []
+  for _ in range(reps):
+    if flush is not None:
+      flush.fill_(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+  return float(np.mean(ts)) * 1e-3
+
+
 def kernel_rooflines(eng, dev, peaks, args):
-  """Times the dominant kernels in isolation with CUDA events (inputs > L2 or L2 flushed between reps)."""
+  """Times the hot kernels in isolation with CUDA events (L2 flushed between repetitions).  Algorithmic bytes
+  per launch are the figures of DESIGN.md "Kernels"; traffic comes from the committed ncu captures."""
   import torch
   from geeco_b200 import ops
   out = {}
+  traffic = load_traffic()
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+  hbm = peaks['hbm_gbs']
 
-  def timed(fn, reps=5):
-    fn(); torch.cuda.synchronize()
-    ts = []
-    for _ in range(reps):
-      flush.fill_(1)
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record(); fn(); b.record()
-      torch.cuda.synchronize()
-      ts.append(a.elapsed_time(b))
-    return float(np.mean(ts)) * 1e-3
+  def entry(name, sec, bytes_alg, flops=None, launches=1):
+    e = {'bound': 'hbm', 'achieved': bytes_alg / sec / 1e9, 'peak': hbm, 'unit': 'GB/s',
+         'frac': bytes_alg / sec / 1e9 / hbm, 'traffic': traffic.get(name), 'kernel': name, 'ms': sec * 1e3,
+         'peak_source': peaks['source'], 'algorithmic_bytes_per_launch': bytes_alg, 'launches_timed': launches}
+    if flops:
+      e['tflops'] = flops / sec / 1e12
+      e['tensor_frac_of_burst'] = flops / sec / 1e12 / peaks['bf16_tflops']
+    out[name] = e
+    return e
 
   # rank pooling: dynimg over K=4 frames, 256 samples of 256x256x3 (805 MB in, 201 MB out)
   Nr, K, H, W, C = 256, 4, 256, 256, 3
   x = torch.rand((Nr, K, H, W, C), device=dev)
   y = torch.empty((Nr, H, W, C), device=dev)
-  sec = timed(lambda: ops.dynimg(x, out=y))
-  bytes_alg = (K + 1) * H * W * C * 4 * Nr
-  out['dynimg_cluster_kernel<4>'] = {'bound': 'hbm', 'achieved': bytes_alg / sec / 1e9, 'peak': peaks['hbm_gbs'],
-                                     'unit': 'GB/s', 'frac': bytes_alg / sec / 1e9 / peaks['hbm_gbs'], 'traffic': None,
-                                     'peak_source': peaks['source'], 'ms': sec * 1e3,
-                                     'algorithmic_bytes_per_launch': bytes_alg}
+  sec = _timed(dev, lambda: ops.dynimg(x, out=y), flush=flush)
+  entry('dynimg_cluster_kernel<4>', sec, (K + 1) * H * W * C * 4 * Nr)
   del x, y
-  dom = dominant_kernel_roofline(eng, dev, peaks, timed, args)
-  out.update(dom[1])
-  return dom[0], out
+  if args.precision != 'bf16':
+    N3 = 3 * args.batch
+    x = torch.rand((N3, 256, 256, 32), device=dev)
+    w = ((torch.rand((3, 3, 32, 48), device=dev) - 0.5) * 0.2)
+    b = torch.zeros(48, device=dev)
+    sec = _timed(dev, lambda: ops.conv2d_same(x, w, b, stride=2), flush=flush)
+    dom = entry('gemm_nn_f32_kernel<3> conv2 fwd', sec, N3 * (256 * 256 * 32 + 128 * 128 * 48) * 4,
+                2.0 * N3 * 128 * 128 * 48 * 288)
+    return dom, out
+  N3 = 3 * args.batch
+  # conv1 (4-channel padded input 256x256 -> 32 ch) and conv2 (32 -> 48, stride 2): the HBM-bound bulk of the step
+  x1 = torch.rand((N3, 256, 256, 4), device=dev).to(torch.bfloat16); x1[..., 3] = 0
+  w1 = ((torch.rand((3, 3, 3, 32), device=dev) - 0.5) * 0.2)
+  b1 = torch.zeros(32, device=dev)
+  g1 = (torch.rand((N3, 256, 256, 32), device=dev) - 0.5).to(torch.bfloat16)
+  sec = _timed(dev, lambda: ops.conv2d_same_bf16(x1, w1, b1, stride=1), flush=flush)
+  entry('tc_nn_kernel<4> conv1 fwd', sec, N3 * 65536 * (4 + 32) * 2, 2.0 * N3 * 65536 * 32 * 27)
+  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x1, w1, g1, stride=1, need_dx=False), flush=flush)
+  dom = entry('tc_wgrad_kernel<4> conv1 wgrad', sec, N3 * 65536 * (4 + 32) * 2, 2.0 * N3 * 65536 * 32 * 27, launches=2)
+  x2 = g1
+  w2 = ((torch.rand((3, 3, 32, 48), device=dev) - 0.5) * 0.2)
+  b2 = torch.zeros(48, device=dev)
+  sec = _timed(dev, lambda: ops.conv2d_same_bf16(x2, w2, b2, stride=2), flush=flush)
+  entry('tc_nn_kernel<8> conv2 fwd', sec, N3 * (65536 * 32 + 16384 * 48) * 2, 2.0 * N3 * 16384 * 48 * 288)
+  g2 = (torch.rand((N3, 128, 128, 48), device=dev) - 0.5).to(torch.bfloat16)
+  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_x=x2), flush=flush)
+  entry('conv2 wgrad + fused dgrad', sec, N3 * ((65536 * 32 + 16384 * 48) + (16384 * 48 + 2 * 65536 * 32)) * 2,
+        2.0 * 2 * N3 * 16384 * 48 * 288, launches=8)
+  # a tensor-bound layer for the tensor-pipe view: conv5 (128 -> 192, 32x32 -> 16x16)
+  x5 = torch.rand((N3, 32, 32, 128), device=dev).to(torch.bfloat16)
+  w5 = ((torch.rand((3, 3, 128, 192), device=dev) - 0.5) * 0.1)
+  b5 = torch.zeros(192, device=dev)
+  sec = _timed(dev, lambda: ops.conv2d_same_bf16(x5, w5, b5, stride=2), flush=flush)
+  e5 = entry('tc_nn_kernel<8> conv5 fwd', sec, N3 * (1024 * 128 + 256 * 192) * 2 + 192 * 1152 * 2, 2.0 * N3 * 256 * 192 * 1152)
+  e5['bound'] = 'tensor'
+  return dom, out
 
 
-def dominant_kernel_roofline(eng, dev, peaks, timed, args):
-  """conv2 forward of the three encoders (39.8 % of the step's FLOPs) at the bench batch."""
+def run_extras(eng, dev, peaks, args):
+  """BASELINE config 4 (batched closed-loop policy steps) and config 5 (rank-pooling sweep)."""
   import torch
   from geeco_b200 import ops
-  N = 3 * args.batch
-  if args.precision == 'bf16' and hasattr(ops, 'conv2d_same_bf16'):
-    x = (torch.rand((N, 256, 256, 32), device=dev)).to(torch.bfloat16)
-    w = ((torch.rand((3, 3, 32, 48), device=dev) - 0.5) * 0.2)
-    b = torch.zeros(48, device=dev)
-    sec = timed(lambda: ops.conv2d_same_bf16(x, w, b, stride=2))
-    name, dt = 'conv_tc fwd conv2 (32->48, s2, 256px)', 2
-  else:
-    x = torch.rand((N, 256, 256, 32), device=dev)
-    w = ((torch.rand((3, 3, 32, 48), device=dev) - 0.5) * 0.2)
-    b = torch.zeros(48, device=dev)
-    sec = timed(lambda: ops.conv2d_same(x, w, b, stride=2))
-    name, dt = 'gemm_nn_f32_kernel<3> conv2 fwd (32->48, s2, 256px)', 4
-  flops = 2.0 * N * 128 * 128 * 48 * 288
-  bytes_alg = N * (256 * 256 * 32 + 128 * 128 * 48) * dt
-  r_hbm = {'bound': 'hbm', 'achieved': bytes_alg / sec / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-           'frac': bytes_alg / sec / 1e9 / peaks['hbm_gbs'], 'traffic': None, 'kernel': name, 'ms': sec * 1e3,
-           'peak_source': peaks['source'], 'algorithmic_bytes_per_launch': bytes_alg,
-           'tensor_tflops': flops / sec / 1e12, 'tensor_frac_of_burst': flops / sec / 1e12 / peaks['bf16_tflops']}
-  return r_hbm, {name: r_hbm}
+  from geeco_b200.predictor import BatchedGoalPredictor
+  res = {}
+  # ---- config 5: dynimg K=2..16 x {128,256,512} px, inputs >= 1 GiB
+  sweep = []
+  for px in (128, 256, 512):
+    for K in (2, 3, 4, 6, 8, 12, 16):
+      per = K * px * px * 3 * 4
+      n = max(2, int(2 ** 30 // per) + 1)
+      n = min(n, 60000)
+      x = torch.rand((n, K, px, px, 3), device=dev)
+      y = torch.empty((n, px, px, 3), device=dev)
+      sec = _timed(dev, lambda: ops.dynimg(x, out=y), reps=3)
+      gbs = (K + 1) * px * px * 3 * 4 * n / sec / 1e9
+      sweep.append({'px': px, 'K': K, 'N': n, 'GBps': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm_gbs']})
+      del x, y
+  res['rankpool_sweep'] = sweep
+  # ---- config 4: 4096 environments, processed as 4 chunks of 1024 (device-resident frame rings)
+  total_envs, chunk = 4096, 1024
+  cfg = eng.cfg
+  bp = BatchedGoalPredictor(cfg, chunk, precision=args.precision, carry_state=True)
+  bp.engine.theta.copy_(eng.theta); bp.engine.params_changed()
+  goals = torch.rand((chunk, 256, 256, 3), device=dev)
+  bp.set_goal(goals)
+  frames = [torch.rand((chunk, 256, 256, 3), device=dev) for _ in range(2)]
+  jn = torch.rand((chunk, 7), device=dev)
+  for i in range(2):
+    bp.predict_batch(frames[i % 2], jn)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  steps = 3
+  e0.record()
+  for s in range(steps):
+    for c in range(total_envs // chunk):
+      out = bp.predict_batch(frames[(s + c) % 2], jn)
+  e1.record()
+  torch.cuda.synchronize()
+  sec = e0.elapsed_time(e1) * 1e-3 / steps
+  res['policy_steps'] = {'envs': total_envs, 'chunk': chunk, 'ms_per_control_step': sec * 1e3,
+                         'env_steps_per_s': total_envs / sec, 'tflops': total_envs * 3.415e9 / sec / 1e12,
+                         'carry_state': True, 'note': 'MuJoCo stepping excluded; frames synthetic, device resident'}
+  with open(os.path.join(ROOT, 'profiles', 'r01_extras.json'), 'w') as fp:
+    json.dump(res, fp, indent=1)
+  return res
 
 
 def main():

@@ -208,6 +208,53 @@ class Engine(object):
     self._dev_in[key].copy_(self._pin_in[key], non_blocking=True)
     return self._dev_in[key]
 
+  # ---- double-buffered staging: upload batch i+1 on a copy stream while batch i computes -------------
+  def stage(self, features, labels, slot):
+    """Starts the host->device copy of one (features, labels) batch into staging slot 0/1 on the copy stream.
+    Returns (device_features, device_labels, ready_event); pass the event to `wait_staged` before the step."""
+    if not hasattr(self, '_stage_bufs'):
+      self._stage_bufs = [{}, {}]
+      self._stage_free = [None, None]
+      self._copy_stream = torch.cuda.Stream(device=self.device)
+    bufs = self._stage_bufs[slot]
+    shapes = self._shapes()
+    out = {}
+    with torch.cuda.stream(self._copy_stream):
+      if self._stage_free[slot] is not None:
+        self._copy_stream.wait_event(self._stage_free[slot])      # the step that last read this slot is done
+      items = [(k, features[k]) for k in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state') if k in features]
+      if labels is not None:
+        items.append(('cmd', labels['cmd']))
+      for k, v in items:
+        if torch.is_tensor(v) and v.is_cuda:
+          out[k] = v
+          continue
+        t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
+        if tuple(t.shape) != shapes[k]:
+          raise ValueError("%s: expected shape %s, got %s" % (k, shapes[k], tuple(t.shape)))
+        if k not in bufs:
+          bufs[k] = torch.empty(shapes[k], dtype=torch.float32, device=self.device)
+        if not (t.dtype == torch.float32 and t.is_pinned()):
+          if (k, slot) not in self._pin_in:
+            self._pin_in[(k, slot)] = torch.empty(shapes[k], dtype=torch.float32).pin_memory()
+          pin = self._pin_in[(k, slot)]
+          pin.copy_(t)
+          t = pin
+        bufs[k].copy_(t, non_blocking=True)
+        out[k] = bufs[k]
+      ev = torch.cuda.Event()
+      ev.record(self._copy_stream)
+    return out, ({'cmd': out['cmd']} if labels is not None else None), ev
+
+  def wait_staged(self, event, slot):
+    torch.cuda.current_stream(self.device).wait_event(event)
+
+  def release_staged(self, slot):
+    """Call after enqueueing the step that consumed `slot`: the next upload into it waits for that step."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(self.device))
+    self._stage_free[slot] = ev
+
   def h2d_bytes(self, with_labels=True):
     keys = list(_FEATURE_KEYS) + (['cmd'] if with_labels else [])
     if not with_labels:

@@ -175,7 +175,7 @@ class Estimator(object):
     p = dict(self.params, engine=eng)
     done, self.last_train_losses = 0, []
     log_steps = int(self.params.get('log_steps', 1000) or 1000)
-    for features, labels in input_fn():
+    for features, labels in self._prefetched(eng, input_fn()):
       self._check_batch(features)
       spec = self._model_fn(features, labels, ModeKeys.TRAIN, p)
       done += 1
@@ -187,9 +187,32 @@ class Estimator(object):
         save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
       if steps is not None and done >= steps:
         break
-    if rank == 0:
+    if rank == 0 and self.params.get('save_final_checkpoint', True):
       save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
     return self
+
+  @staticmethod
+  def _prefetched(eng, batches):
+    """Yields device-resident batches; the upload of batch i+1 (pinned host -> device, copy stream) overlaps
+    the step of batch i.  Device tensors yielded by input_fn pass through untouched."""
+    it = iter(batches)
+    slot = 0
+    try:
+      f, l = next(it)
+    except StopIteration:
+      return
+    cur = eng.stage(f, l, slot)
+    while cur is not None:
+      try:
+        f, l = next(it)
+        nxt = eng.stage(f, l, slot ^ 1)
+      except StopIteration:
+        nxt = None
+      feats, labels, ev = cur
+      eng.wait_staged(ev, slot)
+      yield feats, labels
+      eng.release_staged(slot)
+      cur, slot = nxt, slot ^ 1
 
   def evaluate(self, input_fn, steps=None):
     eng = self.engine
