@@ -38,8 +38,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int PROD_THREADS = 256;
 constexpr int LOOKAHEAD = 2;                          // cp.async groups in flight per producer thread before it signals
 constexpr int NN_THREADS = PROD_THREADS + 128 + 64;   // 448
-constexpr int WG_PROD_THREADS = 512;
-constexpr int WG_THREADS = WG_PROD_THREADS + 128 + 32;   // 672
+
 constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
 constexpr int SUB = 64 * 128;                         // one 64-row x 128-byte sub-tile
 
@@ -380,8 +379,9 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
 // weight-gradient kernel
 //   grid.x = mtile * n_chunks + nchunk ; grid.y = split ; grid.z = group
 // ------------------------------------------------------------------------------------------------
-template <int PIECE>
-__global__ void __launch_bounds__(WG_THREADS, 1)
+// NPROD producer threads: 512 (one CTA per SM, big stages) or 256 (two CTAs per SM when the stage is small)
+template <int PIECE, int NPROD>
+__global__ void __launch_bounds__(NPROD + 160, NPROD == 256 ? 2 : 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
                 int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk) {
@@ -402,9 +402,9 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int EPI_WARP0 = WG_PROD_THREADS / 32, MMA_WARP = EPI_WARP0 + 4;
+  constexpr int EPI_WARP0 = NPROD / 32, MMA_WARP = EPI_WARP0 + 4;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], WG_PROD_THREADS); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
@@ -435,15 +435,16 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   const int nkb = kb_hi - kb_lo;
 
   if (warp < EPI_WARP0) {
-    // ---- G tile mapping: 16-byte chunks, 64 rows in one pass
-    const int g_chunk = threadIdx.x & 7, g_row = threadIdx.x >> 3;
+    // ---- G tile mapping: 16-byte chunks, NPROD/8 rows per pass
+    constexpr int G_ROWS = NPROD / 8, G_PASSES = 64 / G_ROWS;
+    const int g_chunk = threadIdx.x & 7, g_row0 = threadIdx.x >> 3;
     bool g_ok[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) g_ok[j] = j < gsub && (mtile * 128 + j * 64 + g_chunk * 8) < Cout;
     const long long g_col = (long long)mtile * 128 + g_chunk * 8;
     // ---- im2col mapping
     constexpr int PPR = 64 / PIECE;
-    constexpr int ROWS_PER_PASS = WG_PROD_THREADS / PPR;
+    constexpr int ROWS_PER_PASS = NPROD / PPR;
     constexpr int PASSES = 64 / ROWS_PER_PASS;
     const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
@@ -478,7 +479,9 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
       const uint32_t sb = smem_u32(st_base + s * stage_bytes);
       const uint32_t mb = (uint32_t)(kb_lo + it) * 64;
       // G tile: rows = pixels, up to 128 output channels of this M tile
-      {
+#pragma unroll
+      for (int gp_i = 0; gp_i < G_PASSES; ++gp_i) {
+        const int g_row = gp_i * G_ROWS + g_row0;
         const uint32_t m = mb + g_row;
         const bool rvalid = m < Mg;
         const uint32_t roff = g_row * 128 + ((g_chunk ^ (g_row & 7)) << 4);
@@ -897,7 +900,7 @@ int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* 
   return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st);
 }
 
-struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols; };
+struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols, per_sm; };
 
 static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   WgradPlan p;
@@ -912,11 +915,14 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   p.total_kb = (int)((Mg + 63) / 64);
   p.gsub = Cout > 64 ? 2 : 1;
   const int stage_bytes = (2 + p.nsub_chunk) * SUB;
-  p.stages = (int)((SMEM_BUDGET - 1024 - 512) / stage_bytes);
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.tmem_cols = p.nsub_chunk > 4 ? 512 : (p.nsub_chunk > 2 ? 256 : 128);
+  // small stages: two CTAs per SM with 256 producer threads each and a 4-deep ring (measured better than one
+  // CTA with a deeper ring, as for the forward kernel)
+  p.per_sm = (p.tmem_cols <= 256 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  p.stages = (int)((SMEM_BUDGET / p.per_sm - 1024 - 512) / stage_bytes);
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int base = p.m_tiles * p.n_chunks * g.groups;
-  int want = (num_sms() + base - 1) / base;
+  int want = (num_sms() * p.per_sm + base - 1) / base;
   if (want < 1) want = 1;
   if (want > p.total_kb) want = p.total_kb;
   p.kb_per_split = (p.total_kb + want - 1) / want;
@@ -951,17 +957,19 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
   const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_chunk) * SUB + 512;
   const int ones = dbias ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
-  if (g.Cs == 4) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<4><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
-                                                       p.Mrows_pad, ones, p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_wgrad_kernel<8><<<grid, WG_THREADS, smem, st>>>(g, src, G, partial, Cout, p.n_chunks, p.kb_per_split, p.total_kb,
-                                                       p.Mrows_pad, ones, p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);
-  }
+#define WG_LAUNCH(PIECE_, NPROD_)                                                                                   \
+  do {                                                                                                              \
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<PIECE_, NPROD_>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
+                                  cudaSharedmemCarveoutMaxShared));                                                 \
+    CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<PIECE_, NPROD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)smem));                                                                      \
+    tc_wgrad_kernel<PIECE_, NPROD_><<<grid, NPROD_ + 160, smem, st>>>(g, src, G, partial, Cout, p.n_chunks,          \
+                                                                      p.kb_per_split, p.total_kb, p.Mrows_pad, ones, \
+                                                                      p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);  \
+  } while (0)
+  if (g.Cs == 4) { if (p.per_sm == 2) WG_LAUNCH(4, 256); else WG_LAUNCH(4, 512); }
+  else { if (p.per_sm == 2) WG_LAUNCH(8, 256); else WG_LAUNCH(8, 512); }
+#undef WG_LAUNCH
   const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
   int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
   wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
