@@ -677,6 +677,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
   }
 }
 
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs,
+                                                                   long long grand_total) {
+  __shared__ long long s_start[65];
+  for (int j = threadIdx.x; j <= njobs && j <= 64; j += blockDim.x) s_start[j] = j < njobs ? jobs[j].start : grand_total;
+  __syncthreads();
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < grand_total; gi += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_start[mid] <= gi) lo = mid; else hi = mid - 1; }
+    const PackJob& jb = jobs[lo];
+    const long long i = gi - jb.start;
+    const int k = (int)(i % jb.Kpad);
+    const long long rr = i / jb.Kpad;
+    const int r = (int)(rr % jb.rows), grp = (int)(rr / jb.rows);
+    float v = 0.f;
+    const int per_tap = jb.mode == 0 ? jb.Cs : jb.Cout;
+    const int t = k / per_tap, c = k - t * per_tap;
+    if (t < jb.ntaps) {
+      const float* Wg = jb.W + (long long)grp * jb.w_group_stride + (long long)jb.taps[t] * jb.Cin * jb.Cout;
+      if (jb.mode == 0) { if (c < jb.Cin && r < jb.Cout) v = Wg[(long long)c * jb.Cout + r]; }
+      else              { if (r < jb.Cin) v = Wg[(long long)r * jb.Cout + c]; }
+    }
+    jb.out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
@@ -924,7 +949,7 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   const int base = p.m_tiles * p.n_chunks * g.groups;
   int want = (num_sms() * p.per_sm + base - 1) / base;
   if (want < 1) want = 1;
-  if (want > p.total_kb) want = p.total_kb;
+  if (want > p.total_kb / 8) want = p.total_kb / 8 > 0 ? p.total_kb / 8 : 1;     // >= 8 k-blocks per split
   p.kb_per_split = (p.total_kb + want - 1) / want;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.Mrows_pad = p.m_tiles * 128;
@@ -995,6 +1020,16 @@ int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups
   int blocks = ceil_div(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_kernel<<<blocks, 256, 0, st>>>(W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad,
                                               t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st) {
+  if (njobs <= 0 || grand_total <= 0) return GEECO_OK;
+  if (njobs > 64) { geeco_set_error("pack_weights_batched: %d jobs > 64", njobs); return GEECO_ERR_INVALID; }
+  int blocks = ceil_div(grand_total, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weights_batched_kernel<<<blocks, 256, 0, st>>>(jobs_dev, njobs, grand_total);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

@@ -48,6 +48,12 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
 //                       mode 1 (dgrad): out[g][ci][t*Cout + co] = W[g][tap_t][ci][co] ; rows = Cin
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
                         int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, cudaStream_t st);
+// all weight repacks of a step as ONE launch: a table of jobs in device memory
+struct PackJob {
+  const float* W; __nv_bfloat16* out; long long w_group_stride; long long start; long long total;
+  int mode, groups, Cin, Cout, Cs, ntaps, rows, Kpad; int taps[9]; int pad_;
+};
+int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
 // 2-D tensor map over a packed weight matrix [rows_total][Kpad] bf16, box = 64 x box_rows, SWIZZLE_128B

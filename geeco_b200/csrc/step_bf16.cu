@@ -5,6 +5,7 @@
 #include "conv_tc.cuh"
 
 #include <string.h>
+#include <vector>
 
 struct Bf16Layer {
   TcGeom fwd;                          // forward geometry (also the wgrad geometry)
@@ -21,6 +22,10 @@ struct Bf16Plan {
   Bf16Layer L[8];
   float* partial;
   long long partial_cap;
+  PackJob* jobs_dev;          // table of weight-repack jobs (uploaded at the first repack after bind)
+  std::vector<PackJob> jobs;
+  long long jobs_total;
+  bool jobs_uploaded;
 };
 
 static void* carve(size_t* off, char* base, size_t bytes) {
@@ -81,6 +86,8 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   }
   bp->partial_cap = cap;
   bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
+  bp->jobs_dev = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
+  bp->jobs_uploaded = false;
   if (!ws_base) return GEECO_OK;
   // tensor maps (need the real addresses)
   for (int l = 0; l < 8; ++l) {
@@ -114,27 +121,48 @@ void free_bf16(geeco_ctx* c) {
 
 static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
+static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, int groups, long long wstride, int Cin,
+                    int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad) {
+  PackJob j;
+  memset(&j, 0, sizeof(j));
+  j.W = W; j.out = out; j.w_group_stride = wstride; j.mode = mode; j.groups = groups; j.Cin = Cin; j.Cout = Cout;
+  j.Cs = Cs; j.ntaps = ntaps; j.rows = rows; j.Kpad = Kpad;
+  for (int i = 0; i < ntaps && i < 9; ++i) j.taps[i] = taps[i];
+  j.start = bp->jobs_total;
+  j.total = (long long)groups * rows * Kpad;
+  bp->jobs_total += j.total;
+  bp->jobs.push_back(j);
+}
+
+// fp32 master weights -> packed bf16 operands of every conv layer (forward + the data-gradient classes): one launch
 static int repack_weights(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
-  for (int l = 0; l < 8; ++l) {
-    LayerPlan& L = c->layers[l];
-    Bf16Layer& B = bp->L[l];
-    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
-    const int ne = L.grouped ? 1 : 3;
-    for (int e = 0; e < ne; ++e) {
-      const int groups = L.grouped ? 3 : 1;
-      const float* W = c->theta + c->params[L.p_w[e]].offset;
-      int rc = launch_pack_weights(W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps,
-                                   L.Cout[e], B.fwd.Kpad, st);
-      if (rc) return rc;
-      for (int ci = 0; ci < B.n_classes; ++ci) {
-        const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
-        rc = launch_pack_weights(W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps,
-                                 B.dg_taps[ci], L.Cin_real, Kp, st);
-        if (rc) return rc;
+  if (!bp->jobs_uploaded) {
+    bp->jobs.clear();
+    bp->jobs_total = 0;
+    for (int l = 0; l < 8; ++l) {
+      LayerPlan& L = c->layers[l];
+      Bf16Layer& B = bp->L[l];
+      const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
+      const int ne = L.grouped ? 1 : 3;
+      for (int e = 0; e < ne; ++e) {
+        const int groups = L.grouped ? 3 : 1;
+        const float* W = c->theta + c->params[L.p_w[e]].offset;
+        add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad);
+        for (int ci = 0; ci < B.n_classes; ++ci) {
+          const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
+          add_job(bp, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
+                  L.Cin_real, Kp);
+        }
       }
     }
+    if (bp->jobs.size() > 64) { geeco_set_error("repack: %zu jobs > 64", bp->jobs.size()); return GEECO_ERR_INVALID; }
+    CUDA_TRY(cudaMemcpyAsync(bp->jobs_dev, bp->jobs.data(), bp->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    bp->jobs_uploaded = true;
   }
+  int rc = launch_pack_weights_batched(bp->jobs_dev, (int)bp->jobs.size(), bp->jobs_total, st);
+  if (rc) return rc;
   c->weights_dirty = false;
   return GEECO_OK;
 }
