@@ -35,9 +35,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
-constexpr int PROD_THREADS = 256;
 constexpr int LOOKAHEAD = 2;                          // cp.async groups in flight per producer thread before it signals
-constexpr int NN_THREADS = PROD_THREADS + 128 + 64;   // 448
+constexpr int NN_THREADS = 12 * 32 + 64;   // producer + epilogue warps (12), MMA warp, TMA warp
 
 constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
 constexpr int SUB = 64 * 128;                         // one 64-row x 128-byte sub-tile
@@ -108,7 +107,9 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 // ------------------------------------------------------------------------------------------------
 // forward / data-gradient kernel.  PIECE = bf16 elements per cp.async (8 -> 16 B, 4 -> 8 B)
 // ------------------------------------------------------------------------------------------------
-template <int PIECE>
+// NPW gather-producer warps and 12 - NPW epilogue warps (8/4 by default; 4/8 when the epilogue is the bottleneck:
+// one k-block per tile as in conv1), then the MMA warp and the TMA warp
+template <int PIECE, int NPW>
 __global__ void __launch_bounds__(NN_THREADS, 2)
 tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
@@ -127,12 +128,20 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   uint64_t* tmem_empty = tmem_full + 8;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tmem_empty + 8);
 
+  constexpr int PROD_THREADS = NPW * 32;
+  constexpr int EPI_THREADS = (12 - NPW) * 32;
+  constexpr int NHALF = (12 - NPW) / 4;            // epilogue warps per TMEM lane quadrant (column interleave)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS + 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
     fence_barrier_init();
   }
+  // bias of every group staged once in shared memory (epilogue reads it per tile)
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (bias_all)
+    for (int i = threadIdx.x; i < g.groups * BN; i += blockDim.x)
+      bias_s[i] = bias_all[(long long)(i / BN) * g.bias_group_stride + (i % BN)];
   // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
   // they hold later is finite data (multiplied by zero weights)
   zero_smem(a_base, stages * A_STAGE_BYTES);
@@ -151,7 +160,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   // work item j of this CTA: flat tile (j / ncls) * gridDim.x + blockIdx.x, class j % ncls  -> the classes
   // of one tile run back to back (their source rows and destination lines are shared)
 
-  if (warp < 8) {
+  if (warp < NPW) {
     // ===================== A producers: implicit-im2col gather =====================
     constexpr int PPR = BK / PIECE;                 // pieces per 128-byte row
     constexpr int ROWS_PER_PASS = PROD_THREADS / PPR;
@@ -162,22 +171,30 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     if (PIECE == 4 && g.rowwin) {
       // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
       // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
-      // everything that does not depend on the tile is hoisted: thread t owns row (t & 127) for ky = t >> 7
-      // (0 or 1) and, if t < 128, also ky = 2; the three destination byte offsets per (row, ky) are constants
+      // everything that does not depend on the tile is hoisted: thread t owns the (row, ky) pairs p = t + i*PROD,
+      // row = p & 127, ky = p >> 7; the three destination byte offsets and the source offset per pair are constants
       const TcCls& k0 = cl.c[0];
-      const int row = threadIdx.x & (BM - 1);
-      const int kyA = threadIdx.x >> 7;
-      const bool hasB = threadIdx.x < BM;
-      uint32_t dA[3], dB[3];
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const uint32_t ba = (uint32_t)(kyA * 24 + kx * 8), bb = (uint32_t)(2 * 24 + kx * 8);
-        dA[kx] = row * 128 + (((ba >> 4) ^ (uint32_t)(row & 7)) << 4) + (ba & 15u);
-        dB[kx] = row * 128 + (((bb >> 4) ^ (uint32_t)(row & 7)) << 4) + (bb & 15u);
-      }
-      const int dyA = k0.dy[kyA * 3], dyB = k0.dy[6], dx0 = k0.dx[0];
+      constexpr int NP = (3 * BM + PROD_THREADS - 1) / PROD_THREADS;
+      uint32_t dst_off[NP][3];
+      long long src_off[NP];
+      int pdy[NP], prow[NP];
+      bool pvalid[NP];
+      const int dx0 = k0.dx[0];
       const int Hs = g.Hs, Ws = g.Ws, ipg = g.imgs_per_group, hw_shift = g.hw_shift, w_shift = g.w_shift;
-      const long long offA = ((long long)dyA * Ws + row + dx0) * 4, offB = ((long long)dyB * Ws + row + dx0) * 4;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const int p = threadIdx.x + i * PROD_THREADS;
+        pvalid[i] = p < 3 * BM;
+        const int row = p & (BM - 1), ky = pvalid[i] ? (p >> 7) : 0;
+        prow[i] = row;
+        pdy[i] = k0.dy[ky * 3];
+        src_off[i] = ((long long)pdy[i] * Ws + row + dx0) * 4;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t bb = (uint32_t)(ky * 24 + kx * 8);
+          dst_off[i][kx] = row * 128 + (((bb >> 4) ^ (uint32_t)(row & 7)) << 4) + (bb & 15u);
+        }
+      }
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x, ++it) {
         const int group = flat / tiles_per_group;
         const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
@@ -189,21 +206,16 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
         // pointer to pixel (y, x0) of the image; every copy is this plus a per-thread constant
         const __nv_bfloat16* pix = src + ((long long)((group * ipg + img) * Hs + y) * Ws + x0) * 4;
-        const int xl = x0 + row + dx0;                       // leftmost source column of this row's window
-        const bool in0 = xl >= 0, in2 = xl + 2 < Ws;         // kx = 1 is always inside (Ws >= 2)
-        {
-          const bool okr = (unsigned)(y + dyA) < (unsigned)Hs;
-          const __nv_bfloat16* sp = pix + offA;
-          cp_async8(a_s + dA[0], (okr && in0) ? (const void*)sp : (const void*)src, (okr && in0) ? 8u : 0u);
-          cp_async8(a_s + dA[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
-          cp_async8(a_s + dA[2], (okr && in2) ? (const void*)(sp + 8) : (const void*)src, (okr && in2) ? 8u : 0u);
-        }
-        if (hasB) {
-          const bool okr = (unsigned)(y + dyB) < (unsigned)Hs;
-          const __nv_bfloat16* sp = pix + offB;
-          cp_async8(a_s + dB[0], (okr && in0) ? (const void*)sp : (const void*)src, (okr && in0) ? 8u : 0u);
-          cp_async8(a_s + dB[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
-          cp_async8(a_s + dB[2], (okr && in2) ? (const void*)(sp + 8) : (const void*)src, (okr && in2) ? 8u : 0u);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          if (!pvalid[i]) continue;
+          const int xl = x0 + prow[i] + dx0;                       // leftmost source column of this row's window
+          const bool okr = (unsigned)(y + pdy[i]) < (unsigned)Hs;
+          const bool ok0 = okr && xl >= 0, ok2 = okr && xl + 2 < Ws;   // kx = 1 is always inside (Ws >= 2)
+          const __nv_bfloat16* sp = pix + src_off[i];
+          cp_async8(a_s + dst_off[i][0], ok0 ? (const void*)sp : (const void*)src, ok0 ? 8u : 0u);
+          cp_async8(a_s + dst_off[i][1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
+          cp_async8(a_s + dst_off[i][2], ok2 ? (const void*)(sp + 8) : (const void*)src, ok2 ? 8u : 0u);
         }
         cp_async_mbar_arrive_noinc(&full[s]);
       }
@@ -255,7 +267,9 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     }
   } else if (warp < 12) {
     // ===================== epilogue: TMEM -> registers -> global =====================
+    // warp w reads TMEM lanes [32*(w&3), +32) (hardware rule) and the 16-column chunks c0 = 16*(NHALF*i + half)
     const int q = warp & 3;
+    const int half = (warp - NPW) >> 2;
     const int row = q * 32 + lane;
     uint32_t tl = 0;
     for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
@@ -264,7 +278,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
       const bool valid = m < Mg;
       int img = 0, y = 0, x = 0;
       if (valid) decode_pixel(g, m, img, y, x);
-      const float* bias = bias_all ? bias_all + (long long)group * g.bias_group_stride : nullptr;
+      const float* bias = bias_s + group * BN;
       for (int c = 0; c < ncls; ++c, ++tl) {
         const TcCls& kc = cl.c[c];
         const int buf = tl % nbuf;
@@ -273,7 +287,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         mbar_wait(&tmem_full[buf], (tl / nbuf) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = half * 16; c0 < BN; c0 += 16 * NHALF) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
@@ -285,7 +299,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
               const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 bb = __ldg(b4 + i);
+                const float4 bb = b4[i];
                 f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
               }
               if (epi == TC_EPI_BIAS_RELU) {
@@ -485,7 +499,15 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
         const uint32_t m = mb + g_row;
         const bool rvalid = m < Mg;
         const uint32_t roff = g_row * 128 + ((g_chunk ^ (g_row & 7)) << 4);
-        const __nv_bfloat16* gp = G + ((grow + m) * Cout + g_col);
+        // the G row of GEMM row m is the destination pixel of m (contiguous for forward geometries,
+        // every other column for the conv1 pixel-pair classes)
+        long long gpix = grow + m;
+        if (g.dsx != 1 || g.dsy != 1) {
+          int gi, gy, gx;
+          decode_pixel(g, rvalid ? m : 0u, gi, gy, gx);
+          gpix = ((long long)(group * g.imgs_per_group + gi) * g.Hd + (gy * g.dsy + g.dy0)) * g.Wd + (gx * g.dsx + g.dx0);
+        }
+        const __nv_bfloat16* gp = G + (gpix * Cout + g_col);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
           if (g_ok[j]) cp_async16(sb + j * SUB + roff, rvalid ? (const void*)(gp + j * 64) : (const void*)G, rvalid ? 16u : 0u);
@@ -611,6 +633,38 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// conv1 on pixel pairs: dW[ky][kx][c][co] = sum over the two parity classes and splits of the partial column that
+// holds (ky, kx, c) in that class (see pack_value modes 2/3); bias gradient from the ones column k = 48.
+__global__ void conv1pair_reduce_kernel(const float* __restrict__ part_even, const float* __restrict__ part_odd,
+                                        float* __restrict__ dW, float* __restrict__ dbias, int splits, int groups,
+                                        int Mrows_pad, int Kpad, int Cin, int Cout, long long dw_group_stride,
+                                        long long dbias_group_stride) {
+  const int per_group = (9 * Cin + 1) * Cout;
+  const int total = per_group * groups;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int grp = i / per_group, e = i - grp * per_group;
+    const int kk = e / Cout, co = e - kk * Cout;
+    const long long sstride = (long long)groups * Mrows_pad * Kpad;
+    float s = 0.f;
+    for (int par = 0; par < 2; ++par) {
+      const float* P = (par == 0 ? part_even : part_odd) + ((long long)grp * Mrows_pad + co) * Kpad;
+      int col;
+      if (kk < 9 * Cin) {
+        const int tap = kk / Cin, c = kk - tap * Cin, ky = tap / 3, kx = tap - ky * 3;
+        // kx = 2*dx + p + 1 - par  with dx = j - 1 (even) / j (odd)  ->  2*j + p = kx + 1 (even) / kx (odd)
+        const int q = par == 0 ? kx + 1 : kx;
+        const int j = q >> 1, pp = q & 1;
+        col = (ky * 2 + j) * 8 + pp * 4 + c;
+      } else {
+        col = 48;
+      }
+      for (int sp = 0; sp < splits; ++sp) s += P[sp * sstride + col];
+    }
+    if (kk < 9 * Cin) dW[(long long)grp * dw_group_stride + (long long)kk * Cout + co] = s;
+    else if (dbias) dbias[(long long)grp * dbias_group_stride + co] = s;
+  }
+}
+
 // column sums of a bf16 [rows][C] matrix per group (bias gradient when no padding column exists).
 // stage 1: grid (chunks, groups), 16-byte loads, fixed-order in-block reduction -> part[g][chunk][C];
 // stage 2 adds the chunks in order.  C % 8 == 0, C <= 256.
@@ -656,6 +710,30 @@ __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict_
   }
 }
 
+// value of packed weight element (row r, column k) of a pack job.
+//   mode 0 (forward):       out[n][t*Cs + ch]   = W[tap_t][ch][n]
+//   mode 1 (data gradient): out[ci][t*Cout + co] = W[tap_t][ci][co]
+//   mode 2/3 (conv1 on pixel pairs, even / odd output columns): k = (ky*2 + j)*8 + p*4 + c  ->  W[ky][kx][c][n]
+//            with kx = 2*dx + p + 1 - par, dx = j - 1 (even) or j (odd); columns outside the 3x3 window are zero
+__device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int mode, int Cin, int Cout, int Cs, int ntaps,
+                                            const int* taps, int r, int k) {
+  if (mode >= 2) {
+    const int par = mode - 2;
+    if (k >= 48 || r >= Cout) return 0.f;
+    const int t = k >> 3, e = k & 7, ky = t >> 1, j = t & 1, pp = e >> 2, c = e & 3;
+    const int dx = par == 0 ? j - 1 : j;
+    const int kx = 2 * dx + pp + 1 - par;
+    if (kx < 0 || kx > 2 || c >= Cin) return 0.f;
+    return Wg0[((long long)(ky * 3 + kx) * Cin + c) * Cout + r];
+  }
+  const int per_tap = mode == 0 ? Cs : Cout;
+  const int t = k / per_tap, c = k - t * per_tap;
+  if (t >= ntaps) return 0.f;
+  const float* Wg = Wg0 + (long long)taps[t] * Cin * Cout;
+  if (mode == 0) return (c < Cin && r < Cout) ? Wg[(long long)c * Cout + r] : 0.f;
+  return r < Cin ? Wg[(long long)r * Cout + c] : 0.f;
+}
+
 __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int mode, int groups,
                                     long long w_group_stride, int Cin, int Cout, int Cs, int ntaps, int rows, int Kpad,
                                     int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8) {
@@ -665,14 +743,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
     const int k = (int)(i % Kpad);
     const long long rr = i / Kpad;
     const int r = (int)(rr % rows), grp = (int)(rr / rows);
-    float v = 0.f;
-    const int per_tap = mode == 0 ? Cs : Cout;
-    const int t = k / per_tap, c = k - t * per_tap;
-    if (t < ntaps) {
-      const float* Wg = W + (long long)grp * w_group_stride + (long long)taps[t] * Cin * Cout;
-      if (mode == 0) { if (c < Cin && r < Cout) v = Wg[(long long)c * Cout + r]; }      // row = output channel
-      else           { if (r < Cin) v = Wg[(long long)r * Cout + c]; }                   // row = input channel
-    }
+    const float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, r, k);
     out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -690,14 +761,8 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     const int k = (int)(i % jb.Kpad);
     const long long rr = i / jb.Kpad;
     const int r = (int)(rr % jb.rows), grp = (int)(rr / jb.rows);
-    float v = 0.f;
-    const int per_tap = jb.mode == 0 ? jb.Cs : jb.Cout;
-    const int t = k / per_tap, c = k - t * per_tap;
-    if (t < jb.ntaps) {
-      const float* Wg = jb.W + (long long)grp * jb.w_group_stride + (long long)jb.taps[t] * jb.Cin * jb.Cout;
-      if (jb.mode == 0) { if (c < jb.Cin && r < jb.Cout) v = Wg[(long long)c * jb.Cout + r]; }
-      else              { if (r < jb.Cin) v = Wg[(long long)r * jb.Cout + c]; }
-    }
+    const float v = pack_value(jb.W + (long long)grp * jb.w_group_stride, jb.mode, jb.Cin, jb.Cout, jb.Cs, jb.ntaps,
+                               jb.taps, r, k);
     jb.out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -800,6 +865,32 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   return g;
 }
 
+// conv1 (stride 1, <= 4 input channels stored as 4) on pixel pairs: the source is viewed as [imgs, H, W/2, 8]
+// and the outputs of even / odd columns form two classes with 6 taps (3 dy x 2 pairs) each, K = 48.
+TcGeom tc_conv1pair_geom(int H, int W, int Cout, int imgs_per_group, int groups, int par) {
+  TcGeom g;
+  memset(&g, 0, sizeof(g));
+  g.Hs = H; g.Ws = W / 2; g.Cs = 8; g.Hm = H; g.Wm = W / 2; g.sy = 1; g.sx = 1; g.ntaps = 6;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int j = 0; j < 2; ++j) { g.dy[ky * 2 + j] = ky - 1; g.dx[ky * 2 + j] = par == 0 ? j - 1 : j; }
+  g.Ktot = 48; g.Kpad = 64;
+  g.Nn = Cout; g.Hd = H; g.Wd = W; g.dsy = 1; g.dsx = 2; g.dy0 = 0; g.dx0 = par;
+  g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
+  finish_geom(&g);
+  return g;
+}
+
+int launch_conv1pair_reduce(const float* part_even, const float* part_odd, float* dW, float* dbias, int splits,
+                            int groups, int Mrows_pad, int Kpad, int Cin, int Cout, long long dw_group_stride,
+                            long long dbias_group_stride, cudaStream_t st) {
+  const int total = (9 * Cin + 1) * Cout * groups;
+  conv1pair_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(part_even, part_odd, dW, dbias, splits, groups, Mrows_pad,
+                                                               Kpad, Cin, Cout, dw_group_stride, dbias_group_stride);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
 bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, int groups,
                    TcGeom* out, int* taps_out) {
   TcGeom g;
@@ -885,7 +976,8 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   const int tiles_flat = tiles_per_group * g.groups;
   const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;
   // small-N layers are latency/bandwidth-bound: two CTAs per SM; wide layers: one CTA, deeper ring
-  int per_sm = (g.Nn <= 64 && 2 * (1024 + 4 * stage_bytes + 512) <= (int)SMEM_BUDGET) ? 2 : 1;
+  const int tail_bytes = 512 + g.groups * g.Nn * 4;     // barriers + tmem pointer, bias staging
+  int per_sm = (g.Nn <= 64 && 2 * (1024 + 4 * stage_bytes + tail_bytes) <= (int)SMEM_BUDGET) ? 2 : 1;
   // accumulator ring in TMEM: as many buffers (power of two, <= 8) as fit this CTA's share of the 512 columns
   int nbuf = 2;
   while (nbuf < 8 && 2 * nbuf * g.Nn <= 512 / per_sm) nbuf *= 2;
@@ -893,26 +985,30 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   if (const char* e = getenv("GEECO_TC_PERSM")) { const int v = atoi(e); if (v == 1 || v == 2) per_sm = v; }
   if (const char* e = getenv("GEECO_TC_NBUF")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v * g.Nn <= 512 / per_sm) nbuf = v; }
   const int tmem_cols = next_pow2_cols(nbuf * g.Nn);
-  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - 512) / stage_bytes);
+  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - tail_bytes) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (const char* e = getenv("GEECO_TC_STAGES")) { const int v = atoi(e); if (v >= 3 && v <= stages) stages = v; }
   if (stages < 3) { geeco_set_error("tc_nn: stage of %d bytes does not fit 3 times", stage_bytes); return GEECO_ERR_INVALID; }
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
   int ctas = num_sms() * per_sm;
   if (const char* e = getenv("GEECO_TC_CTAS")) { const int v = atoi(e); if (v > 0) ctas = v; }
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > tiles_flat) ctas = tiles_flat;
-  if (g.Cs == 4) {
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_nn_kernel<4><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    tiles_flat, tmem_cols, stages, nbuf);
-  } else {
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc_nn_kernel<8><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi, tiles_per_group,
-                                                    tiles_flat, tmem_cols, stages, nbuf);
-  }
+  if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }     // experiment: time without output stores
+  // warp split: epilogue-heavy (4 producer / 8 epilogue warps) when a tile has a single k-block
+  int npw = (cl.c[0].Kpad == BK && ncls == 1) ? 4 : 8;
+  if (const char* e = getenv("GEECO_TC_NPW")) { const int v = atoi(e); if (v == 4 || v == 8) npw = v; }
+#define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
+  do {                                                                                                                 \
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
+                                  cudaSharedmemCarveoutMaxShared));                                                    \
+    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_nn_kernel<PIECE_, NPW_><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi,          \
+                                                               tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);  \
+  } while (0)
+  if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
+  else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }
+#undef NN_LAUNCH
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -964,23 +1060,21 @@ long long tc_wgrad_partial_floats(const TcGeom& g, int Cout) {
   return main_part + colsum_part + 64;
 }
 
-int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
-                    float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
-                    long long dbias_group_stride, cudaStream_t st) {
+// runs the weight-gradient GEMM into `partial` ([splits][groups][Mrows_pad][Kpad] fp32)
+static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
+                      long long partial_cap, bool want_ones, WgradPlan* plan_out, cudaStream_t st) {
   if (Cout % 8 || Cout > 256 * 8) { geeco_set_error("tc_wgrad: unsupported Cout=%d", Cout); return GEECO_ERR_INVALID; }
   int rc = check_geom(g, "tc_wgrad");
   if (rc) return rc;
-  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
-  if (Mg <= 0) return GEECO_OK;
   WgradPlan p = wgrad_plan(g, Cout);
-  const long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
+  *plan_out = p;
   if (!partial || tc_wgrad_partial_floats(g, Cout) > partial_cap) {
     geeco_set_error("tc_wgrad: partial buffer too small (%lld floats needed, %lld given)", tc_wgrad_partial_floats(g, Cout), partial_cap);
     return GEECO_ERR_WORKSPACE;
   }
   if (p.stages < 3) { geeco_set_error("tc_wgrad: stage does not fit 3 times"); return GEECO_ERR_INVALID; }
   const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_chunk) * SUB + 512;
-  const int ones = dbias ? p.ones_col : -1;
+  const int ones = want_ones ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
 #define WG_LAUNCH(PIECE_, NPROD_)                                                                                   \
   do {                                                                                                              \
@@ -995,11 +1089,38 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
   if (g.Cs == 4) { if (p.per_sm == 2) WG_LAUNCH(4, 256); else WG_LAUNCH(4, 512); }
   else { if (p.per_sm == 2) WG_LAUNCH(8, 256); else WG_LAUNCH(8, 512); }
 #undef WG_LAUNCH
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+// partial-only variant: the caller performs the reduction (conv1 pixel-pair classes)
+int launch_tc_wgrad_partial(const TcGeom& g, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
+                            long long partial_cap, int want_ones, int* splits_out, int* mrows_out, cudaStream_t st) {
+  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  if (Mg <= 0) { geeco_set_error("tc_wgrad_partial: empty problem"); return GEECO_ERR_INVALID; }
+  WgradPlan p;
+  int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, want_ones != 0, &p, st);
+  if (rc) return rc;
+  *splits_out = p.splits; *mrows_out = p.Mrows_pad;
+  return GEECO_OK;
+}
+
+int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
+                    float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
+                    long long dbias_group_stride, cudaStream_t st) {
+  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  if (Mg <= 0) return GEECO_OK;
+  WgradPlan p;
+  int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st);
+  if (rc) return rc;
+  const long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
+  const int ones = dbias ? p.ones_col : -1;
   const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
   int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
   wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
                                           g.Ktot, ones, dw_group_stride, dbias_group_stride);
-  geeco_count_launch(2);
+  geeco_count_launch(1);
   if (dbias && p.ones_col < 0) {
     if (Cout > 256) { geeco_set_error("tc_wgrad: bias gradient needs Cout <= 256"); return GEECO_ERR_INVALID; }
     float* part = partial + main_part;

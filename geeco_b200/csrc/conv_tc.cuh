@@ -44,6 +44,13 @@ long long tc_wgrad_partial_floats(const TcGeom& g, int Cout);
 int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
                     float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
                     long long dbias_group_stride, cudaStream_t st);
+// conv1 on pixel pairs (see conv_tc.cu): geometry of one output-column parity class, partial-only wgrad, its reduce
+TcGeom tc_conv1pair_geom(int H, int W, int Cout, int imgs_per_group, int groups, int par);
+int launch_tc_wgrad_partial(const TcGeom& g, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
+                            long long partial_cap, int want_ones, int* splits_out, int* mrows_out, cudaStream_t st);
+int launch_conv1pair_reduce(const float* part_even, const float* part_odd, float* dW, float* dbias, int splits,
+                            int groups, int Mrows_pad, int Kpad, int Cin, int Cout, long long dw_group_stride,
+                            long long dbias_group_stride, cudaStream_t st);
 // packed bf16 weights.  mode 0 (fwd): out[g][n][t*Cs + ch] = W[g][tap_t][ch][n] ; rows = Nn
 //                       mode 1 (dgrad): out[g][ci][t*Cout + co] = W[g][tap_t][ci][co] ; rows = Cin
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,

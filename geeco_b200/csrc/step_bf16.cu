@@ -4,6 +4,7 @@
 #include "plan.cuh"
 #include "conv_tc.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -16,6 +17,11 @@ struct Bf16Layer {
   int dg_taps[4][9];
   __nv_bfloat16* w_dg[4][3];
   CUtensorMap dg_map[4][3];
+  // conv1 on pixel pairs: two output-column parity classes (see conv_tc.cu)
+  bool pair;
+  TcGeom pg[2];
+  __nv_bfloat16* w_pair[2];
+  CUtensorMap pair_map[2];
 };
 
 struct Bf16Plan {
@@ -45,6 +51,14 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     Bf16Layer& B = bp->L[l];
     const int groups = L.grouped ? 3 : 1;
     B.fwd = tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L.stride, N, groups);
+    // pixel-pair formulation of conv1 (16-byte copies, two parity classes): correct but measured slower than the
+    // row-window producer on B200, kept as an opt-in experiment (GEECO_TC_CONV1_PAIR=1)
+    B.pair = (l == 0 && L.Cin_pad == 4 && L.stride == 1 && L.Hin % 2 == 0 && L.grouped && getenv("GEECO_TC_CONV1_PAIR"));
+    if (B.pair) {
+      for (int par = 0; par < 2; ++par) B.pg[par] = tc_conv1pair_geom(L.Hin, L.Hin, L.Cout[0], N, groups, par);
+      const long long need = 2 * tc_wgrad_partial_floats(B.pg[0], L.Cout[0]);
+      if (need > cap) cap = need;
+    }
     B.n_classes = 0;
     if (l > 0) {
       for (int py = 0; py < L.stride; ++py)
@@ -73,6 +87,8 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     __nv_bfloat16* base = (__nv_bfloat16*)carve(ws_off, ws_base, tot * 2);
     size_t o = 0;
     for (int e = 0; e < 3; ++e) { B.w_fwd[e] = base ? base + o : nullptr; o += (size_t)L.Cout[e] * B.fwd.Kpad; }
+    for (int par = 0; par < 2; ++par)
+      B.w_pair[par] = B.pair ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)3 * L.Cout[0] * 64 * 2) : nullptr;
     for (int ci = 0; ci < B.n_classes; ++ci) {
       size_t t2 = 0;
       for (int e = 0; e < 3; ++e) t2 += (size_t)L.Cin_real * ((B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64);
@@ -93,6 +109,12 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
+    if (B.pair) {
+      for (int par = 0; par < 2; ++par) {
+        int rc = make_weight_tensor_map(&B.pair_map[par], B.w_pair[par], 3ll * L.Cout[0], 64, L.Cout[0]);
+        if (rc) return rc;
+      }
+    }
     if (L.grouped) {
       int rc = make_weight_tensor_map(&B.fwd_map[0], B.w_fwd[0], 3ll * L.Cout[0], B.fwd.Kpad, L.Cout[0]);
       if (rc) return rc;
@@ -148,7 +170,12 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
       for (int e = 0; e < ne; ++e) {
         const int groups = L.grouped ? 3 : 1;
         const float* W = c->theta + c->params[L.p_w[e]].offset;
-        add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad);
+        if (B.pair) {
+          for (int par = 0; par < 2; ++par)
+            add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64);
+        } else {
+          add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad);
+        }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
           add_job(bp, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
@@ -179,7 +206,14 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
-    if (L.grouped) {
+    if (B.pair) {
+      TcGeom pg[2] = {B.pg[0], B.pg[1]};
+      pg[0].bias_group_stride = pg[1].bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+      const CUtensorMap* pm[2] = {&B.pair_map[0], &B.pair_map[1]};
+      int rc = launch_tc_nn_multi(pg, pm, 2, src, c->theta + c->params[L.p_b[0]].offset, nullptr, (__nv_bfloat16*)L.y, nullptr,
+                                  TC_EPI_BIAS_RELU, 0, st);
+      if (rc) return rc;
+    } else if (L.grouped) {
       TcGeom g = B.fwd;
       g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
       int rc = launch_tc_nn(g, &B.fwd_map[0], src, c->theta + c->params[L.p_b[0]].offset, nullptr,
@@ -214,6 +248,20 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
     const __nv_bfloat16* xin = l == 0 ? (const __nv_bfloat16*)c->x0 : (const __nv_bfloat16*)c->layers[l - 1].y;
     const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
     const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+    if (B.pair) {
+      // conv1 weight gradient on pixel pairs: one partial GEMM per output-column parity, one joint reduction
+      const long long half = bp->partial_cap / 2;
+      int splits = 0, mrows = 0;
+      int rc = launch_tc_wgrad_partial(B.pg[0], L.Cout[0], xin, (const __nv_bfloat16*)L.g, bp->partial, half, 1, &splits, &mrows, st);
+      if (rc) return rc;
+      rc = launch_tc_wgrad_partial(B.pg[1], L.Cout[0], xin, (const __nv_bfloat16*)L.g, bp->partial + half, half, 1, &splits, &mrows, st);
+      if (rc) return rc;
+      rc = launch_conv1pair_reduce(bp->partial, bp->partial + half, c->grad + c->params[L.p_w[0]].offset,
+                                   c->grad + c->params[L.p_b[0]].offset, splits, 3, mrows, 64, L.Cin_real, L.Cout[0], wstride,
+                                   bstride, st);
+      if (rc) return rc;
+      continue;
+    }
     const int ne = L.grouped ? 1 : 3;
     for (int e = 0; e < ne; ++e) {
       const int groups = L.grouped ? 3 : 1;
@@ -262,7 +310,13 @@ static size_t conv_bf16_scratch(int N, int H, int W, int Cin, int Cout, int stri
       o_dg[ci++] = take((size_t)Cin * dg.Kpad * 2);
     }
   *part_floats = tc_wgrad_partial_floats(g, Cout);
+  if (Cin == 4 && stride == 1 && W % 2 == 0) {
+    TcGeom pg = tc_conv1pair_geom(H, W, Cout, N, 1, 0);
+    const long long need = 2 * tc_wgrad_partial_floats(pg, Cout);
+    if (need > *part_floats) *part_floats = need;
+  }
   *o_part = take((size_t)*part_floats * 4);
+  take((size_t)2 * Cout * 64 * 2 + 512);      // conv1 pixel-pair packed weights (two classes)
   return off + 256;
 }
 
@@ -283,6 +337,21 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
   }
   char* base = (char*)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
   cudaStream_t st = (cudaStream_t)stream;
+  if (Cin == 4 && stride == 1 && W % 2 == 0 && getenv("GEECO_TC_CONV1_PAIR")) {
+    // conv1 on pixel pairs: two parity classes in one launch
+    __nv_bfloat16* wpp = (__nv_bfloat16*)(base + ((o_part + (size_t)pf * 4 + 255) & ~(size_t)255));
+    TcGeom pg[2]; CUtensorMap pm[2]; const CUtensorMap* pmp[2];
+    for (int par = 0; par < 2; ++par) {
+      pg[par] = tc_conv1pair_geom(H, W, Cout, N, 1, par);
+      int rc = launch_pack_weights(w, wpp + (size_t)par * Cout * 64, 2 + par, 1, 0, Cw, Cout, 8, 6, kAllTaps, Cout, 64, st);
+      if (rc) return rc;
+      rc = make_weight_tensor_map(&pm[par], wpp + (size_t)par * Cout * 64, Cout, 64, Cout);
+      if (rc) return rc;
+      pmp[par] = &pm[par];
+    }
+    return launch_tc_nn_multi(pg, pmp, 2, (const __nv_bfloat16*)x, b, nullptr, (__nv_bfloat16*)y, y_f32,
+                              b ? (relu ? TC_EPI_BIAS_RELU : TC_EPI_BIAS) : TC_EPI_STORE, 0, st);
+  }
   TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
   __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_fwd);
   int rc = launch_pack_weights(w, wp, 0, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, st);
@@ -308,7 +377,19 @@ extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const v
   cudaStream_t st = (cudaStream_t)stream;
   TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
   int rc;
-  if (dw) {
+  if (dw && Cin == 4 && stride == 1 && W % 2 == 0 && getenv("GEECO_TC_CONV1_PAIR")) {
+    float* part = (float*)(base + o_part);
+    const long long half = pf / 2;
+    int splits = 0, mrows = 0;
+    for (int par = 0; par < 2; ++par) {
+      TcGeom pg = tc_conv1pair_geom(H, W, Cout, N, 1, par);
+      rc = launch_tc_wgrad_partial(pg, Cout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_pre, part + par * half, half, 1,
+                                   &splits, &mrows, st);
+      if (rc) return rc;
+    }
+    rc = launch_conv1pair_reduce(part, part + half, dw, db, splits, 1, mrows, 64, Cw, Cout, 0, 0, st);
+    if (rc) return rc;
+  } else if (dw) {
     rc = launch_tc_wgrad(g, Cout, Cw, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy_pre, dw, db,
                          (float*)(base + o_part), pf, 0, 0, st);
     if (rc) return rc;

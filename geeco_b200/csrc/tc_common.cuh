@@ -24,31 +24,40 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a protocol bug must become a trap (an error the host sees), never a hung GPU.
-// try_wait suspends the thread in hardware for a short implementation-defined time (an explicit suspend-time
-// hint compiles to a timed NANOSLEEP and delays wake-ups: measured slower); the clock check, amortised over
-// 2048 polls, only exists to turn a protocol bug into a trap.
+// The inner loop is two instructions (try_wait, branch); the clock check runs once per 1024 polls.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+  if (mbar_try(addr, parity)) return;
   long long t0 = 0;
-  for (uint32_t spin = 1;; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((spin & 2047u) == 0) {           // clock check amortised over 2048 polls
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 8000000000ll) {
-        printf("geeco_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-               addr, parity);
-        __trap();
-      }
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try(addr, parity)) return;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 8000000000ll) {
+      printf("geeco_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             addr, parity);
+      __trap();
     }
   }
+}
+// Role-wide wait: ONE warp polls the mbarrier, its peers block on a hardware named barrier (no issue slots
+// burnt by spinning warps; the kernels here are instruction-issue-bound).  All `nthreads` threads of the role call it.
+__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, bool is_poller_warp, int barrier_id,
+                                               int nthreads) {
+  if (is_poller_warp) mbar_wait(bar, parity);
+  asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nthreads) : "memory");
 }
 
 // ---- cp.async (LDGSTS) ---------------------------------------------------------------------------
