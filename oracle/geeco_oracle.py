@@ -1,11 +1,19 @@
 """CPU oracle for the GEECO e2evmc hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT.
 
-PARITY UNPINNED: the reference (ogroth/geeco) ships no tests, golden vectors or
-fixtures for this path, and its arithmetic lives in TensorFlow 1.15.0
-(environment.yml:189, not vendored, not installable offline).  This file is a
-restatement of the reference graph with TF-1.15 op semantics written out by
-hand; it is pinned only by the known-answer tests in tests/test_oracle_*.py and
-by the independent loop-level restatement in oracle/np_restatement.py.
+PARITY PINNED ON THE REFERENCE'S GRAPH CODE, NOT ON TENSORFLOW ITSELF.  The reference
+(ogroth/geeco) ships no tests, golden vectors or fixtures for this path, and its arithmetic
+lives in TensorFlow 1.15.0 (environment.yml:189, not vendored, not installable offline), so
+TensorFlow's kernels were never executed here.  What pins this file:
+  * tests/golden/geeco_graph_golden.npz -- produced by tests/golden/make_golden.py, which imports
+    the reference's src/models/e2evmc/graph.py UNMODIFIED and executes it over a small
+    torch-backed stand-in for the TF symbols it uses (tests/golden/tf_shim; the per-op semantics
+    stated there -- SAME padding, LSTMCell gate order / forget bias, loss reductions, L2 term --
+    are ours, from TF-1.15's documented behaviour).  The wiring, variable names and creation
+    order, loss functions and (through autograd) every gradient are the reference's own code;
+    tests/test_golden_reference_graph.py holds this oracle to them for seven configurations;
+  * the closed-form known answers of tests/test_oracle_pins.py;
+  * the independent loop-level restatement in oracle/np_restatement.py.
+Residual risk = a TF-1.15 op semantic misread identically in the shim and here.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this module.  Nothing under geeco_b200/ does.

@@ -1,7 +1,7 @@
 """Second, independent CPU restatement (NumPy, explicit index math, hand-written backward).
 
 TEST INFRASTRUCTURE, NOT PRODUCT -- see oracle/geeco_oracle.py for the rules.
-PARITY UNPINNED by the reference (no tests / fixtures upstream).
+Pinned like geeco_oracle.py (see its header): the reference has no fixtures; TF itself never ran here.
 
 Purpose: cross-check oracle/geeco_oracle.py (torch ops + autograd) with code that
 shares nothing with it: the SAME-padding index map is spelled out per output pixel
