@@ -34,7 +34,11 @@ class GeecoParamDesc(C.Structure):
 
 
 class GeecoBatch(C.Structure):
-  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state', 'cmd')]
+  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state', 'cmd')] + [
+      ('frame_format', C.c_int32), ('reserved0', C.c_int32)]
+
+
+FRAMES_F32, FRAMES_U8 = 0, 1
 
 
 class GeecoOutputs(C.Structure):

@@ -58,7 +58,7 @@ int launch_dynimg(const float* in, float* out, int N, int K, long long HWC, cons
                   int cluster_hint, cudaStream_t st);
 int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, int N, int K, long long HWC,
                           const float* alpha_host, cudaStream_t st);
-int launch_preprocess_geecof(const float* rgb, const float* tgt, void* x0, int out_bf16, int CP,
+int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP,
                              float* dynbuff_f32, float* dyndiff_f32, int N, int K, int H, int W, int C,
                              const float* alpha_host, int cluster_hint, cudaStream_t st);
 // conv_fp32.cu

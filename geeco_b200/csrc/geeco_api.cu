@@ -583,7 +583,12 @@ static int carry_update(geeco_ctx* c, cudaStream_t st) {
 static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, bool with_loss, cudaStream_t st) {
   const geeco_config& cfg = c->cfg;
   const bool bf16 = cfg.precision == GEECO_BF16;
-  int rc = launch_preprocess_geecof(b->rgb, b->target_rgb, c->x0, bf16 ? 1 : 0, c->CP, out ? out->dynbuff : nullptr,
+  if (b->frame_format != GEECO_FRAMES_F32 && b->frame_format != GEECO_FRAMES_U8) {
+    geeco_set_error("batch: frame_format %d is neither GEECO_FRAMES_F32 nor GEECO_FRAMES_U8", b->frame_format);
+    return GEECO_ERR_INVALID;
+  }
+  int rc = launch_preprocess_geecof(b->rgb, b->target_rgb, b->frame_format == GEECO_FRAMES_U8, c->x0, bf16 ? 1 : 0,
+                                    c->CP, out ? out->dynbuff : nullptr,
                                     out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
                                     cfg.img_width, cfg.img_channels, c->alpha, 0, st);
   if (rc) return rc;

@@ -214,9 +214,25 @@ __device__ __forceinline__ void store_unit(OutT* dst, const float* e) {
     PixPack<OutT, CP>::store(dst + p * CP, e[p * C], e[p * C + 1], e[p * C + 2], C == 4 ? e[p * C + (C - 1)] : 0.f);
 }
 
-template <typename OutT, int CP, int C, int K>
+// One "float4" of frame data (4 consecutive values of the NHWC stream) in either input format.  uint8 records are
+// divided by 255.0f in fp32, as the reference's input pipeline does on the host (src/data/geeco_gym.py:310).
+template <typename InT> struct FrameLoad;
+template <> struct FrameLoad<float> {
+  static __device__ __forceinline__ float4 at(const float* base, long long i4) {
+    return ldg_stream(reinterpret_cast<const float4*>(base) + i4);
+  }
+};
+template <> struct FrameLoad<unsigned char> {
+  static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4) {
+    const unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(base) + i4);
+    return make_float4(__fdiv_rn((float)(w & 255u), 255.f), __fdiv_rn((float)((w >> 8) & 255u), 255.f),
+                       __fdiv_rn((float)((w >> 16) & 255u), 255.f), __fdiv_rn((float)(w >> 24), 255.f));
+  }
+};
+
+template <typename InT, typename OutT, int CP, int C, int K>
 __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
-    const float* __restrict__ rgb, const float* __restrict__ tgt, OutT* __restrict__ x0,
+    const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
     AlphaTab al) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -229,8 +245,8 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   const long long lo = (long long)blockIdx.x * per_units;
   long long hi = lo + per_units; if (hi > units) hi = units;
   const long long img4 = units * C;                       // float4 per image
-  const float4* fbase = reinterpret_cast<const float4*>(rgb) + n * K * img4;
-  const float4* tbase = reinterpret_cast<const float4*>(tgt) + n * img4;
+  const InT* fbase = rgb + n * K * img4 * 4;
+  const InT* tbase = tgt + n * img4 * 4;
   const long long img_out = units * 4 * CP;               // OutT elements per padded image
   OutT* x_cur = x0 + n * img_out;
   OutT* x_dyn = x0 + ((long long)N + n) * img_out;
@@ -241,9 +257,9 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < C; ++j) v[k][j] = ldg_stream(fbase + k * img4 + u * C + j);
+      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, k * img4 + u * C + j);
 #pragma unroll
-    for (int j = 0; j < C; ++j) t[j] = ldg_stream(tbase + u * C + j);
+    for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j);
     float cur[4 * C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -367,8 +383,8 @@ int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, in
   return GEECO_OK;
 }
 
-template <typename OutT, int CP, int C>
-static int launch_pre_t(const float* rgb, const float* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
+template <typename InT, typename OutT, int CP, int C>
+static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
                         const AlphaTab& al_in, int cluster_hint, cudaStream_t st) {
   long long units = (long long)H * W / 4;
   int cl = pick_cluster(2ll * H * W * C * 4, cluster_hint);
@@ -382,20 +398,24 @@ static int launch_pre_t(const float* rgb, const float* tgt, void* x0, float* db,
   AlphaTab al = al_in;
   void* args[] = {(void*)&rgb, (void*)&tgt, (void*)&x, (void*)&db, (void*)&dd, (void*)&N, (void*)&units,
                   (void*)&per_units, (void*)&al};
-  RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
+  RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<InT, OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
   return GEECO_OK;
 }
 
-int launch_preprocess_geecof(const float* rgb, const float* tgt, void* x0, int out_bf16, int CP, float* dynbuff_f32,
-                             float* dyndiff_f32, int N, int K, int H, int W, int C, const float* alpha_host,
-                             int cluster_hint, cudaStream_t st) {
+int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP,
+                             float* dynbuff_f32, float* dyndiff_f32, int N, int K, int H, int W, int C,
+                             const float* alpha_host, int cluster_hint, cudaStream_t st) {
   if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
   if (N <= 0) return GEECO_OK;
   if (N > 65535) { geeco_set_error("preprocess: N=%d > 65535", N); return GEECO_ERR_INVALID; }
   if (K > 8) { geeco_set_error("preprocess: fused path supports window_size <= 8 (got %d)", K); return GEECO_ERR_INVALID; }
   AlphaTab al = {};
   for (int k = 0; k < K; ++k) al.a[k] = alpha_host[k];
-#define PRE_CASE(T, cp, c) return launch_pre_t<T, cp, c>(rgb, tgt, x0, dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, st)
+#define PRE_CASE(T, cp, c)                                                                                        \
+  return frames_u8 ? launch_pre_t<unsigned char, T, cp, c>((const unsigned char*)rgb, (const unsigned char*)tgt, x0,  \
+                                                           dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, st) \
+                   : launch_pre_t<float, T, cp, c>((const float*)rgb, (const float*)tgt, x0, dynbuff_f32,             \
+                                                   dyndiff_f32, N, K, H, W, al, cluster_hint, st)
   if (!out_bf16 && CP == 4 && C == 3) PRE_CASE(float, 4, 3);
   if (!out_bf16 && CP == 4 && C == 4) PRE_CASE(float, 4, 4);
   if (out_bf16 && CP == 8 && C == 3) PRE_CASE(__nv_bfloat16, 8, 3);

@@ -48,8 +48,11 @@ def rank_slice(batch_index: int, global_batch: int, rank: int, world: int):
 
 
 def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0, first_stream_pos=0,
-                    structured=True, episode_length=EPISODE_LENGTH):
+                    structured=True, episode_length=EPISODE_LENGTH, frame_format='float32'):
   """One (features, labels) tuple of numpy arrays, seeded, uint8-quantised pixels.
+
+  frame_format='float32': pixels divided by 255 as the reference's input pipeline hands them to model_fn
+  (src/data/geeco_gym.py:310); frame_format='uint8': the recorded bytes, same values before that division.
 
   structured=True gives every window temporal structure (frame k = base image rolled by k
   pixels plus fresh noise) so K-frame buffers are never static -- the dynimg min/max
@@ -66,8 +69,13 @@ def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0,
     rgb = np.stack(frames, axis=1)
   else:
     rgb = rng.integers(0, 256, size=(n, K, height, width, channels))
-  rgb = (rgb / 255.0).astype(np.float32)
-  tgt = (rng.integers(0, 256, size=(n, height, width, channels)) / 255.0).astype(np.float32)
+  tgt = rng.integers(0, 256, size=(n, height, width, channels))
+  if frame_format == 'uint8':
+    rgb, tgt = rgb.astype(np.uint8), tgt.astype(np.uint8)
+  elif frame_format == 'float32':
+    rgb, tgt = (rgb / 255.0).astype(np.float32), (tgt / 255.0).astype(np.float32)
+  else:
+    raise ValueError("frame_format must be 'float32' or 'uint8', got %r" % (frame_format,))
   jnt = rng.uniform(-np.pi, np.pi, size=(n, K, 7)).astype(np.float32)
   ee = np.zeros((n, K, 7), dtype=np.float32)
   ee[..., :3] = np.array([1.34, 0.75, 0.55], dtype=np.float32) + rng.uniform(-0.15, 0.15, size=(n, K, 3))

@@ -19,6 +19,7 @@ from .params import E2EVMCConfig
 
 LOSS_KEYS = ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss_reg', 'loss')
 _FEATURE_KEYS = ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state')
+_FRAME_KEYS = ('rgb', 'target_rgb')
 
 
 def _check_switches(cfg: E2EVMCConfig):
@@ -187,26 +188,34 @@ class Engine(object):
     return {'rgb': (N, K, H, W, Cc), 'target_rgb': (N, H, W, Cc), 'jnt_state': (N, K, cfg.dim_jnt_state),
             'ee_state': (N, K, 7), 'obj_state': (N, K, 7), 'cmd': (N, 4)}
 
+  @staticmethod
+  def _wire_dtype(key, dtype):
+    """Frames recorded as uint8 [0..255] stay uint8 on the wire and are divided by 255.0f on the device
+    (geeco_gym.py:310); everything else travels as float32."""
+    return torch.uint8 if key in _FRAME_KEYS and dtype == torch.uint8 else torch.float32
+
   def _to_device(self, key, value):
-    """Accepts a float32 CUDA tensor (used in place) or a host array (staged through pinned memory)."""
+    """Accepts a CUDA tensor (used in place) or a host array (staged through pinned memory)."""
     shape = self._shapes()[key]
     if torch.is_tensor(value) and value.is_cuda:
       if tuple(value.shape) != shape:
         raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(value.shape)))
-      return value.contiguous().float()
+      return value.contiguous().to(self._wire_dtype(key, value.dtype))
     arr = value if torch.is_tensor(value) else torch.from_numpy(np.ascontiguousarray(value))
     if tuple(arr.shape) != shape:
       raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(arr.shape)))
-    if key not in self._dev_in:
-      self._dev_in[key] = torch.empty(shape, dtype=torch.float32, device=self.device)
-    if arr.dtype == torch.float32 and arr.is_pinned():
-      self._dev_in[key].copy_(arr, non_blocking=True)       # caller-pinned: straight H2D
-      return self._dev_in[key]
-    if key not in self._pin_in:
-      self._pin_in[key] = torch.empty(shape, dtype=torch.float32).pin_memory()
-    self._pin_in[key].copy_(arr)
-    self._dev_in[key].copy_(self._pin_in[key], non_blocking=True)
-    return self._dev_in[key]
+    wd = self._wire_dtype(key, arr.dtype)
+    dk = (key, wd)
+    if dk not in self._dev_in:
+      self._dev_in[dk] = torch.empty(shape, dtype=wd, device=self.device)
+    if arr.dtype == wd and arr.is_pinned():
+      self._dev_in[dk].copy_(arr, non_blocking=True)       # caller-pinned: straight H2D
+      return self._dev_in[dk]
+    if dk not in self._pin_in:
+      self._pin_in[dk] = torch.empty(shape, dtype=wd).pin_memory()
+    self._pin_in[dk].copy_(arr)
+    self._dev_in[dk].copy_(self._pin_in[dk], non_blocking=True)
+    return self._dev_in[dk]
 
   # ---- double-buffered staging: upload batch i+1 on a copy stream while batch i computes -------------
   def stage(self, features, labels, slot):
@@ -232,16 +241,17 @@ class Engine(object):
         t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
         if tuple(t.shape) != shapes[k]:
           raise ValueError("%s: expected shape %s, got %s" % (k, shapes[k], tuple(t.shape)))
-        if k not in bufs:
-          bufs[k] = torch.empty(shapes[k], dtype=torch.float32, device=self.device)
-        if not (t.dtype == torch.float32 and t.is_pinned()):
-          if (k, slot) not in self._pin_in:
-            self._pin_in[(k, slot)] = torch.empty(shapes[k], dtype=torch.float32).pin_memory()
-          pin = self._pin_in[(k, slot)]
+        wd = self._wire_dtype(k, t.dtype)
+        if (k, wd) not in bufs:
+          bufs[(k, wd)] = torch.empty(shapes[k], dtype=wd, device=self.device)
+        if not (t.dtype == wd and t.is_pinned()):
+          if (k, wd, slot) not in self._pin_in:
+            self._pin_in[(k, wd, slot)] = torch.empty(shapes[k], dtype=wd).pin_memory()
+          pin = self._pin_in[(k, wd, slot)]
           pin.copy_(t)
           t = pin
-        bufs[k].copy_(t, non_blocking=True)
-        out[k] = bufs[k]
+        bufs[(k, wd)].copy_(t, non_blocking=True)
+        out[k] = bufs[(k, wd)]
       ev = torch.cuda.Event()
       ev.record(self._copy_stream)
     return out, ({'cmd': out['cmd']} if labels is not None else None), ev
@@ -255,11 +265,11 @@ class Engine(object):
     ev.record(torch.cuda.current_stream(self.device))
     self._stage_free[slot] = ev
 
-  def h2d_bytes(self, with_labels=True):
+  def h2d_bytes(self, with_labels=True, frames_u8=False):
     keys = list(_FEATURE_KEYS) + (['cmd'] if with_labels else [])
     if not with_labels:
       keys = ['rgb', 'target_rgb', 'jnt_state']
-    return int(sum(4 * int(np.prod(self._shapes()[k])) for k in keys))
+    return int(sum((1 if frames_u8 and k in _FRAME_KEYS else 4) * int(np.prod(self._shapes()[k])) for k in keys))
 
   def _batch(self, features, labels):
     b = _lib.GeecoBatch()
@@ -268,6 +278,10 @@ class Engine(object):
       t = self._to_device(k, features[k])
       keep.append(t)
       setattr(b, k, t.data_ptr())
+    if keep[0].dtype != keep[1].dtype:
+      raise ValueError("rgb is %s but target_rgb is %s: both must be float32 in [0,1] or both uint8 [0..255]"
+                       % (keep[0].dtype, keep[1].dtype))
+    b.frame_format = _lib.FRAMES_U8 if keep[0].dtype == torch.uint8 else _lib.FRAMES_F32
     if labels is not None:
       for k in ('ee_state', 'obj_state'):
         t = self._to_device(k, features[k])
@@ -344,6 +358,16 @@ class Engine(object):
   def set_lstm_state(self, state_cm=None):
     p = C.c_void_p(state_cm.data_ptr()) if state_cm is not None else None
     _lib.check(self.lib.geeco_set_lstm_state(self._ctx, p, self._stream()))
+
+  def read_losses_async(self, losses, slot):
+    """Starts the device->host copy of one step's loss vector into pinned slot 0/1; returns (pinned, event)."""
+    if not hasattr(self, '_loss_pins'):
+      self._loss_pins = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+    pin = self._loss_pins[slot]
+    pin.copy_(losses, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(self.device))
+    return pin, ev
 
   def losses_dict(self, losses=None):
     v = (self.out_losses if losses is None else losses).detach().cpu().numpy()

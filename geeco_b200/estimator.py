@@ -175,18 +175,32 @@ class Estimator(object):
     p = dict(self.params, engine=eng)
     done, self.last_train_losses = 0, []
     log_steps = int(self.params.get('log_steps', 1000) or 1000)
+    pending = None            # (global_step, pinned losses, copy-done event) of the last logged step
+
+    def resolve(entry):
+      step, pin, ev = entry
+      ev.synchronize()
+      self.last_train_losses.append((step, eng.losses_dict(pin)))
+      if rank == 0 and self.params.get('debug'):
+        print('step %d: %s' % self.last_train_losses[-1])
+
     for features, labels in self._prefetched(eng, input_fn()):
       self._check_batch(features)
       spec = self._model_fn(features, labels, ModeKeys.TRAIN, p)
       done += 1
       if eng.global_step % log_steps == 0 or done == 1:
-        self.last_train_losses.append((eng.global_step, eng.losses_dict(spec.loss)))
-        if rank == 0 and self.params.get('debug'):
-          print('step %d: %s' % self.last_train_losses[-1])
+        # the losses of a logged step travel to the host asynchronously and are read one step later, after the
+        # next step has been enqueued, so the device never idles on the host round trip
+        entry = eng.read_losses_async(spec.loss, done & 1)
+        if pending is not None:
+          resolve(pending)
+        pending = (eng.global_step,) + entry
       if rank == 0 and self.config.save_checkpoints_steps and eng.global_step % self.config.save_checkpoints_steps == 0:
         save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
       if steps is not None and done >= steps:
         break
+    if pending is not None:
+      resolve(pending)
     if rank == 0 and self.params.get('save_final_checkpoint', True):
       save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
     return self

@@ -74,13 +74,19 @@ typedef struct geeco_param_desc {
 } geeco_param_desc;
 
 /* Input features/labels of one step; layout of `_prepare_v4` (src/data/geeco_gym.py:373-399). */
+enum { GEECO_FRAMES_F32 = 0,   /* float32 in [0,1]: what model_fn receives (estimator.py:160-176) */
+       GEECO_FRAMES_U8 = 1 }; /* uint8 [0..255] as recorded; divided by 255.0f on the device, bit-identical to the
+                                 `parsed_example['rgb'] /= 255.0` of the input pipeline (geeco_gym.py:310) */
+
 typedef struct geeco_batch {
-  const float* rgb;         /* [N,K,H,W,C] in [0,1]      features['rgb'] (+depth as 4th channel for rgbd) */
-  const float* target_rgb;  /* [N,H,W,C]                 features['target_rgb'] */
+  const void* rgb;          /* [N,K,H,W,C]               features['rgb'] (+depth as 4th channel for rgbd) */
+  const void* target_rgb;   /* [N,H,W,C]                 features['target_rgb'] */
   const float* jnt_state;   /* [N,K,J]                   features['jnt_state'] */
   const float* ee_state;    /* [N,K,7] or NULL           features['ee_state']   (losses only) */
   const float* obj_state;   /* [N,K,7] or NULL           features['obj_state']  (losses only) */
   const float* cmd;         /* [N,4]   or NULL           labels['cmd']          (losses only) */
+  int32_t frame_format;     /* GEECO_FRAMES_F32 | GEECO_FRAMES_U8: element type of rgb AND target_rgb */
+  int32_t reserved0;
 } geeco_batch;
 
 /* Optional outputs (NULL = not wanted).  heads = [pred_cmd_ee 0:3 | logits_cmd_grp 3:3+G |

@@ -149,3 +149,61 @@ def test_batched_predictor_equals_single_predictor(cuda_device, tmp_path):
   _, ep = O.goal_e2evmc(rgb, jn, torch.tensor(goals), P, cfg_d)
   assert rel_max(out['cmd_ee'].cpu().numpy(), ep['pred_cmd_ee'].numpy()) <= 1e-4
   assert np.array_equal(out['cmd_grp'].cpu().numpy(), (ep['logits_cmd_grp'].argmax(dim=1) - 1).float().numpy())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_uint8_frames_equal_host_divided_frames(cuda_device, precision):
+  """Recorded uint8 frames divided by 255 on the device == the input pipeline's host division (geeco_gym.py:310):
+  same network input bit for bit, hence the same step; covers pinned, pageable and device-resident callers."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import synthetic_batch
+  from geeco_b200.engine import Engine
+  N = 2
+  cfg_d = O.make_config(batch_size=N)
+  P = O.init_params(cfg_d, seed=3, dtype=torch.float32, bias_scale=0.05)
+  f8, labels = synthetic_batch(N, seed=5, frame_format='uint8')
+  f32 = dict(f8)
+  for k in ('rgb', 'target_rgb'):
+    assert f8[k].dtype == np.uint8
+    f32[k] = f8[k].astype(np.float32) / np.float32(255.0)
+  res = {}
+  for tag, feats in (('f32', f32), ('u8', f8), ('u8_cuda', {k: (torch.from_numpy(v).cuda() if k in ('rgb', 'target_rgb')
+                                                                else v) for k, v in f8.items()})):
+    eng = Engine(create_e2evmc_config(cfg_d), batch_size=N, precision=precision, training=True)
+    eng.set_params(P)
+    out = eng.forward(feats, labels, want_dyn=True)
+    torch.cuda.synchronize()
+    x0 = eng.debug_buffer('x0')
+    x0 = (x0.view(torch.int16) if x0.dtype == torch.bfloat16 else x0.view(torch.int32)).cpu().numpy().copy()
+    fwd = {k: out[k].cpu().numpy().copy() for k in ('pred_cmd_ee', 'logits_cmd_grp', 'dynbuff', 'dyndiff', 'losses')}
+    eng.train_step(feats, labels)
+    torch.cuda.synchronize()
+    res[tag] = (x0, fwd, eng.get_grads(), eng.get_params())
+    eng.close()
+  for tag in ('u8', 'u8_cuda'):
+    assert np.array_equal(res[tag][0], res['f32'][0]), tag
+    for k, v in res['f32'][1].items():
+      assert np.array_equal(res[tag][1][k], v), (tag, k)
+    for k, v in res['f32'][2].items():
+      assert np.array_equal(res[tag][2][k], v), (tag, k)
+    for k, v in res['f32'][3].items():
+      assert np.array_equal(res[tag][3][k], v), (tag, k)
+  # oracle on the host-divided frames (the division itself: float32(u) / 255.0f)
+  ref_losses, _, ep = O.train_step({k: v.clone() for k, v in P.items()}, O.adam_init(P), f32, labels, cfg_d)
+  tol = 1e-4 if precision == 'fp32' else 2e-2
+  assert abs(float(res['u8'][1]['losses'][5]) - ref_losses['loss']) <= tol * abs(ref_losses['loss'])
+  assert np.abs(res['u8'][1]['dynbuff'] - ep['dynbuff'].detach().numpy()).max() <= 1e-5
+
+
+def test_mixed_frame_formats_are_rejected(cuda_device):
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import synthetic_batch
+  from geeco_b200.engine import Engine
+  cfg_d = O.make_config(batch_size=1)
+  f8, labels = synthetic_batch(1, seed=5, frame_format='uint8')
+  f8['target_rgb'] = f8['target_rgb'].astype(np.float32) / np.float32(255.0)
+  eng = Engine(create_e2evmc_config(cfg_d), batch_size=1, precision='fp32', training=False)
+  eng.init_params(seed=0)
+  with pytest.raises(ValueError):
+    eng.forward(f8, None)
+  eng.close()
