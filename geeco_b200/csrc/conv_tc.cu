@@ -111,7 +111,8 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 // one k-block per tile as in conv1), then the MMA warp and the TMA warp
 template <int PIECE, int NPW>
 __global__ void __launch_bounds__(NN_THREADS, 2)
-tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps, const __nv_bfloat16* __restrict__ src,
+tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps,
+             const __grid_constant__ CUtensorMap amap, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
              int tiles_flat, int tmem_cols, int stages, int nbuf) {
@@ -131,6 +132,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   constexpr int PROD_THREADS = NPW * 32;
   constexpr int EPI_THREADS = (12 - NPW) * 32;
   constexpr int NHALF = (12 - NPW) / 4;            // epilogue warps per TMEM lane quadrant (column interleave)
+  constexpr bool A_TMA = NPW == 0;                 // no gather producers: the TMA warp fetches the A tiles as well
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS + 1); mbar_init(&empty[s], 1); }
@@ -144,11 +146,12 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
       bias_s[i] = bias_all[(long long)(i / BN) * g.bias_group_stride + (i % BN)];
   // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
   // they hold later is finite data (multiplied by zero weights)
-  zero_smem(a_base, stages * A_STAGE_BYTES);
+  if (!A_TMA) zero_smem(a_base, stages * A_STAGE_BYTES);
   fence_proxy_async();
   if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   if (warp == 13 && lane == 0) {
     for (int c = 0; c < cl.ncls; ++c) tma_prefetch_desc(&maps.m[c]);
+    if (A_TMA) tma_prefetch_desc(&amap);
   }
   tc_fence_before();
   __syncthreads();
@@ -161,6 +164,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   // of one tile run back to back (their source rows and destination lines are shared)
 
   if (warp < NPW) {
+   if constexpr (NPW > 0) {
     // ===================== A producers: implicit-im2col gather =====================
     constexpr int PPR = BK / PIECE;                 // pieces per 128-byte row
     constexpr int ROWS_PER_PASS = PROD_THREADS / PPR;
@@ -265,6 +269,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         }
       }
     }
+   }
   } else if (warp < 12) {
     // ===================== epilogue: TMEM -> registers -> global =====================
     // warp w reads TMEM lanes [32*(w&3), +32) (hardware rule) and the 16-column chunks c0 = 16*(NHALF*i + half)
@@ -367,17 +372,34 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
       }
     }
   } else {
-    // ===================== weight tiles by TMA (one thread) =====================
+    // ===================== weight tiles (and, A_TMA, activation tiles) by TMA (one thread) =====================
     if (lane == 0) {
       uint32_t it = 0;
+      const int cpt = g.Kt / BK;                     // 64-channel chunks per tap (A_TMA)
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
         const int group = flat / tiles_per_group;
+        int img0 = 0, y0 = 0, x0 = 0;
+        if (A_TMA) {
+          const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+          decode_pixel(g, m0, img0, y0, x0);
+          img0 += group * g.imgs_per_group;
+        }
         for (int c = 0; c < ncls; ++c) {
-          const int nkb = cl.c[c].Kpad / BK;
+          const TcCls& kc = cl.c[c];
+          const int nkb = kc.Kpad / BK;
+          int tap = 0, chunk = 0;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % stages;
             mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
+            if (A_TMA) {
+              mbar_arrive_expect_tx(&full[s], (uint32_t)(b_stage_bytes + A_STAGE_BYTES));
+              // box = 64 channels x the tile's pixel block; out-of-image coordinates zero-fill (= SAME padding)
+              tma_load_5d(smem_u32(a_base + s * A_STAGE_BYTES), &amap, &full[s], kc.tc0[tap] + chunk * BK, x0 + kc.twq[tap],
+                          kc.thp[tap], y0 + kc.thq[tap], img0);
+              if (++chunk == cpt) { chunk = 0; ++tap; }
+            } else {
+              mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
+            }
             tma_load_2d(smem_u32(b_base + s * b_stage_bytes), &maps.m[c], &full[s], kb * BK, group * g.b_rows_per_group);
           }
         }
@@ -716,7 +738,7 @@ __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict_
 //   mode 2/3 (conv1 on pixel pairs, even / odd output columns): k = (ky*2 + j)*8 + p*4 + c  ->  W[ky][kx][c][n]
 //            with kx = 2*dx + p + 1 - par, dx = j - 1 (even) or j (odd); columns outside the 3x3 window are zero
 __device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int mode, int Cin, int Cout, int Cs, int ntaps,
-                                            const int* taps, int r, int k) {
+                                            const int* taps, int Kt, int r, int k) {
   if (mode >= 2) {
     const int par = mode - 2;
     if (k >= 48 || r >= Cout) return 0.f;
@@ -726,24 +748,24 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int m
     if (kx < 0 || kx > 2 || c >= Cin) return 0.f;
     return Wg0[((long long)(ky * 3 + kx) * Cin + c) * Cout + r];
   }
-  const int per_tap = mode == 0 ? Cs : Cout;
+  const int per_tap = Kt > 0 ? Kt : (mode == 0 ? Cs : Cout);
   const int t = k / per_tap, c = k - t * per_tap;
   if (t >= ntaps) return 0.f;
   const float* Wg = Wg0 + (long long)taps[t] * Cin * Cout;
   if (mode == 0) return (c < Cin && r < Cout) ? Wg[(long long)c * Cout + r] : 0.f;
-  return r < Cin ? Wg[(long long)r * Cout + c] : 0.f;
+  return (r < Cin && c < Cout) ? Wg[(long long)r * Cout + c] : 0.f;
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int mode, int groups,
                                     long long w_group_stride, int Cin, int Cout, int Cs, int ntaps, int rows, int Kpad,
-                                    int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8) {
+                                    int Kt, int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8) {
   const int taps[9] = {t0, t1, t2, t3, t4, t5, t6, t7, t8};
   const long long total = (long long)groups * rows * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kpad);
     const long long rr = i / Kpad;
     const int r = (int)(rr % rows), grp = (int)(rr / rows);
-    const float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, r, k);
+    const float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, Kt, r, k);
     out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -762,7 +784,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     const long long rr = i / jb.Kpad;
     const int r = (int)(rr % jb.rows), grp = (int)(rr / jb.rows);
     const float v = pack_value(jb.W + (long long)grp * jb.w_group_stride, jb.mode, jb.Cin, jb.Cout, jb.Cs, jb.ntaps,
-                               jb.taps, r, k);
+                               jb.taps, jb.Kt, r, k);
     jb.out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -841,6 +863,83 @@ int make_weight_tensor_map(CUtensorMap* map, const void* base, long long rows_to
   return GEECO_OK;
 }
 
+static PFN_encodeTiled encode_tiled_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// Can the A operand of this geometry be fetched by TMA?  One tile = 128 consecutive GEMM rows = a
+// (bw x bh x bn) block of pixels (bw pixels of a row, bh rows, bn images), so that every k-block is ONE
+// 5-D box of 64 channels; out-of-image coordinates are zero-filled by the hardware (= SAME padding).
+// A stride-2 source is viewed as [img][H/2][2][W/2][2*Cs] (row pairs, pixel pairs), which needs taps >= 0
+// (TensorFlow's SAME padding of an even-sized stride-2 layer pads only after).
+static bool tc_use_tma(const TcGeom& g) {
+  static const bool disabled = getenv("GEECO_TC_NO_TMA") != nullptr;
+  if (disabled) return false;
+  if (g.Cs % 8 || g.Cs < 16 || g.hw_shift < 0) return false;
+  if (((g.Cs + 63) / 64 * 64 - g.Cs) * 3 > (g.Cs + 63) / 64 * 64) return false;   // > 1/3 of every k-block would be padding
+  if (g.sx != g.sy || (g.sx != 1 && g.sx != 2)) return false;
+  if (g.Wm > 128 && g.Wm % 128) return false;
+  if (g.sx == 2) {
+    if ((g.Hs | g.Ws) & 1) return false;
+    for (int t = 0; t < g.ntaps; ++t) if (g.dy[t] < 0 || g.dx[t] < 0) return false;
+  }
+  return true;
+}
+static void tc_tile_block(const TcGeom& g, int* bw, int* bh, int* bn) {
+  *bw = g.Wm < 128 ? g.Wm : 128;
+  *bh = g.Hm < 128 / *bw ? g.Hm : 128 / *bw;
+  *bn = 128 / (*bw * *bh);
+}
+// K layout of the packed weights for this geometry: per-tap extent Kt (Cs, or Cs rounded up to 64 for TMA)
+static void finish_k(TcGeom* g) {
+  g->a_tma = tc_use_tma(*g) ? 1 : 0;
+  g->Kt = g->a_tma ? (g->Cs + 63) / 64 * 64 : g->Cs;
+  g->Ktot = g->ntaps * g->Kt;
+  g->Kpad = (g->Ktot + 63) / 64 * 64;
+}
+// the same geometry as the software-gather kernels (weight gradient) see it: dense K = ntaps * Cs
+static TcGeom gather_view(const TcGeom& g) {
+  TcGeom v = g;
+  v.a_tma = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 63) / 64 * 64;
+  return v;
+}
+
+// 5-D tensor map over a bf16 NHWC activation for the tile blocks of geometry g (see tc_use_tma)
+static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g) {
+  PFN_encodeTiled fn = encode_tiled_fn();
+  if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
+  int bw, bh, bn;
+  tc_tile_block(g, &bw, &bh, &bn);
+  const cuuint64_t imgs = (cuuint64_t)g.imgs_per_group * g.groups;
+  const cuuint64_t row = (cuuint64_t)g.Ws * g.Cs * 2, img = row * g.Hs;
+  cuuint64_t gdim[5], gstr[4];
+  if (g.sx == 1) {
+    gdim[0] = g.Cs; gdim[1] = g.Ws; gdim[2] = 1; gdim[3] = g.Hs; gdim[4] = imgs;
+    gstr[0] = (cuuint64_t)g.Cs * 2; gstr[1] = row; gstr[2] = row; gstr[3] = img;
+  } else {
+    gdim[0] = 2 * g.Cs; gdim[1] = g.Ws / 2; gdim[2] = 2; gdim[3] = g.Hs / 2; gdim[4] = imgs;
+    gstr[0] = (cuuint64_t)g.Cs * 4; gstr[1] = row; gstr[2] = 2 * row; gstr[3] = img;
+  }
+  cuuint32_t box[5] = {64u, (cuuint32_t)bw, 1u, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    geeco_set_error("cuTensorMapEncodeTiled (activation %dx%dx%d, stride %d, box %dx%dx%d) failed with CUresult %d", g.Hs, g.Ws,
+                    g.Cs, g.sx, bw, bh, bn, (int)r);
+    return GEECO_ERR_CUDA;
+  }
+  return GEECO_OK;
+}
+
 static void same_pad_tc(int in, int s, int* out, int* before) {
   *out = (in + s - 1) / s;
   int total = (*out - 1) * s + 3 - in;
@@ -857,10 +956,10 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   g.Hs = H; g.Ws = W; g.Cs = Cs; g.Hm = Ho; g.Wm = Wo; g.sy = stride; g.sx = stride; g.ntaps = 9;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) { g.dy[ky * 3 + kx] = ky - pt; g.dx[ky * 3 + kx] = kx - pl; }
-  g.Ktot = 9 * Cs; g.Kpad = (g.Ktot + 63) / 64 * 64;
   g.Nn = Cout; g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
+  finish_k(&g);
   g.rowwin = (Cs == 4 && stride == 1 && Wo % 128 == 0 && g.hw_shift >= 0) ? 1 : 0;
   return g;
 }
@@ -873,7 +972,7 @@ TcGeom tc_conv1pair_geom(int H, int W, int Cout, int imgs_per_group, int groups,
   g.Hs = H; g.Ws = W / 2; g.Cs = 8; g.Hm = H; g.Wm = W / 2; g.sy = 1; g.sx = 1; g.ntaps = 6;
   for (int ky = 0; ky < 3; ++ky)
     for (int j = 0; j < 2; ++j) { g.dy[ky * 2 + j] = ky - 1; g.dx[ky * 2 + j] = par == 0 ? j - 1 : j; }
-  g.Ktot = 48; g.Kpad = 64;
+  g.Ktot = 48; g.Kpad = 64; g.Kt = 8; g.a_tma = 0;
   g.Nn = Cout; g.Hd = H; g.Wd = W; g.dsy = 1; g.dsx = 2; g.dy0 = 0; g.dx0 = par;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
@@ -917,10 +1016,10 @@ bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, 
   }
   if (!nt) return false;
   g.ntaps = nt;
-  g.Ktot = nt * Cout; g.Kpad = (g.Ktot + 63) / 64 * 64;
   g.Nn = Cin; g.Hd = H; g.Wd = W; g.dsy = stride; g.dsx = stride; g.dy0 = py; g.dx0 = px;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cin; g.bias_group_stride = 0;
   finish_geom(&g);
+  finish_k(&g);
   *out = g;
   return true;
 }
@@ -944,7 +1043,14 @@ static int check_geom(const TcGeom& g, const char* who) {
 
 static void fill_class(TcCls* c, const TcGeom& g) {
   c->ntaps = g.ntaps; c->Ktot = g.Ktot; c->Kpad = g.Kpad; c->dy0 = g.dy0; c->dx0 = g.dx0;
-  for (int t = 0; t < GEECO_MAX_TAPS; ++t) { c->dy[t] = g.dy[t]; c->dx[t] = g.dx[t]; }
+  for (int t = 0; t < GEECO_MAX_TAPS; ++t) {
+    c->dy[t] = g.dy[t]; c->dx[t] = g.dx[t];
+    const int sh = g.sx == 2 ? 1 : 0;       // taps are >= 0 when sh == 1 (tc_use_tma)
+    c->tc0[t] = (short)(sh ? (g.dx[t] & 1) * g.Cs : 0);
+    c->twq[t] = (short)(sh ? g.dx[t] >> 1 : g.dx[t]);
+    c->thp[t] = (short)(sh ? g.dy[t] & 1 : 0);
+    c->thq[t] = (short)(sh ? g.dy[t] >> 1 : g.dy[t]);
+  }
 }
 
 // ncls geometries that differ only in taps / K extent / destination offset (the parity classes of a
@@ -963,7 +1069,8 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   for (int c = 0; c < ncls; ++c) {
     int rc = check_geom(gs[c], "tc_nn");
     if (rc) return rc;
-    if (gs[c].Hm != g.Hm || gs[c].Wm != g.Wm || gs[c].Nn != g.Nn || gs[c].Cs != g.Cs || gs[c].Hs != g.Hs || gs[c].Ws != g.Ws) {
+    if (gs[c].Hm != g.Hm || gs[c].Wm != g.Wm || gs[c].Nn != g.Nn || gs[c].Cs != g.Cs || gs[c].Hs != g.Hs || gs[c].Ws != g.Ws ||
+        gs[c].a_tma != g.a_tma || gs[c].Kt != g.Kt) {
       geeco_set_error("tc_nn: classes of one launch must share the row grid, source and N");
       return GEECO_ERR_INVALID;
     }
@@ -998,15 +1105,23 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   // warp split: epilogue-heavy (4 producer / 8 epilogue warps) when a tile has a single k-block
   int npw = (cl.c[0].Kpad == BK && ncls == 1) ? 4 : 8;
   if (const char* e = getenv("GEECO_TC_NPW")) { const int v = atoi(e); if (v == 4 || v == 8) npw = v; }
+  CUtensorMap amap;
+  memset(&amap, 0, sizeof(amap));
+  if (g.a_tma) {
+    int rc = make_act_tensor_map(&amap, src, g);
+    if (rc) return rc;
+    npw = 0;
+  }
 #define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
   do {                                                                                                                 \
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
                                   cudaSharedmemCarveoutMaxShared));                                                    \
     CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    tc_nn_kernel<PIECE_, NPW_><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, src, bias, mask, dst, dst_f32, epi,          \
+    tc_nn_kernel<PIECE_, NPW_><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi,    \
                                                                tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);  \
   } while (0)
-  if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
+  if (npw == 0) NN_LAUNCH(8, 0);
+  else if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
   else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }
 #undef NN_LAUNCH
   geeco_count_launch(1);
@@ -1053,7 +1168,8 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   return p;
 }
 
-long long tc_wgrad_partial_floats(const TcGeom& g, int Cout) {
+long long tc_wgrad_partial_floats(const TcGeom& g_in, int Cout) {
+  const TcGeom g = gather_view(g_in);
   WgradPlan p = wgrad_plan(g, Cout);
   long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
   long long colsum_part = (long long)g.groups * 296 * Cout;
@@ -1095,8 +1211,9 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
 }
 
 // partial-only variant: the caller performs the reduction (conv1 pixel-pair classes)
-int launch_tc_wgrad_partial(const TcGeom& g, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
+int launch_tc_wgrad_partial(const TcGeom& g_in, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
                             long long partial_cap, int want_ones, int* splits_out, int* mrows_out, cudaStream_t st) {
+  const TcGeom g = gather_view(g_in);
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) { geeco_set_error("tc_wgrad_partial: empty problem"); return GEECO_ERR_INVALID; }
   WgradPlan p;
@@ -1106,9 +1223,10 @@ int launch_tc_wgrad_partial(const TcGeom& g, int Cout, const __nv_bfloat16* src,
   return GEECO_OK;
 }
 
-int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
+int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
                     float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
                     long long dbias_group_stride, cudaStream_t st) {
+  const TcGeom g = gather_view(g_in);       // the weight-gradient kernel gathers its operands itself (dense K)
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
   WgradPlan p;
@@ -1134,12 +1252,12 @@ int launch_tc_wgrad(const TcGeom& g, int Cout, int Cw, const __nv_bfloat16* src,
 }
 
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
-                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, cudaStream_t st) {
+                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st) {
   int t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < ntaps && i < 9; ++i) t[i] = taps[i];
   const long long total = (long long)groups * rows * Kpad;
   int blocks = ceil_div(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad,
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad, Kt,
                                               t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());

@@ -12,7 +12,10 @@ struct TcGeom {
   int sy, sx;
   int ntaps;
   int dy[GEECO_MAX_TAPS], dx[GEECO_MAX_TAPS];
-  int Ktot, Kpad;             // ntaps*Cs and its round-up to 64
+  int Ktot, Kpad;             // ntaps*Kt and its round-up to 64
+  int Kt;                     // K extent of one tap in the packed weight matrix: Cs, or Cs rounded up to 64 when
+                              // the A operand is fetched by TMA (one 64-channel box per k-block, a_tma == 1)
+  int a_tma;                  // 1: A tiles come from a 5-D tiled tensor map over the source (see tc_use_tma)
   int Nn;                     // GEMM N (multiple of 16, <= 256)
   int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
   int dsy, dsx, dy0, dx0;
@@ -22,7 +25,11 @@ struct TcGeom {
 };
 
 // per-class part of a geometry (taps, K extent, destination offset) and the weight maps of a multi-class launch
-struct TcCls { int ntaps; int dy[GEECO_MAX_TAPS], dx[GEECO_MAX_TAPS]; int Ktot, Kpad, dy0, dx0; };
+struct TcCls {
+  int ntaps; int dy[GEECO_MAX_TAPS], dx[GEECO_MAX_TAPS]; int Ktot, Kpad, dy0, dx0;
+  // TMA coordinates of a tap relative to the tile origin: channel base, column, row parity, row (see make_act_tensor_map)
+  short tc0[GEECO_MAX_TAPS], twq[GEECO_MAX_TAPS], thp[GEECO_MAX_TAPS], thq[GEECO_MAX_TAPS];
+};
 struct TcClasses { int ncls; TcCls c[4]; };
 struct TcMaps { CUtensorMap m[4]; };
 
@@ -54,11 +61,11 @@ int launch_conv1pair_reduce(const float* part_even, const float* part_odd, float
 // packed bf16 weights.  mode 0 (fwd): out[g][n][t*Cs + ch] = W[g][tap_t][ch][n] ; rows = Nn
 //                       mode 1 (dgrad): out[g][ci][t*Cout + co] = W[g][tap_t][ci][co] ; rows = Cin
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
-                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, cudaStream_t st);
+                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st);
 // all weight repacks of a step as ONE launch: a table of jobs in device memory
 struct PackJob {
   const float* W; __nv_bfloat16* out; long long w_group_stride; long long start; long long total;
-  int mode, groups, Cin, Cout, Cs, ntaps, rows, Kpad; int taps[9]; int pad_;
+  int mode, groups, Cin, Cout, Cs, ntaps, rows, Kpad; int taps[9]; int Kt;   // Kt: K extent per tap (0 = Cs / Cout)
 };
 int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);

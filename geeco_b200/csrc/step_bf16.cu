@@ -34,6 +34,14 @@ struct Bf16Plan {
   bool jobs_uploaded;
 };
 
+// packed-K extent of a data-gradient class when the layer's output has `cout` channels (the planned geometry was
+// built with Cout[0]; encoders of a non-grouped layer differ only in that number)
+static int dgrad_kpad(const TcGeom& dg, int cout) {
+  const int kt = dg.a_tma ? (cout + 63) / 64 * 64 : cout;
+  return (dg.ntaps * kt + 63) / 64 * 64;
+}
+static int dgrad_kt(const TcGeom& dg, int cout) { return dg.a_tma ? (cout + 63) / 64 * 64 : cout; }
+
 static void* carve(size_t* off, char* base, size_t bytes) {
   *off = (*off + 255) & ~(size_t)255;
   void* p = base ? base + *off : nullptr;
@@ -91,12 +99,12 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
       B.w_pair[par] = B.pair ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)3 * L.Cout[0] * 64 * 2) : nullptr;
     for (int ci = 0; ci < B.n_classes; ++ci) {
       size_t t2 = 0;
-      for (int e = 0; e < 3; ++e) t2 += (size_t)L.Cin_real * ((B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64);
+      for (int e = 0; e < 3; ++e) t2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
       __nv_bfloat16* b2 = (__nv_bfloat16*)carve(ws_off, ws_base, t2 * 2);
       size_t o2 = 0;
       for (int e = 0; e < 3; ++e) {
         B.w_dg[ci][e] = b2 ? b2 + o2 : nullptr;
-        o2 += (size_t)L.Cin_real * ((B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64);
+        o2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
       }
     }
   }
@@ -127,7 +135,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
         int rc = make_weight_tensor_map(&B.fwd_map[e], B.w_fwd[e], L.Cout[e], B.fwd.Kpad, L.Cout[e]);
         if (rc) return rc;
         for (int ci = 0; ci < B.n_classes; ++ci) {
-          const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
+          const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
           rc = make_weight_tensor_map(&B.dg_map[ci][e], B.w_dg[ci][e], L.Cin_real, Kp, L.Cin_real);
           if (rc) return rc;
         }
@@ -144,11 +152,11 @@ void free_bf16(geeco_ctx* c) {
 static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
 static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, int groups, long long wstride, int Cin,
-                    int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad) {
+                    int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt) {
   PackJob j;
   memset(&j, 0, sizeof(j));
   j.W = W; j.out = out; j.w_group_stride = wstride; j.mode = mode; j.groups = groups; j.Cin = Cin; j.Cout = Cout;
-  j.Cs = Cs; j.ntaps = ntaps; j.rows = rows; j.Kpad = Kpad;
+  j.Cs = Cs; j.ntaps = ntaps; j.rows = rows; j.Kpad = Kpad; j.Kt = Kt;
   for (int i = 0; i < ntaps && i < 9; ++i) j.taps[i] = taps[i];
   j.start = bp->jobs_total;
   j.total = (long long)groups * rows * Kpad;
@@ -172,14 +180,15 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
         const float* W = c->theta + c->params[L.p_w[e]].offset;
         if (B.pair) {
           for (int par = 0; par < 2; ++par)
-            add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64);
+            add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
         } else {
-          add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad);
+          add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad,
+                  B.fwd.Kt);
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
-          const int Kp = (B.dg[ci].ntaps * L.Cout[e] + 63) / 64 * 64;
+          const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
           add_job(bp, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
-                  L.Cin_real, Kp);
+                  L.Cin_real, Kp, dgrad_kt(B.dg[ci], L.Cout[e]));
         }
       }
     }
@@ -343,7 +352,7 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
     TcGeom pg[2]; CUtensorMap pm[2]; const CUtensorMap* pmp[2];
     for (int par = 0; par < 2; ++par) {
       pg[par] = tc_conv1pair_geom(H, W, Cout, N, 1, par);
-      int rc = launch_pack_weights(w, wpp + (size_t)par * Cout * 64, 2 + par, 1, 0, Cw, Cout, 8, 6, kAllTaps, Cout, 64, st);
+      int rc = launch_pack_weights(w, wpp + (size_t)par * Cout * 64, 2 + par, 1, 0, Cw, Cout, 8, 6, kAllTaps, Cout, 64, 0, st);
       if (rc) return rc;
       rc = make_weight_tensor_map(&pm[par], wpp + (size_t)par * Cout * 64, Cout, 64, Cout);
       if (rc) return rc;
@@ -354,7 +363,7 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
   }
   TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
   __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_fwd);
-  int rc = launch_pack_weights(w, wp, 0, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, st);
+  int rc = launch_pack_weights(w, wp, 0, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, g.Kt, st);
   if (rc) return rc;
   CUtensorMap map;
   rc = make_weight_tensor_map(&map, wp, Cout, g.Kpad, Cout);
@@ -405,7 +414,7 @@ extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const v
         TcGeom dg; int taps[9];
         if (!tc_dgrad_geom(H, W, Cin, Cout, stride, py, px, N, 1, &dg, taps)) continue;
         __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_dg[ci]);
-        rc = launch_pack_weights(w, wp, 1, 1, 0, Cin, Cout, Cout, dg.ntaps, taps, Cin, dg.Kpad, st);
+        rc = launch_pack_weights(w, wp, 1, 1, 0, Cin, Cout, Cout, dg.ntaps, taps, Cin, dg.Kpad, dg.Kt, st);
         if (rc) return rc;
         rc = make_weight_tensor_map(&dm[ci], wp, Cin, dg.Kpad, Cin);
         if (rc) return rc;
