@@ -105,6 +105,107 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// epilogue shared by the gather/TMA kernel and the row-resident kernel: TMEM -> registers -> global.
+//   warp (q, half) reads TMEM lanes [32q, 32q+32) (hardware rule: q = warp index mod 4) and the 16-column chunks
+//   c0 = 16*(NHALF*i + half); a set of 4*NHALF warps serves the (tile, class) items tl with tl % nsets == set
+// ------------------------------------------------------------------------------------------------
+template <int NHALF>
+__device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl, const float* bias_s,
+                                            const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
+                                            float* __restrict__ dst_f32, int epi, int tiles_per_group, int tiles_flat, int nbuf,
+                                            uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t Mg, int q,
+                                            int half, int lane, int set, int nsets) {
+  const int BN = g.Nn;
+  const int ncls = cl.ncls;
+  {
+    const int row = q * 32 + lane;
+    // ring position / phase / owner set of the (tile, class) item, carried incrementally (no divisions)
+    uint32_t buf = 0, bphase = 0;
+    int turn = 0, group = 0, group_end = tiles_per_group;
+    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+      while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+      const uint32_t m = (uint32_t)(flat - (group_end - tiles_per_group)) * BM + row;
+      const bool valid = m < Mg;
+      int img = 0, y = 0, x = 0;
+      if (valid) decode_pixel(g, m, img, y, x);
+      const float* bias = bias_s + group * BN;
+      for (int c = 0; c < ncls; ++c) {
+        const uint32_t my_buf = buf, my_phase = bphase;
+        const bool mine = turn == set;
+        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+        if (++turn == nsets) turn = 0;
+        if (!mine) continue;
+        const TcCls& kc = cl.c[c];
+        const long long off =
+            ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + kc.dy0)) * g.Wd + (x * g.dsx + kc.dx0)) * g.Nn;
+        // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
+        uint4 pm0 = make_uint4(0, 0, 0, 0), pm1 = pm0;
+        const int c_first = half * 16;
+        if (epi == TC_EPI_MASK && valid && c_first < BN) {
+          pm0 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first));
+          pm1 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first + 8));
+        }
+        mbar_wait(&tmem_full[my_buf], my_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + my_buf * (uint32_t)BN;
+        for (int c0 = c_first; c0 < BN; c0 += 16 * NHALF) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 bb = b4[i];
+                f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+              }
+              if (epi == TC_EPI_BIAS_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+              }
+            } else if (epi == TC_EPI_MASK) {
+              uint4 m0v = pm0, m1v = pm1;
+              if (c0 != c_first) {
+                m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
+                m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
+              }
+              const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                // post-ReLU activations are >= 0: "y > 0" == magnitude bits non-zero and sign clear
+                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) f[2 * i] = 0.f;
+                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) f[2 * i + 1] = 0.f;
+              }
+            }
+            if (dst) {
+              uint4 o0, o1;
+              o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
+              o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+              o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
+              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+              *reinterpret_cast<uint4*>(dst + off + c0) = o0;
+              *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
+            }
+            if (dst_f32) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[my_buf]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward / data-gradient kernel.  PIECE = bf16 elements per cp.async (8 -> 16 B, 4 -> 8 B)
 // ------------------------------------------------------------------------------------------------
 // NPW gather-producer warps and 12 - NPW epilogue warps (8/4 by default; 4/8 when the epilogue is the bottleneck:
@@ -171,7 +272,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     constexpr int PASSES = BM / ROWS_PER_PASS;
     const int piece = threadIdx.x % PPR, rsub = threadIdx.x / PPR;
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
-    uint32_t it = 0;
+    uint32_t s = 0, sphase = 0;
+    int group = 0, group_end = tiles_per_group;
     if (PIECE == 4 && g.rowwin) {
       // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
       // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
@@ -199,14 +301,13 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
           dst_off[i][kx] = row * 128 + (((bb >> 4) ^ (uint32_t)(row & 7)) << 4) + (bb & 15u);
         }
       }
-      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x, ++it) {
-        const int group = flat / tiles_per_group;
-        const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+        while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+        const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
         const int img = (int)(m0 >> hw_shift);
         const uint32_t rem = m0 & ((1u << hw_shift) - 1u);
         const int y = (int)(rem >> w_shift), x0 = (int)(rem & ((1u << w_shift) - 1u));
-        const int s = it % stages;
-        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        mbar_wait(&empty[s], sphase ^ 1u);
         const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
         // pointer to pixel (y, x0) of the image; every copy is this plus a per-thread constant
         const __nv_bfloat16* pix = src + ((long long)((group * ipg + img) * Hs + y) * Ws + x0) * 4;
@@ -222,11 +323,12 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
           cp_async8(a_s + dst_off[i][2], ok2 ? (const void*)(sp + 8) : (const void*)src, ok2 ? 8u : 0u);
         }
         cp_async_mbar_arrive_noinc(&full[s]);
+        if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
       }
     } else {
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-        const int group = flat / tiles_per_group;
-        const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+        while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+        const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
         // per row: pointer to source pixel (ys, xs) and the coordinates themselves; an out-of-range row
         // gets ys = 1<<20 so that every tap fails the bounds test and zero-fills
         const __nv_bfloat16* rptr[PASSES];
@@ -245,9 +347,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         for (int c = 0; c < ncls; ++c) {
           const TcCls& kc = cl.c[c];
           const int nkb = kc.Kpad / BK;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % stages;
-            mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty[s], sphase ^ 1u);
             const int k = kb * BK + piece * PIECE;
             if (k < kc.Ktot) {
               int tap, ch;
@@ -265,122 +366,60 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
             }
             // asynchronous arrival: fires when this thread's copies have landed; the producer never waits
             cp_async_mbar_arrive_noinc(&full[s]);
+            if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
           }
         }
       }
     }
    }
   } else if (warp < 12) {
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    // warp w reads TMEM lanes [32*(w&3), +32) (hardware rule) and the 16-column chunks c0 = 16*(NHALF*i + half)
-    const int q = warp & 3;
-    const int half = (warp - NPW) >> 2;
-    const int row = q * 32 + lane;
-    uint32_t tl = 0;
-    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-      const int group = flat / tiles_per_group;
-      const uint32_t m = (uint32_t)(flat - group * tiles_per_group) * BM + row;
-      const bool valid = m < Mg;
-      int img = 0, y = 0, x = 0;
-      if (valid) decode_pixel(g, m, img, y, x);
-      const float* bias = bias_s + group * BN;
-      for (int c = 0; c < ncls; ++c, ++tl) {
-        const TcCls& kc = cl.c[c];
-        const int buf = tl % nbuf;
-        const long long off =
-            ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + kc.dy0)) * g.Wd + (x * g.dsx + kc.dx0)) * g.Nn;
-        mbar_wait(&tmem_full[buf], (tl / nbuf) & 1);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-        for (int c0 = half * 16; c0 < BN; c0 += 16 * NHALF) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 bb = b4[i];
-                f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
-              }
-              if (epi == TC_EPI_BIAS_RELU) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-            } else if (epi == TC_EPI_MASK) {
-              const uint4 m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
-              const uint4 m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
-              const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                // post-ReLU activations are >= 0: "y > 0" == magnitude bits non-zero and sign clear
-                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) f[2 * i] = 0.f;
-                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) f[2 * i + 1] = 0.f;
-              }
-            }
-            if (dst) {
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-              o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-              o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-              *reinterpret_cast<uint4*>(dst + off + c0) = o0;
-              *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
-            }
-            if (dst_f32) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[buf]);
-      }
-    }
+    nn_epilogue<NHALF>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                       tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1);
   } else if (warp == 12) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      uint32_t it = 0, tl = 0;
-      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-        for (int c = 0; c < ncls; ++c, ++tl) {
-          const int nkb = cl.c[c].Kpad / BK;
-          const int buf = tl % nbuf;
-          mbar_wait(&tmem_empty[buf], ((tl / nbuf) & 1) ^ 1);
+    // ===================== MMA issuer =====================
+    // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
+    // elected lane issues; ring positions and phases are carried incrementally
+    const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+    const uint32_t a_base16 = smem_u32(a_base) >> 4, b_base16 = smem_u32(b_base) >> 4;
+    const uint32_t bstage16 = (uint32_t)b_stage_bytes >> 4;
+    uint32_t s = 0, sphase = 0, buf = 0, bphase = 0;
+    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+      for (int c = 0; c < ncls; ++c) {
+        const int nkb = cl.c[c].Kpad / BK;
+        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[s], sphase);
           tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(buf * BN);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % stages;
-            mbar_wait(&full[s], (it / stages) & 1);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_base + s * A_STAGE_BYTES);
-            const uint32_t b_addr = smem_u32(b_base + s * b_stage_bytes);
+          const uint32_t a16 = a_base16 + s * (uint32_t)(A_STAGE_BYTES >> 4);
+          const uint32_t b16 = b_base16 + s * bstage16;
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < BK / 16; ++j)
-              tc_mma(d, make_desc_sw128(a_addr + j * 32, 16, 1024), make_desc_sw128(b_addr + j * 32, 16, 1024), idesc,
-                     (kb | j) != 0 ? 1u : 0u);
+              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
             tc_commit(&empty[s]);
           }
-          tc_commit(&tmem_full[buf]);
+          __syncwarp();
+          if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
         }
+        if (elect_one()) tc_commit(&tmem_full[buf]);
+        __syncwarp();
+        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
       }
     }
   } else {
     // ===================== weight tiles (and, A_TMA, activation tiles) by TMA (one thread) =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, sphase = 0;
       const int cpt = g.Kt / BK;                     // 64-channel chunks per tap (A_TMA)
+      int group = 0, group_end = tiles_per_group;
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-        const int group = flat / tiles_per_group;
+        while (flat >= group_end) { ++group; group_end += tiles_per_group; }
         int img0 = 0, y0 = 0, x0 = 0;
         if (A_TMA) {
-          const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+          const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
           decode_pixel(g, m0, img0, y0, x0);
           img0 += group * g.imgs_per_group;
         }
@@ -388,9 +427,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
           const TcCls& kc = cl.c[c];
           const int nkb = kc.Kpad / BK;
           int tap = 0, chunk = 0;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % stages;
-            mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty[s], sphase ^ 1u);
             if (A_TMA) {
               mbar_arrive_expect_tx(&full[s], (uint32_t)(b_stage_bytes + A_STAGE_BYTES));
               // box = 64 channels x the tile's pixel block; out-of-image coordinates zero-fill (= SAME padding)
@@ -401,6 +439,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
               mbar_arrive_expect_tx(&full[s], (uint32_t)b_stage_bytes);
             }
             tma_load_2d(smem_u32(b_base + s * b_stage_bytes), &maps.m[c], &full[s], kb * BK, group * g.b_rows_per_group);
+            if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
           }
         }
       }
@@ -409,6 +448,138 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   tc_fence_before();
   __syncthreads();
   if (warp == 12) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// row-resident kernel (layers whose GEMM-row grid is >= 128 pixels wide: conv2 forward / data gradient).
+// The per-tap kernels above re-read every source pixel once per tap from L2 (2.25x - 9x its size) and the
+// weights once per tile; at ~10 TB/s that L2->SM stream, not HBM, is what bounds them.  Here a tile is 128
+// consecutive pixels of ONE row: the TMA warp loads the few source rows the tile touches once (hardware
+// zero-fill = SAME padding), every tap is an MMA on a window of those rows shifted by whole pixels (128-byte
+// rows of the swizzle atom; base_offset in the descriptor), and the packed weights of all taps / classes stay
+// resident in shared memory (reloaded only when the encoder changes).
+//   warps: 12*SETS epilogue (set s serves items tl % SETS == s), then the MMA issuer, then the TMA warp.
+// ------------------------------------------------------------------------------------------------
+template <int SETS>
+__global__ void __launch_bounds__(SETS * 384 + 64, SETS == 1 ? 2 : 1)
+tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __grid_constant__ TcMaps maps,
+               const __grid_constant__ CUtensorMap amap, const float* __restrict__ bias_all,
+               const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi,
+               int tiles_per_group, int tiles_flat, int tmem_cols, int stages, int nbuf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = g.Nn;
+  const int b_slot_bytes = BN * BK * 2;
+  const int stage_bytes = rp.nrows * rp.pitch;
+  uint8_t* b_base = smem;
+  uint8_t* a_base = smem + rp.b_slots * b_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 8;
+  uint64_t* wfull = tmem_empty + 8;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+
+  constexpr int W_MMA = 12 * SETS, W_TMA = 12 * SETS + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 384); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (bias_all)
+    for (int i = threadIdx.x; i < g.groups * BN; i += blockDim.x)
+      bias_s[i] = bias_all[(long long)(i / BN) * g.bias_group_stride + (i % BN)];
+  if (warp == W_MMA) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
+  if (warp == W_TMA && lane == 0) {
+    for (int c = 0; c < cl.ncls; ++c) tma_prefetch_desc(&maps.m[c]);
+    tma_prefetch_desc(&amap);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  const uint32_t Mg = (uint32_t)g.imgs_per_group * (uint32_t)(g.Hm * g.Wm);
+  const int ncls = cl.ncls;
+
+  if (warp < W_MMA) {
+    const int set = warp / 12, w12 = warp - set * 12;
+    nn_epilogue<3>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full, tmem_empty,
+                   Mg, w12 & 3, w12 >> 2, lane, set, SETS);
+  } else if (warp == W_MMA) {
+    // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
+    // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
+    // issuing ~25 instructions per MMA was what bounded the earlier kernels (profiles/r01_ncu_notes.md).
+    const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+    const uint32_t a_base16 = smem_u32(a_base) >> 4, b_base16 = smem_u32(b_base) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, slot16 = (uint32_t)b_slot_bytes >> 4;
+    uint32_t wphase = 0, s = 0, sphase = 0, buf = 0, bphase = 0;
+    int group = 0, group_end = tiles_per_group, cur_group = -1;
+    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+      while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+      if (group != cur_group) { mbar_wait(wfull, wphase); wphase ^= 1u; cur_group = group; }
+      mbar_wait(&full[s], sphase);
+      tc_fence_after();
+      const uint32_t a_stage16 = a_base16 + s * stage16;
+      for (int c = 0; c < ncls; ++c) {
+        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + buf * (uint32_t)BN;
+        const int ns = rp.nsteps[c];
+        for (int st = 0; st < ns; ++st) {
+          const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
+          const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < BK / 16; ++j)
+              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(&tmem_full[buf]);
+        __syncwarp();
+        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+      }
+      if (elect_one()) tc_commit(&empty[s]);
+      __syncwarp();
+      if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int cur_group = -1;
+      for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x, ++it) {
+        const int group = flat / tiles_per_group;
+        if (group != cur_group) {
+          // every MMA that reads the resident weights of the previous encoder has completed once the stage of the
+          // previous tile was released
+          if (it > 0) mbar_wait(&empty[(it - 1) % stages], ((it - 1) / stages) & 1);
+          mbar_arrive_expect_tx(wfull, (uint32_t)(rp.b_slots * b_slot_bytes));
+          for (int sl = 0; sl < rp.b_slots; ++sl)
+            tma_load_2d(smem_u32(b_base + sl * b_slot_bytes), &maps.m[rp.slot_cls[sl]], wfull, rp.slot_kb[sl] * BK,
+                        group * g.b_rows_per_group);
+          cur_group = group;
+        }
+        const uint32_t m0 = (uint32_t)(flat - group * tiles_per_group) * BM;
+        int img0, y0, x0;
+        decode_pixel(g, m0, img0, y0, x0);
+        img0 += group * g.imgs_per_group;
+        const int s = it % stages;
+        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+        for (int r = 0; r < rp.nrows; ++r)
+          tma_load_5d(smem_u32(a_base + s * stage_bytes + r * rp.pitch), &amap, &full[s], rp.r_c0[r], x0 + rp.w0, rp.r_hp[r],
+                      y0 + rp.r_hq[r], img0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,9 +680,9 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
       rw_d[kx] = rw_row * 128 + (((bb >> 4) ^ (uint32_t)(rw_row & 7)) << 4) + (bb & 15u);
     }
     const long long grow = (long long)group * Mg;
+    uint32_t s = 0, sphase = 0;
     for (int it = 0; it < nkb; ++it) {
-      const int s = it % stages;
-      mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+      mbar_wait(&empty[s], sphase ^ 1u);
       const uint32_t sb = smem_u32(st_base + s * stage_bytes);
       const uint32_t mb = (uint32_t)(kb_lo + it) * 64;
       // G tile: rows = pixels, up to 128 output channels of this M tile
@@ -576,6 +747,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
         }
       }
       cp_async_mbar_arrive_noinc(&full[s]);
+      if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
     }
   } else if (warp < MMA_WARP) {
     const int q = warp & 3;
@@ -597,27 +769,35 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
       }
     }
   } else {
-    if (lane == 0) {
+    // whole warp runs the loop, one elected lane issues (see tc_nn_kernel)
+    {
       // N <= 256 per instruction: up to two MMAs per 16-pixel step (columns [0,256) and [256, nsub*64))
       const int n_lo = nsub > 4 ? 256 : nsub * 64, n_hi = nsub > 4 ? (nsub - 4) * 64 : 0;
       const uint32_t idesc_lo = make_idesc_bf16(128, n_lo, 1, 1);
       const uint32_t idesc_hi = make_idesc_bf16(128, n_hi > 0 ? n_hi : 64, 1, 1);
+      const uint64_t dtempl = make_desc_sw128(0, SUB, 1024);
+      const uint32_t base16 = smem_u32(st_base) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      uint32_t s = 0, sphase = 0;
       for (int it = 0; it < nkb; ++it) {
-        const int s = it % stages;
-        mbar_wait(&full[s], (it / stages) & 1);
+        mbar_wait(&full[s], sphase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(st_base + s * stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * SUB;
+        const uint32_t a16 = base16 + s * stage16;
+        const uint32_t b16 = a16 + (2 * SUB >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {   // 4 x 16 pixels
-          const uint64_t ad = make_desc_sw128(a_addr + j * 2048, SUB, 1024);
-          tc_mma(tmem_base, ad, make_desc_sw128(b_addr + j * 2048, SUB, 1024), idesc_lo, (it | j) != 0 ? 1u : 0u);
-          if (n_hi > 0)
-            tc_mma(tmem_base + 256, ad, make_desc_sw128(b_addr + 4 * SUB + j * 2048, SUB, 1024), idesc_hi, (it | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) {   // 4 x 16 pixels
+            const uint64_t ad = dtempl | (uint64_t)(a16 + j * 128);
+            tc_mma(tmem_base, ad, dtempl | (uint64_t)(b16 + j * 128), idesc_lo, (it | j) != 0 ? 1u : 0u);
+            if (n_hi > 0)
+              tc_mma(tmem_base + 256, ad, dtempl | (uint64_t)(b16 + (4 * SUB >> 4) + j * 128), idesc_hi, (it | j) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);
         }
-        tc_commit(&empty[s]);
+        __syncwarp();
+        if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
       }
-      tc_commit(tmem_full);
+      if (elect_one()) tc_commit(tmem_full);
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -737,15 +917,23 @@ __global__ void colsum_stage2(const float* __restrict__ part, float* __restrict_
 //   mode 1 (data gradient): out[ci][t*Cout + co] = W[tap_t][ci][co]
 //   mode 2/3 (conv1 on pixel pairs, even / odd output columns): k = (ky*2 + j)*8 + p*4 + c  ->  W[ky][kx][c][n]
 //            with kx = 2*dx + p + 1 - par, dx = j - 1 (even) or j (odd); columns outside the 3x3 window are zero
+//   mode 4 (forward stride-2 layer on pixel pairs, 2*Cs == 64): k = (ky*2 + j)*64 + p*Cs + c -> W[ky][2j+p][c][n]
 __device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int mode, int Cin, int Cout, int Cs, int ntaps,
                                             const int* taps, int Kt, int r, int k) {
-  if (mode >= 2) {
+  if (mode == 2 || mode == 3) {
     const int par = mode - 2;
     if (k >= 48 || r >= Cout) return 0.f;
     const int t = k >> 3, e = k & 7, ky = t >> 1, j = t & 1, pp = e >> 2, c = e & 3;
     const int dx = par == 0 ? j - 1 : j;
     const int kx = 2 * dx + pp + 1 - par;
     if (kx < 0 || kx > 2 || c >= Cin) return 0.f;
+    return Wg0[((long long)(ky * 3 + kx) * Cin + c) * Cout + r];
+  }
+  if (mode == 4) {
+    // forward stride-2 layer on pixel pairs (2*Cs == 64): k-block (ky, j) holds columns kx = 2j, 2j+1 of kernel row ky
+    const int blk = k >> 6, e = k & 63, ky = blk >> 1, j = blk & 1, pp = e / Cs, c = e - pp * Cs;
+    const int kx = 2 * j + pp;
+    if (ky > 2 || kx > 2 || c >= Cin || r >= Cout) return 0.f;
     return Wg0[((long long)(ky * 3 + kx) * Cin + c) * Cout + r];
   }
   const int per_tap = Kt > 0 ? Kt : (mode == 0 ? Cs : Cout);
@@ -892,6 +1080,10 @@ static bool tc_use_tma(const TcGeom& g) {
   }
   return true;
 }
+static bool tc_rows_enabled() {
+  static const bool off = getenv("GEECO_TC_NO_ROWS") != nullptr || getenv("GEECO_TC_NO_TMA") != nullptr;
+  return !off;
+}
 static void tc_tile_block(const TcGeom& g, int* bw, int* bh, int* bn) {
   *bw = g.Wm < 128 ? g.Wm : 128;
   *bh = g.Hm < 128 / *bw ? g.Hm : 128 / *bw;
@@ -907,16 +1099,17 @@ static void finish_k(TcGeom* g) {
 // the same geometry as the software-gather kernels (weight gradient) see it: dense K = ntaps * Cs
 static TcGeom gather_view(const TcGeom& g) {
   TcGeom v = g;
-  v.a_tma = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 63) / 64 * 64;
+  v.a_tma = 0; v.rows = 0; v.wpack = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 63) / 64 * 64;
   return v;
 }
 
 // 5-D tensor map over a bf16 NHWC activation for the tile blocks of geometry g (see tc_use_tma)
-static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g) {
+static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int row_box_pw = 0) {
   PFN_encodeTiled fn = encode_tiled_fn();
   if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
   int bw, bh, bn;
   tc_tile_block(g, &bw, &bh, &bn);
+  if (row_box_pw > 0) { bw = row_box_pw; bh = 1; bn = 1; }       // row-resident kernel: one row of pw pixels per box
   const cuuint64_t imgs = (cuuint64_t)g.imgs_per_group * g.groups;
   const cuuint64_t row = (cuuint64_t)g.Ws * g.Cs * 2, img = row * g.Hs;
   cuuint64_t gdim[5], gstr[4];
@@ -960,6 +1153,9 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
   finish_k(&g);
+  if (tc_rows_enabled() && stride == 2 && Cs == 32 && Wo % 128 == 0 && !((H | W) & 1) && g.hw_shift >= 0 && pt == 0 && pl == 0) {
+    g.rows = 2; g.wpack = 4; g.a_tma = 0; g.Kt = 64; g.Ktot = g.Kpad = 6 * 64;
+  }
   g.rowwin = (Cs == 4 && stride == 1 && Wo % 128 == 0 && g.hw_shift >= 0) ? 1 : 0;
   return g;
 }
@@ -1020,6 +1216,7 @@ bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, 
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cin; g.bias_group_stride = 0;
   finish_geom(&g);
   finish_k(&g);
+  if (tc_rows_enabled() && g.a_tma && g.Kt == 64 && g.Wm % 128 == 0) g.rows = 1;
   *out = g;
   return true;
 }
@@ -1053,6 +1250,93 @@ static void fill_class(TcCls* c, const TcGeom& g) {
   }
 }
 
+// builds the row program of a row-resident launch (see tc_rows_kernel) and runs it
+static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const TcMaps& maps, const __nv_bfloat16* src,
+                          const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
+                          cudaStream_t st) {
+  const TcGeom& g = gs[0];
+  TcRowProg rp;
+  memset(&rp, 0, sizeof(rp));
+  if (g.rows == 2) {
+    // forward stride-2 layer, source viewed as pixel pairs: rows 2*oy + ky, windows at pair ox (kx = 0, 1) and ox+1 (kx = 2)
+    if (ncls != 1) { geeco_set_error("tc_rows: the pixel-pair forward has one class"); return GEECO_ERR_INVALID; }
+    rp.nrows = 3; rp.w0 = 0; rp.pw = 136;
+    for (int ky = 0; ky < 3; ++ky) { rp.r_c0[ky] = 0; rp.r_hp[ky] = (short)(ky & 1); rp.r_hq[ky] = (short)(ky >> 1); }
+    rp.pitch = rp.pw * 128;
+    rp.nsteps[0] = 6;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int j = 0; j < 2; ++j) {
+        rp.a_off[0][ky * 2 + j] = ky * rp.pitch + j * 128;
+        rp.b_slot[0][ky * 2 + j] = (short)(ky * 2 + j);
+        rp.slot_cls[ky * 2 + j] = 0; rp.slot_kb[ky * 2 + j] = (short)(ky * 2 + j);
+      }
+    rp.b_slots = 6;
+  } else {
+    // unit-stride source (data gradient of a stride-2 layer): rows = the distinct dy of all classes, windows = dx shifts
+    int dys[GEECO_MAX_TAPS], ndy = 0, mindx = 1 << 20, maxdx = -(1 << 20);
+    for (int c = 0; c < ncls; ++c)
+      for (int t = 0; t < gs[c].ntaps; ++t) {
+        bool seen = false;
+        for (int i = 0; i < ndy; ++i) seen = seen || dys[i] == gs[c].dy[t];
+        if (!seen) dys[ndy++] = gs[c].dy[t];
+        if (gs[c].dx[t] < mindx) mindx = gs[c].dx[t];
+        if (gs[c].dx[t] > maxdx) maxdx = gs[c].dx[t];
+      }
+    if (ndy > 4) { geeco_set_error("tc_rows: %d source rows per tile > 4", ndy); return GEECO_ERR_INVALID; }
+    rp.nrows = ndy; rp.w0 = mindx; rp.pw = (128 + maxdx - mindx + 7) / 8 * 8;
+    rp.pitch = rp.pw * 128;
+    for (int i = 0; i < ndy; ++i) { rp.r_c0[i] = 0; rp.r_hp[i] = 0; rp.r_hq[i] = (short)dys[i]; }
+    int slot = 0;
+    for (int c = 0; c < ncls; ++c) {
+      rp.nsteps[c] = gs[c].ntaps;
+      for (int t = 0; t < gs[c].ntaps; ++t, ++slot) {
+        int r = 0;
+        while (dys[r] != gs[c].dy[t]) ++r;
+        rp.a_off[c][t] = r * rp.pitch + (gs[c].dx[t] - mindx) * 128;
+        rp.b_slot[c][t] = (short)slot;
+        rp.slot_cls[slot] = (short)c; rp.slot_kb[slot] = (short)t;
+      }
+    }
+    rp.b_slots = slot;
+  }
+  if (rp.pw > 256) { geeco_set_error("tc_rows: box of %d pixels > 256", rp.pw); return GEECO_ERR_INVALID; }
+  CUtensorMap amap;
+  int rc = make_act_tensor_map(&amap, src, g, rp.pw);
+  if (rc) return rc;
+  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  const int tiles_per_group = ceil_div(Mg, BM);
+  const int tiles_flat = tiles_per_group * g.groups;
+  const int stage_bytes = rp.nrows * rp.pitch;
+  const int b_bytes = rp.b_slots * g.Nn * BK * 2;
+  const int tail_bytes = 512 + g.groups * g.Nn * 4;
+  // two co-resident CTAs with one epilogue set each when two stages fit twice, else one CTA with two sets
+  int per_sm = 2 * (1024 + b_bytes + 2 * stage_bytes + tail_bytes) <= (int)SMEM_BUDGET ? 2 : 1;
+  if (const char* e = getenv("GEECO_TC_ROWS_PERSM")) { const int v = atoi(e); if (v == 1 || (v == 2 && per_sm == 2)) per_sm = v; }
+  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - b_bytes - tail_bytes) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) { geeco_set_error("tc_rows: stage of %d bytes does not fit twice", stage_bytes); return GEECO_ERR_INVALID; }
+  int nbuf = 2;
+  while (nbuf < 8 && 2 * nbuf * g.Nn <= 512 / per_sm) nbuf *= 2;
+  const int tmem_cols = next_pow2_cols(nbuf * g.Nn);
+  const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * stage_bytes + tail_bytes;
+  int ctas = num_sms() * per_sm;
+  if (ctas > tiles_flat) ctas = tiles_flat;
+#define ROWS_LAUNCH(SETS_)                                                                                              \
+  do {                                                                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(tc_rows_kernel<SETS_>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
+                                  cudaSharedmemCarveoutMaxShared));                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(tc_rows_kernel<SETS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    tc_rows_kernel<SETS_><<<ctas, SETS_ * 384 + 64, smem, st>>>(g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,      \
+                                                                tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);  \
+  } while (0)
+  if (per_sm == 2) ROWS_LAUNCH(1); else ROWS_LAUNCH(2);
+#undef ROWS_LAUNCH
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+
 // ncls geometries that differ only in taps / K extent / destination offset (the parity classes of a
 // strided data-gradient) run as ONE launch; ncls == 1 is the plain forward / single-class case
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
@@ -1070,7 +1354,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     int rc = check_geom(gs[c], "tc_nn");
     if (rc) return rc;
     if (gs[c].Hm != g.Hm || gs[c].Wm != g.Wm || gs[c].Nn != g.Nn || gs[c].Cs != g.Cs || gs[c].Hs != g.Hs || gs[c].Ws != g.Ws ||
-        gs[c].a_tma != g.a_tma || gs[c].Kt != g.Kt) {
+        gs[c].a_tma != g.a_tma || gs[c].Kt != g.Kt || gs[c].rows != g.rows) {
       geeco_set_error("tc_nn: classes of one launch must share the row grid, source and N");
       return GEECO_ERR_INVALID;
     }
@@ -1079,6 +1363,10 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   }
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
+  if (g.rows) {
+    if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }
+    return launch_tc_rows(gs, ncls, cl, maps, src, bias, mask, dst, dst_f32, epi, st);
+  }
   const int tiles_per_group = ceil_div(Mg, BM);
   const int tiles_flat = tiles_per_group * g.groups;
   const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;

@@ -16,6 +16,9 @@ struct TcGeom {
   int Kt;                     // K extent of one tap in the packed weight matrix: Cs, or Cs rounded up to 64 when
                               // the A operand is fetched by TMA (one 64-channel box per k-block, a_tma == 1)
   int a_tma;                  // 1: A tiles come from a 5-D tiled tensor map over the source (see tc_use_tma)
+  int rows;                   // row-resident kernel (tc_rows_kernel): 0 no, 1 unit-stride source (data gradient of a
+                              // stride-2 layer), 2 forward stride-2 layer on pixel pairs (Cs == 32)
+  int wpack;                  // weight packing mode of the forward operand (0 tap-major, 4 pixel pairs; see pack_value)
   int Nn;                     // GEMM N (multiple of 16, <= 256)
   int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
   int dsy, dsx, dy0, dx0;
@@ -31,6 +34,17 @@ struct TcCls {
   short tc0[GEECO_MAX_TAPS], twq[GEECO_MAX_TAPS], thp[GEECO_MAX_TAPS], thq[GEECO_MAX_TAPS];
 };
 struct TcClasses { int ncls; TcCls c[4]; };
+// Program of a row-resident launch: per tile the TMA warp loads `nrows` source rows (one box of `pw` pixels x 64
+// channels each) and the MMA warp runs, per class, `nsteps` shifted-window MMAs against resident weight k-blocks.
+struct TcRowProg {
+  int nrows, pw, pitch, w0;                       // pitch = pw * 128 bytes (pw % 8 == 0)
+  short r_c0[4], r_hp[4], r_hq[4];                // TMA coordinates of a row: channel base, row parity, row offset
+  int nsteps[4];
+  int a_off[4][GEECO_MAX_TAPS];                   // byte offset of the 128-pixel window inside the stage
+  short b_slot[4][GEECO_MAX_TAPS];                // resident weight k-block used by the step
+  int b_slots;
+  short slot_cls[4 * GEECO_MAX_TAPS], slot_kb[4 * GEECO_MAX_TAPS];   // where a slot comes from: class map, k-block
+};
 struct TcMaps { CUtensorMap m[4]; };
 
 enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3 };

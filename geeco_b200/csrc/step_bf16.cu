@@ -182,8 +182,8 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
           for (int par = 0; par < 2; ++par)
             add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
         } else {
-          add_job(bp, W, B.w_fwd[e], 0, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e], B.fwd.Kpad,
-                  B.fwd.Kt);
+          add_job(bp, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
+                  B.fwd.Kpad, B.fwd.Kt);
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
@@ -363,7 +363,7 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
   }
   TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
   __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_fwd);
-  int rc = launch_pack_weights(w, wp, 0, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, g.Kt, st);
+  int rc = launch_pack_weights(w, wp, g.wpack, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, g.Kt, st);
   if (rc) return rc;
   CUtensorMap map;
   rc = make_weight_tensor_map(&map, wp, Cout, g.Kpad, Cout);

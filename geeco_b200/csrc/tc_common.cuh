@@ -60,6 +60,14 @@ __device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, b
   asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nthreads) : "memory");
 }
 
+// one lane of a converged warp (the tcgen05 issue instructions take warp-uniform operands: the WHOLE warp runs
+// the issue loop so that the compiler keeps descriptors in uniform registers, and only the instruction is elected)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- cp.async (LDGSTS) ---------------------------------------------------------------------------
 // 16-byte global->shared copy; src_bytes = 0 zero-fills the destination (padding / out-of-image taps)
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -140,6 +148,15 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+// the same for a matrix whose first row does not sit on a 1024-byte boundary of the swizzle pattern (a window that
+// starts r rows into an 8-row atom): base_offset [49,52) = (address >> 7) & 7
+__device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+#ifdef GEECO_DESC_BASE_OFFSET
+  return make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
+#else
+  return make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes);
+#endif
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).

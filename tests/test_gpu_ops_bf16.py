@@ -23,6 +23,8 @@ CASES = [
     (1, 64, 8, 4, 32, 1),        # 4096 rows: 32 tiles, rgbd-like
     (3, 32, 32, 32, 48, 2),      # 768 rows: multi-tile persistent loop
     (40, 2, 256, 256, 256, 2),   # conv8-like at batch 40
+    (2, 256, 32, 32, 48, 2),     # conv2 itself: row-resident kernels (pixel-pair forward, 4-class data gradient)
+    (1, 512, 32, 32, 48, 2),     # 256-pixel output rows: two row tiles per row
 ]
 
 
