@@ -109,7 +109,7 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 //   warp (q, half) reads TMEM lanes [32q, 32q+32) (hardware rule: q = warp index mod 4) and the 16-column chunks
 //   c0 = 16*(NHALF*i + half); a set of 4*NHALF warps serves the (tile, class) items tl with tl % nsets == set
 // ------------------------------------------------------------------------------------------------
-template <int NHALF>
+template <int NHALF, bool MASK>
 __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl, const float* bias_s,
                                             const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
                                             float* __restrict__ dst_f32, int epi, int tiles_per_group, int tiles_flat, int nbuf,
@@ -141,7 +141,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
         // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
         uint4 pm0 = make_uint4(0, 0, 0, 0), pm1 = pm0;
         const int c_first = half * 16;
-        if (epi == TC_EPI_MASK && valid && c_first < BN) {
+        if (MASK && valid && c_first < BN) {
           pm0 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first));
           pm1 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first + 8));
         }
@@ -156,7 +156,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS) {
+            if (!MASK && (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS)) {
               const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -167,7 +167,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 #pragma unroll
                 for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
               }
-            } else if (epi == TC_EPI_MASK) {
+            } else if (MASK) {
               uint4 m0v = pm0, m1v = pm1;
               if (c0 != c_first) {
                 m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
@@ -210,7 +210,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 // ------------------------------------------------------------------------------------------------
 // NPW gather-producer warps and 12 - NPW epilogue warps (8/4 by default; 4/8 when the epilogue is the bottleneck:
 // one k-block per tile as in conv1), then the MMA warp and the TMA warp
-template <int PIECE, int NPW>
+template <int PIECE, int NPW, bool MASK>
 __global__ void __launch_bounds__(NN_THREADS, 2)
 tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps,
              const __grid_constant__ CUtensorMap amap, const __nv_bfloat16* __restrict__ src,
@@ -373,8 +373,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     }
    }
   } else if (warp < 12) {
-    nn_epilogue<NHALF>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                       tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1);
+    nn_epilogue<NHALF, MASK>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                             tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1);
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
     // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
@@ -458,10 +458,11 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
 // zero-fill = SAME padding), every tap is an MMA on a window of those rows shifted by whole pixels (128-byte
 // rows of the swizzle atom; base_offset in the descriptor), and the packed weights of all taps / classes stay
 // resident in shared memory (reloaded only when the encoder changes).
-//   warps: 12*SETS epilogue (set s serves items tl % SETS == s), then the MMA issuer, then the TMA warp.
+//   warps: EPW*SETS epilogue (set s serves every SETS-th (tile, class) item; EPW = 8 when N <= 32, else 12), then the
+//   MMA issuer, then the TMA warp.
 // ------------------------------------------------------------------------------------------------
-template <int SETS>
-__global__ void __launch_bounds__(SETS * 384 + 64, SETS == 1 ? 2 : 1)
+template <int SETS, int EPW, bool MASK>
+__global__ void __launch_bounds__(SETS * EPW * 32 + 64, SETS == 1 ? 2 : 1)
 tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __grid_constant__ TcMaps maps,
                const __grid_constant__ CUtensorMap amap, const float* __restrict__ bias_all,
                const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi,
@@ -482,11 +483,11 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(wfull + 1);
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
-  constexpr int W_MMA = 12 * SETS, W_TMA = 12 * SETS + 1;
+  constexpr int W_MMA = EPW * SETS, W_TMA = EPW * SETS + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 384); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPW * 32); }
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
@@ -506,9 +507,9 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   const int ncls = cl.ncls;
 
   if (warp < W_MMA) {
-    const int set = warp / 12, w12 = warp - set * 12;
-    nn_epilogue<3>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full, tmem_empty,
-                   Mg, w12 & 3, w12 >> 2, lane, set, SETS);
+    const int set = warp / EPW, ws = warp - set * EPW;
+    nn_epilogue<EPW / 4, MASK>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS);
   } else if (warp == W_MMA) {
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
     // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
@@ -1321,15 +1322,19 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
   const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * stage_bytes + tail_bytes;
   int ctas = num_sms() * per_sm;
   if (ctas > tiles_flat) ctas = tiles_flat;
-#define ROWS_LAUNCH(SETS_)                                                                                              \
+#define ROWS_LAUNCH(SETS_, EPW_, MASK_)                                                                                 \
   do {                                                                                                                  \
-    CUDA_TRY(cudaFuncSetAttribute(tc_rows_kernel<SETS_>, cudaFuncAttributePreferredSharedMemoryCarveout,                \
-                                  cudaSharedmemCarveoutMaxShared));                                                     \
-    CUDA_TRY(cudaFuncSetAttribute(tc_rows_kernel<SETS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    tc_rows_kernel<SETS_><<<ctas, SETS_ * 384 + 64, smem, st>>>(g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,      \
-                                                                tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);  \
+    auto kern = tc_rows_kernel<SETS_, EPW_, MASK_>;                                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
+    kern<<<ctas, SETS_ * EPW_ * 32 + 64, smem, st>>>(g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,                \
+                                                     tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);             \
   } while (0)
-  if (per_sm == 2) ROWS_LAUNCH(1); else ROWS_LAUNCH(2);
+#define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
+#define ROWS_LAUNCH_S(MASK_) do { if (per_sm == 2) ROWS_LAUNCH_E(1, MASK_); else ROWS_LAUNCH_E(2, MASK_); } while (0)
+  if (epi == TC_EPI_MASK) ROWS_LAUNCH_S(true); else ROWS_LAUNCH_S(false);
+#undef ROWS_LAUNCH_S
+#undef ROWS_LAUNCH_E
 #undef ROWS_LAUNCH
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
@@ -1363,8 +1368,8 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   }
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
+  if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }     // experiment: time without output stores
   if (g.rows) {
-    if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }
     return launch_tc_rows(gs, ncls, cl, maps, src, bias, mask, dst, dst_f32, epi, st);
   }
   const int tiles_per_group = ceil_div(Mg, BM);
@@ -1389,7 +1394,6 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   if (const char* e = getenv("GEECO_TC_CTAS")) { const int v = atoi(e); if (v > 0) ctas = v; }
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
   if (ctas > tiles_flat) ctas = tiles_flat;
-  if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }     // experiment: time without output stores
   // warp split: epilogue-heavy (4 producer / 8 epilogue warps) when a tile has a single k-block
   int npw = (cl.c[0].Kpad == BK && ncls == 1) ? 4 : 8;
   if (const char* e = getenv("GEECO_TC_NPW")) { const int v = atoi(e); if (v == 4 || v == 8) npw = v; }
@@ -1400,18 +1404,21 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     if (rc) return rc;
     npw = 0;
   }
-#define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
+#define NN_LAUNCH_M(PIECE_, NPW_, MASK_)                                                                               \
   do {                                                                                                                 \
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributePreferredSharedMemoryCarveout,           \
-                                  cudaSharedmemCarveoutMaxShared));                                                    \
-    CUDA_TRY(cudaFuncSetAttribute(tc_nn_kernel<PIECE_, NPW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    tc_nn_kernel<PIECE_, NPW_><<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi,    \
-                                                               tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);  \
+    auto kern = tc_nn_kernel<PIECE_, NPW_, MASK_>;                                                                     \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
+    kern<<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,        \
+                                         tiles_flat, tmem_cols, stages, nbuf);                                         \
   } while (0)
+#define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
+  do { if (epi == TC_EPI_MASK) NN_LAUNCH_M(PIECE_, NPW_, true); else NN_LAUNCH_M(PIECE_, NPW_, false); } while (0)
   if (npw == 0) NN_LAUNCH(8, 0);
   else if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
   else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }
 #undef NN_LAUNCH
+#undef NN_LAUNCH_M
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

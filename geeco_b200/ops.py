@@ -96,14 +96,14 @@ def conv2d_same_bf16(x, w, b=None, stride=1, relu=True, want_f32=False):
   return (y, y32) if want_f32 else y
 
 
-def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True):
+def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True, need_dw=True):
   """Tensor-core gradients of conv2d_same_bf16: returns (dw fp32, db fp32, dx bf16)."""
   lib = _lib.load()
   x, w, dy_pre = _req_bf16(x, 'x'), _req(w, 'w'), _req_bf16(dy_pre, 'dy_pre')
   N, H, W, Cin = x.shape
   Cw, Cout = w.shape[2], w.shape[3]
-  dw = torch.empty_like(w)
-  db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+  dw = torch.empty_like(w) if need_dw else None
+  db = torch.empty(Cout, dtype=torch.float32, device=x.device) if need_dw else None
   dx = torch.zeros_like(x) if need_dx else None
   n = int(lib.geeco_conv2d_bf16_scratch_bytes(N, H, W, Cin, Cout, stride))
   scratch = torch.empty(n, dtype=torch.uint8, device=x.device)

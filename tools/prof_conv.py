@@ -19,7 +19,8 @@ def main():
   ap.add_argument('--layer', type=int, default=1)
   ap.add_argument('--batch', type=int, default=192)
   ap.add_argument('--reps', type=int, default=3)
-  ap.add_argument('--what', type=str, default='fwd,bwd')
+  ap.add_argument('--what', type=str, default='fwd,bwd')     # fwd, bwd (wgrad + dgrad), wgrad, dgrad
+  ap.add_argument('--nomask', action='store_true')
   a = ap.parse_args()
   H, Cin, Cw, Cout, s = LAYERS[a.layer]
   dev = torch.device('cuda:0')
@@ -48,11 +49,20 @@ def main():
   in_b, out_b = a.batch * H * H * Cin * 2, M * Cout * 2
   if 'fwd' in a.what:
     timed(lambda: ops.conv2d_same_bf16(x, w, b, stride=s), 'conv%d fwd' % a.layer, flops, in_b + out_b)
+  extra(a, ops, x, w, dy, s, timed, flops, in_b, out_b)
   if 'bwd' in a.what:
     need_dx = a.layer > 1
     timed(lambda: ops.conv2d_same_bwd_bf16(x, w, dy, stride=s, relu_mask_x=x if need_dx else None, need_dx=need_dx),
           'conv%d wgrad%s' % (a.layer, '+dgrad' if need_dx else ''), flops * (2 if need_dx else 1),
           in_b + out_b + (2 * in_b + out_b if need_dx else 0))
+
+
+def extra(a, ops, x, w, dy, s, timed, flops, in_b, out_b):
+  if 'wgrad' in a.what.split(','):
+    timed(lambda: ops.conv2d_same_bwd_bf16(x, w, dy, stride=s, need_dx=False), 'conv%d wgrad' % a.layer, flops, in_b + out_b)
+  if 'dgrad' in a.what.split(',') and a.layer > 1:
+    timed(lambda: ops.conv2d_same_bwd_bf16(x, w, dy, stride=s, relu_mask_x=None if a.nomask else x, need_dx=True, need_dw=False),
+          'conv%d dgrad%s' % (a.layer, ' (no mask)' if a.nomask else ''), flops, out_b + in_b * (1 if a.nomask else 2))
 
 
 if __name__ == '__main__':
