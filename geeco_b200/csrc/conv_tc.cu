@@ -1453,7 +1453,8 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   p.stages = (int)((SMEM_BUDGET / p.per_sm - 1024 - 512) / stage_bytes);
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const int base = p.m_tiles * p.n_chunks * g.groups;
-  int want = (num_sms() * p.per_sm + base - 1) / base;
+  // one wave: never more CTAs than can be resident at once (a 149th CTA on 148 SMs doubles the kernel time)
+  int want = (num_sms() * p.per_sm) / base;
   if (want < 1) want = 1;
   if (want > p.total_kb / 8) want = p.total_kb / 8 > 0 ? p.total_kb / 8 : 1;     // >= 8 k-blocks per split
   p.kb_per_split = (p.total_kb + want - 1) / want;

@@ -104,7 +104,7 @@ def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True,
   Cw, Cout = w.shape[2], w.shape[3]
   dw = torch.empty_like(w) if need_dw else None
   db = torch.empty(Cout, dtype=torch.float32, device=x.device) if need_dw else None
-  dx = torch.zeros_like(x) if need_dx else None
+  dx = torch.empty_like(x) if need_dx else None   # every pixel is written by one parity class
   n = int(lib.geeco_conv2d_bf16_scratch_bytes(N, H, W, Cin, Cout, stride))
   scratch = torch.empty(n, dtype=torch.uint8, device=x.device)
   _lib.check(lib.geeco_conv2d_same_bwd_bf16(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx),
