@@ -109,98 +109,102 @@ __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
 //   warp (q, half) reads TMEM lanes [32q, 32q+32) (hardware rule: q = warp index mod 4) and the 16-column chunks
 //   c0 = 16*(NHALF*i + half); a set of 4*NHALF warps serves the (tile, class) items tl with tl % nsets == set
 // ------------------------------------------------------------------------------------------------
-template <int NHALF, bool MASK>
+// EPI: compile-time epilogue of the two hot cases (TC_EPI_BIAS_RELU / TC_EPI_MASK with a bf16 destination only);
+// EPI_GENERIC keeps every option (runtime `epi`, optional fp32 copy, optional bf16 destination).
+constexpr int EPI_GENERIC = 7;
+template <int NHALF, int EPI>
 __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl, const float* bias_s,
                                             const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
                                             float* __restrict__ dst_f32, int epi, int tiles_per_group, int tiles_flat, int nbuf,
                                             uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t Mg, int q,
                                             int half, int lane, int set, int nsets) {
+  constexpr bool MASK = EPI == TC_EPI_MASK;
+  constexpr bool GEN = EPI == EPI_GENERIC;
   const int BN = g.Nn;
   const int ncls = cl.ncls;
-  {
-    const int row = q * 32 + lane;
-    // ring position / phase / owner set of the (tile, class) item, carried incrementally (no divisions)
-    uint32_t buf = 0, bphase = 0;
-    int turn = 0, group = 0, group_end = tiles_per_group;
-    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-      while (flat >= group_end) { ++group; group_end += tiles_per_group; }
-      const uint32_t m = (uint32_t)(flat - (group_end - tiles_per_group)) * BM + row;
-      const bool valid = m < Mg;
-      int img = 0, y = 0, x = 0;
-      if (valid) decode_pixel(g, m, img, y, x);
-      const float* bias = bias_s + group * BN;
-      for (int c = 0; c < ncls; ++c) {
-        const uint32_t my_buf = buf, my_phase = bphase;
-        const bool mine = turn == set;
-        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
-        if (++turn == nsets) turn = 0;
-        if (!mine) continue;
-        const TcCls& kc = cl.c[c];
-        const long long off =
-            ((((long long)group * g.imgs_per_group + img) * g.Hd + (y * g.dsy + kc.dy0)) * g.Wd + (x * g.dsx + kc.dx0)) * g.Nn;
-        // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
-        uint4 pm0 = make_uint4(0, 0, 0, 0), pm1 = pm0;
-        const int c_first = half * 16;
-        if (MASK && valid && c_first < BN) {
-          pm0 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first));
-          pm1 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first + 8));
-        }
-        mbar_wait(&tmem_full[my_buf], my_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + my_buf * (uint32_t)BN;
-        for (int c0 = c_first; c0 < BN; c0 += 16 * NHALF) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            float f[16];
+  const int row = q * 32 + lane;
+  const int c_first = half * 16;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  // ring position / phase / owner set of the (tile, class) item, carried incrementally (no divisions)
+  uint32_t buf = 0, bphase = 0;
+  int turn = 0, group = 0, group_end = tiles_per_group;
+  for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+    while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+    const uint32_t m = (uint32_t)(flat - (group_end - tiles_per_group)) * BM + row;
+    const bool valid = m < Mg;
+    int img = 0, y = 0, x = 0;
+    if (valid) decode_pixel(g, m, img, y, x);
+    // destination pixel of class (0, 0); a class adds dy0 rows and dx0 columns
+    const long long pix00 = (((long long)group * g.imgs_per_group + img) * g.Hd + y * g.dsy) * g.Wd + x * g.dsx;
+    const float* bias = bias_s + group * BN;
+    for (int c = 0; c < ncls; ++c) {
+      const uint32_t my_buf = buf, my_phase = bphase;
+      const bool mine = turn == set;
+      if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+      if (++turn == nsets) turn = 0;
+      if (!mine) continue;
+      const TcCls& kc = cl.c[c];
+      const long long off = (pix00 + kc.dy0 * g.Wd + kc.dx0) * BN;
+      // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
+      uint4 pm0 = make_uint4(0, 0, 0, 0), pm1 = pm0;
+      if (MASK && valid && c_first < BN) {
+        pm0 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first));
+        pm1 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first + 8));
+      }
+      mbar_wait(&tmem_full[my_buf], my_phase);
+      tc_fence_after();
+      const uint32_t taddr = lane_addr + my_buf * (uint32_t)BN;
+      for (int c0 = c_first; c0 < BN; c0 += 16 * NHALF) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (!MASK && (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS)) {
-              const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (EPI == TC_EPI_BIAS_RELU || (GEN && (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS))) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 bb = b4[i];
-                f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
-              }
-              if (epi == TC_EPI_BIAS_RELU) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-              }
-            } else if (MASK) {
-              uint4 m0v = pm0, m1v = pm1;
-              if (c0 != c_first) {
-                m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
-                m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
-              }
-              const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                // post-ReLU activations are >= 0: "y > 0" == magnitude bits non-zero and sign clear
-                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) f[2 * i] = 0.f;
-                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) f[2 * i + 1] = 0.f;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = b4[i];
+              f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
             }
-            if (dst) {
-              uint4 o0, o1;
-              o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-              o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-              o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-              o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-              *reinterpret_cast<uint4*>(dst + off + c0) = o0;
-              *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
-            }
-            if (dst_f32) {
+            if (EPI == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_RELU) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+          } else if (MASK) {
+            uint4 m0v = pm0, m1v = pm1;
+            if (c0 != c_first) {
+              m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
+              m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
+            }
+            const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // post-ReLU activations are >= 0 (never -0): "y > 0" == any bit of the bf16 set
+              if ((mw[i] & 0xffffu) == 0) f[2 * i] = 0.f;
+              if ((mw[i] >> 16) == 0) f[2 * i + 1] = 0.f;
             }
           }
+          if (!GEN || dst) {
+            uint4 o0, o1;
+            o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
+            o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
+            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+            *reinterpret_cast<uint4*>(dst + off + c0) = o0;
+            *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
+          }
+          if (GEN && dst_f32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(dst_f32 + off + c0 + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[my_buf]);
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[my_buf]);
     }
   }
 }
@@ -210,7 +214,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 // ------------------------------------------------------------------------------------------------
 // NPW gather-producer warps and 12 - NPW epilogue warps (8/4 by default; 4/8 when the epilogue is the bottleneck:
 // one k-block per tile as in conv1), then the MMA warp and the TMA warp
-template <int PIECE, int NPW, bool MASK>
+template <int PIECE, int NPW, int EPI>
 __global__ void __launch_bounds__(NN_THREADS, 2)
 tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps maps,
              const __grid_constant__ CUtensorMap amap, const __nv_bfloat16* __restrict__ src,
@@ -274,33 +278,14 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     const uint32_t pbyte = (uint32_t)piece * PIECE * 2;
     uint32_t s = 0, sphase = 0;
     int group = 0, group_end = tiles_per_group;
-    if (PIECE == 4 && g.rowwin) {
-      // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block;
-      // a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies from one address
-      // everything that does not depend on the tile is hoisted: thread t owns the (row, ky) pairs p = t + i*PROD,
-      // row = p & 127, ky = p >> 7; the three destination byte offsets and the source offset per pair are constants
+    if (PIECE == 4 && NPW == 4 && g.rowwin) {
+      // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block.
+      // Producer thread t owns GEMM row t; a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies.
+      // Only a handful of values stay live across tiles (the destination offsets are recomputed: two ALU ops each).
       const TcCls& k0 = cl.c[0];
-      constexpr int NP = (3 * BM + PROD_THREADS - 1) / PROD_THREADS;
-      uint32_t dst_off[NP][3];
-      long long src_off[NP];
-      int pdy[NP], prow[NP];
-      bool pvalid[NP];
-      const int dx0 = k0.dx[0];
+      const int dx0 = k0.dx[0], dy0 = k0.dy[0];                   // taps are dy0 + ky, dx0 + kx
       const int Hs = g.Hs, Ws = g.Ws, ipg = g.imgs_per_group, hw_shift = g.hw_shift, w_shift = g.w_shift;
-#pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        const int p = threadIdx.x + i * PROD_THREADS;
-        pvalid[i] = p < 3 * BM;
-        const int row = p & (BM - 1), ky = pvalid[i] ? (p >> 7) : 0;
-        prow[i] = row;
-        pdy[i] = k0.dy[ky * 3];
-        src_off[i] = ((long long)pdy[i] * Ws + row + dx0) * 4;
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const uint32_t bb = (uint32_t)(ky * 24 + kx * 8);
-          dst_off[i][kx] = row * 128 + (((bb >> 4) ^ (uint32_t)(row & 7)) << 4) + (bb & 15u);
-        }
-      }
+      const uint32_t row = threadIdx.x, rsw = row & 7u, rbase = row * 128u;
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
         while (flat >= group_end) { ++group; group_end += tiles_per_group; }
         const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
@@ -308,24 +293,28 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         const uint32_t rem = m0 & ((1u << hw_shift) - 1u);
         const int y = (int)(rem >> w_shift), x0 = (int)(rem & ((1u << w_shift) - 1u));
         mbar_wait(&empty[s], sphase ^ 1u);
-        const uint32_t a_s = smem_u32(a_base + s * A_STAGE_BYTES);
-        // pointer to pixel (y, x0) of the image; every copy is this plus a per-thread constant
-        const __nv_bfloat16* pix = src + ((long long)((group * ipg + img) * Hs + y) * Ws + x0) * 4;
+        const uint32_t a_row = smem_u32(a_base + s * A_STAGE_BYTES) + rbase;
+        const int xl = x0 + (int)row + dx0;                         // leftmost source column of this row's window
+        const bool in0 = xl >= 0, in2 = xl + 2 < Ws;                // kx = 1 is always inside (Ws >= 2)
+        // pointer to source pixel (y + dy0, xl)
+        const __nv_bfloat16* sp = src + ((long long)((group * ipg + img) * Hs + (y + dy0)) * Ws + xl) * 4;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
-          if (!pvalid[i]) continue;
-          const int xl = x0 + prow[i] + dx0;                       // leftmost source column of this row's window
-          const bool okr = (unsigned)(y + pdy[i]) < (unsigned)Hs;
-          const bool ok0 = okr && xl >= 0, ok2 = okr && xl + 2 < Ws;   // kx = 1 is always inside (Ws >= 2)
-          const __nv_bfloat16* sp = pix + src_off[i];
-          cp_async8(a_s + dst_off[i][0], ok0 ? (const void*)sp : (const void*)src, ok0 ? 8u : 0u);
-          cp_async8(a_s + dst_off[i][1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
-          cp_async8(a_s + dst_off[i][2], ok2 ? (const void*)(sp + 8) : (const void*)src, ok2 ? 8u : 0u);
+        for (int ky = 0; ky < 3; ++ky) {
+          const bool okr = (unsigned)(y + dy0 + ky) < (unsigned)Hs;
+          const bool ok0 = okr && in0, ok2 = okr && in2;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint32_t bb = (uint32_t)(ky * 24 + kx * 8);       // byte of (ky, kx) in the 128-byte im2col row
+            const uint32_t d = a_row + (((bb >> 4) ^ rsw) << 4) + (bb & 15u);
+            const bool ok = kx == 0 ? ok0 : (kx == 1 ? okr : ok2);
+            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
+          }
+          sp += (long long)Ws * 4;
         }
         cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
       }
-    } else {
+    } else if constexpr (!(PIECE == 4 && NPW == 4)) {     // (4, 4) is only ever launched on the row-window geometry
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
         while (flat >= group_end) { ++group; group_end += tiles_per_group; }
         const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
@@ -373,7 +362,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     }
    }
   } else if (warp < 12) {
-    nn_epilogue<NHALF, MASK>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+    nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
                              tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1);
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
@@ -461,7 +450,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
 //   warps: EPW*SETS epilogue (set s serves every SETS-th (tile, class) item; EPW = 8 when N <= 32, else 12), then the
 //   MMA issuer, then the TMA warp.
 // ------------------------------------------------------------------------------------------------
-template <int SETS, int EPW, bool MASK>
+template <int SETS, int EPW, int EPI>
 __global__ void __launch_bounds__(SETS * EPW * 32 + 64, SETS == 1 ? 2 : 1)
 tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __grid_constant__ TcMaps maps,
                const __grid_constant__ CUtensorMap amap, const float* __restrict__ bias_all,
@@ -508,7 +497,7 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
 
   if (warp < W_MMA) {
     const int set = warp / EPW, ws = warp - set * EPW;
-    nn_epilogue<EPW / 4, MASK>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+    nn_epilogue<EPW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
                                tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS);
   } else if (warp == W_MMA) {
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
@@ -1251,6 +1240,12 @@ static void fill_class(TcCls* c, const TcGeom& g) {
   }
 }
 
+// compile-time epilogue for the hot cases (bf16 destination only), the generic one otherwise
+static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f32) {
+  if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU)) return epi;
+  return EPI_GENERIC;
+}
+
 // builds the row program of a row-resident launch (see tc_rows_kernel) and runs it
 static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const TcMaps& maps, const __nv_bfloat16* src,
                           const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
@@ -1332,7 +1327,10 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
   } while (0)
 #define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
 #define ROWS_LAUNCH_S(MASK_) do { if (per_sm == 2) ROWS_LAUNCH_E(1, MASK_); else ROWS_LAUNCH_E(2, MASK_); } while (0)
-  if (epi == TC_EPI_MASK) ROWS_LAUNCH_S(true); else ROWS_LAUNCH_S(false);
+  const int epi_t = tc_epi_template(epi, dst, dst_f32);
+  if (epi_t == TC_EPI_MASK) ROWS_LAUNCH_S(TC_EPI_MASK);
+  else if (epi_t == TC_EPI_BIAS_RELU) ROWS_LAUNCH_S(TC_EPI_BIAS_RELU);
+  else ROWS_LAUNCH_S(EPI_GENERIC);
 #undef ROWS_LAUNCH_S
 #undef ROWS_LAUNCH_E
 #undef ROWS_LAUNCH
@@ -1397,6 +1395,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   // warp split: epilogue-heavy (4 producer / 8 epilogue warps) when a tile has a single k-block
   int npw = (cl.c[0].Kpad == BK && ncls == 1) ? 4 : 8;
   if (const char* e = getenv("GEECO_TC_NPW")) { const int v = atoi(e); if (v == 4 || v == 8) npw = v; }
+  if (g.Cs == 4 && !g.rowwin) npw = 8;      // the 4-warp variant of the 8-byte gather exists for the row-window path only
   CUtensorMap amap;
   memset(&amap, 0, sizeof(amap));
   if (g.a_tma) {
@@ -1413,7 +1412,12 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
                                          tiles_flat, tmem_cols, stages, nbuf);                                         \
   } while (0)
 #define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
-  do { if (epi == TC_EPI_MASK) NN_LAUNCH_M(PIECE_, NPW_, true); else NN_LAUNCH_M(PIECE_, NPW_, false); } while (0)
+  do {                                                                                                                 \
+    if (epi_t == TC_EPI_MASK) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_MASK);                                                  \
+    else if (epi_t == TC_EPI_BIAS_RELU) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_BIAS_RELU);                                   \
+    else NN_LAUNCH_M(PIECE_, NPW_, EPI_GENERIC);                                                                       \
+  } while (0)
+  const int epi_t = tc_epi_template(epi, dst, dst_f32);
   if (npw == 0) NN_LAUNCH(8, 0);
   else if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
   else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }
