@@ -146,11 +146,8 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
       const TcCls& kc = cl.c[c];
       const long long off = (pix00 + kc.dy0 * g.Wd + kc.dx0) * BN;
       // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
-      uint4 pm0 = make_uint4(0, 0, 0, 0), pm1 = pm0;
-      if (MASK && valid && c_first < BN) {
-        pm0 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first));
-        pm1 = __ldg(reinterpret_cast<const uint4*>(mask + off + c_first + 8));
-      }
+      uint32_t pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (MASK && valid && c_first < BN) ldg256_nc(mask + off + c_first, pm);
       mbar_wait(&tmem_full[my_buf], my_phase);
       tc_fence_after();
       const uint32_t taddr = lane_addr + my_buf * (uint32_t)BN;
@@ -174,12 +171,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
           } else if (MASK) {
-            uint4 m0v = pm0, m1v = pm1;
-            if (c0 != c_first) {
-              m0v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0));
-              m1v = __ldg(reinterpret_cast<const uint4*>(mask + off + c0 + 8));
-            }
-            const uint32_t mw[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+            uint32_t mw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mw[i] = pm[i];
+            if (c0 != c_first) ldg256_nc(mask + off + c0, mw);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               // post-ReLU activations are >= 0 (never -0): "y > 0" == any bit of the bf16 set
@@ -188,13 +183,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
             }
           }
           if (!GEN || dst) {
-            uint4 o0, o1;
-            o0.x = pack_bf16x2(f[0], f[1]); o0.y = pack_bf16x2(f[2], f[3]);
-            o0.z = pack_bf16x2(f[4], f[5]); o0.w = pack_bf16x2(f[6], f[7]);
-            o1.x = pack_bf16x2(f[8], f[9]); o1.y = pack_bf16x2(f[10], f[11]);
-            o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-            *reinterpret_cast<uint4*>(dst + off + c0) = o0;
-            *reinterpret_cast<uint4*>(dst + off + c0 + 8) = o1;
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            stg256(dst + off + c0, o);
           }
           if (GEN && dst_f32) {
 #pragma unroll
