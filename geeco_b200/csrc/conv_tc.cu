@@ -623,7 +623,45 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   if (kb_hi > total_kb) kb_hi = total_kb;
   const int nkb = kb_hi - kb_lo;
 
-  if (warp < EPI_WARP0) {
+  if (warp < EPI_WARP0 && PIECE == 4 && NPROD == 256 && g.rowwin && Cout == 32 && (Mg & 63u) == 0 && g.dsx == 1 && g.dsy == 1) {
+    // ---- conv1 (3/4 input channels, 32 filters): a k-block is 64 consecutive pixels of one image row.  Everything
+    // that does not change from k-block to k-block is hoisted; per k-block a thread issues one 16-byte G copy
+    // (thread = (row, 16-byte chunk of the 64-byte G row)) and, threads 0..191, the three 8-byte copies of one
+    // (row, ky) window.  ~25 instructions per k-block instead of ~290 in the generic producer below.
+    const uint32_t grow_t = threadIdx.x >> 2, gchunk = threadIdx.x & 3;
+    const uint32_t g_dst = grow_t * 128 + ((gchunk ^ (grow_t & 7u)) << 4);
+    const __nv_bfloat16* gsrc = G + ((long long)group * Mg + (long long)kb_lo * 64 + grow_t) * 32 + gchunk * 8;
+    const bool xthread = threadIdx.x < 192;
+    const uint32_t xrow = threadIdx.x & 63, xky = (threadIdx.x >> 6) % 3;
+    const int xdy = g.dy[xky * 3], xdx0 = g.dx[0];
+    uint32_t xd[3];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const uint32_t bb = xky * 24 + kx * 8;
+      xd[kx] = 2 * SUB + xrow * 128 + (((bb >> 4) ^ (xrow & 7u)) << 4) + (bb & 15u);
+    }
+    const int Hs = g.Hs, Ws = g.Ws;
+    const uint32_t st_u32 = smem_u32(st_base);
+    uint32_t s = 0, sphase = 0;
+    uint32_t mb = (uint32_t)kb_lo * 64;
+    for (int it = 0; it < nkb; ++it, mb += 64, gsrc += 64 * 32) {
+      mbar_wait(&empty[s], sphase ^ 1u);
+      const uint32_t sb = st_u32 + s * (uint32_t)stage_bytes;
+      cp_async16(sb + g_dst, gsrc, 16u);
+      if (xthread) {
+        const int img = (int)(mb >> g.hw_shift);
+        const uint32_t rem = mb & ((1u << g.hw_shift) - 1u);
+        const int y = (int)(rem >> g.w_shift) + xdy, xl = (int)(rem & ((1u << g.w_shift) - 1u)) + (int)xrow + xdx0;
+        const bool okr = (unsigned)y < (unsigned)Hs, ok0 = okr && xl >= 0, ok2 = okr && xl + 2 < Ws;
+        const __nv_bfloat16* sp = src + ((long long)((group * g.imgs_per_group + img) * Hs + y) * Ws + xl) * 4;
+        cp_async8(sb + xd[0], ok0 ? (const void*)sp : (const void*)src, ok0 ? 8u : 0u);
+        cp_async8(sb + xd[1], okr ? (const void*)(sp + 4) : (const void*)src, okr ? 8u : 0u);
+        cp_async8(sb + xd[2], ok2 ? (const void*)(sp + 8) : (const void*)src, ok2 ? 8u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(&full[s]);
+      if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
+    }
+  } else if (warp < EPI_WARP0) {
     // ---- G tile mapping: 16-byte chunks, NPROD/8 rows per pass
     constexpr int G_ROWS = NPROD / 8, G_PASSES = 64 / G_ROWS;
     const int g_chunk = threadIdx.x & 7, g_row0 = threadIdx.x >> 3;
@@ -735,7 +773,9 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int co = mtile * 128 + row;
-    mbar_wait(tmem_full, 0);
+    // these warps have nothing to do until the whole pixel range is accumulated: poll rarely (a tight spin from
+    // 4-8 idle warps took 20 % of the issue slots of an issue-bound kernel)
+    while (!mbar_try(smem_u32(tmem_full), 0)) __nanosleep(2000);
     tc_fence_after();
     float* P = partial + (((long long)split * groups + group) * Mrows_pad + co) * g.Kpad + col0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
