@@ -282,19 +282,22 @@ def run_ours(args):
               'h2d_bytes_per_step': eng.h2d_bytes(True, frames_u8=frames_u8), 'd2h_bytes_per_step': 32,
               'steps': n_e2e}
 
-    # headline: float32 frames in [0,1], exactly what the reference's model_fn is handed (estimator.py:160-176)
-    e2e = timed_train(host_batches, False)
-    e2e['api'] = 'geeco_b200.estimator.Estimator.train(input_fn over pinned host batches, float32 frames), log_steps=1'
-    # same entry fed the RECORDED uint8 frames; the /255 of the input pipeline (geeco_gym.py:310) runs on the device
+    # float32 frames in [0,1]: exactly what the reference's model_fn is handed (estimator.py:160-176); 252 MB of
+    # frames per 64-sample step, so at >= 12k samples/s this leg measures the PCIe link, not the step
+    e2e_f32 = timed_train(host_batches, False)
+    e2e_f32['api'] = 'Estimator.train(input_fn over pinned host batches), float32 frames in [0,1] (model_fn boundary)'
+    # headline: the same entry fed the frames as RECORDED (uint8); the `/= 255.0` of the reference's input pipeline
+    # (geeco_gym.py:310) runs on the device and produces the bit-identical network input (tests/test_gpu_boundary.py)
     u8_batches = []
     for hb in host_batches:
       ub = dict(hb)
       for k in ('rgb', 'target_rgb'):
         ub[k] = torch.round(hb[k] * 255.0).to(torch.uint8).pin_memory()
       u8_batches.append(ub)
-    e2e_u8 = timed_train(u8_batches, True)
-    e2e_u8['api'] = 'same entry, uint8 frames as recorded (4x fewer PCIe bytes); bit-identical network input'
-    e2e['uint8_frames'] = e2e_u8
+    e2e = timed_train(u8_batches, True)
+    e2e['api'] = ('geeco_b200.estimator.Estimator.train(input_fn over pinned host batches, uint8 frames as recorded), '
+                  'log_steps=1: every step uploads its batch and copies its losses back')
+    e2e['float32_frames'] = e2e_f32
 
   peaks = load_peaks()
   roofline, extra = kernel_rooflines(eng, dev, peaks, args) if (rank == 0 and not args.no_kernels) else (None, None)
@@ -374,30 +377,37 @@ def kernel_rooflines(eng, dev, peaks, args):
                 2.0 * N3 * 128 * 128 * 48 * 288)
     return dom, out
   N3 = 3 * args.batch
-  # conv1 (4-channel padded input 256x256 -> 32 ch) and conv2 (32 -> 48, stride 2): the HBM-bound bulk of the step
+  # conv1 (4-channel padded input 256x256 -> 32 ch) and conv2 (32 -> 48, stride 2): the HBM-bound bulk of the step.
+  # Each entry times ONE stand-alone op = the named kernel plus its few-microsecond helpers (weight repack of that layer,
+  # split reduction); algorithmic bytes = every tensor the op must read or write once (DESIGN.md "Kernels").
   x1 = torch.rand((N3, 256, 256, 4), device=dev).to(torch.bfloat16); x1[..., 3] = 0
   w1 = ((torch.rand((3, 3, 3, 32), device=dev) - 0.5) * 0.2)
   b1 = torch.zeros(32, device=dev)
   g1 = (torch.rand((N3, 256, 256, 32), device=dev) - 0.5).to(torch.bfloat16)
+  P1, P2 = N3 * 65536, N3 * 16384                       # pixels of the 256x256 and 128x128 maps
   sec = _timed(dev, lambda: ops.conv2d_same_bf16(x1, w1, b1, stride=1), flush=flush)
-  entry('tc_nn_kernel<4> conv1 fwd', sec, N3 * 65536 * (4 + 32) * 2, 2.0 * N3 * 65536 * 32 * 27)
+  entry('tc_nn_kernel<4,4> conv1 fwd', sec, P1 * (4 + 32) * 2, 2.0 * P1 * 32 * 27, launches=2)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x1, w1, g1, stride=1, need_dx=False), flush=flush)
-  dom = entry('tc_wgrad_kernel<4> conv1 wgrad', sec, N3 * 65536 * (4 + 32) * 2, 2.0 * N3 * 65536 * 32 * 27, launches=2)
-  x2 = g1
+  entry('tc_wgrad_kernel<4,256> conv1 wgrad', sec, P1 * (4 + 32) * 2, 2.0 * P1 * 32 * 27, launches=2)
+  x2 = g1.abs()                                          # post-ReLU activations of conv1 (the mask of the data gradient)
   w2 = ((torch.rand((3, 3, 32, 48), device=dev) - 0.5) * 0.2)
   b2 = torch.zeros(48, device=dev)
   sec = _timed(dev, lambda: ops.conv2d_same_bf16(x2, w2, b2, stride=2), flush=flush)
-  entry('tc_nn_kernel<8> conv2 fwd', sec, N3 * (65536 * 32 + 16384 * 48) * 2, 2.0 * N3 * 16384 * 48 * 288)
+  entry('tc_rows_kernel<2,12> conv2 fwd', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
   g2 = (torch.rand((N3, 128, 128, 48), device=dev) - 0.5).to(torch.bfloat16)
-  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_x=x2), flush=flush)
-  entry('conv2 wgrad + fused dgrad', sec, N3 * ((65536 * 32 + 16384 * 48) + (16384 * 48 + 2 * 65536 * 32)) * 2,
-        2.0 * 2 * N3 * 16384 * 48 * 288, launches=8)
+  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, need_dx=False), flush=flush)
+  entry('tc_wgrad_kernel<8,512> conv2 wgrad', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
+  # the longest kernel of the step: conv2 data gradient = G2 in, ReLU mask (y1) in, G1 out
+  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_x=x2, need_dx=True, need_dw=False),
+               flush=flush)
+  dom = entry('tc_rows_kernel<1,8> conv2 dgrad', sec, (P2 * 48 + 2 * P1 * 32) * 2, 2.0 * P2 * 48 * 288, launches=5)
   # a tensor-bound layer for the tensor-pipe view: conv5 (128 -> 192, 32x32 -> 16x16)
   x5 = torch.rand((N3, 32, 32, 128), device=dev).to(torch.bfloat16)
   w5 = ((torch.rand((3, 3, 128, 192), device=dev) - 0.5) * 0.1)
   b5 = torch.zeros(192, device=dev)
   sec = _timed(dev, lambda: ops.conv2d_same_bf16(x5, w5, b5, stride=2), flush=flush)
-  e5 = entry('tc_nn_kernel<8> conv5 fwd', sec, N3 * (1024 * 128 + 256 * 192) * 2 + 192 * 1152 * 2, 2.0 * N3 * 256 * 192 * 1152)
+  e5 = entry('tc_nn_kernel<8,0> conv5 fwd', sec, N3 * (1024 * 128 + 256 * 192) * 2 + 192 * 1152 * 2, 2.0 * N3 * 256 * 192 * 1152,
+             launches=2)
   e5['bound'] = 'tensor'
   return dom, out
 
@@ -446,8 +456,10 @@ def run_extras(eng, dev, peaks, args):
   res['policy_steps'] = {'envs': total_envs, 'chunk': chunk, 'ms_per_control_step': sec * 1e3,
                          'env_steps_per_s': total_envs / sec, 'tflops': total_envs * 3.415e9 / sec / 1e12,
                          'carry_state': True, 'note': 'MuJoCo stepping excluded; frames synthetic, device resident'}
-  with open(os.path.join(ROOT, 'profiles', 'r01_extras.json'), 'w') as fp:
-    json.dump(res, fp, indent=1)
+  for d in ('profiles', 'gpurun_out'):                   # gpurun_out/ is what travels back from the GPU box
+    os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+    with open(os.path.join(ROOT, d, 'r01_extras.json'), 'w') as fp:
+      json.dump(res, fp, indent=1)
   return res
 
 
