@@ -179,7 +179,7 @@ def run_reference(args):
       'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -232,10 +232,10 @@ def run_ours(args):
 
   for i in range(args.warmup):
     step_dev(i)
-  barrier()
   sampler = ClockSampler(local_rank)
   if rank == 0:
-    sampler.start()
+    sampler.start()          # before the barrier: its start-up delay must not skew rank 0 against the others
+  barrier()
   lib.geeco_launch_count(1)
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   t_wall0 = time.time()
@@ -321,7 +321,7 @@ def run_ours(args):
         'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roofline, 'kernels': extra,
         'cpu_baseline': cpu_baseline, 'peaks': peaks, 'extras': extras,
     }
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -463,8 +463,27 @@ def run_extras(eng, dev, peaks, args):
   return res
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+  """stdout carries exactly ONE line (the JSON result): everything libraries print there (NCCL's version banner,
+  ...) is routed to stderr; emit() writes to the saved descriptor."""
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+
+
+def emit(obj):
+  out = _REAL_STDOUT or sys.stdout
+  out.write(json.dumps(obj) + '\n')
+  out.flush()
+
+
 def main():
   args = parse_args()
+  _quiet_stdout()
   if args.impl == 'reference':
     run_reference(args)
   else:
