@@ -980,22 +980,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
   }
 }
 
+// One launch for all repack jobs of a step.  Jobs start on PACK_CHUNK boundaries of a virtual index space, so a
+// block belongs to exactly one job: the job is looked up once per block and its constants stay in registers.
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs,
                                                                    long long grand_total) {
-  __shared__ long long s_start[65];
-  for (int j = threadIdx.x; j <= njobs && j <= 64; j += blockDim.x) s_start[j] = j < njobs ? jobs[j].start : grand_total;
-  __syncthreads();
-  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < grand_total; gi += (long long)gridDim.x * blockDim.x) {
+  __shared__ int s_job;
+  const long long v0 = (long long)blockIdx.x * PACK_CHUNK;
+  if (threadIdx.x == 0) {
     int lo = 0, hi = njobs - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_start[mid] <= gi) lo = mid; else hi = mid - 1; }
-    const PackJob& jb = jobs[lo];
-    const long long i = gi - jb.start;
-    const int k = (int)(i % jb.Kpad);
-    const long long rr = i / jb.Kpad;
-    const int r = (int)(rr % jb.rows), grp = (int)(rr / jb.rows);
-    const float v = pack_value(jb.W + (long long)grp * jb.w_group_stride, jb.mode, jb.Cin, jb.Cout, jb.Cs, jb.ntaps,
-                               jb.taps, jb.Kt, r, k);
-    jb.out[i] = __float2bfloat16_rn(v);
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].start <= v0) lo = mid; else hi = mid - 1; }
+    s_job = lo;
+  }
+  __syncthreads();
+  const PackJob& jb = jobs[s_job];
+  const uint32_t total = (uint32_t)jb.total, Kp = (uint32_t)jb.Kpad, rows = (uint32_t)jb.rows;
+  const int mode = jb.mode, Cin = jb.Cin, Cout = jb.Cout, Cs = jb.Cs, ntaps = jb.ntaps, Kt = jb.Kt;
+  const float* W = jb.W;
+  const long long wgs = jb.w_group_stride;
+  __nv_bfloat16* out = jb.out;
+  uint32_t i = (uint32_t)(v0 - jb.start) + threadIdx.x;
+#pragma unroll 1
+  for (int e = 0; e < PACK_CHUNK / 256; ++e, i += 256) {
+    if (i >= total) break;
+    const uint32_t rr = i / Kp, k = i - rr * Kp;
+    const uint32_t grp = rr / rows, r = rr - grp * rows;
+    out[i] = __float2bfloat16_rn(pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k));
   }
 }
 
@@ -1599,8 +1608,8 @@ int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups
 int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st) {
   if (njobs <= 0 || grand_total <= 0) return GEECO_OK;
   if (njobs > 64) { geeco_set_error("pack_weights_batched: %d jobs > 64", njobs); return GEECO_ERR_INVALID; }
-  int blocks = ceil_div(grand_total, 256 * 4); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weights_batched_kernel<<<blocks, 256, 0, st>>>(jobs_dev, njobs, grand_total);
+  if (grand_total % PACK_CHUNK) { geeco_set_error("pack_weights_batched: jobs must start on PACK_CHUNK boundaries"); return GEECO_ERR_INVALID; }
+  pack_weights_batched_kernel<<<(unsigned)(grand_total / PACK_CHUNK), 256, 0, st>>>(jobs_dev, njobs, grand_total);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

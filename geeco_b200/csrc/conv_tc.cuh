@@ -81,6 +81,9 @@ struct PackJob {
   const float* W; __nv_bfloat16* out; long long w_group_stride; long long start; long long total;
   int mode, groups, Cin, Cout, Cs, ntaps, rows, Kpad; int taps[9]; int Kt;   // Kt: K extent per tap (0 = Cs / Cout)
 };
+// jobs occupy [start, start + total) of a virtual index space; every start is a multiple of PACK_CHUNK and
+// grand_total is the end of the last job rounded up to PACK_CHUNK (total < 2^31 per job)
+constexpr int PACK_CHUNK = 2048;
 int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);

@@ -160,7 +160,7 @@ static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, 
   for (int i = 0; i < ntaps && i < 9; ++i) j.taps[i] = taps[i];
   j.start = bp->jobs_total;
   j.total = (long long)groups * rows * Kpad;
-  bp->jobs_total += j.total;
+  bp->jobs_total = (j.start + j.total + PACK_CHUNK - 1) / PACK_CHUNK * PACK_CHUNK;
   bp->jobs.push_back(j);
 }
 
@@ -193,6 +193,8 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
       }
     }
     if (bp->jobs.size() > 64) { geeco_set_error("repack: %zu jobs > 64", bp->jobs.size()); return GEECO_ERR_INVALID; }
+    for (const PackJob& pj : bp->jobs)
+      if (pj.total >= (1ll << 31)) { geeco_set_error("repack: a job of %lld elements needs 64-bit indexing", pj.total); return GEECO_ERR_INVALID; }
     CUDA_TRY(cudaMemcpyAsync(bp->jobs_dev, bp->jobs.data(), bp->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     bp->jobs_uploaded = true;

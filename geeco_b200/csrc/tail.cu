@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p,
   __syncthreads();
   for (int j = threadIdx.x; j < d.Fc; j += blockDim.x) {
     float s = p.b_fc1[j];
-    for (int i = 0; i < d.Hl; ++i) s = fmaf(m_s[i], p.w_fc1[(long long)i * d.Fc + j], s);
+#pragma unroll 16
+    for (int i = 0; i < d.Hl; ++i) s = fmaf(m_s[i], __ldg(p.w_fc1 + (long long)i * d.Fc + j), s);   // loads issue ahead of the FMA chain
     s = fmaxf(s, 0.f);
     fc_s[j] = s;
     fc1[(long long)n * d.Fc + j] = s;
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p,
     else if (t < 6 + d.G) { w = p.w_aux_ee; b = p.b_aux_ee; col = t - 3 - d.G; width = 3; }
     else { w = p.w_aux_obj; b = p.b_aux_obj; col = t - 6 - d.G; width = 3; }
     float s = b[col];
-    for (int j = 0; j < d.Fc; ++j) s = fmaf(fc_s[j], w[j * width + col], s);
+#pragma unroll 16
+    for (int j = 0; j < d.Fc; ++j) s = fmaf(fc_s[j], __ldg(w + j * width + col), s);
     out_s[t] = s;
     heads[(long long)n * NH + t] = s;
   }
