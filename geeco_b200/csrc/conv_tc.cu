@@ -1130,7 +1130,9 @@ static void finish_k(TcGeom* g) {
 // the same geometry as the software-gather kernels (weight gradient) see it: dense K = ntaps * Cs
 static TcGeom gather_view(const TcGeom& g) {
   TcGeom v = g;
-  v.a_tma = 0; v.rows = 0; v.wpack = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 63) / 64 * 64;
+  // always at least one padding column: the bias gradient rides in it as a column of ones (one more 64-wide
+  // sub-tile when ntaps * Cs is a multiple of 64) instead of two extra column-sum launches per layer
+  v.a_tma = 0; v.rows = 0; v.wpack = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 64) / 64 * 64;
   return v;
 }
 
