@@ -117,8 +117,11 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
                                             const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst,
                                             float* __restrict__ dst_f32, int epi, int tiles_per_group, int tiles_flat, int nbuf,
                                             uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t Mg, int q,
-                                            int half, int lane, int set, int nsets) {
+                                            int half, int lane, int set, int nsets, unsigned short* __restrict__ bits_out) {
   constexpr bool MASK = EPI == TC_EPI_MASK;
+  constexpr bool MBITS = EPI == TC_EPI_MASKBITS;
+  const unsigned short* __restrict__ mbits = reinterpret_cast<const unsigned short*>(mask);
+  const int chunks_per_pix = g.Nn >> 4;
   constexpr bool GEN = EPI == EPI_GENERIC;
   const int BN = g.Nn;
   const int ncls = cl.ncls;
@@ -144,7 +147,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
       if (++turn == nsets) turn = 0;
       if (!mine) continue;
       const TcCls& kc = cl.c[c];
-      const long long off = (pix00 + kc.dy0 * g.Wd + kc.dx0) * BN;
+      const long long pix = pix00 + kc.dy0 * g.Wd + kc.dx0;
+      const long long off = pix * BN;
+      uint32_t pbits = 0;
+      if (MBITS && valid && c_first < BN) pbits = __ldg(mbits + pix * chunks_per_pix + (c_first >> 4));
       // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
       uint32_t pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (MASK && valid && c_first < BN) ldg256_nc(mask + off + c_first, pm);
@@ -170,6 +176,14 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
+          } else if (MBITS) {
+            uint32_t bits = pbits;
+            if (c0 != c_first) bits = __ldg(mbits + pix * chunks_per_pix + (c0 >> 4));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (!((bits >> i) & 1u)) f[2 * i] = 0.f;
+              if (!((bits >> (8 + i)) & 1u)) f[2 * i + 1] = 0.f;
+            }
           } else if (MASK) {
             uint32_t mw[8];
 #pragma unroll
@@ -187,6 +201,13 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
             stg256(dst + off + c0, o);
+            if (EPI == TC_EPI_BIAS_RELU && bits_out) {
+              // 1-bit ReLU mask of the STORED values: halfword != 0, flags gathered per halfword lane
+              uint32_t acc = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc |= (__vcmpne2(o[i], 0u) & 0x00010001u) << i;
+              bits_out[pix * chunks_per_pix + (c0 >> 4)] = (unsigned short)((acc & 0xffu) | ((acc >> 8) & 0xff00u));
+            }
           }
           if (GEN && dst_f32) {
 #pragma unroll
@@ -212,7 +233,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
              const __grid_constant__ CUtensorMap amap, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
-             int tiles_flat, int tmem_cols, int stages, int nbuf) {
+             int tiles_flat, int tmem_cols, int stages, int nbuf, unsigned short* __restrict__ bits_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -355,7 +376,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
    }
   } else if (warp < 12) {
     nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                             tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1);
+                             tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1, bits_out);
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
     // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
@@ -447,7 +468,8 @@ __global__ void __launch_bounds__(SETS * EPW * 32 + 64, SETS == 1 ? 2 : 1)
 tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __grid_constant__ TcMaps maps,
                const __grid_constant__ CUtensorMap amap, const float* __restrict__ bias_all,
                const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi,
-               int tiles_per_group, int tiles_flat, int tmem_cols, int stages, int nbuf) {
+               int tiles_per_group, int tiles_flat, int tmem_cols, int stages, int nbuf,
+               unsigned short* __restrict__ bits_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -490,7 +512,7 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   if (warp < W_MMA) {
     const int set = warp / EPW, ws = warp - set * EPW;
     nn_epilogue<EPW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS);
+                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS, bits_out);
   } else if (warp == W_MMA) {
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
     // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
@@ -1295,14 +1317,14 @@ static void fill_class(TcCls* c, const TcGeom& g) {
 
 // compile-time epilogue for the hot cases (bf16 destination only), the generic one otherwise
 static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f32) {
-  if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU)) return epi;
+  if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_MASKBITS)) return epi;
   return EPI_GENERIC;
 }
 
 // builds the row program of a row-resident launch (see tc_rows_kernel) and runs it
 static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const TcMaps& maps, const __nv_bfloat16* src,
                           const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
-                          cudaStream_t st) {
+                          cudaStream_t st, unsigned short* bits_out) {
   const TcGeom& g = gs[0];
   TcRowProg rp;
   memset(&rp, 0, sizeof(rp));
@@ -1376,12 +1398,13 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
     kern<<<ctas, SETS_ * EPW_ * 32 + 64, smem, st>>>(g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,                \
-                                                     tiles_per_group, tiles_flat, tmem_cols, stages, nbuf);             \
+                                                     tiles_per_group, tiles_flat, tmem_cols, stages, nbuf, bits_out);   \
   } while (0)
 #define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
 #define ROWS_LAUNCH_S(MASK_) do { if (per_sm == 2) ROWS_LAUNCH_E(1, MASK_); else ROWS_LAUNCH_E(2, MASK_); } while (0)
   const int epi_t = tc_epi_template(epi, dst, dst_f32);
   if (epi_t == TC_EPI_MASK) ROWS_LAUNCH_S(TC_EPI_MASK);
+  else if (epi_t == TC_EPI_MASKBITS) ROWS_LAUNCH_S(TC_EPI_MASKBITS);
   else if (epi_t == TC_EPI_BIAS_RELU) ROWS_LAUNCH_S(TC_EPI_BIAS_RELU);
   else ROWS_LAUNCH_S(EPI_GENERIC);
 #undef ROWS_LAUNCH_S
@@ -1397,7 +1420,11 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
 // strided data-gradient) run as ONE launch; ncls == 1 is the plain forward / single-class case
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
                        const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
-                       int max_ctas, cudaStream_t st) {
+                       int max_ctas, cudaStream_t st, unsigned short* bits_out) {
+  if (epi == TC_EPI_MASKBITS && (!mask || !dst || dst_f32)) {
+    geeco_set_error("tc_nn: TC_EPI_MASKBITS needs the bit mask and a bf16 destination only");
+    return GEECO_ERR_INVALID;
+  }
   if (ncls < 1 || ncls > 4) { geeco_set_error("tc_nn: ncls=%d outside [1,4]", ncls); return GEECO_ERR_INVALID; }
   const TcGeom& g = gs[0];
   if (g.Nn % 16 || g.Nn < 16 || g.Nn > 256) { geeco_set_error("tc_nn: unsupported N=%d", g.Nn); return GEECO_ERR_INVALID; }
@@ -1421,7 +1448,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   if (Mg <= 0) return GEECO_OK;
   if (getenv("GEECO_TC_NOSTORE")) { dst = nullptr; dst_f32 = nullptr; }     // experiment: time without output stores
   if (g.rows) {
-    return launch_tc_rows(gs, ncls, cl, maps, src, bias, mask, dst, dst_f32, epi, st);
+    return launch_tc_rows(gs, ncls, cl, maps, src, bias, mask, dst, dst_f32, epi, st, bits_out);
   }
   const int tiles_per_group = ceil_div(Mg, BM);
   const int tiles_flat = tiles_per_group * g.groups;
@@ -1462,11 +1489,12 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
     kern<<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,        \
-                                         tiles_flat, tmem_cols, stages, nbuf);                                         \
+                                         tiles_flat, tmem_cols, stages, nbuf, bits_out);                               \
   } while (0)
 #define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
   do {                                                                                                                 \
     if (epi_t == TC_EPI_MASK) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_MASK);                                                  \
+    else if (epi_t == TC_EPI_MASKBITS) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_MASKBITS);                                     \
     else if (epi_t == TC_EPI_BIAS_RELU) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_BIAS_RELU);                                   \
     else NN_LAUNCH_M(PIECE_, NPW_, EPI_GENERIC);                                                                       \
   } while (0)
@@ -1483,9 +1511,9 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
 
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
-                 cudaStream_t st) {
+                 cudaStream_t st, unsigned short* bits_out) {
   const CUtensorMap* maps[1] = {wmap};
-  return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st);
+  return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st, bits_out);
 }
 
 struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols, per_sm; };

@@ -47,17 +47,19 @@ struct TcRowProg {
 };
 struct TcMaps { CUtensorMap m[4]; };
 
-enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3 };
+// TC_EPI_MASKBITS: like TC_EPI_MASK, but `mask` points at the 1-bit-per-element mask a TC_EPI_BIAS_RELU launch wrote
+// through `bits_out` (uint16 per (pixel, 16-channel chunk); bit j = channel 2j, bit 8+j = channel 2j+1 of the chunk)
+enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3, TC_EPI_MASKBITS = 4 };
 
 struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packed tap
 
 // fwd / dgrad: dst = epi(A(src) x Wp^T)
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
-                 cudaStream_t st);
+                 cudaStream_t st, unsigned short* bits_out = nullptr);
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
                        const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
-                       int max_ctas, cudaStream_t st);
+                       int max_ctas, cudaStream_t st, unsigned short* bits_out = nullptr);
 // wgrad: dW[(tap,ci)][co] (+ optional bias gradient) from im2col(src)^T x G, deterministic split reduction.
 //   g describes the FORWARD geometry (rows = output pixels); G is [imgs, Hm, Wm, Cout] bf16.
 //   Cw = channels per tap present in the weight tensor (Cin_real); dW fp32 [ntaps*Cw, Cout] per group.

@@ -257,6 +257,8 @@ static int plan(geeco_ctx* c, char* ws_base) {
     L.act_elems = off;
     L.y = cv.take((size_t)off * esz);
     L.g = cfg.training ? cv.take((size_t)off * esz) : nullptr;
+    // the data gradient of layer l+1 needs only the SIGN of y_l: the forward epilogue also writes one bit per element
+    L.mbits = (bf16 && cfg.training && l < 7) ? cv.take((size_t)off / 16 * 2) : nullptr;
   }
   c->NH = 9 + G;
   c->state = (float*)cv.take(sizeof(float) * N * (xdim + Hl));

@@ -14,6 +14,7 @@ struct LayerPlan {
   long long act_elems;
   void* y;                    // post-ReLU output  [3][N][Hout][Hout][Cout]
   void* g;                    // dL/d(pre-activation), same layout (training only)
+  void* mbits;                // bf16 training, conv1-conv7: 1-bit ReLU mask of y, uint16 per (pixel, 16 channels)
   // bf16 mode: packed weight copies (see step_bf16.cu)
   void* w_fwd;                // [3][Cout][Kpad]  bf16, K-major
   void* w_dgrad;              // [3][9][Cin][Cout] bf16 (tap-major, Cout contiguous)

@@ -222,13 +222,14 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
       pg[0].bias_group_stride = pg[1].bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
       const CUtensorMap* pm[2] = {&B.pair_map[0], &B.pair_map[1]};
       int rc = launch_tc_nn_multi(pg, pm, 2, src, c->theta + c->params[L.p_b[0]].offset, nullptr, (__nv_bfloat16*)L.y, nullptr,
-                                  TC_EPI_BIAS_RELU, 0, st);
+                                  TC_EPI_BIAS_RELU, 0, st, (unsigned short*)L.mbits);
       if (rc) return rc;
     } else if (L.grouped) {
       TcGeom g = B.fwd;
       g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
       int rc = launch_tc_nn(g, &B.fwd_map[0], src, c->theta + c->params[L.p_b[0]].offset, nullptr,
-                            (__nv_bfloat16*)L.y, l == 7 ? c->y8_f32 : nullptr, TC_EPI_BIAS_RELU, 0, st);
+                            (__nv_bfloat16*)L.y, l == 7 ? c->y8_f32 : nullptr, TC_EPI_BIAS_RELU, 0, st,
+                            (unsigned short*)L.mbits);
       if (rc) return rc;
     } else {
       for (int e = 0; e < 3; ++e) {
@@ -295,8 +296,12 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
           dmaps[ci] = &B.dg_map[ci][e];
         }
         (void)groups;
-        rc = launch_tc_nn_multi(dgs, dmaps, B.n_classes, gy, nullptr, xin + in_off,
-                                (__nv_bfloat16*)c->layers[l - 1].g + in_off, nullptr, TC_EPI_MASK, 0, st);
+        // ReLU mask of y_{l-1}: the bit mask its forward wrote (grouped layers), else the activation itself
+        const LayerPlan& Lp = c->layers[l - 1];
+        const bool bits = L.grouped && Lp.mbits != nullptr;
+        rc = launch_tc_nn_multi(dgs, dmaps, B.n_classes, gy, nullptr,
+                                bits ? (const __nv_bfloat16*)Lp.mbits : xin + in_off,
+                                (__nv_bfloat16*)Lp.g + in_off, nullptr, bits ? TC_EPI_MASKBITS : TC_EPI_MASK, 0, st);
         if (rc) return rc;
       }
     }
