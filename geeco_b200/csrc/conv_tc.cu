@@ -850,42 +850,32 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
 }
 
 // dW[g][(tap*Cw + ch)][co] = sum_splits partial[s][g][co][tap*Cs + ch] ; bias from the ones column
-// grid (k tiles of 32, co tiles of 32, groups), block (32, 8): partials are read along k (their fastest index) and
-// dW is written along co (its fastest index) through a 32x32 shared-memory transpose; splits are added in order.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW,
-                                                           float* __restrict__ dbias, int splits, int groups, int Mrows_pad,
-                                                           int Kpad, int Cout, int Cs, int Cw, int Ktot, int ones_col,
-                                                           long long dw_group_stride, long long dbias_group_stride) {
-  __shared__ float tile[32][33];
-  const int k0 = blockIdx.x * 32, co0 = blockIdx.y * 32, grp = blockIdx.z;
-  const long long sstride = (long long)groups * Mrows_pad * Kpad;
-  {
-    const int k = k0 + threadIdx.x;
-    const int col = k < Ktot ? k : (k == Ktot ? ones_col : -1);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + threadIdx.y + 8 * j;
-      float sum = 0.f;
-      if (co < Cout && col >= 0) {
-        const float* p = partial + ((long long)grp * Mrows_pad + co) * Kpad + col;
-        for (int sp = 0; sp < splits; ++sp) sum += p[sp * sstride];
-      }
-      tile[threadIdx.y + 8 * j][threadIdx.x] = sum;
-    }
-  }
-  __syncthreads();
-  const int co = co0 + threadIdx.x;
-  if (co >= Cout) return;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int k = k0 + threadIdx.y + 8 * j;
-    const float v = tile[threadIdx.x][threadIdx.y + 8 * j];
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ dbias,
+                                    int splits, int groups, int Mrows_pad, int Kpad, int Cout, int Cs, int Cw,
+                                    int Ktot, int ones_col, long long dw_group_stride, long long dbias_group_stride) {
+  const long long per_group = (long long)(Ktot + 1) * Cout;
+  const long long total = per_group * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int grp = (int)(i / per_group);
+    const long long e = i - (long long)grp * per_group;
+    const int k = (int)(e / Cout), co = (int)(e - (long long)k * Cout);
+    int col;
+    float* out;
     if (k < Ktot) {
       const int tap = k / Cs, ch = k - tap * Cs;
-      if (ch < Cw) dW[(long long)grp * dw_group_stride + (long long)(tap * Cw + ch) * Cout + co] = v;
-    } else if (k == Ktot && dbias && ones_col >= 0) {
-      dbias[(long long)grp * dbias_group_stride + co] = v;
+      if (ch >= Cw) continue;
+      col = k;
+      out = dW + (long long)grp * dw_group_stride + (long long)(tap * Cw + ch) * Cout + co;
+    } else {
+      if (ones_col < 0 || !dbias) continue;
+      col = ones_col;
+      out = dbias + (long long)grp * dbias_group_stride + co;
     }
+    const float* p = partial + ((long long)grp * Mrows_pad + co) * Kpad + col;
+    const long long sstride = (long long)groups * Mrows_pad * Kpad;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += p[sp * sstride];
+    *out = s;
   }
 }
 
@@ -1615,9 +1605,10 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   if (rc) return rc;
   const long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
   const int ones = dbias ? p.ones_col : -1;
-  wgrad_reduce_kernel<<<dim3(ceil_div(g.Ktot + 1, 32), ceil_div(Cout, 32), g.groups), dim3(32, 8), 0, st>>>(
-      partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw, g.Ktot, ones, dw_group_stride,
-      dbias_group_stride);
+  const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
+  int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
+  wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
+                                          g.Ktot, ones, dw_group_stride, dbias_group_stride);
   geeco_count_launch(1);
   if (dbias && p.ones_col < 0) {
     if (Cout > 256) { geeco_set_error("tc_wgrad: bias gradient needs Cout <= 256"); return GEECO_ERR_INVALID; }

@@ -259,6 +259,7 @@ static int plan(geeco_ctx* c, char* ws_base) {
     L.g = cfg.training ? cv.take((size_t)off * esz) : nullptr;
     // the data gradient of layer l+1 needs only the SIGN of y_l: the forward epilogue also writes one bit per element
     L.mbits = (bf16 && cfg.training && l < 7) ? cv.take((size_t)off / 16 * 2) : nullptr;
+    if (l == 0 && getenv("GEECO_NOBITS0")) L.mbits = nullptr;      // experiment: conv2 data gradient from the bf16 mask
   }
   c->NH = 9 + G;
   c->state = (float*)cv.take(sizeof(float) * N * (xdim + Hl));
