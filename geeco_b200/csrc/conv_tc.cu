@@ -149,7 +149,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
       const TcCls& kc = cl.c[c];
       const long long pix = pix00 + kc.dy0 * g.Wd + kc.dx0;
       const long long off = pix * BN;
-      uint32_t pbits = 0;
+      uint32_t pbits = 0, bits_hold = 0;
       if (MBITS && valid && c_first < BN) pbits = __ldg(mbits + pix * chunks_per_pix + (c_first >> 4));
       // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
       uint32_t pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -206,7 +206,15 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
               uint32_t acc = 0;
 #pragma unroll
               for (int i = 0; i < 8; ++i) acc |= (__vcmpne2(o[i], 0u) & 0x00010001u) << i;
-              bits_out[pix * chunks_per_pix + (c0 >> 4)] = (unsigned short)((acc & 0xffu) | ((acc >> 8) & 0xff00u));
+              const uint32_t b16 = (acc & 0xffu) | ((acc >> 8) & 0xff00u);
+              const int ck = c0 >> 4;
+              if (NHALF == 1 && !(chunks_per_pix & 1)) {
+                // this warp owns every chunk of its rows: two chunks = one aligned 32-bit store (full sectors per warp)
+                if (!(ck & 1)) bits_hold = b16;
+                else *reinterpret_cast<uint32_t*>(bits_out + pix * chunks_per_pix + ck - 1) = bits_hold | (b16 << 16);
+              } else {
+                bits_out[pix * chunks_per_pix + ck] = (unsigned short)b16;
+              }
             }
           }
           if (GEN && dst_f32) {
@@ -249,12 +257,15 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
 
   constexpr int PROD_THREADS = NPW * 32;
   constexpr int EPI_THREADS = (12 - NPW) * 32;
-  constexpr int NHALF = (12 - NPW) / 4;            // epilogue warps per TMEM lane quadrant (column interleave)
+  // epilogue warps: NPW == 4 (one k-block per tile, conv1): two sets of 4 warps that alternate tiles, each warp
+  // owning whole rows (per-tile overhead amortised over both column chunks); else one set, NHALF warps per quadrant
+  constexpr int ESETS = NPW == 4 ? 2 : 1;
+  constexpr int NHALF = (12 - NPW) / 4 / ESETS;    // epilogue warps per TMEM lane quadrant (column interleave)
   constexpr bool A_TMA = NPW == 0;                 // no gather producers: the TMA warp fetches the A tiles as well
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], PROD_THREADS + 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_THREADS / ESETS); }
     fence_barrier_init();
   }
   // bias of every group staged once in shared memory (epilogue reads it per tile)
@@ -376,7 +387,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
    }
   } else if (warp < 12) {
     nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                             tmem_empty, Mg, warp & 3, (warp - NPW) >> 2, lane, 0, 1, bits_out);
+                             tmem_empty, Mg, warp & 3, ((warp - NPW) >> 2) % NHALF, lane, ((warp - NPW) >> 2) / NHALF, ESETS,
+                             bits_out);
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
     // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
@@ -487,10 +499,12 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
   constexpr int W_MMA = EPW * SETS, W_TMA = EPW * SETS + 1;
+  constexpr int SUBSETS = EPW == 8 ? 2 : 1;        // N <= 32: sets of 4 warps, each warp owns whole rows
+  constexpr int SETW = EPW / SUBSETS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPW * 32); }
+    for (int b = 0; b < nbuf; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPW * 32 / SUBSETS); }
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
@@ -510,9 +524,9 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   const int ncls = cl.ncls;
 
   if (warp < W_MMA) {
-    const int set = warp / EPW, ws = warp - set * EPW;
-    nn_epilogue<EPW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS, bits_out);
+    const int set = warp / SETW, ws = warp - set * SETW;
+    nn_epilogue<SETW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS * SUBSETS, bits_out);
   } else if (warp == W_MMA) {
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
     // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
