@@ -114,6 +114,27 @@ def predictions_from_endpoints(ep):
           'pos_obj': ep['pred_aux_obj']}
 
 
+def decode_observation(features, config):
+  """estimator.py:160-172: RGB-D observations are the depth frames concatenated behind the RGB channels
+  (`in_rgbd_frames`, `tgt_rgbd_frame`).  Features that already carry img_channels channels pass through."""
+  if config.img_channels != 4 or np.shape(features['rgb'])[-1] == 4:
+    return features
+  if 'depth' not in features or 'target_depth' not in features:
+    raise ValueError("observation_format rgbd needs features['depth'] and features['target_depth']")
+  import torch
+
+  def cat(a, b):
+    if torch.is_tensor(a) or torch.is_tensor(b):
+      a, b = torch.as_tensor(a), torch.as_tensor(b)
+      return torch.cat([a.float(), b.to(a.device).float()], dim=-1)
+    return np.concatenate([np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)], axis=-1)
+
+  out = dict(features)
+  out['rgb'] = cat(features['rgb'], features['depth'])
+  out['target_rgb'] = cat(features['target_rgb'], features['target_depth'])
+  return out
+
+
 def goal_e2evmc_model_fn(features, labels, mode, params):
   """Eager counterpart of estimator.py:144-279.  `params`: {'e2evmc_config', 'log_steps', 'debug'} plus the
   optional execution keys 'precision' ('bf16' | 'fp32') and 'engine' (reuse an existing Engine)."""
@@ -122,6 +143,7 @@ def goal_e2evmc_model_fn(features, labels, mode, params):
     raise ValueError("Unsupported number of channels for input frame: %d!" % config.img_channels)
   if mode not in (ModeKeys.TRAIN, ModeKeys.EVAL, ModeKeys.PREDICT):
     raise RuntimeError("Unknown estimator mode: %s" % (mode,))
+  features = decode_observation(features, config)
   batch = int(np.shape(features['rgb'])[0])
   eng = params.get('engine') or _engine_for(config, batch, params.get('precision', 'bf16'), mode == ModeKeys.TRAIN)
   if mode == ModeKeys.PREDICT:

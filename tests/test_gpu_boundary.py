@@ -207,3 +207,42 @@ def test_mixed_frame_formats_are_rejected(cuda_device):
   with pytest.raises(ValueError):
     eng.forward(f8, None)
   eng.close()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_rgbd_observation_format(cuda_device, precision):
+  """--observation_format rgbd: model_fn concatenates depth behind RGB (estimator.py:164-172), conv1 sees 4 channels."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import synthetic_batch
+  from geeco_b200.engine import Engine
+  from geeco_b200.estimator import ModeKeys, goal_e2evmc_model_fn
+  N = 2
+  cfg_d = O.make_config(batch_size=N, img_channels=4)
+  cfg = create_e2evmc_config(cfg_d)
+  P = O.init_params(cfg_d, seed=4, dtype=torch.float32, bias_scale=0.05)
+  assert tuple(P['GoalVMC/ConvEncoder/conv1/kernel'].shape) == (3, 3, 4, 32)
+  feats, labels = synthetic_batch(N, seed=6)
+  rng = np.random.default_rng(7)
+  feats['depth'] = rng.uniform(0, 1, size=feats['rgb'].shape[:-1] + (1,)).astype(np.float32)
+  feats['target_depth'] = rng.uniform(0, 1, size=feats['target_rgb'].shape[:-1] + (1,)).astype(np.float32)
+  eng = Engine(cfg, batch_size=N, precision=precision, training=True)
+  eng.set_params(P)
+  spec = goal_e2evmc_model_fn(feats, labels, ModeKeys.EVAL, {'e2evmc_config': cfg, 'engine': eng})
+  torch.cuda.synchronize()
+  f4 = dict(feats)
+  f4['rgb'] = np.concatenate([feats['rgb'], feats['depth']], axis=-1)
+  f4['target_rgb'] = np.concatenate([feats['target_rgb'], feats['target_depth']], axis=-1)
+  ref_losses, ref_grads, ep = O.train_step({k: v.clone() for k, v in P.items()}, O.adam_init(P), f4, labels, cfg_d,
+                                           emulate_bf16=(precision == 'bf16'))
+  tol = 1e-4 if precision == 'fp32' else 2e-2
+  got = eng.losses_dict(spec.loss)
+  assert abs(got['loss'] - ref_losses['loss']) <= tol * abs(ref_losses['loss'])
+  for k in ('pred_cmd_ee', 'pred_aux_ee', 'pred_aux_obj'):
+    assert rel_max(spec.endpoints[k].cpu().numpy(), ep[k].detach().numpy()) <= tol, k
+  spec = goal_e2evmc_model_fn(feats, labels, ModeKeys.TRAIN, {'e2evmc_config': cfg, 'engine': eng})
+  torch.cuda.synchronize()
+  g = eng.get_grads()
+  gtol = 1e-4 if precision == 'fp32' else 1e-1
+  for k in ('GoalVMC/ConvEncoder/conv1/kernel', 'GoalVMC/DynDiffEncoder/conv1/kernel', 'GoalVMC/LSTMDecoder/lstm_cell/kernel'):
+    assert rel_max(g[k], ref_grads[k].numpy()) <= gtol, k
+  eng.close()
