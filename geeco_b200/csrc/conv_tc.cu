@@ -172,7 +172,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
               const float4 bb = b4[i];
               f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
             }
-            if (EPI == TC_EPI_BIAS_RELU || epi == TC_EPI_BIAS_RELU) {
+            if (GEN && epi == TC_EPI_BIAS_RELU) {      // (the compile-time mode applies the ReLU inside the bf16 pack)
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
@@ -199,7 +199,8 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
           if (!GEN || dst) {
             uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            for (int i = 0; i < 8; ++i)
+              o[i] = EPI == TC_EPI_BIAS_RELU ? pack_bf16x2_relu(f[2 * i], f[2 * i + 1]) : pack_bf16x2(f[2 * i], f[2 * i + 1]);
             stg256(dst + off + c0, o);
             if (EPI == TC_EPI_BIAS_RELU && bits_out) {
               // 1-bit ReLU mask of the STORED values: halfword != 0, flags gathered per halfword lane

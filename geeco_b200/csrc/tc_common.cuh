@@ -199,6 +199,12 @@ __device__ __forceinline__ void ldg256_nc(const void* p, uint32_t* v) {
                : "l"(p));
 }
 
+// max(x, 0) fused into the round-to-nearest-even pack (cvt.rn.relu.bf16x2.f32): one instruction per two outputs
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
