@@ -204,10 +204,13 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
             stg256(dst + off + c0, o);
             if (EPI == TC_EPI_BIAS_RELU && bits_out) {
               // 1-bit ReLU mask of the STORED values: halfword != 0, flags gathered per halfword lane
+              // both halfwords of o[i] are non-negative bf16 (<= 0x7fff): h + 0x7fff has bit 15 set iff h != 0, and the
+              // sum cannot carry into the other half.  Shifting the accumulator right once per word leaves word i's two
+              // flags at bits 8+i and 24+i: three instructions per word.
               uint32_t acc = 0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc |= (__vcmpne2(o[i], 0u) & 0x00010001u) << i;
-              const uint32_t b16 = (acc & 0xffu) | ((acc >> 8) & 0xff00u);
+              for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[i] + 0x7fff7fffu) & 0x80008000u);
+              const uint32_t b16 = ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
               const int ck = c0 >> 4;
               if (NHALF == 1 && !(chunks_per_pix & 1)) {
                 // this warp owns every chunk of its rows: two chunks = one aligned 32-bit store (full sectors per warp)
