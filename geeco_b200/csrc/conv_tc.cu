@@ -172,7 +172,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
               const float4 bb = b4[i];
               f[4 * i] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
             }
-            if (GEN && epi == TC_EPI_BIAS_RELU) {      // (the compile-time mode applies the ReLU inside the bf16 pack)
+            if (GEN && (epi == TC_EPI_BIAS_RELU || epi == TC_EPI_RELU)) {      // (compile-time modes: ReLU inside the bf16 pack)
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
@@ -200,9 +200,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
             uint32_t o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              o[i] = EPI == TC_EPI_BIAS_RELU ? pack_bf16x2_relu(f[2 * i], f[2 * i + 1]) : pack_bf16x2(f[2 * i], f[2 * i + 1]);
+              o[i] = (EPI == TC_EPI_BIAS_RELU || EPI == TC_EPI_RELU) ? pack_bf16x2_relu(f[2 * i], f[2 * i + 1])
+                                                                      : pack_bf16x2(f[2 * i], f[2 * i + 1]);
             stg256(dst + off + c0, o);
-            if (EPI == TC_EPI_BIAS_RELU && bits_out) {
+            if ((EPI == TC_EPI_BIAS_RELU || EPI == TC_EPI_RELU) && bits_out) {
               // 1-bit ReLU mask of the STORED values: halfword != 0, flags gathered per halfword lane
               // both halfwords of o[i] are non-negative bf16 (<= 0x7fff): h + 0x7fff has bit 15 set iff h != 0, and the
               // sum cannot carry into the other half.  Shifting the accumulator right once per word leaves word i's two
@@ -280,6 +281,17 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
   // they hold later is finite data (multiplied by zero weights)
   if (!A_TMA) zero_smem(a_base, stages * A_STAGE_BYTES);
+  if (!A_TMA && g.bias_in_k) {
+    // bias folded into the GEMM: column Ktot of every im2col row is a constant 1.0 (bf16 0x3f80), written once;
+    // the producers only ever write the columns below Ktot
+    __syncthreads();
+    const uint32_t obyte = (uint32_t)g.Ktot * 2;
+    for (int i = threadIdx.x; i < stages * BM; i += blockDim.x) {
+      const int st_i = i / BM, r = i - st_i * BM;
+      uint8_t* p = a_base + st_i * A_STAGE_BYTES + r * 128 + ((((obyte >> 4) ^ (uint32_t)(r & 7))) << 4) + (obyte & 15u);
+      *reinterpret_cast<uint16_t*>(p) = 0x3f80;
+    }
+  }
   fence_proxy_async();
   if (warp == 12) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   if (warp == 13 && lane == 0) {
@@ -1008,14 +1020,16 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int m
 
 __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ out, int mode, int groups,
                                     long long w_group_stride, int Cin, int Cout, int Cs, int ntaps, int rows, int Kpad,
-                                    int Kt, int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8) {
+                                    int Kt, int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8,
+                                    const float* __restrict__ bias, int bias_col) {
   const int taps[9] = {t0, t1, t2, t3, t4, t5, t6, t7, t8};
   const long long total = (long long)groups * rows * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kpad);
     const long long rr = i / Kpad;
     const int r = (int)(rr % rows), grp = (int)(rr / rows);
-    const float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, Kt, r, k);
+    float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, Kt, r, k);
+    if (k == bias_col && r < Cout) v = bias[r];
     out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -1036,7 +1050,9 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
   const uint32_t total = (uint32_t)jb.total, Kp = (uint32_t)jb.Kpad, rows = (uint32_t)jb.rows;
   const int mode = jb.mode, Cin = jb.Cin, Cout = jb.Cout, Cs = jb.Cs, ntaps = jb.ntaps, Kt = jb.Kt;
   const float* W = jb.W;
-  const long long wgs = jb.w_group_stride;
+  const float* bias = jb.bias;
+  const int bias_col = jb.bias_col;
+  const long long wgs = jb.w_group_stride, bgs = jb.b_group_stride;
   __nv_bfloat16* out = jb.out;
   uint32_t i = (uint32_t)(v0 - jb.start) + threadIdx.x;
 #pragma unroll 1
@@ -1044,7 +1060,9 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
     if (i >= total) break;
     const uint32_t rr = i / Kp, k = i - rr * Kp;
     const uint32_t grp = rr / rows, r = rr - grp * rows;
-    out[i] = __float2bfloat16_rn(pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k));
+    float v = pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k);
+    if ((int)k == bias_col && (int)r < Cout) v = bias[(long long)grp * bgs + r];
+    out[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -1172,7 +1190,7 @@ static TcGeom gather_view(const TcGeom& g) {
   TcGeom v = g;
   // always at least one padding column: the bias gradient rides in it as a column of ones (one more 64-wide
   // sub-tile when ntaps * Cs is a multiple of 64) instead of two extra column-sum launches per layer
-  v.a_tma = 0; v.rows = 0; v.wpack = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 64) / 64 * 64;
+  v.a_tma = 0; v.rows = 0; v.wpack = 0; v.bias_in_k = 0; v.Kt = v.Cs; v.Ktot = v.ntaps * v.Cs; v.Kpad = (v.Ktot + 64) / 64 * 64;
   return v;
 }
 
@@ -1230,6 +1248,7 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
     g.rows = 2; g.wpack = 4; g.a_tma = 0; g.Kt = 64; g.Ktot = g.Kpad = 6 * 64;
   }
   g.rowwin = (Cs == 4 && stride == 1 && Wo % 128 == 0 && g.hw_shift >= 0) ? 1 : 0;
+  g.bias_in_k = (g.rowwin && g.Kpad > g.Ktot && !getenv("GEECO_TC_NO_BIAS_IN_K")) ? 1 : 0;
   return g;
 }
 
@@ -1325,7 +1344,7 @@ static void fill_class(TcCls* c, const TcGeom& g) {
 
 // compile-time epilogue for the hot cases (bf16 destination only), the generic one otherwise
 static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f32) {
-  if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_MASKBITS)) return epi;
+  if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_MASKBITS || epi == TC_EPI_RELU)) return epi;
   return EPI_GENERIC;
 }
 
@@ -1429,6 +1448,12 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
                        const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
                        int max_ctas, cudaStream_t st, unsigned short* bits_out) {
+  if (gs[0].bias_in_k) {
+    // the packed weights carry the bias in column Ktot and the im2col rows a constant 1.0: nothing left to add
+    if (epi == TC_EPI_BIAS_RELU) epi = TC_EPI_RELU;
+    else if (epi == TC_EPI_BIAS) epi = TC_EPI_STORE;
+    bias = nullptr;
+  }
   if (epi == TC_EPI_MASKBITS && (!mask || !dst || dst_f32)) {
     geeco_set_error("tc_nn: TC_EPI_MASKBITS needs the bit mask and a bf16 destination only");
     return GEECO_ERR_INVALID;
@@ -1504,6 +1529,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     if (epi_t == TC_EPI_MASK) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_MASK);                                                  \
     else if (epi_t == TC_EPI_MASKBITS) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_MASKBITS);                                     \
     else if (epi_t == TC_EPI_BIAS_RELU) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_BIAS_RELU);                                   \
+    else if (epi_t == TC_EPI_RELU) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_RELU);                                             \
     else NN_LAUNCH_M(PIECE_, NPW_, EPI_GENERIC);                                                                       \
   } while (0)
   const int epi_t = tc_epi_template(epi, dst, dst_f32);
@@ -1641,13 +1667,16 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
 }
 
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
-                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st) {
+                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st,
+                        const float* bias, int bias_col) {
+  if (groups != 1 && bias_col >= 0) { geeco_set_error("pack_weights: a bias column needs groups == 1 here"); return GEECO_ERR_INVALID; }
   int t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = 0; i < ntaps && i < 9; ++i) t[i] = taps[i];
   const long long total = (long long)groups * rows * Kpad;
   int blocks = ceil_div(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
   pack_weights_kernel<<<blocks, 256, 0, st>>>(W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad, Kt,
-                                              t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+                                              t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], bias,
+                                              bias ? bias_col : -1);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

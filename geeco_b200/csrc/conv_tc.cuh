@@ -19,6 +19,8 @@ struct TcGeom {
   int rows;                   // row-resident kernel (tc_rows_kernel): 0 no, 1 unit-stride source (data gradient of a
                               // stride-2 layer), 2 forward stride-2 layer on pixel pairs (Cs == 32)
   int wpack;                  // weight packing mode of the forward operand (0 tap-major, 4 pixel pairs; see pack_value)
+  int bias_in_k;              // 1: the bias is folded into the GEMM (row-window conv1): packed-weight column Ktot holds the
+                              // bias and the im2col rows carry a constant 1.0 there, so the epilogue neither loads nor adds it
   int Nn;                     // GEMM N (multiple of 16, <= 256)
   int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
   int dsy, dsx, dy0, dx0;
@@ -49,7 +51,8 @@ struct TcMaps { CUtensorMap m[4]; };
 
 // TC_EPI_MASKBITS: like TC_EPI_MASK, but `mask` points at the 1-bit-per-element mask a TC_EPI_BIAS_RELU launch wrote
 // through `bits_out` (uint16 per (pixel, 16-channel chunk); bit j = channel 2j, bit 8+j = channel 2j+1 of the chunk)
-enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3, TC_EPI_MASKBITS = 4 };
+enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3, TC_EPI_MASKBITS = 4,
+       TC_EPI_RELU = 5 };   // TC_EPI_RELU: ReLU only (bias already inside the accumulator, see TcGeom::bias_in_k)
 
 struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packed tap
 
@@ -77,11 +80,13 @@ int launch_conv1pair_reduce(const float* part_even, const float* part_odd, float
 // packed bf16 weights.  mode 0 (fwd): out[g][n][t*Cs + ch] = W[g][tap_t][ch][n] ; rows = Nn
 //                       mode 1 (dgrad): out[g][ci][t*Cout + co] = W[g][tap_t][ci][co] ; rows = Cin
 int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups, long long w_group_stride, int Cin,
-                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st);
+                        int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, cudaStream_t st,
+                        const float* bias = nullptr, int bias_col = -1);
 // all weight repacks of a step as ONE launch: a table of jobs in device memory
 struct PackJob {
   const float* W; __nv_bfloat16* out; long long w_group_stride; long long start; long long total;
   int mode, groups, Cin, Cout, Cs, ntaps, rows, Kpad; int taps[9]; int Kt;   // Kt: K extent per tap (0 = Cs / Cout)
+  const float* bias; long long b_group_stride; int bias_col; int pad_;       // bias_col >= 0: column that holds bias[row]
 };
 // jobs occupy [start, start + total) of a virtual index space; every start is a multiple of PACK_CHUNK and
 // grand_total is the end of the last job rounded up to PACK_CHUNK (total < 2^31 per job)

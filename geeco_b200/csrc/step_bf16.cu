@@ -152,11 +152,13 @@ void free_bf16(geeco_ctx* c) {
 static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
 static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, int groups, long long wstride, int Cin,
-                    int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt) {
+                    int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, const float* bias = nullptr,
+                    long long bstride = 0, int bias_col = -1) {
   PackJob j;
   memset(&j, 0, sizeof(j));
   j.W = W; j.out = out; j.w_group_stride = wstride; j.mode = mode; j.groups = groups; j.Cin = Cin; j.Cout = Cout;
   j.Cs = Cs; j.ntaps = ntaps; j.rows = rows; j.Kpad = Kpad; j.Kt = Kt;
+  j.bias = bias; j.b_group_stride = bstride; j.bias_col = bias ? bias_col : -1;
   for (int i = 0; i < ntaps && i < 9; ++i) j.taps[i] = taps[i];
   j.start = bp->jobs_total;
   j.total = (long long)groups * rows * Kpad;
@@ -182,8 +184,9 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
           for (int par = 0; par < 2; ++par)
             add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
         } else {
+          const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
           add_job(bp, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
-                  B.fwd.Kpad, B.fwd.Kt);
+                  B.fwd.Kpad, B.fwd.Kt, B.fwd.bias_in_k ? c->theta + c->params[L.p_b[e]].offset : nullptr, bstride, B.fwd.Ktot);
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
@@ -370,7 +373,8 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
   }
   TcGeom g = tc_fwd_geom(H, W, Cin, Cout, stride, N, 1);
   __nv_bfloat16* wp = (__nv_bfloat16*)(base + o_fwd);
-  int rc = launch_pack_weights(w, wp, g.wpack, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, g.Kt, st);
+  int rc = launch_pack_weights(w, wp, g.wpack, 1, 0, Cw, Cout, Cin, 9, kAllTaps, Cout, g.Kpad, g.Kt, st,
+                               g.bias_in_k ? b : nullptr, g.Ktot);
   if (rc) return rc;
   CUtensorMap map;
   rc = make_weight_tensor_map(&map, wp, Cout, g.Kpad, Cout);

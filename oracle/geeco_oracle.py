@@ -180,7 +180,8 @@ def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False):
   emulate_bf16=True restates the SAME graph with the storage roundings of the library's bf16 mode
   (DESIGN.md "bf16 policy"): encoder input, conv kernels, every post-ReLU activation except conv8's
   and every pre-activation gradient are rounded to bfloat16; accumulation, biases, master weights and
-  everything after conv8 stay in the working dtype.  It exists because ReLU-mask flips make the bf16
+  everything after conv8 stay in the working dtype.  One exception: conv1's bias is rounded to bfloat16 as well,
+  because the library folds it into the conv1 GEMM as one more column of the packed bf16 weights.  It exists because ReLU-mask flips make the bf16
   gradients differ from the fp32 graph's by O(sqrt(eps)), which says nothing about kernel correctness."""
   acts = []
   net = round_bf16(x_nhwc) if emulate_bf16 else x_nhwc
@@ -188,7 +189,7 @@ def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False):
     w = params['%s/conv%d/kernel' % (scope, li + 1)]
     b = params['%s/conv%d/bias' % (scope, li + 1)]
     if emulate_bf16:
-      z = conv2d_same(net, round_bf16(w), b, ENCODER_STRIDES[li], relu=False)
+      z = conv2d_same(net, round_bf16(w), round_bf16(b) if li == 0 else b, ENCODER_STRIDES[li], relu=False)
       z = _GradRoundBF16.apply(z)
       net = torch.relu(z)
       if li < 7:
