@@ -35,7 +35,6 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
-constexpr int LOOKAHEAD = 2;                          // cp.async groups in flight per producer thread before it signals
 constexpr int NN_THREADS = 12 * 32 + 64;   // producer + epilogue warps (12), MMA warp, TMA warp
 
 constexpr int A_STAGE_BYTES = BM * BK * 2;            // 16 KB
@@ -69,37 +68,6 @@ __device__ __forceinline__ void split_k(const TcGeom& g, int k, int& tap, int& c
   if (g.cs_shift >= 0) { tap = k >> g.cs_shift; ch = k & (g.Cs - 1); }
   else { tap = k / g.Cs; ch = k - tap * g.Cs; }
 }
-// bit t set <=> tap t of source pixel (ys+dy[t], xs+dx[t]) lies inside the image
-__device__ __forceinline__ uint32_t tap_mask(const TcGeom& g, int ys, int xs) {
-  uint32_t mk = 0;
-#pragma unroll
-  for (int t = 0; t < GEECO_MAX_TAPS; ++t) {
-    if (t < g.ntaps) {
-      const int iy = ys + g.dy[t], ix = xs + g.dx[t];
-      if ((unsigned)iy < (unsigned)g.Hs && (unsigned)ix < (unsigned)g.Ws) mk |= 1u << t;
-    }
-  }
-  return mk;
-}
-
-// One mbarrier arrival per producer WARP (per-thread arrivals on one mbarrier serialise in the shared-memory
-// atomic unit): each thread commits its copies of k-block `it` as a cp.async group, waits until the group of
-// k-block it-LOOKAHEAD has landed, the warp converges and lane 0 arrives on that older stage.
-__device__ __forceinline__ void producer_signal(uint64_t* full, uint32_t it, int stages, int lane) {
-  cp_async_commit();
-  if (it >= LOOKAHEAD) {
-    cp_async_wait<LOOKAHEAD>();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&full[(it - LOOKAHEAD) % stages]);
-  }
-}
-__device__ __forceinline__ void producer_drain(uint64_t* full, uint32_t it, int stages, int lane) {
-  cp_async_wait<0>();
-  __syncwarp();
-  if (lane == 0)
-    for (uint32_t j = it >= LOOKAHEAD ? it - LOOKAHEAD : 0; j < it; ++j) mbar_arrive(&full[j % stages]);
-}
-
 __device__ __forceinline__ void zero_smem(uint8_t* base, int bytes) {
   for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16) *reinterpret_cast<uint4*>(base + i) = make_uint4(0, 0, 0, 0);
 }
@@ -941,51 +909,6 @@ __global__ void conv1pair_reduce_kernel(const float* __restrict__ part_even, con
   }
 }
 
-// column sums of a bf16 [rows][C] matrix per group (bias gradient when no padding column exists).
-// stage 1: grid (chunks, groups), 16-byte loads, fixed-order in-block reduction -> part[g][chunk][C];
-// stage 2 adds the chunks in order.  C % 8 == 0, C <= 256.
-__global__ void __launch_bounds__(256) colsum_bf16_stage1(const __nv_bfloat16* __restrict__ G, float* __restrict__ part,
-                                                          long long rows_per_group, int C, int chunks) {
-  __shared__ float red[8][264];
-  const int grp = blockIdx.y, chunk = blockIdx.x;
-  const int cg = C >> 3;                       // 16-byte column groups
-  int rp = 256 / cg; if (rp > 8) rp = 8;       // rows handled in parallel
-  const int rl = threadIdx.x / cg, c8 = threadIdx.x - rl * cg;
-  const long long per = (rows_per_group + chunks - 1) / chunks;
-  const long long lo = (long long)chunk * per;
-  long long hi = lo + per; if (hi > rows_per_group) hi = rows_per_group;
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (rl < rp) {
-    const __nv_bfloat16* base = G + ((long long)grp * rows_per_group) * C + c8 * 8;
-    for (long long r = lo + rl; r < hi; r += rp) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * C));
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        a[2 * i] += __uint_as_float(w[i] << 16);
-        a[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[rl][c8 * 8 + i] = a[i];
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < rp; ++r) s += red[r][c];
-    part[((long long)grp * chunks + chunk) * C + c] = s;
-  }
-}
-__global__ void colsum_stage2(const float* __restrict__ part, float* __restrict__ out, int C, int chunks,
-                              long long out_group_stride) {
-  const int grp = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += part[((long long)grp * chunks + k) * C + c];
-    out[(long long)grp * out_group_stride + c] = s;
-  }
-}
-
 // value of packed weight element (row r, column k) of a pack job.
 //   mode 0 (forward):       out[n][t*Cs + ch]   = W[tap_t][ch][n]
 //   mode 1 (data gradient): out[ci][t*Cout + co] = W[tap_t][ci][co]
@@ -1586,9 +1509,7 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
 long long tc_wgrad_partial_floats(const TcGeom& g_in, int Cout) {
   const TcGeom g = gather_view(g_in);
   WgradPlan p = wgrad_plan(g, Cout);
-  long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
-  long long colsum_part = (long long)g.groups * 296 * Cout;
-  return main_part + colsum_part + 64;
+  return (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad + 64;
 }
 
 // runs the weight-gradient GEMM into `partial` ([splits][groups][Mrows_pad][Kpad] fp32)
@@ -1647,21 +1568,13 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   WgradPlan p;
   int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st);
   if (rc) return rc;
-  const long long main_part = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad;
   const int ones = dbias ? p.ones_col : -1;
   const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
   int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
   wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
                                           g.Ktot, ones, dw_group_stride, dbias_group_stride);
   geeco_count_launch(1);
-  if (dbias && p.ones_col < 0) {
-    if (Cout > 256) { geeco_set_error("tc_wgrad: bias gradient needs Cout <= 256"); return GEECO_ERR_INVALID; }
-    float* part = partial + main_part;
-    int chunks = (int)(Mg / 256); if (chunks > 296 / g.groups) chunks = 296 / g.groups; if (chunks < 1) chunks = 1;
-    colsum_bf16_stage1<<<dim3(chunks, g.groups), 256, 0, st>>>(G, part, Mg, Cout, chunks);
-    colsum_stage2<<<g.groups, 256, 0, st>>>(part, dbias, Cout, chunks, dbias_group_stride);
-    geeco_count_launch(2);
-  }
+  if (dbias && p.ones_col < 0) { geeco_set_error("tc_wgrad: no padding column for the bias gradient"); return GEECO_ERR_INVALID; }
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }

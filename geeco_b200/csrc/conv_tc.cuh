@@ -54,8 +54,6 @@ struct TcMaps { CUtensorMap m[4]; };
 enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3, TC_EPI_MASKBITS = 4,
        TC_EPI_RELU = 5 };   // TC_EPI_RELU: ReLU only (bias already inside the accumulator, see TcGeom::bias_in_k)
 
-struct TcWeightTap { int tap; };   // original 3x3 tap index (ky*3+kx) per packed tap
-
 // fwd / dgrad: dst = epi(A(src) x Wp^T)
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,

@@ -52,14 +52,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
-// Role-wide wait: ONE warp polls the mbarrier, its peers block on a hardware named barrier (no issue slots
-// burnt by spinning warps; the kernels here are instruction-issue-bound).  All `nthreads` threads of the role call it.
-__device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity, bool is_poller_warp, int barrier_id,
-                                               int nthreads) {
-  if (is_poller_warp) mbar_wait(bar, parity);
-  asm volatile("bar.sync %0, %1;" ::"r"(barrier_id), "r"(nthreads) : "memory");
-}
-
 // one lane of a converged warp (the tcgen05 issue instructions take warp-uniform operands: the WHOLE warp runs
 // the issue loop so that the compiler keeps descriptors in uniform registers, and only the instruction is elected)
 __device__ __forceinline__ bool elect_one() {
@@ -99,26 +91,6 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const CUtensorMap
           dst_smem),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
-}
-// shared -> global tile store (bulk async-group completion): the engine scatters the box rows, the SM issues one instruction
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(src_smem), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -169,15 +141,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   d |= (uint64_t)2 << 61;
   return d;
 }
-// the same for a matrix whose first row does not sit on a 1024-byte boundary of the swizzle pattern (a window that
-// starts r rows into an 8-row atom): base_offset [49,52) = (address >> 7) & 7
-__device__ __forceinline__ uint64_t make_desc_sw128_off(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-#ifdef GEECO_DESC_BASE_OFFSET
-  return make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | ((uint64_t)((smem_addr >> 7) & 7u) << 49);
-#else
-  return make_desc_sw128(smem_addr, lbo_bytes, sbo_bytes);
-#endif
-}
+// A matrix may start at any 128-byte row of the swizzle atom (a window shifted by whole pixels): the hardware derives
+// the swizzle phase from the address bits, the base_offset field stays 0 (setting it to (addr >> 7) & 7 gives wrong
+// results; measured, profiles/r01_ncu_notes.md).
 // Instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32 (1<<4), A=B=bf16 (1<<7, 1<<10),
 // a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
