@@ -567,10 +567,11 @@ static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
     if (rc) return rc;
   }
   if (out) {
-    if (out->heads) CUDA_TRY(cudaMemcpyAsync(out->heads, c->heads, sizeof(float) * N * c->NH, cudaMemcpyDeviceToDevice, st));
-    if (out->fc1) CUDA_TRY(cudaMemcpyAsync(out->fc1, c->fc1, sizeof(float) * N * cfg.dim_h_fc, cudaMemcpyDeviceToDevice, st));
-    if (out->lstm_state) CUDA_TRY(cudaMemcpyAsync(out->lstm_state, c->state_out, sizeof(float) * N * 2 * Hl, cudaMemcpyDeviceToDevice, st));
-    if (out->losses && with_loss) CUDA_TRY(cudaMemcpyAsync(out->losses, c->losses, sizeof(float) * 8, cudaMemcpyDeviceToDevice, st));
+    const float* src[4] = {c->heads, c->fc1, c->state_out, c->losses};
+    float* dst[4] = {out->heads, out->fc1, out->lstm_state, with_loss ? out->losses : nullptr};
+    const long long n[4] = {(long long)N * c->NH, (long long)N * cfg.dim_h_fc, (long long)N * 2 * Hl, 8};
+    rc = launch_copy_outputs(src, dst, n, st);
+    if (rc) return rc;
   }
   return GEECO_OK;
 }
@@ -707,6 +708,8 @@ extern "C" int geeco_step_update(geeco_ctx* c, float grad_scale, void* stream) {
 
 extern "C" int geeco_train_step(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, float grad_scale,
                                 void* stream) {
+  // (Replaying the step as a CUDA graph was measured: 2.657 vs 2.659 ms. The ~2 us between dependent kernels are
+  // kernel drain + launch latency, not host enqueue, so the step stays a plain launch sequence.)
   int rc = geeco_step_forward(c, b, out, stream);
   if (rc) return rc;
   for (int bucket = 0; bucket < 3; ++bucket) {

@@ -426,6 +426,26 @@ __global__ void gates_reduce_kernel(const float* __restrict__ partial, const flo
   gates[i] = s;
 }
 
+// the caller-visible outputs of a step (heads, fc1, LSTM state, losses) in ONE launch instead of four D2D copies
+struct CopyList { const float* src[4]; float* dst[4]; long long n[4]; };
+__global__ void copy_outputs_kernel(CopyList cl) {
+  const float* s = cl.src[blockIdx.y];
+  float* d = cl.dst[blockIdx.y];
+  if (!d) return;
+  const long long n = cl.n[blockIdx.y];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) d[i] = s[i];
+}
+int launch_copy_outputs(const float* const* src, float* const* dst, const long long* n, cudaStream_t st) {
+  CopyList cl;
+  bool any = false;
+  for (int i = 0; i < 4; ++i) { cl.src[i] = src[i]; cl.dst[i] = dst[i]; cl.n[i] = n[i]; any = any || dst[i]; }
+  if (!any) return GEECO_OK;
+  copy_outputs_kernel<<<dim3(16, 4), 256, 0, st>>>(cl);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
 long long lstm_gates_partial_floats(int N, int K, int Ncols) {
   return (long long)((K + GK_SLICE - 1) / GK_SLICE) * N * Ncols;
 }

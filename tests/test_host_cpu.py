@@ -272,3 +272,24 @@ def test_compat_import_paths():
           "from utils.runscript import save_run_command; print('ok')") % os.path.join(ROOT, 'compat')
   r = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   assert r.returncode == 0 and 'ok' in r.stdout, r.stdout
+
+
+def test_decode_observation_concatenates_depth_behind_rgb():
+  """estimator.py:160-172: rgbd observations = depth frames concatenated behind the RGB channels."""
+  import numpy as np
+  import pytest
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.estimator import decode_observation
+  cfg3 = create_e2evmc_config({})
+  cfg4 = create_e2evmc_config({'img_channels': 4})
+  rng = np.random.default_rng(0)
+  f = {'rgb': rng.uniform(size=(2, 4, 8, 8, 3)).astype(np.float32), 'target_rgb': rng.uniform(size=(2, 8, 8, 3)).astype(np.float32),
+       'depth': rng.uniform(size=(2, 4, 8, 8, 1)).astype(np.float32), 'target_depth': rng.uniform(size=(2, 8, 8, 1)).astype(np.float32)}
+  assert decode_observation(f, cfg3) is f                       # RGB: untouched
+  out = decode_observation(f, cfg4)
+  assert out['rgb'].shape == (2, 4, 8, 8, 4) and out['target_rgb'].shape == (2, 8, 8, 4)
+  assert np.array_equal(out['rgb'][..., :3], f['rgb']) and np.array_equal(out['rgb'][..., 3:], f['depth'])
+  assert np.array_equal(out['target_rgb'][..., 3:], f['target_depth'])
+  assert decode_observation(out, cfg4) is out                   # already 4 channels: untouched
+  with pytest.raises(ValueError):
+    decode_observation({'rgb': f['rgb'], 'target_rgb': f['target_rgb']}, cfg4)
