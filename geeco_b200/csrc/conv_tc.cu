@@ -877,6 +877,50 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
+// Transposing variant: grid (k tiles of 32, co tiles of 32, groups), block (32, 32 / CPT).  Partials are read along k
+// (their fastest index), dW is written along co (its fastest index) through a 32x32 shared-memory tile; splits are
+// added in order.  CPT = output channels per thread: 4 when there are few splits, 1 when there are many.
+template <int CPT>
+__global__ void __launch_bounds__(1024 / CPT) wgrad_reduce_t_kernel(const float* __restrict__ partial, float* __restrict__ dW,
+                                                                    float* __restrict__ dbias, int splits, int groups,
+                                                                    int Mrows_pad, int Kpad, int Cout, int Cs, int Cw, int Ktot,
+                                                                    int ones_col, long long dw_group_stride,
+                                                                    long long dbias_group_stride) {
+  constexpr int RY = 32 / CPT;                     // blockDim.y
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, co0 = blockIdx.y * 32, grp = blockIdx.z;
+  const long long sstride = (long long)groups * Mrows_pad * Kpad;
+  {
+    const int k = k0 + threadIdx.x;
+    const int col = k < Ktot ? k : (k == Ktot ? ones_col : -1);
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+      const int co = co0 + threadIdx.y + RY * j;
+      float sum = 0.f;
+      if (co < Cout && col >= 0) {
+        const float* p = partial + ((long long)grp * Mrows_pad + co) * Kpad + col;
+#pragma unroll 4
+        for (int sp = 0; sp < splits; ++sp) sum += p[sp * sstride];
+      }
+      tile[threadIdx.y + RY * j][threadIdx.x] = sum;
+    }
+  }
+  __syncthreads();
+  const int co = co0 + threadIdx.x;
+  if (co >= Cout) return;
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) {
+    const int k = k0 + threadIdx.y + RY * j;
+    const float v = tile[threadIdx.x][threadIdx.y + RY * j];
+    if (k < Ktot) {
+      const int tap = k / Cs, ch = k - tap * Cs;
+      if (ch < Cw) dW[(long long)grp * dw_group_stride + (long long)(tap * Cw + ch) * Cout + co] = v;
+    } else if (k == Ktot && dbias && ones_col >= 0) {
+      dbias[(long long)grp * dbias_group_stride + co] = v;
+    }
+  }
+}
+
 // conv1 on pixel pairs: dW[ky][kx][c][co] = sum over the two parity classes and splits of the partial column that
 // holds (ky, kx, c) in that class (see pack_value modes 2/3); bias gradient from the ones column k = 48.
 __global__ void conv1pair_reduce_kernel(const float* __restrict__ part_even, const float* __restrict__ part_odd,
@@ -1569,10 +1613,23 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st);
   if (rc) return rc;
   const int ones = dbias ? p.ones_col : -1;
-  const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
-  int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
-  wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
-                                          g.Ktot, ones, dw_group_stride, dbias_group_stride);
+  const dim3 tgrid(ceil_div(g.Ktot + 1, 32), ceil_div(Cout, 32), g.groups);
+  const int tiles = (int)(tgrid.x * tgrid.y * tgrid.z);
+  if (p.splits <= 12 && tiles >= 2 * num_sms()) {
+    // few splits, many outputs (conv5-conv8)
+    wgrad_reduce_t_kernel<4><<<tgrid, dim3(32, 8), 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
+                                                           g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
+  } else if (tiles >= 64) {
+    // more splits (conv3, conv4): one output channel per thread, 1024 threads per tile
+    wgrad_reduce_t_kernel<1><<<tgrid, dim3(32, 32), 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
+                                                            g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
+  } else {
+    // many splits, few outputs (conv1, conv2): one thread per output, no transpose
+    const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
+    int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
+    wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
+                                            g.Ktot, ones, dw_group_stride, dbias_group_stride);
+  }
   geeco_count_launch(1);
   if (dbias && p.ones_col < 0) { geeco_set_error("tc_wgrad: no padding column for the bias gradient"); return GEECO_ERR_INVALID; }
   CUDA_TRY(cudaGetLastError());
