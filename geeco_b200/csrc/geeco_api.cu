@@ -674,8 +674,7 @@ extern "C" int geeco_step_backward(geeco_ctx* c, int32_t bucket, void* stream) {
     GatherGeom gw = dense_geom(N, c->xdim + Hl, 4 * Hl, 4 * Hl, 0);
     rc = launch_gemm_tn_f32(gw, c->state, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), c->partial, c->partial_cap, 1, 0, 0, st);
     if (rc) return rc;
-    GatherGeom gx = dense_geom(N, 4 * Hl, c->xdim, 4 * Hl, 1);
-    rc = launch_gemm_nn_f32(gx, c->dgates, P(c, c->p_lstm_w), nullptr, nullptr, c->dstate, 1, EPI_STORE, st);
+    rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstate, N, c->xdim, 4 * Hl, c->xdim, st);
     if (rc) return rc;
     LayerPlan& L8 = c->layers[7];
     const float* y8 = bf16 ? c->y8_f32 : (const float*)L8.y;

@@ -30,6 +30,9 @@ int launch_adam(float* theta, const float* grad, float* m, float* v, long long n
                 double b2, double eps, float gscale, float l2, cudaStream_t st);
 int launch_l2_term(const float* theta, long long n, float l2, float* sc, cudaStream_t st);
 long long lstm_gates_partial_floats(int N, int K, int Ncols);
+// d(state) of the LSTM gate GEMM for the x part of its input: dstate[N][ld] (first xdim columns) = dgates[N][ncols] x W[.][ncols]^T
+int launch_lstm_dstate(const float* dgates, const float* W, float* dstate, int N, int xdim, int ncols, int ld,
+                       cudaStream_t st);
 // up to four device-to-device output copies in one launch (dst[i] == NULL skips one)
 int launch_copy_outputs(const float* const* src, float* const* dst, const long long* n, cudaStream_t st);
 int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias, float* gates, float* partial, int N,
