@@ -591,13 +591,17 @@ static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
     geeco_set_error("batch: frame_format %d is neither GEECO_FRAMES_F32 nor GEECO_FRAMES_U8", b->frame_format);
     return GEECO_ERR_INVALID;
   }
-  int rc = launch_preprocess_geecof(b->rgb, b->target_rgb, b->frame_format == GEECO_FRAMES_U8, c->x0, bf16 ? 1 : 0,
+  int rc = bf16 ? repack_fork_bf16(c, st) : GEECO_OK;
+  if (rc) return rc;
+  rc = launch_preprocess_geecof(b->rgb, b->target_rgb, b->frame_format == GEECO_FRAMES_U8, c->x0, bf16 ? 1 : 0,
                                     c->CP, out ? out->dynbuff : nullptr,
                                     out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
                                     cfg.img_width, cfg.img_channels, c->alpha, 0, st);
   if (rc) return rc;
   const float* y8;
   if (bf16) {
+    rc = repack_join_bf16(c, st);
+    if (rc) return rc;
     rc = encoders_fwd_bf16(c, st);
     if (rc) return rc;
     y8 = c->y8_f32;

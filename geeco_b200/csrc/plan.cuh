@@ -52,5 +52,7 @@ void geeco_count_launch(int n);
 // step_bf16.cu
 int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base);
 void free_bf16(geeco_ctx* c);
+int repack_fork_bf16(geeco_ctx* c, cudaStream_t st);     // weight repack on a side stream, ordered after `st` so far
+int repack_join_bf16(geeco_ctx* c, cudaStream_t st);     // `st` waits for it
 int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st);
 int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st);

@@ -32,6 +32,11 @@ struct Bf16Plan {
   std::vector<PackJob> jobs;
   long long jobs_total;
   bool jobs_uploaded;
+  // the weight repack of a step does not depend on the batch: it runs on a side stream next to the rank-pooling
+  // kernel (whose 16-CTA clusters leave a quarter of the SMs idle) and is joined before the first convolution
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool forked = false;
 };
 
 // packed-K extent of a data-gradient class when the layer's output has `cout` channels (the planned geometry was
@@ -113,6 +118,11 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   bp->jobs_dev = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_uploaded = false;
   if (!ws_base) return GEECO_OK;
+  if (!bp->side) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&bp->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join, cudaEventDisableTiming));
+  }
   // tensor maps (need the real addresses)
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
@@ -146,7 +156,14 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
 }
 
 void free_bf16(geeco_ctx* c) {
-  if (c->bf16_ws) { delete (Bf16Plan*)c->bf16_ws; c->bf16_ws = nullptr; }
+  if (c->bf16_ws) {
+    Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+    if (bp->side) { cudaStreamSynchronize(bp->side); cudaStreamDestroy(bp->side); }
+    if (bp->ev_fork) cudaEventDestroy(bp->ev_fork);
+    if (bp->ev_join) cudaEventDestroy(bp->ev_join);
+    delete bp;
+    c->bf16_ws = nullptr;
+  }
 }
 
 static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
@@ -205,6 +222,29 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st) {
   int rc = launch_pack_weights_batched(bp->jobs_dev, (int)bp->jobs.size(), bp->jobs_total, st);
   if (rc) return rc;
   c->weights_dirty = false;
+  return GEECO_OK;
+}
+
+// Starts the weight repack (if the weights changed) on the side stream, ordered after everything already enqueued on
+// `st` (the previous Adam update); repack_join makes `st` wait for it.  Between the two calls the caller enqueues work
+// that does not read the packed weights (rank pooling).
+int repack_fork_bf16(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  static const bool off = getenv("GEECO_NO_OVERLAP") != nullptr;
+  if (!bp || !c->weights_dirty || !bp->side || !bp->jobs_uploaded || off) return GEECO_OK;   // first step: inline repack
+  CUDA_TRY(cudaEventRecord(bp->ev_fork, st));
+  CUDA_TRY(cudaStreamWaitEvent(bp->side, bp->ev_fork, 0));
+  int rc = repack_weights(c, bp->side);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(bp->ev_join, bp->side));
+  bp->forked = true;
+  return GEECO_OK;
+}
+int repack_join_bf16(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!bp || !bp->forked) return GEECO_OK;
+  CUDA_TRY(cudaStreamWaitEvent(st, bp->ev_join, 0));
+  bp->forked = false;
   return GEECO_OK;
 }
 
