@@ -397,10 +397,16 @@ def kernel_rooflines(eng, dev, peaks, args):
   g2 = (torch.rand((N3, 128, 128, 48), device=dev) - 0.5).to(torch.bfloat16)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, need_dx=False), flush=flush)
   entry('tc_wgrad_kernel<8,512> conv2 wgrad', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
-  # the longest kernel of the step: conv2 data gradient = G2 in, ReLU mask (y1) in, G1 out
+  # the longest kernel of the step: conv2 data gradient = G2 in, 1-bit ReLU mask of y1 in (as in the step), G1 out
+  bits1 = ops.relu_mask_bits(x2)
+  sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_bits=bits1, need_dx=True, need_dw=False),
+               flush=flush)
+  dom = entry('tc_rows_kernel<1,8,MASKBITS> conv2 dgrad', sec, (P2 * 48 + P1 * 32) * 2 + P1 * 4, 2.0 * P2 * 48 * 288,
+              launches=5)
+  # the same with the bf16 activation as the mask (stand-alone C-ABI default): 0.8 GB more to read
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_x=x2, need_dx=True, need_dw=False),
                flush=flush)
-  dom = entry('tc_rows_kernel<1,8> conv2 dgrad', sec, (P2 * 48 + 2 * P1 * 32) * 2, 2.0 * P2 * 48 * 288, launches=5)
+  entry('tc_rows_kernel<1,8,MASK> conv2 dgrad (bf16 mask)', sec, (P2 * 48 + 2 * P1 * 32) * 2, 2.0 * P2 * 48 * 288, launches=5)
   # a tensor-bound layer for the tensor-pipe view: conv5 (128 -> 192, 32x32 -> 16x16)
   x5 = torch.rand((N3, 32, 32, 128), device=dev).to(torch.bfloat16)
   w5 = ((torch.rand((3, 3, 128, 192), device=dev) - 0.5) * 0.1)

@@ -1033,6 +1033,23 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
   }
 }
 
+// one thread per 16-value chunk: bit j = value 2j != 0, bit 8+j = value 2j+1 != 0 (same layout the forward epilogue writes)
+__global__ void relu_mask_bits_kernel(const __nv_bfloat16* __restrict__ y, unsigned short* __restrict__ bits, long long chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(y + i * 16)), b = __ldg(reinterpret_cast<const uint4*>(y + i * 16) + 1);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // "y > 0": post-ReLU values are >= 0, so any set magnitude bit; a (never produced) negative value counts as masked
+      const uint32_t lo = w[j] & 0xffffu, hi = w[j] >> 16;
+      if ((lo & 0x7fffu) && !(lo & 0x8000u)) r |= 1u << j;
+      if ((hi & 0x7fffu) && !(hi & 0x8000u)) r |= 1u << (8 + j);
+    }
+    bits[i] = (unsigned short)r;
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
@@ -1662,6 +1679,14 @@ int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long gr
   return GEECO_OK;
 }
 
+int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long long chunks, cudaStream_t st) {
+  if (chunks <= 0) return GEECO_OK;
+  int blocks = ceil_div(chunks, 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  relu_mask_bits_kernel<<<blocks, 256, 0, st>>>(y, bits, chunks);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
   if (n <= 0) return GEECO_OK;
   int blocks = ceil_div(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;

@@ -90,6 +90,8 @@ struct PackJob {
 // grand_total is the end of the last job rounded up to PACK_CHUNK (total < 2^31 per job)
 constexpr int PACK_CHUNK = 2048;
 int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st);
+// 1-bit ReLU mask (layout of TC_EPI_MASKBITS) of a bf16 tensor: one uint16 per 16 consecutive values
+int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long long chunks, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st);
 // 2-D tensor map over a packed weight matrix [rows_total][Kpad] bf16, box = 64 x box_rows, SWIZZLE_128B

@@ -423,10 +423,36 @@ extern "C" int geeco_conv2d_same_bf16(const void* x, const float* w, const float
                       b ? (relu ? TC_EPI_BIAS_RELU : TC_EPI_BIAS) : TC_EPI_STORE, 0, st);
 }
 
+static int conv2d_bwd_bf16_impl(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x, bool mask_is_bits,
+                                float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes, int32_t N, int32_t H,
+                                int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride, void* stream);
+
 extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x,
                                           float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes,
                                           int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cw, int32_t Cout,
                                           int32_t stride, void* stream) {
+  return conv2d_bwd_bf16_impl(x, w, dy_pre, relu_mask_x, false, dw, db, dx, scratch, scratch_bytes, N, H, W, Cin, Cw, Cout,
+                              stride, stream);
+}
+
+extern "C" int geeco_conv2d_same_bwd_bf16_bits(const void* x, const float* w, const void* dy_pre, const void* relu_mask_bits,
+                                               float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes,
+                                               int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cw, int32_t Cout,
+                                               int32_t stride, void* stream) {
+  if (!relu_mask_bits) { geeco_set_error("conv2d_bwd_bf16_bits: NULL mask"); return GEECO_ERR_INVALID; }
+  if (Cin % 16) { geeco_set_error("conv2d_bwd_bf16_bits: Cin=%d must be a multiple of 16", Cin); return GEECO_ERR_INVALID; }
+  return conv2d_bwd_bf16_impl(x, w, dy_pre, relu_mask_bits, true, dw, db, dx, scratch, scratch_bytes, N, H, W, Cin, Cw, Cout,
+                              stride, stream);
+}
+
+extern "C" int geeco_relu_mask_bits(const void* y, void* bits, int64_t pixels, int32_t C, void* stream) {
+  if (!y || !bits || pixels < 0 || C <= 0 || C % 16) { geeco_set_error("relu_mask_bits: bad arguments"); return GEECO_ERR_INVALID; }
+  return launch_relu_mask_bits((const __nv_bfloat16*)y, (unsigned short*)bits, (long long)pixels * (C / 16), (cudaStream_t)stream);
+}
+
+static int conv2d_bwd_bf16_impl(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x, bool mask_is_bits,
+                                float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes, int32_t N, int32_t H,
+                                int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride, void* stream) {
   if (!x || !w || !dy_pre || !scratch) { geeco_set_error("conv2d_bwd_bf16: NULL tensor"); return GEECO_ERR_INVALID; }
   if (H != W) { geeco_set_error("conv2d_bwd_bf16: square inputs only"); return GEECO_ERR_INVALID; }
   size_t o_fwd, o_dg[4], o_part; long long pf;
@@ -476,12 +502,14 @@ extern "C" int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const v
     for (int i = 1; i < ci; ++i) same_grid = same_grid && dgs[i].Hm == dgs[0].Hm && dgs[i].Wm == dgs[0].Wm;
     if (same_grid) {
       rc = launch_tc_nn_multi(dgs, dmaps, ci, (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
-                              (__nv_bfloat16*)dx, nullptr, relu_mask_x ? TC_EPI_MASK : TC_EPI_STORE, 0, st);
+                              (__nv_bfloat16*)dx, nullptr, relu_mask_x ? (mask_is_bits ? TC_EPI_MASKBITS : TC_EPI_MASK) : TC_EPI_STORE,
+                              0, st);
       if (rc) return rc;
     } else {
       for (int i = 0; i < ci; ++i) {
         rc = launch_tc_nn(dgs[i], dmaps[i], (const __nv_bfloat16*)dy_pre, nullptr, (const __nv_bfloat16*)relu_mask_x,
-                          (__nv_bfloat16*)dx, nullptr, relu_mask_x ? TC_EPI_MASK : TC_EPI_STORE, 0, st);
+                          (__nv_bfloat16*)dx, nullptr, relu_mask_x ? (mask_is_bits ? TC_EPI_MASKBITS : TC_EPI_MASK) : TC_EPI_STORE,
+                          0, st);
         if (rc) return rc;
       }
     }

@@ -96,7 +96,18 @@ def conv2d_same_bf16(x, w, b=None, stride=1, relu=True, want_f32=False):
   return (y, y32) if want_f32 else y
 
 
-def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True, need_dw=True):
+def relu_mask_bits(y):
+  """1-bit ReLU mask of a bf16 activation [..., C] (C % 16 == 0): uint16 per (pixel, 16-channel chunk)."""
+  lib = _lib.load()
+  y = _req_bf16(y, 'y')
+  Cc = y.shape[-1]
+  pixels = y.numel() // Cc
+  bits = torch.empty((pixels, Cc // 16), dtype=torch.int16, device=y.device)
+  _lib.check(lib.geeco_relu_mask_bits(_p(y), _p(bits), pixels, Cc, _stream(y)))
+  return bits
+
+
+def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True, need_dw=True, relu_mask_bits=None):
   """Tensor-core gradients of conv2d_same_bf16: returns (dw fp32, db fp32, dx bf16)."""
   lib = _lib.load()
   x, w, dy_pre = _req_bf16(x, 'x'), _req(w, 'w'), _req_bf16(dy_pre, 'dy_pre')
@@ -107,6 +118,10 @@ def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True,
   dx = torch.empty_like(x) if need_dx else None   # every pixel is written by one parity class
   n = int(lib.geeco_conv2d_bf16_scratch_bytes(N, H, W, Cin, Cout, stride))
   scratch = torch.empty(n, dtype=torch.uint8, device=x.device)
+  if relu_mask_bits is not None:
+    _lib.check(lib.geeco_conv2d_same_bwd_bf16_bits(_p(x), _p(w), _p(dy_pre), _p(relu_mask_bits), _p(dw), _p(db), _p(dx),
+                                                   _p(scratch), n, N, H, W, Cin, Cw, Cout, stride, _stream(x)))
+    return dw, db, dx
   _lib.check(lib.geeco_conv2d_same_bwd_bf16(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx),
                                             _p(scratch), n, N, H, W, Cin, Cw, Cout, stride, _stream(x)))
   return dw, db, dx

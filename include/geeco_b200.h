@@ -152,6 +152,15 @@ int geeco_conv2d_same_bf16(const void* x, const float* w, const float* b, void* 
 int geeco_conv2d_same_bwd_bf16(const void* x, const float* w, const void* dy_pre, const void* relu_mask_x, float* dw,
                                float* db, void* dx, void* scratch, int64_t scratch_bytes, int32_t N, int32_t H,
                                int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride, void* stream);
+/* The model step keeps the ReLU mask of an activation as ONE BIT per element (written by the forward epilogue): uint16
+ * per (pixel, 16-channel chunk), bit j = channel 2j, bit 8+j = channel 2j+1 of the chunk.  geeco_relu_mask_bits builds
+ * that mask from a bf16 activation [pixels][C] (C % 16 == 0); geeco_conv2d_same_bwd_bf16_bits is
+ * geeco_conv2d_same_bwd_bf16 with the mask of x given in that form (same results bit for bit, 16x fewer mask bytes). */
+int geeco_relu_mask_bits(const void* y, void* bits, int64_t pixels, int32_t C, void* stream);
+int geeco_conv2d_same_bwd_bf16_bits(const void* x, const float* w, const void* dy_pre, const void* relu_mask_bits,
+                                    float* dw, float* db, void* dx, void* scratch, int64_t scratch_bytes, int32_t N,
+                                    int32_t H, int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride,
+                                    void* stream);
 
 /* ---- model step ------------------------------------------------------------------------------ */
 /* goal_e2evmc forward (graph.py:321-416) [+ losses when batch->cmd and out->losses are given];

@@ -66,3 +66,24 @@ def test_conv2d_bf16_fwd_bwd_matches_oracle(cuda_device, case):
   if want_dx:
     ref_dx = xt.grad.numpy() * (xb.double().numpy() > 0)
     assert rel_max(dx.float().cpu().numpy(), ref_dx) <= 5e-3, 'dx'
+
+
+@pytest.mark.parametrize("case", [(3, 8, 48, 48, 64, 2), (2, 256, 32, 32, 48, 2)])
+def test_bit_mask_data_gradient_equals_bf16_mask(cuda_device, case):
+  """The model step's 1-bit ReLU mask (uint16 per pixel and 16 channels) gives the same data gradient, bit for bit,
+  as masking with the bf16 activation itself."""
+  from geeco_b200 import ops
+  N, H, Cin, Cw, Cout, stride = case
+  rng = np.random.default_rng(sum(case) + 1)
+  x = torch.from_numpy(np.maximum(rng.uniform(-1, 1, size=(N, H, H, Cin)), 0).astype(np.float32)).to(torch.bfloat16).cuda()
+  w = torch.from_numpy(rng.uniform(-0.2, 0.2, size=(3, 3, Cw, Cout)).astype(np.float32)).cuda()
+  dy = torch.from_numpy(rng.uniform(-1, 1, size=(N, H // stride, H // stride, Cout)).astype(np.float32)).to(torch.bfloat16).cuda()
+  bits = ops.relu_mask_bits(x)
+  xb = x.view(torch.int16).cpu().numpy().reshape(-1, Cin // 16, 8, 2)          # [pixel][chunk][j][lo/hi]
+  want = ((xb[..., 0] != 0) << np.arange(8)).sum(-1) + (((xb[..., 1] != 0) << (8 + np.arange(8))).sum(-1))
+  assert np.array_equal(bits.cpu().numpy().astype(np.uint16), want.astype(np.uint16))
+  _, _, dx_mask = ops.conv2d_same_bwd_bf16(x, w, dy, stride=stride, relu_mask_x=x, need_dw=False)
+  _, _, dx_bits = ops.conv2d_same_bwd_bf16(x, w, dy, stride=stride, relu_mask_bits=bits, need_dw=False)
+  torch.cuda.synchronize()
+  assert torch.equal(dx_mask.view(torch.int16), dx_bits.view(torch.int16))
+  assert float((dx_bits.float().abs() * (x == 0)).max()) == 0.0                    # masked positions are exactly zero
