@@ -588,6 +588,8 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
 // weight-gradient kernel
 //   grid.x = mtile * n_chunks + nchunk ; grid.y = split ; grid.z = group
 // ------------------------------------------------------------------------------------------------
+__device__ int g_wgrad_m128 = 0;       // experiment switch (GEECO_TC_WGRAD_M128=1): keep M = 128 for Cout <= 64
+
 // NPROD producer threads: 512 (one CTA per SM, big stages) or 256 (two CTAs per SM when the stage is small)
 template <int PIECE, int NPROD>
 __global__ void __launch_bounds__(NPROD + 160, NPROD == 256 ? 2 : 1)
@@ -791,8 +793,11 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     }
   } else if (warp < MMA_WARP) {
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int co = mtile * 128 + row;
+    // M = 128: TMEM lane = output channel.  M = 64 (Cout <= 64): the accumulator occupies half of every lane quadrant,
+    // row r sits in lane (r % 16) + 32 * (r / 16)
+    const bool m64 = Cout <= 64 && gridDim.x == n_chunks && !g_wgrad_m128;
+    const int row = m64 ? q * 16 + (lane & 15) : q * 32 + lane;
+    const int co = (m64 && lane >= 16) ? (1 << 30) : mtile * 128 + row;
     // these warps have nothing to do until the whole pixel range is accumulated: poll rarely (a tight spin from
     // 4-8 idle warps took 20 % of the issue slots of an issue-bound kernel)
     while (!mbar_try(smem_u32(tmem_full), 0)) __nanosleep(2000);
@@ -815,8 +820,10 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
     {
       // N <= 256 per instruction: up to two MMAs per 16-pixel step (columns [0,256) and [256, nsub*64))
       const int n_lo = nsub > 4 ? 256 : nsub * 64, n_hi = nsub > 4 ? (nsub - 4) * 64 : 0;
-      const uint32_t idesc_lo = make_idesc_bf16(128, n_lo, 1, 1);
-      const uint32_t idesc_hi = make_idesc_bf16(128, n_hi > 0 ? n_hi : 64, 1, 1);
+      // Cout <= 64: M = 64 (one G sub-tile), half the operand reads and tensor work of the zero-padded M = 128
+      const int Mm = (Cout <= 64 && gridDim.x == n_chunks && !g_wgrad_m128) ? 64 : 128;
+      const uint32_t idesc_lo = make_idesc_bf16(Mm, n_lo, 1, 1);
+      const uint32_t idesc_hi = make_idesc_bf16(Mm, n_hi > 0 ? n_hi : 64, 1, 1);
       const uint64_t dtempl = make_desc_sw128(0, SUB, 1024);
       const uint32_t base16 = smem_u32(st_base) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
       uint32_t s = 0, sphase = 0;
@@ -1589,6 +1596,14 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
   const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_chunk) * SUB + 512;
   const int ones = want_ones ? p.ones_col : -1;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
+  {
+    static int flag_set = -1;
+    if (flag_set < 0) {
+      const int v = getenv("GEECO_TC_WGRAD_M128") ? 1 : 0;
+      CUDA_TRY(cudaMemcpyToSymbol(g_wgrad_m128, &v, sizeof(int)));
+      flag_set = v;
+    }
+  }
 #define WG_LAUNCH(PIECE_, NPROD_)                                                                                   \
   do {                                                                                                              \
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<PIECE_, NPROD_>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
