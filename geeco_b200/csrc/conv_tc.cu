@@ -89,7 +89,8 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
   constexpr bool MASK = EPI == TC_EPI_MASK;
   constexpr bool MBITS = EPI == TC_EPI_MASKBITS;
   const unsigned short* __restrict__ mbits = reinterpret_cast<const unsigned short*>(mask);
-  const int chunks_per_pix = g.Nn >> 4;
+  const int chunks_per_pix = g.Ntot >> 4;
+  const int nsplit = g.nsplit, ntot = g.Ntot;
   constexpr bool GEN = EPI == EPI_GENERIC;
   const int BN = g.Nn;
   const int ncls = cl.ncls;
@@ -106,7 +107,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
     int img = 0, y = 0, x = 0;
     if (valid) decode_pixel(g, m, img, y, x);
     // destination pixel of class (0, 0); a class adds dy0 rows and dx0 columns
-    const long long pix00 = (((long long)group * g.imgs_per_group + img) * g.Hd + y * g.dsy) * g.Wd + x * g.dsx;
+    // a virtual group = (encoder, column tile): images and destination pixels belong to the encoder
+    const int enc = nsplit == 1 ? group : group / nsplit;
+    const int ncol0 = nsplit == 1 ? 0 : (group - enc * nsplit) * BN;
+    const long long pix00 = (((long long)enc * g.imgs_per_group + img) * g.Hd + y * g.dsy) * g.Wd + x * g.dsx;
     const float* bias = bias_s + group * BN;
     for (int c = 0; c < ncls; ++c) {
       const uint32_t my_buf = buf, my_phase = bphase;
@@ -116,9 +120,10 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
       if (!mine) continue;
       const TcCls& kc = cl.c[c];
       const long long pix = pix00 + kc.dy0 * g.Wd + kc.dx0;
-      const long long off = pix * BN;
+      const long long off = pix * ntot + ncol0;
+      const long long bidx = pix * chunks_per_pix + (ncol0 >> 4);          // first mask word of this row's columns
       uint32_t pbits = 0, bits_hold = 0;
-      if (MBITS && valid && c_first < BN) pbits = __ldg(mbits + pix * chunks_per_pix + (c_first >> 4));
+      if (MBITS && valid && c_first < BN) pbits = __ldg(mbits + bidx + (c_first >> 4));
       // the ReLU mask of this warp's first chunk is fetched before the accumulator wait (hides the DRAM latency)
       uint32_t pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       if (MASK && valid && c_first < BN) ldg256_nc(mask + off + c_first, pm);
@@ -146,7 +151,7 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
             }
           } else if (MBITS) {
             uint32_t bits = pbits;
-            if (c0 != c_first) bits = __ldg(mbits + pix * chunks_per_pix + (c0 >> 4));
+            if (c0 != c_first) bits = __ldg(mbits + bidx + (c0 >> 4));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (!((bits >> i) & 1u)) f[2 * i] = 0.f;
@@ -181,12 +186,12 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
               for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[i] + 0x7fff7fffu) & 0x80008000u);
               const uint32_t b16 = ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
               const int ck = c0 >> 4;
-              if (NHALF == 1 && !(chunks_per_pix & 1)) {
+              if (NHALF == 1 && !((chunks_per_pix | (BN >> 4)) & 1)) {
                 // this warp owns every chunk of its rows: two chunks = one aligned 32-bit store (full sectors per warp)
                 if (!(ck & 1)) bits_hold = b16;
-                else *reinterpret_cast<uint32_t*>(bits_out + pix * chunks_per_pix + ck - 1) = bits_hold | (b16 << 16);
+                else *reinterpret_cast<uint32_t*>(bits_out + bidx + ck - 1) = bits_hold | (b16 << 16);
               } else {
-                bits_out[pix * chunks_per_pix + ck] = (unsigned short)b16;
+                bits_out[bidx + ck] = (unsigned short)b16;
               }
             }
           }
@@ -245,7 +250,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
   if (bias_all)
     for (int i = threadIdx.x; i < g.groups * BN; i += blockDim.x)
-      bias_s[i] = bias_all[(long long)(i / BN) * g.bias_group_stride + (i % BN)];
+      bias_s[i] = bias_all[(long long)((i / BN) / g.nsplit) * g.bias_group_stride + ((i / BN) % g.nsplit) * BN + (i % BN)];
   // padding columns (k >= Ktot) are never written by the producers: start from zeros so that whatever
   // they hold later is finite data (multiplied by zero weights)
   if (!A_TMA) zero_smem(a_base, stages * A_STAGE_BYTES);
@@ -419,7 +424,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
         if (A_TMA) {
           const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
           decode_pixel(g, m0, img0, y0, x0);
-          img0 += group * g.imgs_per_group;
+          img0 += (group / g.nsplit) * g.imgs_per_group;
         }
         for (int c = 0; c < ncls; ++c) {
           const TcCls& kc = cl.c[c];
@@ -494,7 +499,7 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
   }
   if (bias_all)
     for (int i = threadIdx.x; i < g.groups * BN; i += blockDim.x)
-      bias_s[i] = bias_all[(long long)(i / BN) * g.bias_group_stride + (i % BN)];
+      bias_s[i] = bias_all[(long long)((i / BN) / g.nsplit) * g.bias_group_stride + ((i / BN) % g.nsplit) * BN + (i % BN)];
   if (warp == W_MMA) tmem_alloc(tmem_ptr_s, (uint32_t)tmem_cols);
   if (warp == W_TMA && lane == 0) {
     for (int c = 0; c < cl.ncls; ++c) tma_prefetch_desc(&maps.m[c]);
@@ -1231,7 +1236,7 @@ TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_grou
   g.Hs = H; g.Ws = W; g.Cs = Cs; g.Hm = Ho; g.Wm = Wo; g.sy = stride; g.sx = stride; g.ntaps = 9;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) { g.dy[ky * 3 + kx] = ky - pt; g.dx[ky * 3 + kx] = kx - pl; }
-  g.Nn = Cout; g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1;
+  g.Nn = Cout; g.nsplit = 1; g.Ntot = Cout; g.Hd = Ho; g.Wd = Wo; g.dsy = 1; g.dsx = 1;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
   finish_k(&g);
@@ -1252,7 +1257,7 @@ TcGeom tc_conv1pair_geom(int H, int W, int Cout, int imgs_per_group, int groups,
   for (int ky = 0; ky < 3; ++ky)
     for (int j = 0; j < 2; ++j) { g.dy[ky * 2 + j] = ky - 1; g.dx[ky * 2 + j] = par == 0 ? j - 1 : j; }
   g.Ktot = 48; g.Kpad = 64; g.Kt = 8; g.a_tma = 0;
-  g.Nn = Cout; g.Hd = H; g.Wd = W; g.dsy = 1; g.dsx = 2; g.dy0 = 0; g.dx0 = par;
+  g.Nn = Cout; g.nsplit = 1; g.Ntot = Cout; g.Hd = H; g.Wd = W; g.dsy = 1; g.dsx = 2; g.dy0 = 0; g.dx0 = par;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cout; g.bias_group_stride = Cout;
   finish_geom(&g);
   return g;
@@ -1295,7 +1300,7 @@ bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, 
   }
   if (!nt) return false;
   g.ntaps = nt;
-  g.Nn = Cin; g.Hd = H; g.Wd = W; g.dsy = stride; g.dsx = stride; g.dy0 = py; g.dx0 = px;
+  g.Nn = Cin; g.nsplit = 1; g.Ntot = Cin; g.Hd = H; g.Wd = W; g.dsy = stride; g.dsx = stride; g.dy0 = py; g.dx0 = px;
   g.imgs_per_group = imgs_per_group; g.groups = groups; g.b_rows_per_group = Cin; g.bias_group_stride = 0;
   finish_geom(&g);
   finish_k(&g);
@@ -1438,7 +1443,7 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
 // strided data-gradient) run as ONE launch; ncls == 1 is the plain forward / single-class case
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
                        const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
-                       int max_ctas, cudaStream_t st, unsigned short* bits_out) {
+                       int max_ctas, cudaStream_t st, unsigned short* bits_out, const __nv_bfloat16* const* wptrs) {
   if (gs[0].bias_in_k) {
     // the packed weights carry the bias in column Ktot and the im2col rows a constant 1.0: nothing left to add
     if (epi == TC_EPI_BIAS_RELU) epi = TC_EPI_RELU;
@@ -1450,7 +1455,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     return GEECO_ERR_INVALID;
   }
   if (ncls < 1 || ncls > 4) { geeco_set_error("tc_nn: ncls=%d outside [1,4]", ncls); return GEECO_ERR_INVALID; }
-  const TcGeom& g = gs[0];
+  TcGeom g = gs[0];
   if (g.Nn % 16 || g.Nn < 16 || g.Nn > 256) { geeco_set_error("tc_nn: unsupported N=%d", g.Nn); return GEECO_ERR_INVALID; }
   TcClasses cl;
   memset(&cl, 0, sizeof(cl));
@@ -1475,6 +1480,21 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     return launch_tc_rows(gs, ncls, cl, maps, src, bias, mask, dst, dst_f32, epi, st, bits_out);
   }
   const int tiles_per_group = ceil_div(Mg, BM);
+  // Small layers (conv7, conv8 and their data gradients): fewer 128-row tiles than half the SMs (measured: splitting
+  // conv6's 96 tiles costs more in repeated A tiles than it gains).  Cut N into 64-column tiles,
+  // each a virtual group with its own slice of the packed weights / bias / destination columns: 2-4x the CTAs.
+  static const bool no_nsplit = getenv("GEECO_TC_NO_NSPLIT") != nullptr;
+  if (!no_nsplit && g.a_tma && wptrs && g.Nn >= 128 && g.Nn % 64 == 0 && 2 * tiles_per_group * g.groups <= num_sms() &&
+      g.b_rows_per_group == g.Nn) {
+    const int S = g.Nn / 64;
+    bool ok = true;
+    for (int c = 0; c < ncls && ok; ++c) {
+      ok = wptrs[c] != nullptr &&
+           make_weight_tensor_map(&maps.m[c], wptrs[c], (long long)g.groups * g.Nn, gs[c].Kpad, 64) == GEECO_OK;
+    }
+    if (!ok) return GEECO_ERR_CUDA;
+    g.Ntot = g.Nn; g.nsplit = S; g.Nn = 64; g.groups *= S; g.b_rows_per_group = 64;
+  }
   const int tiles_flat = tiles_per_group * g.groups;
   const int stage_bytes = A_STAGE_BYTES + g.Nn * BK * 2;
   // small-N layers are latency/bandwidth-bound: two CTAs per SM; wide layers: one CTA, deeper ring
@@ -1503,7 +1523,9 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   CUtensorMap amap;
   memset(&amap, 0, sizeof(amap));
   if (g.a_tma) {
-    int rc = make_act_tensor_map(&amap, src, g);
+    TcGeom ga = g;
+    ga.groups = gs[0].groups;               // the source holds the real groups (a column tile is not a new image set)
+    int rc = make_act_tensor_map(&amap, src, ga);
     if (rc) return rc;
     npw = 0;
   }
@@ -1536,9 +1558,10 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
 
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
-                 cudaStream_t st, unsigned short* bits_out) {
+                 cudaStream_t st, unsigned short* bits_out, const __nv_bfloat16* wptr) {
   const CUtensorMap* maps[1] = {wmap};
-  return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st, bits_out);
+  const __nv_bfloat16* wp[1] = {wptr};
+  return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st, bits_out, wptr ? wp : nullptr);
 }
 
 struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols, per_sm; };

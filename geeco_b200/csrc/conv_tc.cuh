@@ -21,7 +21,9 @@ struct TcGeom {
   int wpack;                  // weight packing mode of the forward operand (0 tap-major, 4 pixel pairs; see pack_value)
   int bias_in_k;              // 1: the bias is folded into the GEMM (row-window conv1): packed-weight column Ktot holds the
                               // bias and the im2col rows carry a constant 1.0 there, so the epilogue neither loads nor adds it
-  int Nn;                     // GEMM N (multiple of 16, <= 256)
+  int Nn;                     // GEMM N of one tile (multiple of 16, <= 256)
+  int nsplit, Ntot;           // small layers: the N = Ntot output channels of a group are cut into nsplit column tiles
+                              // of Nn, each a "virtual group" (more CTAs); nsplit == 1, Ntot == Nn otherwise
   int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
   int dsy, dsx, dy0, dx0;
   int imgs_per_group, groups;
@@ -57,10 +59,12 @@ enum { TC_EPI_BIAS_RELU = 0, TC_EPI_MASK = 1, TC_EPI_STORE = 2, TC_EPI_BIAS = 3,
 // fwd / dgrad: dst = epi(A(src) x Wp^T)
 int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* src, const float* bias,
                  const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi, int max_ctas,
-                 cudaStream_t st, unsigned short* bits_out = nullptr);
+                 cudaStream_t st, unsigned short* bits_out = nullptr, const __nv_bfloat16* wptr = nullptr);
+//   wptrs (optional): base of the packed weight matrix behind each wmaps[c]; lets the launcher re-tile N for small layers
 int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int ncls, const __nv_bfloat16* src,
                        const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
-                       int max_ctas, cudaStream_t st, unsigned short* bits_out = nullptr);
+                       int max_ctas, cudaStream_t st, unsigned short* bits_out = nullptr,
+                       const __nv_bfloat16* const* wptrs = nullptr);
 // wgrad: dW[(tap,ci)][co] (+ optional bias gradient) from im2col(src)^T x G, deterministic split reduction.
 //   g describes the FORWARD geometry (rows = output pixels); G is [imgs, Hm, Wm, Cout] bf16.
 //   Cw = channels per tap present in the weight tensor (Cin_real); dW fp32 [ntaps*Cw, Cout] per group.

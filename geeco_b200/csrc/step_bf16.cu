@@ -272,7 +272,7 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
       g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
       int rc = launch_tc_nn(g, &B.fwd_map[0], src, c->theta + c->params[L.p_b[0]].offset, nullptr,
                             (__nv_bfloat16*)L.y, l == 7 ? c->y8_f32 : nullptr, TC_EPI_BIAS_RELU, 0, st,
-                            (unsigned short*)L.mbits);
+                            (unsigned short*)L.mbits, B.w_fwd[0]);
       if (rc) return rc;
     } else {
       for (int e = 0; e < 3; ++e) {
@@ -330,8 +330,10 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
       {
         TcGeom dgs[4];
         const CUtensorMap* dmaps[4];
+        const __nv_bfloat16* dptrs[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int ci = 0; ci < B.n_classes; ++ci) {
           dgs[ci] = B.dg[ci];
+          dptrs[ci] = B.w_dg[ci][e];
           if (!L.grouped) {
             int taps[9];
             tc_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, B.dg[ci].dy0, B.dg[ci].dx0, N, 1, &dgs[ci], taps);
@@ -344,7 +346,8 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
         const bool bits = L.grouped && Lp.mbits != nullptr;
         rc = launch_tc_nn_multi(dgs, dmaps, B.n_classes, gy, nullptr,
                                 bits ? (const __nv_bfloat16*)Lp.mbits : xin + in_off,
-                                (__nv_bfloat16*)Lp.g + in_off, nullptr, bits ? TC_EPI_MASKBITS : TC_EPI_MASK, 0, st);
+                                (__nv_bfloat16*)Lp.g + in_off, nullptr, bits ? TC_EPI_MASKBITS : TC_EPI_MASK, 0, st, nullptr,
+                                L.grouped ? dptrs : nullptr);
         if (rc) return rc;
       }
     }
