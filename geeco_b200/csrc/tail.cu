@@ -106,17 +106,20 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p,
     fc1[(long long)n * d.Fc + j] = s;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < NH; t += blockDim.x) {
+  // heads: one warp per output column (lanes stride over fc1, fixed-order lane reduction), 4 warps take turns
+  for (int t = threadIdx.x >> 5; t < NH; t += blockDim.x >> 5) {
     const float* w; const float* b; int col, width;
     if (t < 3) { w = p.w_cmd_ee; b = p.b_cmd_ee; col = t; width = 3; }
     else if (t < 3 + d.G) { w = p.w_grp; b = p.b_grp; col = t - 3; width = d.G; }
     else if (t < 6 + d.G) { w = p.w_aux_ee; b = p.b_aux_ee; col = t - 3 - d.G; width = 3; }
     else { w = p.w_aux_obj; b = p.b_aux_obj; col = t - 6 - d.G; width = 3; }
-    float s = b[col];
-#pragma unroll 16
-    for (int j = 0; j < d.Fc; ++j) s = fmaf(fc_s[j], __ldg(w + j * width + col), s);
-    out_s[t] = s;
-    heads[(long long)n * NH + t] = s;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int j = lane; j < d.Fc; j += 32) s = fmaf(fc_s[j], __ldg(w + j * width + col), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s += b[col];
+    if (lane == 0) { out_s[t] = s; heads[(long long)n * NH + t] = s; }
   }
   __syncthreads();
   if (with_loss && threadIdx.x == 0) {
