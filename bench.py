@@ -43,7 +43,7 @@ WORKLOAD = ("GEECO-F train step (fwd+bwd+Adam), synthetic 256x256 RGB pick-pad2-
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
   ap.add_argument('--precision', type=str, default=os.environ.get('GEECO_PRECISION', 'bf16'), choices=['bf16', 'fp32'])
@@ -87,7 +87,7 @@ class ClockSampler(object):
   def start(self):
     try:
       self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                    '--format=csv,noheader,nounits', '-lms', '50'], stdout=subprocess.PIPE,
+                                    '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
                                    stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
