@@ -238,9 +238,10 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
   __shared__ float s_mm[2 * 2 * RP_MAX_CLUSTER];
-  // smem: [2][per_units][C] float4
+  // smem: [per_units][C] float4 = the un-normalised dynamic image d.  The goal difference 0.5*(tgt - cur) is NOT staged:
+  // pass 2 recomputes it from cur / tgt (two L2-resident re-reads), which halves the shared memory per CTA and lets
+  // twice as many clusters (samples) run at once (ncu: 14 clusters of 16 x 98 KB were the occupancy limit)
   float4* sd0 = reinterpret_cast<float4*>(smem_raw);
-  float4* sd1 = sd0 + per_units * C;
   const long long n = blockIdx.y;
   const long long lo = (long long)blockIdx.x * per_units;
   long long hi = lo + per_units; if (hi > units) hi = units;
@@ -269,7 +270,6 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
       const float4 c4 = v[K - 1][j];
       float4 dd = f4_axpy(f4_scale(-0.5f, c4), 0.5f, t[j]);
       sd0[(u - lo) * C + j] = acc;
-      sd1[(u - lo) * C + j] = dd;
       f4_minmax(acc, mn0, mx0);
       f4_minmax(dd, mn1, mx1);
       cur[j * 4] = c4.x; cur[j * 4 + 1] = c4.y; cur[j * 4 + 2] = c4.z; cur[j * 4 + 3] = c4.w;
@@ -288,7 +288,10 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
-      const float4 b = f4_norm(sd1[(u - lo) * C + j], mn1, rng1);
+      // same two operations on the same operands as in pass 1: bit-identical difference image
+      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)(K - 1) * img4 + u * C + j);
+      const float4 tj = FrameLoad<InT>::at(tbase, u * C + j);
+      const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, c4), 0.5f, tj), mn1, rng1);
       e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
       e1[j * 4] = b.x; e1[j * 4 + 1] = b.y; e1[j * 4 + 2] = b.z; e1[j * 4 + 3] = b.w;
       if (o0) stg_stream(o0 + u * C + j, a);
@@ -387,9 +390,9 @@ template <typename InT, typename OutT, int CP, int C>
 static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
                         const AlphaTab& al_in, int cluster_hint, cudaStream_t st) {
   long long units = (long long)H * W / 4;
-  int cl = pick_cluster(2ll * H * W * C * 4, cluster_hint);
+  int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
   long long per_units = (units + cl - 1) / cl;
-  size_t smem = (size_t)per_units * C * 16 * 2;
+  size_t smem = (size_t)per_units * C * 16;
   if (smem > RP_SMEM_CAP) {
     geeco_set_error("preprocess: %dx%dx%d needs %zu B of shared memory per CTA at cluster %d", H, W, C, smem, cl);
     return GEECO_ERR_INVALID;
