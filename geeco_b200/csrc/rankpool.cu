@@ -13,6 +13,7 @@
 // 128-bit, read-only, no-L1-allocate; K is a template parameter so all K loads of a position are
 // in flight together.
 #include "common.cuh"
+#include <stdlib.h>
 #include <cooperative_groups.h>
 #include <float.h>
 
@@ -390,6 +391,7 @@ template <typename InT, typename OutT, int CP, int C>
 static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
                         const AlphaTab& al_in, int cluster_hint, cudaStream_t st) {
   long long units = (long long)H * W / 4;
+  if (cluster_hint <= 0) { if (const char* e = getenv("GEECO_PRE_CLUSTER")) cluster_hint = atoi(e); }
   int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
   long long per_units = (units + cl - 1) / cl;
   size_t smem = (size_t)per_units * C * 16;
