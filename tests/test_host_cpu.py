@@ -181,13 +181,20 @@ print('ok', rank)
 '''
 
 
+def _free_port():
+  import socket
+  with socket.socket() as sk:
+    sk.bind(('127.0.0.1', 0))
+    return sk.getsockname()[1]
+
+
 @pytest.mark.timeout(180)
 def test_data_parallel_step_world_size_2_gloo(tmp_path):
   script = os.path.join(str(tmp_path), 'worker.py')
   with open(script, 'w') as fp:
     fp.write(_GLOO_WORKER % {'root': ROOT})
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr',
-         '127.0.0.1', '--master-port', '29541', script]
+         '127.0.0.1', '--master-port', str(_free_port()), script]       # a fixed port can still be in TIME_WAIT
   r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=170)
   assert r.returncode == 0, r.stdout[-3000:]
   assert 'ok 0' in r.stdout and 'ok 1' in r.stdout
