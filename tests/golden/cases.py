@@ -13,6 +13,7 @@ CASES = OrderedDict([
     ('seq_residual', (dict(proc_obs='sequence', proc_tgt='residual', window_size=2), 1, 15, True)),
     ('seq_dyndiff', (dict(proc_obs='sequence', proc_tgt='dyndiff', window_size=2), 1, 16, True)),
     ('vmc_baseline', (dict(window_size=2), 1, 17, False)),
+    ('geecof_rgbd', (dict(proc_obs='dynimg', proc_tgt='dyndiff', img_channels=4), 1, 18, True)),
 ])
 
 GRAD_SAMPLES = 24

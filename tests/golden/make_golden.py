@@ -36,7 +36,7 @@ def run_case(over, N, seed, goal):
   cfg_d = O.make_config(batch_size=N, **over)
   ref_cfg = RP.create_e2evmc_config(cfg_d)
   K = ref_cfg.window_size
-  feats, labels = C.make_inputs(N, K, seed)
+  feats, labels = C.make_inputs(N, K, seed, C=cfg_d['img_channels'])
   P = O.init_params(cfg_d, seed=seed, goal=goal, dtype=torch.float64, bias_scale=C.BIAS_SCALE)
   tf.reset_state()
   for k, v in P.items():

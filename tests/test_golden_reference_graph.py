@@ -28,7 +28,7 @@ def golden():
 def _run_oracle(name):
   over, N, seed, goal = C.CASES[name]
   cfg_d = O.make_config(batch_size=N, **over)
-  feats, labels = C.make_inputs(N, cfg_d['window_size'], seed)
+  feats, labels = C.make_inputs(N, cfg_d['window_size'], seed, C=cfg_d['img_channels'])
   P = O.init_params(cfg_d, seed=seed, goal=goal, dtype=torch.float64, bias_scale=C.BIAS_SCALE)
   leaves = {k: v.clone().requires_grad_(True) for k, v in P.items()}
   f = {k: torch.tensor(v) for k, v in feats.items()}
@@ -68,8 +68,8 @@ def test_oracle_matches_reference_graph(golden, name):
   # losses: cmd_ee, cmd_grp, pos_ee, pos_obj, reg, total
   got = [float(losses[k].detach()) for k in ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss_reg', 'loss')]
   assert np.allclose(got, g('losses'), rtol=TOL, atol=1e-12)
-  assert list(O.gripper_classes(torch.tensor(C.make_inputs(C.CASES[name][1], cfg_d['window_size'], seed)[1]['cmd'])[:, 3])
-              .numpy()) == list(g('classes'))
+  cmd = C.make_inputs(C.CASES[name][1], cfg_d['window_size'], seed, C=cfg_d['img_channels'])[1]['cmd']
+  assert list(O.gripper_classes(torch.tensor(cmd)[:, 3]).numpy()) == list(g('classes'))
   # gradients
   for n in shapes:
     gr = grads[n].ravel()
