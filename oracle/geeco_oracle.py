@@ -10,7 +10,7 @@ TensorFlow's kernels were never executed here.  What pins this file:
     stated there -- SAME padding, LSTMCell gate order / forget bias, loss reductions, L2 term --
     are ours, from TF-1.15's documented behaviour).  The wiring, variable names and creation
     order, loss functions and (through autograd) every gradient are the reference's own code;
-    tests/test_golden_reference_graph.py holds this oracle to them for seven configurations;
+    tests/test_golden_reference_graph.py holds this oracle to them for eight configurations;
   * the closed-form known answers of tests/test_oracle_pins.py;
   * the independent loop-level restatement in oracle/np_restatement.py.
 Residual risk = a TF-1.15 op semantic misread identically in the shim and here.
