@@ -217,17 +217,18 @@ __device__ __forceinline__ void store_unit(OutT* dst, const float* e) {
 
 // One "float4" of frame data (4 consecutive values of the NHWC stream) in either input format.  uint8 records are
 // divided by 255.0f in fp32, as the reference's input pipeline does on the host (src/data/geeco_gym.py:310).
+// `lut` (uint8 only): 256 floats in shared memory, lut[b] = float(b) / 255.0f computed once per CTA with the IEEE
+// division; a lookup per byte replaces ~60 divisions per 4-pixel unit (the uint8 kernel was compute-bound on them).
 template <typename InT> struct FrameLoad;
 template <> struct FrameLoad<float> {
-  static __device__ __forceinline__ float4 at(const float* base, long long i4) {
+  static __device__ __forceinline__ float4 at(const float* base, long long i4, const float*) {
     return ldg_stream(reinterpret_cast<const float4*>(base) + i4);
   }
 };
 template <> struct FrameLoad<unsigned char> {
-  static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4) {
+  static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4, const float* lut) {
     const unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(base) + i4);
-    return make_float4(__fdiv_rn((float)(w & 255u), 255.f), __fdiv_rn((float)((w >> 8) & 255u), 255.f),
-                       __fdiv_rn((float)((w >> 16) & 255u), 255.f), __fdiv_rn((float)(w >> 24), 255.f));
+    return make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
   }
 };
 
@@ -239,6 +240,11 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
   __shared__ float s_mm[2 * 2 * RP_MAX_CLUSTER];
+  __shared__ float s_lut[256];
+  if (sizeof(InT) == 1) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s_lut[b] = __fdiv_rn((float)b, 255.f);
+    __syncthreads();
+  }
   // smem: [per_units][C] float4 = the un-normalised dynamic image d.  The goal difference 0.5*(tgt - cur) is NOT staged:
   // pass 2 recomputes it from cur / tgt (two L2-resident re-reads), which halves the shared memory per CTA and lets
   // twice as many clusters (samples) run at once (ncu: 14 clusters of 16 x 98 KB were the occupancy limit)
@@ -259,9 +265,9 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, k * img4 + u * C + j);
+      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, k * img4 + u * C + j, s_lut);
 #pragma unroll
-    for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j);
+    for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
     float cur[4 * C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
@@ -290,8 +296,8 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     for (int j = 0; j < C; ++j) {
       const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
       // same two operations on the same operands as in pass 1: bit-identical difference image
-      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)(K - 1) * img4 + u * C + j);
-      const float4 tj = FrameLoad<InT>::at(tbase, u * C + j);
+      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)(K - 1) * img4 + u * C + j, s_lut);
+      const float4 tj = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
       const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, c4), 0.5f, tj), mn1, rng1);
       e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
       e1[j * 4] = b.x; e1[j * 4 + 1] = b.y; e1[j * 4 + 2] = b.z; e1[j * 4 + 3] = b.w;
