@@ -1,4 +1,5 @@
-"""Builds geeco_b200/libgeeco_b200.so (CUDA, sm_100a only) in-tree with nvcc."""
+"""Builds geeco_b200/libgeeco_b200.so (CUDA, sm_100a only, nvcc) and geeco_b200/libgeeco_io.so (host data
+formats, g++ + zlib) in-tree."""
 from __future__ import annotations
 
 import os
@@ -58,5 +59,24 @@ def build_library(force=False, verbose=False):
   return LIB
 
 
+IO_SRC = os.path.join(HERE, 'csrc_io', 'geeco_io.cpp')
+IO_LIB = os.path.join(HERE, 'libgeeco_io.so')
+
+
+def build_io_library(force=False):
+  """Compiles the host-side format library (include/geeco_io.h): no CUDA, links zlib."""
+  deps = [IO_SRC, os.path.join(HERE, '..', 'include', 'geeco_io.h')]
+  if not force and os.path.exists(IO_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(IO_LIB) for d in deps):
+    return IO_LIB
+  cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-fPIC', '-shared', '-Wall', '-Wextra', '-o', IO_LIB,
+         IO_SRC, '-lz']
+  r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  if r.returncode:
+    sys.stderr.write(r.stdout)
+    raise RuntimeError('g++ failed on %s' % IO_SRC)
+  return IO_LIB
+
+
 if __name__ == '__main__':
   print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+  print(build_io_library(force='--force' in sys.argv))

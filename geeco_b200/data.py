@@ -95,3 +95,82 @@ def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0,
   features = {'step': step, 'rgb': rgb, 'jnt_state': jnt, 'ee_state': ee, 'obj_state': obj, 'target_rgb': tgt}
   labels = {'cmd': cmd}
   return features, labels
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic datasets on disk, in the recorder's format (src/data/data_recorder.py, PickAndPlaceEncodingV4)
+# ------------------------------------------------------------------------------------------------
+def synthetic_episode(episode_length=EPISODE_LENGTH, height=256, width=256, seed=0, monitored_joints=None):
+  """One episode as the dict `TfrSequenceEncoding.encode` takes (context keys + 'sequence' list of frames), with
+  the frame keys of PickAndPlaceEncodingV4 (geeco_gym.py:105-113).  Pixels are uint8 arrays, stored by the
+  recorder as floats 0..255 (utils/tfrecord.py:75-76)."""
+  from .input_pipeline import ARM_JOINTS, FINGER_JOINTS, MOCAP
+  rng = np.random.default_rng(seed)
+  joints = list(monitored_joints or (ARM_JOINTS + FINGER_JOINTS))
+  context = {
+      'episode_length': int(episode_length), 'img_height': int(height), 'img_width': int(width),
+      'monitored_joints': joints, 'actuated_joints': list(FINGER_JOINTS), 'monitored_mocaps': [MOCAP],
+      'monitored_objects': ['object0:joint'], 'dim_cmd': 4, 'dim_ctrl': 2, 'task_goal': 'pad2',
+      'task_object': 'cube2'}
+  base = rng.integers(0, 256, size=(height, width, 3))
+  frames = []
+  for t in range(episode_length):
+    rgb = np.clip(np.roll(base, shift=(t, 2 * t), axis=(0, 1)) + rng.integers(-24, 25, size=base.shape), 0, 255)
+    frame = {
+        'step': t, 'ts': float(np.float32(0.04 * t)), 'rgb': rgb.astype(np.uint8),
+        'depth': rng.uniform(0.5, 2.0, size=(height, width, 1)).astype(np.float32),
+        'cmd': np.concatenate([rng.uniform(-2.0, 2.0, size=3), [float(rng.integers(-1, 2))]]).astype(np.float32),
+        'ctrl': rng.uniform(-1.0, 1.0, size=2).astype(np.float32),
+        'goal_qpos': rng.uniform(0.3, 1.5, size=7).astype(np.float32),
+        'obj_qpos': rng.uniform(0.3, 1.5, size=7).astype(np.float32),
+        'mocap_qpos-%s' % MOCAP: rng.uniform(0.3, 1.5, size=7).astype(np.float32),
+        'object_qpos-object0:joint': rng.uniform(0.3, 1.5, size=7).astype(np.float32),
+    }
+    for j in joints:
+      frame['joint_qpos-%s' % j] = float(rng.uniform(-np.pi, np.pi))
+      frame['joint_qvel-%s' % j] = float(rng.uniform(-1.0, 1.0))
+    frames.append(frame)
+  data = dict(context)
+  data['sequence'] = frames
+  return data
+
+
+def encoding_keys_v4(data):
+  """(context_keys, frame_keys) of PickAndPlaceEncodingV4.__init__ (geeco_gym.py:102-113) for one episode dict."""
+  context_keys = ['episode_length', 'img_height', 'img_width', 'monitored_joints', 'actuated_joints',
+                  'monitored_mocaps', 'monitored_objects', 'dim_cmd', 'dim_ctrl', 'task_goal', 'task_object']
+  frame_keys = ['step', 'ts', 'rgb', 'depth', 'cmd', 'ctrl', 'goal_qpos', 'obj_qpos']
+  for j in data['monitored_joints']:
+    frame_keys += ['joint_qpos-%s' % j, 'joint_qvel-%s' % j]
+  frame_keys += ['mocap_qpos-%s' % m for m in data['monitored_mocaps']]
+  frame_keys += ['object_qpos-%s' % o for o in data['monitored_objects']]
+  return context_keys, frame_keys
+
+
+def write_synthetic_dataset(dataset_dir, episodes=2, episode_length=EPISODE_LENGTH, height=256, width=256, seed=0,
+                            split_name='default', eval_episodes=1):
+  """Writes a dataset with the directory layout pickplace_input_fn_v4 expects (geeco_gym.py:414-431):
+  meta/meta_info.json, data/<name>.tfrecord.zlib (one episode each), splits/<split>/{train,eval}.txt.
+  Returns the list of episode dicts (train episodes first)."""
+  import json
+  import os
+  from .tfrecord import encode_sequence_example, write_tfrecord
+  os.makedirs(os.path.join(dataset_dir, 'meta'), exist_ok=True)
+  os.makedirs(os.path.join(dataset_dir, 'data'), exist_ok=True)
+  os.makedirs(os.path.join(dataset_dir, 'splits', split_name), exist_ok=True)
+  all_eps, names = [], []
+  for e in range(episodes + eval_episodes):
+    data = synthetic_episode(episode_length, height, width, seed=seed * 1000 + e)
+    ck, fk = encoding_keys_v4(data)
+    name = '%06d.tfrecord.zlib' % e
+    write_tfrecord(os.path.join(dataset_dir, 'data', name), [encode_sequence_example(data, ck, fk)], 'zlib')
+    all_eps.append(data)
+    names.append(name)
+  meta = {k: all_eps[0][k] for k in ('episode_length', 'img_height', 'img_width', 'monitored_joints',
+                                     'actuated_joints', 'monitored_mocaps', 'monitored_objects', 'dim_cmd', 'dim_ctrl')}
+  with open(os.path.join(dataset_dir, 'meta', 'meta_info.json'), 'w') as fp:
+    json.dump(meta, fp)
+  for mode, part in (('train', names[:episodes]), ('eval', names[episodes:]), ('test', names[episodes:])):
+    with open(os.path.join(dataset_dir, 'splits', split_name, '%s.txt' % mode), 'w') as fp:
+      fp.write('\n'.join(part) + '\n')
+  return all_eps

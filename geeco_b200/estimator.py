@@ -11,7 +11,10 @@ mechanics that the caller can observe are kept:
     `model.ckpt-<global_step>` files plus the `checkpoint` header, keeps `keep_checkpoint_max` of them;
   * `evaluate()` returns {'loss' (mean of per-batch losses), 'cmd_ee','pos_ee','pos_obj' (streaming MSE),
     'cmd_grp' (accuracy), 'global_step'} (estimator.py:246-258);
-  * checkpoints store variables under their TF names (GoalVMC/.../kernel, .../kernel/Adam, ...).
+  * checkpoints store variables under their TF names (GoalVMC/.../kernel, .../kernel/Adam, ...), either as
+    one `.npz` per step (default) or as TF V2 bundles `model.ckpt-<step>.index` + `.data-00000-of-00001`
+    (`params['checkpoint_format'] = 'bundle'`, geeco_b200/checkpoint.py); both are restored, so a run directory
+    written by the reference's tf.estimator resumes here.
 """
 from __future__ import annotations
 
@@ -49,10 +52,15 @@ def latest_checkpoint(model_dir):
   if not m:
     return None
   prefix = os.path.join(model_dir, os.path.basename(m.group(1)))
-  return prefix if os.path.exists(prefix + '.npz') else None
+  return prefix if (os.path.exists(prefix + '.npz') or os.path.exists(prefix + '.index')) else None
 
 
-def save_checkpoint(engine, model_dir, keep_max=2):
+_CKPT_FILE = re.compile(r'model\.ckpt-(\d+)(\.npz|\.index|\.meta|\.data-\d{5}-of-\d{5})$')
+
+
+def save_checkpoint(engine, model_dir, keep_max=2, fmt='npz'):
+  if fmt not in ('npz', 'bundle'):
+    raise ValueError("checkpoint_format must be 'npz' or 'bundle', got %r" % (fmt,))
   step = int(engine.global_step)
   name = 'model.ckpt-%d' % step
   arrays = {'global_step': np.array(step, dtype=np.int64)}
@@ -66,12 +74,17 @@ def save_checkpoint(engine, model_dir, keep_max=2):
   # the reference saves the (never written, all-zero) lstm_memory variable as well (graph.py:219,226)
   arrays['GoalVMC/LSTMDecoder/lstm_memory'] = np.zeros((engine.N, 2 * engine.cfg.dim_h_lstm), dtype=np.float32)
   os.makedirs(model_dir, exist_ok=True)
-  np.savez(os.path.join(model_dir, name + '.npz'), **arrays)
-  existing = sorted((int(re.search(r'model\.ckpt-(\d+)\.npz$', f).group(1)) for f in os.listdir(model_dir)
-                     if re.search(r'model\.ckpt-(\d+)\.npz$', f)))
+  if fmt == 'bundle':
+    from .checkpoint import write_bundle
+    write_bundle(os.path.join(model_dir, name), arrays)
+  else:
+    np.savez(os.path.join(model_dir, name + '.npz'), **arrays)
+  files = [(int(m.group(1)), f) for f in os.listdir(model_dir) for m in [_CKPT_FILE.match(f)] if m]
+  existing = sorted({s for s, _ in files})
   if keep_max > 0:
-    for old in existing[:-keep_max]:
-      os.remove(os.path.join(model_dir, 'model.ckpt-%d.npz' % old))
+    for old, f in files:
+      if old in existing[:-keep_max]:
+        os.remove(os.path.join(model_dir, f))
     existing = existing[-keep_max:]
   with open(os.path.join(model_dir, 'checkpoint'), 'w') as fp:
     fp.write('model_checkpoint_path: "%s"\n' % name)
@@ -80,9 +93,30 @@ def save_checkpoint(engine, model_dir, keep_max=2):
   return os.path.join(model_dir, name)
 
 
+class _BundleView(object):
+  """The `name in data` / `data[name]` face of np.load over a TF V2 bundle."""
+
+  def __init__(self, prefix):
+    from .checkpoint import BundleReader
+    self._r = BundleReader(prefix)
+
+  def __contains__(self, name):
+    return self._r.has_tensor(name)
+
+  def __getitem__(self, name):
+    return self._r.get_tensor(name)
+
+  def __enter__(self):
+    return self
+
+  def __exit__(self, *exc):
+    self._r.close()
+
+
 def restore_checkpoint(engine, prefix):
-  """Restores every variable except lstm_memory (predictor.py:87) and, when present, the Adam slots."""
-  with np.load(prefix + '.npz') as data:
+  """Restores every variable except lstm_memory (predictor.py:87) and, when present, the Adam slots; `prefix`
+  names either `<prefix>.npz` or a TF V2 bundle `<prefix>.index` / `.data-*`."""
+  with (np.load(prefix + '.npz') if os.path.exists(prefix + '.npz') else _BundleView(prefix)) as data:
     engine.set_params({n: data[n] for n in engine.param_names()})
     if engine.training and all((n + '/Adam') in data for n in engine.param_names()):
       import torch
@@ -169,6 +203,7 @@ class Estimator(object):
     self._cfg = self.params['e2evmc_config']
     self._batch = int(batch_size or self._cfg.batch_size)
     self._engine = None
+    self._ckpt_format = self.params.get('checkpoint_format', 'npz')
     self.last_train_losses = []
     os.makedirs(model_dir, exist_ok=True)
 
@@ -218,13 +253,13 @@ class Estimator(object):
           resolve(pending)
         pending = (eng.global_step,) + entry
       if rank == 0 and self.config.save_checkpoints_steps and eng.global_step % self.config.save_checkpoints_steps == 0:
-        save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
+        save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max, self._ckpt_format)
       if steps is not None and done >= steps:
         break
     if pending is not None:
       resolve(pending)
     if rank == 0 and self.params.get('save_final_checkpoint', True):
-      save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max)
+      save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max, self._ckpt_format)
     return self
 
   @staticmethod

@@ -1,0 +1,313 @@
+"""Native input pipeline: recorded GEECO-gym episodes -> (features, labels) batches for the train step.
+
+Counterpart of `pickplace_input_fn_v4` (src/data/geeco_gym.py:401-474): the same dataset layout
+(`meta/meta_info.json`, `data/*.tfrecord.zlib`, `splits/<split>/<mode>.txt`), the same stages and the same
+output -- only executed differently.  The reference chains tf.data ops on 4 CPU threads and materialises every
+episode as float32 (78 MB of pixels per 100-frame episode); here
+
+  * a worker pool decodes whole episodes in C++ (libgeeco_io.so: inflate, TFRecord framing + CRC-32C,
+    SequenceExample index, bulk value reads; ctypes releases the GIL so the workers run in parallel),
+  * pixels come back as the recorded uint8 values (`frame_format='uint8'`, 4x fewer bytes over PCIe; the
+    `/= 255.0` of geeco_gym.py:310 then runs inside the rank-pooling kernel and yields bit-identical network
+    input) or as float32 already divided by 255 (`frame_format='float32'`, the reference's exact tensors),
+  * windows of consecutive stream positions are gathered straight into (optionally pinned) batch buffers,
+  * batches are assembled `prefetch_size` ahead by a background thread.
+
+Stage by stage (all file:line into src/data/geeco_gym.py):
+  _parse_v4 :291-316            reshape rgb [L,H,W,3], depth [L,H,W,1]; rgb /= 255; target = last frame
+  _preprocess_states_v4 :318-371  jnt_state / vel_state = the 7 arm joints in the order of :339-345 / :353-359,
+                                grp_state = the two finger joints, ee_state = mocap_qpos-robot0:mocap,
+                                goal_state = goal_qpos, obj_state = obj_qpos
+  _preprocess_targets_v3 :598-612 vel/ee/grp targets = next frame's state (roll by -1), then every sequence
+                                loses its last frame (targets stay): S = L - 1
+  _window_v3 :614-631           num_windows = S - K + 1 windows of K consecutive frames, targets tiled
+  unbatch + _prepare_v4 :373-399  one example per window; labels = values of the window's last frame
+  repeat(num_epochs).batch(batch_size).prefetch(prefetch_size) :470-473
+Train mode shuffles the episode order only (`np.random.shuffle(tfrecord_paths)`, :436-437); windows keep
+their order inside an episode and every file holds one episode, so the stream position of window w of the
+e-th file is g = e * num_windows + w (geeco_b200.data.locate).
+
+Data parallel: with `world > 1` a global batch is `batch_size * world` consecutive stream
+positions and rank r takes rows [r * batch_size, (r+1) * batch_size); each rank decodes only the episodes
+its rows touch.  Incomplete trailing global batches are dropped there (ranks must step together).
+"""
+from __future__ import annotations
+
+import collections
+import concurrent.futures
+import json
+import os
+import queue
+import threading
+
+import numpy as np
+
+from . import _io
+from .tfrecord import SequenceExample, TFRecordFile, window_gather
+
+PickAndPlaceMetaV4 = collections.namedtuple('PickAndPlaceMetaV4', [
+    'episode_length', 'img_height', 'img_width', 'monitored_joints', 'actuated_joints', 'monitored_mocaps',
+    'monitored_objects', 'dim_cmd', 'dim_ctrl'])           # geeco_gym.py:34-49
+
+ARM_JOINTS = ('robot0:shoulder_pan_joint', 'robot0:shoulder_lift_joint', 'robot0:upperarm_roll_joint',
+              'robot0:elbow_flex_joint', 'robot0:forearm_roll_joint', 'robot0:wrist_flex_joint',
+              'robot0:wrist_roll_joint')                     # geeco_gym.py:339-345
+FINGER_JOINTS = ('robot0:l_gripper_finger_joint', 'robot0:r_gripper_finger_joint')   # :366-367
+MOCAP = 'robot0:mocap'                                     # :331
+
+FEATURE_KEYS = ('step', 'ts', 'rgb', 'depth', 'jnt_state', 'vel_state', 'ee_state', 'grp_state', 'goal_state',
+                'obj_state', 'cmd', 'ctrl')                # _prepare_v4 :375-388
+TARGET_KEYS = ('target_rgb', 'target_depth')               # :389-391
+LABEL_KEYS = ('cmd', 'ctrl', 'vel_target', 'ee_target', 'grp_target')   # :392-398
+
+
+def get_meta_v4(dataset_dir):
+  """_get_meta_v4 (geeco_gym.py:283-289)."""
+  with open(os.path.join(dataset_dir, 'meta', 'meta_info.json'), 'r') as fp:
+    return PickAndPlaceMetaV4(**json.load(fp))
+
+
+def collect_tfrecords_v2(data_dir, split_name, mode):
+  """_collect_tfrecords_v2 (geeco_gym.py:780-793): the split file's entries, or every record of the dataset when
+  split_name and mode are None (directory order, as os.listdir returns it)."""
+  record_dir = os.path.join(data_dir, 'data')
+  if split_name is None and mode is None:
+    record_files = [fn for fn in os.listdir(record_dir) if fn.endswith('.tfrecord.zlib')]
+  else:
+    with open(os.path.join(data_dir, 'splits', split_name, '%s.txt' % (mode,))) as fp:
+      record_files = fp.read().split('\n')
+  return [os.path.join(record_dir, fn) for fn in record_files if fn.endswith('.tfrecord.zlib')]
+
+
+def decode_episode(path, meta, fetch_target=True, frame_format='uint8', verify_crc=True, want_depth=True):
+  """One episode file -> dict of per-frame arrays after _parse_v4, _preprocess_states_v4 and
+  _preprocess_targets_v3 (every sequence has S = L - 1 frames; targets are single frames).
+
+  `rgb` is uint8 [S,H,W,3] (`frame_format='uint8'`) or float32 in [0,1]; with 'uint8' a file whose pixel floats
+  are not exact bytes is rejected rather than silently quantised."""
+  if frame_format not in ('uint8', 'float32'):
+    raise ValueError("frame_format must be 'float32' or 'uint8', got %r" % (frame_format,))
+  H, W = int(meta.img_height), int(meta.img_width)
+  with TFRecordFile(path, compression='zlib', verify_crc=verify_crc) as rec:
+    if len(rec) != 1:
+      raise ValueError("%s holds %d records, expected one episode" % (path, len(rec)))
+    addr, n = rec.record_view(0)
+    ex = SequenceExample(address=addr, length=n, keepalive=rec)
+    try:
+      seq = {}
+      seq['step'] = ex.ints('step', per_frame=1)[:, 0]
+      L = seq['step'].shape[0]
+      seq['ts'] = ex.floats('ts', per_frame=1)[:, 0]
+      rgb8, inexact = ex.pixel_bytes('rgb', per_frame=H * W * 3)
+      if rgb8.shape[0] != L:
+        raise ValueError("%s: rgb has %d frames, step has %d" % (path, rgb8.shape[0], L))
+      if frame_format == 'uint8':
+        if inexact:
+          raise ValueError("%s: %d rgb values are not bytes; read it with frame_format='float32'" % (path, inexact))
+        seq['rgb'] = rgb8.reshape(L, H, W, 3)
+      elif inexact == 0:
+        # fp32 division of exact bytes == the reference's `rgb /= 255.0` on the float-decoded pixels
+        seq['rgb'] = rgb8.reshape(L, H, W, 3).astype(np.float32) / np.float32(255.0)
+      else:
+        seq['rgb'] = ex.floats('rgb', per_frame=H * W * 3).reshape(L, H, W, 3) / np.float32(255.0)
+      if want_depth:
+        seq['depth'] = ex.floats('depth', per_frame=H * W).reshape(L, H, W, 1)
+      seq['cmd'] = ex.floats('cmd', per_frame=int(meta.dim_cmd))
+      seq['ctrl'] = ex.floats('ctrl', per_frame=int(meta.dim_ctrl))
+      seq['jnt_state'] = np.stack([ex.floats('joint_qpos-%s' % j, per_frame=1)[:, 0] for j in ARM_JOINTS], axis=1)
+      seq['vel_state'] = np.stack([ex.floats('joint_qvel-%s' % j, per_frame=1)[:, 0] for j in ARM_JOINTS], axis=1)
+      seq['grp_state'] = np.stack([ex.floats('joint_qpos-%s' % j, per_frame=1)[:, 0] for j in FINGER_JOINTS], axis=1)
+      seq['ee_state'] = ex.floats('mocap_qpos-%s' % MOCAP, per_frame=7)
+      seq['goal_state'] = ex.floats('goal_qpos', per_frame=7)
+      seq['obj_state'] = ex.floats('obj_qpos', per_frame=7)
+    finally:
+      ex.close()
+  for k, v in seq.items():
+    if v.shape[0] != L:
+      raise ValueError("%s: feature %s has %d frames, step has %d" % (path, k, v.shape[0], L))
+  out = {}
+  if fetch_target:                                          # _parse_v4 :312-315: the episode's last frame
+    out['target_rgb'] = seq['rgb'][L - 1].copy()
+    if want_depth:
+      out['target_depth'] = seq['depth'][L - 1].copy()
+  for name in ('vel', 'ee', 'grp'):                         # _preprocess_targets_v3 :600-606
+    seq['%s_target' % name] = np.roll(seq['%s_state' % name], shift=-1, axis=0)
+  for k, v in seq.items():                                  # :607-612 drop the last frame
+    out[k] = v[:L - 1]
+  return out
+
+
+def _pinned_empty(shape, dtype):
+  """Page-locked numpy array (the array keeps the torch storage it views alive)."""
+  import torch
+  t = torch.empty(tuple(int(s) for s in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+  return t.numpy()
+
+
+class WindowBatches(object):
+  """Iterable over (features, labels) batches of consecutive window stream positions (see module docstring)."""
+
+  def __init__(self, tfrecord_paths, meta, window_size=4, fetch_target=False, batch_size=1, num_epochs=1,
+               num_threads=4, prefetch_size=4, frame_format='float32', drop_remainder=False, rank=0, world=1,
+               pin_memory=False, verify_crc=True, want_depth=True):
+    if window_size < 1 or window_size > meta.episode_length - 1:
+      raise ValueError("window_size %d does not fit episodes of %d frames" % (window_size, meta.episode_length))
+    if not 0 <= rank < world:
+      raise ValueError("rank %d outside world of %d" % (rank, world))
+    self.paths = list(tfrecord_paths)
+    self.meta = meta
+    self.K = int(window_size)
+    self.fetch_target = bool(fetch_target)
+    self.B = int(batch_size)
+    self.epochs = int(num_epochs)
+    self.threads = max(1, int(num_threads))
+    self.prefetch = max(1, int(prefetch_size))
+    self.frame_format = frame_format
+    self.drop_remainder = bool(drop_remainder) or world > 1
+    self.rank, self.world = int(rank), int(world)
+    self.pin = bool(pin_memory)
+    self.verify_crc = bool(verify_crc)
+    self.want_depth = bool(want_depth)
+    self.nw = meta.episode_length - 1 - self.K + 1          # _window_v3 :616-617
+    self.total = len(self.paths) * self.epochs * self.nw    # windows in the whole stream
+
+  # -- index math ---------------------------------------------------------------------------------
+  def batch_ranges(self):
+    """[(lo, hi)] stream-position ranges of this rank's batches, in order."""
+    G = self.B * self.world
+    out, b = [], 0
+    while b * G < self.total:
+      lo = b * G + self.rank * self.B
+      hi = min(lo + self.B, self.total)
+      if self.drop_remainder and (b + 1) * G > self.total:
+        break
+      if hi > lo:
+        out.append((lo, hi))
+      b += 1
+    return out
+
+  def pieces(self, lo, hi):
+    """[(stream episode index, first window, count)] covering stream positions [lo, hi)."""
+    out = []
+    g = lo
+    while g < hi:
+      e, w = divmod(g, self.nw)
+      n = min(hi - g, self.nw - w)
+      out.append((e, w, n))
+      g += n
+    return out
+
+  def __len__(self):
+    return len(self.batch_ranges())
+
+  # -- assembly -----------------------------------------------------------------------------------
+  def _decode(self, stream_episode):
+    path = self.paths[stream_episode % len(self.paths)]
+    ep = decode_episode(path, self.meta, self.fetch_target, self.frame_format, self.verify_crc, self.want_depth)
+    if ep['step'].shape[0] != self.meta.episode_length - 1:
+      raise ValueError("%s holds %d frames but meta_info.json says episode_length=%d"
+                       % (path, ep['step'].shape[0] + 1, self.meta.episode_length))
+    return ep
+
+  def _alloc(self, shape, dtype):
+    return _pinned_empty(shape, dtype) if self.pin else np.empty(shape, dtype=dtype)
+
+  def _assemble(self, lo, hi, episodes):
+    n = hi - lo
+    feats, labels = {}, {}
+    at = 0
+    for e, w0, cnt in self.pieces(lo, hi):
+      ep = episodes[e]
+      for k in FEATURE_KEYS:
+        if k not in ep:
+          continue
+        if k not in feats:
+          feats[k] = self._alloc((n, self.K) + ep[k].shape[1:], ep[k].dtype)
+        window_gather(ep[k], self.K, w0, cnt, out=feats[k][at:at + cnt])
+      if self.fetch_target:
+        for k in TARGET_KEYS:
+          if k not in ep:
+            continue
+          if k not in feats:
+            feats[k] = self._alloc((n,) + ep[k].shape, ep[k].dtype)
+          feats[k][at:at + cnt] = ep[k]                     # tf.tile over the windows (:624-625)
+      last = slice(w0 + self.K - 1, w0 + self.K - 1 + cnt)  # the window's last frame (_prepare_v4 :393-397)
+      for k in LABEL_KEYS:
+        if k not in labels:
+          labels[k] = np.empty((n,) + ep[k].shape[1:], dtype=ep[k].dtype)
+        labels[k][at:at + cnt] = ep[k][last]
+      at += cnt
+    return feats, labels
+
+  def _produce(self, out_q, stop):
+    try:
+      ranges = self.batch_ranges()
+      need = [[e for e, _, _ in self.pieces(lo, hi)] for lo, hi in ranges]
+      order = sorted({e for es in need for e in es})        # stream episodes this rank reads, ascending
+      with concurrent.futures.ThreadPoolExecutor(self.threads) as pool:
+        pending, nxt = {}, 0
+        for i, ((lo, hi), es) in enumerate(zip(ranges, need)):
+          if stop.is_set():
+            break
+          # submit what this batch needs plus `threads` episodes of lookahead
+          while nxt < len(order) and (order[nxt] <= es[-1] or len(pending) < len(es) + self.threads):
+            pending[order[nxt]] = pool.submit(self._decode, order[nxt])
+            nxt += 1
+          batch = self._assemble(lo, hi, {e: pending[e].result() for e in es})
+          keep_from = need[i + 1][0] if i + 1 < len(need) else None
+          for e in [e for e in pending if keep_from is None or e < keep_from]:
+            del pending[e]                                  # no later batch of this rank reads them
+          out_q.put(batch)
+      out_q.put(None)
+    except BaseException as exc:                            # surfaces in the consumer
+      out_q.put(exc)
+
+  def __iter__(self):
+    out_q = queue.Queue(maxsize=self.prefetch)
+    stop = threading.Event()
+    worker = threading.Thread(target=self._produce, args=(out_q, stop), daemon=True)
+    worker.start()
+    try:
+      while True:
+        item = out_q.get()
+        if item is None:
+          return
+        if isinstance(item, BaseException):
+          raise item
+        yield item
+    finally:
+      stop.set()
+      while worker.is_alive():                              # unblock a producer waiting on a full queue
+        try:
+          out_q.get(timeout=0.05)
+        except queue.Empty:
+          pass
+
+
+def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_target=False, shuffle_buffer=128,
+                          batch_size=1, num_epochs=1, num_threads=4, prefetch_size=4, seed=None,
+                          frame_format='float32', drop_remainder=False, rank=0, world=1, pin_memory=False):
+  """Same signature and defaults as the reference (geeco_gym.py:401-412) plus the execution keywords after
+  `seed`.  `shuffle_buffer` is accepted and unused, as in the reference (its window-level shuffle is commented
+  out, :446-448); `mode == 'train'` shuffles the episode order with numpy's global generator (:436-437), or
+  with `seed` when one is given so that all ranks of a data-parallel job agree on the order."""
+  del shuffle_buffer
+  meta = get_meta_v4(dataset_dir)
+  paths = collect_tfrecords_v2(dataset_dir, split_name, mode)
+  if mode == 'train':
+    (np.random if seed is None else np.random.RandomState(seed)).shuffle(paths)
+  print("[pickplace_input_fn_v4] #tfrecords: %d" % len(paths))
+  return WindowBatches(paths, meta, window_size=window_size, fetch_target=fetch_target, batch_size=batch_size,
+                       num_epochs=num_epochs, num_threads=num_threads, prefetch_size=prefetch_size,
+                       frame_format=frame_format, drop_remainder=drop_remainder, rank=rank, world=world,
+                       pin_memory=pin_memory)
+
+
+def pickplace_input_fn(dataset_dir, split_name, mode, encoding='v4', window_size=4, fetch_target=False,
+                       shuffle_buffer=128, batch_size=1, num_epochs=1, num_threads=4, prefetch_size=4, seed=None,
+                       **execution):
+  """Dispatcher of geeco_gym.py:234-279; only the V4 encoding (the published datasets) is implemented."""
+  if encoding != 'v4':
+    raise NotImplementedError("data encoding %r: only 'v4' is available" % (encoding,))
+  return pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size, fetch_target, shuffle_buffer, batch_size,
+                               num_epochs, num_threads, prefetch_size, seed, **execution)

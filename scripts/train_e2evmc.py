@@ -6,9 +6,12 @@ name, type and default), same run-directory protocol (:213-252: `<ts>-runcmd.jso
 which, when it already exists, overrides the model flags), same epoch loop (:288-291: train -> evaluate ->
 best-k snapshot export, :143-205).
 
-The reference's tf.data/TFRecord input pipeline is outside this build's scope and no
-dataset ships offline: `--dataset_dir synthetic[:<episodes>]` streams synthetic episodes that follow the
-pipeline's layout and index contract (geeco_b200/data.py); any other value is rejected.
+`--dataset_dir <dir>` reads a recorded dataset (meta/meta_info.json, data/*.tfrecord.zlib, splits/<split>/) through
+the native input pipeline (geeco_b200/input_pipeline.py over libgeeco_io.so: same stages as the reference's
+pickplace_input_fn, :266-278; frames travel as the recorded bytes and are divided by 255 on the device; only
+full batches are fed because the engine, like the reference's lstm_memory variable, has a static batch size).
+No dataset ships offline: `--dataset_dir synthetic[:<episodes>]` streams synthetic episodes that follow the
+pipeline's layout and index contract (geeco_b200/data.py) without touching the disk.
 Launch under torchrun for data-parallel training (one process per GPU, NCCL gradient all-reduce).
 """
 import argparse
@@ -66,6 +69,7 @@ _A('--debug', default=False, action='store_true')
 _A('--initial_eval', default=False, action='store_true')
 # --- execution switches of this build (not in the reference)
 _A('--precision', type=str, default='bf16', help='bf16 (tcgen05 tensor cores) | fp32')
+_A('--checkpoint_format', type=str, default='npz', help='npz | bundle (TF V2 .index/.data files)')
 
 _OBSERVATION_FORMAT_TO_CHANNELS = {'rgb': 3, 'rgbd': 4}
 _GOAL_CONDITIONS = ('none', 'target')
@@ -128,6 +132,23 @@ def synthetic_input_fn(spec, config, batch_size, mode, rank=0, world=1):
   return gen
 
 
+def recorded_input_fn(args, config, mode, rank=0, world=1):
+  """pickplace_input_fn over a recorded dataset with the arguments of the reference's call (:266-278)."""
+  from geeco_b200.input_pipeline import pickplace_input_fn
+  epoch = [0]
+
+  def make():
+    epoch[0] += 1
+    # every rank must shuffle the episodes identically: a per-epoch seed replaces numpy's global generator
+    return pickplace_input_fn(
+        dataset_dir=args.dataset_dir, split_name=args.split_name, mode=mode, encoding=args.data_encoding,
+        window_size=config.window_size, fetch_target=(args.goal_condition == 'target'),
+        shuffle_buffer=args.shuffle_buffer, batch_size=config.batch_size, num_epochs=1,
+        num_threads=args.num_threads, prefetch_size=args.prefetch_size, seed=epoch[0] if world > 1 else None,
+        frame_format='uint8', drop_remainder=True, rank=rank, world=world, pin_memory=True)
+  return make
+
+
 def main(args, argv=None):
   from geeco_b200 import parallel
   from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
@@ -135,9 +156,6 @@ def main(args, argv=None):
     raise KeyError(args.goal_condition)
   if args.goal_condition != 'target':
     raise NotImplementedError("--goal_condition none (unconditional e2e_vmc) is not on the CUDA path yet")
-  if not args.dataset_dir.startswith('synthetic'):
-    raise NotImplementedError("only --dataset_dir synthetic[:<episodes>] is available: the TFRecord pipeline "
-                              "of the reference is outside this build's scope and no dataset ships offline")
   import torch
   import torch.distributed as dist
   if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
@@ -163,10 +181,15 @@ def main(args, argv=None):
     if rank == 0:
       save_model_config(e2evmc_config._asdict(), args.model_dir, config_name)
   estimator = Estimator(model_fn=goal_e2evmc_model_fn, model_dir=args.model_dir, config=run_config,
-                        params={'e2evmc_config': e2evmc_config, 'log_steps': args.log_steps, 'debug': args.debug},
+                        params={'e2evmc_config': e2evmc_config, 'log_steps': args.log_steps, 'debug': args.debug,
+                                'checkpoint_format': args.checkpoint_format},
                         precision=args.precision, batch_size=e2evmc_config.batch_size)
-  train_input = synthetic_input_fn(args.dataset_dir, e2evmc_config, e2evmc_config.batch_size, 'train', rank, world)
-  eval_input = synthetic_input_fn(args.dataset_dir, e2evmc_config, e2evmc_config.batch_size, 'eval', rank, world)
+  if args.dataset_dir.startswith('synthetic'):
+    train_input = synthetic_input_fn(args.dataset_dir, e2evmc_config, e2evmc_config.batch_size, 'train', rank, world)
+    eval_input = synthetic_input_fn(args.dataset_dir, e2evmc_config, e2evmc_config.batch_size, 'eval', rank, world)
+  else:
+    train_input = recorded_input_fn(args, e2evmc_config, 'train', rank, world)
+    eval_input = recorded_input_fn(args, e2evmc_config, 'eval', rank, world)
   results = []
   if args.initial_eval:
     results.append(estimator.evaluate(input_fn=eval_input))
