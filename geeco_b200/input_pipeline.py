@@ -10,8 +10,12 @@ episode as float32 (78 MB of pixels per 100-frame episode); here
   * pixels come back as the recorded uint8 values (`frame_format='uint8'`, 4x fewer bytes over PCIe; the
     `/= 255.0` of geeco_gym.py:310 then runs inside the rank-pooling kernel and yields bit-identical network
     input) or as float32 already divided by 255 (`frame_format='float32'`, the reference's exact tensors),
-  * windows of consecutive stream positions are gathered straight into (optionally pinned) batch buffers,
-  * batches are assembled `prefetch_size` ahead by a background thread.
+  * windows of consecutive stream positions are gathered straight into the batch buffers (`pin_memory=True`:
+    page-locked torch tensors that the engine uploads without a staging copy),
+  * batches are assembled `prefetch_size` ahead by a background thread,
+  * `cache_dir` keeps every decoded episode as uncompressed arrays (uint8 pixels: 19.7 MB instead of the 100 MB
+    protobuf per 100-frame episode), so only the first epoch pays for inflating the recorder's float encoding
+    (a single zlib stream per file: ~0.6 s per episode and thread, the format's own limit).
 
 Stage by stage (all file:line into src/data/geeco_gym.py):
   _parse_v4 :291-316            reshape rgb [L,H,W,3], depth [L,H,W,1]; rgb /= 255; target = last frame
@@ -138,10 +142,10 @@ def decode_episode(path, meta, fetch_target=True, frame_format='uint8', verify_c
 
 
 def _pinned_empty(shape, dtype):
-  """Page-locked numpy array (the array keeps the torch storage it views alive)."""
+  """Page-locked torch tensor (torch's caching host allocator keeps a block alive until the asynchronous copies
+  that read it have run, which a bare numpy view of the same memory would not get)."""
   import torch
-  t = torch.empty(tuple(int(s) for s in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
-  return t.numpy()
+  return torch.empty(tuple(int(s) for s in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
 
 
 class WindowBatches(object):
@@ -149,7 +153,7 @@ class WindowBatches(object):
 
   def __init__(self, tfrecord_paths, meta, window_size=4, fetch_target=False, batch_size=1, num_epochs=1,
                num_threads=4, prefetch_size=4, frame_format='float32', drop_remainder=False, rank=0, world=1,
-               pin_memory=False, verify_crc=True, want_depth=True):
+               pin_memory=False, verify_crc=True, want_depth=True, cache_dir=None):
     if window_size < 1 or window_size > meta.episode_length - 1:
       raise ValueError("window_size %d does not fit episodes of %d frames" % (window_size, meta.episode_length))
     if not 0 <= rank < world:
@@ -168,6 +172,9 @@ class WindowBatches(object):
     self.pin = bool(pin_memory)
     self.verify_crc = bool(verify_crc)
     self.want_depth = bool(want_depth)
+    self.cache_dir = cache_dir
+    if cache_dir:
+      os.makedirs(cache_dir, exist_ok=True)
     self.nw = meta.episode_length - 1 - self.K + 1          # _window_v3 :616-617
     self.total = len(self.paths) * self.epochs * self.nw    # windows in the whole stream
 
@@ -203,18 +210,43 @@ class WindowBatches(object):
   # -- assembly -----------------------------------------------------------------------------------
   def _decode(self, stream_episode):
     path = self.paths[stream_episode % len(self.paths)]
-    ep = decode_episode(path, self.meta, self.fetch_target, self.frame_format, self.verify_crc, self.want_depth)
+    ep = self._cached(path)
     if ep['step'].shape[0] != self.meta.episode_length - 1:
       raise ValueError("%s holds %d frames but meta_info.json says episode_length=%d"
                        % (path, ep['step'].shape[0] + 1, self.meta.episode_length))
     return ep
 
+  def _cached(self, path):
+    """decode_episode, through the episode cache when one is configured.  A cache entry is keyed by the record's
+    name, size and mtime and by what was decoded; it is written under a temporary name and renamed, so
+    concurrent ranks sharing a cache directory never read a partial file."""
+    args = (self.meta, self.fetch_target, self.frame_format, self.verify_crc, self.want_depth)
+    if not self.cache_dir:
+      return decode_episode(path, *args)
+    st = os.stat(path)
+    key = '%s.%d.%d.%s.t%d.d%d.npz' % (os.path.basename(path), st.st_size, int(st.st_mtime), self.frame_format,
+                                       self.fetch_target, self.want_depth)
+    entry = os.path.join(self.cache_dir, key)
+    if os.path.exists(entry):
+      with np.load(entry) as z:
+        return {k: z[k] for k in z.files}
+    ep = decode_episode(path, *args)
+    tmp = '%s.%d.%d.tmp.npz' % (entry, os.getpid(), threading.get_ident())
+    np.savez(tmp, **ep)
+    os.replace(tmp, entry)
+    return ep
+
   def _alloc(self, shape, dtype):
-    return _pinned_empty(shape, dtype) if self.pin else np.empty(shape, dtype=dtype)
+    if not self.pin:
+      return np.empty(shape, dtype=dtype)
+    t = _pinned_empty(shape, dtype)
+    self._pinned.append(t)
+    return t.numpy()
 
   def _assemble(self, lo, hi, episodes):
     n = hi - lo
     feats, labels = {}, {}
+    self._pinned = []
     at = 0
     for e, w0, cnt in self.pieces(lo, hi):
       ep = episodes[e]
@@ -237,6 +269,9 @@ class WindowBatches(object):
           labels[k] = np.empty((n,) + ep[k].shape[1:], dtype=ep[k].dtype)
         labels[k][at:at + cnt] = ep[k][last]
       at += cnt
+    if self.pin:      # hand out the pinned tensors themselves (features are filled through their numpy views)
+      by_ptr = {t.data_ptr(): t for t in self._pinned}
+      feats = {k: by_ptr[v.ctypes.data] for k, v in feats.items()}
     return feats, labels
 
   def _produce(self, out_q, stop):
@@ -286,7 +321,8 @@ class WindowBatches(object):
 
 def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_target=False, shuffle_buffer=128,
                           batch_size=1, num_epochs=1, num_threads=4, prefetch_size=4, seed=None,
-                          frame_format='float32', drop_remainder=False, rank=0, world=1, pin_memory=False):
+                          frame_format='float32', drop_remainder=False, rank=0, world=1, pin_memory=False,
+                          cache_dir=None, want_depth=True):
   """Same signature and defaults as the reference (geeco_gym.py:401-412) plus the execution keywords after
   `seed`.  `shuffle_buffer` is accepted and unused, as in the reference (its window-level shuffle is commented
   out, :446-448); `mode == 'train'` shuffles the episode order with numpy's global generator (:436-437), or
@@ -300,7 +336,7 @@ def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_ta
   return WindowBatches(paths, meta, window_size=window_size, fetch_target=fetch_target, batch_size=batch_size,
                        num_epochs=num_epochs, num_threads=num_threads, prefetch_size=prefetch_size,
                        frame_format=frame_format, drop_remainder=drop_remainder, rank=rank, world=world,
-                       pin_memory=pin_memory)
+                       pin_memory=pin_memory, cache_dir=cache_dir, want_depth=want_depth)
 
 
 def pickplace_input_fn(dataset_dir, split_name, mode, encoding='v4', window_size=4, fetch_target=False,

@@ -466,3 +466,32 @@ def test_pipeline_errors(dataset, tmp_path):
   # early exit of the consumer does not hang the producer thread
   it = iter(ip.pickplace_input_fn_v4(d, 'default', 'eval', 4, True, batch_size=1, prefetch_size=1))
   next(it); it.close()
+
+
+def test_episode_cache_serves_identical_batches(dataset, tmp_path):
+  d, eps = dataset
+  cache = str(tmp_path / 'cache')
+  kw = dict(window_size=4, fetch_target=True, batch_size=5, frame_format='uint8')
+  plain = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', **kw))
+  first = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', cache_dir=cache, **kw))
+  entries = sorted(os.listdir(cache))
+  assert len(entries) == 2 and all(e.endswith('.uint8.t1.d1.npz') for e in entries)
+  # the second pass must not touch the records: make them unreadable and read again
+  recs = [os.path.join(d, 'data', f) for f in ('000003.tfrecord.zlib', '000004.tfrecord.zlib')]
+  saved = [(p, open(p, 'rb').read(), os.stat(p)) for p in recs]
+  try:
+    for p, raw, st in saved:
+      open(p, 'wb').write(b'x' * len(raw)); os.utime(p, (st.st_atime, st.st_mtime))
+    second = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', cache_dir=cache, **kw))
+  finally:
+    for p, raw, st in saved:
+      open(p, 'wb').write(raw); os.utime(p, (st.st_atime, st.st_mtime))
+  for a, b, c in zip(plain, first, second):
+    for k in a[0]:
+      np.testing.assert_array_equal(a[0][k], b[0][k]); np.testing.assert_array_equal(a[0][k], c[0][k])
+      assert a[0][k].dtype == c[0][k].dtype
+    for k in a[1]:
+      np.testing.assert_array_equal(a[1][k], c[1][k])
+  # a different decode configuration gets its own entries
+  list(ip.pickplace_input_fn_v4(d, 'default', 'eval', cache_dir=cache, window_size=4, fetch_target=True, batch_size=5))
+  assert len(os.listdir(cache)) == 4
