@@ -113,6 +113,20 @@ class _BundleView(object):
     self._r.close()
 
 
+def verify_checkpoint(prefix, config, goal_condition='target'):
+  """Checks, before anything is loaded, that the checkpoint holds the variables of `config`'s graph variant with
+  the right shapes (geeco_b200.graph.variable_table); a checkpoint trained with other switches raises ValueError."""
+  from .graph import check_checkpoint_variables, variable_table
+  if os.path.exists(prefix + '.npz'):
+    with np.load(prefix + '.npz') as data:
+      have = {n: data[n].shape for n, _ in variable_table(config, goal_condition) if n in data}
+  else:
+    from .checkpoint import BundleReader
+    with BundleReader(prefix) as r:
+      have = {n: r.shape(n) for n in r.names()}
+  check_checkpoint_variables(have, config, goal_condition)
+
+
 def restore_checkpoint(engine, prefix):
   """Restores every variable except lstm_memory (predictor.py:87) and, when present, the Adam slots; `prefix`
   names either `<prefix>.npz` or a TF V2 bundle `<prefix>.index` / `.data-*`."""
@@ -216,6 +230,7 @@ class Estimator(object):
       parallel.broadcast_parameters(self._engine)
       ckpt = latest_checkpoint(self.model_dir)
       if ckpt:
+        verify_checkpoint(ckpt, self._cfg)
         restore_checkpoint(self._engine, ckpt)
     return self._engine
 

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import torch
 
-from .estimator import latest_checkpoint, restore_checkpoint
+from .estimator import latest_checkpoint, restore_checkpoint, verify_checkpoint
 from .params import create_e2evmc_config, load_model_config
 
 TOL_FRAME_RANGE = 1e-6   # predictor.py:17
@@ -36,6 +36,7 @@ class GoalE2EVMCPredictor(object):
       raise FileNotFoundError("no checkpoint found in %s" % (model_dir,))
     if prefix.endswith('.npz'):
       prefix = prefix[:-4]
+    verify_checkpoint(prefix, self._cfg)
     restore_checkpoint(self._engine, prefix)
     self._frame_buffer = []
     self._buffer_size = self._cfg.window_size

@@ -335,3 +335,29 @@ def test_estimator_checkpoint_protocol(tmp_path, fmt):
   assert torch.equal(c.view('GoalVMC/LSTMDecoder/fc1/kernel'), a.view('GoalVMC/LSTMDecoder/fc1/kernel')) and torch.equal(c.adam_m, m0)
   with pytest.raises(ValueError, match='checkpoint_format'):
     save_checkpoint(a, md, fmt='hdf5')
+
+
+@pytest.mark.parametrize('fmt', ['npz', 'bundle'])
+def test_verify_checkpoint_names_the_mismatch(tmp_path, fmt):
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.estimator import verify_checkpoint
+  from geeco_b200.graph import variable_table
+  seq = create_e2evmc_config(dict(proc_obs='sequence', proc_tgt='residual'))
+  geecof = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff'))
+  # tiny stand-ins with the right names: shapes are checked too, so use the real ones for a few small variables
+  arrays = {n: np.zeros(s, np.float32) for n, s in variable_table(seq) if int(np.prod(s)) < 20000}
+  prefix = str(tmp_path / 'model.ckpt-1')
+  if fmt == 'bundle':
+    write_bundle(prefix, arrays)
+  else:
+    np.savez(prefix + '.npz', **arrays)
+  with pytest.raises(ValueError, match="no variable 'GoalVMC/ConvEncoder/conv3/kernel'"):
+    verify_checkpoint(prefix, seq)                              # (the large kernels were left out above)
+  full = {n: np.zeros(s, np.float32) for n, s in variable_table(seq)}
+  if fmt == 'bundle':
+    write_bundle(prefix, full)
+  else:
+    np.savez(prefix + '.npz', **full)
+  verify_checkpoint(prefix, seq)
+  with pytest.raises(ValueError, match='DynBuffEncoder'):
+    verify_checkpoint(prefix, geecof)

@@ -5,6 +5,7 @@ strides, variable names / shapes / creation order, concat order of the state vec
 feeds which slot, zero LSTM state, loss assembly (lambda_aux, L2 term over every variable), class
 shift of the gripper label, and the full backward pass (per-variable gradient norm, sum, samples).
 """
+import ast
 import os
 
 import numpy as np
@@ -86,3 +87,36 @@ def test_fixture_covers_every_variable_of_geecof(golden):
   assert len(names) == 60
   total = sum(int(np.prod(eval(s))) for s in golden['geecof_n2::var_shapes'])
   assert total == 7552796                      # SURVEY 8c pin: GEECO-F parameter count
+
+
+def test_variable_tables_match_the_reference_graph():
+  """geeco_b200.graph.variable_table reproduces names, shapes and creation order of the variables that the
+  reference's graph.py created in every golden configuration (all switch values, both graph functions)."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.graph import check_checkpoint_variables, lstm_input_width, variable_table
+  from tests.golden import cases as C
+  with np.load(os.path.join(os.path.dirname(__file__), 'golden', 'geeco_graph_golden.npz'), allow_pickle=True) as z:
+    for name, (over, _, _, goal) in C.CASES.items():
+      cfg = create_e2evmc_config(dict(over))
+      table = variable_table(cfg, 'target' if goal else 'none')
+      assert [n for n, _ in table] == [str(n) for n in z[name + '::var_names']], name
+      assert [tuple(s) for _, s in table] == [ast.literal_eval(str(s)) for s in z[name + '::var_shapes']], name
+      width = dict(table)[('GoalVMC' if goal else 'VMC') + '/LSTMDecoder/lstm_cell/kernel'][0] - cfg.dim_h_lstm
+      assert width == lstm_input_width(cfg, 'target' if goal else 'none')
+  geecof = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff'))
+  assert sum(int(np.prod(s)) for _, s in variable_table(geecof)) == 7552796          # SURVEY 8c pin (10)
+  stored = {n: s for n, s in variable_table(create_e2evmc_config(dict(proc_obs='sequence', proc_tgt='constant')))}
+  with pytest.raises(ValueError, match='DynBuffEncoder'):                           # another model's checkpoint
+    check_checkpoint_variables(stored, geecof)
+  check_checkpoint_variables(dict(variable_table(geecof)), geecof)
+  wide = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff', dim_h_lstm=64))
+  with pytest.raises(ValueError, match='shape'):
+    check_checkpoint_variables(dict(variable_table(geecof)), wide)
+  vel = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff', control_mode='velocity'))
+  names = [n for n, _ in variable_table(vel)]
+  assert names[-10:-4] == ['GoalVMC/LSTMDecoder/pred_cmd_vel/kernel', 'GoalVMC/LSTMDecoder/pred_cmd_vel/bias',
+                           'GoalVMC/LSTMDecoder/pred_cmd_ee/kernel', 'GoalVMC/LSTMDecoder/pred_cmd_ee/bias',
+                           'GoalVMC/LSTMDecoder/pred_cmd_grp/kernel', 'GoalVMC/LSTMDecoder/pred_cmd_grp/bias']
+  for bad in (dict(control_mode='torque'), dict(proc_tgt='foo'), dict(proc_obs='bar')):
+    with pytest.raises(ValueError):
+      variable_table(create_e2evmc_config(bad))
