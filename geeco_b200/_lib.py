@@ -69,6 +69,9 @@ SYMBOLS = {
     'geeco_conv2d_same_bwd_bf16': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     'geeco_relu_mask_bits': (C.c_int, [_P, _P, _I64, _I32, _P]),
     'geeco_conv2d_same_bwd_bf16_bits': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    'geeco_lstm_seq_scratch_floats': (_I64, [_I32, _I32, _I32, _I32]),
+    'geeco_lstm_seq_fwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
+    'geeco_lstm_seq_bwd': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
     'geeco_forward': (C.c_int, [_P, C.POINTER(GeecoBatch), C.POINTER(GeecoOutputs), _P]),
     'geeco_train_step': (C.c_int, [_P, C.POINTER(GeecoBatch), C.POINTER(GeecoOutputs), _F, _P]),
     'geeco_step_forward': (C.c_int, [_P, C.POINTER(GeecoBatch), C.POINTER(GeecoOutputs), _P]),

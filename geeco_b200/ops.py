@@ -125,3 +125,53 @@ def conv2d_same_bwd_bf16(x, w, dy_pre, stride=1, relu_mask_x=None, need_dx=True,
   _lib.check(lib.geeco_conv2d_same_bwd_bf16(_p(x), _p(w), _p(dy_pre), _p(relu_mask_x), _p(dw), _p(db), _p(dx),
                                             _p(scratch), n, N, H, W, Cin, Cw, Cout, stride, _stream(x)))
   return dw, db, dx
+
+
+def _lstm_scratch(lib, N, K, xdim, Hl, device):
+  n = int(lib.geeco_lstm_seq_scratch_floats(N, K, xdim, Hl))
+  if n < 0:
+    _lib.check(_lib.GEECO_ERR_INVALID)
+  buf = torch.empty(n + 64, dtype=torch.float32, device=device)
+  off = (-buf.data_ptr() // 4) % 64                      # 256-byte aligned start
+  return buf[off:off + n], n
+
+
+def lstm_sequence(feat_list, kernel, bias):
+  """The LSTM recurrence of lstm_decoder (graph.py:212-225) over a list of K feature tensors [N, xdim] (or one
+  tensor [K, N, xdim]) from the zero state.  Returns (outputs[-1] [N,Hl], state [N,2*Hl] = [c | m], saved) where
+  `saved` feeds lstm_sequence_bwd."""
+  lib = _lib.load()
+  x = feat_list if torch.is_tensor(feat_list) else torch.stack(list(feat_list), dim=0)
+  x, kernel, bias = _req(x.contiguous(), 'feat_list'), _req(kernel, 'kernel'), _req(bias, 'bias')
+  if x.dim() != 3:
+    raise ValueError("feat_list must be K tensors [N, xdim]")
+  K, N, xdim = x.shape
+  Hl = kernel.shape[1] // 4
+  if tuple(kernel.shape) != (xdim + Hl, 4 * Hl) or tuple(bias.shape) != (4 * Hl,):
+    raise ValueError("kernel must be [xdim + Hl, 4*Hl] and bias [4*Hl]; got %s, %s for xdim=%d"
+                     % (tuple(kernel.shape), tuple(bias.shape), xdim))
+  gates = torch.empty((K, N, 4 * Hl), dtype=torch.float32, device=x.device)
+  c = torch.empty((K, N, Hl), dtype=torch.float32, device=x.device)
+  m = torch.empty((K, N, Hl), dtype=torch.float32, device=x.device)
+  scratch, n = _lstm_scratch(lib, N, K, xdim, Hl, x.device)
+  _lib.check(lib.geeco_lstm_seq_fwd(_p(x), _p(kernel), _p(bias), _p(gates), _p(c), _p(m), _p(scratch), n, N, K, xdim, Hl,
+                                    _stream(x)))
+  return m[K - 1], torch.cat([c[K - 1], m[K - 1]], dim=1), (x, kernel, gates, c, m)
+
+
+def lstm_sequence_bwd(saved, dm_last, need_dx=True):
+  """Back-propagation through time of lstm_sequence: dL/d(outputs[-1]) [N,Hl] -> (dkernel, dbias, dx [K,N,xdim])."""
+  lib = _lib.load()
+  x, kernel, gates, c, m = saved
+  dm_last = _req(dm_last.contiguous(), 'dm_last')
+  K, N, xdim = x.shape
+  Hl = kernel.shape[1] // 4
+  if tuple(dm_last.shape) != (N, Hl):
+    raise ValueError("dm_last must be [N, Hl]")
+  dkernel = torch.empty_like(kernel)
+  dbias = torch.empty(4 * Hl, dtype=torch.float32, device=x.device)
+  dx = torch.empty_like(x) if need_dx else None
+  scratch, n = _lstm_scratch(lib, N, K, xdim, Hl, x.device)
+  _lib.check(lib.geeco_lstm_seq_bwd(_p(x), _p(kernel), _p(gates), _p(c), _p(m), _p(dm_last), _p(dkernel), _p(dbias),
+                                    _p(dx), _p(scratch), n, N, K, xdim, Hl, _stream(x)))
+  return dkernel, dbias, dx

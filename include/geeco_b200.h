@@ -162,6 +162,21 @@ int geeco_conv2d_same_bwd_bf16_bits(const void* x, const float* w, const void* d
                                     int32_t H, int32_t W, int32_t Cin, int32_t Cw, int32_t Cout, int32_t stride,
                                     void* stream);
 
+/* LSTMCell over K steps from the zero state, and its back-propagation through time: the recurrence of `lstm_decoder`
+ * (src/models/e2evmc/graph.py:212-225) for the graphs that feed one feature vector per frame (`--proc_obs sequence`,
+ * :360-385, and the unconditional e2e_vmc, :304-313).  fp32.  x [K][N][xdim] (feat_list, xdim % 4 == 0), kernel
+ * [xdim+Hl][4*Hl] with gate order i, j, f, o and forget_bias 1, bias [4*Hl]; outputs gates [K][N][4*Hl] (kept for the
+ * backward), c and m [K][N][Hl]; m[K-1] is `outputs[-1]`, [c[K-1] | m[K-1]] the final state.  The backward takes
+ * dm_last = dL/d(outputs[-1]) [N][Hl] and returns d(kernel), d(bias) and (optional) dx [K][N][xdim].  Both need the
+ * same 256-byte aligned scratch of geeco_lstm_seq_scratch_floats floats; deterministic (fixed-order split sums). */
+int64_t geeco_lstm_seq_scratch_floats(int32_t N, int32_t K, int32_t xdim, int32_t Hl);
+int geeco_lstm_seq_fwd(const float* x, const float* kernel, const float* bias, float* gates, float* c, float* m,
+                       float* scratch, int64_t scratch_floats, int32_t N, int32_t K, int32_t xdim, int32_t Hl,
+                       void* stream);
+int geeco_lstm_seq_bwd(const float* x, const float* kernel, const float* gates, const float* c, const float* m,
+                       const float* dm_last, float* dkernel, float* dbias, float* dx, float* scratch,
+                       int64_t scratch_floats, int32_t N, int32_t K, int32_t xdim, int32_t Hl, void* stream);
+
 /* ---- model step ------------------------------------------------------------------------------ */
 /* goal_e2evmc forward (graph.py:321-416) [+ losses when batch->cmd and out->losses are given];
  * the predictor hook (predictor.py:148-190) and EVAL mode (estimator.py:246-258) use this. */

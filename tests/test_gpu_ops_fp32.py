@@ -116,3 +116,33 @@ def test_conv2d_same_padding_index_map(cuda_device):
         if 0 <= ky < 3 and 0 <= kx < 3:
           exp[oy, ox] = 1.0 + ky * 3 + kx
     assert np.array_equal(y, exp), (iy, ix, y, exp)
+
+
+@pytest.mark.parametrize('N,K,xdim,Hl', [(3, 1, 1052, 128), (5, 4, 2076, 128), (2, 3, 8, 8), (70, 2, 1052, 64)])
+def test_lstm_sequence_forward_and_bptt(cuda_device, N, K, xdim, Hl):
+  """K-step LSTM recurrence (graph.py:212-225, `--proc_obs sequence` / e2e_vmc) against the oracle's lstm_cell chain
+  and its autograd gradients in float64."""
+  from geeco_b200 import ops
+  g = torch.Generator().manual_seed(100 * N + K)
+  x = torch.randn(K, N, xdim, generator=g, dtype=torch.float64) * 0.5
+  lim = (6.0 / (xdim + Hl + 4 * Hl)) ** 0.5
+  kernel = ((torch.rand(xdim + Hl, 4 * Hl, generator=g, dtype=torch.float64) * 2 - 1) * lim * 3).requires_grad_(True)
+  bias = (torch.randn(4 * Hl, generator=g, dtype=torch.float64) * 0.1).requires_grad_(True)
+  r = torch.randn(N, Hl, generator=g, dtype=torch.float64)
+  xr = x.clone().requires_grad_(True)
+  state = torch.zeros(N, 2 * Hl, dtype=torch.float64)
+  for t in range(K):
+    out, state = O.lstm_cell(xr[t], state, kernel, bias)
+  (out * r).sum().backward()
+  dev = lambda t: t.detach().float().to(cuda_device).contiguous()
+  m_last, st, saved = ops.lstm_sequence([dev(x[t]) for t in range(K)], dev(kernel), dev(bias))
+  assert rel_max(m_last.cpu().double(), out.detach()) <= 1e-5
+  assert rel_max(st.cpu().double(), state.detach()) <= 1e-5
+  dk, db, dx = ops.lstm_sequence_bwd(saved, dev(r))
+  assert rel_max(dk.cpu().double(), kernel.grad) <= 1e-4
+  assert rel_max(db.cpu().double(), bias.grad) <= 1e-4
+  assert rel_max(dx.cpu().double(), xr.grad) <= 1e-4
+  dk2, db2, none = ops.lstm_sequence_bwd(saved, dev(r), need_dx=False)      # deterministic, dx optional
+  assert none is None and torch.equal(dk2, dk) and torch.equal(db2, db)
+  with pytest.raises(ValueError):
+    ops.lstm_sequence(dev(x)[:, :, :xdim - 1].contiguous(), dev(kernel), dev(bias))

@@ -128,6 +128,11 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
   c.img_channels = 5
   with pytest.raises(ValueError):
     _lib.check(lib.geeco_query_sizes(ctypes.byref(c), ctypes.byref(s)))
+  # K-step LSTM op: scratch planning is host arithmetic; unsupported shapes answer -1 with a message
+  need = lib.geeco_lstm_seq_scratch_floats(64, 4, 2076, 128)
+  assert need >= 4 * 64 * (2076 + 128) + 4 * 64 * 512 and need % 64 == 0
+  assert lib.geeco_lstm_seq_scratch_floats(64, 4, 2075, 128) == -1 and 'multiple of 4' in _lib.last_error()
+  assert lib.geeco_lstm_seq_scratch_floats(64, 0, 2076, 128) == -1
 
 
 def test_product_fails_loudly_without_gpu():
