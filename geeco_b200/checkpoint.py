@@ -37,7 +37,7 @@ class BundleReader(object):
     for i in range(int(self._lib.geeco_bundle_num_tensors(self._h))):
       p, n = C.c_void_p(), C.c_uint64()
       _io.check(self._lib.geeco_bundle_name(self._h, i, C.byref(p), C.byref(n)))
-      out.append(C.string_at(p.value, n.value).decode('utf-8'))
+      out.append(C.string_at(p.value, n.value).decode('utf-8', 'replace'))
     return out
 
   def _info(self, name):

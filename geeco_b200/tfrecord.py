@@ -7,7 +7,7 @@ Reference:
   * reader: `tf.data.TFRecordDataset(compression_type='ZLIB')` + `tf.parse_single_sequence_example`
     (src/data/geeco_gym.py:298-301, :443-446).
 
-`read_episode` is the native path (C++: inflate, framing + CRC-32C, protobuf index, bulk value readers);
+`TFRecordFile` + `SequenceExample` are the native path (used by input_pipeline.decode_episode ; C++: inflate, framing + CRC-32C, protobuf index, bulk value readers);
 `encode_sequence_example` / `write_tfrecord` serialise the same format so recorded data can be produced without
 TensorFlow (and so the tests have episodes to read).
 """
@@ -162,7 +162,7 @@ class SequenceExample(object):
     for i in range(int(self._lib.geeco_seqex_num_keys(self._h, which))):
       p, n = C.c_void_p(), C.c_uint64()
       _io.check(self._lib.geeco_seqex_key(self._h, which, i, C.byref(p), C.byref(n)))
-      out.append(C.string_at(p.value, n.value).decode('utf-8'))
+      out.append(C.string_at(p.value, n.value).decode('utf-8', 'replace'))
     return out
 
   def info(self, name, which=_io.SEQUENCE):
