@@ -183,6 +183,12 @@ def decode_observation(features, config):
   return out
 
 
+def e2evmc_model_fn(features, labels, mode, params):
+  """model_fn of the unconditional controller (estimator.py:14-141), imported by train_e2evmc.py:14 next to
+  goal_e2evmc_model_fn.  `e2e_vmc` is not on the CUDA path yet: calling it raises, no fallback."""
+  raise NotImplementedError("e2evmc_model_fn (--goal_condition none) is not on the CUDA path yet")
+
+
 def goal_e2evmc_model_fn(features, labels, mode, params):
   """Eager counterpart of estimator.py:144-279.  `params`: {'e2evmc_config', 'log_steps', 'debug'} plus the
   optional execution keys 'precision' ('bf16' | 'fp32') and 'engine' (reuse an existing Engine)."""

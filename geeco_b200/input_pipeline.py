@@ -83,6 +83,45 @@ def collect_tfrecords_v2(data_dir, split_name, mode):
   return [os.path.join(record_dir, fn) for fn in record_files if fn.endswith('.tfrecord.zlib')]
 
 
+def _load_rgbd(rgb_path, depth_path):
+  from PIL import Image
+  rgb = np.array(Image.open(rgb_path), dtype=np.float32) / 255.0
+  if depth_path is None:
+    return rgb
+  return np.concatenate([rgb, np.expand_dims(np.load(depth_path), axis=-1)], axis=-1)
+
+
+def load_target_frame(dataset_dir, tfrecord_name, load_depth=True):
+  """Target frame of an episode as float32 RGB(-D) in [0,1] (geeco_gym.py:184-198):
+  `images/targets/rgb/<name>.png` (+ `images/targets/depth/<name>.npy`)."""
+  filename = os.path.basename(tfrecord_name).split('.')[0]
+  rgb_path = os.path.join(dataset_dir, 'images', 'targets', 'rgb', filename + '.png')
+  depth_path = os.path.join(dataset_dir, 'images', 'targets', 'depth', filename + '.npy') if load_depth else None
+  frame = _load_rgbd(rgb_path, depth_path)
+  print("Read %s" % filename)
+  return frame
+
+
+def load_keyframes(dataset_dir, tfrecord_name):
+  """All key frames `images/keyframes/{rgb,depth}/<name>*` of an episode as RGB-D tensors, sorted by file name
+  (geeco_gym.py:200-217)."""
+  filename = os.path.basename(tfrecord_name).split('.')[0]
+  rgb_dir = os.path.join(dataset_dir, 'images', 'keyframes', 'rgb')
+  depth_dir = os.path.join(dataset_dir, 'images', 'keyframes', 'depth')
+  rgb_files = sorted(f for f in os.listdir(rgb_dir) if f.startswith(filename))
+  depth_files = sorted(f for f in os.listdir(depth_dir) if f.startswith(filename))
+  return [_load_rgbd(os.path.join(rgb_dir, r), os.path.join(depth_dir, d)) for r, d in zip(rgb_files, depth_files)]
+
+
+def load_target_frames(dataset_dir, tfrecord_name, load_depth=True):
+  """Key frames when `data/key_frames_<id>.json` exists, else the single target frame (geeco_gym.py:168-182)."""
+  import re
+  record_id = re.search(r'\d+', tfrecord_name).group(0)
+  if os.path.exists(os.path.join(dataset_dir, 'data', 'key_frames_%s.json' % (record_id,))):
+    return load_keyframes(dataset_dir, tfrecord_name)
+  return [load_target_frame(dataset_dir, tfrecord_name, load_depth)]
+
+
 def decode_episode(path, meta, fetch_target=True, frame_format='uint8', verify_crc=True, want_depth=True):
   """One episode file -> dict of per-frame arrays after _parse_v4, _preprocess_states_v4 and
   _preprocess_targets_v3 (every sequence has S = L - 1 frames; targets are single frames).

@@ -100,6 +100,17 @@ class GoalE2EVMCPredictor(object):
     self._target_frame = np.copy(tgt_frame[:, :, :self._cfg.img_channels])
 
 
+class E2EVMCPredictor(object):
+  """Unconditional twin of GoalE2EVMCPredictor (src/models/e2evmc/predictor.py:212-379): same constructor, so the
+  controller scripts' `from models.e2evmc.predictor import E2EVMCPredictor, GoalE2EVMCPredictor`
+  (scripts/gym_pickplace.py:43, gym_pushing.py:40) resolves.  The unconditional graph (`e2e_vmc`, graph.py:268-319)
+  is not on the CUDA path yet: constructing one raises NotImplementedError, there is no fallback."""
+
+  def __init__(self, model_dir, checkpoint_name=None, memcap=0.8):
+    raise NotImplementedError("E2EVMCPredictor (--goal_condition none, the unconditional e2e_vmc graph) is not on "
+                              "the CUDA path yet; GoalE2EVMCPredictor (--goal_condition target) is")
+
+
 class BatchedGoalPredictor(object):
   """N environments at once; frame history [N,K,H,W,C] is a device ring (extension, not in the reference).
 

@@ -276,14 +276,53 @@ def test_run_command_file(tmp_path):
 
 
 def test_compat_import_paths():
+  # the import lines of the reference's scripts, verbatim (gym_pickplace.py:41-44, train_e2evmc.py:13-16)
   code = ("import sys; sys.path.insert(0, %r); "
-          "from models.e2evmc.predictor import GoalE2EVMCPredictor; "
-          "from models.e2evmc.estimator import goal_e2evmc_model_fn; "
+          "from data.geeco_gym import load_target_frame; "
+          "from data.geeco_gym import pickplace_input_fn; "
+          "from models.e2evmc.predictor import E2EVMCPredictor, GoalE2EVMCPredictor; "
+          "from models.e2evmc.estimator import e2evmc_model_fn, goal_e2evmc_model_fn; "
+          "from models.e2evmc.utils import save_model_config, load_model_config; "
           "from models.e2evmc.params import create_e2evmc_config; "
           "from models.e2evmc.utils import load_model_config; "
           "from utils.runscript import save_run_command; print('ok')") % os.path.join(ROOT, 'compat')
   r = subprocess.run([sys.executable, '-c', code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   assert r.returncode == 0 and 'ok' in r.stdout, r.stdout
+
+
+def test_unconditional_twins_raise_instead_of_falling_back(tmp_path):
+  from geeco_b200.estimator import e2evmc_model_fn
+  from geeco_b200.predictor import E2EVMCPredictor
+  with pytest.raises(NotImplementedError):
+    E2EVMCPredictor(str(tmp_path))
+  with pytest.raises(NotImplementedError):
+    e2evmc_model_fn({}, {}, 'train', {})
+
+
+def test_target_frame_loaders(tmp_path):
+  """load_target_frame / load_target_frames / load_keyframes of geeco_gym.py:168-217 on a dataset directory."""
+  from PIL import Image
+  from geeco_b200.input_pipeline import load_keyframes, load_target_frame, load_target_frames
+  rng = np.random.default_rng(0)
+  d = str(tmp_path)
+  for sub in ('images/targets/rgb', 'images/targets/depth', 'images/keyframes/rgb', 'images/keyframes/depth', 'data'):
+    os.makedirs(os.path.join(d, sub))
+  rgb = rng.integers(0, 256, size=(8, 6, 3), dtype=np.uint8)
+  depth = rng.uniform(0.5, 2.0, size=(8, 6)).astype(np.float32)
+  Image.fromarray(rgb).save(os.path.join(d, 'images/targets/rgb/000007.png'))
+  np.save(os.path.join(d, 'images/targets/depth/000007.npy'), depth)
+  f = load_target_frame(d, 'some/dir/000007.tfrecord.zlib')
+  assert f.shape == (8, 6, 4) and f.dtype == np.float32
+  assert np.array_equal(f[..., :3], rgb.astype(np.float32) / 255.0) and np.array_equal(f[..., 3], depth)
+  assert load_target_frame(d, '000007.tfrecord.zlib', load_depth=False).shape == (8, 6, 3)
+  assert len(load_target_frames(d, '000007.tfrecord.zlib')) == 1
+  for i in (1, 0):
+    Image.fromarray(np.full((8, 6, 3), 10 * i, np.uint8)).save(os.path.join(d, 'images/keyframes/rgb/000007_%d.png' % i))
+    np.save(os.path.join(d, 'images/keyframes/depth/000007_%d.npy' % i), depth + i)
+  keys = load_keyframes(d, '000007.tfrecord.zlib')
+  assert len(keys) == 2 and keys[0][0, 0, 0] == 0.0 and keys[1][0, 0, 3] == depth[0, 0] + 1
+  open(os.path.join(d, 'data', 'key_frames_000007.json'), 'w').write('{}')
+  assert len(load_target_frames(d, '000007.tfrecord.zlib')) == 2
 
 
 def test_decode_observation_concatenates_depth_behind_rgb():
