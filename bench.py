@@ -16,6 +16,8 @@ LSTM cell -> heads -> losses -> backward -> Adam) on a synthetic batch of 64 win
             and reads the step's losses back to the host
   roofline  the kernel with the largest share of the step, timed alone with CUDA events (L2 flushed between
             repetitions) against the measured HBM copy bandwidth; `kernels` holds the other hot kernels
+  input_pipeline  (N=1) host-side rate of the native episode decoder (libgeeco_io.so) on this box's cores, measured
+            beside cpu_baseline on one synthetic recorded episode; never part of the timed GPU region
 """
 from __future__ import annotations
 
@@ -163,6 +165,40 @@ def time_cpu_reference(batch, steps, warmup):
           'ms_per_step': med * 1e3, 'cpu_model': cpu_model, 'os_cpu_count': os.cpu_count()}
 
 
+def time_input_pipeline(frames=24):
+  """Host-side leg next to cpu_baseline: the native episode decoder (libgeeco_io.so) on this box's host cores.  One
+  synthetic 256x256 episode in the recorder's format (float-encoded pixels, one zlib stream) is written to a
+  scratch directory and decoded to uint8 frames; the rate is per decode thread (episodes decode in parallel).  A
+  failure here never takes the bench line down: it is reported under 'error'."""
+  import shutil
+  import tempfile
+  d = tempfile.mkdtemp(prefix='geeco_bench_ds_')
+  try:
+    from geeco_b200.data import write_synthetic_dataset
+    from geeco_b200.input_pipeline import decode_episode, get_meta_v4
+    write_synthetic_dataset(d, episodes=1, episode_length=frames, eval_episodes=0)
+    meta = get_meta_v4(d)
+    path = os.path.join(d, 'data', '000000.tfrecord.zlib')
+    decode_episode(path, meta, True, 'uint8', want_depth=False)
+    ts = []
+    for _ in range(3):
+      t0 = time.perf_counter()
+      ep = decode_episode(path, meta, True, 'uint8', want_depth=False)
+      ts.append(time.perf_counter() - t0)
+    t = sorted(ts)[1]
+    return {'frames_per_s_per_thread': frames / t, 'ms_per_episode': 1e3 * t, 'episode_frames': frames,
+            'file_mb': os.path.getsize(path) / 1e6, 'protobuf_mb': frames * 256 * 256 * 4 * 4 / 1e6,
+            'decoded': {k: list(v.shape) for k, v in ep.items() if k in ('rgb', 'jnt_state', 'target_rgb')},
+            'host_cores': os.cpu_count(),
+            'sample': 'decode_episode (inflate + CRC-32C + SequenceExample -> uint8 frames, states, targets) of one '
+                      'synthetic %d-frame 256x256 episode, median of 3; pixel noise makes it the worst case for zlib'
+                      % frames}
+  except Exception as e:    # noqa: BLE001
+    return {'error': repr(e)}
+  finally:
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
@@ -304,6 +340,7 @@ def run_ours(args):
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     cpu_baseline = time_cpu_reference(args.cpu_batch, 5, 2)
+  input_pipeline = time_input_pipeline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
   extras = run_extras(eng, dev, peaks, args) if (args.extras and rank == 0 and world == 1) else None
 
   if rank == 0:
@@ -319,7 +356,7 @@ def run_ours(args):
         'step_tflops': value * FLOP_PER_SAMPLE_TRAIN / 1e12,
         'final_loss': final_loss,
         'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roofline, 'kernels': extra,
-        'cpu_baseline': cpu_baseline, 'peaks': peaks, 'extras': extras,
+        'cpu_baseline': cpu_baseline, 'input_pipeline': input_pipeline, 'peaks': peaks, 'extras': extras,
     }
     emit(line)
   if world > 1:
