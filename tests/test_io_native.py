@@ -495,3 +495,73 @@ def test_episode_cache_serves_identical_batches(dataset, tmp_path):
   # a different decode configuration gets its own entries
   list(ip.pickplace_input_fn_v4(d, 'default', 'eval', cache_dir=cache, window_size=4, fetch_target=True, batch_size=5))
   assert len(os.listdir(cache)) == 4
+
+
+def test_recorder_writes_what_the_pipeline_reads(tmp_path):
+  """TfrSequenceRecorder + PickAndPlaceEncodingV4 (data_recorder.py:71-156, geeco_gym.py:54-115) -> decode_episode."""
+  from geeco_b200.data_recorder import PickAndPlaceEncodingV4, TfrSequenceRecorder
+  data = gdata.synthetic_episode(episode_length=7, height=8, width=6, seed=9)
+  meta = ip.PickAndPlaceMetaV4(**{k: data[k] for k in ip.PickAndPlaceMetaV4._fields})
+  enc = PickAndPlaceEncodingV4(meta)
+  assert (enc.context_keys, enc.frame_keys) == gdata.encoding_keys_v4(data)
+  ctx_spec, seq_spec = enc.decode()
+  assert set(seq_spec) == set(enc.frame_keys) and seq_spec['rgb'] == ('float', 8 * 6 * 3) and set(ctx_spec) == set(enc.context_keys)
+  rec = TfrSequenceRecorder(enc, {k: data[k] for k in enc.context_keys}, str(tmp_path), record_name='000042')
+  assert rec.record_path == str(tmp_path / '000042.tfrecord')
+  for frame in data['sequence']:
+    rec.feed(frame)
+  with pytest.raises(ValueError, match='expected data fields'):
+    rec.feed({k: v for k, v in data['sequence'][0].items() if k != 'ts'})
+  with pytest.raises(KeyError):
+    rec.finalize(compression='lz4')
+  path = rec.finalize(compression='zlib')
+  assert path.endswith('000042.tfrecord.zlib')
+  ep = ip.decode_episode(path, meta, fetch_target=True, frame_format='uint8')
+  want = np.stack([f['rgb'] for f in data['sequence']])
+  np.testing.assert_array_equal(ep['rgb'], want[:-1])
+  np.testing.assert_array_equal(ep['target_rgb'], want[-1])
+  np.testing.assert_array_equal(ep['cmd'], np.stack([f['cmd'] for f in data['sequence']])[:-1])
+  with tfr.TFRecordFile(path) as f:                                 # context as recorded
+    s = tfr.SequenceExample(f[0])
+    assert s.strings('task_object') == [b'cube2'] and s.ints('episode_length', _io.CONTEXT).tolist() == [[7]]
+    assert s.strings('monitored_joints') == [j.encode() for j in data['monitored_joints']]
+  plain = TfrSequenceRecorder(enc, {k: data[k] for k in enc.context_keys}, str(tmp_path), record_name='p')
+  for frame in data['sequence']:
+    plain.feed(frame)
+  assert len(tfr.TFRecordFile(plain.finalize())) == 1               # uncompressed .tfrecord
+
+
+def test_batch_ranges_partition_the_stream_property():
+  """Every stream position is read exactly once across ranks (up to the dropped incomplete global batch), pieces
+  never cross an episode, and a rank's ranges follow SURVEY 8e's contiguous-slice rule."""
+  from hypothesis import given, settings, strategies as st
+  Meta = ip.PickAndPlaceMetaV4
+
+  @settings(max_examples=80, deadline=None)
+  @given(st.integers(2, 30), st.integers(1, 6), st.integers(1, 9), st.integers(1, 4), st.integers(0, 5), st.integers(1, 3),
+         st.booleans())
+  def prop(L, K, B, world, files, epochs, drop):
+    if K > L - 1:
+      return
+    meta = Meta(L, 4, 4, [], [], [], [], 4, 2)
+    its = [ip.WindowBatches(['f%d' % i for i in range(files)], meta, window_size=K, batch_size=B, num_epochs=epochs,
+                            drop_remainder=drop, rank=r, world=world) for r in range(world)]
+    nw = L - 1 - K + 1
+    total = files * epochs * nw
+    seen = []
+    for r, it in enumerate(its):
+      for lo, hi in it.batch_ranges():
+        b = lo // (B * world)
+        assert lo == b * B * world + r * B and lo < hi <= lo + B          # rank_slice of global batch b
+        cover = 0
+        for e, w0, cnt in it.pieces(lo, hi):
+          assert 0 <= w0 and cnt >= 1 and w0 + cnt <= nw and e * nw + w0 == lo + cover
+          cover += cnt
+        assert cover == hi - lo
+        seen += list(range(lo, hi))
+    G = B * world
+    kept = total if (world == 1 and not drop) else (total // G) * G
+    assert sorted(seen) == list(range(kept))
+    assert len({len(it) for it in its}) == 1                                # ranks step together
+
+  prop()
