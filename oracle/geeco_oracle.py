@@ -10,7 +10,8 @@ TensorFlow's kernels were never executed here.  What pins this file:
     stated there -- SAME padding, LSTMCell gate order / forget bias, loss reductions, L2 term --
     are ours, from TF-1.15's documented behaviour).  The wiring, variable names and creation
     order, loss functions and (through autograd) every gradient are the reference's own code;
-    tests/test_golden_reference_graph.py holds this oracle to them for eight configurations;
+    tests/test_golden_reference_graph.py holds this oracle to them for eight configurations, plus two
+    `--control_mode velocity` configurations in geeco_graph_golden_velocity.npz (make_golden.py --velocity);
   * the closed-form known answers of tests/test_oracle_pins.py;
   * the independent loop-level restatement in oracle/np_restatement.py.
 Residual risk = a TF-1.15 op semantic misread identically in the shim and here.
@@ -374,6 +375,28 @@ def losses_cartesian(ep, features, labels, params, cfg):
   return out
 
 
+VELOCITY_LOSS_KEYS = ('cmd_vel', 'cmd_ee', 'cmd_grp', 'pos_ee', 'pos_obj')     # _PREDICTION_KEYS, graph.py:421-428
+
+
+def losses_velocity(ep, features, labels, params, cfg):
+  """estimator.py:229-239 for control_mode == 'velocity': targets :230-236, `mse_loss` (graph.py:430-450) = the
+  plain sum of five `tf.losses.mean_squared_error` terms (no lambda_aux), plus the regularisation term."""
+  pred = {'cmd_vel': ep['pred_cmd_vel'], 'cmd_ee': ep['pred_cmd_ee'], 'cmd_grp': ep['pred_cmd_grp'],
+          'pos_ee': ep['pred_aux_ee'], 'pos_obj': ep['pred_aux_obj']}                      # estimator.py:191-197
+  tgt = {'cmd_vel': labels['vel_target'], 'cmd_ee': labels['ee_target'][:, :3], 'cmd_grp': labels['grp_target'],
+         'pos_ee': features['ee_state'][:, -1, :3], 'pos_obj': features['obj_state'][:, -1, :3]}
+  out = OrderedDict()
+  for k in VELOCITY_LOSS_KEYS:
+    out['loss_' + k] = mean_squared_error(pred[k], tgt[k])
+  reg = l2_reg_loss(params, cfg['l2_regularizer'])
+  out['loss_reg'] = reg if reg is not None else torch.zeros((), dtype=pred['cmd_vel'].dtype)
+  total = out['loss_' + VELOCITY_LOSS_KEYS[0]]
+  for k in VELOCITY_LOSS_KEYS[1:]:
+    total = total + out['loss_' + k]
+  out['loss'] = total + out['loss_reg']
+  return out
+
+
 # --------------------------------------------------------------------------
 # parameters: names, shapes, init
 # --------------------------------------------------------------------------
@@ -496,8 +519,11 @@ def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=
   tgt = _to(features['target_rgb'], dt)
   jnt = _to(features['jnt_state'], dt)
   f2 = {'ee_state': _to(features['ee_state'], dt), 'obj_state': _to(features['obj_state'], dt)}
-  l2 = {'cmd': _to(labels['cmd'], dt)}
   net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16)
+  if cfg['control_mode'] == 'velocity':
+    l2 = {k: _to(labels[k], dt) for k in ('vel_target', 'ee_target', 'grp_target')}
+    return losses_velocity(ep, f2, l2, params, cfg), ep
+  l2 = {'cmd': _to(labels['cmd'], dt)}
   losses = losses_cartesian(ep, f2, l2, params, cfg)
   return losses, ep
 

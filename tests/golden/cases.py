@@ -16,6 +16,13 @@ CASES = OrderedDict([
     ('geecof_rgbd', (dict(proc_obs='dynimg', proc_tgt='dyndiff', img_channels=4), 1, 18, True)),
 ])
 
+# --control_mode velocity (graph.py:240-249, estimator.py:190-197, :229-237): its own fixture file
+# (geeco_graph_golden_velocity.npz) so that the cases above keep the bytes they were generated with
+VELOCITY_CASES = OrderedDict([
+    ('geecof_velocity', (dict(proc_obs='dynimg', proc_tgt='dyndiff', control_mode='velocity', l2_regularizer=1e-3), 2, 19, True)),
+    ('seq_constant_velocity', (dict(proc_obs='sequence', proc_tgt='constant', control_mode='velocity', window_size=2), 1, 20, True)),
+])
+
 GRAD_SAMPLES = 24
 BIAS_SCALE = 0.05
 
@@ -35,7 +42,12 @@ def make_inputs(N, K, seed, H=256, W=256, C=3, dj=7):
   }
   cmd = rng.normal(0.0, 0.05, size=(N, 4))
   cmd[:, 3] = rng.integers(-1, 2, size=N).astype(np.float64) + rng.uniform(-0.3, 0.3, size=N)
-  return feats, {'cmd': cmd}
+  labels = {'cmd': cmd}
+  # velocity-mode labels (geeco_gym.py:392-398), drawn after everything else so the inputs above never change
+  labels['vel_target'] = rng.normal(0.0, 0.3, size=(N, dj))
+  labels['ee_target'] = rng.normal(0.0, 0.5, size=(N, 7))
+  labels['grp_target'] = rng.uniform(0.0, 0.05, size=(N, 2))
+  return feats, labels
 
 
 def sample_indices(name, size, seed):

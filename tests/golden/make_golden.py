@@ -49,6 +49,8 @@ def run_case(over, N, seed, goal):
     net, ep = G.goal_e2evmc(f['rgb'], f['jnt_state'], f['target_rgb'], reset, params=ref_cfg)
   else:
     net, ep = G.e2e_vmc(f['rgb'], f['jnt_state'], reset, params=ref_cfg)
+  if ref_cfg.control_mode == 'velocity':
+    return run_velocity_tail(ep, f, labels, ref_cfg, seed)
   predictions = {'cmd_ee': ep['pred_cmd_ee'], 'logits_cmd_grp': ep['logits_cmd_grp'],
                  'pos_ee': ep['pred_aux_ee'], 'pos_obj': ep['pred_aux_obj']}
   # estimator.py:205-239 (cartesian): regularisation term, targets, class shift, loss assembly
@@ -88,7 +90,49 @@ def run_case(over, N, seed, goal):
   return out
 
 
+def run_velocity_tail(ep, f, labels, ref_cfg, seed):
+  """estimator.py:190-197 (predictions), :201-204 (regularisation), :229-239 (targets, mse_loss, total)."""
+  predictions = {'cmd_vel': ep['pred_cmd_vel'], 'cmd_ee': ep['pred_cmd_ee'], 'cmd_grp': ep['pred_cmd_grp'],
+                 'pos_ee': ep['pred_aux_ee'], 'pos_obj': ep['pred_aux_obj']}
+  loss_reg = tf.reduce_sum(tf.get_collection(tf.GraphKeys.REGULARIZATION_LOSSES))
+  targets = {'cmd_vel': torch.tensor(labels['vel_target']), 'cmd_ee': torch.tensor(labels['ee_target'])[:, :3],
+             'cmd_grp': torch.tensor(labels['grp_target']), 'pos_ee': f['ee_state'][:, -1, :3],
+             'pos_obj': f['obj_state'][:, -1, :3]}
+  loss, ep_losses = G.mse_loss(predictions, targets)
+  loss = tf.add(loss, loss_reg)
+  names = [n for n, _ in tf.CREATED]
+  grads = torch.autograd.grad(loss, [tf.VARIABLES[n] for n in names], allow_unused=True)
+  keys = ('cmd_vel', 'cmd_ee', 'cmd_grp', 'pos_ee', 'pos_obj')
+  out = {
+      'var_names': np.array(names), 'var_shapes': np.array([str(s) for _, s in tf.CREATED]),
+      'losses': np.array([float(ep_losses['loss_' + k]) for k in keys] + [float(loss_reg), float(loss)]),
+  }
+  for k in ('pred_cmd_vel', 'pred_cmd_ee', 'pred_cmd_grp', 'pred_aux_ee', 'pred_aux_obj', 'fc1'):
+    out['ep_' + k] = ep[k].detach().numpy()
+  for n, g in zip(names, grads):
+    g = torch.zeros_like(tf.VARIABLES[n]) if g is None else g
+    g = g.detach().numpy().ravel()
+    idx = C.sample_indices(n, g.size, seed)
+    out['grad_stats/' + n] = np.array([np.linalg.norm(g), g.sum()])
+    out['grad_samples/' + n] = g[idx]
+  return out
+
+
+def main_velocity():
+  blob = {}
+  for name, (over, N, seed, goal) in C.VELOCITY_CASES.items():
+    res = run_case(over, N, seed, goal)
+    for k, v in res.items():
+      blob[name + '::' + k] = v
+    print('%-22s loss=%.9f  vars=%d' % (name, res['losses'][-1], len(res['var_names'])))
+  path = os.path.join(HERE, 'geeco_graph_golden_velocity.npz')
+  np.savez_compressed(path, **blob)
+  print('wrote %s (%.1f KiB)' % (path, os.path.getsize(path) / 1024.0))
+
+
 def main():
+  if '--velocity' in sys.argv:       # the velocity cases live in their own fixture file
+    return main_velocity()
   blob = {}
   for name, (over, N, seed, goal) in C.CASES.items():
     res = run_case(over, N, seed, goal)

@@ -120,3 +120,36 @@ def test_variable_tables_match_the_reference_graph():
   for bad in (dict(control_mode='torque'), dict(proc_tgt='foo'), dict(proc_obs='bar')):
     with pytest.raises(ValueError):
       variable_table(create_e2evmc_config(bad))
+
+
+@pytest.mark.parametrize('name', list(C.VELOCITY_CASES))
+def test_oracle_velocity_mode_matches_reference_graph(name):
+  """--control_mode velocity (heads graph.py:240-249, mse_loss :430-450, targets estimator.py:229-237) against the
+  reference graph executed by tests/golden/make_golden.py --velocity."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.graph import variable_table
+  over, N, seed, goal = C.VELOCITY_CASES[name]
+  with np.load(os.path.join(os.path.dirname(GOLDEN), 'geeco_graph_golden_velocity.npz')) as z:
+    g = lambda k: z[name + '::' + k]
+    cfg_d = O.make_config(batch_size=N, **over)
+    feats, labels = C.make_inputs(N, cfg_d['window_size'], seed, C=cfg_d['img_channels'])
+    P = O.init_params(cfg_d, seed=seed, goal=goal, dtype=torch.float64, bias_scale=C.BIAS_SCALE)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    losses, ep = O.forward_losses(leaves, feats, labels, cfg_d)
+    losses['loss'].backward()
+    shapes = O.param_shapes(cfg_d, goal)
+    assert list(g('var_names')) == list(shapes.keys())
+    assert [str(tuple(s)) for s in shapes.values()] == list(g('var_shapes'))
+    table = variable_table(create_e2evmc_config(dict(over)))                 # the product's table agrees too
+    assert [n for n, _ in table] == list(g('var_names')) and [str(tuple(s)) for _, s in table] == list(g('var_shapes'))
+    for k in ('pred_cmd_vel', 'pred_cmd_ee', 'pred_cmd_grp', 'pred_aux_ee', 'pred_aux_obj', 'fc1'):
+      assert rel_max(ep[k].detach().numpy(), g('ep_' + k)) <= TOL, k
+    got = [float(losses['loss_' + k].detach()) for k in O.VELOCITY_LOSS_KEYS] + [float(losses['loss_reg'].detach()),
+                                                                                float(losses['loss'].detach())]
+    assert np.allclose(got, g('losses'), rtol=TOL, atol=1e-12)
+    for n in shapes:
+      gr = (leaves[n].grad if leaves[n].grad is not None else torch.zeros_like(leaves[n])).numpy().ravel()
+      ref_norm, _ = g('grad_stats/' + n)
+      assert abs(np.linalg.norm(gr) - ref_norm) <= TOL * ref_norm + 1e-15, n
+      idx = C.sample_indices(n, gr.size, seed)
+      assert np.abs(gr[idx] - g('grad_samples/' + n)).max() <= TOL * (np.abs(gr).max() + 1e-30), n
