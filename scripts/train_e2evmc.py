@@ -158,18 +158,10 @@ def main(args, argv=None):
     raise KeyError(args.goal_condition)
   if args.goal_condition != 'target':
     raise NotImplementedError("--goal_condition none (unconditional e2e_vmc) is not on the CUDA path yet")
-  import torch
-  import torch.distributed as dist
-  if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
-    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
-    dist.init_process_group('nccl')
-  rank, world = parallel.world_info()
-  os.makedirs(args.model_dir, exist_ok=True)
-  if rank == 0:
-    save_run_command(ARGPARSER, args.model_dir, argv)
-  run_config = RunConfig(save_checkpoints_steps=args.ckpt_steps, keep_checkpoint_max=args.num_last_ckpt)
+  # the model config: an existing run directory overrides the model flags (train_e2evmc.py:229-232)
   config_name = 'e2evmc_config'
-  if os.path.exists(os.path.join(args.model_dir, config_name + '.json')):
+  have_config = os.path.exists(os.path.join(args.model_dir, config_name + '.json'))
+  if have_config:
     e2evmc_config = create_e2evmc_config(load_model_config(args.model_dir, config_name))
     print(">>> Loaded existing model config from %s" % (args.model_dir,))
   else:
@@ -180,8 +172,24 @@ def main(args, argv=None):
         'dim_s_diff': args.dim_s_diff, 'proc_obs': args.proc_obs, 'proc_tgt': args.proc_tgt,
         'l2_regularizer': args.l2_regularizer, 'lambda_aux': args.lambda_aux, 'batch_size': args.batch_size,
         'lr': args.lr})
-    if rank == 0:
+  # everything that can be refused is refused before the run directory is touched
+  from geeco_b200.engine import _check_switches
+  _check_switches(e2evmc_config)
+  if not args.dataset_dir.startswith('synthetic') and not os.path.isdir(args.dataset_dir):
+    raise FileNotFoundError("--dataset_dir %s does not exist (use synthetic[:<episodes>] for synthetic episodes)"
+                            % (args.dataset_dir,))
+  import torch
+  import torch.distributed as dist
+  if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    dist.init_process_group('nccl')
+  rank, world = parallel.world_info()
+  os.makedirs(args.model_dir, exist_ok=True)
+  if rank == 0:
+    save_run_command(ARGPARSER, args.model_dir, argv)
+    if not have_config:
       save_model_config(e2evmc_config._asdict(), args.model_dir, config_name)
+  run_config = RunConfig(save_checkpoints_steps=args.ckpt_steps, keep_checkpoint_max=args.num_last_ckpt)
   estimator = Estimator(model_fn=goal_e2evmc_model_fn, model_dir=args.model_dir, config=run_config,
                         params={'e2evmc_config': e2evmc_config, 'log_steps': args.log_steps, 'debug': args.debug,
                                 'checkpoint_format': args.checkpoint_format},

@@ -234,8 +234,23 @@ def test_train_cli_accepts_the_reference_flags():
                               '--proc_tgt', 'dyndiff', '--batch_size', '64', '--debug'])
   assert (a.observation_format, a.goal_condition, a.proc_obs, a.proc_tgt, a.batch_size, a.debug) == \
       ('rgb', 'target', 'dynimg', 'dyndiff', 64, True)
-  with pytest.raises(NotImplementedError):
-    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'target', '--dataset_dir', '/nonexistent']))
+
+
+def test_train_cli_refuses_before_touching_the_run_directory(tmp_path):
+  m = _train_module()
+  md = str(tmp_path / 'run')
+  geecof = ['--goal_condition', 'target', '--proc_obs', 'dynimg', '--proc_tgt', 'dyndiff', '--model_dir', md]
+  with pytest.raises(NotImplementedError):          # reference default switches (sequence / constant): not on CUDA yet
+    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'target', '--dataset_dir', 'synthetic:1', '--model_dir', md]))
+  with pytest.raises(NotImplementedError):          # unconditional model
+    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'none', '--model_dir', md]))
+  with pytest.raises(FileNotFoundError):
+    m.main(m.ARGPARSER.parse_args(geecof + ['--dataset_dir', str(tmp_path / 'nonexistent')]))
+  with pytest.raises(ValueError):
+    m.main(m.ARGPARSER.parse_args(geecof + ['--control_mode', 'torque', '--dataset_dir', 'synthetic:1']))
+  with pytest.raises(KeyError):
+    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'sometimes', '--model_dir', md]))
+  assert not os.path.exists(md)
 
 
 def test_snapshot_export_protocol(tmp_path):
