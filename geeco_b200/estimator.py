@@ -323,6 +323,10 @@ class Estimator(object):
       cnt += n * 3; correct += v[6]; rows += n
       if steps is not None and nb >= steps:
         break
+    # data parallel: every rank evaluated its share of each global batch; the accumulators add across ranks, so all
+    # ranks return the metrics of the whole evaluation set (what the single-process reference computes)
+    loss_sum, nb, se['cmd_ee'], se['pos_ee'], se['pos_obj'], cnt, correct, rows = parallel.allreduce_sums(
+        [loss_sum, nb, se['cmd_ee'], se['pos_ee'], se['pos_obj'], cnt, correct, rows])
     if nb == 0:
       raise ValueError("evaluate(): input_fn yielded no batches")
     out = {k: se[k] / cnt for k in se}

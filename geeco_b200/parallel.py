@@ -28,6 +28,19 @@ def allreduce_bucket(flat_grad: torch.Tensor, bucket, async_op=True):
   return dist.all_reduce(flat_grad[off:off + cnt], op=dist.ReduceOp.SUM, async_op=async_op)
 
 
+def allreduce_sums(values, device=None):
+  """Sums a short list of Python numbers over all ranks (float64); identity for a single process.  Used for the
+  streaming evaluation metrics, whose accumulators (sums and counts) add across the ranks' shards."""
+  rank, world = world_info()
+  if world == 1:
+    return [float(v) for v in values]
+  if device is None:
+    device = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+  t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+  dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  return [float(v) for v in t.cpu()]
+
+
 def data_parallel_step(engine, features, labels):
   """forward -> [backward bucket b ; all-reduce bucket b (async)]* -> wait -> Adam with 1/world."""
   rank, world = world_info()

@@ -181,8 +181,25 @@ parallel.broadcast_parameters(e, src=0)
 assert float(e.theta.abs().max()) == 0.0
 lo, hi = rank_slice(0, 8, rank, world)
 assert (lo, hi) == (rank * 4, rank * 4 + 4)
+# evaluation metrics: accumulators add across ranks, every rank gets the whole-set result
+assert parallel.allreduce_sums([rank + 1.0, 2, 0.5]) == [3.0, 4.0, 1.0]
+from geeco_b200.estimator import Estimator, ModeKeys, EstimatorSpec
+class EvalEngine:
+  global_step = 7
+def model_fn(features, labels, mode, params):
+  v = torch.tensor([features['mse'], 0., features['mse'] * 2, features['mse'] * 3, 0., features['loss'], features['hits'], 4.])
+  return EstimatorSpec(mode, v, None, None, None, None)
+est = Estimator.__new__(Estimator)
+est._model_fn, est.params, est._batch, est._engine = model_fn, {}, 4, EvalEngine()
+est._check_batch = lambda f: None
+shard = [{'mse': 1.0 + rank, 'loss': 2.0 + rank, 'hits': 1.0 + 2 * rank}, {'mse': 3.0, 'loss': 4.0 - rank, 'hits': 2.0}]
+res = est.evaluate(lambda: iter([(f, None) for f in shard]))
+# whole set: 4 rank-batches of 4 rows; mse accumulators are sums of (mse * n * 3) over 16 * 3 values
+assert abs(res['cmd_ee'] - (1.0 + 3.0 + 2.0 + 3.0) / 4) < 1e-12, res
+assert abs(res['loss'] - (2.0 + 4.0 + 3.0 + 3.0) / 4) < 1e-12 and abs(res['cmd_grp'] - (1 + 2 + 3 + 2) / 16) < 1e-12, res
+assert res['global_step'] == 7
 dist.destroy_process_group()
-print('ok', rank)
+sys.stdout.write('ok %%d\n' %% rank); sys.stdout.flush()      # one write: the two ranks' lines never interleave
 '''
 
 
