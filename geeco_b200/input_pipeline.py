@@ -31,6 +31,13 @@ Train mode shuffles the episode order only (`np.random.shuffle(tfrecord_paths)`,
 their order inside an episode and every file holds one episode, so the stream position of window w of the
 e-th file is g = e * num_windows + w (geeco_b200.data.locate).
 
+Device-resident frames (`device='cuda'`): consecutive windows share K-1 of their K frames, so a batch of B windows
+holds only about B + K - 1 distinct frames.  In this mode every episode's frames are uploaded ONCE (pinned host ->
+device, 19.4 MB of uint8 per 100-frame episode instead of 77 MB of windows), stay resident while batches read them,
+and the [B,K,H,W,C] window tensor is gathered on the device (an index-select: data movement only); the host never
+copies a pixel per batch.  Features `rgb` / `depth` / `target_*` are then device tensors, which the engine uses in
+place; everything else is unchanged.
+
 Data parallel: with `world > 1` a global batch is `batch_size * world` consecutive stream
 positions and rank r takes rows [r * batch_size, (r+1) * batch_size); each rank decodes only the episodes
 its rows touch.  Incomplete trailing global batches are dropped there (ranks must step together).
@@ -63,6 +70,7 @@ FEATURE_KEYS = ('step', 'ts', 'rgb', 'depth', 'jnt_state', 'vel_state', 'ee_stat
                 'obj_state', 'cmd', 'ctrl')                # _prepare_v4 :375-388
 TARGET_KEYS = ('target_rgb', 'target_depth')               # :389-391
 LABEL_KEYS = ('cmd', 'ctrl', 'vel_target', 'ee_target', 'grp_target')   # :392-398
+BULK_KEYS = ('rgb', 'depth')                               # per-frame images: kept on the device in device mode
 
 
 def get_meta_v4(dataset_dir):
@@ -187,12 +195,34 @@ def _pinned_empty(shape, dtype):
   return torch.empty(tuple(int(s) for s in shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
 
 
+def _host_tensor(arr, pin):
+  """One copy of an array (possibly a read-only memory map of the episode cache) into a torch host tensor,
+  page-locked when it is going to be uploaded."""
+  import torch
+  t = torch.empty(tuple(arr.shape), dtype=getattr(torch, np.dtype(arr.dtype).name), pin_memory=bool(pin))
+  np.copyto(t.numpy(), arr)
+  return t
+
+
+def _gather_frames(frames, idx):
+  """frames[idx] along dim 0, moving 8-byte words when a frame's byte size allows it (a uint8 index_select moves one
+  byte per element; 256x256x3 frames are 24576 words)."""
+  import torch
+  flat = frames.reshape(frames.shape[0], -1)
+  row_bytes = flat.shape[1] * flat.element_size()
+  if flat.element_size() < 8 and row_bytes % 8 == 0 and flat.shape[0] > 0:
+    out = flat.view(torch.int64).index_select(0, idx).view(frames.dtype)
+  else:
+    out = flat.index_select(0, idx)
+  return out.reshape((idx.shape[0],) + tuple(frames.shape[1:]))
+
+
 class WindowBatches(object):
   """Iterable over (features, labels) batches of consecutive window stream positions (see module docstring)."""
 
   def __init__(self, tfrecord_paths, meta, window_size=4, fetch_target=False, batch_size=1, num_epochs=1,
                num_threads=4, prefetch_size=4, frame_format='float32', drop_remainder=False, rank=0, world=1,
-               pin_memory=False, verify_crc=True, want_depth=True, cache_dir=None):
+               pin_memory=False, verify_crc=True, want_depth=True, cache_dir=None, device=None):
     if window_size < 1 or window_size > meta.episode_length - 1:
       raise ValueError("window_size %d does not fit episodes of %d frames" % (window_size, meta.episode_length))
     if not 0 <= rank < world:
@@ -211,6 +241,9 @@ class WindowBatches(object):
     self.pin = bool(pin_memory)
     self.verify_crc = bool(verify_crc)
     self.want_depth = bool(want_depth)
+    self.device = device                                   # None: host batches; 'cuda' / 'cpu': resident frames
+    self._resident = collections.OrderedDict()             # stream episode -> {key: tensor on self.device}
+    self.uploaded_bytes = 0
     self.cache_dir = cache_dir
     if cache_dir:
       os.makedirs(cache_dir, exist_ok=True)
@@ -250,6 +283,9 @@ class WindowBatches(object):
   def _decode(self, stream_episode):
     path = self.paths[stream_episode % len(self.paths)]
     ep = self._cached(path)
+    if self.device is not None and str(self.device).startswith('cuda'):
+      import torch                                          # page-locked copies, so the one upload per episode is a DMA
+      ep['_pinned'] = {k: _host_tensor(ep[k], pin=True) for k in BULK_KEYS + TARGET_KEYS if k in ep}
     if ep['step'].shape[0] != self.meta.episode_length - 1:
       raise ValueError("%s holds %d frames but meta_info.json says episode_length=%d"
                        % (path, ep['step'].shape[0] + 1, self.meta.episode_length))
@@ -257,22 +293,29 @@ class WindowBatches(object):
 
   def _cached(self, path):
     """decode_episode, through the episode cache when one is configured.  A cache entry is keyed by the record's
-    name, size and mtime and by what was decoded; it is written under a temporary name and renamed, so
-    concurrent ranks sharing a cache directory never read a partial file."""
+    name, size and mtime and by what was decoded; it is a directory written under a temporary name and renamed, so
+    concurrent ranks sharing a cache directory never read a partial entry."""
     args = (self.meta, self.fetch_target, self.frame_format, self.verify_crc, self.want_depth)
     if not self.cache_dir:
       return decode_episode(path, *args)
     st = os.stat(path)
-    key = '%s.%d.%d.%s.t%d.d%d.npz' % (os.path.basename(path), st.st_size, int(st.st_mtime), self.frame_format,
-                                       self.fetch_target, self.want_depth)
+    key = '%s.%d.%d.%s.t%d.d%d.ep' % (os.path.basename(path), st.st_size, int(st.st_mtime), self.frame_format,
+                                      self.fetch_target, self.want_depth)
     entry = os.path.join(self.cache_dir, key)
-    if os.path.exists(entry):
-      with np.load(entry) as z:
-        return {k: z[k] for k in z.files}
+    if os.path.isdir(entry):
+      # one .npy per array, memory-mapped: nothing is copied or checksummed until a window (or the one upload
+      # of device mode) reads it from the page cache
+      return {f[:-4]: np.load(os.path.join(entry, f), mmap_mode='r') for f in os.listdir(entry) if f.endswith('.npy')}
     ep = decode_episode(path, *args)
-    tmp = '%s.%d.%d.tmp.npz' % (entry, os.getpid(), threading.get_ident())
-    np.savez(tmp, **ep)
-    os.replace(tmp, entry)
+    tmp = '%s.%d.%d.tmp' % (entry, os.getpid(), threading.get_ident())
+    os.makedirs(tmp)
+    for k, v in ep.items():
+      np.save(os.path.join(tmp, k + '.npy'), v)
+    try:
+      os.rename(tmp, entry)
+    except OSError:                                         # another rank / thread finished the same entry first
+      import shutil
+      shutil.rmtree(tmp, ignore_errors=True)
     return ep
 
   def _alloc(self, shape, dtype):
@@ -287,15 +330,16 @@ class WindowBatches(object):
     feats, labels = {}, {}
     self._pinned = []
     at = 0
+    on_device = self.device is not None
     for e, w0, cnt in self.pieces(lo, hi):
       ep = episodes[e]
       for k in FEATURE_KEYS:
-        if k not in ep:
+        if k not in ep or (on_device and k in BULK_KEYS):
           continue
         if k not in feats:
           feats[k] = self._alloc((n, self.K) + ep[k].shape[1:], ep[k].dtype)
         window_gather(ep[k], self.K, w0, cnt, out=feats[k][at:at + cnt])
-      if self.fetch_target:
+      if self.fetch_target and not on_device:
         for k in TARGET_KEYS:
           if k not in ep:
             continue
@@ -311,7 +355,42 @@ class WindowBatches(object):
     if self.pin:      # hand out the pinned tensors themselves (features are filled through their numpy views)
       by_ptr = {t.data_ptr(): t for t in self._pinned}
       feats = {k: by_ptr[v.ctypes.data] for k, v in feats.items()}
+    if on_device:     # the consumer thread uploads / gathers the images (see _device_images)
+      return feats, labels, self.pieces(lo, hi), {e: episodes[e] for e, _, _ in self.pieces(lo, hi)}
     return feats, labels
+
+  def _device_images(self, feats, plan, episodes):
+    """Adds the image features of one batch as tensors on self.device: uploads the episodes that are not resident
+    yet (once each), gathers the windows by index, drops the episodes no later batch can read.  Runs in the
+    consumer's thread on its current stream, so uploads, gathers and the step that follows are ordered."""
+    import torch
+    dev = torch.device(self.device)
+    for e in [e for e in self._resident if e < plan[0][0]]:
+      del self._resident[e]                                 # the stream only moves forward
+    parts = collections.defaultdict(list)
+    steps = torch.arange(self.K, device=dev)
+    for e, w0, cnt in plan:
+      if e not in self._resident:
+        ep, res = episodes[e], {}
+        for k in BULK_KEYS + (TARGET_KEYS if self.fetch_target else ()):
+          if k not in ep:
+            continue
+          src = ep['_pinned'][k] if '_pinned' in ep else _host_tensor(ep[k], pin=False)
+          res[k] = src.to(dev, non_blocking=True)
+          self.uploaded_bytes += src.numel() * src.element_size()
+        res['_host'] = ep.get('_pinned')                    # keeps the page-locked source alive with its copy
+        self._resident[e] = res
+      res = self._resident[e]
+      idx = (torch.arange(w0, w0 + cnt, device=dev).unsqueeze(1) + steps.unsqueeze(0)).reshape(-1)
+      for k in BULK_KEYS:
+        if k in res:
+          parts[k].append(_gather_frames(res[k], idx).reshape((cnt, self.K) + tuple(res[k].shape[1:])))
+      for k in TARGET_KEYS:
+        if k in res:
+          parts[k].append(res[k].unsqueeze(0).expand((cnt,) + tuple(res[k].shape)))
+    for k, ps in parts.items():
+      feats[k] = (torch.cat(ps, dim=0) if len(ps) > 1 else ps[0]).contiguous()
+    return feats
 
   def _produce(self, out_q, stop):
     try:
@@ -348,9 +427,13 @@ class WindowBatches(object):
           return
         if isinstance(item, BaseException):
           raise item
+        if self.device is not None:
+          feats, labels, plan, episodes = item
+          item = (self._device_images(feats, plan, episodes), labels)
         yield item
     finally:
       stop.set()
+      self._resident.clear()
       while worker.is_alive():                              # unblock a producer waiting on a full queue
         try:
           out_q.get(timeout=0.05)
@@ -361,7 +444,7 @@ class WindowBatches(object):
 def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_target=False, shuffle_buffer=128,
                           batch_size=1, num_epochs=1, num_threads=4, prefetch_size=4, seed=None,
                           frame_format='float32', drop_remainder=False, rank=0, world=1, pin_memory=False,
-                          cache_dir=None, want_depth=True):
+                          cache_dir=None, want_depth=True, device=None):
   """Same signature and defaults as the reference (geeco_gym.py:401-412) plus the execution keywords after
   `seed`.  `shuffle_buffer` is accepted and unused, as in the reference (its window-level shuffle is commented
   out, :446-448); `mode == 'train'` shuffles the episode order with numpy's global generator (:436-437), or
@@ -375,7 +458,7 @@ def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_ta
   return WindowBatches(paths, meta, window_size=window_size, fetch_target=fetch_target, batch_size=batch_size,
                        num_epochs=num_epochs, num_threads=num_threads, prefetch_size=prefetch_size,
                        frame_format=frame_format, drop_remainder=drop_remainder, rank=rank, world=world,
-                       pin_memory=pin_memory, cache_dir=cache_dir, want_depth=want_depth)
+                       pin_memory=pin_memory, cache_dir=cache_dir, want_depth=want_depth, device=device)
 
 
 def pickplace_input_fn(dataset_dir, split_name, mode, encoding='v4', window_size=4, fetch_target=False,

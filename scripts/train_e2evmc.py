@@ -70,6 +70,8 @@ _A('--initial_eval', default=False, action='store_true')
 # --- execution switches of this build (not in the reference)
 _A('--precision', type=str, default='bf16', help='bf16 (tcgen05 tensor cores) | fp32')
 _A('--cache_dir', type=str, default='', help='directory for decoded-episode caches (recorded datasets)')
+_A('--device_frames', default=False, action='store_true',
+   help='recorded datasets: upload every episode once and gather the K-frame windows on the device')
 _A('--checkpoint_format', type=str, default='npz', help='npz | bundle (TF V2 .index/.data files)')
 
 _OBSERVATION_FORMAT_TO_CHANNELS = {'rgb': 3, 'rgbd': 4}
@@ -146,8 +148,9 @@ def recorded_input_fn(args, config, mode, rank=0, world=1):
         window_size=config.window_size, fetch_target=(args.goal_condition == 'target'),
         shuffle_buffer=args.shuffle_buffer, batch_size=config.batch_size, num_epochs=1,
         num_threads=args.num_threads, prefetch_size=args.prefetch_size, seed=epoch[0] if world > 1 else None,
-        frame_format='uint8', drop_remainder=True, rank=rank, world=world, pin_memory=True,
-        cache_dir=args.cache_dir or None, want_depth=(args.observation_format == 'rgbd'))
+        frame_format='uint8', drop_remainder=True, rank=rank, world=world, pin_memory=not args.device_frames,
+        cache_dir=args.cache_dir or None, want_depth=(args.observation_format == 'rgbd'),
+        device='cuda' if args.device_frames else None)
   return make
 
 

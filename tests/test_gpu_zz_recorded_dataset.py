@@ -86,3 +86,31 @@ def test_train_cli_on_a_recorded_dataset_and_predictor_from_bundle(cuda_device, 
   pred.set_goal(rng.integers(0, 256, size=(256, 256, 3)) / 255.0)
   out = pred.predict(rng.integers(0, 256, size=(256, 256, 3)) / 255.0, rng.uniform(-1, 1, size=7).astype(np.float32))
   assert out['cmd_ee'].shape == (3,) and out['cmd_grp'].shape == (1,) and np.all(np.isfinite(out['cmd_ee']))
+
+
+def test_device_resident_frames_train_like_host_batches(cuda_device, recorded, tmp_path):
+  """device='cuda' pipeline mode: every episode is uploaded once, the windows are gathered on the device; training is
+  bit-identical to the host-window batches and the upload is one frame per frame, not K."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
+  from geeco_b200.input_pipeline import pickplace_input_fn_v4
+  cfg = create_e2evmc_config(O.make_config(batch_size=2, lr=1e-3))
+  thetas, pipes = [], []
+  for name, kw in (('host', dict(pin_memory=True)), ('dev', dict(device='cuda'))):
+    est = Estimator(goal_e2evmc_model_fn, str(tmp_path / name), RunConfig(), {'e2evmc_config': cfg, 'log_steps': 1},
+                    precision='fp32', batch_size=2)
+
+    def inp(kw=kw):
+      pipes.append(pickplace_input_fn_v4(recorded, 'default', 'train', 4, True, batch_size=2, drop_remainder=True,
+                                         frame_format='uint8', want_depth=False, num_epochs=2, **kw))
+      return pipes[-1]
+    est.train(inp)
+    assert est.engine.global_step == 6
+    thetas.append(est.engine.theta.clone())
+  assert torch.equal(thetas[0], thetas[1])
+  first = next(iter(pickplace_input_fn_v4(recorded, 'default', 'train', 4, True, batch_size=2, frame_format='uint8',
+                                          want_depth=False, device='cuda')))[0]
+  assert first['rgb'].is_cuda and first['rgb'].dtype == torch.uint8 and tuple(first['rgb'].shape) == (2, 4, 256, 256, 3)
+  assert first['target_rgb'].is_cuda and not torch.is_tensor(first['jnt_state'])
+  frame = 256 * 256 * 3
+  assert pipes[1].uploaded_bytes == 2 * (9 + 1) * frame          # 2 epochs x (9 frames + the target), once each

@@ -475,7 +475,7 @@ def test_episode_cache_serves_identical_batches(dataset, tmp_path):
   plain = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', **kw))
   first = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', cache_dir=cache, **kw))
   entries = sorted(os.listdir(cache))
-  assert len(entries) == 2 and all(e.endswith('.uint8.t1.d1.npz') for e in entries)
+  assert len(entries) == 2 and all(e.endswith('.uint8.t1.d1.ep') for e in entries)
   # the second pass must not touch the records: make them unreadable and read again
   recs = [os.path.join(d, 'data', f) for f in ('000003.tfrecord.zlib', '000004.tfrecord.zlib')]
   saved = [(p, open(p, 'rb').read(), os.stat(p)) for p in recs]
@@ -565,3 +565,45 @@ def test_batch_ranges_partition_the_stream_property():
     assert len({len(it) for it in its}) == 1                                # ranks step together
 
   prop()
+
+
+@pytest.mark.parametrize('fmt', ['uint8', 'float32'])
+def test_device_resident_frames_equal_host_batches(dataset, fmt):
+  """device mode (frames uploaded once per episode, windows gathered by index on the device) yields the same batches
+  as the host path; exercised here with device='cpu' -- the same torch code path, minus the DMA."""
+  import torch
+  d, eps = dataset
+  kw = dict(window_size=4, fetch_target=True, batch_size=5, frame_format=fmt, num_epochs=2)
+  host = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', **kw))
+  it = ip.pickplace_input_fn_v4(d, 'default', 'eval', device='cpu', **kw)
+  got = list(it)
+  assert len(got) == len(host) == 6                                      # 2 episodes x 2 epochs x 7 windows in fives
+  for (hf, hl), (df, dl) in zip(host, got):
+    assert set(hf) == set(df) and set(hl) == set(dl)
+    for k in hf:
+      if k in ip.BULK_KEYS + ip.TARGET_KEYS:
+        assert torch.is_tensor(df[k]) and df[k].is_contiguous()
+        np.testing.assert_array_equal(df[k].numpy(), hf[k], err_msg=k)
+        assert df[k].numpy().dtype == hf[k].dtype
+      else:
+        np.testing.assert_array_equal(df[k], hf[k], err_msg=k)
+    for k in hl:
+      np.testing.assert_array_equal(dl[k], hl[k])
+  # each (episode, epoch) was uploaded exactly once: 4 uploads of rgb + depth + targets, not one per window
+  px = 10 * 8 * 6                                                        # S = 10 frames of 8 x 6 pixels
+  per_episode = px * 3 * (1 if fmt == 'uint8' else 4) * (1 + 0.1) + px * 4 * (1 + 0.1)
+  assert it.uploaded_bytes == int(round(4 * per_episode))
+  assert len(it._resident) == 0                                          # released when the iterator ends
+
+
+def test_device_resident_frames_rank_shards(dataset):
+  d, eps = dataset
+  whole = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', 4, True, batch_size=4, drop_remainder=True, frame_format='uint8'))
+  for r in range(2):
+    part = list(ip.pickplace_input_fn_v4(d, 'default', 'eval', 4, True, batch_size=2, rank=r, world=2, frame_format='uint8',
+                                         device='cpu'))
+    assert len(part) == len(whole)
+    for gb, pb in zip(whole, part):
+      np.testing.assert_array_equal(pb[0]['rgb'].numpy(), gb[0]['rgb'][r * 2:(r + 1) * 2])
+      np.testing.assert_array_equal(pb[0]['target_rgb'].numpy(), gb[0]['target_rgb'][r * 2:(r + 1) * 2])
+      np.testing.assert_array_equal(pb[0]['jnt_state'], gb[0]['jnt_state'][r * 2:(r + 1) * 2])
