@@ -109,7 +109,3 @@ def write_bundle(prefix, tensors: dict):
     raise
   _io.check(lib.geeco_bundle_writer_finish(h))
 
-
-def bundle_exists(prefix):
-  import os
-  return os.path.exists(prefix + '.index')

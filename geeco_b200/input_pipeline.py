@@ -53,7 +53,6 @@ import threading
 
 import numpy as np
 
-from . import _io
 from .tfrecord import SequenceExample, TFRecordFile, window_gather
 
 PickAndPlaceMetaV4 = collections.namedtuple('PickAndPlaceMetaV4', [
