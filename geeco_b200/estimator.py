@@ -172,10 +172,14 @@ def decode_observation(features, config):
   import torch
 
   def cat(a, b):
+    # recorded uint8 pixels become the float32 values of geeco_gym.py:310 before they share a tensor with the depth
     if torch.is_tensor(a) or torch.is_tensor(b):
       a, b = torch.as_tensor(a), torch.as_tensor(b)
-      return torch.cat([a.float(), b.to(a.device).float()], dim=-1)
-    return np.concatenate([np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)], axis=-1)
+      a = a.float() / 255.0 if a.dtype == torch.uint8 else a.float()
+      return torch.cat([a, b.to(a.device).float()], dim=-1)
+    a = np.asarray(a)
+    a = a.astype(np.float32) / np.float32(255.0) if a.dtype == np.uint8 else a.astype(np.float32)
+    return np.concatenate([a, np.asarray(b, dtype=np.float32)], axis=-1)
 
   out = dict(features)
   out['rgb'] = cat(features['rgb'], features['depth'])

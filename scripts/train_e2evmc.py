@@ -148,7 +148,9 @@ def recorded_input_fn(args, config, mode, rank=0, world=1):
         window_size=config.window_size, fetch_target=(args.goal_condition == 'target'),
         shuffle_buffer=args.shuffle_buffer, batch_size=config.batch_size, num_epochs=1,
         num_threads=args.num_threads, prefetch_size=args.prefetch_size, seed=epoch[0] if world > 1 else None,
-        frame_format='uint8', drop_remainder=True, rank=rank, world=world, pin_memory=not args.device_frames,
+        # RGB-D frames share one float tensor with the depth channel (estimator.py:166-172): no uint8 wire format
+        frame_format='float32' if args.observation_format == 'rgbd' else 'uint8',
+        drop_remainder=True, rank=rank, world=world, pin_memory=not args.device_frames,
         cache_dir=args.cache_dir or None, want_depth=(args.observation_format == 'rgbd'),
         device='cuda' if args.device_frames else None)
   return make

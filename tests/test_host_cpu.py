@@ -369,6 +369,15 @@ def test_decode_observation_concatenates_depth_behind_rgb():
   f = {'rgb': rng.uniform(size=(2, 4, 8, 8, 3)).astype(np.float32), 'target_rgb': rng.uniform(size=(2, 8, 8, 3)).astype(np.float32),
        'depth': rng.uniform(size=(2, 4, 8, 8, 1)).astype(np.float32), 'target_depth': rng.uniform(size=(2, 8, 8, 1)).astype(np.float32)}
   assert decode_observation(f, cfg3) is f                       # RGB: untouched
+  # recorded uint8 pixels are divided by 255 before they are concatenated with the float depth
+  u8 = dict(f, rgb=(f['rgb'] * 255).astype(np.uint8), target_rgb=(f['target_rgb'] * 255).astype(np.uint8))
+  g8 = decode_observation(u8, cfg4)
+  assert g8['rgb'].dtype == np.float32 and g8['rgb'].shape == (2, 4, 8, 8, 4)
+  assert np.array_equal(g8['rgb'][..., :3], u8['rgb'].astype(np.float32) / np.float32(255.0))
+  assert np.array_equal(g8['rgb'][..., 3:], f['depth']) and float(g8['target_rgb'][..., :3].max()) <= 1.0
+  import torch
+  t8 = decode_observation({k: torch.from_numpy(v) for k, v in u8.items()}, cfg4)
+  assert torch.equal(t8['rgb'], torch.from_numpy(g8['rgb']))
   out = decode_observation(f, cfg4)
   assert out['rgb'].shape == (2, 4, 8, 8, 4) and out['target_rgb'].shape == (2, 8, 8, 4)
   assert np.array_equal(out['rgb'][..., :3], f['rgb']) and np.array_equal(out['rgb'][..., 3:], f['depth'])
