@@ -607,3 +607,75 @@ def test_device_resident_frames_rank_shards(dataset):
       np.testing.assert_array_equal(pb[0]['rgb'].numpy(), gb[0]['rgb'][r * 2:(r + 1) * 2])
       np.testing.assert_array_equal(pb[0]['target_rgb'].numpy(), gb[0]['target_rgb'][r * 2:(r + 1) * 2])
       np.testing.assert_array_equal(pb[0]['jnt_state'], gb[0]['jnt_state'][r * 2:(r + 1) * 2])
+
+
+class _StubEngine(object):
+  """What Estimator.train / evaluate need from an Engine, on the CPU: staging is the identity, a 'train step' folds
+  the batch into a checksum so the test can tell exactly which rows were fed, in which order."""
+  training = True
+
+  def __init__(self, batch):
+    import torch
+    self.N, self.global_step, self.fed = batch, 0, []
+    self._torch = torch
+
+  def stage(self, features, labels, slot):
+    return features, labels, None
+
+  def wait_staged(self, event, slot):
+    pass
+
+  def release_staged(self, slot):
+    pass
+
+  def _vector(self, features, labels):
+    rgb = np.asarray(features['rgb'])
+    self.fed.append((np.asarray(features['step'])[:, -1].tolist(), int(rgb.astype(np.int64).sum()), rgb.dtype.name,
+                     np.asarray(labels['cmd'])[:, 0].tolist()))
+    n = rgb.shape[0]
+    return self._torch.tensor([1.0, 0.0, 2.0, 3.0, 0.0, 10.0 + len(self.fed), float(n), float(n)])
+
+  def train_step(self, features, labels, grad_scale=1.0):
+    self.global_step += 1
+    return self._vector(features, labels)
+
+  def forward(self, features, labels=None, want_dyn=False):
+    return {'losses': self._vector(features, labels)}
+
+  def read_losses_async(self, losses, slot):
+    class Done:
+      def synchronize(self):
+        pass
+    return losses, Done()
+
+  def losses_dict(self, losses=None):
+    return dict(zip(('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss_reg', 'loss'),
+                    [float(x) for x in losses[:6]]))
+
+
+def test_estimator_consumes_the_pipeline(dataset, tmp_path):
+  """Estimator.train / evaluate over WindowBatches (host logic only, stub engine): every full batch is fed once, in
+  stream order, as recorded bytes; a partial batch is refused like the reference's static batch size would."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
+  d, eps = dataset
+  cfg = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff', batch_size=4, img_height=8, img_width=6))
+  est = Estimator(goal_e2evmc_model_fn, str(tmp_path), RunConfig(save_checkpoints_steps=0), {'e2evmc_config': cfg, 'log_steps': 1,
+                                                                                              'save_final_checkpoint': False},
+                  batch_size=4)
+  est._engine = _StubEngine(4)
+  inp = lambda **kw: (lambda: ip.pickplace_input_fn_v4(d, 'default', 'eval', 4, True, batch_size=4, frame_format='uint8', **kw))
+  est.train(inp(drop_remainder=True))
+  meta = ip.get_meta_v4(d)
+  ref = _reference_stream(eps[3:], meta, 4, True)                     # 14 windows -> 3 full batches
+  assert est.engine.global_step == 3 and len(est.last_train_losses) == 3
+  for b, (steps, pixel_sum, dtype, cmd0) in enumerate(est.engine.fed):
+    rows = ref[4 * b:4 * b + 4]
+    assert steps == [int(r[0]['step'][-1]) for r in rows] and dtype == 'uint8'
+    assert pixel_sum == int(round(sum(float(r[0]['rgb'].astype(np.float64).sum()) for r in rows) * 255.0))
+    assert cmd0 == [float(r[1]['cmd'][0]) for r in rows]
+  assert [round(l['loss']) for _, l in est.last_train_losses] == [11, 12, 13]
+  ev = est.evaluate(inp(drop_remainder=True))
+  assert ev['cmd_ee'] == 1.0 and ev['pos_obj'] == 3.0 and ev['cmd_grp'] == 1.0 and ev['global_step'] == 3
+  with pytest.raises(ValueError, match='batch of 2 rows'):            # the trailing partial batch (14 = 3 * 4 + 2)
+    est.train(inp())
