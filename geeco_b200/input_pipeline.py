@@ -242,6 +242,7 @@ class WindowBatches(object):
     self.want_depth = bool(want_depth)
     self.device = device                                   # None: host batches; 'cuda' / 'cpu': resident frames
     self._resident = collections.OrderedDict()             # stream episode -> {key: tensor on self.device}
+    self._cuda_index = None                                # the consumer's CUDA device, adopted by the helper threads
     self.uploaded_bytes = 0
     self.cache_dir = cache_dir
     if cache_dir:
@@ -281,6 +282,7 @@ class WindowBatches(object):
   # -- assembly -----------------------------------------------------------------------------------
   def _decode(self, stream_episode):
     path = self.paths[stream_episode % len(self.paths)]
+    self._adopt_cuda_device()
     ep = self._cached(path)
     if self.device is not None and str(self.device).startswith('cuda'):
       import torch                                          # page-locked copies, so the one upload per episode is a DMA
@@ -391,8 +393,16 @@ class WindowBatches(object):
       feats[k] = (torch.cat(ps, dim=0) if len(ps) > 1 else ps[0]).contiguous()
     return feats
 
+  def _adopt_cuda_device(self):
+    """Page-locked allocations made in a helper thread must belong to the consumer's GPU, not to device 0 (one
+    process per GPU: a thread that never called set_device would open a context on GPU 0 from every rank)."""
+    if self._cuda_index is not None:
+      import torch
+      torch.cuda.set_device(self._cuda_index)
+
   def _produce(self, out_q, stop):
     try:
+      self._adopt_cuda_device()
       ranges = self.batch_ranges()
       need = [[e for e, _, _ in self.pieces(lo, hi)] for lo, hi in ranges]
       order = sorted({e for es in need for e in es})        # stream episodes this rank reads, ascending
@@ -415,6 +425,10 @@ class WindowBatches(object):
       out_q.put(exc)
 
   def __iter__(self):
+    if self.pin or (self.device is not None and str(self.device).startswith('cuda')):
+      import torch
+      if torch.cuda.is_available():
+        self._cuda_index = torch.cuda.current_device()
     out_q = queue.Queue(maxsize=self.prefetch)
     stop = threading.Event()
     worker = threading.Thread(target=self._produce, args=(out_q, stop), daemon=True)
