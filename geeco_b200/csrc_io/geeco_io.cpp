@@ -576,13 +576,20 @@ extern "C" int geeco_seqex_read_u8(const geeco_seqex* s, int which, const char* 
       if (at + static_cast<int64_t>(n) > capacity) { room = false; return false; }
       uint8_t* d = dst + at;
       int64_t b = 0;
-      for (size_t i = 0; i < n; ++i) {               // unaligned-safe loads; the loop vectorises
-        float v;
-        memcpy(&v, p + 4 * i, 4);
-        float c = v < 0.f ? 0.f : (v > 255.f ? 255.f : v);   // NaN falls through to the cast below as 0
-        uint8_t q = static_cast<uint8_t>(c != c ? 0.f : c);
-        d[i] = q;
-        b += (static_cast<float>(q) != v);
+      // blocks of 4096 values with a 32-bit mismatch counter: the inner loop has no 64-bit lane and vectorises
+      for (size_t i0 = 0; i0 < n; i0 += 4096) {
+        const size_t i1 = i0 + 4096 < n ? i0 + 4096 : n;
+        uint32_t miss = 0;
+        for (size_t i = i0; i < i1; ++i) {
+          float v;
+          memcpy(&v, p + 4 * i, 4);                    // unaligned-safe load
+          float c = v > 0.f ? v : 0.f;                  // NaN compares false: becomes 0 and counts as inexact
+          c = c < 255.f ? c : 255.f;
+          const uint8_t q = static_cast<uint8_t>(static_cast<int32_t>(c));
+          d[i] = q;
+          miss += (static_cast<float>(q) != v);
+        }
+        b += miss;
       }
       bad += b;
       at += static_cast<int64_t>(n);
