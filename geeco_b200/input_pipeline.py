@@ -284,12 +284,12 @@ class WindowBatches(object):
     path = self.paths[stream_episode % len(self.paths)]
     self._adopt_cuda_device()
     ep = self._cached(path)
-    if self.device is not None and str(self.device).startswith('cuda'):
-      import torch                                          # page-locked copies, so the one upload per episode is a DMA
-      ep['_pinned'] = {k: _host_tensor(ep[k], pin=True) for k in BULK_KEYS + TARGET_KEYS if k in ep}
     if ep['step'].shape[0] != self.meta.episode_length - 1:
       raise ValueError("%s holds %d frames but meta_info.json says episode_length=%d"
                        % (path, ep['step'].shape[0] + 1, self.meta.episode_length))
+    if self.device is not None and str(self.device).startswith('cuda'):
+      # page-locked copies, so that the one upload per episode is a DMA
+      ep['_pinned'] = {k: _host_tensor(ep[k], pin=True) for k in BULK_KEYS + TARGET_KEYS if k in ep}
     return ep
 
   def _cached(self, path):
