@@ -69,7 +69,7 @@ def build_io_library(force=False):
   if not force and os.path.exists(IO_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(IO_LIB) for d in deps):
     return IO_LIB
   cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-fPIC', '-shared', '-Wall', '-Wextra', '-o', IO_LIB,
-         IO_SRC, '-lz']
+         IO_SRC, '-lz', '-pthread']
   r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
   if r.returncode:
     sys.stderr.write(r.stdout)

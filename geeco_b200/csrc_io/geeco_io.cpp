@@ -21,6 +21,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -670,7 +671,25 @@ extern "C" int geeco_io_window_gather(const void* src, int64_t frames, int64_t f
   const uint8_t* s = static_cast<const uint8_t*>(src);
   uint8_t* d = static_cast<uint8_t*>(dst);
   const size_t wb = static_cast<size_t>(K) * frame_bytes;
-  for (int64_t i = 0; i < nwin; ++i) memcpy(d + i * wb, s + (w0 + i) * frame_bytes, wb);
+  auto copy_range = [=](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) memcpy(d + i * wb, s + (w0 + i) * frame_bytes, wb);
+  };
+  // image windows (tens of MB per batch) are split over a few threads: one memcpy stream does not saturate the
+  // host's memory bandwidth; small state vectors stay on the calling thread
+  const size_t total = static_cast<size_t>(nwin) * wb;
+  int nthreads = total >= (8u << 20) ? static_cast<int>(std::min<int64_t>(4, nwin)) : 1;
+  if (nthreads <= 1) {
+    copy_range(0, nwin);
+    return GEECO_IO_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (nwin + nthreads - 1) / nthreads;
+  for (int t = 1; t < nthreads; ++t) {
+    const int64_t lo = t * per, hi = std::min<int64_t>(nwin, lo + per);
+    if (lo < hi) pool.emplace_back(copy_range, lo, hi);
+  }
+  copy_range(0, std::min<int64_t>(nwin, per));
+  for (auto& th : pool) th.join();
   return GEECO_IO_OK;
 }
 
