@@ -385,3 +385,15 @@ def test_decode_observation_concatenates_depth_behind_rgb():
   assert decode_observation(out, cfg4) is out                   # already 4 channels: untouched
   with pytest.raises(ValueError):
     decode_observation({'rgb': f['rgb'], 'target_rgb': f['target_rgb']}, cfg4)
+
+
+def test_bench_input_pipeline_leg_runs_on_the_host():
+  """bench.py's `input_pipeline` object (host decode rate next to cpu_baseline) needs no GPU and never raises."""
+  import importlib.util
+  spec = importlib.util.spec_from_file_location('geeco_bench', os.path.join(ROOT, 'bench.py'))
+  bench = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(bench)
+  r = bench.time_input_pipeline(frames=6)
+  assert 'error' not in r, r
+  assert r['frames_per_s_per_thread'] > 0 and r['episode_frames'] == 6 and r['decoded']['rgb'] == [5, 256, 256, 3]
+  assert r['decoded']['target_rgb'] == [256, 256, 3] and r['host_cores'] == os.cpu_count()
