@@ -19,8 +19,16 @@ class GeecoConfig(C.Structure):
   _fields_ = [(n, C.c_int32) for n in (
       'img_height', 'img_width', 'img_channels', 'dim_jnt_state', 'window_size', 'dim_s_obs', 'dim_s_dyn',
       'dim_s_diff', 'dim_h_lstm', 'dim_h_fc', 'num_grp_states', 'batch_size', 'precision', 'carry_state',
-      'training', 'reserved0')] + [(n, C.c_float) for n in (
-          'lr', 'lambda_aux', 'l2_regularizer', 'adam_beta1', 'adam_beta2', 'adam_eps')]
+      'training', 'goal_condition', 'proc_obs', 'proc_tgt', 'control_mode', 'dim_grp_command')] + [
+          (n, C.c_float) for n in ('lr', 'lambda_aux', 'l2_regularizer', 'adam_beta1', 'adam_beta2', 'adam_eps')]
+
+
+# values of the graph switches (include/geeco_b200.h)
+GOAL_CONDITION = {'target': 0, 'none': 1}
+PROC_OBS = {'dynimg': 0, 'sequence': 1}
+PROC_TGT = {'dyndiff': 0, 'constant': 1, 'residual': 2}
+CONTROL_MODE = {'cartesian': 0, 'velocity': 1}
+NUM_LOSS_SLOTS = 12
 
 
 class GeecoSizes(C.Structure):
@@ -34,8 +42,9 @@ class GeecoParamDesc(C.Structure):
 
 
 class GeecoBatch(C.Structure):
-  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state', 'cmd')] + [
-      ('frame_format', C.c_int32), ('reserved0', C.c_int32)]
+  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state', 'cmd', 'vel_target',
+                                        'ee_target', 'grp_target', 'reset_mask')] + [
+      ('frame_format', C.c_int32), ('ring_start', C.c_int32)]
 
 
 FRAMES_F32, FRAMES_U8 = 0, 1
@@ -55,6 +64,7 @@ SYMBOLS = {
     'geeco_destroy': (C.c_int, [_P]),
     'geeco_bind': (C.c_int, [_P, _P, _P, _P, _P, _P, _I64]),
     'geeco_param_info': (C.c_int, [_P, _I32, C.POINTER(GeecoParamDesc)]),
+    'geeco_head_columns': (C.c_int, [C.POINTER(GeecoConfig)]),
     'geeco_grad_bucket': (C.c_int, [_P, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
     'geeco_params_changed': (C.c_int, [_P, _P]),
     'geeco_set_step': (C.c_int, [_P, _I64, _P]),
@@ -77,6 +87,7 @@ SYMBOLS = {
     'geeco_step_forward': (C.c_int, [_P, C.POINTER(GeecoBatch), C.POINTER(GeecoOutputs), _P]),
     'geeco_step_backward': (C.c_int, [_P, _I32, _P]),
     'geeco_step_update': (C.c_int, [_P, _F, _P]),
+    'geeco_ring_push': (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _I32, _P]),
     'geeco_debug_buffer': (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     'geeco_launch_count': (_I64, [_I32]),
 }

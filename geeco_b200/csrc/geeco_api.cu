@@ -131,7 +131,6 @@ GatherGeom dense_geom(int rows, int K, int Nn, int ldb, int transB) {
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
-static const char* kEncScopes[3] = {"GoalVMC/ConvEncoder", "GoalVMC/DynBuffEncoder", "GoalVMC/DynDiffEncoder"};
 static const int kEncChannels[7] = {32, 48, 64, 128, 192, 256, 256};   // graph.py:76-110
 static const int kEncStrides[8] = {1, 2, 2, 2, 2, 2, 2, 2};            // graph.py:78-113
 
@@ -172,16 +171,31 @@ static int validate(const geeco_config* cfg) {
                     cfg->img_height, cfg->img_width);
     return GEECO_ERR_INVALID;
   }
+  if (cfg->goal_condition != GEECO_GOAL_TARGET && cfg->goal_condition != GEECO_GOAL_NONE) { geeco_set_error("unknown goal_condition %d", cfg->goal_condition); return GEECO_ERR_INVALID; }
+  if (cfg->proc_obs != GEECO_OBS_DYNIMG && cfg->proc_obs != GEECO_OBS_SEQUENCE) {
+    geeco_set_error("Unknown processing mode for frame buffer: %d!", cfg->proc_obs);              // graph.py:408-410
+    return GEECO_ERR_INVALID;
+  }
+  if (cfg->proc_tgt < GEECO_TGT_DYNDIFF || cfg->proc_tgt > GEECO_TGT_RESIDUAL) {
+    geeco_set_error("Unknown processing mode for target image: %d!", cfg->proc_tgt);              // graph.py:357-359
+    return GEECO_ERR_INVALID;
+  }
+  if (cfg->control_mode != GEECO_CTRL_CARTESIAN && cfg->control_mode != GEECO_CTRL_VELOCITY) {
+    geeco_set_error("Unknown control mode '%d'", cfg->control_mode);                               // graph.py:250-252
+    return GEECO_ERR_INVALID;
+  }
   if (cfg->window_size < 2 || cfg->window_size > 8) { geeco_set_error("window_size %d outside [2,8]", cfg->window_size); return GEECO_ERR_INVALID; }
-  if (cfg->batch_size < 1 || cfg->batch_size > 21845) { geeco_set_error("batch_size %d outside [1,21845]", cfg->batch_size); return GEECO_ERR_INVALID; }
+  if (cfg->batch_size < 1 || cfg->batch_size > 7000) { geeco_set_error("batch_size %d outside [1,7000]", cfg->batch_size); return GEECO_ERR_INVALID; }
   if (cfg->dim_s_obs % 4 || cfg->dim_s_dyn % 4 || cfg->dim_s_diff % 4 || cfg->dim_h_lstm % 4 || cfg->dim_s_obs < 4 ||
       cfg->dim_s_dyn < 4 || cfg->dim_s_diff < 4 || cfg->dim_h_lstm < 4 || cfg->dim_h_fc < 1) {
     geeco_set_error("dim_s_obs/dim_s_dyn/dim_s_diff/dim_h_lstm must be positive multiples of 4");
     return GEECO_ERR_INVALID;
   }
-  if ((4 * (cfg->dim_s_obs + cfg->dim_s_dyn + cfg->dim_jnt_state + cfg->dim_s_diff)) % 4) return GEECO_ERR_INVALID;
   if (cfg->num_grp_states < 1 || cfg->num_grp_states > 6) { geeco_set_error("num_grp_states %d outside [1,6]", cfg->num_grp_states); return GEECO_ERR_INVALID; }
-  if (cfg->dim_jnt_state < 1) { geeco_set_error("dim_jnt_state must be positive"); return GEECO_ERR_INVALID; }
+  if (cfg->dim_jnt_state < 1 || cfg->dim_jnt_state > 12) { geeco_set_error("dim_jnt_state %d outside [1,12]", cfg->dim_jnt_state); return GEECO_ERR_INVALID; }
+  if (cfg->control_mode == GEECO_CTRL_VELOCITY && (cfg->dim_grp_command < 1 || cfg->dim_grp_command > 6)) {
+    geeco_set_error("dim_grp_command %d outside [1,6]", cfg->dim_grp_command); return GEECO_ERR_INVALID;
+  }
   if (cfg->precision != GEECO_FP32 && cfg->precision != GEECO_BF16) { geeco_set_error("unknown precision %d", cfg->precision); return GEECO_ERR_INVALID; }
   if (cfg->precision == GEECO_BF16 && (cfg->dim_s_obs % 16 || cfg->dim_s_dyn % 16 || cfg->dim_s_diff % 16 ||
                                         cfg->dim_s_obs > 256 || cfg->dim_s_dyn > 256 || cfg->dim_s_diff > 256)) {
@@ -189,6 +203,46 @@ static int validate(const geeco_config* cfg) {
     return GEECO_ERR_INVALID;
   }
   return GEECO_OK;
+}
+
+// graph variant -> encoder groups, images per group, LSTM steps, scopes, conv8 widths, LSTM input width
+static void select_variant(geeco_ctx* c) {
+  const geeco_config& cfg = c->cfg;
+  const int N = cfg.batch_size, K = cfg.window_size, J = cfg.dim_jnt_state;
+  c->dim8[0] = c->dim8[1] = c->dim8[2] = 0;
+  if (cfg.goal_condition == GEECO_GOAL_NONE) {                          // e2e_vmc, graph.py:268-319
+    c->variant = VAR_VMC; c->G = 1; c->M = K * N; c->T = K;
+    c->enc_scope[0] = "VMC/ConvEncoder"; c->dec_scope = "VMC/LSTMDecoder/";
+    c->dim8[0] = 256;                                                   // conv_encoder's default dim_out (graph.py:61)
+    c->xdim = 4 * (256 + J);
+    return;
+  }
+  c->dec_scope = "GoalVMC/LSTMDecoder/";
+  c->enc_scope[0] = "GoalVMC/ConvEncoder";
+  c->dim8[0] = cfg.dim_s_obs;
+  if (cfg.proc_obs == GEECO_OBS_DYNIMG) {                               // graph.py:386-407 (proc_tgt is not consulted there)
+    c->variant = VAR_GEECOF; c->G = 3; c->M = N; c->T = 1;
+    c->enc_scope[1] = "GoalVMC/DynBuffEncoder"; c->enc_scope[2] = "GoalVMC/DynDiffEncoder";
+    c->dim8[1] = cfg.dim_s_dyn; c->dim8[2] = cfg.dim_s_diff;
+    c->xdim = 4 * (cfg.dim_s_obs + cfg.dim_s_dyn + J + cfg.dim_s_diff);
+  } else if (cfg.proc_tgt == GEECO_TGT_CONSTANT) {                      // graph.py:352-355, :365-367
+    c->variant = VAR_SEQ_CONSTANT; c->G = 1; c->M = (K + 1) * N; c->T = K;
+    c->xdim = 4 * (2 * cfg.dim_s_obs + J);
+  } else if (cfg.proc_tgt == GEECO_TGT_RESIDUAL) {                      // graph.py:368-370
+    c->variant = VAR_SEQ_RESIDUAL; c->G = 1; c->M = (K + 1) * N; c->T = K;
+    c->xdim = 4 * (cfg.dim_s_obs + J);
+  } else {                                                              // graph.py:371-379
+    c->variant = VAR_SEQ_DYNDIFF; c->G = 2; c->M = K * N; c->T = K;
+    c->enc_scope[1] = "GoalVMC/DynDiffEncoder";
+    c->dim8[1] = cfg.dim_s_diff;
+    c->xdim = 4 * (cfg.dim_s_obs + J + cfg.dim_s_diff);
+  }
+}
+
+extern "C" int geeco_head_columns(const geeco_config* cfg) {
+  if (!cfg) return -1;
+  return cfg->control_mode == GEECO_CTRL_VELOCITY ? cfg->dim_jnt_state + 3 + cfg->dim_grp_command + 6
+                                                  : 9 + cfg->num_grp_states;
 }
 
 // builds layer table, parameter table and (when base != NULL) the workspace pointers
@@ -199,44 +253,59 @@ static int plan(geeco_ctx* c, char* ws_base) {
   c->arena_floats = 0;
   const bool bf16 = cfg.precision == GEECO_BF16;
   c->CP = 4;   // network input is channel-padded 3 -> 4 (fp32: 16 B / pixel, bf16: 8 B / pixel)
+  select_variant(c);
+  const int G = c->G, M = c->M, T = c->T;
   // ---- layer geometry
-  const int dims8[3] = {cfg.dim_s_obs, cfg.dim_s_dyn, cfg.dim_s_diff};
-  c->uniform8 = (dims8[0] == dims8[1] && dims8[1] == dims8[2]);
+  c->uniform8 = true;
+  for (int e = 1; e < G; ++e) c->uniform8 = c->uniform8 && c->dim8[e] == c->dim8[0];
   int H = cfg.img_height, Cin_real = cfg.img_channels, Cin_pad = c->CP;
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     L.Hin = H; L.stride = kEncStrides[l]; L.Hout = (H + L.stride - 1) / L.stride;
     L.Cin_real = Cin_real; L.Cin_pad = Cin_pad;
-    for (int e = 0; e < 3; ++e) L.Cout[e] = l < 7 ? kEncChannels[l] : dims8[e];
+    for (int e = 0; e < 3; ++e) L.Cout[e] = l < 7 ? kEncChannels[l] : c->dim8[e < G ? e : 0];
     L.grouped = l < 7 || c->uniform8;
     H = L.Hout; Cin_real = L.Cout[0]; Cin_pad = L.Cout[0];
   }
   // ---- parameters, arena order = gradient-bucket order (late layers first)
-  const int xdim = 4 * (cfg.dim_s_obs + cfg.dim_s_dyn + cfg.dim_jnt_state + cfg.dim_s_diff);
-  const int Hl = cfg.dim_h_lstm, Fc = cfg.dim_h_fc, G = cfg.num_grp_states;
-  c->xdim = xdim;
-  const std::string dsc = "GoalVMC/LSTMDecoder/";
+  const int xdim = c->xdim;
+  const int Hl = cfg.dim_h_lstm, Fc = cfg.dim_h_fc;
+  const std::string dsc = c->dec_scope;
   c->p_lstm_w = add_param(c, dsc + "lstm_cell/kernel", {xdim + Hl, 4 * Hl});
   c->p_lstm_b = add_param(c, dsc + "lstm_cell/bias", {4 * Hl});
   c->p_fc1_w = add_param(c, dsc + "fc1/kernel", {Hl, Fc});
   c->p_fc1_b = add_param(c, dsc + "fc1/bias", {Fc});
-  c->p_head_w[0] = add_param(c, dsc + "pred_cmd_ee/kernel", {Fc, 3});
-  c->p_head_b[0] = add_param(c, dsc + "pred_cmd_ee/bias", {3});
-  c->p_head_w[1] = add_param(c, dsc + "logits_cmd_grp/kernel", {Fc, G});
-  c->p_head_b[1] = add_param(c, dsc + "logits_cmd_grp/bias", {G});
-  c->p_head_w[2] = add_param(c, dsc + "pred_aux_ee/kernel", {Fc, 3});
-  c->p_head_b[2] = add_param(c, dsc + "pred_aux_ee/bias", {3});
-  c->p_head_w[3] = add_param(c, dsc + "pred_aux_obj/kernel", {Fc, 3});
-  c->p_head_b[3] = add_param(c, dsc + "pred_aux_obj/bias", {3});
+  // heads in the order the graph creates them (graph.py:233-259); loss slots: include/geeco_b200.h
+  if (cfg.control_mode == GEECO_CTRL_CARTESIAN) {
+    c->nheads = 4;
+    c->heads_plan[0] = {"pred_cmd_ee", 3, 0, 0, 0, 0, 0};
+    c->heads_plan[1] = {"logits_cmd_grp", cfg.num_grp_states, 1, 1, 0, 0, 0};
+    c->heads_plan[2] = {"pred_aux_ee", 3, 0, 2, 1, 0, 0};
+    c->heads_plan[3] = {"pred_aux_obj", 3, 0, 3, 1, 0, 0};
+  } else {
+    c->nheads = 5;
+    c->heads_plan[0] = {"pred_cmd_vel", cfg.dim_jnt_state, 0, 8, 0, 0, 0};
+    c->heads_plan[1] = {"pred_cmd_ee", 3, 0, 0, 0, 0, 0};
+    c->heads_plan[2] = {"pred_cmd_grp", cfg.dim_grp_command, 0, 1, 0, 0, 0};
+    c->heads_plan[3] = {"pred_aux_ee", 3, 0, 2, 0, 0, 0};     // mse_loss adds all five terms with weight 1 (graph.py:446-449)
+    c->heads_plan[4] = {"pred_aux_obj", 3, 0, 3, 0, 0, 0};
+  }
+  c->NH = 0;
+  for (int h = 0; h < c->nheads; ++h) {
+    HeadPlan& hp = c->heads_plan[h];
+    hp.p_w = add_param(c, dsc + hp.name + "/kernel", {Fc, hp.width});
+    hp.p_b = add_param(c, dsc + hp.name + "/bias", {hp.width});
+    c->NH += hp.width;
+  }
   for (int l = 7; l >= 0; --l) {
     LayerPlan& L = c->layers[l];
     char nm[128];
-    for (int e = 0; e < 3; ++e) {
-      snprintf(nm, sizeof(nm), "%s/conv%d/kernel", kEncScopes[e], l + 1);
+    for (int e = 0; e < G; ++e) {
+      snprintf(nm, sizeof(nm), "%s/conv%d/kernel", c->enc_scope[e], l + 1);
       L.p_w[e] = add_param(c, nm, {3, 3, L.Cin_real, L.Cout[e]});
     }
-    for (int e = 0; e < 3; ++e) {
-      snprintf(nm, sizeof(nm), "%s/conv%d/bias", kEncScopes[e], l + 1);
+    for (int e = 0; e < G; ++e) {
+      snprintf(nm, sizeof(nm), "%s/conv%d/bias", c->enc_scope[e], l + 1);
       L.p_b[e] = add_param(c, nm, {L.Cout[e]});
     }
     if (l == 4) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[0] = c->arena_floats; }
@@ -249,11 +318,11 @@ static int plan(geeco_ctx* c, char* ws_base) {
   Carver cv{ws_base, 0};
   const size_t esz = bf16 ? 2 : 4;
   const long long HW = (long long)cfg.img_height * cfg.img_width;
-  c->x0 = cv.take((size_t)3 * N * HW * c->CP * esz);
+  c->x0 = cv.take((size_t)G * M * HW * c->CP * esz);
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     long long off = 0;
-    for (int e = 0; e < 3; ++e) { L.act_off[e] = off; off += (long long)N * L.Hout * L.Hout * L.Cout[e]; }
+    for (int e = 0; e < G; ++e) { L.act_off[e] = off; off += (long long)M * L.Hout * L.Hout * L.Cout[e]; }
     L.act_elems = off;
     L.y = cv.take((size_t)off * esz);
     L.g = cfg.training ? cv.take((size_t)off * esz) : nullptr;
@@ -261,41 +330,44 @@ static int plan(geeco_ctx* c, char* ws_base) {
     L.mbits = (bf16 && cfg.training && l < 7) ? cv.take((size_t)off / 16 * 2) : nullptr;
     if (l == 0 && getenv("GEECO_NOBITS0")) L.mbits = nullptr;      // experiment: conv2 data gradient from the bf16 mask
   }
-  c->NH = 9 + G;
-  c->state = (float*)cv.take(sizeof(float) * N * (xdim + Hl));
-  c->gates = (float*)cv.take(sizeof(float) * N * 4 * Hl);
-  c->c_cur = (float*)cv.take(sizeof(float) * N * Hl);
-  c->m_cur = (float*)cv.take(sizeof(float) * N * Hl);
+  const int ld = xdim + Hl;
+  c->states = (float*)cv.take(sizeof(float) * T * N * ld);
+  c->gates = (float*)cv.take(sizeof(float) * T * N * 4 * Hl);
+  c->c_seq = (float*)cv.take(sizeof(float) * T * N * Hl);
+  c->m_seq = (float*)cv.take(sizeof(float) * T * N * Hl);
   c->state_out = (float*)cv.take(sizeof(float) * N * 2 * Hl);
   c->c_carry = (float*)cv.take(sizeof(float) * N * Hl);
   c->m_carry = (float*)cv.take(sizeof(float) * N * Hl);
   c->fc1 = (float*)cv.take(sizeof(float) * N * Fc);
   c->heads = (float*)cv.take(sizeof(float) * N * c->NH);
-  c->loss_parts = (float*)cv.take(sizeof(float) * N * 5);
+  c->loss_parts = (float*)cv.take(sizeof(float) * N * 6);
   c->dheads = (float*)cv.take(sizeof(float) * N * c->NH);
-  c->losses = (float*)cv.take(sizeof(float) * 8);
+  c->losses = (float*)cv.take(sizeof(float) * GEECO_NUM_LOSS_SLOTS);
   c->sc = (float*)cv.take(sizeof(float) * 8);
-  c->gates_partial = (float*)cv.take(sizeof(float) * lstm_gates_partial_floats(N, xdim + Hl, 4 * Hl));
-  // fp32 staging of the first / last conv maps for the tail (bf16 mode converts conv8 output)
+  c->mm_scratch = (int*)cv.take(sizeof(int) * 2 * cfg.window_size * N);
+  c->gates_partial = (float*)cv.take(sizeof(float) * lstm_gates_partial_floats(N, ld, 4 * Hl));
+  // fp32 staging of the last conv maps for the tail (bf16 mode converts conv8 output)
   c->y8_f32 = bf16 ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
   c->g8_f32 = (bf16 && cfg.training) ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
   if (cfg.training) {
     c->dfc1 = (float*)cv.take(sizeof(float) * N * Fc);
-    c->dgates = (float*)cv.take(sizeof(float) * N * 4 * Hl);
-    c->dstate = (float*)cv.take(sizeof(float) * N * (xdim + Hl));
+    c->dgates = (float*)cv.take(sizeof(float) * T * N * 4 * Hl);
+    c->dstates = (float*)cv.take(sizeof(float) * T * N * ld);
+    c->dm_last = (float*)cv.take(sizeof(float) * N * Hl);
+    c->dc = (float*)cv.take(sizeof(float) * N * Hl);
     // split-K partial buffer: worst case over all TN launches
     long long cap = 0;
     for (int l = 0; l < 8; ++l) {
       LayerPlan& L = c->layers[l];
-      const int groups = L.grouped ? 3 : 1;
-      for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
-        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
+      const int groups = L.grouped ? G : 1;
+      for (int e = 0; e < (L.grouped ? 1 : G); ++e) {
+        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, M);
         long long need = gemm_tn_partial_floats(g, groups);
         if (need > cap) cap = need;
       }
     }
     {
-      GatherGeom g = dense_geom(N, xdim + Hl, 4 * Hl, 4 * Hl, 0);
+      GatherGeom g = dense_geom(T * N, ld, 4 * Hl, 4 * Hl, 0);
       long long need = gemm_tn_partial_floats(g, 1);
       if (need > cap) cap = need;
     }
@@ -482,54 +554,86 @@ static inline float* GR(geeco_ctx* c, int idx) { return c->grad + c->params[idx]
 
 static TailDims tail_dims(const geeco_ctx* c) {
   TailDims d;
-  d.N = c->cfg.batch_size; d.K = c->cfg.window_size; d.J = c->cfg.dim_jnt_state;
-  d.D_obs = c->cfg.dim_s_obs; d.D_dyn = c->cfg.dim_s_dyn; d.D_diff = c->cfg.dim_s_diff;
-  d.Hl = c->cfg.dim_h_lstm; d.Fc = c->cfg.dim_h_fc; d.G = c->cfg.num_grp_states;
-  d.lambda_aux = c->cfg.lambda_aux;
+  d.N = c->cfg.batch_size; d.Hl = c->cfg.dim_h_lstm; d.Fc = c->cfg.dim_h_fc; d.G = c->cfg.num_grp_states;
   return d;
 }
-static TailParams tail_params(geeco_ctx* c) {
-  TailParams p;
-  p.w_fc1 = P(c, c->p_fc1_w); p.b_fc1 = P(c, c->p_fc1_b);
-  p.w_cmd_ee = P(c, c->p_head_w[0]); p.b_cmd_ee = P(c, c->p_head_b[0]);
-  p.w_grp = P(c, c->p_head_w[1]); p.b_grp = P(c, c->p_head_b[1]);
-  p.w_aux_ee = P(c, c->p_head_w[2]); p.b_aux_ee = P(c, c->p_head_b[2]);
-  p.w_aux_obj = P(c, c->p_head_w[3]); p.b_aux_obj = P(c, c->p_head_b[3]);
-  return p;
+
+// head table of this step: parameter / gradient pointers and where each head finds its target in the batch
+// (estimator.py:206-216 cartesian, :229-236 velocity; the auxiliary poses come from the LAST frame of the window)
+static TailHeads tail_heads(geeco_ctx* c, const geeco_batch* b) {
+  const geeco_config& cfg = c->cfg;
+  const int K = cfg.window_size;
+  const int last = (c->ring_start + K - 1) % K;
+  TailHeads th;
+  memset(&th, 0, sizeof(th));
+  th.nheads = c->nheads; th.NH = c->NH;
+  int col = 0;
+  for (int h = 0; h < c->nheads; ++h) {
+    const HeadPlan& hp = c->heads_plan[h];
+    HeadSpec& hs = th.h[h];
+    hs.col = col; hs.width = hp.width; hs.kind = hp.kind; hs.slot = hp.slot; hs.aux = hp.aux;
+    hs.weight = hp.aux ? cfg.lambda_aux : 1.f;
+    hs.w = P(c, hp.p_w); hs.b = P(c, hp.p_b);
+    hs.gw = c->grad ? GR(c, hp.p_w) : nullptr; hs.gb = c->grad ? GR(c, hp.p_b) : nullptr;
+    col += hp.width;
+    if (!b) continue;
+    const std::string nm = hp.name;
+    if (nm == "pred_aux_ee") { hs.target = b->ee_state; hs.tstride = K * 7; hs.toff = last * 7; }
+    else if (nm == "pred_aux_obj") { hs.target = b->obj_state; hs.tstride = K * 7; hs.toff = last * 7; }
+    else if (nm == "pred_cmd_vel") { hs.target = b->vel_target; hs.tstride = cfg.dim_jnt_state; hs.toff = 0; }
+    else if (nm == "pred_cmd_grp") { hs.target = b->grp_target; hs.tstride = cfg.dim_grp_command; hs.toff = 0; }
+    else if (nm == "logits_cmd_grp") { hs.target = b->cmd; hs.tstride = 4; hs.toff = 3; }
+    else if (cfg.control_mode == GEECO_CTRL_VELOCITY) { hs.target = b->ee_target; hs.tstride = 7; hs.toff = 0; }   // pred_cmd_ee
+    else { hs.target = b->cmd; hs.tstride = 4; hs.toff = 0; }                                                       // pred_cmd_ee
+  }
+  return th;
 }
-static TailGrads tail_grads(geeco_ctx* c) {
-  TailGrads p;
-  p.w_fc1 = GR(c, c->p_fc1_w); p.b_fc1 = GR(c, c->p_fc1_b);
-  p.w_cmd_ee = GR(c, c->p_head_w[0]); p.b_cmd_ee = GR(c, c->p_head_b[0]);
-  p.w_grp = GR(c, c->p_head_w[1]); p.b_grp = GR(c, c->p_head_b[1]);
-  p.w_aux_ee = GR(c, c->p_head_w[2]); p.b_aux_ee = GR(c, c->p_head_b[2]);
-  p.w_aux_obj = GR(c, c->p_head_w[3]); p.b_aux_obj = GR(c, c->p_head_b[3]);
-  return p;
+
+static StateMap state_map(geeco_ctx* c, const float* y8, float* g8) {
+  const geeco_config& cfg = c->cfg;
+  StateMap sm;
+  memset(&sm, 0, sizeof(sm));
+  sm.variant = c->variant; sm.N = cfg.batch_size; sm.T = c->T; sm.K = cfg.window_size; sm.J = cfg.dim_jnt_state;
+  sm.D0 = c->dim8[0]; sm.D1 = c->dim8[1]; sm.D2 = c->variant == VAR_SEQ_DYNDIFF ? c->dim8[1] : c->dim8[2];
+  sm.xdim = c->xdim; sm.per = c->xdim / 4; sm.Hl = cfg.dim_h_lstm; sm.ld = c->xdim + cfg.dim_h_lstm;
+  const LayerPlan& L8 = c->layers[7];
+  for (int e = 0; e < c->G; ++e) { sm.y[e] = y8 + L8.act_off[e]; sm.g[e] = g8 ? g8 + L8.act_off[e] : nullptr; }
+  sm.ring_start = c->ring_start;
+  return sm;
 }
 
 static int check_batch(const geeco_ctx* c, const geeco_batch* b, bool need_labels) {
   if (!c || !c->bound) { geeco_set_error("context not bound (call geeco_bind first)"); return GEECO_ERR_STATE; }
-  if (!b || !b->rgb || !b->target_rgb || !b->jnt_state) { geeco_set_error("batch: rgb / target_rgb / jnt_state must be given"); return GEECO_ERR_INVALID; }
-  if (need_labels && (!b->cmd || !b->ee_state || !b->obj_state)) { geeco_set_error("batch: cmd / ee_state / obj_state needed for the losses"); return GEECO_ERR_INVALID; }
+  const bool goal = c->cfg.goal_condition == GEECO_GOAL_TARGET;
+  if (!b || !b->rgb || !b->jnt_state || (goal && !b->target_rgb)) { geeco_set_error("batch: rgb / target_rgb / jnt_state must be given"); return GEECO_ERR_INVALID; }
+  if (b->ring_start < 0 || b->ring_start >= c->cfg.window_size) { geeco_set_error("batch: ring_start %d outside [0,%d)", b->ring_start, c->cfg.window_size); return GEECO_ERR_INVALID; }
+  if (need_labels) {
+    const bool vel = c->cfg.control_mode == GEECO_CTRL_VELOCITY;
+    if (!b->ee_state || !b->obj_state || (!vel && !b->cmd) || (vel && (!b->vel_target || !b->ee_target || !b->grp_target))) {
+      geeco_set_error(vel ? "batch: vel_target / ee_target / grp_target / ee_state / obj_state needed for the losses"
+                          : "batch: cmd / ee_state / obj_state needed for the losses");
+      return GEECO_ERR_INVALID;
+    }
+  }
   return GEECO_OK;
 }
 
 // conv stack forward, fp32
 static int encoders_fwd_f32(geeco_ctx* c, cudaStream_t st) {
-  const int N = c->cfg.batch_size;
+  const int M = c->M, G = c->G;
   const float* src = (const float*)c->x0;
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     if (L.grouped) {
-      GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[0], L.stride, N);
-      g.b_group_stride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
-      g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
-      int rc = launch_gemm_nn_f32(g, src, P(c, L.p_w[0]), P(c, L.p_b[0]), nullptr, (float*)L.y, 3, EPI_BIAS_RELU, st);
+      GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[0], L.stride, M);
+      g.b_group_stride = w_group_stride(c, L);
+      g.bias_group_stride = b_group_stride(c, L);
+      int rc = launch_gemm_nn_f32(g, src, P(c, L.p_w[0]), P(c, L.p_b[0]), nullptr, (float*)L.y, G, EPI_BIAS_RELU, st);
       if (rc) return rc;
     } else {
-      for (int e = 0; e < 3; ++e) {
-        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
-        const float* s = src + (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+      for (int e = 0; e < G; ++e) {
+        GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, M);
+        const float* s = src + (long long)e * M * L.Hin * L.Hin * L.Cin_pad;
         int rc = launch_gemm_nn_f32(g, s, P(c, L.p_w[e]), P(c, L.p_b[e]), nullptr, (float*)L.y + L.act_off[e], 1, EPI_BIAS_RELU, st);
         if (rc) return rc;
       }
@@ -542,34 +646,44 @@ static int encoders_fwd_f32(geeco_ctx* c, cudaStream_t st) {
 static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, const float* y8, bool with_loss,
                         cudaStream_t st) {
   const geeco_config& cfg = c->cfg;
-  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm;
+  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm, T = c->T, ld = c->xdim + Hl;
   TailDims d = tail_dims(c);
-  LayerPlan& L8 = c->layers[7];
   const bool carry = cfg.carry_state != 0;
-  int rc = launch_build_state(d, y8 + L8.act_off[0], y8 + L8.act_off[1], y8 + L8.act_off[2], b->jnt_state,
-                              carry ? c->m_carry : nullptr, c->state, st);
+  const unsigned char* rmask = carry ? b->reset_mask : nullptr;
+  c->reset_mask = rmask;
+  StateMap sm = state_map(c, y8, nullptr);
+  int rc = launch_build_states(sm, b->jnt_state, carry ? c->m_carry : nullptr, rmask, c->states, st);
   if (rc) return rc;
-  // in the reference-faithful mode m_prev == 0, so the h-rows of the kernel contribute nothing: K = xdim
-  rc = launch_lstm_gates(c->state, c->xdim + Hl, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, N,
-                         carry ? c->xdim + Hl : c->xdim, 4 * Hl, st);
-  if (rc) return rc;
-  rc = launch_lstm_cell(N, Hl, c->gates, carry ? c->c_carry : nullptr, c->c_cur, c->m_cur, c->state_out, st);
-  if (rc) return rc;
+  // lstm_decoder's loop over feat_list (graph.py:223-225): T = 1 for the dynimg graph, K for the sequence graphs
+  for (int t = 0; t < T; ++t) {
+    const bool has_prev = t > 0 || carry;
+    float* gates_t = c->gates + (long long)t * N * 4 * Hl;
+    // without a previous state m_prev == 0 and the h-rows of the kernel contribute nothing: K = xdim
+    rc = launch_lstm_gates(c->states + (long long)t * N * ld, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), gates_t,
+                           c->gates_partial, N, has_prev ? ld : c->xdim, 4 * Hl, st);
+    if (rc) return rc;
+    const float* c_prev = t > 0 ? c->c_seq + (long long)(t - 1) * N * Hl : (carry ? c->c_carry : nullptr);
+    rc = launch_lstm_cell(N, Hl, gates_t, c_prev, t == 0 ? rmask : nullptr, c->c_seq + (long long)t * N * Hl,
+                          c->m_seq + (long long)t * N * Hl, t == T - 1 ? c->state_out : nullptr,
+                          t + 1 < T ? c->states + (long long)(t + 1) * N * ld + c->xdim : nullptr, ld, st);
+    if (rc) return rc;
+  }
   if (with_loss && cfg.l2_regularizer > 0.f) {
     rc = launch_l2_term(c->theta, c->arena_floats, cfg.l2_regularizer, c->sc, st);
     if (rc) return rc;
   }
-  rc = launch_tail_fwd(d, tail_params(c), c->m_cur, c->fc1, c->heads, b->cmd, b->ee_state, b->obj_state, c->loss_parts,
-                       c->dheads, with_loss ? 1 : 0, st);
+  TailHeads th = tail_heads(c, with_loss ? b : nullptr);
+  rc = launch_tail_fwd(d, th, P(c, c->p_fc1_w), P(c, c->p_fc1_b), c->m_seq + (long long)(T - 1) * N * Hl, c->fc1, c->heads,
+                       c->loss_parts, c->dheads, with_loss ? 1 : 0, st);
   if (rc) return rc;
   if (with_loss) {
-    rc = launch_loss_reduce(d, c->loss_parts, cfg.l2_regularizer > 0.f ? c->sc + 2 : nullptr, c->losses, st);
+    rc = launch_loss_reduce(d, th, c->loss_parts, cfg.l2_regularizer > 0.f ? c->sc + 2 : nullptr, c->losses, st);
     if (rc) return rc;
   }
   if (out) {
     const float* src[4] = {c->heads, c->fc1, c->state_out, c->losses};
     float* dst[4] = {out->heads, out->fc1, out->lstm_state, with_loss ? out->losses : nullptr};
-    const long long n[4] = {(long long)N * c->NH, (long long)N * cfg.dim_h_fc, (long long)N * 2 * Hl, 8};
+    const long long n[4] = {(long long)N * c->NH, (long long)N * cfg.dim_h_fc, (long long)N * 2 * Hl, GEECO_NUM_LOSS_SLOTS};
     rc = launch_copy_outputs(src, dst, n, st);
     if (rc) return rc;
   }
@@ -578,9 +692,10 @@ static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
 
 static int carry_update(geeco_ctx* c, cudaStream_t st) {
   if (!c->cfg.carry_state) return GEECO_OK;
+  const long long last = (long long)(c->T - 1) * c->cfg.batch_size * c->cfg.dim_h_lstm;
   const size_t bytes = sizeof(float) * c->cfg.batch_size * c->cfg.dim_h_lstm;
-  CUDA_TRY(cudaMemcpyAsync(c->c_carry, c->c_cur, bytes, cudaMemcpyDeviceToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->m_carry, c->m_cur, bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->c_carry, c->c_seq + last, bytes, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->m_carry, c->m_seq + last, bytes, cudaMemcpyDeviceToDevice, st));
   return GEECO_OK;
 }
 
@@ -591,12 +706,21 @@ static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
     geeco_set_error("batch: frame_format %d is neither GEECO_FRAMES_F32 nor GEECO_FRAMES_U8", b->frame_format);
     return GEECO_ERR_INVALID;
   }
+  c->ring_start = b->ring_start;
   int rc = bf16 ? repack_fork_bf16(c, st) : GEECO_OK;
   if (rc) return rc;
-  rc = launch_preprocess_geecof(b->rgb, b->target_rgb, b->frame_format == GEECO_FRAMES_U8, c->x0, bf16 ? 1 : 0,
-                                    c->CP, out ? out->dynbuff : nullptr,
-                                    out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
-                                    cfg.img_width, cfg.img_channels, c->alpha, 0, st);
+  const int u8 = b->frame_format == GEECO_FRAMES_U8;
+  if (c->variant == VAR_GEECOF) {
+    rc = launch_preprocess_geecof(b->rgb, b->target_rgb, u8, c->x0, bf16 ? 1 : 0, c->CP, out ? out->dynbuff : nullptr,
+                                  out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
+                                  cfg.img_width, cfg.img_channels, c->alpha, 0, b->ring_start, st);
+  } else {
+    const int with_tgt = c->variant == VAR_SEQ_CONSTANT || c->variant == VAR_SEQ_RESIDUAL;
+    const int with_diff = c->variant == VAR_SEQ_DYNDIFF;
+    rc = launch_preprocess_seq(b->rgb, b->target_rgb, u8, c->x0, bf16 ? 1 : 0, c->CP, c->mm_scratch,
+                               out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
+                               cfg.img_width, cfg.img_channels, with_tgt, with_diff, b->ring_start, st);
+  }
   if (rc) return rc;
   const float* y8;
   if (bf16) {
@@ -614,7 +738,7 @@ static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
 }
 
 extern "C" int geeco_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, void* stream) {
-  const bool with_loss = b && b->cmd && out && out->losses;
+  const bool with_loss = b && (b->cmd || b->vel_target) && out && out->losses;
   int rc = check_batch(c, b, with_loss);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -634,16 +758,16 @@ extern "C" int geeco_step_forward(geeco_ctx* c, const geeco_batch* b, const geec
 }
 
 static int conv_layer_bwd_f32(geeco_ctx* c, int l, cudaStream_t st) {
-  const int N = c->cfg.batch_size;
+  const int M = c->M, G = c->G;
   LayerPlan& L = c->layers[l];
   const float* xin = l == 0 ? (const float*)c->x0 : (const float*)c->layers[l - 1].y;
-  const int ngroups = L.grouped ? 3 : 1;
-  for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
-    const long long in_off = L.grouped ? 0 : (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
+  const int ngroups = L.grouped ? G : 1;
+  for (int e = 0; e < (L.grouped ? 1 : G); ++e) {
+    const long long in_off = L.grouped ? 0 : (long long)e * M * L.Hin * L.Hin * L.Cin_pad;
     const float* gy = (const float*)L.g + (L.grouped ? 0 : L.act_off[e]);
-    GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, N);
-    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
-    const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+    GatherGeom g = conv_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cin_real, L.Cout[e], L.stride, M);
+    const long long wstride = w_group_stride(c, L);
+    const long long bstride = b_group_stride(c, L);
     int rc = launch_gemm_tn_f32(g, xin + in_off, gy, GR(c, L.p_w[e]), GR(c, L.p_b[e]), c->partial, c->partial_cap,
                                 ngroups, wstride, bstride, st);
     if (rc) return rc;
@@ -651,7 +775,7 @@ static int conv_layer_bwd_f32(geeco_ctx* c, int l, cudaStream_t st) {
     for (int py = 0; py < L.stride; ++py)
       for (int px = 0; px < L.stride; ++px) {
         GatherGeom dg;
-        if (!conv_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, py, px, N, &dg)) continue;
+        if (!conv_dgrad_geom(L.Hin, L.Hin, L.Cin_real, L.Cout[e], L.stride, py, px, M, &dg)) continue;
         dg.b_group_stride = wstride;
         rc = launch_gemm_nn_f32(dg, gy, P(c, L.p_w[e]), nullptr, xin + in_off, (float*)c->layers[l - 1].g + in_off,
                                 ngroups, EPI_MASK, st);
@@ -661,30 +785,58 @@ static int conv_layer_bwd_f32(geeco_ctx* c, int l, cudaStream_t st) {
   return GEECO_OK;
 }
 
+// backward of the tail: heads + fc1 -> dL/dm_T, back-propagation through the T LSTM steps, d(kernel) / d(bias) as ONE
+// split GEMM over the T*N state rows, d(states) scattered into the conv8 gradients
+static int tail_backward(geeco_ctx* c, cudaStream_t st) {
+  const geeco_config& cfg = c->cfg;
+  const bool bf16 = cfg.precision == GEECO_BF16;
+  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm, T = c->T, ld = c->xdim + Hl;
+  const bool carry = cfg.carry_state != 0;
+  TailDims d = tail_dims(c);
+  TailHeads th = tail_heads(c, nullptr);
+  const float* m_last = c->m_seq + (long long)(T - 1) * N * Hl;
+  int rc;
+  if (T == 1) {
+    rc = launch_tail_bwd(d, th, P(c, c->p_fc1_w), GR(c, c->p_fc1_w), GR(c, c->p_fc1_b), m_last, c->fc1, c->dheads, c->gates,
+                         carry ? c->c_carry : nullptr, c->reset_mask, c->dfc1, c->dgates, nullptr, st);
+    if (rc) return rc;
+    rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstates, N, c->xdim, 4 * Hl, ld, st);
+    if (rc) return rc;
+  } else {
+    rc = launch_tail_bwd(d, th, P(c, c->p_fc1_w), GR(c, c->p_fc1_w), GR(c, c->p_fc1_b), m_last, c->fc1, c->dheads, nullptr,
+                         nullptr, nullptr, c->dfc1, nullptr, c->dm_last, st);
+    if (rc) return rc;
+    for (int t = T - 1; t >= 0; --t) {
+      const bool last = t == T - 1;
+      float* dgates_t = c->dgates + (long long)t * N * 4 * Hl;
+      float* dstate_t = c->dstates + (long long)t * N * ld;
+      const float* c_prev = t > 0 ? c->c_seq + (long long)(t - 1) * N * Hl : (carry ? c->c_carry : nullptr);
+      // d(m_t): from the decoder for the last step, else the m part of d(state_{t+1})
+      rc = launch_lstm_cell_bwd(N, Hl, c->gates + (long long)t * N * 4 * Hl, c_prev, t == 0 ? c->reset_mask : nullptr,
+                                last ? c->dm_last : dstate_t + (long long)N * ld + c->xdim, last ? Hl : ld,
+                                last ? nullptr : c->dc, dgates_t, c->dc, st);
+      if (rc) return rc;
+      // d(state_t) = d(gates_t) @ kernel^T: the x part for the encoders; for t > 0 also the m part, which feeds step t-1
+      rc = launch_lstm_dstate(dgates_t, P(c, c->p_lstm_w), dstate_t, N, t > 0 ? ld : c->xdim, 4 * Hl, ld, st);
+      if (rc) return rc;
+    }
+  }
+  GatherGeom gw = dense_geom(T * N, ld, 4 * Hl, 4 * Hl, 0);
+  rc = launch_gemm_tn_f32(gw, c->states, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), c->partial, c->partial_cap, 1, 0, 0, st);
+  if (rc) return rc;
+  LayerPlan& L8 = c->layers[7];
+  StateMap sm = state_map(c, bf16 ? c->y8_f32 : (const float*)L8.y, bf16 ? c->g8_f32 : (float*)L8.g);
+  return launch_scatter_dstates(sm, c->dstates, st);
+}
+
 extern "C" int geeco_step_backward(geeco_ctx* c, int32_t bucket, void* stream) {
   if (!c || !c->bound || !c->fwd_done) { geeco_set_error("step_backward: call geeco_step_forward first"); return GEECO_ERR_STATE; }
   if (bucket < 0 || bucket > 2) { geeco_set_error("step_backward: bucket %d outside [0,2]", bucket); return GEECO_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
-  const geeco_config& cfg = c->cfg;
-  const bool bf16 = cfg.precision == GEECO_BF16;
-  const int N = cfg.batch_size, Hl = cfg.dim_h_lstm;
+  const bool bf16 = c->cfg.precision == GEECO_BF16;
   int rc;
   if (bucket == 0) {
-    TailDims d = tail_dims(c);
-    const bool carry = cfg.carry_state != 0;
-    rc = launch_tail_bwd(d, tail_params(c), tail_grads(c), c->m_cur, c->fc1, c->dheads, c->gates,
-                         carry ? c->c_carry : nullptr, c->dfc1, c->dgates, st);
-    if (rc) return rc;
-    GatherGeom gw = dense_geom(N, c->xdim + Hl, 4 * Hl, 4 * Hl, 0);
-    rc = launch_gemm_tn_f32(gw, c->state, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), c->partial, c->partial_cap, 1, 0, 0, st);
-    if (rc) return rc;
-    rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstate, N, c->xdim, 4 * Hl, c->xdim, st);
-    if (rc) return rc;
-    LayerPlan& L8 = c->layers[7];
-    const float* y8 = bf16 ? c->y8_f32 : (const float*)L8.y;
-    float* g8 = bf16 ? c->g8_f32 : (float*)L8.g;
-    rc = launch_scatter_dstate(d, c->dstate, c->xdim, y8 + L8.act_off[0], y8 + L8.act_off[1], y8 + L8.act_off[2],
-                               g8 + L8.act_off[0], g8 + L8.act_off[1], g8 + L8.act_off[2], st);
+    rc = tail_backward(c, st);
     if (rc) return rc;
   }
   const int lhi = bucket == 0 ? 7 : (bucket == 1 ? 3 : 1);
@@ -722,6 +874,15 @@ extern "C" int geeco_train_step(geeco_ctx* c, const geeco_batch* b, const geeco_
   return geeco_step_update(c, grad_scale, stream);
 }
 
+extern "C" int geeco_ring_push(void* ring, const void* frame, const uint8_t* fresh, int32_t N, int32_t K, int64_t row_bytes,
+                               int32_t slot, void* stream) {
+  if (!ring || !frame || K < 1 || slot < 0 || slot >= K || row_bytes <= 0 || (row_bytes & 3)) {
+    geeco_set_error("ring_push: bad arguments (K=%d slot=%d row_bytes=%lld)", K, slot, (long long)row_bytes);
+    return GEECO_ERR_INVALID;
+  }
+  return launch_ring_push(ring, frame, fresh, N, K, row_bytes, slot, (cudaStream_t)stream);
+}
+
 extern "C" int geeco_debug_buffer(const geeco_ctx* c, const char* name, void** ptr, int64_t* numel, int32_t* dtype) {
   if (!c || !c->bound || !name || !ptr || !numel || !dtype) { geeco_set_error("debug_buffer: bad arguments"); return GEECO_ERR_INVALID; }
   const geeco_config& cfg = c->cfg;
@@ -729,19 +890,21 @@ extern "C" int geeco_debug_buffer(const geeco_ctx* c, const char* name, void** p
   const int act_dt = cfg.precision == GEECO_BF16 ? 1 : 0;
   *dtype = 0;
   std::string s(name);
-  if (s == "x0") { *ptr = c->x0; *numel = 3ll * N * cfg.img_height * cfg.img_width * c->CP; *dtype = act_dt; return GEECO_OK; }
+  if (s == "x0") { *ptr = c->x0; *numel = (long long)c->G * c->M * cfg.img_height * cfg.img_width * c->CP; *dtype = act_dt; return GEECO_OK; }
   if (s.size() == 2 && (s[0] == 'y' || s[0] == 'g') && s[1] >= '1' && s[1] <= '8') {
     const LayerPlan& L = c->layers[s[1] - '1'];
     *ptr = s[0] == 'y' ? L.y : L.g; *numel = L.act_elems; *dtype = act_dt;
     if (!*ptr) { geeco_set_error("debug_buffer: %s not allocated", name); return GEECO_ERR_INVALID; }
     return GEECO_OK;
   }
+  const int T = c->T;
+  const long long last = (long long)(T - 1) * N * Hl;
   struct { const char* n; float* p; long long cnt; } tab[] = {
-      {"state", c->state, (long long)N * (c->xdim + Hl)}, {"gates", c->gates, (long long)N * 4 * Hl},
-      {"c", c->c_cur, (long long)N * Hl}, {"m", c->m_cur, (long long)N * Hl}, {"fc1", c->fc1, (long long)N * cfg.dim_h_fc},
+      {"state", c->states, (long long)T * N * (c->xdim + Hl)}, {"gates", c->gates, (long long)T * N * 4 * Hl},
+      {"c", c->c_seq + last, (long long)N * Hl}, {"m", c->m_seq + last, (long long)N * Hl}, {"fc1", c->fc1, (long long)N * cfg.dim_h_fc},
       {"heads", c->heads, (long long)N * c->NH}, {"dheads", c->dheads, (long long)N * c->NH},
-      {"dfc1", c->dfc1, (long long)N * cfg.dim_h_fc}, {"dgates", c->dgates, (long long)N * 4 * Hl},
-      {"dstate", c->dstate, (long long)N * c->xdim}, {"losses", c->losses, 8}, {"sc", c->sc, 8},
+      {"dfc1", c->dfc1, (long long)N * cfg.dim_h_fc}, {"dgates", c->dgates, (long long)T * N * 4 * Hl},
+      {"dstate", c->dstates, (long long)T * N * (c->xdim + Hl)}, {"losses", c->losses, GEECO_NUM_LOSS_SLOTS}, {"sc", c->sc, 8},
       {"y8_f32", c->y8_f32, c->layers[7].act_elems}, {"g8_f32", c->g8_f32, c->layers[7].act_elems}};
   for (auto& t : tab)
     if (s == t.n) {

@@ -13,32 +13,6 @@
 #include "plan.cuh"
 #include "../../include/geeco_b200.h"
 
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
-
-// d(gates_t) and d(c_{t-1}) from d(m_t) (row stride ld_dm) and the d(c_t) that flows back from step t+1
-__global__ void lstm_cell_bwd_kernel(int N, int Hl, const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                     const float* __restrict__ dm, int ld_dm, const float* __restrict__ dc_in,
-                                     float* __restrict__ dgates, float* __restrict__ dc_prev) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * Hl) return;
-  const int n = idx / Hl, i = idx - n * Hl;
-  const float* gr = gates + (long long)n * 4 * Hl;
-  const float gi = gr[i], gj = gr[Hl + i], gf = gr[2 * Hl + i], go = gr[3 * Hl + i];
-  const float cp = c_prev ? c_prev[idx] : 0.f;
-  const float si = sigm(gi), tj = tanhf(gj), sf = sigm(gf + 1.0f), so = sigm(go);
-  const float c = sf * cp + si * tj;
-  const float tc = tanhf(c);
-  const float dmv = dm[(long long)n * ld_dm + i];
-  const float dso = dmv * tc;
-  const float dc = dmv * so * (1.f - tc * tc) + (dc_in ? dc_in[idx] : 0.f);
-  float* dg = dgates + (long long)n * 4 * Hl;
-  dg[i] = dc * tj * si * (1.f - si);
-  dg[Hl + i] = dc * si * (1.f - tj * tj);
-  dg[2 * Hl + i] = dc * cp * sf * (1.f - sf);
-  dg[3 * Hl + i] = dso * so * (1.f - so);
-  dc_prev[idx] = dc * sf;
-}
-
 struct SeqScratch {
   float *states, *dgates, *dstate, *dc, *partial;
   long long partial_cap, total;
@@ -109,8 +83,8 @@ extern "C" int geeco_lstm_seq_fwd(const float* x, const float* kernel, const flo
     float* gates_t = gates + (long long)t * N * 4 * Hl;
     rc = launch_lstm_gates(state_t, ld, kernel, bias, gates_t, s.partial, N, ld, 4 * Hl, st);
     if (rc) return rc;
-    rc = launch_lstm_cell(N, Hl, gates_t, t ? c + (long long)(t - 1) * N * Hl : nullptr, c + (long long)t * N * Hl,
-                          m + (long long)t * N * Hl, nullptr, st);
+    rc = launch_lstm_cell(N, Hl, gates_t, t ? c + (long long)(t - 1) * N * Hl : nullptr, nullptr, c + (long long)t * N * Hl,
+                          m + (long long)t * N * Hl, nullptr, nullptr, 0, st);
     if (rc) return rc;
   }
   return GEECO_OK;
@@ -136,11 +110,9 @@ extern "C" int geeco_lstm_seq_bwd(const float* x, const float* kernel, const flo
     const bool last = t == K - 1;
     float* dgates_t = s.dgates + (long long)t * N * 4 * Hl;
     // d(m_t): from the decoder for the last step, else the m part of d(state_{t+1}) left in s.dstate
-    lstm_cell_bwd_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(
-        N, Hl, gates + (long long)t * N * 4 * Hl, t ? c + (long long)(t - 1) * N * Hl : nullptr,
-        last ? dm_last : s.dstate + xdim, last ? Hl : ld, last ? nullptr : s.dc, dgates_t, s.dc);
-    geeco_count_launch(1);
-    CUDA_TRY(cudaGetLastError());
+    rc = launch_lstm_cell_bwd(N, Hl, gates + (long long)t * N * 4 * Hl, t ? c + (long long)(t - 1) * N * Hl : nullptr, nullptr,
+                              last ? dm_last : s.dstate + xdim, last ? Hl : ld, last ? nullptr : s.dc, dgates_t, s.dc, st);
+    if (rc) return rc;
     if (t > 0 || dx) {
       // d(state_t) = d(gates_t) @ kernel^T over all xdim + Hl kernel rows (x part -> dx_t, m part -> step t-1)
       rc = launch_lstm_dstate(dgates_t, kernel, s.dstate, N, ld, 4 * Hl, ld, st);

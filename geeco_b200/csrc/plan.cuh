@@ -8,11 +8,11 @@ struct LayerPlan {
   int Hin, Hout, stride;
   int Cin_real, Cin_pad;
   int Cout[3];
-  bool grouped;               // the three encoders share shapes -> one grouped launch
+  bool grouped;               // all encoder groups share shapes -> one grouped launch
   int p_w[3], p_b[3];         // parameter-table indices
   long long act_off[3];       // element offset of encoder e inside y / g
   long long act_elems;
-  void* y;                    // post-ReLU output  [3][N][Hout][Hout][Cout]
+  void* y;                    // post-ReLU output  [G][M][Hout][Hout][Cout]
   void* g;                    // dL/d(pre-activation), same layout (training only)
   void* mbits;                // bf16 training, conv1-conv7: 1-bit ReLU mask of y, uint16 per (pixel, 16 channels)
   // bf16 mode: packed weight copies (see step_bf16.cu)
@@ -21,6 +21,8 @@ struct LayerPlan {
   int Kpad;
 };
 
+struct HeadPlan { const char* name; int width, kind, slot, aux; int p_w, p_b; };
+
 struct geeco_ctx {
   geeco_config cfg;
   std::vector<geeco_param_desc> params;
@@ -28,20 +30,39 @@ struct geeco_ctx {
   long long bucket_end[3] = {0, 0, 0};
   size_t workspace_bytes = 0;
   bool bound = false, weights_dirty = true, fwd_done = false, uniform8 = true;
+  // graph variant (tail.cuh: VAR_*): G encoder weight sets ("groups") of M images each, T LSTM steps
+  int variant = 0, G = 3, M = 0, T = 1;
+  int dim8[3] = {0, 0, 0};          // conv8 width per group
+  const char* enc_scope[3] = {nullptr, nullptr, nullptr};
+  const char* dec_scope = nullptr;
+  int nheads = 0;
+  HeadPlan heads_plan[5];
   int CP = 4, NH = 12, xdim = 0;
   float alpha[16];
   float host_sc[8];
   LayerPlan layers[8];
-  int p_lstm_w, p_lstm_b, p_fc1_w, p_fc1_b, p_head_w[4], p_head_b[4];
+  int p_lstm_w, p_lstm_b, p_fc1_w, p_fc1_b;
   float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr;
   void* x0 = nullptr;
-  float *state, *gates, *c_cur, *m_cur, *state_out, *c_carry, *m_carry, *fc1, *heads, *loss_parts, *dheads, *losses, *sc;
+  // tail buffers: states [T][N][xdim+Hl], gates [T][N][4Hl], c / m [T][N][Hl]
+  float *states, *gates, *c_seq, *m_seq, *state_out, *c_carry, *m_carry, *fc1, *heads, *loss_parts, *dheads, *losses, *sc;
   float *y8_f32 = nullptr, *g8_f32 = nullptr, *gates_partial = nullptr;
-  float *dfc1 = nullptr, *dgates = nullptr, *dstate = nullptr, *partial = nullptr;
+  float *dfc1 = nullptr, *dgates = nullptr, *dstates = nullptr, *dm_last = nullptr, *dc = nullptr, *partial = nullptr;
+  int* mm_scratch = nullptr;
   long long partial_cap = 0;
+  const unsigned char* reset_mask = nullptr;   // of the batch of the last forward (carry_state)
+  int ring_start = 0;
   // bf16 extras
   void* bf16_ws = nullptr;
 };
+
+// group stride helpers: distance (floats) between the kernels / biases of consecutive encoder groups of layer L
+static inline long long w_group_stride(const geeco_ctx* c, const LayerPlan& L) {
+  return c->G > 1 ? c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset : 0;
+}
+static inline long long b_group_stride(const geeco_ctx* c, const LayerPlan& L) {
+  return c->G > 1 ? c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset : 0;
+}
 
 GatherGeom conv_fwd_geom(int H, int W, int Cs, int Cw, int Cout, int stride, int imgs_per_group);
 bool conv_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, GatherGeom* out);

@@ -236,7 +236,7 @@ template <typename InT, typename OutT, int CP, int C, int K>
 __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
-    AlphaTab al) {
+    AlphaTab al, int ring_start) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
   __shared__ float s_mm[2 * 2 * RP_MAX_CLUSTER];
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, k * img4 + u * C + j, s_lut);
+      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, ((k + ring_start) % K) * img4 + u * C + j, s_lut);
 #pragma unroll
     for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
     float cur[4 * C];
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     for (int j = 0; j < C; ++j) {
       const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
       // same two operations on the same operands as in pass 1: bit-identical difference image
-      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)(K - 1) * img4 + u * C + j, s_lut);
+      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)((K - 1 + ring_start) % K) * img4 + u * C + j, s_lut);
       const float4 tj = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
       const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, c4), 0.5f, tj), mn1, rng1);
       e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
@@ -395,7 +395,7 @@ int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, in
 
 template <typename InT, typename OutT, int CP, int C>
 static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
-                        const AlphaTab& al_in, int cluster_hint, cudaStream_t st) {
+                        const AlphaTab& al_in, int cluster_hint, int ring_start, cudaStream_t st) {
   long long units = (long long)H * W / 4;
   if (cluster_hint <= 0) { if (const char* e = getenv("GEECO_PRE_CLUSTER")) cluster_hint = atoi(e); }
   int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
@@ -408,15 +408,16 @@ static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, flo
   OutT* x = reinterpret_cast<OutT*>(x0);
   AlphaTab al = al_in;
   void* args[] = {(void*)&rgb, (void*)&tgt, (void*)&x, (void*)&db, (void*)&dd, (void*)&N, (void*)&units,
-                  (void*)&per_units, (void*)&al};
+                  (void*)&per_units, (void*)&al, (void*)&ring_start};
   RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<InT, OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
   return GEECO_OK;
 }
 
 int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP,
                              float* dynbuff_f32, float* dyndiff_f32, int N, int K, int H, int W, int C,
-                             const float* alpha_host, int cluster_hint, cudaStream_t st) {
+                             const float* alpha_host, int cluster_hint, int ring_start, cudaStream_t st) {
   if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
+  if (ring_start < 0 || ring_start >= K) { geeco_set_error("preprocess: ring_start %d outside [0,%d)", ring_start, K); return GEECO_ERR_INVALID; }
   if (N <= 0) return GEECO_OK;
   if (N > 65535) { geeco_set_error("preprocess: N=%d > 65535", N); return GEECO_ERR_INVALID; }
   if (K > 8) { geeco_set_error("preprocess: fused path supports window_size <= 8 (got %d)", K); return GEECO_ERR_INVALID; }
@@ -424,9 +425,9 @@ int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, vo
   for (int k = 0; k < K; ++k) al.a[k] = alpha_host[k];
 #define PRE_CASE(T, cp, c)                                                                                        \
   return frames_u8 ? launch_pre_t<unsigned char, T, cp, c>((const unsigned char*)rgb, (const unsigned char*)tgt, x0,  \
-                                                           dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, st) \
+                                                           dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, st) \
                    : launch_pre_t<float, T, cp, c>((const float*)rgb, (const float*)tgt, x0, dynbuff_f32,             \
-                                                   dyndiff_f32, N, K, H, W, al, cluster_hint, st)
+                                                   dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, st)
   if (!out_bf16 && CP == 4 && C == 3) PRE_CASE(float, 4, 3);
   if (!out_bf16 && CP == 4 && C == 4) PRE_CASE(float, 4, 4);
   if (out_bf16 && CP == 8 && C == 3) PRE_CASE(__nv_bfloat16, 8, 3);
@@ -434,6 +435,124 @@ int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, vo
   if (out_bf16 && CP == 4 && C == 3) PRE_CASE(__nv_bfloat16, 4, 3);
   if (out_bf16 && CP == 4 && C == 4) PRE_CASE(__nv_bfloat16, 4, 4);
 #undef PRE_CASE
+  geeco_set_error("preprocess: unsupported (bf16=%d, CP=%d, C=%d)", out_bf16, CP, C);
+  return GEECO_ERR_INVALID;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// pre-process of the graphs that feed every frame through the encoder (`--proc_obs sequence`, graph.py:360-385, and the
+// unconditional e2e_vmc, :304-309).  Group 0 of x0 = the K frames (+ the target frame for --proc_tgt constant / residual,
+// :352-355), step-major: image t*N + n = frame t of sample n, channel-padded, OutT.  With --proc_tgt dyndiff group 1 =
+// dynimg([frame_t, target]) (:371-376): two passes (per-image min / max through ordered-int atomics, then the
+// normalised write); both evaluate 0.5*tgt - 0.5*frame with the same two roundings, so they see the same values.
+// ---------------------------------------------------------------------------------------
+template <typename InT, typename OutT, int CP, int C>
+__global__ void __launch_bounds__(256) seq_frames_kernel(const InT* __restrict__ rgb, const InT* __restrict__ tgt,
+                                                         OutT* __restrict__ x0, int* __restrict__ mm, int N, int K,
+                                                         int with_diff, long long units, int ring_start) {
+  __shared__ float s_lut[256];
+  if (sizeof(InT) == 1) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s_lut[b] = __fdiv_rn((float)b, 255.f);
+    __syncthreads();
+  }
+  const int img = blockIdx.y, t = img / N, n = img - t * N;
+  const long long img4 = units * C;
+  const InT* fbase = t < K ? rgb + ((long long)n * K + (t + ring_start) % K) * img4 * 4 : tgt + (long long)n * img4 * 4;
+  const InT* tbase = tgt ? tgt + (long long)n * img4 * 4 : nullptr;
+  OutT* xo = x0 + (long long)img * units * 4 * CP;
+  const bool diff = with_diff && t < K;
+  float mn = FLT_MAX, mx = -FLT_MAX;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+    float e[4 * C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float4 v = FrameLoad<InT>::at(fbase, u * C + j, s_lut);
+      e[j * 4] = v.x; e[j * 4 + 1] = v.y; e[j * 4 + 2] = v.z; e[j * 4 + 3] = v.w;
+      if (diff) f4_minmax(f4_axpy(f4_scale(-0.5f, v), 0.5f, FrameLoad<InT>::at(tbase, u * C + j, s_lut)), mn, mx);
+    }
+    store_unit<OutT, CP, C>(xo + u * 4 * CP, e);
+  }
+  if (diff) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm + 2 * img, f2ord(mn)); atomicMax(mm + 2 * img + 1, f2ord(mx)); }
+  }
+}
+
+template <typename InT, typename OutT, int CP, int C>
+__global__ void __launch_bounds__(256) seq_dyndiff_kernel(const InT* __restrict__ rgb, const InT* __restrict__ tgt,
+                                                          OutT* __restrict__ x1, const int* __restrict__ mm,
+                                                          float* __restrict__ dyndiff_f32, int N, int K, long long units,
+                                                          int ring_start) {
+  __shared__ float s_lut[256];
+  if (sizeof(InT) == 1) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s_lut[b] = __fdiv_rn((float)b, 255.f);
+    __syncthreads();
+  }
+  const int img = blockIdx.y, t = img / N, n = img - t * N;
+  const long long img4 = units * C;
+  const InT* fbase = rgb + ((long long)n * K + (t + ring_start) % K) * img4 * 4;
+  const InT* tbase = tgt + (long long)n * img4 * 4;
+  OutT* xo = x1 + (long long)img * units * 4 * CP;
+  const float mn = ord2f(mm[2 * img]), mx = ord2f(mm[2 * img + 1]);
+  const float rng = __fadd_rn(__fsub_rn(mx, mn), 1e-6f);
+  float4* o = (dyndiff_f32 && t == K - 1) ? reinterpret_cast<float4*>(dyndiff_f32) + (long long)n * img4 : nullptr;   // endpoints['dyndiff'] keeps the last frame's image
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+    float e[4 * C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      const float4 v = FrameLoad<InT>::at(fbase, u * C + j, s_lut);
+      const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, v), 0.5f, FrameLoad<InT>::at(tbase, u * C + j, s_lut)), mn, rng);
+      e[j * 4] = b.x; e[j * 4 + 1] = b.y; e[j * 4 + 2] = b.z; e[j * 4 + 3] = b.w;
+      if (o) stg_stream(o + u * C + j, b);
+    }
+    store_unit<OutT, CP, C>(xo + u * 4 * CP, e);
+  }
+}
+
+template <typename InT, typename OutT, int CP, int C>
+static int launch_seq_t(const InT* rgb, const InT* tgt, void* x0, int* mm, float* dd, int N, int K, int H, int W,
+                        int with_tgt, int with_diff, int ring_start, cudaStream_t st) {
+  const long long units = (long long)H * W / 4;
+  const int imgs = K * N + (with_tgt ? N : 0);
+  int bx = (int)((units + 256 * 4 - 1) / (256 * 4)); if (bx < 1) bx = 1;
+  OutT* x = reinterpret_cast<OutT*>(x0);
+  if (with_diff) minmax_init_kernel<<<ceil_div(K * N, 256), 256, 0, st>>>(mm, K * N);
+  seq_frames_kernel<InT, OutT, CP, C><<<dim3(bx, imgs), 256, 0, st>>>(rgb, tgt, x, mm, N, K, with_diff, units, ring_start);
+  geeco_count_launch(with_diff ? 2 : 1);
+  if (with_diff) {
+    seq_dyndiff_kernel<InT, OutT, CP, C><<<dim3(bx, K * N), 256, 0, st>>>(rgb, tgt, x + (long long)K * N * units * 4 * CP, mm, dd,
+                                                                         N, K, units, ring_start);
+    geeco_count_launch(1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+int launch_preprocess_seq(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP, int* minmax_scratch,
+                          float* dyndiff_f32, int N, int K, int H, int W, int C, int with_tgt, int with_diff,
+                          int ring_start, cudaStream_t st) {
+  if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
+  if (N <= 0) return GEECO_OK;
+  if ((long long)(K + 1) * N > 65535) { geeco_set_error("preprocess: (K+1)*N = %lld images > 65535", (long long)(K + 1) * N); return GEECO_ERR_INVALID; }
+  if (ring_start < 0 || ring_start >= K) { geeco_set_error("preprocess: ring_start %d outside [0,%d)", ring_start, K); return GEECO_ERR_INVALID; }
+  if ((with_tgt || with_diff) && !tgt) { geeco_set_error("preprocess: target frame needed"); return GEECO_ERR_INVALID; }
+  if (with_diff && !minmax_scratch) { geeco_set_error("preprocess: min/max scratch missing"); return GEECO_ERR_INVALID; }
+#define SEQ_CASE(T, cp, c)                                                                                          \
+  return frames_u8 ? launch_seq_t<unsigned char, T, cp, c>((const unsigned char*)rgb, (const unsigned char*)tgt, x0,    \
+                                                           minmax_scratch, dyndiff_f32, N, K, H, W, with_tgt, with_diff, \
+                                                           ring_start, st)                                              \
+                   : launch_seq_t<float, T, cp, c>((const float*)rgb, (const float*)tgt, x0, minmax_scratch, dyndiff_f32, \
+                                                   N, K, H, W, with_tgt, with_diff, ring_start, st)
+  if (!out_bf16 && CP == 4 && C == 3) SEQ_CASE(float, 4, 3);
+  if (!out_bf16 && CP == 4 && C == 4) SEQ_CASE(float, 4, 4);
+  if (out_bf16 && CP == 4 && C == 3) SEQ_CASE(__nv_bfloat16, 4, 3);
+  if (out_bf16 && CP == 4 && C == 4) SEQ_CASE(__nv_bfloat16, 4, 4);
+#undef SEQ_CASE
   geeco_set_error("preprocess: unsupported (bf16=%d, CP=%d, C=%d)", out_bf16, CP, C);
   return GEECO_ERR_INVALID;
 }

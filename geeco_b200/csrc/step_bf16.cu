@@ -57,12 +57,12 @@ static void* carve(size_t* off, char* base, size_t bytes) {
 int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   if (!c->bf16_ws) c->bf16_ws = new Bf16Plan();
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
-  const int N = c->cfg.batch_size;
+  const int N = c->M, G = c->G;      // images per encoder group, encoder groups
   long long cap = 0;
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
-    const int groups = L.grouped ? 3 : 1;
+    const int groups = L.grouped ? G : 1;
     B.fwd = tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L.stride, N, groups);
     // pixel-pair formulation of conv1 (16-byte copies, two parity classes): correct but measured slower than the
     // row-window producer on B200, kept as an opt-in experiment (GEECO_TC_CONV1_PAIR=1)
@@ -85,7 +85,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
           for (int e = 0; e < 3; ++e) B.w_dg[ci][e] = nullptr;
         }
     }
-    for (int e = 0; e < (L.grouped ? 1 : 3); ++e) {
+    for (int e = 0; e < (L.grouped ? 1 : G); ++e) {
       TcGeom g = B.fwd;
       const long long need = tc_wgrad_partial_floats(g, L.Cout[e]);
       if (need > cap) cap = need;
@@ -96,18 +96,18 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
     size_t tot = 0;
-    for (int e = 0; e < 3; ++e) tot += (size_t)L.Cout[e] * B.fwd.Kpad;
+    for (int e = 0; e < G; ++e) tot += (size_t)L.Cout[e] * B.fwd.Kpad;
     __nv_bfloat16* base = (__nv_bfloat16*)carve(ws_off, ws_base, tot * 2);
     size_t o = 0;
-    for (int e = 0; e < 3; ++e) { B.w_fwd[e] = base ? base + o : nullptr; o += (size_t)L.Cout[e] * B.fwd.Kpad; }
+    for (int e = 0; e < G; ++e) { B.w_fwd[e] = base ? base + o : nullptr; o += (size_t)L.Cout[e] * B.fwd.Kpad; }
     for (int par = 0; par < 2; ++par)
-      B.w_pair[par] = B.pair ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)3 * L.Cout[0] * 64 * 2) : nullptr;
+      B.w_pair[par] = B.pair ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)G * L.Cout[0] * 64 * 2) : nullptr;
     for (int ci = 0; ci < B.n_classes; ++ci) {
       size_t t2 = 0;
-      for (int e = 0; e < 3; ++e) t2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
+      for (int e = 0; e < G; ++e) t2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
       __nv_bfloat16* b2 = (__nv_bfloat16*)carve(ws_off, ws_base, t2 * 2);
       size_t o2 = 0;
-      for (int e = 0; e < 3; ++e) {
+      for (int e = 0; e < G; ++e) {
         B.w_dg[ci][e] = b2 ? b2 + o2 : nullptr;
         o2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
       }
@@ -129,19 +129,19 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     Bf16Layer& B = bp->L[l];
     if (B.pair) {
       for (int par = 0; par < 2; ++par) {
-        int rc = make_weight_tensor_map(&B.pair_map[par], B.w_pair[par], 3ll * L.Cout[0], 64, L.Cout[0]);
+        int rc = make_weight_tensor_map(&B.pair_map[par], B.w_pair[par], (long long)G * L.Cout[0], 64, L.Cout[0]);
         if (rc) return rc;
       }
     }
     if (L.grouped) {
-      int rc = make_weight_tensor_map(&B.fwd_map[0], B.w_fwd[0], 3ll * L.Cout[0], B.fwd.Kpad, L.Cout[0]);
+      int rc = make_weight_tensor_map(&B.fwd_map[0], B.w_fwd[0], (long long)G * L.Cout[0], B.fwd.Kpad, L.Cout[0]);
       if (rc) return rc;
       for (int ci = 0; ci < B.n_classes; ++ci) {
-        rc = make_weight_tensor_map(&B.dg_map[ci][0], B.w_dg[ci][0], 3ll * L.Cin_real, B.dg[ci].Kpad, L.Cin_real);
+        rc = make_weight_tensor_map(&B.dg_map[ci][0], B.w_dg[ci][0], (long long)G * L.Cin_real, B.dg[ci].Kpad, L.Cin_real);
         if (rc) return rc;
       }
     } else {
-      for (int e = 0; e < 3; ++e) {
+      for (int e = 0; e < G; ++e) {
         int rc = make_weight_tensor_map(&B.fwd_map[e], B.w_fwd[e], L.Cout[e], B.fwd.Kpad, L.Cout[e]);
         if (rc) return rc;
         for (int ci = 0; ci < B.n_classes; ++ci) {
@@ -186,22 +186,23 @@ static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, 
 // fp32 master weights -> packed bf16 operands of every conv layer (forward + the data-gradient classes): one launch
 static int repack_weights(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  const int G = c->G;
   if (!bp->jobs_uploaded) {
     bp->jobs.clear();
     bp->jobs_total = 0;
     for (int l = 0; l < 8; ++l) {
       LayerPlan& L = c->layers[l];
       Bf16Layer& B = bp->L[l];
-      const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
-      const int ne = L.grouped ? 1 : 3;
+      const long long wstride = w_group_stride(c, L);
+      const int ne = L.grouped ? 1 : G;
       for (int e = 0; e < ne; ++e) {
-        const int groups = L.grouped ? 3 : 1;
+        const int groups = L.grouped ? G : 1;
         const float* W = c->theta + c->params[L.p_w[e]].offset;
         if (B.pair) {
           for (int par = 0; par < 2; ++par)
             add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
         } else {
-          const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+          const long long bstride = b_group_stride(c, L);
           add_job(bp, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
                   B.fwd.Kpad, B.fwd.Kt, B.fwd.bias_in_k ? c->theta + c->params[L.p_b[e]].offset : nullptr, bstride, B.fwd.Ktot);
         }
@@ -255,27 +256,27 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
     int rc = repack_weights(c, st);
     if (rc) return rc;
   }
-  const int N = c->cfg.batch_size;
+  const int N = c->M, G = c->G;
   const __nv_bfloat16* src = (const __nv_bfloat16*)c->x0;
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
     if (B.pair) {
       TcGeom pg[2] = {B.pg[0], B.pg[1]};
-      pg[0].bias_group_stride = pg[1].bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+      pg[0].bias_group_stride = pg[1].bias_group_stride = b_group_stride(c, L);
       const CUtensorMap* pm[2] = {&B.pair_map[0], &B.pair_map[1]};
       int rc = launch_tc_nn_multi(pg, pm, 2, src, c->theta + c->params[L.p_b[0]].offset, nullptr, (__nv_bfloat16*)L.y, nullptr,
                                   TC_EPI_BIAS_RELU, 0, st, (unsigned short*)L.mbits);
       if (rc) return rc;
     } else if (L.grouped) {
       TcGeom g = B.fwd;
-      g.bias_group_stride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+      g.bias_group_stride = b_group_stride(c, L);
       int rc = launch_tc_nn(g, &B.fwd_map[0], src, c->theta + c->params[L.p_b[0]].offset, nullptr,
                             (__nv_bfloat16*)L.y, l == 7 ? c->y8_f32 : nullptr, TC_EPI_BIAS_RELU, 0, st,
                             (unsigned short*)L.mbits, B.w_fwd[0]);
       if (rc) return rc;
     } else {
-      for (int e = 0; e < 3; ++e) {
+      for (int e = 0; e < G; ++e) {
         TcGeom g = tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[e], L.stride, N, 1);
         const __nv_bfloat16* s = src + (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
         int rc = launch_tc_nn(g, &B.fwd_map[e], s, c->theta + c->params[L.p_b[e]].offset, nullptr,
@@ -292,7 +293,7 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
 int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
-  const int N = c->cfg.batch_size;
+  const int N = c->M, G = c->G;
   if (lhi == 7) {
     int rc = launch_f32_to_bf16(c->g8_f32, (__nv_bfloat16*)c->layers[7].g, c->layers[7].act_elems, st);
     if (rc) return rc;
@@ -301,8 +302,8 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
     const __nv_bfloat16* xin = l == 0 ? (const __nv_bfloat16*)c->x0 : (const __nv_bfloat16*)c->layers[l - 1].y;
-    const long long wstride = c->params[L.p_w[1]].offset - c->params[L.p_w[0]].offset;
-    const long long bstride = c->params[L.p_b[1]].offset - c->params[L.p_b[0]].offset;
+    const long long wstride = w_group_stride(c, L);
+    const long long bstride = b_group_stride(c, L);
     if (B.pair) {
       // conv1 weight gradient on pixel pairs: one partial GEMM per output-column parity, one joint reduction
       const long long half = bp->partial_cap / 2;
@@ -312,14 +313,14 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
       rc = launch_tc_wgrad_partial(B.pg[1], L.Cout[0], xin, (const __nv_bfloat16*)L.g, bp->partial + half, half, 1, &splits, &mrows, st);
       if (rc) return rc;
       rc = launch_conv1pair_reduce(bp->partial, bp->partial + half, c->grad + c->params[L.p_w[0]].offset,
-                                   c->grad + c->params[L.p_b[0]].offset, splits, 3, mrows, 64, L.Cin_real, L.Cout[0], wstride,
+                                   c->grad + c->params[L.p_b[0]].offset, splits, G, mrows, 64, L.Cin_real, L.Cout[0], wstride,
                                    bstride, st);
       if (rc) return rc;
       continue;
     }
-    const int ne = L.grouped ? 1 : 3;
+    const int ne = L.grouped ? 1 : G;
     for (int e = 0; e < ne; ++e) {
-      const int groups = L.grouped ? 3 : 1;
+      const int groups = L.grouped ? G : 1;
       const long long in_off = L.grouped ? 0 : (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
       const __nv_bfloat16* gy = (const __nv_bfloat16*)L.g + (L.grouped ? 0 : L.act_off[e]);
       TcGeom g = L.grouped ? B.fwd : tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[e], L.stride, N, 1);

@@ -7,86 +7,164 @@
 #include "tail.cuh"
 
 // ---------------------------------------------------------------------------------------
-// state[n] = flatten_hwc(concat_c[obs, dyn, jnt, tgt]) ++ m_prev          (graph.py:187-190)
-// feature index = cell * per + block_offset + c,  cell = h*2 + w
+// LSTM inputs of all T steps:  states[t][n] = [ flatten_hwc(concat_c[...]) | m_{t-1} ]       (graph.py:123-192)
+// feature index = cell * per + block_offset + c,  cell = h*2 + w.  The m part is written here for t = 0 only
+// (carried m or zeros); the cell kernel of step t writes it for step t+1.
 // ---------------------------------------------------------------------------------------
-__global__ void build_state_kernel(TailDims d, const float* __restrict__ y_obs, const float* __restrict__ y_dyn,
-                                   const float* __restrict__ y_tgt, const float* __restrict__ jnt_states,
-                                   const float* __restrict__ m_prev, float* __restrict__ state) {
-  const int n = blockIdx.x;
-  const int per = d.D_obs + d.D_dyn + d.J + d.D_diff;
-  const int xdim = 4 * per;
-  float* row = state + (long long)n * (xdim + d.Hl);
-  const float* jn = jnt_states + ((long long)n * d.K + (d.K - 1)) * d.J;   // last frame of the window, graph.py:388
-  for (int i = threadIdx.x; i < xdim + d.Hl; i += blockDim.x) {
-    float v;
-    if (i >= xdim) {
-      v = m_prev ? m_prev[(long long)n * d.Hl + (i - xdim)] : 0.f;
-    } else {
-      const int cell = i / per, c = i - cell * per;
-      if (c < d.D_obs) v = y_obs[((long long)n * 4 + cell) * d.D_obs + c];
-      else if (c < d.D_obs + d.D_dyn) v = y_dyn[((long long)n * 4 + cell) * d.D_dyn + (c - d.D_obs)];
-      else if (c < d.D_obs + d.D_dyn + d.J) v = jn[c - d.D_obs - d.D_dyn];
-      else v = y_tgt[((long long)n * 4 + cell) * d.D_diff + (c - d.D_obs - d.D_dyn - d.J)];
+__device__ __forceinline__ float state_value(const StateMap& sm, const float* __restrict__ jnt, int t, int n, int cell, int c) {
+  const int N = sm.N;
+  switch (sm.variant) {
+    case VAR_GEECOF: {
+      if (c < sm.D0) return sm.y[0][((long long)n * 4 + cell) * sm.D0 + c];
+      c -= sm.D0;
+      if (c < sm.D1) return sm.y[1][((long long)n * 4 + cell) * sm.D1 + c];
+      c -= sm.D1;
+      if (c < sm.J) return jnt[((long long)n * sm.K + (sm.ring_start + sm.K - 1) % sm.K) * sm.J + c];   // last frame, graph.py:388
+      c -= sm.J;
+      return sm.y[2][((long long)n * 4 + cell) * sm.D2 + c];
     }
+    case VAR_SEQ_CONSTANT: {
+      if (c < sm.D0) return sm.y[0][(((long long)t * N + n) * 4 + cell) * sm.D0 + c];
+      c -= sm.D0;
+      if (c < sm.J) return jnt[((long long)n * sm.K + (sm.ring_start + t) % sm.K) * sm.J + c];
+      c -= sm.J;
+      return sm.y[0][(((long long)sm.K * N + n) * 4 + cell) * sm.D0 + c];
+    }
+    case VAR_SEQ_RESIDUAL: {
+      if (c < sm.D0)
+        return sm.y[0][(((long long)sm.K * N + n) * 4 + cell) * sm.D0 + c] - sm.y[0][(((long long)t * N + n) * 4 + cell) * sm.D0 + c];
+      c -= sm.D0;
+      return jnt[((long long)n * sm.K + (sm.ring_start + t) % sm.K) * sm.J + c];
+    }
+    case VAR_SEQ_DYNDIFF: {
+      if (c < sm.D0) return sm.y[0][(((long long)t * N + n) * 4 + cell) * sm.D0 + c];
+      c -= sm.D0;
+      if (c < sm.J) return jnt[((long long)n * sm.K + (sm.ring_start + t) % sm.K) * sm.J + c];
+      c -= sm.J;
+      return sm.y[1][(((long long)t * N + n) * 4 + cell) * sm.D2 + c];
+    }
+    default: {   // VAR_VMC
+      if (c < sm.D0) return sm.y[0][(((long long)t * N + n) * 4 + cell) * sm.D0 + c];
+      c -= sm.D0;
+      return jnt[((long long)n * sm.K + (sm.ring_start + t) % sm.K) * sm.J + c];
+    }
+  }
+}
+
+__global__ void build_states_kernel(StateMap sm, const float* __restrict__ jnt_states, const float* __restrict__ m_prev,
+                                    const unsigned char* __restrict__ reset_mask, float* __restrict__ states) {
+  const int n = blockIdx.x, t = blockIdx.y;
+  float* row = states + ((long long)t * sm.N + n) * sm.ld;
+  const int hi = t == 0 ? sm.ld : sm.xdim;
+  const bool keep = m_prev && !(reset_mask && reset_mask[n]);
+  for (int i = threadIdx.x; i < hi; i += blockDim.x) {
+    float v;
+    if (i >= sm.xdim) v = keep ? m_prev[(long long)n * sm.Hl + (i - sm.xdim)] : 0.f;
+    else { const int cell = i / sm.per; v = state_value(sm, jnt_states, t, n, cell, i - cell * sm.per); }
     row[i] = v;
   }
 }
 
-// dY8(pre-activation)[enc][n][cell][c] = dstate[n][cell*per + off_enc + c] * (Y8 > 0)
-__global__ void scatter_dstate_kernel(TailDims d, const float* __restrict__ dstate, int ld_dstate,
-                                      const float* __restrict__ y_obs, const float* __restrict__ y_dyn,
-                                      const float* __restrict__ y_tgt, float* __restrict__ g_obs,
-                                      float* __restrict__ g_dyn, float* __restrict__ g_tgt) {
-  const int n = blockIdx.x;
-  const int per = d.D_obs + d.D_dyn + d.J + d.D_diff;
-  const float* row = dstate + (long long)n * ld_dstate;
-  for (int i = threadIdx.x; i < 4 * per; i += blockDim.x) {
-    const int cell = i / per, c = i - cell * per;
-    const float v = row[i];
-    if (c < d.D_obs) {
-      const long long o = ((long long)n * 4 + cell) * d.D_obs + c;
-      g_obs[o] = y_obs[o] > 0.f ? v : 0.f;
-    } else if (c < d.D_obs + d.D_dyn) {
-      const long long o = ((long long)n * 4 + cell) * d.D_dyn + (c - d.D_obs);
-      g_dyn[o] = y_dyn[o] > 0.f ? v : 0.f;
-    } else if (c >= d.D_obs + d.D_dyn + d.J) {
-      const long long o = ((long long)n * 4 + cell) * d.D_diff + (c - d.D_obs - d.D_dyn - d.J);
-      g_tgt[o] = y_tgt[o] > 0.f ? v : 0.f;
-    }
+// dY8(pre-activation)[group][img][cell][c] = (sum of the d(state) entries that read Y8[group][img][cell][c]) * (Y8 > 0).
+// One thread per conv8 element gathers its contributions (a target feature is read by all T steps): deterministic.
+__global__ void scatter_dstates_kernel(StateMap sm, const float* __restrict__ ds, int imgs0, int imgs1, int imgs2) {
+  const long long n0 = (long long)imgs0 * 4 * sm.D0, n1 = (long long)imgs1 * 4 * sm.D1, n2 = (long long)imgs2 * 4 * sm.D2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0 + n1 + n2) return;
+  int grp = 0, D = sm.D0;
+  if (i >= n0 + n1) { grp = 2; i -= n0 + n1; D = sm.D2; }
+  else if (i >= n0) { grp = 1; i -= n0; D = sm.variant == VAR_SEQ_DYNDIFF ? sm.D2 : sm.D1; }
+  const int c = (int)(i % D);
+  const int cell = (int)((i / D) & 3);
+  const int img = (int)(i / (4ll * D));
+  const int N = sm.N;
+  auto at = [&](int t, int n, int off) { return ds[((long long)t * N + n) * sm.ld + cell * sm.per + off + c]; };
+  float v = 0.f;
+  switch (sm.variant) {
+    case VAR_GEECOF:
+      v = at(0, img, grp == 0 ? 0 : (grp == 1 ? sm.D0 : sm.D0 + sm.D1 + sm.J));
+      break;
+    case VAR_SEQ_CONSTANT:
+      if (img < sm.K * N) v = at(img / N, img % N, 0);
+      else for (int t = 0; t < sm.T; ++t) v += at(t, img - sm.K * N, sm.D0 + sm.J);
+      break;
+    case VAR_SEQ_RESIDUAL:
+      if (img < sm.K * N) v = -at(img / N, img % N, 0);
+      else for (int t = 0; t < sm.T; ++t) v += at(t, img - sm.K * N, 0);
+      break;
+    case VAR_SEQ_DYNDIFF:
+      v = at(img / N, img % N, grp == 0 ? 0 : sm.D0 + sm.J);
+      break;
+    default:
+      v = at(img / N, img % N, 0);
+      break;
   }
+  sm.g[grp][i] = sm.y[grp][i] > 0.f ? v : 0.f;
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // LSTMCell (state_is_tuple=False, forget_bias=1): gates already hold [x,m]W + b.
 __global__ void lstm_cell_kernel(int N, int Hl, const float* __restrict__ gates, const float* __restrict__ c_prev,
-                                 float* __restrict__ c_out, float* __restrict__ m_out, float* __restrict__ state_out) {
+                                 const unsigned char* __restrict__ reset_mask, float* __restrict__ c_out,
+                                 float* __restrict__ m_out, float* __restrict__ state_out, float* __restrict__ m_next,
+                                 int ld_next) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * Hl) return;
   const int n = idx / Hl, i = idx - n * Hl;
   const float* gr = gates + (long long)n * 4 * Hl;
   const float gi = gr[i], gj = gr[Hl + i], gf = gr[2 * Hl + i], go = gr[3 * Hl + i];
-  const float cp = c_prev ? c_prev[idx] : 0.f;
+  const float cp = (c_prev && !(reset_mask && reset_mask[n])) ? c_prev[idx] : 0.f;
   const float c = sigmoidf_(gf + 1.0f) * cp + sigmoidf_(gi) * tanhf(gj);
   const float m = sigmoidf_(go) * tanhf(c);
   c_out[idx] = c;
   m_out[idx] = m;
+  if (m_next) m_next[(long long)n * ld_next + i] = m;
   if (state_out) {
     state_out[(long long)n * 2 * Hl + i] = c;
     state_out[(long long)n * 2 * Hl + Hl + i] = m;
   }
 }
 
+// d(gates_t) and d(c_{t-1}) from d(m_t) (row stride ld_dm) and the d(c_t) that flows back from step t+1
+__global__ void lstm_cell_bwd_kernel(int N, int Hl, const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                     const unsigned char* __restrict__ reset_mask, const float* __restrict__ dm, int ld_dm,
+                                     const float* __restrict__ dc_in, float* __restrict__ dgates,
+                                     float* __restrict__ dc_prev) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * Hl) return;
+  const int n = idx / Hl, i = idx - n * Hl;
+  const float* gr = gates + (long long)n * 4 * Hl;
+  const float gi = gr[i], gj = gr[Hl + i], gf = gr[2 * Hl + i], go = gr[3 * Hl + i];
+  const float cp = (c_prev && !(reset_mask && reset_mask[n])) ? c_prev[idx] : 0.f;
+  const float si = sigmoidf_(gi), tj = tanhf(gj), sf = sigmoidf_(gf + 1.0f), so = sigmoidf_(go);
+  const float c = sf * cp + si * tj;
+  const float tc = tanhf(c);
+  const float dmv = dm[(long long)n * ld_dm + i];
+  const float dso = dmv * tc;
+  const float dc = dmv * so * (1.f - tc * tc) + (dc_in ? dc_in[idx] : 0.f);
+  float* dg = dgates + (long long)n * 4 * Hl;
+  dg[i] = dc * tj * si * (1.f - si);
+  dg[Hl + i] = dc * si * (1.f - tj * tj);
+  dg[2 * Hl + i] = dc * cp * sf * (1.f - sf);
+  dg[3 * Hl + i] = dso * so * (1.f - so);
+  if (dc_prev) dc_prev[idx] = dc * sf;
+}
+
 // ---------------------------------------------------------------------------------------
 // fc1 + heads + per-sample loss pieces + d(loss)/d(head outputs).  One CTA per sample.
-// head columns: [cmd_ee 0:3 | logits_cmd_grp 3:3+G | aux_ee | aux_obj]
-// loss_parts[n] = {se_cmd_ee, ce_cmd_grp, se_pos_ee, se_pos_obj, correct}
+// Head table: TailHeads (columns, loss kind, target location).  loss_parts[n] = {term of head 0..4, correct}
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p, const float* __restrict__ m,
+__device__ __forceinline__ int head_of(const TailHeads& th, int t) {
+  int h = 0;
+#pragma unroll
+  for (int i = 1; i < 5; ++i) if (i < th.nheads && t >= th.h[i].col) h = i;
+  return h;
+}
+
+__global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th, const float* __restrict__ w_fc1,
+                                                       const float* __restrict__ b_fc1, const float* __restrict__ m,
                                                        float* __restrict__ fc1, float* __restrict__ heads,
-                                                       const float* __restrict__ cmd, const float* __restrict__ ee_state,
-                                                       const float* __restrict__ obj_state,
                                                        float* __restrict__ loss_parts, float* __restrict__ dheads,
                                                        int with_loss) {
   extern __shared__ float sm[];
@@ -94,13 +172,13 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p,
   float* fc_s = sm + d.Hl;         // Fc
   float* out_s = fc_s + d.Fc;      // NH
   const int n = blockIdx.x;
-  const int NH = 9 + d.G;
+  const int NH = th.NH;
   for (int i = threadIdx.x; i < d.Hl; i += blockDim.x) m_s[i] = m[(long long)n * d.Hl + i];
   __syncthreads();
   for (int j = threadIdx.x; j < d.Fc; j += blockDim.x) {
-    float s = p.b_fc1[j];
+    float s = b_fc1[j];
 #pragma unroll 16
-    for (int i = 0; i < d.Hl; ++i) s = fmaf(m_s[i], __ldg(p.w_fc1 + (long long)i * d.Fc + j), s);   // loads issue ahead of the FMA chain
+    for (int i = 0; i < d.Hl; ++i) s = fmaf(m_s[i], __ldg(w_fc1 + (long long)i * d.Fc + j), s);   // loads issue ahead of the FMA chain
     s = fmaxf(s, 0.f);
     fc_s[j] = s;
     fc1[(long long)n * d.Fc + j] = s;
@@ -108,94 +186,109 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailParams p,
   __syncthreads();
   // heads: one warp per output column (lanes stride over fc1, fixed-order lane reduction), 4 warps take turns
   for (int t = threadIdx.x >> 5; t < NH; t += blockDim.x >> 5) {
-    const float* w; const float* b; int col, width;
-    if (t < 3) { w = p.w_cmd_ee; b = p.b_cmd_ee; col = t; width = 3; }
-    else if (t < 3 + d.G) { w = p.w_grp; b = p.b_grp; col = t - 3; width = d.G; }
-    else if (t < 6 + d.G) { w = p.w_aux_ee; b = p.b_aux_ee; col = t - 3 - d.G; width = 3; }
-    else { w = p.w_aux_obj; b = p.b_aux_obj; col = t - 6 - d.G; width = 3; }
+    const HeadSpec& hs = th.h[head_of(th, t)];
+    const int col = t - hs.col, width = hs.width;
     const int lane = threadIdx.x & 31;
     float s = 0.f;
-    for (int j = lane; j < d.Fc; j += 32) s = fmaf(fc_s[j], __ldg(w + j * width + col), s);
+    for (int j = lane; j < d.Fc; j += 32) s = fmaf(fc_s[j], __ldg(hs.w + j * width + col), s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    s += b[col];
+    s += hs.b[col];
     if (lane == 0) { out_s[t] = s; heads[(long long)n * NH + t] = s; }
   }
   __syncthreads();
   if (with_loss && threadIdx.x == 0) {
-    const float* c = cmd + (long long)n * 4;
-    const float* ee = ee_state + ((long long)n * d.K + (d.K - 1)) * 7;
-    const float* ob = obj_state + ((long long)n * d.K + (d.K - 1)) * 7;
     float* dh = dheads + (long long)n * NH;
-    const float inv = 1.f / (3.f * d.N);
-    float se0 = 0.f, se2 = 0.f, se3 = 0.f;
-    for (int k = 0; k < 3; ++k) {
-      const float e0 = out_s[k] - c[k];
-      const float e2 = out_s[3 + d.G + k] - ee[k];
-      const float e3 = out_s[6 + d.G + k] - ob[k];
-      se0 += e0 * e0; se2 += e2 * e2; se3 += e3 * e3;
-      dh[k] = 2.f * e0 * inv;
-      dh[3 + d.G + k] = d.lambda_aux * 2.f * e2 * inv;
-      dh[6 + d.G + k] = d.lambda_aux * 2.f * e3 * inv;
+    float* lp = loss_parts + (long long)n * 6;
+    lp[5] = 0.f;
+    for (int hi = 0; hi < th.nheads; ++hi) {
+      const HeadSpec& hs = th.h[hi];
+      const float* tg = hs.target + (long long)n * hs.tstride + hs.toff;
+      const float* o = out_s + hs.col;
+      if (hs.kind == 0) {
+        // tf.losses.mean_squared_error: mean over N*width elements (SUM_BY_NONZERO_WEIGHTS)
+        const float inv = 1.f / ((float)hs.width * d.N);
+        float se = 0.f;
+        for (int k = 0; k < hs.width; ++k) {
+          const float e = o[k] - tg[k];
+          se += e * e;
+          dh[hs.col + k] = hs.weight * 2.f * e * inv;
+        }
+        lp[hi] = se;
+      } else {
+        // estimator.py:213-216: class = int32(rint(cmd[:,3])) + 1 ; one_hot of an out-of-range index is all zeros
+        const int cls = (int)rintf(tg[0]) + 1;
+        float zmax = -3.4e38f; int amax = 0;
+        for (int k = 0; k < hs.width; ++k) if (o[k] > zmax) { zmax = o[k]; amax = k; }
+        float se = 0.f;
+        for (int k = 0; k < hs.width; ++k) se += expf(o[k] - zmax);
+        const float lse = zmax + logf(se);
+        const bool ok = cls >= 0 && cls < hs.width;
+        for (int k = 0; k < hs.width; ++k) {
+          const float pk = expf(o[k] - lse);
+          dh[hs.col + k] = ok ? hs.weight * (pk - (k == cls ? 1.f : 0.f)) / d.N : 0.f;
+        }
+        lp[hi] = ok ? lse - o[cls] : 0.f;
+        lp[5] = (amax == cls) ? 1.f : 0.f;
+      }
     }
-    // estimator.py:213-216: class = int32(rint(cmd[:,3])) + 1 ; one_hot of an out-of-range index is all zeros
-    const int cls = (int)rintf(c[3]) + 1;
-    float zmax = -3.4e38f; int amax = 0;
-    for (int k = 0; k < d.G; ++k) if (out_s[3 + k] > zmax) { zmax = out_s[3 + k]; amax = k; }
-    float se = 0.f;
-    for (int k = 0; k < d.G; ++k) se += expf(out_s[3 + k] - zmax);
-    const float lse = zmax + logf(se);
-    const bool ok = cls >= 0 && cls < d.G;
-    for (int k = 0; k < d.G; ++k) {
-      const float pk = expf(out_s[3 + k] - lse);
-      dh[3 + k] = ok ? (pk - (k == cls ? 1.f : 0.f)) / d.N : 0.f;
-    }
-    float* lp = loss_parts + (long long)n * 5;
-    lp[0] = se0; lp[1] = ok ? lse - out_s[3 + cls] : 0.f; lp[2] = se2; lp[3] = se3;
-    lp[4] = (amax == cls) ? 1.f : 0.f;
   }
 }
 
-// losses[8] = {loss_cmd_ee, loss_cmd_grp, loss_pos_ee, loss_pos_obj, loss_reg, loss, sum_correct, N}
-__global__ void loss_reduce_kernel(int N, float lambda_aux, const float* __restrict__ loss_parts,
+// losses[12]: slot of every head (HeadSpec::slot), [4] loss_reg, [5] loss, [6] sum_correct, [7] N
+__global__ void loss_reduce_kernel(int N, TailHeads th, const float* __restrict__ loss_parts,
                                    const float* __restrict__ reg_term, float* __restrict__ losses) {
-  __shared__ float s[5][256];
-  float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  __shared__ float s[6][256];
+  float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int n = threadIdx.x; n < N; n += blockDim.x)
-    for (int k = 0; k < 5; ++k) a[k] += loss_parts[(long long)n * 5 + k];
-  for (int k = 0; k < 5; ++k) s[k][threadIdx.x] = a[k];
+    for (int k = 0; k < 6; ++k) a[k] += loss_parts[(long long)n * 6 + k];
+  for (int k = 0; k < 6; ++k) s[k][threadIdx.x] = a[k];
   __syncthreads();
   for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) for (int k = 0; k < 5; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
+    if (threadIdx.x < o) for (int k = 0; k < 6; ++k) s[k][threadIdx.x] += s[k][threadIdx.x + o];
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const float l0 = s[0][0] / (3.f * N), l1 = s[1][0] / N, l2 = s[2][0] / (3.f * N), l3 = s[3][0] / (3.f * N);
+    for (int k = 0; k < 12; ++k) losses[k] = 0.f;
+    // command terms (weight 1) and auxiliary terms (one common weight): estimator.py:224-225 adds
+    // add_n(command losses) + lambda_aux * add_n(pose losses); mse_loss (graph.py:449) is one add_n over all five
+    float cmd = 0.f, aux = 0.f, wa = 1.f;
+    bool any_cmd = false, any_aux = false;
+    for (int hi = 0; hi < th.nheads; ++hi) {
+      const HeadSpec& hs = th.h[hi];
+      const float l = hs.kind == 0 ? s[hi][0] / ((float)hs.width * N) : s[hi][0] / N;
+      losses[hs.slot] = l;
+      if (!hs.aux) { cmd = any_cmd ? cmd + l : l; any_cmd = true; }
+      else { aux = any_aux ? aux + l : l; any_aux = true; wa = hs.weight; }
+    }
     const float lr = reg_term ? reg_term[0] : 0.f;
-    losses[0] = l0; losses[1] = l1; losses[2] = l2; losses[3] = l3; losses[4] = lr;
-    losses[5] = (l0 + l1) + lambda_aux * (l2 + l3) + lr;
-    losses[6] = s[4][0]; losses[7] = (float)N;
+    losses[4] = lr;
+    losses[5] = cmd + (any_aux ? wa * aux : 0.f) + lr;
+    losses[6] = s[5][0]; losses[7] = (float)N;
   }
 }
 
-// backward through heads, fc1 and the LSTM cell -> d(gates).  One CTA per sample.
-__global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailParams p, const float* __restrict__ fc1,
-                                                       const float* __restrict__ dheads, const float* __restrict__ gates,
-                                                       const float* __restrict__ c_prev, float* __restrict__ dfc1,
-                                                       float* __restrict__ dgates) {
+// backward through heads and fc1 -> dL/dm; with dm_out == NULL also through the (single) LSTM cell -> d(gates).
+// One CTA per sample.
+__global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailHeads th, const float* __restrict__ w_fc1,
+                                                       const float* __restrict__ fc1, const float* __restrict__ dheads,
+                                                       const float* __restrict__ gates, const float* __restrict__ c_prev,
+                                                       const unsigned char* __restrict__ reset_mask,
+                                                       float* __restrict__ dfc1, float* __restrict__ dgates,
+                                                       float* __restrict__ dm_out) {
   extern __shared__ float sm[];
-  float* dh_s = sm;                // NH (padded to 16)
-  float* dfc_s = sm + 16;          // Fc
+  float* dh_s = sm;                // NH (padded to 32)
+  float* dfc_s = sm + 32;          // Fc
   const int n = blockIdx.x;
-  const int NH = 9 + d.G;
+  const int NH = th.NH;
   if (threadIdx.x < NH) dh_s[threadIdx.x] = dheads[(long long)n * NH + threadIdx.x];
   __syncthreads();
   for (int j = threadIdx.x; j < d.Fc; j += blockDim.x) {
     float s = 0.f;
-    for (int k = 0; k < 3; ++k) s = fmaf(dh_s[k], p.w_cmd_ee[j * 3 + k], s);
-    for (int k = 0; k < d.G; ++k) s = fmaf(dh_s[3 + k], p.w_grp[j * d.G + k], s);
-    for (int k = 0; k < 3; ++k) s = fmaf(dh_s[3 + d.G + k], p.w_aux_ee[j * 3 + k], s);
-    for (int k = 0; k < 3; ++k) s = fmaf(dh_s[6 + d.G + k], p.w_aux_obj[j * 3 + k], s);
+    for (int hi = 0; hi < th.nheads; ++hi) {
+      const HeadSpec& hs = th.h[hi];
+      for (int k = 0; k < hs.width; ++k) s = fmaf(dh_s[hs.col + k], hs.w[j * hs.width + k], s);
+    }
     s = fc1[(long long)n * d.Fc + j] > 0.f ? s : 0.f;
     dfc_s[j] = s;
     dfc1[(long long)n * d.Fc + j] = s;
@@ -203,11 +296,12 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailParams p,
   __syncthreads();
   for (int i = threadIdx.x; i < d.Hl; i += blockDim.x) {
     float dm = 0.f;
-    const float* wr = p.w_fc1 + (long long)i * d.Fc;
+    const float* wr = w_fc1 + (long long)i * d.Fc;
     for (int j = 0; j < d.Fc; ++j) dm = fmaf(dfc_s[j], wr[j], dm);
+    if (dm_out) { dm_out[(long long)n * d.Hl + i] = dm; continue; }
     const float* gr = gates + (long long)n * 4 * d.Hl;
     const float gi = gr[i], gj = gr[d.Hl + i], gf = gr[2 * d.Hl + i], go = gr[3 * d.Hl + i];
-    const float cp = c_prev ? c_prev[(long long)n * d.Hl + i] : 0.f;
+    const float cp = (c_prev && !(reset_mask && reset_mask[n])) ? c_prev[(long long)n * d.Hl + i] : 0.f;
     const float si = sigmoidf_(gi), tj = tanhf(gj), sf = sigmoidf_(gf + 1.0f), so = sigmoidf_(go);
     const float c = sf * cp + si * tj;
     const float tc = tanhf(c);
@@ -222,21 +316,22 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailParams p,
 }
 
 // weight / bias gradients of fc1 and the heads: one thread per element, fixed-order sum over n
-__global__ void tail_wgrad_kernel(TailDims d, TailGrads g, const float* __restrict__ m, const float* __restrict__ fc1,
+__global__ void tail_wgrad_kernel(TailDims d, TailHeads th, float* __restrict__ gw_fc1, float* __restrict__ gb_fc1,
+                                  const float* __restrict__ m, const float* __restrict__ fc1,
                                   const float* __restrict__ dfc1, const float* __restrict__ dheads) {
-  const int NH = 9 + d.G;
+  const int NH = th.NH;
   const int n_w1 = d.Hl * d.Fc, n_b1 = d.Fc, n_wh = d.Fc * NH, n_bh = NH;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n_w1) {
     const int i = idx / d.Fc, j = idx - i * d.Fc;
     float s = 0.f;
     for (int n = 0; n < d.N; ++n) s = fmaf(m[(long long)n * d.Hl + i], dfc1[(long long)n * d.Fc + j], s);
-    g.w_fc1[idx] = s;
+    gw_fc1[idx] = s;
   } else if (idx < n_w1 + n_b1) {
     const int j = idx - n_w1;
     float s = 0.f;
     for (int n = 0; n < d.N; ++n) s += dfc1[(long long)n * d.Fc + j];
-    g.b_fc1[j] = s;
+    gb_fc1[j] = s;
   } else if (idx < n_w1 + n_b1 + n_wh + n_bh) {
     const int e = idx - n_w1 - n_b1;
     const bool is_bias = e >= n_wh;
@@ -244,12 +339,9 @@ __global__ void tail_wgrad_kernel(TailDims d, TailGrads g, const float* __restri
     float s = 0.f;
     if (is_bias) for (int n = 0; n < d.N; ++n) s += dheads[(long long)n * NH + t];
     else for (int n = 0; n < d.N; ++n) s = fmaf(fc1[(long long)n * d.Fc + j], dheads[(long long)n * NH + t], s);
-    float* w; float* b; int col, width;
-    if (t < 3) { w = g.w_cmd_ee; b = g.b_cmd_ee; col = t; width = 3; }
-    else if (t < 3 + d.G) { w = g.w_grp; b = g.b_grp; col = t - 3; width = d.G; }
-    else if (t < 6 + d.G) { w = g.w_aux_ee; b = g.b_aux_ee; col = t - 3 - d.G; width = 3; }
-    else { w = g.w_aux_obj; b = g.b_aux_obj; col = t - 6 - d.G; width = 3; }
-    if (is_bias) b[col] = s; else w[j * width + col] = s;
+    const HeadSpec& hs = th.h[head_of(th, t)];
+    const int col = t - hs.col;
+    if (is_bias) hs.gb[col] = s; else hs.gw[j * hs.width + col] = s;
   }
 }
 
@@ -304,51 +396,74 @@ __global__ void l2_term_kernel(const float* __restrict__ theta, long long n, flo
 // ---------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------
-int launch_build_state(const TailDims& d, const float* y_obs, const float* y_dyn, const float* y_tgt, const float* jnt,
-                       const float* m_prev, float* state, cudaStream_t st) {
-  build_state_kernel<<<d.N, 256, 0, st>>>(d, y_obs, y_dyn, y_tgt, jnt, m_prev, state);
+int launch_build_states(const StateMap& sm, const float* jnt, const float* m_prev, const unsigned char* reset_mask,
+                        float* states, cudaStream_t st) {
+  build_states_kernel<<<dim3(sm.N, sm.T), 256, 0, st>>>(sm, jnt, m_prev, reset_mask, states);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_scatter_dstate(const TailDims& d, const float* dstate, int ld, const float* y_obs, const float* y_dyn,
-                          const float* y_tgt, float* g_obs, float* g_dyn, float* g_tgt, cudaStream_t st) {
-  scatter_dstate_kernel<<<d.N, 256, 0, st>>>(d, dstate, ld, y_obs, y_dyn, y_tgt, g_obs, g_dyn, g_tgt);
+static void group_images(const StateMap& sm, int* imgs) {
+  imgs[0] = imgs[1] = imgs[2] = 0;
+  switch (sm.variant) {
+    case VAR_GEECOF: imgs[0] = imgs[1] = imgs[2] = sm.N; break;
+    case VAR_SEQ_CONSTANT: case VAR_SEQ_RESIDUAL: imgs[0] = (sm.K + 1) * sm.N; break;
+    case VAR_SEQ_DYNDIFF: imgs[0] = imgs[1] = sm.K * sm.N; break;
+    default: imgs[0] = sm.K * sm.N; break;
+  }
+}
+int launch_scatter_dstates(const StateMap& sm, const float* dstates, cudaStream_t st) {
+  int imgs[3];
+  group_images(sm, imgs);
+  const int D1 = sm.variant == VAR_SEQ_DYNDIFF ? sm.D2 : sm.D1;
+  const long long total = 4ll * ((long long)imgs[0] * sm.D0 + (long long)imgs[1] * D1 + (long long)imgs[2] * sm.D2);
+  // scatter_dstates_kernel indexes group 1 with width D1 (= D2 for sequence/dyndiff, whose second group is the
+  // DynDiffEncoder): pass that width in the D1 slot of a copy
+  StateMap k = sm;
+  k.D1 = D1;
+  scatter_dstates_kernel<<<ceil_div(total, 256), 256, 0, st>>>(k, dstates, imgs[0], imgs[1], imgs[2]);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_lstm_cell(int N, int Hl, const float* gates, const float* c_prev, float* c_out, float* m_out,
-                     float* state_out, cudaStream_t st) {
-  lstm_cell_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(N, Hl, gates, c_prev, c_out, m_out, state_out);
+int launch_lstm_cell(int N, int Hl, const float* gates, const float* c_prev, const unsigned char* reset_mask,
+                     float* c_out, float* m_out, float* state_out, float* m_next, int ld_next, cudaStream_t st) {
+  lstm_cell_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(N, Hl, gates, c_prev, reset_mask, c_out, m_out,
+                                                                    state_out, m_next, ld_next);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_tail_fwd(const TailDims& d, const TailParams& p, const float* m, float* fc1, float* heads, const float* cmd,
-                    const float* ee, const float* obj, float* loss_parts, float* dheads, int with_loss,
-                    cudaStream_t st) {
-  const size_t smem = (size_t)(d.Hl + d.Fc + 16 + d.G) * sizeof(float);
-  tail_fwd_kernel<<<d.N, 128, smem, st>>>(d, p, m, fc1, heads, cmd, ee, obj, loss_parts, dheads, with_loss);
+int launch_lstm_cell_bwd(int N, int Hl, const float* gates, const float* c_prev, const unsigned char* reset_mask,
+                         const float* dm, int ld_dm, const float* dc_in, float* dgates, float* dc_prev, cudaStream_t st) {
+  lstm_cell_bwd_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(N, Hl, gates, c_prev, reset_mask, dm, ld_dm, dc_in,
+                                                                        dgates, dc_prev);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_loss_reduce(const TailDims& d, const float* loss_parts, const float* reg_term, float* losses,
-                       cudaStream_t st) {
-  loss_reduce_kernel<<<1, 256, 0, st>>>(d.N, d.lambda_aux, loss_parts, reg_term, losses);
+int launch_tail_fwd(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1, const float* m,
+                    float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, cudaStream_t st) {
+  const size_t smem = (size_t)(d.Hl + d.Fc + 32) * sizeof(float);
+  tail_fwd_kernel<<<d.N, 128, smem, st>>>(d, th, w_fc1, b_fc1, m, fc1, heads, loss_parts, dheads, with_loss);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_tail_bwd(const TailDims& d, const TailParams& p, const TailGrads& g, const float* m, const float* fc1,
-                    const float* dheads, const float* gates, const float* c_prev, float* dfc1, float* dgates,
-                    cudaStream_t st) {
-  const size_t smem = (size_t)(16 + d.Fc) * sizeof(float);
-  tail_bwd_kernel<<<d.N, 128, smem, st>>>(d, p, fc1, dheads, gates, c_prev, dfc1, dgates);
-  const int NH = 9 + d.G;
-  const int total = d.Hl * d.Fc + d.Fc + d.Fc * NH + NH;
-  tail_wgrad_kernel<<<ceil_div(total, 128), 128, 0, st>>>(d, g, m, fc1, dfc1, dheads);
+int launch_loss_reduce(const TailDims& d, const TailHeads& th, const float* loss_parts, const float* reg_term,
+                       float* losses, cudaStream_t st) {
+  loss_reduce_kernel<<<1, 256, 0, st>>>(d.N, th, loss_parts, reg_term, losses);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+int launch_tail_bwd(const TailDims& d, const TailHeads& th, const float* w_fc1, float* gw_fc1, float* gb_fc1,
+                    const float* m, const float* fc1, const float* dheads, const float* gates, const float* c_prev,
+                    const unsigned char* reset_mask, float* dfc1, float* dgates, float* dm_out, cudaStream_t st) {
+  const size_t smem = (size_t)(32 + d.Fc) * sizeof(float);
+  tail_bwd_kernel<<<d.N, 128, smem, st>>>(d, th, w_fc1, fc1, dheads, gates, c_prev, reset_mask, dfc1, dgates, dm_out);
+  const int total = d.Hl * d.Fc + d.Fc + d.Fc * th.NH + th.NH;
+  tail_wgrad_kernel<<<ceil_div(total, 128), 128, 0, st>>>(d, th, gw_fc1, gb_fc1, m, fc1, dfc1, dheads);
   geeco_count_launch(2);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -511,6 +626,37 @@ int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias
   else gates_splitk_kernel<4><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
   gates_reduce_kernel<<<ceil_div((long long)N * Ncols, 256), 256, 0, st>>>(partial, bias, gates, slices, N, Ncols);
   geeco_count_launch(2);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// device ring of K-frame histories (include/geeco_b200.h: geeco_ring_push)
+// ---------------------------------------------------------------------------------------
+template <typename V>
+__global__ void ring_push_kernel(V* __restrict__ ring, const V* __restrict__ frame, const unsigned char* __restrict__ fresh,
+                                 int K, long long row_v, int slot) {
+  const int n = blockIdx.y;
+  const bool all = fresh && fresh[n];
+  const V* src = frame + (long long)n * row_v;
+  V* dst = ring + (long long)n * K * row_v;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < row_v; i += (long long)gridDim.x * blockDim.x) {
+    const V v = src[i];
+    if (all) { for (int k = 0; k < K; ++k) dst[(long long)k * row_v + i] = v; }
+    else dst[(long long)slot * row_v + i] = v;
+  }
+}
+int launch_ring_push(void* ring, const void* frame, const unsigned char* fresh, int N, int K, long long row_bytes,
+                     int slot, cudaStream_t st) {
+  if (N <= 0) return GEECO_OK;
+  if (N > 65535) { geeco_set_error("ring_push: N=%d > 65535", N); return GEECO_ERR_INVALID; }
+  const bool v16 = row_bytes % 16 == 0 && ((uintptr_t)ring % 16 == 0) && ((uintptr_t)frame % 16 == 0);
+  const long long row_v = row_bytes / (v16 ? 16 : 4);
+  int bx = (int)((row_v + 255) / 256); if (bx > 64) bx = 64; if (bx < 1) bx = 1;
+  if (v16) ring_push_kernel<uint4><<<dim3(bx, N), 256, 0, st>>>((uint4*)ring, (const uint4*)frame, fresh, K, row_v, slot);
+  else ring_push_kernel<unsigned int><<<dim3(bx, N), 256, 0, st>>>((unsigned int*)ring, (const unsigned int*)frame, fresh, K, row_v, slot);
+  geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }

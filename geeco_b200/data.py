@@ -94,6 +94,15 @@ def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0,
   cmd[:, 3] = rng.integers(-1, 2, size=n)
   features = {'step': step, 'rgb': rgb, 'jnt_state': jnt, 'ee_state': ee, 'obj_state': obj, 'target_rgb': tgt}
   labels = {'cmd': cmd}
+  # labels of --control_mode velocity (geeco_gym.py:392-398), from their own generator so that the values above
+  # do not depend on them
+  rv = np.random.default_rng([int(seed), 7919])
+  labels['vel_target'] = rv.uniform(-1.0, 1.0, size=(n, 7)).astype(np.float32)
+  ee_t = np.zeros((n, 7), dtype=np.float32)
+  ee_t[:, :3] = np.array([1.34, 0.75, 0.55], dtype=np.float32) + rv.uniform(-0.15, 0.15, size=(n, 3))
+  ee_t[:, 3:] = np.array([1.0, 0.0, 1.0, 0.0], dtype=np.float32)
+  labels['ee_target'] = ee_t
+  labels['grp_target'] = rv.uniform(0.0, 0.05, size=(n, 2)).astype(np.float32)
   return features, labels
 
 

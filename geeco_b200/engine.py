@@ -18,34 +18,37 @@ from . import _lib
 from .params import E2EVMCConfig
 
 LOSS_KEYS = ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss_reg', 'loss')
+LOSS_SLOT_CMD_VEL = 8          # velocity control: loss_cmd_vel (include/geeco_b200.h, geeco_outputs.losses)
 _FEATURE_KEYS = ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state')
 _FRAME_KEYS = ('rgb', 'target_rgb')
+_LABEL_KEYS = {'cartesian': ('cmd',), 'velocity': ('vel_target', 'ee_target', 'grp_target')}   # estimator.py:206-236
 
 
-def _check_switches(cfg: E2EVMCConfig):
-  """Same ValueErrors as graph.py:250-252,357-359,408-410 for unknown values; the switch values that
-  exist in the reference but are not yet on the CUDA path raise NotImplementedError."""
+def _check_switches(cfg: E2EVMCConfig, goal_condition='target'):
+  """Same ValueErrors as graph.py:250-252,357-359,382-384,408-410 and estimator.py:173-175 for unknown values; the
+  KeyError of `_GOAL_CONDITION_TO_MODEL[goal_condition]` (train_e2evmc.py:258) for an unknown goal condition."""
+  if goal_condition not in _lib.GOAL_CONDITION:
+    raise KeyError(goal_condition)
   if cfg.control_mode not in ('cartesian', 'velocity'):
     raise ValueError("Unknown control mode '%s'" % (cfg.control_mode,))
-  if cfg.proc_tgt not in ('constant', 'residual', 'dyndiff'):
-    raise ValueError("Unknown processing mode for target image: %s!" % (cfg.proc_tgt,))
-  if cfg.proc_obs not in ('sequence', 'dynimg'):
-    raise ValueError("Unknown processing mode for frame buffer: %s!" % (cfg.proc_obs,))
+  if goal_condition == 'target':
+    if cfg.proc_tgt not in ('constant', 'residual', 'dyndiff'):
+      raise ValueError("Unknown processing mode for target image: %s!" % (cfg.proc_tgt,))
+    if cfg.proc_obs not in ('sequence', 'dynimg'):
+      raise ValueError("Unknown processing mode for frame buffer: %s!" % (cfg.proc_obs,))
   if cfg.img_channels not in (3, 4):
     raise ValueError("Unsupported number of channels for input frame: %d!" % cfg.img_channels)
-  if (cfg.proc_obs, cfg.proc_tgt, cfg.control_mode) != ('dynimg', 'dyndiff', 'cartesian'):
-    raise NotImplementedError(
-        "geeco_b200 currently runs the GEECO-F wiring (--proc_obs dynimg --proc_tgt dyndiff "
-        "--control_mode cartesian); got proc_obs=%s proc_tgt=%s control_mode=%s"
-        % (cfg.proc_obs, cfg.proc_tgt, cfg.control_mode))
 
 
 class Engine(object):
-  """One replica of the goal-conditioned controller on one GPU."""
+  """One replica of the controller on one GPU: `goal_e2evmc` (goal_condition='target', every --proc_obs / --proc_tgt
+  value) or the unconditional `e2e_vmc` (goal_condition='none'), cartesian or velocity control."""
 
   def __init__(self, cfg: E2EVMCConfig, batch_size=None, precision='fp32', training=True, carry_state=False,
-               device=None):
-    _check_switches(cfg)
+               device=None, goal_condition='target'):
+    _check_switches(cfg, goal_condition)
+    self.goal_condition = goal_condition
+    self.scope = 'GoalVMC' if goal_condition == 'target' else 'VMC'
     if not torch.cuda.is_available():
       raise RuntimeError("geeco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     self.lib = _lib.load()
@@ -60,6 +63,11 @@ class Engine(object):
               'dim_s_diff', 'dim_h_lstm', 'dim_h_fc', 'num_grp_states'):
       setattr(c, k, int(getattr(cfg, k)))
     c.batch_size = self.N
+    c.goal_condition = _lib.GOAL_CONDITION[goal_condition]
+    c.proc_obs = _lib.PROC_OBS.get(cfg.proc_obs, 0)
+    c.proc_tgt = _lib.PROC_TGT.get(cfg.proc_tgt, 0)
+    c.control_mode = _lib.CONTROL_MODE[cfg.control_mode]
+    c.dim_grp_command = int(cfg.dim_grp_command)
     c.precision = {'fp32': _lib.GEECO_FP32, 'bf16': _lib.GEECO_BF16}[precision]
     c.carry_state = 1 if carry_state else 0
     c.training = 1 if training else 0
@@ -95,13 +103,13 @@ class Engine(object):
       _lib.check(self.lib.geeco_grad_bucket(ctx, b, C.byref(off), C.byref(cnt)))
       self.buckets.append((int(off.value), int(cnt.value)))
     self.global_step = 0
-    self.NH = 9 + cfg.num_grp_states
+    self.NH = int(self.lib.geeco_head_columns(C.byref(c)))
     # persistent device inputs/outputs + pinned host staging (allocated lazily)
-    self._dev_in, self._pin_in = {}, {}
+    self._dev_in, self._pin_in, self._pin_busy = {}, {}, {}
     self.out_heads = torch.zeros(self.N, self.NH, dtype=torch.float32, device=self.device)
     self.out_fc1 = torch.zeros(self.N, cfg.dim_h_fc, dtype=torch.float32, device=self.device)
     self.out_state = torch.zeros(self.N, 2 * cfg.dim_h_lstm, dtype=torch.float32, device=self.device)
-    self.out_losses = torch.zeros(8, dtype=torch.float32, device=self.device)
+    self.out_losses = torch.zeros(_lib.NUM_LOSS_SLOTS, dtype=torch.float32, device=self.device)
     self._out_dyn = None
 
   # ------------------------------------------------------------------ lifecycle
@@ -186,7 +194,15 @@ class Engine(object):
     cfg, N, K = self.cfg, self.N, self.cfg.window_size
     H, W, Cc = cfg.img_height, cfg.img_width, cfg.img_channels
     return {'rgb': (N, K, H, W, Cc), 'target_rgb': (N, H, W, Cc), 'jnt_state': (N, K, cfg.dim_jnt_state),
-            'ee_state': (N, K, 7), 'obj_state': (N, K, 7), 'cmd': (N, 4)}
+            'ee_state': (N, K, 7), 'obj_state': (N, K, 7), 'cmd': (N, 4), 'vel_target': (N, cfg.dim_jnt_state),
+            'ee_target': (N, 7), 'grp_target': (N, cfg.dim_grp_command)}
+
+  def _feature_keys(self, with_labels):
+    keys = ['rgb'] + (['target_rgb'] if self.goal_condition == 'target' else []) + ['jnt_state']
+    return keys + (['ee_state', 'obj_state'] if with_labels else [])
+
+  def _label_keys(self):
+    return _LABEL_KEYS[self.cfg.control_mode]
 
   @staticmethod
   def _wire_dtype(key, dtype):
@@ -213,9 +229,25 @@ class Engine(object):
       return self._dev_in[dk]
     if dk not in self._pin_in:
       self._pin_in[dk] = torch.empty(shape, dtype=wd).pin_memory()
+    self._pin_wait(dk)                                     # the upload that last read this pinned buffer is done
     self._pin_in[dk].copy_(arr)
     self._dev_in[dk].copy_(self._pin_in[dk], non_blocking=True)
+    self._pin_mark(dk, torch.cuda.current_stream(self.device))
     return self._dev_in[dk]
+
+  # A pinned staging buffer is written by the HOST (`pin.copy_`) and read by an asynchronous H2D copy.  Nothing in
+  # a train step synchronises the host, so the host may run several steps ahead of the device: before it rewrites
+  # a pinned buffer it waits for the event recorded right after the copy that last read that buffer.
+  def _pin_wait(self, key):
+    ev = self._pin_busy.get(key)
+    if ev is not None:
+      ev.synchronize()
+
+  def _pin_mark(self, key, stream):
+    ev = self._pin_busy.get(key)
+    if ev is None:
+      ev = self._pin_busy[key] = torch.cuda.Event()
+    ev.record(stream)
 
   # ---- double-buffered staging: upload batch i+1 on a copy stream while batch i computes -------------
   def stage(self, features, labels, slot):
@@ -231,9 +263,9 @@ class Engine(object):
     with torch.cuda.stream(self._copy_stream):
       if self._stage_free[slot] is not None:
         self._copy_stream.wait_event(self._stage_free[slot])      # the step that last read this slot is done
-      items = [(k, features[k]) for k in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state') if k in features]
+      items = [(k, features[k]) for k in self._feature_keys(True) if k in features]
       if labels is not None:
-        items.append(('cmd', labels['cmd']))
+        items += [(k, labels[k]) for k in self._label_keys()]
       for k, v in items:
         if torch.is_tensor(v) and v.is_cuda:
           out[k] = v
@@ -248,13 +280,16 @@ class Engine(object):
           if (k, wd, slot) not in self._pin_in:
             self._pin_in[(k, wd, slot)] = torch.empty(shapes[k], dtype=wd).pin_memory()
           pin = self._pin_in[(k, wd, slot)]
+          self._pin_wait((k, wd, slot))
           pin.copy_(t)
-          t = pin
-        bufs[(k, wd)].copy_(t, non_blocking=True)
+          bufs[(k, wd)].copy_(pin, non_blocking=True)
+          self._pin_mark((k, wd, slot), self._copy_stream)
+        else:
+          bufs[(k, wd)].copy_(t, non_blocking=True)
         out[k] = bufs[(k, wd)]
       ev = torch.cuda.Event()
       ev.record(self._copy_stream)
-    return out, ({'cmd': out['cmd']} if labels is not None else None), ev
+    return out, ({k: out[k] for k in self._label_keys()} if labels is not None else None), ev
 
   def wait_staged(self, event, slot):
     torch.cuda.current_stream(self.device).wait_event(event)
@@ -266,30 +301,39 @@ class Engine(object):
     self._stage_free[slot] = ev
 
   def h2d_bytes(self, with_labels=True, frames_u8=False):
-    keys = list(_FEATURE_KEYS) + (['cmd'] if with_labels else [])
-    if not with_labels:
-      keys = ['rgb', 'target_rgb', 'jnt_state']
+    keys = self._feature_keys(with_labels) + (list(self._label_keys()) if with_labels else [])
     return int(sum((1 if frames_u8 and k in _FRAME_KEYS else 4) * int(np.prod(self._shapes()[k])) for k in keys))
 
-  def _batch(self, features, labels):
+  def _batch(self, features, labels, ring_start=0, reset_mask=None):
     b = _lib.GeecoBatch()
     keep = []
-    for k in ('rgb', 'target_rgb', 'jnt_state'):
+    fkeys = self._feature_keys(False)
+    for k in fkeys:
       t = self._to_device(k, features[k])
       keep.append(t)
       setattr(b, k, t.data_ptr())
-    if keep[0].dtype != keep[1].dtype:
+    if 'target_rgb' in fkeys and keep[0].dtype != keep[1].dtype:
       raise ValueError("rgb is %s but target_rgb is %s: both must be float32 in [0,1] or both uint8 [0..255]"
                        % (keep[0].dtype, keep[1].dtype))
     b.frame_format = _lib.FRAMES_U8 if keep[0].dtype == torch.uint8 else _lib.FRAMES_F32
+    b.ring_start = int(ring_start)
+    if reset_mask is not None:
+      if not (torch.is_tensor(reset_mask) and reset_mask.is_cuda and reset_mask.dtype in (torch.uint8, torch.bool)
+              and reset_mask.numel() == self.N and reset_mask.is_contiguous()):
+        raise ValueError("reset_mask must be a contiguous CUDA uint8 / bool tensor of batch_size entries")
+      keep.append(reset_mask)
+      b.reset_mask = reset_mask.data_ptr()
     if labels is not None:
       for k in ('ee_state', 'obj_state'):
         t = self._to_device(k, features[k])
         keep.append(t)
         setattr(b, k, t.data_ptr())
-      t = self._to_device('cmd', labels['cmd'])
-      keep.append(t)
-      b.cmd = t.data_ptr()
+      for k in self._label_keys():
+        if k not in labels:
+          raise KeyError("labels['%s'] is needed for control_mode=%s" % (k, self.cfg.control_mode))
+        t = self._to_device(k, labels[k])
+        keep.append(t)
+        setattr(b, k, t.data_ptr())
     return b, keep
 
   def _outputs(self, want_dyn=False, want_losses=True):
@@ -307,26 +351,38 @@ class Engine(object):
     return o
 
   # ------------------------------------------------------------------ steps
-  def forward(self, features, labels=None, want_dyn=False):
-    """goal_e2evmc forward (+ losses when labels are given).  Returns a dict of DEVICE tensors
-    (views of persistent output buffers, overwritten by the next call)."""
-    b, keep = self._batch(features, labels)
+  def forward(self, features, labels=None, want_dyn=False, ring_start=0, reset_mask=None):
+    """Forward of the graph (+ losses when labels are given).  Returns a dict of DEVICE tensors (views of
+    persistent output buffers, overwritten by the next call).  ring_start / reset_mask: geeco_batch in
+    include/geeco_b200.h (frame history as a ring; rows whose carried LSTM state is cleared)."""
+    b, keep = self._batch(features, labels, ring_start, reset_mask)
     o = self._outputs(want_dyn=want_dyn, want_losses=labels is not None)
     _lib.check(self.lib.geeco_forward(self._ctx, C.byref(b), C.byref(o), self._stream()))
     return self._endpoints(want_dyn, labels is not None)
 
+  def head_slices(self):
+    """Endpoint name -> column slice of the heads matrix, in the order the graph creates the heads (graph.py:233-259)."""
+    cfg = self.cfg
+    if cfg.control_mode == 'cartesian':
+      heads = [('pred_cmd_ee', 3), ('logits_cmd_grp', cfg.num_grp_states)]
+    else:
+      heads = [('pred_cmd_vel', cfg.dim_jnt_state), ('pred_cmd_ee', 3), ('pred_cmd_grp', cfg.dim_grp_command)]
+    out, col = OrderedDict(), 0
+    for name, width in heads + [('pred_aux_ee', 3), ('pred_aux_obj', 3)]:
+      out[name] = slice(col, col + width)
+      col += width
+    return out
+
   def _endpoints(self, want_dyn, with_losses):
-    G = self.cfg.num_grp_states
     h = self.out_heads
-    ep = OrderedDict()
-    ep['pred_cmd_ee'] = h[:, 0:3]
-    ep['logits_cmd_grp'] = h[:, 3:3 + G]
-    ep['pred_aux_ee'] = h[:, 3 + G:6 + G]
-    ep['pred_aux_obj'] = h[:, 6 + G:9 + G]
+    ep = OrderedDict((name, h[:, sl]) for name, sl in self.head_slices().items())
     ep['fc1'] = self.out_fc1
     ep['lstm_state'] = self.out_state
     if want_dyn:
-      ep['dynbuff'], ep['dyndiff'] = self._out_dyn
+      if self.goal_condition == 'target' and self.cfg.proc_obs == 'dynimg':
+        ep['dynbuff'] = self._out_dyn[0]
+      if self.goal_condition == 'target' and (self.cfg.proc_obs == 'dynimg' or self.cfg.proc_tgt == 'dyndiff'):
+        ep['dyndiff'] = self._out_dyn[1]
     if with_losses:
       ep['losses'] = self.out_losses
     return ep
@@ -362,7 +418,7 @@ class Engine(object):
   def read_losses_async(self, losses, slot):
     """Starts the device->host copy of one step's loss vector into pinned slot 0/1; returns (pinned, event)."""
     if not hasattr(self, '_loss_pins'):
-      self._loss_pins = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+      self._loss_pins = [torch.empty(_lib.NUM_LOSS_SLOTS, dtype=torch.float32).pin_memory() for _ in range(2)]
     pin = self._loss_pins[slot]
     pin.copy_(losses, non_blocking=True)
     ev = torch.cuda.Event()
@@ -371,7 +427,10 @@ class Engine(object):
 
   def losses_dict(self, losses=None):
     v = (self.out_losses if losses is None else losses).detach().cpu().numpy()
-    return OrderedDict(zip(LOSS_KEYS, [float(x) for x in v[:6]]))
+    d = OrderedDict(zip(LOSS_KEYS, [float(x) for x in v[:6]]))
+    if self.cfg.control_mode == 'velocity':
+      d['loss_cmd_vel'] = float(v[LOSS_SLOT_CMD_VEL])
+    return d
 
   # ------------------------------------------------------------------ debugging
   def debug_buffer(self, name):

@@ -69,10 +69,13 @@ def save_checkpoint(engine, model_dir, keep_max=2, fmt='npz'):
     if engine.training:
       arrays[n + '/Adam'] = engine.view(n, engine.adam_m).detach().cpu().numpy()
       arrays[n + '/Adam_1'] = engine.view(n, engine.adam_v).detach().cpu().numpy()
-  arrays['beta1_power'] = np.array(0.9 ** step, dtype=np.float32)
-  arrays['beta2_power'] = np.array(0.999 ** step, dtype=np.float32)
+  # tf.train.AdamOptimizer initialises its power accumulators to beta and multiplies AFTER every step: a checkpoint at
+  # global_step = t holds beta ** (t + 1)
+  arrays['beta1_power'] = np.array(0.9 ** (step + 1), dtype=np.float32)
+  arrays['beta2_power'] = np.array(0.999 ** (step + 1), dtype=np.float32)
   # the reference saves the (never written, all-zero) lstm_memory variable as well (graph.py:219,226)
-  arrays['GoalVMC/LSTMDecoder/lstm_memory'] = np.zeros((engine.N, 2 * engine.cfg.dim_h_lstm), dtype=np.float32)
+  arrays['%s/LSTMDecoder/lstm_memory' % getattr(engine, 'scope', 'GoalVMC')] = np.zeros(
+      (engine.N, 2 * engine.cfg.dim_h_lstm), dtype=np.float32)
   os.makedirs(model_dir, exist_ok=True)
   if fmt == 'bundle':
     from .checkpoint import write_bundle
@@ -147,28 +150,32 @@ def restore_checkpoint(engine, prefix):
 _ENGINES = {}
 
 
-def _engine_for(config: E2EVMCConfig, batch, precision, training):
+def _engine_for(config: E2EVMCConfig, batch, precision, training, goal_condition='target'):
   from .engine import Engine
-  key = (tuple(config), int(batch), precision, bool(training))
+  key = (tuple(config), int(batch), precision, bool(training), goal_condition)
   if key not in _ENGINES:
-    _ENGINES[key] = Engine(config, batch_size=batch, precision=precision, training=training)
+    _ENGINES[key] = Engine(config, batch_size=batch, precision=precision, training=training,
+                           goal_condition=goal_condition)
     _ENGINES[key].init_params(seed=0)
   return _ENGINES[key]
 
 
-def predictions_from_endpoints(ep):
-  """estimator.py:183-189 (cartesian control)."""
-  return {'cmd_ee': ep['pred_cmd_ee'], 'logits_cmd_grp': ep['logits_cmd_grp'], 'pos_ee': ep['pred_aux_ee'],
-          'pos_obj': ep['pred_aux_obj']}
+def predictions_from_endpoints(ep, control_mode='cartesian'):
+  """estimator.py:32-47 / :183-197."""
+  if control_mode == 'cartesian':
+    return {'cmd_ee': ep['pred_cmd_ee'], 'logits_cmd_grp': ep['logits_cmd_grp'], 'pos_ee': ep['pred_aux_ee'],
+            'pos_obj': ep['pred_aux_obj']}
+  return {'cmd_vel': ep['pred_cmd_vel'], 'cmd_ee': ep['pred_cmd_ee'], 'cmd_grp': ep['pred_cmd_grp'],
+          'pos_ee': ep['pred_aux_ee'], 'pos_obj': ep['pred_aux_obj']}
 
 
-def decode_observation(features, config):
-  """estimator.py:160-172: RGB-D observations are the depth frames concatenated behind the RGB channels
+def decode_observation(features, config, goal=True):
+  """estimator.py:17-29 / :160-176: RGB-D observations are the depth frames concatenated behind the RGB channels
   (`in_rgbd_frames`, `tgt_rgbd_frame`).  Features that already carry img_channels channels pass through."""
   if config.img_channels != 4 or np.shape(features['rgb'])[-1] == 4:
     return features
-  if 'depth' not in features or 'target_depth' not in features:
-    raise ValueError("observation_format rgbd needs features['depth'] and features['target_depth']")
+  if 'depth' not in features or (goal and 'target_depth' not in features):
+    raise ValueError("observation_format rgbd needs features['depth']" + (" and features['target_depth']" if goal else ""))
   import torch
 
   def cat(a, b):
@@ -183,36 +190,45 @@ def decode_observation(features, config):
 
   out = dict(features)
   out['rgb'] = cat(features['rgb'], features['depth'])
-  out['target_rgb'] = cat(features['target_rgb'], features['target_depth'])
+  if goal:
+    out['target_rgb'] = cat(features['target_rgb'], features['target_depth'])
   return out
 
 
-def e2evmc_model_fn(features, labels, mode, params):
-  """model_fn of the unconditional controller (estimator.py:14-141), imported by train_e2evmc.py:14 next to
-  goal_e2evmc_model_fn.  `e2e_vmc` is not on the CUDA path yet: calling it raises, no fallback."""
-  raise NotImplementedError("e2evmc_model_fn (--goal_condition none) is not on the CUDA path yet")
-
-
-def goal_e2evmc_model_fn(features, labels, mode, params):
-  """Eager counterpart of estimator.py:144-279.  `params`: {'e2evmc_config', 'log_steps', 'debug'} plus the
-  optional execution keys 'precision' ('bf16' | 'fp32') and 'engine' (reuse an existing Engine)."""
+def _model_fn(features, labels, mode, params, goal_condition):
   config = params['e2evmc_config']
   if config.img_channels not in (3, 4):
     raise ValueError("Unsupported number of channels for input frame: %d!" % config.img_channels)
   if mode not in (ModeKeys.TRAIN, ModeKeys.EVAL, ModeKeys.PREDICT):
     raise RuntimeError("Unknown estimator mode: %s" % (mode,))
-  features = decode_observation(features, config)
+  features = decode_observation(features, config, goal=goal_condition == 'target')
   batch = int(np.shape(features['rgb'])[0])
-  eng = params.get('engine') or _engine_for(config, batch, params.get('precision', 'bf16'), mode == ModeKeys.TRAIN)
+  eng = params.get('engine') or _engine_for(config, batch, params.get('precision', 'bf16'), mode == ModeKeys.TRAIN,
+                                            goal_condition)
+  if getattr(eng, 'goal_condition', goal_condition) != goal_condition:
+    raise ValueError("engine was built for goal_condition=%s, model_fn is the one of %s" % (eng.goal_condition, goal_condition))
   if mode == ModeKeys.PREDICT:
     ep = eng.forward(features, None)
     return EstimatorSpec(mode, None, None, None, {k: v.detach().cpu().numpy() for k, v in
-                                                   predictions_from_endpoints(ep).items()}, ep)
+                                                   predictions_from_endpoints(ep, config.control_mode).items()}, ep)
   if mode == ModeKeys.TRAIN:
     losses = parallel.data_parallel_step(eng, features, labels)
     return EstimatorSpec(mode, losses, 'adam', None, None, None)
   ep = eng.forward(features, labels)
   return EstimatorSpec(mode, ep['losses'], None, ep['losses'], None, ep)
+
+
+def e2evmc_model_fn(features, labels, mode, params):
+  """Eager counterpart of the unconditional controller's model_fn (estimator.py:14-141): `e2e_vmc` (graph.py:268-319)
+  over features['rgb'] / ['jnt_state'], cartesian or velocity losses (:63-98), Adam, the eval metrics of :104-117.
+  `params` as for goal_e2evmc_model_fn."""
+  return _model_fn(features, labels, mode, params, 'none')
+
+
+def goal_e2evmc_model_fn(features, labels, mode, params):
+  """Eager counterpart of estimator.py:144-279.  `params`: {'e2evmc_config', 'log_steps', 'debug'} plus the
+  optional execution keys 'precision' ('bf16' | 'fp32') and 'engine' (reuse an existing Engine)."""
+  return _model_fn(features, labels, mode, params, 'target')
 
 
 class Estimator(object):
@@ -228,6 +244,9 @@ class Estimator(object):
     self._batch = int(batch_size or self._cfg.batch_size)
     self._engine = None
     self._ckpt_format = self.params.get('checkpoint_format', 'npz')
+    # train_e2evmc.py:258-259 picks the model_fn from --goal_condition; the graph variant follows from it
+    self._goal = 'none' if model_fn is e2evmc_model_fn else self.params.get('goal_condition', 'target')
+    self._writers = {}
     self.last_train_losses = []
     os.makedirs(model_dir, exist_ok=True)
 
@@ -235,12 +254,13 @@ class Estimator(object):
   def engine(self):
     if self._engine is None:
       from .engine import Engine
-      self._engine = Engine(self._cfg, batch_size=self._batch, precision=self.precision, training=True)
+      self._engine = Engine(self._cfg, batch_size=self._batch, precision=self.precision, training=True,
+                            goal_condition=self._goal)
       self._engine.init_params(seed=int(self.params.get('seed', 0)))
       parallel.broadcast_parameters(self._engine)
       ckpt = latest_checkpoint(self.model_dir)
       if ckpt:
-        verify_checkpoint(ckpt, self._cfg)
+        verify_checkpoint(ckpt, self._cfg, self._goal)
         restore_checkpoint(self._engine, ckpt)
     return self._engine
 
@@ -255,7 +275,7 @@ class Estimator(object):
     eng = self.engine
     rank, _ = parallel.world_info()
     p = dict(self.params, engine=eng)
-    done, self.last_train_losses = 0, []
+    done, logged, self.last_train_losses = 0, 0, []
     log_steps = int(self.params.get('log_steps', 1000) or 1000)
     pending = None            # (global_step, pinned losses, copy-done event) of the last logged step
 
@@ -263,6 +283,10 @@ class Estimator(object):
       step, pin, ev = entry
       ev.synchronize()
       self.last_train_losses.append((step, eng.losses_dict(pin)))
+      if rank == 0 and self.params.get('summaries', True):
+        # estimator.py:262-265, :305-313: one scalar per member of GraphKeys.LOSSES every log_steps, into model_dir
+        from .summaries import loss_scalars
+        self._summary_writer('').scalars(step, loss_scalars(self.last_train_losses[-1][1], self._cfg.control_mode))
       if rank == 0 and self.params.get('debug'):
         print('step %d: %s' % self.last_train_losses[-1])
 
@@ -273,9 +297,10 @@ class Estimator(object):
       if eng.global_step % log_steps == 0 or done == 1:
         # the losses of a logged step travel to the host asynchronously and are read one step later, after the
         # next step has been enqueued, so the device never idles on the host round trip
-        entry = eng.read_losses_async(spec.loss, done & 1)
         if pending is not None:
-          resolve(pending)
+          resolve(pending)              # before its pinned slot can be reused
+        entry = eng.read_losses_async(spec.loss, logged & 1)
+        logged += 1
         pending = (eng.global_step,) + entry
       if rank == 0 and self.config.save_checkpoints_steps and eng.global_step % self.config.save_checkpoints_steps == 0:
         save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max, self._ckpt_format)
@@ -285,7 +310,15 @@ class Estimator(object):
       resolve(pending)
     if rank == 0 and self.params.get('save_final_checkpoint', True):
       save_checkpoint(eng, self.model_dir, self.config.keep_checkpoint_max, self._ckpt_format)
+    for w in self._writers.values():
+      w.flush()
     return self
+
+  def _summary_writer(self, sub):
+    if sub not in self._writers:
+      from .summaries import SummaryWriter
+      self._writers[sub] = SummaryWriter(os.path.join(self.model_dir, sub) if sub else self.model_dir)
+    return self._writers[sub]
 
   @staticmethod
   def _prefetched(eng, batches):
@@ -311,30 +344,47 @@ class Estimator(object):
       cur, slot = nxt, slot ^ 1
 
   def evaluate(self, input_fn, steps=None):
+    """estimator.py:100-117 / :246-258: streaming MSE per prediction key (sum of squared errors / element count over
+    the whole evaluation set), accuracy of the gripper class (cartesian), 'loss' = mean of the per-batch losses."""
     eng = self.engine
     p = dict(self.params, engine=eng)
+    cfg = self._cfg
+    if cfg.control_mode == 'cartesian':
+      mse_keys = [('cmd_ee', 0, 3), ('pos_ee', 2, 3), ('pos_obj', 3, 3)]            # (metric, loss slot, width)
+    else:
+      from .engine import LOSS_SLOT_CMD_VEL
+      mse_keys = [('cmd_vel', LOSS_SLOT_CMD_VEL, cfg.dim_jnt_state), ('cmd_ee', 0, 3),
+                  ('cmd_grp', 1, cfg.dim_grp_command), ('pos_ee', 2, 3), ('pos_obj', 3, 3)]
     loss_sum, nb = 0.0, 0
-    se = {'cmd_ee': 0.0, 'pos_ee': 0.0, 'pos_obj': 0.0}
-    cnt, correct, rows = 0, 0.0, 0
+    se = {k: 0.0 for k, _, _ in mse_keys}
+    correct, rows = 0.0, 0
     for features, labels in input_fn():
       self._check_batch(features)
       spec = self._model_fn(features, labels, ModeKeys.EVAL, p)
       v = spec.loss.detach().cpu().numpy().astype(np.float64)
       n = int(v[7])
       loss_sum += v[5]; nb += 1
-      # v[0], v[2], v[3] are per-batch MSEs (mean over n*3): recover the sums for the streaming metric
-      se['cmd_ee'] += v[0] * n * 3; se['pos_ee'] += v[2] * n * 3; se['pos_obj'] += v[3] * n * 3
-      cnt += n * 3; correct += v[6]; rows += n
+      # the loss slots are per-batch MSEs (mean over n*width): recover the sums for the streaming metric
+      for k, slot, width in mse_keys:
+        se[k] += v[slot] * n * width
+      correct += v[6]; rows += n
       if steps is not None and nb >= steps:
         break
     # data parallel: every rank evaluated its share of each global batch; the accumulators add across ranks, so all
     # ranks return the metrics of the whole evaluation set (what the single-process reference computes)
-    loss_sum, nb, se['cmd_ee'], se['pos_ee'], se['pos_obj'], cnt, correct, rows = parallel.allreduce_sums(
-        [loss_sum, nb, se['cmd_ee'], se['pos_ee'], se['pos_obj'], cnt, correct, rows])
+    red = parallel.allreduce_sums([loss_sum, nb, correct, rows] + [se[k] for k, _, _ in mse_keys])
+    loss_sum, nb, correct, rows = red[:4]
     if nb == 0:
       raise ValueError("evaluate(): input_fn yielded no batches")
-    out = {k: se[k] / cnt for k in se}
-    out.update({'loss': loss_sum / nb, 'cmd_grp': correct / rows, 'global_step': eng.global_step})
+    out = {k: red[4 + i] / (rows * width) for i, (k, _, width) in enumerate(mse_keys)}
+    if cfg.control_mode == 'cartesian':
+      out['cmd_grp'] = correct / rows
+    out.update({'loss': loss_sum / nb, 'global_step': eng.global_step})
+    rank, _ = parallel.world_info()
+    if rank == 0 and self.params.get('summaries', True):
+      w = self._summary_writer('eval')                       # tf.estimator writes evaluation summaries to model_dir/eval
+      w.scalars(eng.global_step, {k: v for k, v in out.items() if k != 'global_step'})
+      w.flush()
     return out
 
   def predict(self, input_fn):

@@ -31,10 +31,16 @@ def conv_encoder(rgb_frame, params, scope='GoalVMC/ConvEncoder'):
 
 
 def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, reset, engine):
-  """graph.py:321-416 through an Engine built for params (E2EVMCConfig).  `reset` is accepted for signature
-  compatibility; in the reference it only selects between two all-zero LSTM states (graph.py:218-220,226).
-  Returns (net = fc1 [N,dim_h_fc], endpoints dict) of device tensors."""
+  """graph.py:321-416 through an Engine built for params (E2EVMCConfig), every --proc_obs / --proc_tgt value.
+  `reset` is accepted for signature compatibility; in the reference it only selects between two all-zero LSTM states
+  (graph.py:218-220,226).  Returns (net = fc1 [N,dim_h_fc], endpoints dict) of device tensors."""
   ep = engine.forward({'rgb': rgb_frames, 'jnt_state': jnt_states, 'target_rgb': tgt_frame}, None, want_dyn=True)
+  return ep['fc1'], ep
+
+
+def e2e_vmc(rgb_frames, jnt_states, reset, engine):
+  """graph.py:268-319 (the unconditional baseline) through an Engine built with goal_condition='none'."""
+  ep = engine.forward({'rgb': rgb_frames, 'jnt_state': jnt_states}, None)
   return ep['fc1'], ep
 
 

@@ -39,9 +39,20 @@ extern "C" {
 
 typedef struct geeco_ctx geeco_ctx;
 
-/* Subset of E2EVMCConfig (src/models/e2evmc/params.py:7-28) that shapes the GEECO-F graph
- * (goal_condition=target, proc_obs=dynimg, proc_tgt=dyndiff, control_mode=cartesian), plus
- * the execution switches of this library. */
+/* Graph switches: the values of train_e2evmc.py's --goal_condition / --proc_obs / --proc_tgt / --control_mode
+ * (scripts/train_e2evmc.py:34-75).  Zero everywhere = GEECO-F (goal_e2evmc, dynimg, dyndiff, cartesian). */
+enum { GEECO_GOAL_TARGET = 0,   /* goal_e2evmc, graph.py:321-416 (scope GoalVMC) */
+       GEECO_GOAL_NONE = 1 };   /* e2e_vmc, graph.py:268-319 (scope VMC); proc_obs / proc_tgt are ignored */
+enum { GEECO_OBS_DYNIMG = 0,    /* graph.py:386-407: current frame + rank-pooled buffer + rank-pooled goal difference */
+       GEECO_OBS_SEQUENCE = 1 };/* graph.py:360-385: every frame through the encoder, K LSTM steps */
+enum { GEECO_TGT_DYNDIFF = 0,   /* graph.py:371-379 / :396-402 */
+       GEECO_TGT_CONSTANT = 1,  /* graph.py:352-355,365-367: target frame through ConvEncoder, concatenated */
+       GEECO_TGT_RESIDUAL = 2 };/* graph.py:368-370: tgt_feat - feat */
+enum { GEECO_CTRL_CARTESIAN = 0,/* heads pred_cmd_ee, logits_cmd_grp (graph.py:233-239) */
+       GEECO_CTRL_VELOCITY = 1 };/* heads pred_cmd_vel, pred_cmd_ee, pred_cmd_grp (graph.py:240-249), mse_loss (:430-450) */
+
+/* Subset of E2EVMCConfig (src/models/e2evmc/params.py:7-28) that shapes the graph, plus the execution
+ * switches of this library. */
 typedef struct geeco_config {
   int32_t img_height, img_width, img_channels;
   int32_t dim_jnt_state, window_size;
@@ -51,7 +62,11 @@ typedef struct geeco_config {
   int32_t carry_state;    /* 0: zero LSTM state at every call, as the reference executes (dead assign,
                              graph.py:226); 1: carry [c|m] across calls (the intended semantics) */
   int32_t training;       /* 1: reserve backward + optimizer workspace */
-  int32_t reserved0;
+  int32_t goal_condition; /* GEECO_GOAL_*  */
+  int32_t proc_obs;       /* GEECO_OBS_*   */
+  int32_t proc_tgt;       /* GEECO_TGT_*   */
+  int32_t control_mode;   /* GEECO_CTRL_*  */
+  int32_t dim_grp_command;/* width of pred_cmd_grp in velocity mode (params.py: dim_grp_command = 2) */
   float lr, lambda_aux, l2_regularizer;          /* params.py:24-27 */
   float adam_beta1, adam_beta2, adam_eps;        /* tf.train.AdamOptimizer defaults 0.9 / 0.999 / 1e-8 */
 } geeco_config;
@@ -80,26 +95,36 @@ enum { GEECO_FRAMES_F32 = 0,   /* float32 in [0,1]: what model_fn receives (esti
 
 typedef struct geeco_batch {
   const void* rgb;          /* [N,K,H,W,C]               features['rgb'] (+depth as 4th channel for rgbd) */
-  const void* target_rgb;   /* [N,H,W,C]                 features['target_rgb'] */
+  const void* target_rgb;   /* [N,H,W,C]                 features['target_rgb']; unused (may be NULL) with GEECO_GOAL_NONE */
   const float* jnt_state;   /* [N,K,J]                   features['jnt_state'] */
   const float* ee_state;    /* [N,K,7] or NULL           features['ee_state']   (losses only) */
   const float* obj_state;   /* [N,K,7] or NULL           features['obj_state']  (losses only) */
-  const float* cmd;         /* [N,4]   or NULL           labels['cmd']          (losses only) */
+  const float* cmd;         /* [N,4]   or NULL           labels['cmd']          (losses, cartesian control) */
+  const float* vel_target;  /* [N,J]   or NULL           labels['vel_target']   (losses, velocity control; estimator.py:230-236) */
+  const float* ee_target;   /* [N,7]   or NULL           labels['ee_target']    (first three columns are used) */
+  const float* grp_target;  /* [N,dim_grp_command] / NULL labels['grp_target'] */
+  const uint8_t* reset_mask;/* [N] or NULL; with carry_state = 1 the rows whose byte is non-zero start from the zero LSTM
+                               state (an environment that was reset); ignored with carry_state = 0 */
   int32_t frame_format;     /* GEECO_FRAMES_F32 | GEECO_FRAMES_U8: element type of rgb AND target_rgb */
-  int32_t reserved0;
+  int32_t ring_start;       /* rgb / jnt_state as ring buffers over the K axis: physical slot of the OLDEST frame; logical
+                               frame k lives in slot (ring_start + k) % K.  0 = plain layout */
 } geeco_batch;
 
-/* Optional outputs (NULL = not wanted).  heads = [pred_cmd_ee 0:3 | logits_cmd_grp 3:3+G |
- * pred_aux_ee | pred_aux_obj] (graph.py:233-259). */
+/* Optional outputs (NULL = not wanted).  heads, cartesian control = [pred_cmd_ee 0:3 | logits_cmd_grp 3:3+G |
+ * pred_aux_ee | pred_aux_obj] (graph.py:233-259); velocity control = [pred_cmd_vel 0:J | pred_cmd_ee | pred_cmd_grp
+ * (dim_grp_command) | pred_aux_ee | pred_aux_obj] (graph.py:240-259): geeco_head_columns(). */
 typedef struct geeco_outputs {
-  float* heads;             /* [N, 9+G] */
+  float* heads;             /* [N, NH] */
   float* fc1;               /* [N, dim_h_fc]             endpoints['fc1'] */
-  float* dynbuff;           /* [N,H,W,C]                 endpoints['dynbuff']  (graph.py:393) */
-  float* dyndiff;           /* [N,H,W,C]                 endpoints['dyndiff']  (graph.py:401) */
+  float* dynbuff;           /* [N,H,W,C]                 endpoints['dynbuff']  (graph.py:393; dynimg graphs only) */
+  float* dyndiff;           /* [N,H,W,C]                 endpoints['dyndiff']  (graph.py:376,401; with sequence/dyndiff the
+                                                         image of the LAST frame, as the endpoint dict keeps it) */
   float* lstm_state;        /* [N, 2*dim_h_lstm]         [c | m] after the step */
-  float* losses;            /* [8]: loss_cmd_ee, loss_cmd_grp, loss_pos_ee, loss_pos_obj, loss_reg, loss,
-                                    #correct gripper classes, N   (estimator.py:218-239,246-254) */
+  float* losses;            /* [12]: loss_cmd_ee, loss_cmd_grp, loss_pos_ee, loss_pos_obj, loss_reg, loss,
+                                    #correct gripper classes (cartesian), N, loss_cmd_vel (velocity), 0, 0, 0
+                                    (estimator.py:218-239,246-254; graph.py:430-450) */
 } geeco_outputs;
+#define GEECO_NUM_LOSS_SLOTS 12
 
 const char* geeco_last_error(void);
 int geeco_version(void);
@@ -112,6 +137,8 @@ int geeco_destroy(geeco_ctx* ctx);
 int geeco_bind(geeco_ctx* ctx, float* theta, float* grad, float* m, float* v, void* workspace,
                int64_t workspace_bytes);
 int geeco_param_info(const geeco_ctx* ctx, int32_t index, geeco_param_desc* out);
+/* number of columns of geeco_outputs.heads for this configuration */
+int geeco_head_columns(const geeco_config* cfg);
 /* gradient bucket `b` covers arena floats [offset, offset+numel); bucket b is complete after
  * geeco_step_backward(ctx, b, ...) returns (work enqueued on the stream). */
 int geeco_grad_bucket(const geeco_ctx* ctx, int32_t bucket, int64_t* offset, int64_t* numel);
@@ -189,6 +216,14 @@ int geeco_train_step(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outpu
 int geeco_step_forward(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outputs* out, void* stream);
 int geeco_step_backward(geeco_ctx* ctx, int32_t bucket, void* stream);
 int geeco_step_update(geeco_ctx* ctx, float grad_scale, void* stream);
+
+/* ---- K-frame history of many environments as a device ring (BASELINE config 4) ------------------------------------
+ * The FIFO of predictor.py:140-146 without shifting: writes frame[n] ([N][row_bytes]) into slot `slot` of
+ * ring [N][K][row_bytes]; rows with fresh[n] != 0 get it in ALL K slots (a new episode's buffer is padded by repeating its
+ * first frame, predictor.py:196-198).  row_bytes % 4 == 0; everything is device memory; no host synchronisation.  The step
+ * then reads the ring through geeco_batch.ring_start = (slot + 1) % K. */
+int geeco_ring_push(void* ring, const void* frame, const uint8_t* fresh, int32_t N, int32_t K, int64_t row_bytes,
+                    int32_t slot, void* stream);
 
 /* ---- introspection for tests / profiling ------------------------------------------------------ */
 /* internal activation buffers by name ("x0", "y1".."y8", "g1".."g8", "state", "gates", "dstate", ...);

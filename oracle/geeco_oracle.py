@@ -175,8 +175,12 @@ def round_bf16(x):
   return _RoundBF16.apply(x)
 
 
-def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False):
+def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False, relu_masks=None):
   """graph.py:61-117; `scope` e.g. 'GoalVMC/ConvEncoder'.
+
+  relu_masks (test aid, used with emulate_bf16): eight 0/1 tensors shaped like the layer outputs.  Layer l then
+  computes `z * mask_l` instead of `relu(z)`, i.e. the ReLU decisions are GIVEN (taken from the path under test)
+  instead of re-derived from this run's own roundings, which makes a bf16 gradient comparison free of mask flips.
 
   emulate_bf16=True restates the SAME graph with the storage roundings of the library's bf16 mode
   (DESIGN.md "bf16 policy"): encoder input, conv kernels, every post-ReLU activation except conv8's
@@ -192,7 +196,7 @@ def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False):
     if emulate_bf16:
       z = conv2d_same(net, round_bf16(w), round_bf16(b) if li == 0 else b, ENCODER_STRIDES[li], relu=False)
       z = _GradRoundBF16.apply(z)
-      net = torch.relu(z)
+      net = torch.relu(z) if relu_masks is None else z * relu_masks[li].to(z.dtype)
       if li < 7:
         net = round_bf16(net)
     else:
@@ -270,8 +274,9 @@ def lstm_decoder(feat_list, params, cfg, scope='GoalVMC/LSTMDecoder', init_state
 # model fns (graph.py:268-416)
 # --------------------------------------------------------------------------
 def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC', init_state=None,
-                alpha=None, emulate_bf16=False):
-  """graph.py:321-416.  rgb_frames [N,K,H,W,C], jnt_states [N,K,7], tgt_frame [N,H,W,C]."""
+                alpha=None, emulate_bf16=False, relu_masks=None):
+  """graph.py:321-416.  rgb_frames [N,K,H,W,C], jnt_states [N,K,7], tgt_frame [N,H,W,C].
+  relu_masks (dynimg branch only): {'obs' | 'dyn' | 'diff': eight masks}, see conv_encoder."""
   ep = OrderedDict()
   K = cfg['window_size']
   frames = [rgb_frames[:, k] for k in range(K)]
@@ -298,14 +303,16 @@ def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC',
   elif proc_obs == 'dynimg':
     cur, jnt = frames[-1], jnts[-1]
     eb = emulate_bf16
-    feat, acts = conv_encoder(cur, params, scope + '/ConvEncoder', return_all=True, emulate_bf16=eb)
+    rm = relu_masks or {}
+    feat, acts = conv_encoder(cur, params, scope + '/ConvEncoder', return_all=True, emulate_bf16=eb,
+                              relu_masks=rm.get('obs'))
     ep['obs_acts'] = acts
     dyn_buff = dynimg(rgb_frames, alpha)
     ep['dynbuff'] = dyn_buff
-    dyn_feat = conv_encoder(dyn_buff, params, scope + '/DynBuffEncoder', emulate_bf16=eb)
+    dyn_feat = conv_encoder(dyn_buff, params, scope + '/DynBuffEncoder', emulate_bf16=eb, relu_masks=rm.get('dyn'))
     dd = dyndiff(cur, tgt_frame)
     ep['dyndiff'] = dd
-    tgt_feat = conv_encoder(dd, params, scope + '/DynDiffEncoder', emulate_bf16=eb)
+    tgt_feat = conv_encoder(dd, params, scope + '/DynDiffEncoder', emulate_bf16=eb, relu_masks=rm.get('diff'))
     ep['conv8_obs'], ep['conv8_dyn'], ep['conv8_diff'] = feat, dyn_feat, tgt_feat
     feat_list.append(representation_concatenation_v2(feat, dyn_feat, jnt, tgt_feat))
   else:
@@ -513,13 +520,19 @@ def _to(x, dtype):
   return torch.as_tensor(np.asarray(x)).to(dtype) if not torch.is_tensor(x) else x.to(dtype)
 
 
-def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=False):
+def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=False, relu_masks=None, goal=True):
+  """goal=True: goal_e2evmc_model_fn (estimator.py:144-279); goal=False: e2evmc_model_fn (:14-141, the
+  unconditional `e2e_vmc` graph, no target frame)."""
   dt = next(iter(params.values())).dtype
   rgb = _to(features['rgb'], dt)
-  tgt = _to(features['target_rgb'], dt)
   jnt = _to(features['jnt_state'], dt)
   f2 = {'ee_state': _to(features['ee_state'], dt), 'obj_state': _to(features['obj_state'], dt)}
-  net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16)
+  if goal:
+    tgt = _to(features['target_rgb'], dt)
+    net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16,
+                          relu_masks=relu_masks)
+  else:
+    net, ep = e2e_vmc(rgb, jnt, params, cfg, init_state=init_state)
   if cfg['control_mode'] == 'velocity':
     l2 = {k: _to(labels[k], dt) for k in ('vel_target', 'ee_target', 'grp_target')}
     return losses_velocity(ep, f2, l2, params, cfg), ep
@@ -528,11 +541,12 @@ def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=
   return losses, ep
 
 
-def train_step(params, opt_state, features, labels, cfg, retain=(), emulate_bf16=False):
+def train_step(params, opt_state, features, labels, cfg, retain=(), emulate_bf16=False, relu_masks=None, goal=True):
   """model_fn in TRAIN mode: forward, losses, gradients, one Adam update (in place).
   Returns (losses, grads, endpoints)."""
   leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in params.items())
-  losses, ep = forward_losses(leaves, features, labels, cfg, emulate_bf16=emulate_bf16)
+  losses, ep = forward_losses(leaves, features, labels, cfg, emulate_bf16=emulate_bf16, relu_masks=relu_masks,
+                              goal=goal)
   for k in retain:
     ep[k].retain_grad()
   losses['loss'].backward()

@@ -75,7 +75,6 @@ _A('--device_frames', default=False, action='store_true',
 _A('--checkpoint_format', type=str, default='npz', help='npz | bundle (TF V2 .index/.data files)')
 
 _OBSERVATION_FORMAT_TO_CHANNELS = {'rgb': 3, 'rgbd': 4}
-_GOAL_CONDITIONS = ('none', 'target')
 
 
 def export_snapshot(model_dir, eval_results, num_best_ckpt):
@@ -158,11 +157,9 @@ def recorded_input_fn(args, config, mode, rank=0, world=1):
 
 def main(args, argv=None):
   from geeco_b200 import parallel
-  from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
-  if args.goal_condition not in _GOAL_CONDITIONS:
-    raise KeyError(args.goal_condition)
-  if args.goal_condition != 'target':
-    raise NotImplementedError("--goal_condition none (unconditional e2e_vmc) is not on the CUDA path yet")
+  from geeco_b200.estimator import Estimator, RunConfig, e2evmc_model_fn, goal_e2evmc_model_fn
+  # train_e2evmc.py:127-130, :258: the model_fn follows --goal_condition (KeyError for anything else)
+  model_fn = {'none': e2evmc_model_fn, 'target': goal_e2evmc_model_fn}[args.goal_condition]
   # the model config: an existing run directory overrides the model flags (train_e2evmc.py:229-232)
   config_name = 'e2evmc_config'
   have_config = os.path.exists(os.path.join(args.model_dir, config_name + '.json'))
@@ -179,12 +176,14 @@ def main(args, argv=None):
         'lr': args.lr})
   # everything that can be refused is refused before the run directory is touched
   from geeco_b200.engine import _check_switches
-  _check_switches(e2evmc_config)
+  _check_switches(e2evmc_config, args.goal_condition)
   if not args.dataset_dir.startswith('synthetic') and not os.path.isdir(args.dataset_dir):
     raise FileNotFoundError("--dataset_dir %s does not exist (use synthetic[:<episodes>] for synthetic episodes)"
                             % (args.dataset_dir,))
   import torch
   import torch.distributed as dist
+  if not torch.cuda.is_available():
+    raise RuntimeError("geeco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
   if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     dist.init_process_group('nccl')
@@ -195,7 +194,7 @@ def main(args, argv=None):
     if not have_config:
       save_model_config(e2evmc_config._asdict(), args.model_dir, config_name)
   run_config = RunConfig(save_checkpoints_steps=args.ckpt_steps, keep_checkpoint_max=args.num_last_ckpt)
-  estimator = Estimator(model_fn=goal_e2evmc_model_fn, model_dir=args.model_dir, config=run_config,
+  estimator = Estimator(model_fn=model_fn, model_dir=args.model_dir, config=run_config,
                         params={'e2evmc_config': e2evmc_config, 'log_steps': args.log_steps, 'debug': args.debug,
                                 'checkpoint_format': args.checkpoint_format},
                         precision=args.precision, batch_size=e2evmc_config.batch_size)

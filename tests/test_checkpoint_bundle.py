@@ -328,6 +328,9 @@ def test_estimator_checkpoint_protocol(tmp_path, fmt):
     names = BundleReader(latest_checkpoint(md)).names()
     assert 'GoalVMC/ConvEncoder/conv1/kernel/Adam_1' in names and 'beta2_power' in names and 'global_step' in names
     assert read_bundle(latest_checkpoint(md))['GoalVMC/LSTMDecoder/lstm_memory'].shape == (4, 16)
+    # tf.train.AdamOptimizer: the accumulators start at beta and are multiplied after each step -> beta ** (t + 1)
+    rb = read_bundle(latest_checkpoint(md))
+    assert rb['beta1_power'] == np.float32(0.9 ** 16) and rb['beta2_power'] == np.float32(0.999 ** 16)
   # an inference engine restores weights only, from either format
   c = _ArenaEngine(3); c.training = False
   m0 = c.adam_m.clone()

@@ -1,0 +1,129 @@
+"""Full-step parity at BASELINE.json's own batch sizes (N = 4: config 1, N = 64: config 2 and the bench line).
+
+At N = 64 the weight-gradient split counts, the one-wave grid sizes, the virtual groups and the tile counts of the
+CUDA path all differ from the N = 2 cases of test_gpu_step_*.py, so the step is held to the oracle there as well:
+  * fp32 mode: head outputs, losses and EVERY gradient tensor <= 1e-4 relative (north_star's fp32 tolerance);
+  * bf16 mode: head outputs and losses <= 2e-2 relative against the fp64 graph;
+  * bf16 gradients <= 2e-2 relative L2 against the oracle run with the same storage roundings AND the ReLU decisions
+    of the CUDA path (read back through geeco_debug_buffer), which removes mask flips from the comparison: what is
+    left is kernel arithmetic.  The comparison with the oracle's own masks stays in test_gpu_step_bf16.py (1e-1).
+The oracle runs in float64, four rows at a time (tests/util.py:oracle_step_chunked, exact for mean-reduced losses).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geeco_oracle as O
+from tests.util import engine_relu_masks, oracle_step_chunked, rel_l2, rel_max
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1800)]
+
+FP32_REL = 1e-4
+BF16_REL = 2e-2
+HEADS = ('pred_cmd_ee', 'logits_cmd_grp', 'pred_aux_ee', 'pred_aux_obj', 'fc1')
+LOSSES = ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss')
+
+
+def _setup(N, precision, seed=0, **over):
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import synthetic_batch
+  from geeco_b200.engine import Engine
+  cfg_d = O.make_config(batch_size=N, **over)
+  P = O.init_params(cfg_d, seed=seed, dtype=torch.float32, bias_scale=0.05)
+  feats, labels = synthetic_batch(N, seed=seed + 1)
+  eng = Engine(create_e2evmc_config(cfg_d), batch_size=N, precision=precision, training=True)
+  eng.set_params(P)
+  return cfg_d, {k: v.double() for k, v in P.items()}, feats, labels, eng
+
+
+@pytest.mark.parametrize('N', [4, 64])
+def test_fp32_train_step_at_baseline_batch(cuda_device, N):
+  cfg_d, P64, feats, labels, eng = _setup(N, 'fp32', seed=20 + N)
+  ref_l, ref_g, ep = oracle_step_chunked(O, P64, feats, labels, cfg_d, keep=HEADS)
+  out = eng.forward(feats, labels)
+  torch.cuda.synchronize()
+  for k in HEADS:
+    assert rel_max(out[k].cpu().numpy(), ep[k].numpy()) <= FP32_REL, k
+  got = eng.losses_dict(out['losses'])
+  for k in LOSSES:
+    assert abs(got[k] - ref_l[k]) <= FP32_REL * abs(ref_l[k]) + 1e-7, (k, got[k], ref_l[k])
+  theta0 = eng.get_params()
+  eng.train_step(feats, labels)
+  torch.cuda.synchronize()
+  grads = eng.get_grads()
+  worst = max((rel_max(grads[k], g.numpy()), k) for k, g in ref_g.items())
+  print("N=%d fp32 worst gradient rel_max: %.3e (%s)" % (N, worst[0], worst[1]))
+  assert worst[0] <= FP32_REL, worst
+  # TF-Adam step 1: theta moves by -lr * g / (|g| + eps / sqrt(1 - beta2))
+  theta1, lr = eng.get_params(), cfg_d['lr']
+  for k, g in ref_g.items():
+    g = g.numpy()
+    want = -lr * g / (np.abs(g) + O.ADAM_EPS / np.sqrt(1.0 - O.ADAM_BETA2))
+    d = theta1[k].astype(np.float64) - theta0[k].astype(np.float64)
+    sure = np.abs(g) > 1e-6 * (np.abs(g).max() + 1e-30)
+    assert np.abs(d - want)[sure].max(initial=0.0) <= 0.02 * lr, k
+
+
+@pytest.mark.parametrize('N', [4, 64])
+def test_bf16_train_step_at_baseline_batch(cuda_device, N):
+  cfg_d, P64, feats, labels, eng = _setup(N, 'bf16', seed=30 + N)
+  ref_l, ref_g, ep = oracle_step_chunked(O, P64, feats, labels, cfg_d, keep=HEADS)
+  out = eng.forward(feats, labels)
+  torch.cuda.synchronize()
+  report = {k: rel_max(out[k].cpu().numpy(), ep[k].numpy()) for k in HEADS}
+  got = eng.losses_dict(out['losses'])
+  report.update({k: abs(got[k] - ref_l[k]) / abs(ref_l[k]) for k in LOSSES})
+  print("\n".join("N=%d bf16 vs fp64 graph  %-20s %.3e" % (N, k, v) for k, v in report.items()))
+  bad = {k: v for k, v in report.items() if not v <= BF16_REL}
+  assert not bad, bad
+  # gradients, flip-free: the oracle takes the CUDA path's own ReLU decisions (and its bf16 storage roundings)
+  eng.train_step(feats, labels)
+  torch.cuda.synchronize()
+  grads = eng.get_grads()
+  masks = engine_relu_masks(eng, N)
+  emu_l, emu_g, _ = oracle_step_chunked(O, P64, feats, labels, cfg_d, emulate_bf16=True, relu_masks=masks)
+  gl = eng.losses_dict()
+  assert abs(gl['loss'] - emu_l['loss']) <= BF16_REL * abs(emu_l['loss'])
+  rep = {k: rel_l2(grads[k], g.numpy()) for k, g in emu_g.items() if float(g.abs().max()) > 0}
+  info = {k: rel_l2(grads[k], ref_g[k].numpy()) for k in rep}
+  print("\n".join("N=%d bf16 grad  %-52s flip-free %.3e   (vs fp64 graph, informational: %.3e)" % (N, k, v, info[k])
+                  for k, v in rep.items()))
+  bad = {k: v for k, v in rep.items() if not v <= BF16_REL}
+  assert not bad, bad
+  # rows / columns that are exactly zero in the graph (h-rows and forget-gate columns of the LSTM kernel)
+  gk = grads['GoalVMC/LSTMDecoder/lstm_cell/kernel']
+  assert np.all(gk[3100:, :] == 0.0) and np.all(gk[:, 256:384] == 0.0)
+
+
+def test_bf16_loss_curve_tracks_fp32_over_1k_steps(cuda_device):
+  """north_star: "loss curves tracking over 1k steps".  Both precisions run on the GPU from the same weights over
+  the same cycle of 8 synthetic batches (N = 4, lr 1e-3); the curves are compared as means over windows of 50
+  steps (single steps of two Adam trajectories are not comparable: they drift apart chaotically).  Bound: every
+  window mean within 10 % of the fp32 curve (+ 2 % of the initial loss as an absolute floor once the loss is
+  small), and both curves end below half of where they started."""
+  from geeco_b200.data import synthetic_batch
+  N, steps, win = 4, 1000, 50
+  cfg_d, P64, _, _, e16 = _setup(N, 'bf16', seed=40, lr=1e-3)
+  _, _, _, _, e32 = _setup(N, 'fp32', seed=40, lr=1e-3)
+  batches = []
+  for s in range(8):
+    f, l = synthetic_batch(N, seed=100 + s)
+    batches.append(({k: torch.as_tensor(v).cuda() for k, v in f.items() if k != 'step'},
+                    {k: torch.as_tensor(v).cuda() for k, v in l.items()}))
+  curves = {}
+  for name, eng in (('bf16', e16), ('fp32', e32)):
+    hist = torch.zeros(steps, device='cuda')
+    for t in range(steps):
+      f, l = batches[t % len(batches)]
+      hist[t] = eng.train_step(f, l)[5]
+    torch.cuda.synchronize()
+    curves[name] = hist.cpu().numpy().astype(np.float64)
+  a = curves['bf16'].reshape(-1, win).mean(axis=1)
+  b = curves['fp32'].reshape(-1, win).mean(axis=1)
+  dev = np.abs(a - b) / (b + 0.2 * b[0])          # == 0.10 bound below: |a-b| <= 0.10*b + 0.02*b[0]
+  print("window means bf16:", np.array2string(a, precision=4))
+  print("window means fp32:", np.array2string(b, precision=4))
+  print("max window deviation %.3e, first-step losses %.6f / %.6f" % (dev.max(), curves['bf16'][0], curves['fp32'][0]))
+  assert abs(curves['bf16'][0] - curves['fp32'][0]) <= BF16_REL * curves['fp32'][0]
+  assert dev.max() <= 0.10, dev
+  assert a[-1] < 0.5 * a[0] and b[-1] < 0.5 * b[0]

@@ -190,7 +190,9 @@ def model_fn(features, labels, mode, params):
   v = torch.tensor([features['mse'], 0., features['mse'] * 2, features['mse'] * 3, 0., features['loss'], features['hits'], 4.])
   return EstimatorSpec(mode, v, None, None, None, None)
 est = Estimator.__new__(Estimator)
-est._model_fn, est.params, est._batch, est._engine = model_fn, {}, 4, EvalEngine()
+from geeco_b200 import create_e2evmc_config
+est._model_fn, est.params, est._batch, est._engine = model_fn, {'summaries': False}, 4, EvalEngine()
+est._cfg = create_e2evmc_config({})
 est._check_batch = lambda f: None
 shard = [{'mse': 1.0 + rank, 'loss': 2.0 + rank, 'hits': 1.0 + 2 * rank}, {'mse': 3.0, 'loss': 4.0 - rank, 'hits': 2.0}]
 res = est.evaluate(lambda: iter([(f, None) for f in shard]))
@@ -257,10 +259,14 @@ def test_train_cli_refuses_before_touching_the_run_directory(tmp_path):
   m = _train_module()
   md = str(tmp_path / 'run')
   geecof = ['--goal_condition', 'target', '--proc_obs', 'dynimg', '--proc_tgt', 'dyndiff', '--model_dir', md]
-  with pytest.raises(NotImplementedError):          # reference default switches (sequence / constant): not on CUDA yet
-    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'target', '--dataset_dir', 'synthetic:1', '--model_dir', md]))
-  with pytest.raises(NotImplementedError):          # unconditional model
-    m.main(m.ARGPARSER.parse_args(['--goal_condition', 'none', '--model_dir', md]))
+  import torch
+  if not torch.cuda.is_available():
+    # every switch value of the reference is on the CUDA path: its default flags (sequence / constant, unconditional
+    # model) get as far as the device check -- there is no CPU fallback -- and still leave no run directory behind
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+      m.main(m.ARGPARSER.parse_args(['--goal_condition', 'target', '--dataset_dir', 'synthetic:1', '--model_dir', md]))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+      m.main(m.ARGPARSER.parse_args(['--goal_condition', 'none', '--dataset_dir', 'synthetic:1', '--model_dir', md]))
   with pytest.raises(FileNotFoundError):
     m.main(m.ARGPARSER.parse_args(geecof + ['--dataset_dir', str(tmp_path / 'nonexistent')]))
   with pytest.raises(ValueError):
@@ -322,13 +328,26 @@ def test_compat_import_paths():
   assert r.returncode == 0 and 'ok' in r.stdout, r.stdout
 
 
-def test_unconditional_twins_raise_instead_of_falling_back(tmp_path):
-  from geeco_b200.estimator import e2evmc_model_fn
+def test_unconditional_twins_need_the_cuda_path(tmp_path):
+  """`E2EVMCPredictor` / `e2evmc_model_fn` (--goal_condition none) have bodies now; without a CUDA device they raise
+  like every other entry point (no CPU fallback), after the reference's own argument errors."""
+  import torch
+  from geeco_b200 import create_e2evmc_config, save_model_config
+  from geeco_b200.estimator import ModeKeys, e2evmc_model_fn
   from geeco_b200.predictor import E2EVMCPredictor
-  with pytest.raises(NotImplementedError):
+  with pytest.raises(FileNotFoundError):                    # load_model_config(model_dir, 'e2evmc_config'), predictor.py:224
     E2EVMCPredictor(str(tmp_path))
-  with pytest.raises(NotImplementedError):
-    e2evmc_model_fn({}, {}, 'train', {})
+  cfg = create_e2evmc_config({})
+  with pytest.raises(RuntimeError, match='Unknown estimator mode'):                     # estimator.py:138-140
+    e2evmc_model_fn({'rgb': np.zeros((1, 4, 256, 256, 3), np.float32)}, None, 'serve', {'e2evmc_config': cfg})
+  with pytest.raises(ValueError, match='number of channels'):                           # estimator.py:27-29
+    e2evmc_model_fn({}, None, ModeKeys.PREDICT, {'e2evmc_config': cfg._replace(img_channels=5)})
+  if not torch.cuda.is_available():
+    save_model_config(cfg._asdict(), str(tmp_path), 'e2evmc_config')
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+      E2EVMCPredictor(str(tmp_path))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+      e2evmc_model_fn({'rgb': np.zeros((1, 4, 256, 256, 3), np.float32)}, None, ModeKeys.PREDICT, {'e2evmc_config': cfg})
 
 
 def test_target_frame_loaders(tmp_path):
