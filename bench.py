@@ -3,8 +3,10 @@
 
   python bench.py --gpus N --steps K --warmup W            our arm  (one process per GPU under torchrun for N>1)
   python bench.py --impl reference ...                      the CPU restatement of the reference graph
-  python bench.py --extras                                  + BASELINE configs 4 (batched policy steps) and 5
-                                                             (rank-pooling sweep), written to profiles/
+  python bench.py --extras                                  BASELINE configs 4 (batched policy steps) and 5 (rank-
+                                                             pooling sweep) in full, written to profiles/; every 1-GPU
+                                                             line carries a one-chunk / six-point version of both
+  python bench.py --scaling strong --gpus N                 BASELINE config 3: global batch 512 split over N GPUs
 
 Prints ONE JSON line on rank 0.  A "step" is one full train step (rank pooling -> 3 conv encoders ->
 LSTM cell -> heads -> losses -> backward -> Adam) on a synthetic batch of 64 windows per GPU
@@ -50,11 +52,17 @@ def parse_args():
   ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
   ap.add_argument('--precision', type=str, default=os.environ.get('GEECO_PRECISION', 'bf16'), choices=['bf16', 'fp32'])
   ap.add_argument('--batch', type=int, default=64, help='windows per GPU per step')
-  ap.add_argument('--cpu-batch', type=int, default=4, help='windows per step of the CPU baseline sample')
+  ap.add_argument('--cpu-batch', type=int, default=0,
+                  help='windows per step of the CPU arm / baseline (0: the per-GPU batch of the workload, at most 64)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
   ap.add_argument('--no-kernels', action='store_true', help='skip the isolated kernel roofline timings')
-  ap.add_argument('--extras', action='store_true', help='also run BASELINE configs 4 and 5 (1 GPU)')
+  ap.add_argument('--extras', action='store_true',
+                  help='BASELINE config 4 over all 4096 environments and the full config 5 sweep (default: one '
+                       '1024-environment chunk and a 6-point sweep subset)')
+  ap.add_argument('--scaling', type=str, default='weak', choices=['weak', 'strong'],
+                  help='weak: --batch windows per GPU; strong: BASELINE config 3, global batch 512 split over the GPUs')
+  ap.add_argument('--global-batch', type=int, default=512, help='global batch of --scaling strong')
   return ap.parse_args()
 
 
@@ -199,18 +207,30 @@ def time_input_pipeline(frames=24):
     shutil.rmtree(d, ignore_errors=True)
 
 
+def bench_config(args, world, precision=None):
+  """`config` of the JSON line: the workload both arms measure."""
+  per_gpu = args.global_batch // world if args.scaling == 'strong' else args.batch
+  return {'workload': WORKLOAD, 'per_gpu_batch': per_gpu, 'global_batch': per_gpu * world, 'window_size': 4,
+          'parallelism': 'dp%d' % world}
+
+
 def run_reference(args):
+  """Reference arm: the reference's CPU implementation of the path (the oracle port -- TensorFlow 1.15 is not
+  installable here) on all host cores, rank 0 only, EXACTLY --steps timed steps after --warmup warm-up steps.  One
+  step = one full train step on one batch of the workload's per-GPU size (a bounded sample of the N-GPU job: the CPU
+  has no second replica to add)."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  steps = max(1, min(args.steps, 10))
-  warm = max(1, min(args.warmup, 2))
-  cb = time_cpu_reference(args.cpu_batch, steps, warm)
+  world = int(os.environ.get('WORLD_SIZE', str(args.gpus)))
+  cfg = bench_config(args, max(world, 1))
+  batch = args.cpu_batch if args.cpu_batch > 0 else min(cfg['per_gpu_batch'], 64)
+  cb = time_cpu_reference(batch, args.steps, args.warmup)
   line = {
-      'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-      'warmup': warm, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+      'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': cb['ms_per_step'], 'higher_is_better': True, 'scaling': args.scaling,
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'per_step_sample': 'batch %d on host cores' % args.cpu_batch},
+      'config': cfg,
       'cpu_baseline': cb,
       'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
@@ -239,7 +259,10 @@ def run_ours(args):
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     dist.init_process_group('nccl', device_id=dev)
-  N = args.batch
+  bcfg = bench_config(args, world)
+  N = bcfg['per_gpu_batch']
+  if args.scaling == 'strong' and args.global_batch % world:
+    raise ValueError("--global-batch %d is not divisible by %d GPUs" % (args.global_batch, world))
   cfg = create_e2evmc_config(dict(proc_obs='dynimg', proc_tgt='dyndiff', batch_size=N))
   eng = Engine(cfg, batch_size=N, precision=args.precision, training=True, device=dev)
   eng.init_params(seed=0)
@@ -339,24 +362,25 @@ def run_ours(args):
   roofline, extra = kernel_rooflines(eng, dev, peaks, args) if (rank == 0 and not args.no_kernels) else (None, None)
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    cpu_baseline = time_cpu_reference(args.cpu_batch, 5, 2)
+    # bounded sample of the same workload on the host cores: one batch of the per-GPU size, 1 warm-up + 4 timed steps
+    cpu_baseline = time_cpu_reference(args.cpu_batch if args.cpu_batch > 0 else min(N, 64), 4, 1)
   input_pipeline = time_input_pipeline() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-  extras = run_extras(eng, dev, peaks, args) if (args.extras and rank == 0 and world == 1) else None
+  # the other half of BASELINE's metric (batched policy steps, config 4) and the rank-pooling sweep (config 5) ride in
+  # every single-GPU line: one 1024-environment chunk / six sweep points by default, everything with --extras
+  extras = run_extras(eng, dev, peaks, args, full=args.extras) if (rank == 0 and world == 1 and not args.no_kernels) else None
 
   if rank == 0:
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'bf16' if args.precision == 'bf16' else 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'per_gpu_batch': N, 'global_batch': N * world, 'window_size': 4,
-                   'parallelism': 'dp%d' % world,
-                   'l2_policy': 'inputs larger than L2: %d rotating batches x %.0f MB of frames' % (
-                       NB, eng.h2d_bytes(True) / 1e6),
-                   'master_weights': 'fp32', 'optimizer': 'TF-Adam fused'},
+        'config': dict(bcfg, l2_policy='inputs larger than L2: %d rotating batches x %.0f MB of frames' % (
+            NB, eng.h2d_bytes(True) / 1e6), master_weights='fp32', optimizer='TF-Adam fused'),
         'step_tflops': value * FLOP_PER_SAMPLE_TRAIN / 1e12,
         'final_loss': final_loss,
         'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roofline, 'kernels': extra,
-        'cpu_baseline': cpu_baseline, 'input_pipeline': input_pipeline, 'peaks': peaks, 'extras': extras,
+        'cpu_baseline': cpu_baseline, 'input_pipeline': input_pipeline, 'peaks': peaks,
+        'policy_steps': (extras or {}).get('policy_steps'), 'rankpool_sweep': (extras or {}).get('rankpool_sweep'),
     }
     emit(line)
   if world > 1:
@@ -452,57 +476,93 @@ def kernel_rooflines(eng, dev, peaks, args):
   e5 = entry('tc_nn_kernel<8,0> conv5 fwd', sec, N3 * (1024 * 128 + 256 * 192) * 2 + 192 * 1152 * 2, 2.0 * N3 * 256 * 192 * 1152,
              launches=2)
   e5['bound'] = 'tensor'
+  # tensor-pipe view of every layer above the ridge (conv4-conv8), all three passes, as stand-alone ops on 3 x batch
+  # images (each = the tcgen05 kernel + its few-microsecond weight repack / split reduce): FLOPs / time against the
+  # measured bf16 burst.  conv7 / conv8 hold 2 % of the FLOPs in 2-30 us launches: latency, not tensor, bound.
+  Hin, Cin = 64, 64
+  for li, Cout in ((4, 128), (5, 192), (6, 256), (7, 256), (8, 256)):
+    Ho = Hin // 2
+    x = torch.rand((N3, Hin, Hin, Cin), device=dev).to(torch.bfloat16)
+    w = ((torch.rand((3, 3, Cin, Cout), device=dev) - 0.5) * 0.1)
+    b = torch.zeros(Cout, device=dev)
+    g = (torch.rand((N3, Ho, Ho, Cout), device=dev) - 0.5).to(torch.bfloat16)
+    bits = ops.relu_mask_bits(x)
+    flops = 2.0 * N3 * Ho * Ho * Cout * 9 * Cin
+    act = N3 * (Hin * Hin * Cin + Ho * Ho * Cout) * 2 + 9 * Cin * Cout * 2
+    for tag, fn in (('fwd', lambda: ops.conv2d_same_bf16(x, w, b, stride=2)),
+                    ('dgrad', lambda: ops.conv2d_same_bwd_bf16(x, w, g, stride=2, relu_mask_bits=bits, need_dx=True, need_dw=False)),
+                    ('wgrad', lambda: ops.conv2d_same_bwd_bf16(x, w, g, stride=2, need_dx=False))):
+      if li == 5 and tag == 'fwd':
+        continue                                            # timed above
+      sec = _timed(dev, fn, flush=flush)
+      e = entry('conv%d %s' % (li, tag), sec, act, flops, launches=2)
+      e['bound'] = 'tensor'
+    del x, w, b, g, bits
+    Hin, Cin = Ho, Cout
   return dom, out
 
 
-def run_extras(eng, dev, peaks, args):
-  """BASELINE config 4 (batched closed-loop policy steps) and config 5 (rank-pooling sweep)."""
+def run_extras(eng, dev, peaks, args, full=False):
+  """BASELINE config 4 (batched closed-loop policy steps) and config 5 (rank-pooling sweep).
+  full=False: one chunk of 1024 environments and six sweep points (a second or two, part of every 1-GPU line);
+  full=True: all 4096 environments (4 chunks) and the whole K x resolution sweep."""
   import torch
   from geeco_b200 import ops
   from geeco_b200.predictor import BatchedGoalPredictor
   res = {}
   # ---- config 5: dynimg K=2..16 x {128,256,512} px, inputs >= 1 GiB
   sweep = []
-  for px in (128, 256, 512):
-    for K in (2, 3, 4, 6, 8, 12, 16):
-      per = K * px * px * 3 * 4
-      n = max(2, int(2 ** 30 // per) + 1)
-      n = min(n, 60000)
-      x = torch.rand((n, K, px, px, 3), device=dev)
-      y = torch.empty((n, px, px, 3), device=dev)
-      sec = _timed(dev, lambda: ops.dynimg(x, out=y), reps=3)
-      gbs = (K + 1) * px * px * 3 * 4 * n / sec / 1e9
-      sweep.append({'px': px, 'K': K, 'N': n, 'GBps': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm_gbs']})
-      del x, y
+  points = [(px, K) for px in (128, 256, 512) for K in (2, 3, 4, 6, 8, 12, 16)] if full else [
+      (128, 4), (256, 3), (256, 4), (256, 8), (256, 16), (512, 4)]
+  for px, K in points:
+    per = K * px * px * 3 * 4
+    n = min(max(2, int(2 ** 30 // per) + 1), 60000)
+    x = torch.rand((n, K, px, px, 3), device=dev)
+    y = torch.empty((n, px, px, 3), device=dev)
+    sec = _timed(dev, lambda: ops.dynimg(x, out=y), reps=3)
+    gbs = (K + 1) * px * px * 3 * 4 * n / sec / 1e9
+    sweep.append({'px': px, 'K': K, 'N': n, 'GBps': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm_gbs']})
+    del x, y
   res['rankpool_sweep'] = sweep
-  # ---- config 4: 4096 environments, processed as 4 chunks of 1024 (device-resident frame rings)
-  total_envs, chunk = 4096, 1024
+  # ---- config 4: 4096 environments as chunks of 1024; K-frame histories in a device ring of uint8 frames (what the
+  # hook renders, gym_pickplace.py:869-872), LSTM state carried across control steps, per-environment resets on the
+  # device.  Every control step pushes one NEW frame per environment and runs the forward.
+  total_envs, chunk = (4096, 1024) if full else (1024, 1024)
   cfg = eng.cfg
-  bp = BatchedGoalPredictor(cfg, chunk, precision=args.precision, carry_state=True)
+  bp = BatchedGoalPredictor(cfg, chunk, precision=args.precision, carry_state=True, frame_dtype='uint8')
   bp.engine.theta.copy_(eng.theta); bp.engine.params_changed()
-  goals = torch.rand((chunk, 256, 256, 3), device=dev)
-  bp.set_goal(goals)
-  frames = [torch.rand((chunk, 256, 256, 3), device=dev) for _ in range(2)]
+  bp.set_goal(torch.randint(0, 256, (chunk, 256, 256, 3), dtype=torch.uint8, device=dev))
+  frames = [torch.randint(0, 256, (chunk, 256, 256, 3), dtype=torch.uint8, device=dev) for _ in range(3)]
   jn = torch.rand((chunk, 7), device=dev)
-  for i in range(2):
-    bp.predict_batch(frames[i % 2], jn)
+  lib = bp.engine.lib
+  for i in range(4):
+    bp.predict_batch(frames[i % 3], jn)
   torch.cuda.synchronize()
+  lib.geeco_launch_count(1)
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   steps = 3
   e0.record()
   for s in range(steps):
     for c in range(total_envs // chunk):
-      out = bp.predict_batch(frames[(s + c) % 2], jn)
+      out = bp.predict_batch(frames[(s + c) % 3], jn)
   e1.record()
   torch.cuda.synchronize()
   sec = e0.elapsed_time(e1) * 1e-3 / steps
-  res['policy_steps'] = {'envs': total_envs, 'chunk': chunk, 'ms_per_control_step': sec * 1e3,
-                         'env_steps_per_s': total_envs / sec, 'tflops': total_envs * 3.415e9 / sec / 1e12,
-                         'carry_state': True, 'note': 'MuJoCo stepping excluded; frames synthetic, device resident'}
-  for d in ('profiles', 'gpurun_out'):                   # gpurun_out/ is what travels back from the GPU box
-    os.makedirs(os.path.join(ROOT, d), exist_ok=True)
-    with open(os.path.join(ROOT, d, 'r01_extras.json'), 'w') as fp:
-      json.dump(res, fp, indent=1)
+  res['policy_steps'] = {'metric': 'batched policy env-steps/s (BASELINE config 4)', 'envs': total_envs, 'chunk': chunk,
+                         'ms_per_control_step': sec * 1e3, 'env_steps_per_s': total_envs / sec,
+                         'tflops': total_envs * 3.415e9 / sec / 1e12,
+                         'tensor_frac_of_sustained': total_envs * 3.415e9 / sec / 1e12 / peaks['bf16_tflops_sustained'],
+                         'carry_state': True, 'frame_dtype': 'uint8', 'ring': 'device ring, index rotation',
+                         'gpu_launches_per_control_step': int(lib.geeco_launch_count(1)) // steps,
+                         'note': 'MuJoCo stepping excluded; frames synthetic, device resident; ' + (
+                             '4 chunks of 1024 environments' if full else
+                             'one chunk of 1024 environments (the 4096-environment job is 4 such chunks back to back: --extras)')}
+  del bp
+  if full:
+    for d in ('profiles', 'gpurun_out'):                   # gpurun_out/ is what travels back from the GPU box
+      os.makedirs(os.path.join(ROOT, d), exist_ok=True)
+      with open(os.path.join(ROOT, d, 'r02_extras.json'), 'w') as fp:
+        json.dump(res, fp, indent=1)
   return res
 
 

@@ -178,9 +178,11 @@ def round_bf16(x):
 def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False, relu_masks=None):
   """graph.py:61-117; `scope` e.g. 'GoalVMC/ConvEncoder'.
 
-  relu_masks (test aid, used with emulate_bf16): eight 0/1 tensors shaped like the layer outputs.  Layer l then
-  computes `z * mask_l` instead of `relu(z)`, i.e. the ReLU decisions are GIVEN (taken from the path under test)
-  instead of re-derived from this run's own roundings, which makes a bf16 gradient comparison free of mask flips.
+  relu_masks (test aid): eight 0/1 tensors shaped like the layer outputs.  Layer l then computes `z * mask_l`
+  instead of `relu(z)`, i.e. the ReLU decisions are GIVEN (taken from the path under test) instead of re-derived from
+  this run's own roundings.  A unit whose pre-activation is within rounding error of zero has a continuous output but
+  a discontinuous gradient mask, so two correct implementations in different precisions (fp32 / bf16 kernels vs this
+  float64 graph) disagree on a few such units; with the masks given the gradient comparison is free of those flips.
 
   emulate_bf16=True restates the SAME graph with the storage roundings of the library's bf16 mode
   (DESIGN.md "bf16 policy"): encoder input, conv kernels, every post-ReLU activation except conv8's
@@ -199,6 +201,8 @@ def conv_encoder(x_nhwc, params, scope, return_all=False, emulate_bf16=False, re
       net = torch.relu(z) if relu_masks is None else z * relu_masks[li].to(z.dtype)
       if li < 7:
         net = round_bf16(net)
+    elif relu_masks is not None:
+      net = conv2d_same(net, w, b, ENCODER_STRIDES[li], relu=False) * relu_masks[li].to(net.dtype)
     else:
       net = conv2d_same(net, w, b, ENCODER_STRIDES[li], relu=True)
     acts.append(net)
@@ -276,20 +280,24 @@ def lstm_decoder(feat_list, params, cfg, scope='GoalVMC/LSTMDecoder', init_state
 def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC', init_state=None,
                 alpha=None, emulate_bf16=False, relu_masks=None):
   """graph.py:321-416.  rgb_frames [N,K,H,W,C], jnt_states [N,K,7], tgt_frame [N,H,W,C].
-  relu_masks (dynimg branch only): {'obs' | 'dyn' | 'diff': eight masks}, see conv_encoder."""
+  relu_masks (see conv_encoder): dynimg branch {'obs' | 'dyn' | 'diff': eight masks}; sequence branch
+  {'frames': [eight masks per frame], 'tgt': eight masks, 'diff': [eight masks per frame]}."""
   ep = OrderedDict()
   K = cfg['window_size']
   frames = [rgb_frames[:, k] for k in range(K)]
   jnts = [jnt_states[:, k] for k in range(K)]
   proc_obs, proc_tgt = cfg['proc_obs'], cfg['proc_tgt']
+  rm = relu_masks or {}
   if proc_tgt in ('constant', 'residual'):
-    tgt_feat = conv_encoder(tgt_frame, params, scope + '/ConvEncoder')
+    tgt_feat = conv_encoder(tgt_frame, params, scope + '/ConvEncoder', emulate_bf16=emulate_bf16,
+                            relu_masks=rm.get('tgt') if proc_obs == 'sequence' else None)
   elif proc_tgt != 'dyndiff':
     raise ValueError("Unknown processing mode for target image: %s!" % (proc_tgt,))
   feat_list = []
   if proc_obs == 'sequence':
-    for frame, jnt in zip(frames, jnts):
-      feat = conv_encoder(frame, params, scope + '/ConvEncoder')
+    for t, (frame, jnt) in enumerate(zip(frames, jnts)):
+      feat = conv_encoder(frame, params, scope + '/ConvEncoder', emulate_bf16=emulate_bf16,
+                          relu_masks=rm['frames'][t] if 'frames' in rm else None)
       if proc_tgt == 'constant':
         state = representation_concatenation(feat, tgt_feat, jnt)
       elif proc_tgt == 'residual':
@@ -297,13 +305,13 @@ def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC',
       else:
         dd = dyndiff(frame, tgt_frame)
         ep['dyndiff'] = dd
-        dfeat = conv_encoder(dd, params, scope + '/DynDiffEncoder')
+        dfeat = conv_encoder(dd, params, scope + '/DynDiffEncoder', emulate_bf16=emulate_bf16,
+                             relu_masks=rm['diff'][t] if 'diff' in rm else None)
         state = representation_concatenation(feat, dfeat, jnt)
       feat_list.append(state)
   elif proc_obs == 'dynimg':
     cur, jnt = frames[-1], jnts[-1]
     eb = emulate_bf16
-    rm = relu_masks or {}
     feat, acts = conv_encoder(cur, params, scope + '/ConvEncoder', return_all=True, emulate_bf16=eb,
                               relu_masks=rm.get('obs'))
     ep['obs_acts'] = acts
@@ -323,12 +331,13 @@ def goal_e2evmc(rgb_frames, jnt_states, tgt_frame, params, cfg, scope='GoalVMC',
   return net, ep
 
 
-def e2e_vmc(rgb_frames, jnt_states, params, cfg, scope='VMC', init_state=None):
-  """graph.py:268-319 (unconditional baseline)."""
+def e2e_vmc(rgb_frames, jnt_states, params, cfg, scope='VMC', init_state=None, emulate_bf16=False, relu_masks=None):
+  """graph.py:268-319 (unconditional baseline).  relu_masks: {'frames': [eight masks per frame]}, see conv_encoder."""
   ep = OrderedDict()
   feat_list = []
   for k in range(cfg['window_size']):
-    feat = conv_encoder(rgb_frames[:, k], params, scope + '/ConvEncoder')
+    feat = conv_encoder(rgb_frames[:, k], params, scope + '/ConvEncoder', emulate_bf16=emulate_bf16,
+                        relu_masks=relu_masks['frames'][k] if relu_masks else None)
     feat_list.append(state_concatenation(feat, jnt_states[:, k]))
   ep['flat_state'] = feat_list[-1]
   net, ep_dec = lstm_decoder(feat_list, params, cfg, scope + '/LSTMDecoder', init_state)
@@ -532,7 +541,7 @@ def forward_losses(params, features, labels, cfg, init_state=None, emulate_bf16=
     net, ep = goal_e2evmc(rgb, jnt, tgt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16,
                           relu_masks=relu_masks)
   else:
-    net, ep = e2e_vmc(rgb, jnt, params, cfg, init_state=init_state)
+    net, ep = e2e_vmc(rgb, jnt, params, cfg, init_state=init_state, emulate_bf16=emulate_bf16, relu_masks=relu_masks)
   if cfg['control_mode'] == 'velocity':
     l2 = {k: _to(labels[k], dt) for k in ('vel_target', 'ee_target', 'grp_target')}
     return losses_velocity(ep, f2, l2, params, cfg), ep

