@@ -6,6 +6,7 @@
 #include "../../include/geeco_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <string.h>
 #include <string>
@@ -345,7 +346,7 @@ static int plan(geeco_ctx* c, char* ws_base) {
   c->losses = (float*)cv.take(sizeof(float) * GEECO_NUM_LOSS_SLOTS);
   c->sc = (float*)cv.take(sizeof(float) * 8);
   c->mm_scratch = (int*)cv.take(sizeof(int) * 2 * cfg.window_size * N);
-  c->gates_partial = (float*)cv.take(sizeof(float) * lstm_gates_partial_floats(N, ld, 4 * Hl));
+  c->gates_partial = (float*)cv.take(sizeof(float) * lstm_gates_partial_floats(T * N, ld, 4 * Hl));
   // fp32 staging of the last conv maps for the tail (bf16 mode converts conv8 output)
   c->y8_f32 = bf16 ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
   c->g8_f32 = (bf16 && cfg.training) ? (float*)cv.take(sizeof(float) * c->layers[7].act_elems) : nullptr;
@@ -643,6 +644,11 @@ static int encoders_fwd_f32(geeco_ctx* c, cudaStream_t st) {
   return GEECO_OK;
 }
 
+static bool use_persistent_lstm(const geeco_ctx* c) {
+  static const bool off = getenv("GEECO_LSTM_STEPWISE") != nullptr;      // per-step launches (kept as the fallback)
+  return c->T > 1 && !off && lstm_persistent_supported(c->cfg.dim_h_lstm);
+}
+
 static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs* out, const float* y8, bool with_loss,
                         cudaStream_t st) {
   const geeco_config& cfg = c->cfg;
@@ -654,7 +660,17 @@ static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
   StateMap sm = state_map(c, y8, nullptr);
   int rc = launch_build_states(sm, b->jnt_state, carry ? c->m_carry : nullptr, rmask, c->states, st);
   if (rc) return rc;
-  // lstm_decoder's loop over feat_list (graph.py:223-225): T = 1 for the dynimg graph, K for the sequence graphs
+  // lstm_decoder's loop over feat_list (graph.py:223-225): T = 1 for the dynimg graph, K for the sequence graphs.
+  // T > 1: the x part of all T steps is ONE split GEMM over T*N rows, the recurrence ONE persistent cluster launch
+  // with W_h resident in shared memory (lstm_persistent.cu)
+  if (use_persistent_lstm(c)) {
+    rc = launch_lstm_gates(c->states, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, T * N, c->xdim,
+                           4 * Hl, st);
+    if (rc) return rc;
+    rc = launch_lstm_seq_fwd(T, N, Hl, c->xdim, P(c, c->p_lstm_w), carry ? c->c_carry : nullptr, carry ? c->m_carry : nullptr,
+                             rmask, c->gates, c->c_seq, c->m_seq, c->states, c->state_out, st);
+    if (rc) return rc;
+  } else
   for (int t = 0; t < T; ++t) {
     const bool has_prev = t > 0 || carry;
     float* gates_t = c->gates + (long long)t * N * 4 * Hl;
@@ -806,6 +822,14 @@ static int tail_backward(geeco_ctx* c, cudaStream_t st) {
     rc = launch_tail_bwd(d, th, P(c, c->p_fc1_w), GR(c, c->p_fc1_w), GR(c, c->p_fc1_b), m_last, c->fc1, c->dheads, nullptr,
                          nullptr, nullptr, c->dfc1, nullptr, c->dm_last, st);
     if (rc) return rc;
+    if (use_persistent_lstm(c)) {
+      rc = launch_lstm_seq_bwd(T, N, Hl, c->xdim, P(c, c->p_lstm_w), carry ? c->c_carry : nullptr, c->reset_mask, c->gates,
+                               c->c_seq, c->dm_last, c->dgates, st);
+      if (rc) return rc;
+      // d(x_t) of all steps: d(gates) [T*N, 4Hl] @ W_x^T in one launch
+      rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstates, T * N, c->xdim, 4 * Hl, ld, st);
+      if (rc) return rc;
+    } else
     for (int t = T - 1; t >= 0; --t) {
       const bool last = t == T - 1;
       float* dgates_t = c->dgates + (long long)t * N * 4 * Hl;

@@ -67,3 +67,12 @@ int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias
                       int K, int Ncols, cudaStream_t st);
 int launch_ring_push(void* ring, const void* frame, const unsigned char* fresh, int N, int K, long long row_bytes,
                      int slot, cudaStream_t st);
+
+// lstm_persistent.cu: the T-step recurrence / its back-propagation through time as one cluster launch each, W_h resident
+// in shared memory.  gates holds x_t @ W_x + bias on entry of the forward and the full pre-activations on exit.
+bool lstm_persistent_supported(int Hl);
+int launch_lstm_seq_fwd(int T, int N, int Hl, int xdim, const float* kernel, const float* c0, const float* m0,
+                        const unsigned char* reset, float* gates, float* c, float* m, float* states, float* state_out,
+                        cudaStream_t st);
+int launch_lstm_seq_bwd(int T, int N, int Hl, int xdim, const float* kernel, const float* c0, const unsigned char* reset,
+                        const float* gates, const float* c, const float* dm_last, float* dgates, cudaStream_t st);

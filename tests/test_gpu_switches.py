@@ -214,3 +214,55 @@ def test_staged_batches_survive_a_host_that_runs_ahead(cuda_device):
   assert np.array_equal(snap_cmd.cpu().numpy(), la['cmd']) and np.array_equal(snap_jnt.cpu().numpy(), fa['jnt_state'])
   assert np.array_equal(eng._stage_bufs[0][('cmd', torch.float32)].cpu().numpy(), lb['cmd'])
   eng.close()
+
+
+@pytest.mark.parametrize('variant', ['seq_constant', 'seq_residual', 'seq_dyndiff', 'vmc'])
+def test_sequence_graphs_train_step_k4(cuda_device, variant):
+  """K = 4 frames through the encoder, four LSTM steps (the persistent recurrent kernels of lstm_persistent.cu with W_h in
+  shared memory), back-propagation through time; batch of 3 (not a multiple of any tile).  fp32: losses, head outputs and
+  every gradient entry <= 1e-4 against the float64 oracle (ReLU decisions given, tests/util.py); bf16: forward <= 2e-2."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import synthetic_batch
+  from geeco_b200.engine import Engine
+  from tests.util import engine_relu_masks
+  over = {'seq_constant': dict(proc_obs='sequence', proc_tgt='constant'), 'seq_residual': dict(proc_obs='sequence', proc_tgt='residual'),
+          'seq_dyndiff': dict(proc_obs='sequence', proc_tgt='dyndiff'), 'vmc': dict(proc_obs='sequence', proc_tgt='constant')}[variant]
+  goal = variant != 'vmc'
+  N = 3
+  cfg_d = O.make_config(batch_size=N, window_size=4, **over)
+  P = O.init_params(cfg_d, seed=31, goal=goal, dtype=torch.float32, bias_scale=0.05)
+  feats, labels = synthetic_batch(N, seed=32)
+  P64 = {k: v.double() for k, v in P.items()}
+  ref_l, _, ep = O.train_step({k: v.clone() for k, v in P64.items()}, O.adam_init(P64), feats, labels, cfg_d, goal=goal)
+  for precision, tol in (('fp32', 1e-4), ('bf16', 2e-2)):
+    eng = Engine(create_e2evmc_config(cfg_d), batch_size=N, precision=precision, training=True,
+                 goal_condition='target' if goal else 'none')
+    eng.set_params(P)
+    out = eng.forward(feats, labels)
+    torch.cuda.synchronize()
+    for k in ('pred_cmd_ee', 'logits_cmd_grp', 'pred_aux_ee', 'pred_aux_obj', 'fc1'):
+      assert rel_max(out[k].cpu().numpy(), ep[k].detach().numpy()) <= tol, (precision, k)
+    assert rel_max(out['lstm_state'].cpu().numpy(), ep['lstm_state'].detach().numpy()) <= tol
+    got = eng.losses_dict(out['losses'])
+    for k in ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss'):
+      assert abs(got[k] - ref_l[k]) <= tol * abs(ref_l[k]) + 1e-7, (precision, k, got[k], ref_l[k])
+    eng.train_step(feats, labels)
+    torch.cuda.synchronize()
+    grads = eng.get_grads()
+    if precision == 'fp32':
+      _, mask_g, _ = O.train_step({k: v.clone() for k, v in P64.items()}, O.adam_init(P64), feats, labels, cfg_d,
+                                  relu_masks=engine_relu_masks(eng), goal=goal)
+      worst = max((rel_max(grads[k], g.numpy()), k) for k, g in mask_g.items())
+      print("%s K=4 fp32 worst gradient entry %.3e (%s)" % (variant, worst[0], worst[1]))
+      assert worst[0] <= 1e-4, worst
+      # the recurrent rows of the LSTM kernel receive gradient now (steps 1..3 see a non-zero m_{t-1})
+      gk = grads[('GoalVMC' if goal else 'VMC') + '/LSTMDecoder/lstm_cell/kernel']
+      assert np.abs(gk[-cfg_d['dim_h_lstm']:]).max() > 0
+    else:
+      _, emu_g, _ = O.train_step({k: v.clone() for k, v in P64.items()}, O.adam_init(P64), feats, labels, cfg_d,
+                                 emulate_bf16=True, relu_masks=engine_relu_masks(eng), goal=goal)
+      from tests.util import rel_l2
+      worst = max((rel_l2(grads[k], g.numpy()), k) for k, g in emu_g.items() if float(g.abs().max()) > 0)
+      print("%s K=4 bf16 worst gradient rel-L2 (given ReLU masks, bf16 storage emulated) %.3e (%s)" % (variant, worst[0], worst[1]))
+      assert worst[0] <= 2e-2, worst
+    eng.close()
