@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgeeco_b200.so')
+LIB_PATH = os.environ.get('GEECO_LIB_PATH') or os.path.join(_HERE, 'libgeeco_b200.so')
 
 GEECO_OK, GEECO_ERR_INVALID, GEECO_ERR_CUDA, GEECO_ERR_WORKSPACE, GEECO_ERR_STATE = 0, 1, 2, 3, 4
 GEECO_FP32, GEECO_BF16 = 0, 1

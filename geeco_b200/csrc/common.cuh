@@ -52,6 +52,36 @@ void geeco_count_launch(int n);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// A step is ~50 dependent launches of 2-300 us each; between two of them the GPU drains, the next grid is launched and
+// its CTAs are scheduled: 1-3 us per edge.  Every kernel of this library starts with pdl_enter(): it lets the NEXT
+// kernel of the stream be launched as soon as all CTAs of this one are resident (griddepcontrol.launch_dependents) and
+// then waits until the PREVIOUS kernel has completed and flushed its memory (griddepcontrol.wait) -- before the first
+// global access, so the data dependencies are exactly those of a plain stream.  The host side launches with
+// cudaLaunchAttributeProgrammaticStreamSerialization (GEECO_LAUNCH); GEECO_NO_PDL=1 turns the attribute off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+#ifdef GEECO_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;");
+#endif
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool geeco_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void geeco_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = geeco_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface in the cudaGetLastError() that follows every launch
+}
+#define GEECO_LAUNCH(kernel, grid, block, smem, st, ...) \
+  geeco_launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
+#endif
+
 // ---- launchers implemented in the .cu files --------------------------------------------
 // rankpool.cu
 int launch_dynimg(const float* in, float* out, int N, int K, long long HWC, const float* alpha_host,

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_nn_f32_kernel(const GatherGeo
                                                                  const float* __restrict__ bias_all,
                                                                  const float* __restrict__ mask,
                                                                  float* __restrict__ dst, int epi) {
+  pdl_enter();
   constexpr int BN = 16 * TN;
   __shared__ __align__(16) float As[2][GM_BK][GM_BM + 4];
   __shared__ __align__(16) float Bs[2][GM_BK][BN + 4];
@@ -186,9 +187,9 @@ int launch_gemm_nn_f32(const GatherGeom& g, const float* src, const float* B, co
   if (Mg <= 0) return GEECO_OK;
   const int TN = g.Nn <= 32 ? 2 : (g.Nn <= 48 ? 3 : 4);
   dim3 grid(ceil_div(Mg, GM_BM), groups, ceil_div(g.Nn, 16 * TN));
-  if (TN == 2) gemm_nn_f32_kernel<2><<<grid, GM_THREADS, 0, st>>>(g, src, B, bias, mask, dst, epi);
-  else if (TN == 3) gemm_nn_f32_kernel<3><<<grid, GM_THREADS, 0, st>>>(g, src, B, bias, mask, dst, epi);
-  else gemm_nn_f32_kernel<4><<<grid, GM_THREADS, 0, st>>>(g, src, B, bias, mask, dst, epi);
+  if (TN == 2) GEECO_LAUNCH((gemm_nn_f32_kernel<2>), grid, GM_THREADS, 0, st, g, src, B, bias, mask, dst, epi);
+  else if (TN == 3) GEECO_LAUNCH((gemm_nn_f32_kernel<3>), grid, GM_THREADS, 0, st, g, src, B, bias, mask, dst, epi);
+  else GEECO_LAUNCH((gemm_nn_f32_kernel<4>), grid, GM_THREADS, 0, st, g, src, B, bias, mask, dst, epi);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tn_f32_kernel(const GatherGeo
                                                                  float* __restrict__ partial,
                                                                  float* __restrict__ bias_partial, int splits,
                                                                  long long Mchunk, int Krows) {
+  pdl_enter();
   constexpr int BN = 16 * TN;
   __shared__ __align__(16) float As[2][GM_BK][GM_BM + 4];
   __shared__ __align__(16) float Gs[2][GM_BK][BN + 4];
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(GM_THREADS) gemm_tn_f32_kernel(const GatherGeo
 // out[g][i] = sum_s partial[(g*splits + s)][i]   (fixed order -> deterministic)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits,
                                        long long count, long long out_group_stride, int groups) {
+  pdl_enter();
   const long long total = count * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int grp = (int)(i / count);
@@ -373,15 +376,15 @@ int launch_gemm_tn_f32(const GatherGeom& g, const float* src, const float* G, fl
   Mchunk = (Mchunk + GM_BK - 1) / GM_BK * GM_BK;
   float* bias_partial = dbias ? partial + splits * groups * (long long)Krows * g.Nn : nullptr;
   dim3 grid(ktiles, (unsigned)(groups * splits), ntiles);
-  if (TN == 2) gemm_tn_f32_kernel<2><<<grid, GM_THREADS, 0, st>>>(g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
-  else if (TN == 3) gemm_tn_f32_kernel<3><<<grid, GM_THREADS, 0, st>>>(g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
-  else gemm_tn_f32_kernel<4><<<grid, GM_THREADS, 0, st>>>(g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
+  if (TN == 2) GEECO_LAUNCH((gemm_tn_f32_kernel<2>), grid, GM_THREADS, 0, st, g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
+  else if (TN == 3) GEECO_LAUNCH((gemm_tn_f32_kernel<3>), grid, GM_THREADS, 0, st, g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
+  else GEECO_LAUNCH((gemm_tn_f32_kernel<4>), grid, GM_THREADS, 0, st, g, src, G, partial, bias_partial, (int)splits, Mchunk, Krows);
   const long long cnt = (long long)Krows * g.Nn;
   int rb = ceil_div(cnt * groups, 256); if (rb > 1184) rb = 1184;
-  reduce_partials_kernel<<<rb, 256, 0, st>>>(partial, dW, (int)splits, cnt, dw_group_stride, groups);
+  GEECO_LAUNCH((reduce_partials_kernel), rb, 256, 0, st, partial, dW, (int)splits, cnt, dw_group_stride, groups);
   geeco_count_launch(2);
   if (dbias) {
-    reduce_partials_kernel<<<ceil_div((long long)g.Nn * groups, 256), 256, 0, st>>>(bias_partial, dbias, (int)splits,
+    GEECO_LAUNCH((reduce_partials_kernel), ceil_div((long long)g.Nn * groups, 256), 256, 0, st, bias_partial, dbias, (int)splits,
                                                                                   g.Nn, dbias_group_stride, groups);
     geeco_count_launch(1);
   }

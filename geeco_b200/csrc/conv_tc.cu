@@ -220,6 +220,7 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
              int tiles_flat, int tmem_cols, int stages, int nbuf, unsigned short* __restrict__ bits_out) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -471,6 +472,7 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
                const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi,
                int tiles_per_group, int tiles_flat, int tmem_cols, int stages, int nbuf,
                unsigned short* __restrict__ bits_out) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.Nn;
@@ -601,6 +603,7 @@ __global__ void __launch_bounds__(NPROD + 160, NPROD == 256 ? 2 : 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
                 int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk) {
+  pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int mtile = blockIdx.x / n_chunks, nchunk = blockIdx.x - mtile * n_chunks;
@@ -863,6 +866,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, float* __restrict__ dbias,
                                     int splits, int groups, int Mrows_pad, int Kpad, int Cout, int Cs, int Cw,
                                     int Ktot, int ones_col, long long dw_group_stride, long long dbias_group_stride) {
+  pdl_enter();
   const long long per_group = (long long)(Ktot + 1) * Cout;
   const long long total = per_group * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -898,6 +902,7 @@ __global__ void __launch_bounds__(1024 / CPT) wgrad_reduce_t_kernel(const float*
                                                                     int Mrows_pad, int Kpad, int Cout, int Cs, int Cw, int Ktot,
                                                                     int ones_col, long long dw_group_stride,
                                                                     long long dbias_group_stride) {
+  pdl_enter();
   constexpr int RY = 32 / CPT;                     // blockDim.y
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, co0 = blockIdx.y * 32, grp = blockIdx.z;
@@ -939,6 +944,7 @@ __global__ void conv1pair_reduce_kernel(const float* __restrict__ part_even, con
                                         float* __restrict__ dW, float* __restrict__ dbias, int splits, int groups,
                                         int Mrows_pad, int Kpad, int Cin, int Cout, long long dw_group_stride,
                                         long long dbias_group_stride) {
+  pdl_enter();
   const int per_group = (9 * Cin + 1) * Cout;
   const int total = per_group * groups;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -1001,6 +1007,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
                                     long long w_group_stride, int Cin, int Cout, int Cs, int ntaps, int rows, int Kpad,
                                     int Kt, int t0, int t1, int t2, int t3, int t4, int t5, int t6, int t7, int t8,
                                     const float* __restrict__ bias, int bias_col) {
+  pdl_enter();
   const int taps[9] = {t0, t1, t2, t3, t4, t5, t6, t7, t8};
   const long long total = (long long)groups * rows * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1017,6 +1024,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
 // block belongs to exactly one job: the job is looked up once per block and its constants stay in registers.
 __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs,
                                                                    long long grand_total) {
+  pdl_enter();
   __shared__ int s_job;
   const long long v0 = (long long)blockIdx.x * PACK_CHUNK;
   if (threadIdx.x == 0) {
@@ -1047,6 +1055,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
 
 // one thread per 16-value chunk: bit j = value 2j != 0, bit 8+j = value 2j+1 != 0 (same layout the forward epilogue writes)
 __global__ void relu_mask_bits_kernel(const __nv_bfloat16* __restrict__ y, unsigned short* __restrict__ bits, long long chunks) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (long long)gridDim.x * blockDim.x) {
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(y + i * 16)), b = __ldg(reinterpret_cast<const uint4*>(y + i * 16) + 1);
     const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
@@ -1063,10 +1072,12 @@ __global__ void relu_mask_bits_kernel(const __nv_bfloat16* __restrict__ y, unsig
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_enter();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __bfloat162float(in[i]);
 }
@@ -1267,7 +1278,7 @@ int launch_conv1pair_reduce(const float* part_even, const float* part_odd, float
                             int groups, int Mrows_pad, int Kpad, int Cin, int Cout, long long dw_group_stride,
                             long long dbias_group_stride, cudaStream_t st) {
   const int total = (9 * Cin + 1) * Cout * groups;
-  conv1pair_reduce_kernel<<<ceil_div(total, 256), 256, 0, st>>>(part_even, part_odd, dW, dbias, splits, groups, Mrows_pad,
+  GEECO_LAUNCH((conv1pair_reduce_kernel), ceil_div(total, 256), 256, 0, st, part_even, part_odd, dW, dbias, splits, groups, Mrows_pad,
                                                                Kpad, Cin, Cout, dw_group_stride, dbias_group_stride);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
@@ -1420,7 +1431,7 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
     auto kern = tc_rows_kernel<SETS_, EPW_, MASK_>;                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-    kern<<<ctas, SETS_ * EPW_ * 32 + 64, smem, st>>>(g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,                \
+    GEECO_LAUNCH((kern), ctas, SETS_ * EPW_ * 32 + 64, smem, st, g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,                \
                                                      tiles_per_group, tiles_flat, tmem_cols, stages, nbuf, bits_out);   \
   } while (0)
 #define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
@@ -1534,7 +1545,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     auto kern = tc_nn_kernel<PIECE_, NPW_, MASK_>;                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
-    kern<<<ctas, NN_THREADS, smem, st>>>(g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,        \
+    GEECO_LAUNCH((kern), ctas, NN_THREADS, smem, st, g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,        \
                                          tiles_flat, tmem_cols, stages, nbuf, bits_out);                               \
   } while (0)
 #define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
@@ -1633,7 +1644,7 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
                                   cudaSharedmemCarveoutMaxShared));                                                 \
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<PIECE_, NPROD_>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                   (int)smem));                                                                      \
-    tc_wgrad_kernel<PIECE_, NPROD_><<<grid, NPROD_ + 160, smem, st>>>(g, src, G, partial, Cout, p.n_chunks,          \
+    GEECO_LAUNCH((tc_wgrad_kernel<PIECE_, NPROD_>), grid, NPROD_ + 160, smem, st, g, src, G, partial, Cout, p.n_chunks,          \
                                                                       p.kb_per_split, p.total_kb, p.Mrows_pad, ones, \
                                                                       p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);  \
   } while (0)
@@ -1672,17 +1683,17 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   const int tiles = (int)(tgrid.x * tgrid.y * tgrid.z);
   if (p.splits <= 12 && tiles >= 2 * num_sms()) {
     // few splits, many outputs (conv5-conv8)
-    wgrad_reduce_t_kernel<4><<<tgrid, dim3(32, 8), 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
+    GEECO_LAUNCH((wgrad_reduce_t_kernel<4>), tgrid, dim3(32, 8), 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
                                                            g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
   } else if (tiles >= 64) {
     // more splits (conv3, conv4): one output channel per thread, 1024 threads per tile
-    wgrad_reduce_t_kernel<1><<<tgrid, dim3(32, 32), 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
+    GEECO_LAUNCH((wgrad_reduce_t_kernel<1>), tgrid, dim3(32, 32), 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
                                                             g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
   } else {
     // many splits, few outputs (conv1, conv2): one thread per output, no transpose
     const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
     int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
-    wgrad_reduce_kernel<<<rb, 256, 0, st>>>(partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
+    GEECO_LAUNCH((wgrad_reduce_kernel), rb, 256, 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
                                             g.Ktot, ones, dw_group_stride, dbias_group_stride);
   }
   geeco_count_launch(1);
@@ -1699,7 +1710,7 @@ int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups
   for (int i = 0; i < ntaps && i < 9; ++i) t[i] = taps[i];
   const long long total = (long long)groups * rows * Kpad;
   int blocks = ceil_div(total, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad, Kt,
+  GEECO_LAUNCH((pack_weights_kernel), blocks, 256, 0, st, W, out, mode, groups, w_group_stride, Cin, Cout, Cs, ntaps, rows, Kpad, Kt,
                                               t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], bias,
                                               bias ? bias_col : -1);
   geeco_count_launch(1);
@@ -1711,7 +1722,7 @@ int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long gr
   if (njobs <= 0 || grand_total <= 0) return GEECO_OK;
   if (njobs > 64) { geeco_set_error("pack_weights_batched: %d jobs > 64", njobs); return GEECO_ERR_INVALID; }
   if (grand_total % PACK_CHUNK) { geeco_set_error("pack_weights_batched: jobs must start on PACK_CHUNK boundaries"); return GEECO_ERR_INVALID; }
-  pack_weights_batched_kernel<<<(unsigned)(grand_total / PACK_CHUNK), 256, 0, st>>>(jobs_dev, njobs, grand_total);
+  GEECO_LAUNCH((pack_weights_batched_kernel), (unsigned)(grand_total / PACK_CHUNK), 256, 0, st, jobs_dev, njobs, grand_total);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -1720,7 +1731,7 @@ int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long gr
 int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long long chunks, cudaStream_t st) {
   if (chunks <= 0) return GEECO_OK;
   int blocks = ceil_div(chunks, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  relu_mask_bits_kernel<<<blocks, 256, 0, st>>>(y, bits, chunks);
+  GEECO_LAUNCH((relu_mask_bits_kernel), blocks, 256, 0, st, y, bits, chunks);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -1728,7 +1739,7 @@ int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long lon
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
   if (n <= 0) return GEECO_OK;
   int blocks = ceil_div(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  GEECO_LAUNCH((f32_to_bf16_kernel), blocks, 256, 0, st, in, out, n);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -1736,7 +1747,7 @@ int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStr
 int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStream_t st) {
   if (n <= 0) return GEECO_OK;
   int blocks = ceil_div(n, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  bf16_to_f32_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  GEECO_LAUNCH((bf16_to_f32_kernel), blocks, 256, 0, st, in, out, n);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

@@ -25,6 +25,10 @@ void geeco_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void geeco_count_launch(int n) { g_launches += n; }
+bool geeco_pdl_enabled() {
+  static const bool on = getenv("GEECO_NO_PDL") == nullptr;
+  return on;
+}
 
 extern "C" const char* geeco_last_error(void) { return g_err; }
 extern "C" int geeco_version(void) { return 100; }

@@ -37,6 +37,7 @@ struct LstmSeqArgs {
 // forward.  shared: Ws [Hl][4U] | mb [2][RB][Hl]
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LP_THREADS) lstm_seq_fwd_kernel(LstmSeqArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float lp_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = cluster.num_blocks(), rank = cluster.block_rank();
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(LP_THREADS) lstm_seq_fwd_kernel(LstmSeqArgs a)
 // d(m_t) = (t == T-1 ? dm_last : d(gates_{t+1}) @ W_h^T) ; cell backward with the d(c) carried from step t+1
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LP_THREADS) lstm_seq_bwd_kernel(LstmSeqArgs a) {
+  pdl_enter();
   extern __shared__ __align__(16) float lp_smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = cluster.num_blocks(), rank = cluster.block_rank();
@@ -189,10 +191,12 @@ static int lp_launch(const void* kernel, LstmSeqArgs& a, bool backward, cudaStre
   CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, (a.N + LP_RB - 1) / LP_RB); cfg.blockDim = dim3(LP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = geeco_pdl_enabled() ? 2 : 1;
   void* args[] = {(void*)&a};
   CUDA_TRY(cudaLaunchKernelExC(&cfg, kernel, args));
   geeco_count_launch(1);

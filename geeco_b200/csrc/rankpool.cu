@@ -97,6 +97,7 @@ template <int K>
 __global__ void __launch_bounds__(RP_THREADS) dynimg_cluster_kernel(const float* __restrict__ in,
                                                                     float* __restrict__ out, long long total4,
                                                                     long long per4, AlphaTab al) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
   __shared__ float s_mm[2 * RP_MAX_CLUSTER];
@@ -141,12 +142,14 @@ __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); retur
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 __global__ void minmax_init_kernel(int* mm, int n) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { mm[2 * i] = f2ord(FLT_MAX); mm[2 * i + 1] = f2ord(-FLT_MAX); }
 }
 template <int K>
 __global__ void __launch_bounds__(256) dynimg_pass1_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            int* __restrict__ mm, long long total4, AlphaTab al) {
+  pdl_enter();
   const long long n = blockIdx.y;
   const float4* base = reinterpret_cast<const float4*>(in) + n * K * total4;
   float4* o = reinterpret_cast<float4*>(out) + n * total4;
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(256) dynimg_pass1_kernel(const float* __restri
 }
 __global__ void __launch_bounds__(256) dynimg_pass2_kernel(float* __restrict__ out, const int* __restrict__ mm,
                                                            long long total4) {
+  pdl_enter();
   const long long n = blockIdx.y;
   const float mn = ord2f(mm[2 * n]), mx = ord2f(mm[2 * n + 1]);
   const float rng = __fadd_rn(__fsub_rn(mx, mn), 1e-6f);
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
     AlphaTab al, int ring_start) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
   __shared__ float s_mm[2 * 2 * RP_MAX_CLUSTER];
@@ -325,10 +330,12 @@ static int launch_clustered(KernelT kernel, dim3 grid, int cl, size_t smem, cuda
   if (cl > 8) CUDA_TRY(cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(RP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = geeco_pdl_enabled() ? 2 : 1;
   CUDA_TRY(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
   geeco_count_launch(1);
   return GEECO_OK;
@@ -383,11 +390,11 @@ int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, in
   for (int k = 0; k < K && k < 16; ++k) al.a[k] = alpha_host[k];
   long long total4 = HWC / 4;
   int* mm = reinterpret_cast<int*>(minmax_scratch);
-  minmax_init_kernel<<<ceil_div(N, 256), 256, 0, st>>>(mm, N);
+  GEECO_LAUNCH((minmax_init_kernel), ceil_div(N, 256), 256, 0, st, mm, N);
   int bps = (int)((total4 + 256 * 8 - 1) / (256 * 8)); if (bps < 1) bps = 1; if (bps > 1024) bps = 1024;
   dim3 grid(bps, N);
-  RP_SWITCH_K(K, (dynimg_pass1_kernel<KK><<<grid, 256, 0, st>>>(in, out, mm, total4, al)));
-  dynimg_pass2_kernel<<<grid, 256, 0, st>>>(out, mm, total4);
+  RP_SWITCH_K(K, (GEECO_LAUNCH((dynimg_pass1_kernel<KK>), grid, 256, 0, st, in, out, mm, total4, al)));
+  GEECO_LAUNCH((dynimg_pass2_kernel), grid, 256, 0, st, out, mm, total4);
   geeco_count_launch(3);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -451,6 +458,7 @@ template <typename InT, typename OutT, int CP, int C>
 __global__ void __launch_bounds__(256) seq_frames_kernel(const InT* __restrict__ rgb, const InT* __restrict__ tgt,
                                                          OutT* __restrict__ x0, int* __restrict__ mm, int N, int K,
                                                          int with_diff, long long units, int ring_start) {
+  pdl_enter();
   __shared__ float s_lut[256];
   if (sizeof(InT) == 1) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x) s_lut[b] = __fdiv_rn((float)b, 255.f);
@@ -488,6 +496,7 @@ __global__ void __launch_bounds__(256) seq_dyndiff_kernel(const InT* __restrict_
                                                           OutT* __restrict__ x1, const int* __restrict__ mm,
                                                           float* __restrict__ dyndiff_f32, int N, int K, long long units,
                                                           int ring_start) {
+  pdl_enter();
   __shared__ float s_lut[256];
   if (sizeof(InT) == 1) {
     for (int b = threadIdx.x; b < 256; b += blockDim.x) s_lut[b] = __fdiv_rn((float)b, 255.f);
@@ -521,11 +530,11 @@ static int launch_seq_t(const InT* rgb, const InT* tgt, void* x0, int* mm, float
   const int imgs = K * N + (with_tgt ? N : 0);
   int bx = (int)((units + 256 * 4 - 1) / (256 * 4)); if (bx < 1) bx = 1;
   OutT* x = reinterpret_cast<OutT*>(x0);
-  if (with_diff) minmax_init_kernel<<<ceil_div(K * N, 256), 256, 0, st>>>(mm, K * N);
-  seq_frames_kernel<InT, OutT, CP, C><<<dim3(bx, imgs), 256, 0, st>>>(rgb, tgt, x, mm, N, K, with_diff, units, ring_start);
+  if (with_diff) GEECO_LAUNCH((minmax_init_kernel), ceil_div(K * N, 256), 256, 0, st, mm, K * N);
+  GEECO_LAUNCH((seq_frames_kernel<InT, OutT, CP, C>), dim3(bx, imgs), 256, 0, st, rgb, tgt, x, mm, N, K, with_diff, units, ring_start);
   geeco_count_launch(with_diff ? 2 : 1);
   if (with_diff) {
-    seq_dyndiff_kernel<InT, OutT, CP, C><<<dim3(bx, K * N), 256, 0, st>>>(rgb, tgt, x + (long long)K * N * units * 4 * CP, mm, dd,
+    GEECO_LAUNCH((seq_dyndiff_kernel<InT, OutT, CP, C>), dim3(bx, K * N), 256, 0, st, rgb, tgt, x + (long long)K * N * units * 4 * CP, mm, dd,
                                                                          N, K, units, ring_start);
     geeco_count_launch(1);
   }

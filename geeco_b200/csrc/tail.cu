@@ -53,6 +53,7 @@ __device__ __forceinline__ float state_value(const StateMap& sm, const float* __
 
 __global__ void build_states_kernel(StateMap sm, const float* __restrict__ jnt_states, const float* __restrict__ m_prev,
                                     const unsigned char* __restrict__ reset_mask, float* __restrict__ states) {
+  pdl_enter();
   const int n = blockIdx.x, t = blockIdx.y;
   float* row = states + ((long long)t * sm.N + n) * sm.ld;
   const int hi = t == 0 ? sm.ld : sm.xdim;
@@ -68,6 +69,7 @@ __global__ void build_states_kernel(StateMap sm, const float* __restrict__ jnt_s
 // dY8(pre-activation)[group][img][cell][c] = (sum of the d(state) entries that read Y8[group][img][cell][c]) * (Y8 > 0).
 // One thread per conv8 element gathers its contributions (a target feature is read by all T steps): deterministic.
 __global__ void scatter_dstates_kernel(StateMap sm, const float* __restrict__ ds, int imgs0, int imgs1, int imgs2) {
+  pdl_enter();
   const long long n0 = (long long)imgs0 * 4 * sm.D0, n1 = (long long)imgs1 * 4 * sm.D1, n2 = (long long)imgs2 * 4 * sm.D2;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n0 + n1 + n2) return;
@@ -109,6 +111,7 @@ __global__ void lstm_cell_kernel(int N, int Hl, const float* __restrict__ gates,
                                  const unsigned char* __restrict__ reset_mask, float* __restrict__ c_out,
                                  float* __restrict__ m_out, float* __restrict__ state_out, float* __restrict__ m_next,
                                  int ld_next) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * Hl) return;
   const int n = idx / Hl, i = idx - n * Hl;
@@ -131,6 +134,7 @@ __global__ void lstm_cell_bwd_kernel(int N, int Hl, const float* __restrict__ ga
                                      const unsigned char* __restrict__ reset_mask, const float* __restrict__ dm, int ld_dm,
                                      const float* __restrict__ dc_in, float* __restrict__ dgates,
                                      float* __restrict__ dc_prev) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * Hl) return;
   const int n = idx / Hl, i = idx - n * Hl;
@@ -167,6 +171,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th,
                                                        float* __restrict__ fc1, float* __restrict__ heads,
                                                        float* __restrict__ loss_parts, float* __restrict__ dheads,
                                                        int with_loss) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* m_s = sm;                 // Hl
   float* fc_s = sm + d.Hl;         // Fc
@@ -238,6 +243,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th,
 // losses[12]: slot of every head (HeadSpec::slot), [4] loss_reg, [5] loss, [6] sum_correct, [7] N
 __global__ void loss_reduce_kernel(int N, TailHeads th, const float* __restrict__ loss_parts,
                                    const float* __restrict__ reg_term, float* __restrict__ losses) {
+  pdl_enter();
   __shared__ float s[6][256];
   float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int n = threadIdx.x; n < N; n += blockDim.x)
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailHeads th,
                                                        const unsigned char* __restrict__ reset_mask,
                                                        float* __restrict__ dfc1, float* __restrict__ dgates,
                                                        float* __restrict__ dm_out) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* dh_s = sm;                // NH (padded to 32)
   float* dfc_s = sm + 32;          // Fc
@@ -319,6 +326,7 @@ __global__ void __launch_bounds__(128) tail_bwd_kernel(TailDims d, TailHeads th,
 __global__ void tail_wgrad_kernel(TailDims d, TailHeads th, float* __restrict__ gw_fc1, float* __restrict__ gb_fc1,
                                   const float* __restrict__ m, const float* __restrict__ fc1,
                                   const float* __restrict__ dfc1, const float* __restrict__ dheads) {
+  pdl_enter();
   const int NH = th.NH;
   const int n_w1 = d.Hl * d.Fc, n_b1 = d.Fc, n_wh = d.Fc * NH, n_bh = NH;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -351,6 +359,7 @@ __global__ void tail_wgrad_kernel(TailDims d, TailHeads th, float* __restrict__ 
 // sc[0] = t (as float), sc[1] = lr_t, sc[2] = 0.5*l2*sum(theta^2)
 // ---------------------------------------------------------------------------------------
 __global__ void adam_prep_kernel(float* sc, double lr, double b1, double b2) {
+  pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const double t = (double)sc[0] + 1.0;
     sc[0] = (float)t;
@@ -362,6 +371,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ theta, c
                                                    float4* __restrict__ m, float4* __restrict__ v, long long n4,
                                                    const float* __restrict__ sc, float b1, float b2, float eps,
                                                    float gscale, float l2) {
+  pdl_enter();
   const float lr_t = sc[1];
   const float omb1 = 1.f - b1, omb2 = 1.f - b2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -381,6 +391,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ theta, c
 
 // 0.5 * l2 * sum(theta^2) -> sc[2]  (single block, fixed order; only launched when l2 > 0)
 __global__ void l2_term_kernel(const float* __restrict__ theta, long long n, float l2, float* sc) {
+  pdl_enter();
   __shared__ double s[1024];
   double a = 0.0;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) a += (double)theta[i] * theta[i];
@@ -398,7 +409,7 @@ __global__ void l2_term_kernel(const float* __restrict__ theta, long long n, flo
 // ---------------------------------------------------------------------------------------
 int launch_build_states(const StateMap& sm, const float* jnt, const float* m_prev, const unsigned char* reset_mask,
                         float* states, cudaStream_t st) {
-  build_states_kernel<<<dim3(sm.N, sm.T), 256, 0, st>>>(sm, jnt, m_prev, reset_mask, states);
+  GEECO_LAUNCH((build_states_kernel), dim3(sm.N, sm.T), 256, 0, st, sm, jnt, m_prev, reset_mask, states);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -421,14 +432,14 @@ int launch_scatter_dstates(const StateMap& sm, const float* dstates, cudaStream_
   // DynDiffEncoder): pass that width in the D1 slot of a copy
   StateMap k = sm;
   k.D1 = D1;
-  scatter_dstates_kernel<<<ceil_div(total, 256), 256, 0, st>>>(k, dstates, imgs[0], imgs[1], imgs[2]);
+  GEECO_LAUNCH((scatter_dstates_kernel), ceil_div(total, 256), 256, 0, st, k, dstates, imgs[0], imgs[1], imgs[2]);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
 int launch_lstm_cell(int N, int Hl, const float* gates, const float* c_prev, const unsigned char* reset_mask,
                      float* c_out, float* m_out, float* state_out, float* m_next, int ld_next, cudaStream_t st) {
-  lstm_cell_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(N, Hl, gates, c_prev, reset_mask, c_out, m_out,
+  GEECO_LAUNCH((lstm_cell_kernel), ceil_div((long long)N * Hl, 256), 256, 0, st, N, Hl, gates, c_prev, reset_mask, c_out, m_out,
                                                                     state_out, m_next, ld_next);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
@@ -436,7 +447,7 @@ int launch_lstm_cell(int N, int Hl, const float* gates, const float* c_prev, con
 }
 int launch_lstm_cell_bwd(int N, int Hl, const float* gates, const float* c_prev, const unsigned char* reset_mask,
                          const float* dm, int ld_dm, const float* dc_in, float* dgates, float* dc_prev, cudaStream_t st) {
-  lstm_cell_bwd_kernel<<<ceil_div((long long)N * Hl, 256), 256, 0, st>>>(N, Hl, gates, c_prev, reset_mask, dm, ld_dm, dc_in,
+  GEECO_LAUNCH((lstm_cell_bwd_kernel), ceil_div((long long)N * Hl, 256), 256, 0, st, N, Hl, gates, c_prev, reset_mask, dm, ld_dm, dc_in,
                                                                         dgates, dc_prev);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
@@ -445,14 +456,14 @@ int launch_lstm_cell_bwd(int N, int Hl, const float* gates, const float* c_prev,
 int launch_tail_fwd(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1, const float* m,
                     float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, cudaStream_t st) {
   const size_t smem = (size_t)(d.Hl + d.Fc + 32) * sizeof(float);
-  tail_fwd_kernel<<<d.N, 128, smem, st>>>(d, th, w_fc1, b_fc1, m, fc1, heads, loss_parts, dheads, with_loss);
+  GEECO_LAUNCH((tail_fwd_kernel), d.N, 128, smem, st, d, th, w_fc1, b_fc1, m, fc1, heads, loss_parts, dheads, with_loss);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
 int launch_loss_reduce(const TailDims& d, const TailHeads& th, const float* loss_parts, const float* reg_term,
                        float* losses, cudaStream_t st) {
-  loss_reduce_kernel<<<1, 256, 0, st>>>(d.N, th, loss_parts, reg_term, losses);
+  GEECO_LAUNCH((loss_reduce_kernel), 1, 256, 0, st, d.N, th, loss_parts, reg_term, losses);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -461,19 +472,19 @@ int launch_tail_bwd(const TailDims& d, const TailHeads& th, const float* w_fc1, 
                     const float* m, const float* fc1, const float* dheads, const float* gates, const float* c_prev,
                     const unsigned char* reset_mask, float* dfc1, float* dgates, float* dm_out, cudaStream_t st) {
   const size_t smem = (size_t)(32 + d.Fc) * sizeof(float);
-  tail_bwd_kernel<<<d.N, 128, smem, st>>>(d, th, w_fc1, fc1, dheads, gates, c_prev, reset_mask, dfc1, dgates, dm_out);
+  GEECO_LAUNCH((tail_bwd_kernel), d.N, 128, smem, st, d, th, w_fc1, fc1, dheads, gates, c_prev, reset_mask, dfc1, dgates, dm_out);
   const int total = d.Hl * d.Fc + d.Fc + d.Fc * th.NH + th.NH;
-  tail_wgrad_kernel<<<ceil_div(total, 128), 128, 0, st>>>(d, th, gw_fc1, gb_fc1, m, fc1, dfc1, dheads);
+  GEECO_LAUNCH((tail_wgrad_kernel), ceil_div(total, 128), 128, 0, st, d, th, gw_fc1, gb_fc1, m, fc1, dfc1, dheads);
   geeco_count_launch(2);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
 int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, float* sc, double lr, double b1,
                 double b2, double eps, float gscale, float l2, cudaStream_t st) {
-  adam_prep_kernel<<<1, 32, 0, st>>>(sc, lr, b1, b2);
+  GEECO_LAUNCH((adam_prep_kernel), 1, 32, 0, st, sc, lr, b1, b2);
   const long long n4 = n / 4;
   int blocks = ceil_div(n4, 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(grad),
+  GEECO_LAUNCH((adam_kernel), blocks, 256, 0, st, reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(grad),
                                       reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4, sc, (float)b1,
                                       (float)b2, (float)eps, gscale, l2);
   geeco_count_launch(2);
@@ -481,7 +492,7 @@ int launch_adam(float* theta, const float* grad, float* m, float* v, long long n
   return GEECO_OK;
 }
 int launch_l2_term(const float* theta, long long n, float l2, float* sc, cudaStream_t st) {
-  l2_term_kernel<<<1, 1024, 0, st>>>(theta, n, l2, sc);
+  GEECO_LAUNCH((l2_term_kernel), 1, 1024, 0, st, theta, n, l2, sc);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -497,6 +508,7 @@ template <int CPT>
 __global__ void __launch_bounds__(256) gates_splitk_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                            float* __restrict__ partial, int N, int K, int ldx,
                                                            int Ncols) {
+  pdl_enter();
   __shared__ float xs[32][GK_SLICE + 1];
   const int k0 = blockIdx.x * GK_SLICE, n0 = blockIdx.y * 32;
   for (int e = threadIdx.x; e < 32 * GK_SLICE; e += 256) {
@@ -536,6 +548,7 @@ __global__ void __launch_bounds__(256) gates_splitk_kernel(const float* __restri
 }
 __global__ void gates_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
                                     float* __restrict__ gates, int slices, int N, int Ncols) {
+  pdl_enter();
   const long long total = (long long)N * Ncols;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -547,6 +560,7 @@ __global__ void gates_reduce_kernel(const float* __restrict__ partial, const flo
 // the caller-visible outputs of a step (heads, fc1, LSTM state, losses) in ONE launch instead of four D2D copies
 struct CopyList { const float* src[4]; float* dst[4]; long long n[4]; };
 __global__ void copy_outputs_kernel(CopyList cl) {
+  pdl_enter();
   const float* s = cl.src[blockIdx.y];
   float* d = cl.dst[blockIdx.y];
   if (!d) return;
@@ -558,7 +572,7 @@ int launch_copy_outputs(const float* const* src, float* const* dst, const long l
   bool any = false;
   for (int i = 0; i < 4; ++i) { cl.src[i] = src[i]; cl.dst[i] = dst[i]; cl.n[i] = n[i]; any = any || dst[i]; }
   if (!any) return GEECO_OK;
-  copy_outputs_kernel<<<dim3(16, 4), 256, 0, st>>>(cl);
+  GEECO_LAUNCH((copy_outputs_kernel), dim3(16, 4), 256, 0, st, cl);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -572,6 +586,7 @@ int launch_copy_outputs(const float* const* src, float* const* dst, const long l
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) lstm_dstate_kernel(const float* __restrict__ dgates, const float* __restrict__ W,
                                                           float* __restrict__ dstate, int N, int xdim, int NC, int ld) {
+  pdl_enter();
   __shared__ float Ws[32][65];
   __shared__ float Ds[64][65];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 64;
@@ -605,7 +620,7 @@ __global__ void __launch_bounds__(256) lstm_dstate_kernel(const float* __restric
 }
 int launch_lstm_dstate(const float* dgates, const float* W, float* dstate, int N, int xdim, int ncols, int ld,
                        cudaStream_t st) {
-  lstm_dstate_kernel<<<dim3((xdim + 31) / 32, (N + 63) / 64), 256, 0, st>>>(dgates, W, dstate, N, xdim, ncols, ld);
+  GEECO_LAUNCH((lstm_dstate_kernel), dim3((xdim + 31) / 32, (N + 63) / 64), 256, 0, st, dgates, W, dstate, N, xdim, ncols, ld);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -620,11 +635,11 @@ int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias
   const int slices = (K + GK_SLICE - 1) / GK_SLICE;
   dim3 grid(slices, (N + 31) / 32);
   const int cpt = (Ncols + 255) / 256;
-  if (cpt == 1) gates_splitk_kernel<1><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
-  else if (cpt == 2) gates_splitk_kernel<2><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
-  else if (cpt == 3) gates_splitk_kernel<3><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
-  else gates_splitk_kernel<4><<<grid, 256, 0, st>>>(x, W, partial, N, K, ldx, Ncols);
-  gates_reduce_kernel<<<ceil_div((long long)N * Ncols, 256), 256, 0, st>>>(partial, bias, gates, slices, N, Ncols);
+  if (cpt == 1) GEECO_LAUNCH((gates_splitk_kernel<1>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
+  else if (cpt == 2) GEECO_LAUNCH((gates_splitk_kernel<2>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
+  else if (cpt == 3) GEECO_LAUNCH((gates_splitk_kernel<3>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
+  else GEECO_LAUNCH((gates_splitk_kernel<4>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
+  GEECO_LAUNCH((gates_reduce_kernel), ceil_div((long long)N * Ncols, 256), 256, 0, st, partial, bias, gates, slices, N, Ncols);
   geeco_count_launch(2);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -637,6 +652,7 @@ int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias
 template <typename V>
 __global__ void ring_push_kernel(V* __restrict__ ring, const V* __restrict__ frame, const unsigned char* __restrict__ fresh,
                                  int K, long long row_v, int slot) {
+  pdl_enter();
   const int n = blockIdx.y;
   const bool all = fresh && fresh[n];
   const V* src = frame + (long long)n * row_v;
@@ -654,8 +670,8 @@ int launch_ring_push(void* ring, const void* frame, const unsigned char* fresh, 
   const bool v16 = row_bytes % 16 == 0 && ((uintptr_t)ring % 16 == 0) && ((uintptr_t)frame % 16 == 0);
   const long long row_v = row_bytes / (v16 ? 16 : 4);
   int bx = (int)((row_v + 255) / 256); if (bx > 64) bx = 64; if (bx < 1) bx = 1;
-  if (v16) ring_push_kernel<uint4><<<dim3(bx, N), 256, 0, st>>>((uint4*)ring, (const uint4*)frame, fresh, K, row_v, slot);
-  else ring_push_kernel<unsigned int><<<dim3(bx, N), 256, 0, st>>>((unsigned int*)ring, (const unsigned int*)frame, fresh, K, row_v, slot);
+  if (v16) GEECO_LAUNCH((ring_push_kernel<uint4>), dim3(bx, N), 256, 0, st, (uint4*)ring, (const uint4*)frame, fresh, K, row_v, slot);
+  else GEECO_LAUNCH((ring_push_kernel<unsigned int>), dim3(bx, N), 256, 0, st, (unsigned int*)ring, (const unsigned int*)frame, fresh, K, row_v, slot);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
