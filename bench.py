@@ -338,7 +338,7 @@ def run_ours(args):
       if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
       return {'value': world * N * n_e2e / (float(t2.item()) * 1e-3), 'unit': UNIT,
-              'h2d_bytes_per_step': eng.h2d_bytes(True, frames_u8=frames_u8), 'd2h_bytes_per_step': 32,
+              'h2d_bytes_per_step': eng.h2d_bytes(True, frames_u8=frames_u8), 'd2h_bytes_per_step': 4 * 12,
               'steps': n_e2e}
 
     # float32 frames in [0,1]: exactly what the reference's model_fn is handed (estimator.py:160-176); 252 MB of
@@ -353,9 +353,25 @@ def run_ours(args):
       for k in ('rgb', 'target_rgb'):
         ub[k] = torch.round(hb[k] * 255.0).to(torch.uint8).pin_memory()
       u8_batches.append(ub)
-    e2e = timed_train(u8_batches, True)
-    e2e['api'] = ('geeco_b200.estimator.Estimator.train(input_fn over pinned host batches, uint8 frames as recorded), '
+    e2e_u8 = timed_train(u8_batches, True)
+    e2e_u8['api'] = ('Estimator.train(input_fn over pinned host batches, uint8 frames as recorded, dense [N,K,H,W,C] windows)')
+    # headline: the batches as the input pipeline emits them for consecutive windows (layout='pool': every distinct
+    # frame once + an int32 index; the 64 windows of a batch are consecutive windows of two episodes, as in the
+    # reference's batches of 32 consecutive windows).  Same pixels reach the network (bit-identical step:
+    # tests/test_gpu_switches.py::test_frame_pool_layout_trains_bit_identically), ~4x fewer bytes cross PCIe.
+    from geeco_b200.data import synthetic_pool_batch
+    pool_batches = []
+    for i in range(NB):
+      pf, pl = synthetic_pool_batch(N, pieces=max(1, N // 32), seed=4321 + rank * 16 + i, structured=False)
+      hb = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pf.items() if k != 'step'}
+      hb['cmd'] = torch.from_numpy(pl['cmd']).pin_memory()
+      pool_batches.append(hb)
+    e2e = timed_train(pool_batches, True)
+    e2e['h2d_bytes_per_step'] = eng.h2d_bytes(True, frames_u8=True, features=pool_batches[0])
+    e2e['api'] = ('geeco_b200.estimator.Estimator.train(input_fn over pinned host batches in the frame-pool layout of '
+                  "pickplace_input_fn(layout='pool'): uint8 frames as recorded, each distinct frame once + index), "
                   'log_steps=1: every step uploads its batch and copies its losses back')
+    e2e['dense_uint8_windows'] = e2e_u8
     e2e['float32_frames'] = e2e_f32
 
   peaks = load_peaks()

@@ -43,7 +43,7 @@ class GeecoParamDesc(C.Structure):
 
 class GeecoBatch(C.Structure):
   _fields_ = [(n, C.c_void_p) for n in ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state', 'cmd', 'vel_target',
-                                        'ee_target', 'grp_target', 'reset_mask')] + [
+                                        'ee_target', 'grp_target', 'reset_mask', 'frame_index', 'target_index')] + [
       ('frame_format', C.c_int32), ('ring_start', C.c_int32)]
 
 

@@ -90,10 +90,11 @@ int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, in
                           const float* alpha_host, cudaStream_t st);
 int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP,
                              float* dynbuff_f32, float* dyndiff_f32, int N, int K, int H, int W, int C,
-                             const float* alpha_host, int cluster_hint, int ring_start, cudaStream_t st);
+                             const float* alpha_host, int cluster_hint, int ring_start, const int* frame_index,
+                             const int* target_index, cudaStream_t st);
 int launch_preprocess_seq(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP, int* minmax_scratch,
                           float* dyndiff_f32, int N, int K, int H, int W, int C, int with_tgt, int with_diff,
-                          int ring_start, cudaStream_t st);
+                          int ring_start, const int* frame_index, const int* target_index, cudaStream_t st);
 // conv_fp32.cu
 int launch_gemm_nn_f32(const GatherGeom& g, const float* src, const float* B, const float* bias,
                        const float* mask, float* dst, int groups, int epi, cudaStream_t st);

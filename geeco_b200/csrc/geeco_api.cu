@@ -733,13 +733,13 @@ static int forward_impl(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
   if (c->variant == VAR_GEECOF) {
     rc = launch_preprocess_geecof(b->rgb, b->target_rgb, u8, c->x0, bf16 ? 1 : 0, c->CP, out ? out->dynbuff : nullptr,
                                   out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
-                                  cfg.img_width, cfg.img_channels, c->alpha, 0, b->ring_start, st);
+                                  cfg.img_width, cfg.img_channels, c->alpha, 0, b->ring_start, b->frame_index, b->target_index, st);
   } else {
     const int with_tgt = c->variant == VAR_SEQ_CONSTANT || c->variant == VAR_SEQ_RESIDUAL;
     const int with_diff = c->variant == VAR_SEQ_DYNDIFF;
     rc = launch_preprocess_seq(b->rgb, b->target_rgb, u8, c->x0, bf16 ? 1 : 0, c->CP, c->mm_scratch,
                                out ? out->dyndiff : nullptr, cfg.batch_size, cfg.window_size, cfg.img_height,
-                               cfg.img_width, cfg.img_channels, with_tgt, with_diff, b->ring_start, st);
+                               cfg.img_width, cfg.img_channels, with_tgt, with_diff, b->ring_start, b->frame_index, b->target_index, st);
   }
   if (rc) return rc;
   const float* y8;

@@ -240,7 +240,7 @@ template <typename InT, typename OutT, int CP, int C, int K>
 __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
-    AlphaTab al, int ring_start) {
+    AlphaTab al, int ring_start, const int* __restrict__ frame_index, const int* __restrict__ target_index) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
@@ -258,8 +258,15 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   const long long lo = (long long)blockIdx.x * per_units;
   long long hi = lo + per_units; if (hi > units) hi = units;
   const long long img4 = units * C;                       // float4 per image
-  const InT* fbase = rgb + n * K * img4 * 4;
-  const InT* tbase = tgt + n * img4 * 4;
+  // frame k of this sample: dense [N,K,...] layout, or a pool of frames addressed through frame_index (windows of
+  // one episode share frames: the pool holds each once)
+  const InT* fk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int kp = (k + ring_start) % K;
+    fk[k] = rgb + (frame_index ? (long long)frame_index[n * K + kp] : n * K + kp) * img4 * 4;
+  }
+  const InT* tbase = tgt + (target_index ? (long long)target_index[n] : n) * img4 * 4;
   const long long img_out = units * 4 * CP;               // OutT elements per padded image
   OutT* x_cur = x0 + n * img_out;
   OutT* x_dyn = x0 + ((long long)N + n) * img_out;
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fbase, ((k + ring_start) % K) * img4 + u * C + j, s_lut);
+      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fk[k], u * C + j, s_lut);
 #pragma unroll
     for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
     float cur[4 * C];
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     for (int j = 0; j < C; ++j) {
       const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
       // same two operations on the same operands as in pass 1: bit-identical difference image
-      const float4 c4 = FrameLoad<InT>::at(fbase, (long long)((K - 1 + ring_start) % K) * img4 + u * C + j, s_lut);
+      const float4 c4 = FrameLoad<InT>::at(fk[K - 1], u * C + j, s_lut);
       const float4 tj = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
       const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, c4), 0.5f, tj), mn1, rng1);
       e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
@@ -402,7 +409,8 @@ int launch_dynimg_twopass(const float* in, float* out, float* minmax_scratch, in
 
 template <typename InT, typename OutT, int CP, int C>
 static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, float* dd, int N, int K, int H, int W,
-                        const AlphaTab& al_in, int cluster_hint, int ring_start, cudaStream_t st) {
+                        const AlphaTab& al_in, int cluster_hint, int ring_start, const int* frame_index,
+                        const int* target_index, cudaStream_t st) {
   long long units = (long long)H * W / 4;
   if (cluster_hint <= 0) { if (const char* e = getenv("GEECO_PRE_CLUSTER")) cluster_hint = atoi(e); }
   int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
@@ -415,14 +423,15 @@ static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, flo
   OutT* x = reinterpret_cast<OutT*>(x0);
   AlphaTab al = al_in;
   void* args[] = {(void*)&rgb, (void*)&tgt, (void*)&x, (void*)&db, (void*)&dd, (void*)&N, (void*)&units,
-                  (void*)&per_units, (void*)&al, (void*)&ring_start};
+                  (void*)&per_units, (void*)&al, (void*)&ring_start, (void*)&frame_index, (void*)&target_index};
   RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<InT, OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
   return GEECO_OK;
 }
 
 int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP,
                              float* dynbuff_f32, float* dyndiff_f32, int N, int K, int H, int W, int C,
-                             const float* alpha_host, int cluster_hint, int ring_start, cudaStream_t st) {
+                             const float* alpha_host, int cluster_hint, int ring_start, const int* frame_index,
+                             const int* target_index, cudaStream_t st) {
   if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
   if (ring_start < 0 || ring_start >= K) { geeco_set_error("preprocess: ring_start %d outside [0,%d)", ring_start, K); return GEECO_ERR_INVALID; }
   if (N <= 0) return GEECO_OK;
@@ -432,9 +441,10 @@ int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, vo
   for (int k = 0; k < K; ++k) al.a[k] = alpha_host[k];
 #define PRE_CASE(T, cp, c)                                                                                        \
   return frames_u8 ? launch_pre_t<unsigned char, T, cp, c>((const unsigned char*)rgb, (const unsigned char*)tgt, x0,  \
-                                                           dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, st) \
+                                                           dynbuff_f32, dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, frame_index, \
+                                                           target_index, st) \
                    : launch_pre_t<float, T, cp, c>((const float*)rgb, (const float*)tgt, x0, dynbuff_f32,             \
-                                                   dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, st)
+                                                   dyndiff_f32, N, K, H, W, al, cluster_hint, ring_start, frame_index, target_index, st)
   if (!out_bf16 && CP == 4 && C == 3) PRE_CASE(float, 4, 3);
   if (!out_bf16 && CP == 4 && C == 4) PRE_CASE(float, 4, 4);
   if (out_bf16 && CP == 8 && C == 3) PRE_CASE(__nv_bfloat16, 8, 3);
@@ -457,7 +467,9 @@ int launch_preprocess_geecof(const void* rgb, const void* tgt, int frames_u8, vo
 template <typename InT, typename OutT, int CP, int C>
 __global__ void __launch_bounds__(256) seq_frames_kernel(const InT* __restrict__ rgb, const InT* __restrict__ tgt,
                                                          OutT* __restrict__ x0, int* __restrict__ mm, int N, int K,
-                                                         int with_diff, long long units, int ring_start) {
+                                                         int with_diff, long long units, int ring_start,
+                                                         const int* __restrict__ frame_index,
+                                                         const int* __restrict__ target_index) {
   pdl_enter();
   __shared__ float s_lut[256];
   if (sizeof(InT) == 1) {
@@ -466,8 +478,10 @@ __global__ void __launch_bounds__(256) seq_frames_kernel(const InT* __restrict__
   }
   const int img = blockIdx.y, t = img / N, n = img - t * N;
   const long long img4 = units * C;
-  const InT* fbase = t < K ? rgb + ((long long)n * K + (t + ring_start) % K) * img4 * 4 : tgt + (long long)n * img4 * 4;
-  const InT* tbase = tgt ? tgt + (long long)n * img4 * 4 : nullptr;
+  const long long fsel = (long long)n * K + (t + ring_start) % K;
+  const long long tsel = target_index ? (long long)target_index[n] : n;
+  const InT* fbase = t < K ? rgb + (frame_index ? (long long)frame_index[fsel] : fsel) * img4 * 4 : tgt + tsel * img4 * 4;
+  const InT* tbase = tgt ? tgt + tsel * img4 * 4 : nullptr;
   OutT* xo = x0 + (long long)img * units * 4 * CP;
   const bool diff = with_diff && t < K;
   float mn = FLT_MAX, mx = -FLT_MAX;
@@ -495,7 +509,8 @@ template <typename InT, typename OutT, int CP, int C>
 __global__ void __launch_bounds__(256) seq_dyndiff_kernel(const InT* __restrict__ rgb, const InT* __restrict__ tgt,
                                                           OutT* __restrict__ x1, const int* __restrict__ mm,
                                                           float* __restrict__ dyndiff_f32, int N, int K, long long units,
-                                                          int ring_start) {
+                                                          int ring_start, const int* __restrict__ frame_index,
+                                                          const int* __restrict__ target_index) {
   pdl_enter();
   __shared__ float s_lut[256];
   if (sizeof(InT) == 1) {
@@ -504,8 +519,9 @@ __global__ void __launch_bounds__(256) seq_dyndiff_kernel(const InT* __restrict_
   }
   const int img = blockIdx.y, t = img / N, n = img - t * N;
   const long long img4 = units * C;
-  const InT* fbase = rgb + ((long long)n * K + (t + ring_start) % K) * img4 * 4;
-  const InT* tbase = tgt + (long long)n * img4 * 4;
+  const long long fsel = (long long)n * K + (t + ring_start) % K;
+  const InT* fbase = rgb + (frame_index ? (long long)frame_index[fsel] : fsel) * img4 * 4;
+  const InT* tbase = tgt + (target_index ? (long long)target_index[n] : n) * img4 * 4;
   OutT* xo = x1 + (long long)img * units * 4 * CP;
   const float mn = ord2f(mm[2 * img]), mx = ord2f(mm[2 * img + 1]);
   const float rng = __fadd_rn(__fsub_rn(mx, mn), 1e-6f);
@@ -525,17 +541,18 @@ __global__ void __launch_bounds__(256) seq_dyndiff_kernel(const InT* __restrict_
 
 template <typename InT, typename OutT, int CP, int C>
 static int launch_seq_t(const InT* rgb, const InT* tgt, void* x0, int* mm, float* dd, int N, int K, int H, int W,
-                        int with_tgt, int with_diff, int ring_start, cudaStream_t st) {
+                        int with_tgt, int with_diff, int ring_start, const int* frame_index, const int* target_index,
+                        cudaStream_t st) {
   const long long units = (long long)H * W / 4;
   const int imgs = K * N + (with_tgt ? N : 0);
   int bx = (int)((units + 256 * 4 - 1) / (256 * 4)); if (bx < 1) bx = 1;
   OutT* x = reinterpret_cast<OutT*>(x0);
   if (with_diff) GEECO_LAUNCH((minmax_init_kernel), ceil_div(K * N, 256), 256, 0, st, mm, K * N);
-  GEECO_LAUNCH((seq_frames_kernel<InT, OutT, CP, C>), dim3(bx, imgs), 256, 0, st, rgb, tgt, x, mm, N, K, with_diff, units, ring_start);
+  GEECO_LAUNCH((seq_frames_kernel<InT, OutT, CP, C>), dim3(bx, imgs), 256, 0, st, rgb, tgt, x, mm, N, K, with_diff, units, ring_start, frame_index, target_index);
   geeco_count_launch(with_diff ? 2 : 1);
   if (with_diff) {
     GEECO_LAUNCH((seq_dyndiff_kernel<InT, OutT, CP, C>), dim3(bx, K * N), 256, 0, st, rgb, tgt, x + (long long)K * N * units * 4 * CP, mm, dd,
-                                                                         N, K, units, ring_start);
+                                                                         N, K, units, ring_start, frame_index, target_index);
     geeco_count_launch(1);
   }
   CUDA_TRY(cudaGetLastError());
@@ -544,7 +561,7 @@ static int launch_seq_t(const InT* rgb, const InT* tgt, void* x0, int* mm, float
 
 int launch_preprocess_seq(const void* rgb, const void* tgt, int frames_u8, void* x0, int out_bf16, int CP, int* minmax_scratch,
                           float* dyndiff_f32, int N, int K, int H, int W, int C, int with_tgt, int with_diff,
-                          int ring_start, cudaStream_t st) {
+                          int ring_start, const int* frame_index, const int* target_index, cudaStream_t st) {
   if ((H * (long long)W) % 4) { geeco_set_error("preprocess: H*W must be a multiple of 4"); return GEECO_ERR_INVALID; }
   if (N <= 0) return GEECO_OK;
   if ((long long)(K + 1) * N > 65535) { geeco_set_error("preprocess: (K+1)*N = %lld images > 65535", (long long)(K + 1) * N); return GEECO_ERR_INVALID; }
@@ -554,9 +571,9 @@ int launch_preprocess_seq(const void* rgb, const void* tgt, int frames_u8, void*
 #define SEQ_CASE(T, cp, c)                                                                                          \
   return frames_u8 ? launch_seq_t<unsigned char, T, cp, c>((const unsigned char*)rgb, (const unsigned char*)tgt, x0,    \
                                                            minmax_scratch, dyndiff_f32, N, K, H, W, with_tgt, with_diff, \
-                                                           ring_start, st)                                              \
+                                                           ring_start, frame_index, target_index, st)                   \
                    : launch_seq_t<float, T, cp, c>((const float*)rgb, (const float*)tgt, x0, minmax_scratch, dyndiff_f32, \
-                                                   N, K, H, W, with_tgt, with_diff, ring_start, st)
+                                                   N, K, H, W, with_tgt, with_diff, ring_start, frame_index, target_index, st)
   if (!out_bf16 && CP == 4 && C == 3) SEQ_CASE(float, 4, 3);
   if (!out_bf16 && CP == 4 && C == 4) SEQ_CASE(float, 4, 4);
   if (out_bf16 && CP == 4 && C == 3) SEQ_CASE(__nv_bfloat16, 4, 3);

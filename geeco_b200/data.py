@@ -106,6 +106,51 @@ def synthetic_batch(n, window_size=4, height=256, width=256, channels=3, seed=0,
   return features, labels
 
 
+def to_pool_layout(features, pieces=2):
+  """Re-expresses a dense batch whose windows are CONSECUTIVE windows of `pieces` episodes (what the input pipeline
+  emits: batches are consecutive stream positions, geeco_gym.py:471-473) in the frame-pool layout of
+  include/geeco_b200.h: `rgb` [F,H,W,C] holds every distinct frame once, `rgb_index` [N,K] int32 addresses it,
+  `target_rgb` [pieces,H,W,C] + `target_index` [N].  Only the layout changes; `synthetic_pool_batch` builds batches
+  that really have this structure."""
+  rgb, tgt = np.asarray(features['rgb']), np.asarray(features['target_rgb'])
+  n, K = rgb.shape[:2]
+  per = -(-n // pieces)
+  frames, index, tix, targets = [], np.empty((n, K), np.int32), np.empty((n,), np.int32), []
+  base = 0
+  for p in range(pieces):
+    lo, hi = p * per, min(n, (p + 1) * per)
+    if hi <= lo:
+      break
+    cnt = hi - lo
+    # window i of the piece = frames i .. i+K-1 of the piece's frame run
+    run = [rgb[lo, k] for k in range(K - 1)] + [rgb[lo + i, K - 1] for i in range(cnt)]
+    frames += run
+    index[lo:hi] = base + np.arange(cnt, dtype=np.int32)[:, None] + np.arange(K, dtype=np.int32)[None, :]
+    targets.append(tgt[lo])
+    tix[lo:hi] = p
+    base += len(run)
+  out = dict(features)
+  out['rgb'], out['rgb_index'] = np.stack(frames), index
+  out['target_rgb'], out['target_index'] = np.stack(targets), tix
+  return out
+
+
+def expand_pool_layout(features):
+  """The dense [N,K,H,W,C] / [N,H,W,C] tensors a frame-pool batch stands for."""
+  out = {k: v for k, v in features.items() if k not in ('rgb_index', 'target_index')}
+  out['rgb'] = np.asarray(features['rgb'])[np.asarray(features['rgb_index'])]
+  if 'target_index' in features:
+    out['target_rgb'] = np.asarray(features['target_rgb'])[np.asarray(features['target_index'])]
+  return out
+
+
+def synthetic_pool_batch(n, window_size=4, pieces=2, seed=0, frame_format='uint8', **kw):
+  """A synthetic batch of `n` windows that are consecutive windows of `pieces` episodes, in the frame-pool layout
+  (see to_pool_layout).  Returns (features, labels); `expand_pool_layout(features)` gives the equivalent dense batch."""
+  feats, labels = synthetic_batch(n, window_size=window_size, seed=seed, frame_format=frame_format, **kw)
+  return to_pool_layout(feats, pieces), labels
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic datasets on disk, in the recorder's format (src/data/data_recorder.py, PickAndPlaceEncodingV4)
 # ------------------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@ LOSS_KEYS = ('loss_cmd_ee', 'loss_cmd_grp', 'loss_pos_ee', 'loss_pos_obj', 'loss
 LOSS_SLOT_CMD_VEL = 8          # velocity control: loss_cmd_vel (include/geeco_b200.h, geeco_outputs.losses)
 _FEATURE_KEYS = ('rgb', 'target_rgb', 'jnt_state', 'ee_state', 'obj_state')
 _FRAME_KEYS = ('rgb', 'target_rgb')
+_INDEX_KEYS = ('rgb_index', 'target_index')
 _LABEL_KEYS = {'cartesian': ('cmd',), 'velocity': ('vel_target', 'ee_target', 'grp_target')}   # estimator.py:206-236
 
 
@@ -197,12 +198,35 @@ class Engine(object):
             'ee_state': (N, K, 7), 'obj_state': (N, K, 7), 'cmd': (N, 4), 'vel_target': (N, cfg.dim_jnt_state),
             'ee_target': (N, 7), 'grp_target': (N, cfg.dim_grp_command)}
 
-  def _feature_keys(self, with_labels):
-    keys = ['rgb'] + (['target_rgb'] if self.goal_condition == 'target' else []) + ['jnt_state']
+  def _feature_keys(self, with_labels, features=None):
+    goal = self.goal_condition == 'target'
+    keys = ['rgb'] + (['target_rgb'] if goal else []) + ['jnt_state']
+    if features is not None and 'rgb_index' in features:          # frame-pool layout (include/geeco_b200.h: frame_index)
+      keys += ['rgb_index'] + (['target_index'] if goal else [])
     return keys + (['ee_state', 'obj_state'] if with_labels else [])
 
   def _label_keys(self):
     return _LABEL_KEYS[self.cfg.control_mode]
+
+  def _expect(self, key, tensor, pooled):
+    """(capacity shape, wire dtype) of an input; raises ValueError on a shape the graph cannot take.  In the
+    frame-pool layout `rgb` / `target_rgb` are [F,H,W,C] with any F up to the dense frame count."""
+    cfg, N, K = self.cfg, self.N, self.cfg.window_size
+    if key in _INDEX_KEYS:
+      shape = (N, K) if key == 'rgb_index' else (N,)
+      if tuple(tensor.shape) != shape:
+        raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(tensor.shape)))
+      return shape, torch.int32
+    shape = self._shapes()[key]
+    wd = self._wire_dtype(key, tensor.dtype)
+    if pooled and key in _FRAME_KEYS:
+      cap = (N * K if key == 'rgb' else N,) + shape[-3:]
+      if tensor.dim() != 4 or tuple(tensor.shape[1:]) != cap[1:] or not 1 <= tensor.shape[0] <= cap[0]:
+        raise ValueError("%s pool: expected [F<=%d,%d,%d,%d], got %s" % ((key, cap[0]) + cap[1:] + (tuple(tensor.shape),)))
+      return cap, wd
+    if tuple(tensor.shape) != shape:
+      raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(tensor.shape)))
+    return shape, wd
 
   @staticmethod
   def _wire_dtype(key, dtype):
@@ -210,30 +234,28 @@ class Engine(object):
     (geeco_gym.py:310); everything else travels as float32."""
     return torch.uint8 if key in _FRAME_KEYS and dtype == torch.uint8 else torch.float32
 
-  def _to_device(self, key, value):
+  def _to_device(self, key, value, pooled=False):
     """Accepts a CUDA tensor (used in place) or a host array (staged through pinned memory)."""
-    shape = self._shapes()[key]
     if torch.is_tensor(value) and value.is_cuda:
-      if tuple(value.shape) != shape:
-        raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(value.shape)))
-      return value.contiguous().to(self._wire_dtype(key, value.dtype))
+      _, wd = self._expect(key, value, pooled)
+      return value.contiguous().to(wd)
     arr = value if torch.is_tensor(value) else torch.from_numpy(np.ascontiguousarray(value))
-    if tuple(arr.shape) != shape:
-      raise ValueError("%s: expected shape %s, got %s" % (key, shape, tuple(arr.shape)))
-    wd = self._wire_dtype(key, arr.dtype)
-    dk = (key, wd)
+    cap, wd = self._expect(key, arr, pooled)
+    dk = (key, wd, pooled)
     if dk not in self._dev_in:
-      self._dev_in[dk] = torch.empty(shape, dtype=wd, device=self.device)
+      self._dev_in[dk] = torch.empty(cap, dtype=wd, device=self.device)
+    dst = self._dev_in[dk][:arr.shape[0]] if len(cap) else self._dev_in[dk]
     if arr.dtype == wd and arr.is_pinned():
-      self._dev_in[dk].copy_(arr, non_blocking=True)       # caller-pinned: straight H2D
-      return self._dev_in[dk]
+      dst.copy_(arr, non_blocking=True)                     # caller-pinned: straight H2D
+      return dst
     if dk not in self._pin_in:
-      self._pin_in[dk] = torch.empty(shape, dtype=wd).pin_memory()
+      self._pin_in[dk] = torch.empty(cap, dtype=wd).pin_memory()
     self._pin_wait(dk)                                     # the upload that last read this pinned buffer is done
-    self._pin_in[dk].copy_(arr)
-    self._dev_in[dk].copy_(self._pin_in[dk], non_blocking=True)
+    pin = self._pin_in[dk][:arr.shape[0]]
+    pin.copy_(arr)
+    dst.copy_(pin, non_blocking=True)
     self._pin_mark(dk, torch.cuda.current_stream(self.device))
-    return self._dev_in[dk]
+    return dst
 
   # A pinned staging buffer is written by the HOST (`pin.copy_`) and read by an asynchronous H2D copy.  Nothing in
   # a train step synchronises the host, so the host may run several steps ahead of the device: before it rewrites
@@ -258,12 +280,12 @@ class Engine(object):
       self._stage_free = [None, None]
       self._copy_stream = torch.cuda.Stream(device=self.device)
     bufs = self._stage_bufs[slot]
-    shapes = self._shapes()
     out = {}
+    pooled = 'rgb_index' in features
     with torch.cuda.stream(self._copy_stream):
       if self._stage_free[slot] is not None:
         self._copy_stream.wait_event(self._stage_free[slot])      # the step that last read this slot is done
-      items = [(k, features[k]) for k in self._feature_keys(True) if k in features]
+      items = [(k, features[k]) for k in self._feature_keys(True, features) if k in features]
       if labels is not None:
         items += [(k, labels[k]) for k in self._label_keys()]
       for k, v in items:
@@ -271,22 +293,23 @@ class Engine(object):
           out[k] = v
           continue
         t = v if torch.is_tensor(v) else torch.from_numpy(np.ascontiguousarray(v))
-        if tuple(t.shape) != shapes[k]:
-          raise ValueError("%s: expected shape %s, got %s" % (k, shapes[k], tuple(t.shape)))
-        wd = self._wire_dtype(k, t.dtype)
-        if (k, wd) not in bufs:
-          bufs[(k, wd)] = torch.empty(shapes[k], dtype=wd, device=self.device)
+        cap, wd = self._expect(k, t, pooled)
+        bk = (k, wd, pooled)
+        if bk not in bufs:
+          bufs[bk] = torch.empty(cap, dtype=wd, device=self.device)
+        dst = bufs[bk][:t.shape[0]]
         if not (t.dtype == wd and t.is_pinned()):
-          if (k, wd, slot) not in self._pin_in:
-            self._pin_in[(k, wd, slot)] = torch.empty(shapes[k], dtype=wd).pin_memory()
-          pin = self._pin_in[(k, wd, slot)]
-          self._pin_wait((k, wd, slot))
+          pk = bk + (slot,)
+          if pk not in self._pin_in:
+            self._pin_in[pk] = torch.empty(cap, dtype=wd).pin_memory()
+          pin = self._pin_in[pk][:t.shape[0]]
+          self._pin_wait(pk)
           pin.copy_(t)
-          bufs[(k, wd)].copy_(pin, non_blocking=True)
-          self._pin_mark((k, wd, slot), self._copy_stream)
+          dst.copy_(pin, non_blocking=True)
+          self._pin_mark(pk, self._copy_stream)
         else:
-          bufs[(k, wd)].copy_(t, non_blocking=True)
-        out[k] = bufs[(k, wd)]
+          dst.copy_(t, non_blocking=True)
+        out[k] = dst
       ev = torch.cuda.Event()
       ev.record(self._copy_stream)
     return out, ({k: out[k] for k in self._label_keys()} if labels is not None else None), ev
@@ -300,18 +323,24 @@ class Engine(object):
     ev.record(torch.cuda.current_stream(self.device))
     self._stage_free[slot] = ev
 
-  def h2d_bytes(self, with_labels=True, frames_u8=False):
-    keys = self._feature_keys(with_labels) + (list(self._label_keys()) if with_labels else [])
+  def h2d_bytes(self, with_labels=True, frames_u8=False, features=None):
+    """Bytes one step uploads.  With `features` (a host batch) the actual tensor sizes are counted, which is what
+    matters for the frame-pool layout; else the dense layout of the graph's input shapes."""
+    keys = self._feature_keys(with_labels, features) + (list(self._label_keys()) if with_labels else [])
+    if features is not None:
+      return int(sum(int(np.prod(np.shape(features[k]))) * (1 if (k in _FRAME_KEYS and frames_u8) else 4)
+                     for k in keys if k in features))
     return int(sum((1 if frames_u8 and k in _FRAME_KEYS else 4) * int(np.prod(self._shapes()[k])) for k in keys))
 
   def _batch(self, features, labels, ring_start=0, reset_mask=None):
     b = _lib.GeecoBatch()
     keep = []
-    fkeys = self._feature_keys(False)
+    pooled = 'rgb_index' in features
+    fkeys = self._feature_keys(False, features)
     for k in fkeys:
-      t = self._to_device(k, features[k])
+      t = self._to_device(k, features[k], pooled)
       keep.append(t)
-      setattr(b, k, t.data_ptr())
+      setattr(b, {'rgb_index': 'frame_index'}.get(k, k), t.data_ptr())
     if 'target_rgb' in fkeys and keep[0].dtype != keep[1].dtype:
       raise ValueError("rgb is %s but target_rgb is %s: both must be float32 in [0,1] or both uint8 [0..255]"
                        % (keep[0].dtype, keep[1].dtype))

@@ -202,7 +202,7 @@ def _model_fn(features, labels, mode, params, goal_condition):
   if mode not in (ModeKeys.TRAIN, ModeKeys.EVAL, ModeKeys.PREDICT):
     raise RuntimeError("Unknown estimator mode: %s" % (mode,))
   features = decode_observation(features, config, goal=goal_condition == 'target')
-  batch = int(np.shape(features['rgb'])[0])
+  batch = int(np.shape(features['jnt_state'])[0])
   eng = params.get('engine') or _engine_for(config, batch, params.get('precision', 'bf16'), mode == ModeKeys.TRAIN,
                                             goal_condition)
   if getattr(eng, 'goal_condition', goal_condition) != goal_condition:
@@ -265,7 +265,7 @@ class Estimator(object):
     return self._engine
 
   def _check_batch(self, features):
-    n = int(np.shape(features['rgb'])[0])
+    n = int(np.shape(features['jnt_state'])[0])          # (rgb may be a frame pool: its first axis counts frames)
     if n != self._batch:
       # lstm_memory is created with the static shape [batch_size, 2*dim_h_lstm] (graph.py:212,218): every
       # batch the reference sees has exactly batch_size rows

@@ -221,7 +221,7 @@ class WindowBatches(object):
 
   def __init__(self, tfrecord_paths, meta, window_size=4, fetch_target=False, batch_size=1, num_epochs=1,
                num_threads=4, prefetch_size=4, frame_format='float32', drop_remainder=False, rank=0, world=1,
-               pin_memory=False, verify_crc=True, want_depth=True, cache_dir=None, device=None):
+               pin_memory=False, verify_crc=True, want_depth=True, cache_dir=None, device=None, layout='windows'):
     if window_size < 1 or window_size > meta.episode_length - 1:
       raise ValueError("window_size %d does not fit episodes of %d frames" % (window_size, meta.episode_length))
     if not 0 <= rank < world:
@@ -241,6 +241,15 @@ class WindowBatches(object):
     self.verify_crc = bool(verify_crc)
     self.want_depth = bool(want_depth)
     self.device = device                                   # None: host batches; 'cuda' / 'cpu': resident frames
+    if layout not in ('windows', 'pool'):
+      raise ValueError("layout must be 'windows' or 'pool', got %r" % (layout,))
+    if layout == 'pool' and device is not None:
+      raise ValueError("layout='pool' is a host-batch layout; device-resident frames already share frames between windows")
+    # 'pool': the image features of a batch are the DISTINCT frames its windows touch ([F,H,W,C], F = windows + K - 1
+    # per episode piece) plus an int32 index [B,K] into them, and one goal frame per piece with an index [B]: the
+    # frame-pool layout of include/geeco_b200.h (geeco_batch.frame_index).  Consecutive windows share K-1 frames, so
+    # the host copies and the upload move ~K times fewer bytes; the step reads the same pixels.
+    self.layout = layout
     self._resident = collections.OrderedDict()             # stream episode -> {key: tensor on self.device}
     self._cuda_index = None                                # the consumer's CUDA device, adopted by the helper threads
     self.uploaded_bytes = 0
@@ -332,15 +341,41 @@ class WindowBatches(object):
     self._pinned = []
     at = 0
     on_device = self.device is not None
-    for e, w0, cnt in self.pieces(lo, hi):
+    pool = self.layout == 'pool'
+    if pool:
+      pieces = self.pieces(lo, hi)
+      F = sum(cnt + self.K - 1 for _, _, cnt in pieces)
+      feats['rgb_index'] = self._alloc((n, self.K), np.int32)
+      if self.fetch_target:
+        feats['target_index'] = self._alloc((n,), np.int32)
+      fat = 0
+    for pi, (e, w0, cnt) in enumerate(self.pieces(lo, hi)):
       ep = episodes[e]
+      if pool:
+        nf = cnt + self.K - 1
+        for k in BULK_KEYS:
+          if k not in ep:
+            continue
+          if k not in feats:
+            feats[k] = self._alloc((F,) + ep[k].shape[1:], ep[k].dtype)
+          feats[k][fat:fat + nf] = ep[k][w0:w0 + nf]        # the frames windows w0 .. w0+cnt-1 touch, once each
+        feats['rgb_index'][at:at + cnt] = fat + np.arange(cnt, dtype=np.int32)[:, None] + np.arange(self.K, dtype=np.int32)[None, :]
+        if self.fetch_target:
+          for k in TARGET_KEYS:
+            if k not in ep:
+              continue
+            if k not in feats:
+              feats[k] = self._alloc((len(pieces),) + ep[k].shape, ep[k].dtype)
+            feats[k][pi] = ep[k]
+          feats['target_index'][at:at + cnt] = pi
+        fat += nf
       for k in FEATURE_KEYS:
-        if k not in ep or (on_device and k in BULK_KEYS):
+        if k not in ep or ((on_device or pool) and k in BULK_KEYS):
           continue
         if k not in feats:
           feats[k] = self._alloc((n, self.K) + ep[k].shape[1:], ep[k].dtype)
         window_gather(ep[k], self.K, w0, cnt, out=feats[k][at:at + cnt])
-      if self.fetch_target and not on_device:
+      if self.fetch_target and not on_device and not pool:
         for k in TARGET_KEYS:
           if k not in ep:
             continue
@@ -457,7 +492,7 @@ class WindowBatches(object):
 def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_target=False, shuffle_buffer=128,
                           batch_size=1, num_epochs=1, num_threads=4, prefetch_size=4, seed=None,
                           frame_format='float32', drop_remainder=False, rank=0, world=1, pin_memory=False,
-                          cache_dir=None, want_depth=True, device=None):
+                          cache_dir=None, want_depth=True, device=None, layout='windows'):
   """Same signature and defaults as the reference (geeco_gym.py:401-412) plus the execution keywords after
   `seed`.  `shuffle_buffer` is accepted and unused, as in the reference (its window-level shuffle is commented
   out, :446-448); `mode == 'train'` shuffles the episode order with numpy's global generator (:436-437), or
@@ -471,7 +506,7 @@ def pickplace_input_fn_v4(dataset_dir, split_name, mode, window_size=4, fetch_ta
   return WindowBatches(paths, meta, window_size=window_size, fetch_target=fetch_target, batch_size=batch_size,
                        num_epochs=num_epochs, num_threads=num_threads, prefetch_size=prefetch_size,
                        frame_format=frame_format, drop_remainder=drop_remainder, rank=rank, world=world,
-                       pin_memory=pin_memory, cache_dir=cache_dir, want_depth=want_depth, device=device)
+                       pin_memory=pin_memory, cache_dir=cache_dir, want_depth=want_depth, device=device, layout=layout)
 
 
 def pickplace_input_fn(dataset_dir, split_name, mode, encoding='v4', window_size=4, fetch_target=False,

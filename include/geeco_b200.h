@@ -105,6 +105,12 @@ typedef struct geeco_batch {
   const float* grp_target;  /* [N,dim_grp_command] / NULL labels['grp_target'] */
   const uint8_t* reset_mask;/* [N] or NULL; with carry_state = 1 the rows whose byte is non-zero start from the zero LSTM
                                state (an environment that was reset); ignored with carry_state = 0 */
+  const int32_t* frame_index; /* [N,K] or NULL.  Non-NULL: rgb is a POOL of frames [F,H,W,C] and frame k of row n is pool frame
+                               frame_index[n*K + k].  Consecutive windows of an episode share K-1 of their K frames
+                               (_window_v3, geeco_gym.py:615-631), so a batch of B windows is B+K-1 pool frames instead of
+                               B*K: the layout the input pipeline emits with layout='pool' (4x fewer bytes to upload) */
+  const int32_t* target_index;/* [N] or NULL.  Non-NULL: target_rgb is a pool [Ft,H,W,C] (one goal frame per episode,
+                               geeco_gym.py:313,624-625) and row n uses pool frame target_index[n] */
   int32_t frame_format;     /* GEECO_FRAMES_F32 | GEECO_FRAMES_U8: element type of rgb AND target_rgb */
   int32_t ring_start;       /* rgb / jnt_state as ring buffers over the K axis: physical slot of the OLDEST frame; logical
                                frame k lives in slot (ring_start + k) % K.  0 = plain layout */

@@ -73,6 +73,8 @@ _A('--cache_dir', type=str, default='', help='directory for decoded-episode cach
 _A('--device_frames', default=False, action='store_true',
    help='recorded datasets: upload every episode once and gather the K-frame windows on the device')
 _A('--checkpoint_format', type=str, default='npz', help='npz | bundle (TF V2 .index/.data files)')
+_A('--frame_layout', type=str, default='pool',
+   help='recorded datasets, host batches: pool (distinct frames + index: ~window_size x fewer bytes to upload) | windows')
 
 _OBSERVATION_FORMAT_TO_CHANNELS = {'rgb': 3, 'rgbd': 4}
 
@@ -151,7 +153,8 @@ def recorded_input_fn(args, config, mode, rank=0, world=1):
         frame_format='float32' if args.observation_format == 'rgbd' else 'uint8',
         drop_remainder=True, rank=rank, world=world, pin_memory=not args.device_frames,
         cache_dir=args.cache_dir or None, want_depth=(args.observation_format == 'rgbd'),
-        device='cuda' if args.device_frames else None)
+        device='cuda' if args.device_frames else None,
+        layout='windows' if args.device_frames else args.frame_layout)
   return make
 
 

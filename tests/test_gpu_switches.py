@@ -212,7 +212,7 @@ def test_staged_batches_survive_a_host_that_runs_ahead(cuda_device):
   eng.stage(fb, lb, 0)                                  # the host is a full batch ahead of the device now
   torch.cuda.synchronize()
   assert np.array_equal(snap_cmd.cpu().numpy(), la['cmd']) and np.array_equal(snap_jnt.cpu().numpy(), fa['jnt_state'])
-  assert np.array_equal(eng._stage_bufs[0][('cmd', torch.float32)].cpu().numpy(), lb['cmd'])
+  assert np.array_equal(eng._stage_bufs[0][('cmd', torch.float32, False)].cpu().numpy(), lb['cmd'])
   eng.close()
 
 
@@ -266,3 +266,70 @@ def test_sequence_graphs_train_step_k4(cuda_device, variant):
       print("%s K=4 bf16 worst gradient rel-L2 (given ReLU masks, bf16 storage emulated) %.3e (%s)" % (variant, worst[0], worst[1]))
       assert worst[0] <= 2e-2, worst
     eng.close()
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_frame_pool_layout_trains_bit_identically(cuda_device, precision, tmp_path):
+  """geeco_batch.frame_index / target_index (include/geeco_b200.h): a batch given as the distinct frames its windows
+  touch plus an index reads the same pixels as the dense [N,K,H,W,C] layout -- same network input, same step, bit for
+  bit -- while uploading ~K times fewer frame bytes.  Checked through Engine.train_step, through
+  Estimator.train(input_fn) over host batches (the e2e entry of bench.py), and for a sequence graph."""
+  from geeco_b200 import create_e2evmc_config
+  from geeco_b200.data import expand_pool_layout, synthetic_pool_batch
+  from geeco_b200.engine import Engine
+  from geeco_b200.estimator import Estimator, RunConfig, goal_e2evmc_model_fn
+  N = 6
+  cfg_d = O.make_config(batch_size=N, lr=1e-3)
+  cfg = create_e2evmc_config(cfg_d)
+  P = O.init_params(cfg_d, seed=41, dtype=torch.float32, bias_scale=0.05)
+  pooled, labels = synthetic_pool_batch(N, pieces=2, seed=42)
+  dense = expand_pool_layout(pooled)
+  assert pooled['rgb'].shape[0] == N + 2 * 3 and pooled['rgb'].dtype == np.uint8 and dense['rgb'].shape[:2] == (N, 4)
+  res = {}
+  for tag, feats in (('dense', dense), ('pool', pooled)):
+    eng = Engine(cfg, batch_size=N, precision=precision, training=True)
+    eng.set_params(P)
+    out = eng.forward(feats, labels, want_dyn=True)
+    torch.cuda.synchronize()
+    x0 = eng.debug_buffer('x0')
+    x0 = (x0.view(torch.int16) if x0.dtype == torch.bfloat16 else x0.view(torch.int32)).cpu().numpy().copy()
+    fwd = {k: out[k].cpu().numpy().copy() for k in ('pred_cmd_ee', 'dynbuff', 'dyndiff', 'losses')}
+    eng.train_step(feats, labels)
+    torch.cuda.synchronize()
+    res[tag] = (x0, fwd, eng.theta.cpu().numpy().copy())
+    assert eng.h2d_bytes(True, frames_u8=True, features=dict(feats, **labels)) == sum(
+        np.asarray(feats[k]).nbytes if k in ('rgb', 'target_rgb') else np.asarray(feats[k]).size * 4
+        for k in eng._feature_keys(True, feats)) + labels['cmd'].size * 4
+    eng.close()
+  assert np.array_equal(res['pool'][0], res['dense'][0])
+  for k, v in res['dense'][1].items():
+    assert np.array_equal(res['pool'][1][k], v), k
+  assert np.array_equal(res['pool'][2], res['dense'][2])
+  # Estimator.train over host batches in both layouts: same parameters after two steps
+  thetas = []
+  for tag, feats in (('dense', dense), ('pool', pooled)):
+    est = Estimator(goal_e2evmc_model_fn, str(tmp_path / tag), RunConfig(save_checkpoints_steps=0),
+                    {'e2evmc_config': cfg, 'log_steps': 1, 'save_final_checkpoint': False, 'seed': 5},
+                    precision=precision, batch_size=N)
+    est.train(lambda: iter([(feats, labels), (feats, labels)]))
+    torch.cuda.synchronize()
+    thetas.append(est.engine.theta.cpu().numpy().copy())
+  assert np.array_equal(thetas[0], thetas[1])
+  # a sequence graph (every frame through the encoder) reads the pool the same way
+  cfg_s = create_e2evmc_config(O.make_config(batch_size=N, proc_obs='sequence', proc_tgt='dyndiff'))
+  outs = []
+  for feats in (dense, pooled):
+    eng = Engine(cfg_s, batch_size=N, precision=precision, training=False)
+    eng.init_params(seed=6)
+    outs.append(eng.forward(feats, None)['pred_cmd_ee'].cpu().numpy().copy())
+    eng.close()
+  assert np.array_equal(outs[0], outs[1])
+  # malformed pools are refused
+  eng = Engine(cfg, batch_size=N, precision=precision, training=False)
+  bad = dict(pooled); bad['rgb'] = pooled['rgb'][:, :128]
+  with pytest.raises(ValueError, match='pool'):
+    eng.forward(bad, None)
+  bad = dict(pooled); bad['rgb_index'] = pooled['rgb_index'][:, :3]
+  with pytest.raises(ValueError, match='rgb_index'):
+    eng.forward(bad, None)
+  eng.close()

@@ -338,8 +338,9 @@ def test_unconditional_twins_need_the_cuda_path(tmp_path):
   with pytest.raises(FileNotFoundError):                    # load_model_config(model_dir, 'e2evmc_config'), predictor.py:224
     E2EVMCPredictor(str(tmp_path))
   cfg = create_e2evmc_config({})
+  feats = {'rgb': np.zeros((1, 4, 256, 256, 3), np.float32), 'jnt_state': np.zeros((1, 4, 7), np.float32)}
   with pytest.raises(RuntimeError, match='Unknown estimator mode'):                     # estimator.py:138-140
-    e2evmc_model_fn({'rgb': np.zeros((1, 4, 256, 256, 3), np.float32)}, None, 'serve', {'e2evmc_config': cfg})
+    e2evmc_model_fn(feats, None, 'serve', {'e2evmc_config': cfg})
   with pytest.raises(ValueError, match='number of channels'):                           # estimator.py:27-29
     e2evmc_model_fn({}, None, ModeKeys.PREDICT, {'e2evmc_config': cfg._replace(img_channels=5)})
   if not torch.cuda.is_available():
@@ -347,7 +348,7 @@ def test_unconditional_twins_need_the_cuda_path(tmp_path):
     with pytest.raises(RuntimeError, match='no CPU fallback'):
       E2EVMCPredictor(str(tmp_path))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
-      e2evmc_model_fn({'rgb': np.zeros((1, 4, 256, 256, 3), np.float32)}, None, ModeKeys.PREDICT, {'e2evmc_config': cfg})
+      e2evmc_model_fn(feats, None, ModeKeys.PREDICT, {'e2evmc_config': cfg})
 
 
 def test_target_frame_loaders(tmp_path):

@@ -407,6 +407,38 @@ def test_pipeline_uint8_frames_and_epochs(dataset):
     np.testing.assert_array_equal(b[0]['jnt_state'], a[0]['jnt_state'])
 
 
+@pytest.mark.parametrize('B', [4, 7])
+def test_pipeline_pool_layout_expands_to_the_window_layout(dataset, B):
+  """layout='pool' (frame pool + index, include/geeco_b200.h: geeco_batch.frame_index): gathering the pool through the
+  index gives the window tensors of the default layout bit for bit; every frame a batch touches is stored once per
+  episode piece; everything that is not an image is unchanged."""
+  d, eps = dataset
+  kw = dict(batch_size=B, num_epochs=1, frame_format='uint8')
+  win = list(ip.pickplace_input_fn_v4(d, 'default', 'train', 4, True, seed=3, **kw))
+  pool = list(ip.pickplace_input_fn_v4(d, 'default', 'train', 4, True, seed=3, layout='pool', **kw))
+  assert len(win) == len(pool) > 0
+  total_pool = total_win = 0
+  for (fw, lw), (fp, lp) in zip(win, pool):
+    idx, tix = fp['rgb_index'], fp['target_index']
+    assert idx.dtype == np.int32 and idx.shape == fw['rgb'].shape[:2] and tix.shape == (fw['rgb'].shape[0],)
+    assert fp['rgb'].ndim == 4 and fp['rgb'].shape[0] <= idx.size           # frames are shared (a 1-window rest: K frames)
+    np.testing.assert_array_equal(fp['rgb'][idx], fw['rgb'])
+    np.testing.assert_array_equal(fp['depth'][idx], fw['depth'])
+    np.testing.assert_array_equal(fp['target_rgb'][tix], fw['target_rgb'])
+    assert np.all(idx[:, 1:] == idx[:, :-1] + 1)                            # a window is K consecutive pool frames
+    for k in fw:
+      if k not in ('rgb', 'depth', 'target_rgb', 'target_depth'):
+        np.testing.assert_array_equal(fp[k], fw[k], err_msg=k)
+    for k in lw:
+      np.testing.assert_array_equal(lp[k], lw[k], err_msg=k)
+    total_pool += fp['rgb'].shape[0]; total_win += idx.size
+  assert total_pool < 0.6 * total_win                                    # (B + K - 1) / (B * K) per piece
+  with pytest.raises(ValueError, match='layout'):
+    ip.pickplace_input_fn_v4(d, 'default', 'train', 4, True, layout='ring', **kw)
+  with pytest.raises(ValueError, match='pool'):
+    ip.pickplace_input_fn_v4(d, 'default', 'train', 4, True, layout='pool', device='cpu', **kw)
+
+
 def test_pipeline_train_shuffles_episodes_only(dataset):
   d, eps = dataset
   meta = ip.get_meta_v4(d)
