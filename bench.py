@@ -256,6 +256,7 @@ def run_ours(args):
     raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda:%d' % local_rank)
+  numa_cores = parallel.pin_to_gpu_numa_node(local_rank, world) if (world > 1 and not os.environ.get('GEECO_NO_NUMA_PIN')) else None
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     dist.init_process_group('nccl', device_id=dev)
@@ -396,6 +397,7 @@ def run_ours(args):
         'final_loss': final_loss,
         'clocks': clocks, 'gpu_launches': launches, 'e2e': e2e, 'roofline': roofline, 'kernels': extra,
         'cpu_baseline': cpu_baseline, 'input_pipeline': input_pipeline, 'peaks': peaks,
+        'host': {'cpu_count': os.cpu_count(), 'rank0_numa_cores': len(numa_cores) if numa_cores else None},
         'policy_steps': (extras or {}).get('policy_steps'), 'rankpool_sweep': (extras or {}).get('rankpool_sweep'),
     }
     emit(line)

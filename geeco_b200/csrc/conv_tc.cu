@@ -1083,12 +1083,17 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* 
 }
 
 int g_num_sms = 0;
+// SMs the persistent / one-wave grids are sized for.  GEECO_NUM_SMS=<n> sizes them for fewer than the device has:
+// under data-parallel training NCCL's all-reduce CTAs share the SMs with the backward kernels, and a grid sized for
+// "exactly two CTAs on every SM" then runs its last CTAs as a second wave (bench.py sets it together with
+// NCCL_MAX_CTAS when world > 1).
 int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_num_sms <= 0) g_num_sms = 148;
+    if (const char* e = getenv("GEECO_NUM_SMS")) { const int v = atoi(e); if (v >= 8 && v <= g_num_sms) g_num_sms = v; }
   }
   return g_num_sms;
 }

@@ -214,9 +214,23 @@ template <> struct PixPack<__nv_bfloat16, 8> {
 // values e[0..4*C) of 4 consecutive pixels -> padded pixels (channels >= C are zero)
 template <typename OutT, int CP, int C>
 __device__ __forceinline__ void store_unit(OutT* dst, const float* e) {
+  if constexpr (sizeof(OutT) == 2 && CP == 4) {
+    // bf16, 4 channels: the four pixels of a unit are 32 contiguous bytes -> ONE 256-bit store (lanes hold consecutive
+    // units: 1 KB contiguous per warp instruction instead of four instructions of 8 bytes at a 32-byte stride)
+    uint32_t w[8];
 #pragma unroll
-  for (int p = 0; p < 4; ++p)
-    PixPack<OutT, CP>::store(dst + p * CP, e[p * C], e[p * C + 1], e[p * C + 2], C == 4 ? e[p * C + (C - 1)] : 0.f);
+    for (int p = 0; p < 4; ++p) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(e[p * C], e[p * C + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(e[p * C + 2], C == 4 ? e[p * C + (C - 1)] : 0.f);
+      w[2 * p] = *reinterpret_cast<uint32_t*>(&p0); w[2 * p + 1] = *reinterpret_cast<uint32_t*>(&p1);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      PixPack<OutT, CP>::store(dst + p * CP, e[p * C], e[p * C + 1], e[p * C + 2], C == 4 ? e[p * C + (C - 1)] : 0.f);
+  }
 }
 
 // One "float4" of frame data (4 consecutive values of the NHWC stream) in either input format.  uint8 records are
@@ -228,19 +242,25 @@ template <> struct FrameLoad<float> {
   static __device__ __forceinline__ float4 at(const float* base, long long i4, const float*) {
     return ldg_stream(reinterpret_cast<const float4*>(base) + i4);
   }
+  // second pass of the fused kernel: the C float4 of a 4-pixel unit share cache lines with each other and with the
+  // neighbouring lanes' units, so these loads allocate in L1 (ld.global.nc)
+  static __device__ __forceinline__ float4 at_l1(const float* base, long long i4, const float*) {
+    return __ldg(reinterpret_cast<const float4*>(base) + i4);
+  }
 };
 template <> struct FrameLoad<unsigned char> {
   static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4, const float* lut) {
     const unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(base) + i4);
     return make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
   }
+  static __device__ __forceinline__ float4 at_l1(const unsigned char* base, long long i4, const float* lut) { return at(base, i4, lut); }
 };
 
 template <typename InT, typename OutT, int CP, int C, int K>
 __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
-    AlphaTab al, int ring_start, const int* __restrict__ frame_index, const int* __restrict__ target_index) {
+    AlphaTab al, int ring_start, const int* __restrict__ frame_index, const int* __restrict__ target_index, int dbg) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_red[64];
@@ -272,28 +292,39 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   OutT* x_dyn = x0 + ((long long)N + n) * img_out;
   OutT* x_dif = x0 + (2ll * N + n) * img_out;
   float mn0 = FLT_MAX, mx0 = -FLT_MAX, mn1 = FLT_MAX, mx1 = -FLT_MAX;
-  for (long long u = lo + threadIdx.x; u < hi; u += RP_THREADS) {
-    float4 v[K][C], t[C];
+  // Pass 1 walks this CTA's slice as a FLAT array of float4 (d and the goal difference are element-wise): lane i of a
+  // warp reads float4 i of every stream, 512 contiguous bytes per load instruction.  (The first version mapped a thread
+  // to a 4-pixel unit = C float4: 48-byte lane stride, every 32-byte sector requested by two different instructions,
+  // 12 partial lines per instruction -- ncu r02: 48 % of the samples on the load scoreboard at 31 % DRAM.)  The
+  // channel-padded copy of the current frame needs whole pixels and is written in pass 2, which re-reads cur anyway.
+  {
+    const long long f_lo = lo * C, f_hi = hi * C;
+    constexpr int U = K >= 6 ? 1 : 2;                      // float4 positions per thread in flight
+    for (long long f0 = f_lo + threadIdx.x; f0 < f_hi; f0 += (long long)U * RP_THREADS) {
+      float4 v[U][K], t[U];
 #pragma unroll
-    for (int k = 0; k < K; ++k)
+      for (int q = 0; q < U; ++q) {
+        const long long f = f0 + (long long)q * RP_THREADS;
+        if (f < f_hi) {
 #pragma unroll
-      for (int j = 0; j < C; ++j) v[k][j] = FrameLoad<InT>::at(fk[k], u * C + j, s_lut);
+          for (int k = 0; k < K; ++k) v[q][k] = FrameLoad<InT>::at(fk[k], f, s_lut);
+          t[q] = FrameLoad<InT>::at(tbase, f, s_lut);
+        }
+      }
 #pragma unroll
-    for (int j = 0; j < C; ++j) t[j] = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
-    float cur[4 * C];
+      for (int q = 0; q < U; ++q) {
+        const long long f = f0 + (long long)q * RP_THREADS;
+        if (f < f_hi) {
+          float4 acc = f4_scale(al.a[0], v[q][0]);
 #pragma unroll
-    for (int j = 0; j < C; ++j) {
-      float4 acc = f4_scale(al.a[0], v[0][j]);
-#pragma unroll
-      for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[k][j]);
-      const float4 c4 = v[K - 1][j];
-      float4 dd = f4_axpy(f4_scale(-0.5f, c4), 0.5f, t[j]);
-      sd0[(u - lo) * C + j] = acc;
-      f4_minmax(acc, mn0, mx0);
-      f4_minmax(dd, mn1, mx1);
-      cur[j * 4] = c4.x; cur[j * 4 + 1] = c4.y; cur[j * 4 + 2] = c4.z; cur[j * 4 + 3] = c4.w;
+          for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[q][k]);
+          const float4 dd = f4_axpy(f4_scale(-0.5f, v[q][K - 1]), 0.5f, t[q]);
+          sd0[f - f_lo] = acc;
+          f4_minmax(acc, mn0, mx0);
+          f4_minmax(dd, mn1, mx1);
+        }
+      }
     }
-    store_unit<OutT, CP, C>(x_cur + u * 4 * CP, cur);
   }
   cluster_minmax(mn0, mx0, s_red, s_mm, 0, 2);
   cluster_minmax(mn1, mx1, s_red, s_mm, 1, 2);
@@ -302,20 +333,23 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   const float rng0 = __fadd_rn(__fsub_rn(mx0, mn0), 1e-6f), rng1 = __fadd_rn(__fsub_rn(mx1, mn1), 1e-6f);
   float4* o0 = dynbuff_f32 ? reinterpret_cast<float4*>(dynbuff_f32) + n * img4 : nullptr;
   float4* o1 = dyndiff_f32 ? reinterpret_cast<float4*>(dyndiff_f32) + n * img4 : nullptr;
+  if (dbg & 1) return;                                     // timing experiment: first pass only
   for (long long u = lo + threadIdx.x; u < hi; u += RP_THREADS) {
-    float e0[4 * C], e1[4 * C];
+    float e0[4 * C], e1[4 * C], ec[4 * C];
 #pragma unroll
     for (int j = 0; j < C; ++j) {
       const float4 a = f4_norm(sd0[(u - lo) * C + j], mn0, rng0);
       // same two operations on the same operands as in pass 1: bit-identical difference image
-      const float4 c4 = FrameLoad<InT>::at(fk[K - 1], u * C + j, s_lut);
-      const float4 tj = FrameLoad<InT>::at(tbase, u * C + j, s_lut);
+      const float4 c4 = (dbg & 2) ? FrameLoad<InT>::at(fk[K - 1], u * C + j, s_lut) : FrameLoad<InT>::at_l1(fk[K - 1], u * C + j, s_lut);
+      const float4 tj = (dbg & 2) ? FrameLoad<InT>::at(tbase, u * C + j, s_lut) : FrameLoad<InT>::at_l1(tbase, u * C + j, s_lut);
       const float4 b = f4_norm(f4_axpy(f4_scale(-0.5f, c4), 0.5f, tj), mn1, rng1);
       e0[j * 4] = a.x; e0[j * 4 + 1] = a.y; e0[j * 4 + 2] = a.z; e0[j * 4 + 3] = a.w;
       e1[j * 4] = b.x; e1[j * 4 + 1] = b.y; e1[j * 4 + 2] = b.z; e1[j * 4 + 3] = b.w;
+      ec[j * 4] = c4.x; ec[j * 4 + 1] = c4.y; ec[j * 4 + 2] = c4.z; ec[j * 4 + 3] = c4.w;
       if (o0) stg_stream(o0 + u * C + j, a);
       if (o1) stg_stream(o1 + u * C + j, b);
     }
+    store_unit<OutT, CP, C>(x_cur + u * 4 * CP, ec);
     store_unit<OutT, CP, C>(x_dyn + u * 4 * CP, e0);
     store_unit<OutT, CP, C>(x_dif + u * 4 * CP, e1);
   }
@@ -414,6 +448,10 @@ static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, flo
   long long units = (long long)H * W / 4;
   if (cluster_hint <= 0) { if (const char* e = getenv("GEECO_PRE_CLUSTER")) cluster_hint = atoi(e); }
   int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
+  // float32 frames: one CTA per SM with a 2x larger slice beats two co-resident CTAs (measured r02, batch 64: 91 vs
+  // 111 us: half as many cluster barriers and second-pass ramps per byte); uint8 frames are LUT-bound and prefer
+  // the occupancy (75 vs 91 us)
+  if (cluster_hint <= 0 && sizeof(InT) == 4 && cl > 1 && (size_t)((units + cl / 2 - 1) / (cl / 2)) * C * 16 <= RP_SMEM_CAP) cl /= 2;
   long long per_units = (units + cl - 1) / cl;
   size_t smem = (size_t)per_units * C * 16;
   if (smem > RP_SMEM_CAP) {
@@ -422,8 +460,10 @@ static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, flo
   }
   OutT* x = reinterpret_cast<OutT*>(x0);
   AlphaTab al = al_in;
+  static const int dbg_env = getenv("GEECO_PRE_DBG") ? atoi(getenv("GEECO_PRE_DBG")) : 0;
+  int dbg = dbg_env;
   void* args[] = {(void*)&rgb, (void*)&tgt, (void*)&x, (void*)&db, (void*)&dd, (void*)&N, (void*)&units,
-                  (void*)&per_units, (void*)&al, (void*)&ring_start, (void*)&frame_index, (void*)&target_index};
+                  (void*)&per_units, (void*)&al, (void*)&ring_start, (void*)&frame_index, (void*)&target_index, (void*)&dbg};
   RP_SWITCH_K_LO(K, return launch_clustered(preprocess_geecof_kernel<InT, OutT, CP, C, KK>, dim3(cl, N), cl, smem, st, args));
   return GEECO_OK;
 }

@@ -28,15 +28,18 @@ struct Bf16Plan {
   Bf16Layer L[8];
   float* partial;
   long long partial_cap;
-  PackJob* jobs_dev;          // table of weight-repack jobs (uploaded at the first repack after bind)
-  std::vector<PackJob> jobs;
-  long long jobs_total;
+  // weight-repack jobs in two tables (uploaded at the first repack after bind).  EARLY = forward operands of
+  // conv1-conv3, a few hundred KB that the first kernels of the step need; LATE = everything else (forward operands
+  // of conv4-conv8 and all data-gradient operands, 95 % of the elements), needed ~0.6 ms into the step
+  PackJob* jobs_dev[2];
+  std::vector<PackJob> jobs[2];
+  long long jobs_total[2];
   bool jobs_uploaded;
   // the weight repack of a step does not depend on the batch: it runs on a side stream next to the rank-pooling
   // kernel (whose 16-CTA clusters leave a quarter of the SMs idle) and is joined before the first convolution
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool forked = false;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_late = nullptr;
+  bool forked = false, late_pending = false;
 };
 
 // packed-K extent of a data-gradient class when the layer's output has `cout` channels (the planned geometry was
@@ -115,13 +118,15 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   }
   bp->partial_cap = cap;
   bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
-  bp->jobs_dev = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
+  bp->jobs_dev[0] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
+  bp->jobs_dev[1] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_uploaded = false;
   if (!ws_base) return GEECO_OK;
   if (!bp->side) {
     CUDA_TRY(cudaStreamCreateWithFlags(&bp->side, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join_late, cudaEventDisableTiming));
   }
   // tensor maps (need the real addresses)
   for (int l = 0; l < 8; ++l) {
@@ -161,6 +166,7 @@ void free_bf16(geeco_ctx* c) {
     if (bp->side) { cudaStreamSynchronize(bp->side); cudaStreamDestroy(bp->side); }
     if (bp->ev_fork) cudaEventDestroy(bp->ev_fork);
     if (bp->ev_join) cudaEventDestroy(bp->ev_join);
+    if (bp->ev_join_late) cudaEventDestroy(bp->ev_join_late);
     delete bp;
     c->bf16_ws = nullptr;
   }
@@ -168,7 +174,7 @@ void free_bf16(geeco_ctx* c) {
 
 static const int kAllTaps[9] = {0, 1, 2, 3, 4, 5, 6, 7, 8};
 
-static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, int groups, long long wstride, int Cin,
+static void add_job(Bf16Plan* bp, int table, const float* W, __nv_bfloat16* out, int mode, int groups, long long wstride, int Cin,
                     int Cout, int Cs, int ntaps, const int* taps, int rows, int Kpad, int Kt, const float* bias = nullptr,
                     long long bstride = 0, int bias_col = -1) {
   PackJob j;
@@ -177,52 +183,59 @@ static void add_job(Bf16Plan* bp, const float* W, __nv_bfloat16* out, int mode, 
   j.Cs = Cs; j.ntaps = ntaps; j.rows = rows; j.Kpad = Kpad; j.Kt = Kt;
   j.bias = bias; j.b_group_stride = bstride; j.bias_col = bias ? bias_col : -1;
   for (int i = 0; i < ntaps && i < 9; ++i) j.taps[i] = taps[i];
-  j.start = bp->jobs_total;
+  j.start = bp->jobs_total[table];
   j.total = (long long)groups * rows * Kpad;
-  bp->jobs_total = (j.start + j.total + PACK_CHUNK - 1) / PACK_CHUNK * PACK_CHUNK;
-  bp->jobs.push_back(j);
+  bp->jobs_total[table] = (j.start + j.total + PACK_CHUNK - 1) / PACK_CHUNK * PACK_CHUNK;
+  bp->jobs[table].push_back(j);
 }
 
 // fp32 master weights -> packed bf16 operands of every conv layer (forward + the data-gradient classes): one launch
-static int repack_weights(geeco_ctx* c, cudaStream_t st) {
+// per job table.  which: 0 = EARLY table, 1 = LATE table, 2 = both
+static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 2) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   const int G = c->G;
   if (!bp->jobs_uploaded) {
-    bp->jobs.clear();
-    bp->jobs_total = 0;
+    for (int t = 0; t < 2; ++t) { bp->jobs[t].clear(); bp->jobs_total[t] = 0; }
     for (int l = 0; l < 8; ++l) {
       LayerPlan& L = c->layers[l];
       Bf16Layer& B = bp->L[l];
       const long long wstride = w_group_stride(c, L);
       const int ne = L.grouped ? 1 : G;
+      const int fwd_table = l < 3 ? 0 : 1;
       for (int e = 0; e < ne; ++e) {
         const int groups = L.grouped ? G : 1;
         const float* W = c->theta + c->params[L.p_w[e]].offset;
         if (B.pair) {
           for (int par = 0; par < 2; ++par)
-            add_job(bp, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
+            add_job(bp, fwd_table, W, B.w_pair[par], 2 + par, groups, wstride, L.Cin_real, L.Cout[e], 8, 6, kAllTaps, L.Cout[e], 64, 0);
         } else {
           const long long bstride = b_group_stride(c, L);
-          add_job(bp, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
+          add_job(bp, fwd_table, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
                   B.fwd.Kpad, B.fwd.Kt, B.fwd.bias_in_k ? c->theta + c->params[L.p_b[e]].offset : nullptr, bstride, B.fwd.Ktot);
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
-          add_job(bp, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
+          add_job(bp, 1, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
                   L.Cin_real, Kp, dgrad_kt(B.dg[ci], L.Cout[e]));
         }
       }
     }
-    if (bp->jobs.size() > 64) { geeco_set_error("repack: %zu jobs > 64", bp->jobs.size()); return GEECO_ERR_INVALID; }
-    for (const PackJob& pj : bp->jobs)
-      if (pj.total >= (1ll << 31)) { geeco_set_error("repack: a job of %lld elements needs 64-bit indexing", pj.total); return GEECO_ERR_INVALID; }
-    CUDA_TRY(cudaMemcpyAsync(bp->jobs_dev, bp->jobs.data(), bp->jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    for (int t = 0; t < 2; ++t) {
+      if (bp->jobs[t].size() > 64) { geeco_set_error("repack: %zu jobs > 64", bp->jobs[t].size()); return GEECO_ERR_INVALID; }
+      for (const PackJob& pj : bp->jobs[t])
+        if (pj.total >= (1ll << 31)) { geeco_set_error("repack: a job of %lld elements needs 64-bit indexing", pj.total); return GEECO_ERR_INVALID; }
+      if (!bp->jobs[t].empty())
+        CUDA_TRY(cudaMemcpyAsync(bp->jobs_dev[t], bp->jobs[t].data(), bp->jobs[t].size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     bp->jobs_uploaded = true;
   }
-  int rc = launch_pack_weights_batched(bp->jobs_dev, (int)bp->jobs.size(), bp->jobs_total, st);
-  if (rc) return rc;
-  c->weights_dirty = false;
+  for (int t = 0; t < 2; ++t) {
+    if ((which != 2 && which != t) || bp->jobs[t].empty()) continue;
+    int rc = launch_pack_weights_batched(bp->jobs_dev[t], (int)bp->jobs[t].size(), bp->jobs_total[t], st);
+    if (rc) return rc;
+  }
+  if (which != 0) c->weights_dirty = false;
   return GEECO_OK;
 }
 
@@ -235,12 +248,18 @@ int repack_fork_bf16(geeco_ctx* c, cudaStream_t st) {
   if (!bp || !c->weights_dirty || !bp->side || !bp->jobs_uploaded || off) return GEECO_OK;   // first step: inline repack
   CUDA_TRY(cudaEventRecord(bp->ev_fork, st));
   CUDA_TRY(cudaStreamWaitEvent(bp->side, bp->ev_fork, 0));
-  int rc = repack_weights(c, bp->side);
+  int rc = repack_weights(c, bp->side, 0);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(bp->ev_join, bp->side));
+  rc = repack_weights(c, bp->side, 1);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(bp->ev_join_late, bp->side));
   bp->forked = true;
+  bp->late_pending = true;
   return GEECO_OK;
 }
+// `st` waits for the EARLY table (conv1-conv3 forward operands); the LATE table is joined inside encoders_fwd_bf16
+// right before conv4, ~0.6 ms of forward work later
 int repack_join_bf16(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp || !bp->forked) return GEECO_OK;
@@ -261,6 +280,10 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
   for (int l = 0; l < 8; ++l) {
     LayerPlan& L = c->layers[l];
     Bf16Layer& B = bp->L[l];
+    if (l == 3 && bp->late_pending) {
+      CUDA_TRY(cudaStreamWaitEvent(st, bp->ev_join_late, 0));
+      bp->late_pending = false;
+    }
     if (B.pair) {
       TcGeom pg[2] = {B.pg[0], B.pg[1]};
       pg[0].bias_group_stride = pg[1].bias_group_stride = b_group_stride(c, L);

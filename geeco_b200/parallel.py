@@ -67,3 +67,48 @@ def broadcast_parameters(engine, src=0):
     if t is not None:
       dist.broadcast(t, src=src)
   engine.params_changed()
+
+
+def pin_to_gpu_numa_node(local_rank, local_world=1):
+  """Binds this process to the CPU cores next to its GPU (the GPU's NUMA node, from sysfs), split evenly between the
+  ranks that share the node, and returns the chosen core list (None when the topology cannot be read -- nothing is
+  changed then).  One process per GPU uploads ~25 GB/s of pinned batches at full rate: with all ranks on one NUMA
+  node the uploads of 8 GPUs share one memory controller and the far GPUs cross the socket link (round-1 end-to-end
+  scaling: 0.74 at 8 GPUs).  Call before the first pinned allocation so that first-touch places it on the right node."""
+  import os
+  try:
+    p = torch.cuda.get_device_properties(local_rank)
+    dev = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    base = '/sys/bus/pci/devices/' + dev
+    with open(base + '/numa_node') as fp:
+      node = int(fp.read().strip())
+    with open(base + '/local_cpulist') as fp:
+      spec = fp.read().strip()
+    cpus = set()
+    for part in spec.split(','):
+      if '-' in part:
+        a, b = part.split('-')
+        cpus.update(range(int(a), int(b) + 1))
+      elif part:
+        cpus.add(int(part))
+    allowed = sorted(cpus & os.sched_getaffinity(0))
+    if not allowed:
+      return None
+    # ranks whose GPUs sit on the same node share its cores
+    peers = []
+    for r in range(local_world):
+      q = torch.cuda.get_device_properties(r)
+      try:
+        with open('/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node' % (q.pci_domain_id, q.pci_bus_id, q.pci_device_id)) as fp:
+          if int(fp.read().strip()) == node:
+            peers.append(r)
+      except OSError:
+        pass
+    if local_rank in peers and len(peers) > 1 and len(allowed) >= len(peers):
+      per = len(allowed) // len(peers)
+      i = peers.index(local_rank)
+      allowed = allowed[i * per:(i + 1) * per]
+    os.sched_setaffinity(0, allowed)
+    return allowed
+  except Exception:      # noqa: BLE001  (sysfs layout, permissions, cpusets: never fatal)
+    return None

@@ -189,6 +189,7 @@ def main(args, argv=None):
     raise RuntimeError("geeco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
   if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    parallel.pin_to_gpu_numa_node(int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
     dist.init_process_group('nccl')
   rank, world = parallel.world_info()
   os.makedirs(args.model_dir, exist_ok=True)
