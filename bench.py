@@ -252,6 +252,7 @@ def run_ours(args):
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  parallel.tune_for_data_parallel(world)
   if not torch.cuda.is_available():
     raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback for the product path")
   torch.cuda.set_device(local_rank)

@@ -505,6 +505,18 @@ extern "C" int geeco_dynimg(const float* in, float* out, int32_t N, int32_t K, i
   if (!alpha) { geeco_alpha_table(K, tab); alpha = tab; }
   const long long HWC = (long long)H * W * C;
   cudaStream_t st = (cudaStream_t)stream;
+  if (cluster == 0) {
+    // measured choice (tools/sweep_dynimg.py on B200, profiles/r02_rankpool_sweep.txt): the one-read cluster kernel
+    // wins while a sample's slice and the K-deep load batch fit comfortably; large samples with deep windows do
+    // better as two streaming passes (d written un-normalised, normalised in place), and K = 3 / 5..7 at 256 px
+    // prefer 4 CTAs with the whole SM's shared memory over 8 with half
+    const long long bytes = HWC * 4;
+    if (bytes >= (2ll << 20)) { if (K >= 8 && scratch) cluster = -1; }
+    else if (bytes >= (512ll << 10)) {
+      if (K == 8 && scratch) cluster = -1;
+      else if (K == 3 || (K >= 5 && K <= 7)) cluster = 4;
+    }
+  }
   if (cluster >= 0) {
     int rc = launch_dynimg(in, out, N, K, HWC, alpha, cluster, st);
     if (rc != GEECO_ERR_WORKSPACE) return rc;
@@ -667,44 +679,60 @@ static int tail_forward(geeco_ctx* c, const geeco_batch* b, const geeco_outputs*
   // lstm_decoder's loop over feat_list (graph.py:223-225): T = 1 for the dynimg graph, K for the sequence graphs.
   // T > 1: the x part of all T steps is ONE split GEMM over T*N rows, the recurrence ONE persistent cluster launch
   // with W_h resident in shared memory (lstm_persistent.cu)
-  if (use_persistent_lstm(c)) {
-    rc = launch_lstm_gates(c->states, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, T * N, c->xdim,
-                           4 * Hl, st);
-    if (rc) return rc;
-    rc = launch_lstm_seq_fwd(T, N, Hl, c->xdim, P(c, c->p_lstm_w), carry ? c->c_carry : nullptr, carry ? c->m_carry : nullptr,
-                             rmask, c->gates, c->c_seq, c->m_seq, c->states, c->state_out, st);
-    if (rc) return rc;
-  } else
-  for (int t = 0; t < T; ++t) {
-    const bool has_prev = t > 0 || carry;
-    float* gates_t = c->gates + (long long)t * N * 4 * Hl;
-    // without a previous state m_prev == 0 and the h-rows of the kernel contribute nothing: K = xdim
-    rc = launch_lstm_gates(c->states + (long long)t * N * ld, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), gates_t,
-                           c->gates_partial, N, has_prev ? ld : c->xdim, 4 * Hl, st);
-    if (rc) return rc;
-    const float* c_prev = t > 0 ? c->c_seq + (long long)(t - 1) * N * Hl : (carry ? c->c_carry : nullptr);
-    rc = launch_lstm_cell(N, Hl, gates_t, c_prev, t == 0 ? rmask : nullptr, c->c_seq + (long long)t * N * Hl,
-                          c->m_seq + (long long)t * N * Hl, t == T - 1 ? c->state_out : nullptr,
-                          t + 1 < T ? c->states + (long long)(t + 1) * N * ld + c->xdim : nullptr, ld, st);
-    if (rc) return rc;
-  }
   if (with_loss && cfg.l2_regularizer > 0.f) {
     rc = launch_l2_term(c->theta, c->arena_floats, cfg.l2_regularizer, c->sc, st);
     if (rc) return rc;
   }
   TailHeads th = tail_heads(c, with_loss ? b : nullptr);
-  rc = launch_tail_fwd(d, th, P(c, c->p_fc1_w), P(c, c->p_fc1_b), c->m_seq + (long long)(T - 1) * N * Hl, c->fc1, c->heads,
-                       c->loss_parts, c->dheads, with_loss ? 1 : 0, st);
-  if (rc) return rc;
-  if (with_loss) {
-    rc = launch_loss_reduce(d, th, c->loss_parts, cfg.l2_regularizer > 0.f ? c->sc + 2 : nullptr, c->losses, st);
+  float* o_heads = out ? out->heads : nullptr;
+  float* o_fc1 = out ? out->fc1 : nullptr;
+  float* o_state = out ? out->lstm_state : nullptr;
+  if (T == 1) {
+    // one step: split-K gate GEMM (partials only), then ONE launch for reduce + cell + fc1 + heads + per-sample losses
+    int slices = 0;
+    rc = launch_lstm_gates(c->states, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, N,
+                           carry ? ld : c->xdim, 4 * Hl, st, &slices);
     if (rc) return rc;
+    rc = launch_tail_fwd_fused(d, th, P(c, c->p_fc1_w), P(c, c->p_fc1_b), c->gates_partial, slices, P(c, c->p_lstm_b), c->gates,
+                               carry ? c->c_carry : nullptr, rmask, c->c_seq, c->m_seq, c->state_out, c->fc1, c->heads,
+                               c->loss_parts, c->dheads, with_loss ? 1 : 0, o_heads, o_fc1, o_state, st);
+    if (rc) return rc;
+  } else {
+    if (use_persistent_lstm(c)) {
+      rc = launch_lstm_gates(c->states, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), c->gates, c->gates_partial, T * N, c->xdim,
+                             4 * Hl, st);
+      if (rc) return rc;
+      rc = launch_lstm_seq_fwd(T, N, Hl, c->xdim, P(c, c->p_lstm_w), carry ? c->c_carry : nullptr, carry ? c->m_carry : nullptr,
+                               rmask, c->gates, c->c_seq, c->m_seq, c->states, c->state_out, st);
+      if (rc) return rc;
+    } else
+    for (int t = 0; t < T; ++t) {
+      const bool has_prev = t > 0 || carry;
+      float* gates_t = c->gates + (long long)t * N * 4 * Hl;
+      // without a previous state m_prev == 0 and the h-rows of the kernel contribute nothing: K = xdim
+      rc = launch_lstm_gates(c->states + (long long)t * N * ld, ld, P(c, c->p_lstm_w), P(c, c->p_lstm_b), gates_t,
+                             c->gates_partial, N, has_prev ? ld : c->xdim, 4 * Hl, st);
+      if (rc) return rc;
+      const float* c_prev = t > 0 ? c->c_seq + (long long)(t - 1) * N * Hl : (carry ? c->c_carry : nullptr);
+      rc = launch_lstm_cell(N, Hl, gates_t, c_prev, t == 0 ? rmask : nullptr, c->c_seq + (long long)t * N * Hl,
+                            c->m_seq + (long long)t * N * Hl, t == T - 1 ? c->state_out : nullptr,
+                            t + 1 < T ? c->states + (long long)(t + 1) * N * ld + c->xdim : nullptr, ld, st);
+      if (rc) return rc;
+    }
+    rc = launch_tail_fwd(d, th, P(c, c->p_fc1_w), P(c, c->p_fc1_b), c->m_seq + (long long)(T - 1) * N * Hl, c->fc1, c->heads,
+                         c->loss_parts, c->dheads, with_loss ? 1 : 0, o_heads, o_fc1, st);
+    if (rc) return rc;
+    if (o_state) {
+      const float* src[4] = {c->state_out, nullptr, nullptr, nullptr};
+      float* dst[4] = {o_state, nullptr, nullptr, nullptr};
+      const long long n[4] = {(long long)N * 2 * Hl, 0, 0, 0};
+      rc = launch_copy_outputs(src, dst, n, st);
+      if (rc) return rc;
+    }
   }
-  if (out) {
-    const float* src[4] = {c->heads, c->fc1, c->state_out, c->losses};
-    float* dst[4] = {out->heads, out->fc1, out->lstm_state, with_loss ? out->losses : nullptr};
-    const long long n[4] = {(long long)N * c->NH, (long long)N * cfg.dim_h_fc, (long long)N * 2 * Hl, GEECO_NUM_LOSS_SLOTS};
-    rc = launch_copy_outputs(src, dst, n, st);
+  if (with_loss) {
+    rc = launch_loss_reduce(d, th, c->loss_parts, cfg.l2_regularizer > 0.f ? c->sc + 2 : nullptr, c->losses,
+                            out ? out->losses : nullptr, st);
     if (rc) return rc;
   }
   return GEECO_OK;
@@ -816,12 +844,26 @@ static int tail_backward(geeco_ctx* c, cudaStream_t st) {
   TailHeads th = tail_heads(c, nullptr);
   const float* m_last = c->m_seq + (long long)(T - 1) * N * Hl;
   int rc;
+  LayerPlan& L8 = c->layers[7];
+  StateMap sm = state_map(c, bf16 ? c->y8_f32 : (const float*)L8.y, bf16 ? c->g8_f32 : (float*)L8.g);
+  bool scattered = false;
   if (T == 1) {
     rc = launch_tail_bwd(d, th, P(c, c->p_fc1_w), GR(c, c->p_fc1_w), GR(c, c->p_fc1_b), m_last, c->fc1, c->dheads, c->gates,
                          carry ? c->c_carry : nullptr, c->reset_mask, c->dfc1, c->dgates, nullptr, st);
     if (rc) return rc;
-    rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstates, N, c->xdim, 4 * Hl, ld, st);
-    if (rc) return rc;
+    if (c->variant == VAR_GEECOF) {
+      // d(state) is never materialised: the GEMM's epilogue writes the masked conv8 gradients directly (bf16 mode: as
+      // bf16, which also saves the fp32 -> bf16 conversion launch)
+      __nv_bfloat16* gb[3] = {nullptr, nullptr, nullptr};
+      if (bf16) for (int e = 0; e < c->G; ++e) gb[e] = (__nv_bfloat16*)L8.g + L8.act_off[e];
+      rc = launch_lstm_dstate_scatter(c->dgates, P(c, c->p_lstm_w), sm, bf16 ? gb : nullptr, 4 * Hl, st);
+      if (rc) return rc;
+      scattered = true;
+      c->g8_bf16_ready = bf16;
+    } else {
+      rc = launch_lstm_dstate(c->dgates, P(c, c->p_lstm_w), c->dstates, N, c->xdim, 4 * Hl, ld, st);
+      if (rc) return rc;
+    }
   } else {
     rc = launch_tail_bwd(d, th, P(c, c->p_fc1_w), GR(c, c->p_fc1_w), GR(c, c->p_fc1_b), m_last, c->fc1, c->dheads, nullptr,
                          nullptr, nullptr, c->dfc1, nullptr, c->dm_last, st);
@@ -849,11 +891,10 @@ static int tail_backward(geeco_ctx* c, cudaStream_t st) {
       if (rc) return rc;
     }
   }
-  GatherGeom gw = dense_geom(T * N, ld, 4 * Hl, 4 * Hl, 0);
-  rc = launch_gemm_tn_f32(gw, c->states, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), c->partial, c->partial_cap, 1, 0, 0, st);
+  rc = launch_lstm_wgrad(c->states, c->dgates, GR(c, c->p_lstm_w), GR(c, c->p_lstm_b), T * N, ld, 4 * Hl, st);
   if (rc) return rc;
-  LayerPlan& L8 = c->layers[7];
-  StateMap sm = state_map(c, bf16 ? c->y8_f32 : (const float*)L8.y, bf16 ? c->g8_f32 : (float*)L8.g);
+  if (scattered) return GEECO_OK;
+  c->g8_bf16_ready = false;
   return launch_scatter_dstates(sm, c->dstates, st);
 }
 

@@ -317,7 +317,7 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
   const int N = c->M, G = c->G;
-  if (lhi == 7) {
+  if (lhi == 7 && !c->g8_bf16_ready) {
     int rc = launch_f32_to_bf16(c->g8_f32, (__nv_bfloat16*)c->layers[7].g, c->layers[7].act_elems, st);
     if (rc) return rc;
   }

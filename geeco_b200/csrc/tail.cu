@@ -166,19 +166,61 @@ __device__ __forceinline__ int head_of(const TailHeads& th, int t) {
   return h;
 }
 
-__global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th, const float* __restrict__ w_fc1,
+// One-step graphs fuse what used to be three launches in front of it (split-K reduce of the gate GEMM, LSTM cell):
+// `cell.partial != NULL` -> this sample's gates = bias + sum of the split-K partials (same order as gates_reduce_kernel),
+// then the cell, then fc1 / heads / losses from the m it just produced.
+struct CellFuse {
+  const float* partial; int slices;            // [slices][N][4Hl] split-K partials of the gate GEMM (NULL: m is given)
+  const float* bias; float* gates;             // LSTM bias; full pre-activations out (kept for the backward)
+  const float* c_prev; const unsigned char* reset_mask;
+  float *c_out, *m_out, *state_out, *state_out2;   // state_out2: the caller's copy (geeco_outputs.lstm_state), may be NULL
+};
+struct TailOut { float *heads2, *fc1_2; };       // the caller's copies (geeco_outputs.heads / .fc1), may be NULL
+
+__global__ void __launch_bounds__(512) tail_fwd_kernel(TailDims d, TailHeads th, const float* __restrict__ w_fc1,
                                                        const float* __restrict__ b_fc1, const float* __restrict__ m,
                                                        float* __restrict__ fc1, float* __restrict__ heads,
                                                        float* __restrict__ loss_parts, float* __restrict__ dheads,
-                                                       int with_loss) {
+                                                       int with_loss, CellFuse cell, TailOut outs) {
   pdl_enter();
   extern __shared__ float sm[];
   float* m_s = sm;                 // Hl
   float* fc_s = sm + d.Hl;         // Fc
-  float* out_s = fc_s + d.Fc;      // NH
+  float* out_s = fc_s + d.Fc;      // NH (<= 32)
+  float* g_s = out_s + 32;         // 4*Hl (fused cell only)
   const int n = blockIdx.x;
   const int NH = th.NH;
-  for (int i = threadIdx.x; i < d.Hl; i += blockDim.x) m_s[i] = m[(long long)n * d.Hl + i];
+  if (cell.partial) {
+    const int G4 = 4 * d.Hl;
+    const long long total = (long long)d.N * G4;
+    for (int j = threadIdx.x; j < G4; j += blockDim.x) {
+      float s = cell.bias[j];
+      const float* p = cell.partial + (long long)n * G4 + j;
+      int k = 0;
+      for (; k + 8 <= cell.slices; k += 8) {          // eight loads in flight, added in slice order
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = __ldg(p + (long long)(k + q) * total);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += v[q];
+      }
+      for (; k < cell.slices; ++k) s += __ldg(p + (long long)k * total);
+      g_s[j] = s;
+      cell.gates[(long long)n * G4 + j] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d.Hl; i += blockDim.x) {
+      const long long idx = (long long)n * d.Hl + i;
+      const float cp = (cell.c_prev && !(cell.reset_mask && cell.reset_mask[n])) ? cell.c_prev[idx] : 0.f;
+      const float c = sigmoidf_(g_s[2 * d.Hl + i] + 1.0f) * cp + sigmoidf_(g_s[i]) * tanhf(g_s[d.Hl + i]);
+      const float mv = sigmoidf_(g_s[3 * d.Hl + i]) * tanhf(c);
+      cell.c_out[idx] = c; cell.m_out[idx] = mv; m_s[i] = mv;
+      cell.state_out[(long long)n * 2 * d.Hl + i] = c; cell.state_out[(long long)n * 2 * d.Hl + d.Hl + i] = mv;
+      if (cell.state_out2) { cell.state_out2[(long long)n * 2 * d.Hl + i] = c; cell.state_out2[(long long)n * 2 * d.Hl + d.Hl + i] = mv; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < d.Hl; i += blockDim.x) m_s[i] = m[(long long)n * d.Hl + i];
+  }
   __syncthreads();
   for (int j = threadIdx.x; j < d.Fc; j += blockDim.x) {
     float s = b_fc1[j];
@@ -187,6 +229,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th,
     s = fmaxf(s, 0.f);
     fc_s[j] = s;
     fc1[(long long)n * d.Fc + j] = s;
+    if (outs.fc1_2) outs.fc1_2[(long long)n * d.Fc + j] = s;
   }
   __syncthreads();
   // heads: one warp per output column (lanes stride over fc1, fixed-order lane reduction), 4 warps take turns
@@ -199,7 +242,7 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     s += hs.b[col];
-    if (lane == 0) { out_s[t] = s; heads[(long long)n * NH + t] = s; }
+    if (lane == 0) { out_s[t] = s; heads[(long long)n * NH + t] = s; if (outs.heads2) outs.heads2[(long long)n * NH + t] = s; }
   }
   __syncthreads();
   if (with_loss && threadIdx.x == 0) {
@@ -242,7 +285,8 @@ __global__ void __launch_bounds__(128) tail_fwd_kernel(TailDims d, TailHeads th,
 
 // losses[12]: slot of every head (HeadSpec::slot), [4] loss_reg, [5] loss, [6] sum_correct, [7] N
 __global__ void loss_reduce_kernel(int N, TailHeads th, const float* __restrict__ loss_parts,
-                                   const float* __restrict__ reg_term, float* __restrict__ losses) {
+                                   const float* __restrict__ reg_term, float* __restrict__ losses,
+                                   float* __restrict__ losses2) {
   pdl_enter();
   __shared__ float s[6][256];
   float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -271,6 +315,7 @@ __global__ void loss_reduce_kernel(int N, TailHeads th, const float* __restrict_
     losses[4] = lr;
     losses[5] = cmd + (any_aux ? wa * aux : 0.f) + lr;
     losses[6] = s[5][0]; losses[7] = (float)N;
+    if (losses2) for (int k = 0; k < 12; ++k) losses2[k] = losses[k];
   }
 }
 
@@ -454,16 +499,35 @@ int launch_lstm_cell_bwd(int N, int Hl, const float* gates, const float* c_prev,
   return GEECO_OK;
 }
 int launch_tail_fwd(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1, const float* m,
-                    float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, cudaStream_t st) {
+                    float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, float* heads_out,
+                    float* fc1_out, cudaStream_t st) {
   const size_t smem = (size_t)(d.Hl + d.Fc + 32) * sizeof(float);
-  GEECO_LAUNCH((tail_fwd_kernel), d.N, 128, smem, st, d, th, w_fc1, b_fc1, m, fc1, heads, loss_parts, dheads, with_loss);
+  CellFuse cell = {};
+  TailOut outs = {heads_out, fc1_out};
+  GEECO_LAUNCH((tail_fwd_kernel), d.N, 128, smem, st, d, th, w_fc1, b_fc1, m, fc1, heads, loss_parts, dheads, with_loss, cell, outs);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+// one-step graphs: split-K partials of the gate GEMM -> gates -> cell -> fc1 -> heads -> losses in ONE launch
+int launch_tail_fwd_fused(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1,
+                          const float* partial, int slices, const float* lstm_bias, float* gates, const float* c_prev,
+                          const unsigned char* reset_mask, float* c_out, float* m_out, float* state_out, float* fc1,
+                          float* heads, float* loss_parts, float* dheads, int with_loss, float* heads_out, float* fc1_out,
+                          float* state_out2, cudaStream_t st) {
+  const size_t smem = (size_t)(d.Hl + d.Fc + 32 + 4 * d.Hl) * sizeof(float);
+  CellFuse cell = {partial, slices, lstm_bias, gates, c_prev, reset_mask, c_out, m_out, state_out, state_out2};
+  TailOut outs = {heads_out, fc1_out};
+  int threads = 4 * d.Hl; if (threads > 512) threads = 512; if (threads < 128) threads = 128;
+  GEECO_LAUNCH((tail_fwd_kernel), d.N, threads, smem, st, d, th, w_fc1, b_fc1, (const float*)nullptr, fc1, heads, loss_parts, dheads,
+               with_loss, cell, outs);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
 int launch_loss_reduce(const TailDims& d, const TailHeads& th, const float* loss_parts, const float* reg_term,
-                       float* losses, cudaStream_t st) {
-  GEECO_LAUNCH((loss_reduce_kernel), 1, 256, 0, st, d.N, th, loss_parts, reg_term, losses);
+                       float* losses, float* losses_out, cudaStream_t st) {
+  GEECO_LAUNCH((loss_reduce_kernel), 1, 256, 0, st, d.N, th, loss_parts, reg_term, losses, losses_out);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -509,11 +573,11 @@ __global__ void __launch_bounds__(256) gates_splitk_kernel(const float* __restri
                                                            float* __restrict__ partial, int N, int K, int ldx,
                                                            int Ncols) {
   pdl_enter();
-  __shared__ float xs[32][GK_SLICE + 1];
+  __shared__ float xs[32][GK_SLICE + 8 + 1];      // (+8: the last chunk of a short slice reads zero-weighted columns)
   const int k0 = blockIdx.x * GK_SLICE, n0 = blockIdx.y * 32;
-  for (int e = threadIdx.x; e < 32 * GK_SLICE; e += 256) {
-    const int n = e / GK_SLICE, k = e - n * GK_SLICE;
-    xs[n][k] = (n0 + n < N && k0 + k < K) ? x[(long long)(n0 + n) * ldx + k0 + k] : 0.f;
+  for (int e = threadIdx.x; e < 32 * (GK_SLICE + 8); e += 256) {
+    const int n = e / (GK_SLICE + 8), k = e - n * (GK_SLICE + 8);
+    xs[n][k] = (k < GK_SLICE && n0 + n < N && k0 + k < K) ? x[(long long)(n0 + n) * ldx + k0 + k] : 0.f;
   }
   __syncthreads();
   float acc[32][CPT];
@@ -522,18 +586,25 @@ __global__ void __launch_bounds__(256) gates_splitk_kernel(const float* __restri
 #pragma unroll
     for (int c = 0; c < CPT; ++c) acc[n][c] = 0.f;
   const int kend = (K - k0) < GK_SLICE ? (K - k0) : GK_SLICE;
-  for (int kk = 0; kk < kend; ++kk) {
-    float w[CPT];
+  // in chunks of 8 kernel rows: all loads of a chunk are issued before its FMAs (the first version loaded one row per
+  // iteration and waited for it: 32 dependent L2 round trips per CTA)
+  for (int kc = 0; kc < kend; kc += 8) {
+    float w[8][CPT];
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int col = threadIdx.x + c * 256;
-      w[c] = col < Ncols ? __ldg(W + (long long)(k0 + kk) * Ncols + col) : 0.f;
-    }
+    for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
-    for (int n = 0; n < 32; ++n) {
-      const float a = xs[n][kk];
+      for (int c = 0; c < CPT; ++c) {
+        const int col = threadIdx.x + c * 256;
+        w[kk][c] = (kc + kk < kend && col < Ncols) ? __ldg(W + (long long)(k0 + kc + kk) * Ncols + col) : 0.f;
+      }
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) acc[n][c] = fmaf(a, w[c], acc[n][c]);
+    for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+      for (int n = 0; n < 32; ++n) {
+        const float a = xs[n][kc + kk];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[n][c] = fmaf(a, w[kk][c], acc[n][c]);
+      }
     }
   }
 #pragma unroll
@@ -584,43 +655,132 @@ int launch_copy_outputs(const float* const* src, float* const* dst, const long l
 // reduction runs over 64-column chunks staged in shared memory (kernel rows padded against bank conflicts, the
 // dgates values are warp-wide broadcasts).  0.2 GFLOP; the generic gather GEMM took 50 us with 49 CTAs.
 // ---------------------------------------------------------------------------------------
+// fused GEECO-F scatter: instead of d(state), write dL/d(pre-activation) of conv8 directly (state index -> encoder
+// group / cell / channel, ReLU mask from the conv8 output), fp32 or bf16
+struct DstateScatter { int on; int D0, D1, D2, J, per; const float* y[3]; float* g[3]; __nv_bfloat16* gb[3]; };
+
 __global__ void __launch_bounds__(256) lstm_dstate_kernel(const float* __restrict__ dgates, const float* __restrict__ W,
-                                                          float* __restrict__ dstate, int N, int xdim, int NC, int ld) {
+                                                          float* __restrict__ dstate, int N, int xdim, int NC, int ld,
+                                                          DstateScatter sc) {
   pdl_enter();
-  __shared__ float Ws[32][65];
+  __shared__ float Ws[16][65];
   __shared__ float Ds[64][65];
-  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 64;
-  const int k = threadIdx.x & 31, ng = threadIdx.x >> 5;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int k0 = blockIdx.x * 16, n0 = blockIdx.y * 64;
+  const int k = threadIdx.x & 15, ng = threadIdx.x >> 4;      // 16 kernel rows x 16 groups of 4 samples
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j0 = 0; j0 < NC; j0 += 64) {
-    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
-      const int r = e >> 6, c = e & 63;
-      Ws[r][c] = (k0 + r < xdim && j0 + c < NC) ? __ldg(W + (long long)(k0 + r) * NC + j0 + c) : 0.f;
+    // all 20 loads of this thread are issued before the first shared-memory store (a load/store loop serialised them)
+    float wv[4], dv[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = threadIdx.x + q * 256, r = e >> 6, c = e & 63;
+      wv[q] = (k0 + r < xdim && j0 + c < NC) ? __ldg(W + (long long)(k0 + r) * NC + j0 + c) : 0.f;
     }
-    for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-      const int r = e >> 6, c = e & 63;
-      Ds[r][c] = (n0 + r < N && j0 + c < NC) ? __ldg(dgates + (long long)(n0 + r) * NC + j0 + c) : 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int e = threadIdx.x + q * 256, r = e >> 6, c = e & 63;
+      dv[q] = (n0 + r < N && j0 + c < NC) ? __ldg(dgates + (long long)(n0 + r) * NC + j0 + c) : 0.f;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const int e = threadIdx.x + q * 256; Ws[e >> 6][e & 63] = wv[q]; }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const int e = threadIdx.x + q * 256; Ds[e >> 6][e & 63] = dv[q]; }
     __syncthreads();
 #pragma unroll 8
     for (int jj = 0; jj < 64; ++jj) {
       const float w = Ws[k][jj];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(Ds[ng * 8 + i][jj], w, acc[i]);
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(Ds[ng * 4 + i][jj], w, acc[i]);
     }
     __syncthreads();
   }
-  if (k0 + k < xdim) {
+  const int col = k0 + k;
+  if (col >= xdim) return;
+  int grp = -1, D = 0, cell = 0, cc = 0;
+  if (sc.on) {
+    cell = col / sc.per;
+    int c = col - cell * sc.per;
+    if (c < sc.D0) { grp = 0; D = sc.D0; cc = c; }
+    else if (c < sc.D0 + sc.D1) { grp = 1; D = sc.D1; cc = c - sc.D0; }
+    else if (c >= sc.D0 + sc.D1 + sc.J) { grp = 2; D = sc.D2; cc = c - sc.D0 - sc.D1 - sc.J; }
+  }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int n = n0 + ng * 8 + i;
-      if (n < N) dstate[(long long)n * ld + k0 + k] = acc[i];
-    }
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ng * 4 + i;
+    if (n >= N) continue;
+    if (!sc.on) { dstate[(long long)n * ld + col] = acc[i]; continue; }
+    if (grp < 0) continue;                                    // joint-state columns: data, no gradient wanted
+    const long long o = ((long long)n * 4 + cell) * D + cc;
+    const float v = sc.y[grp][o] > 0.f ? acc[i] : 0.f;
+    if (sc.gb[grp]) sc.gb[grp][o] = __float2bfloat16_rn(v);
+    else sc.g[grp][o] = v;
   }
 }
 int launch_lstm_dstate(const float* dgates, const float* W, float* dstate, int N, int xdim, int ncols, int ld,
                        cudaStream_t st) {
-  GEECO_LAUNCH((lstm_dstate_kernel), dim3((xdim + 31) / 32, (N + 63) / 64), 256, 0, st, dgates, W, dstate, N, xdim, ncols, ld);
+  DstateScatter sc = {};
+  GEECO_LAUNCH((lstm_dstate_kernel), dim3((xdim + 15) / 16, (N + 63) / 64), 256, 0, st, dgates, W, dstate, N, xdim, ncols, ld, sc);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+// GEECO-F (one step): d(state) is never materialised, the conv8 gradients are written directly
+int launch_lstm_dstate_scatter(const float* dgates, const float* W, const StateMap& sm, __nv_bfloat16* const* g_bf16, int ncols,
+                               cudaStream_t st) {
+  DstateScatter sc = {};
+  sc.on = 1; sc.D0 = sm.D0; sc.D1 = sm.D1; sc.D2 = sm.D2; sc.J = sm.J; sc.per = sm.per;
+  for (int e = 0; e < 3; ++e) { sc.y[e] = sm.y[e]; sc.g[e] = sm.g[e]; sc.gb[e] = g_bf16 ? g_bf16[e] : nullptr; }
+  GEECO_LAUNCH((lstm_dstate_kernel), dim3((sm.xdim + 15) / 16, (sm.N + 63) / 64), 256, 0, st, dgates, W, (float*)nullptr, sm.N, sm.xdim,
+               ncols, sm.ld, sc);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// d(kernel)[k][j] = sum_r states[r][k] * dgates[r][j], d(bias)[j] = sum_r dgates[r][j] over the R = T*N state rows.
+// R is small (64 at batch 64): no split over the reduction, one pass, fixed order.  Tile = 32 kernel rows x 64 gate
+// columns per CTA, the rows of both operands staged 32 at a time.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lstm_wgrad_kernel(const float* __restrict__ states, const float* __restrict__ dgates,
+                                                         float* __restrict__ dW, float* __restrict__ db, int R, int ld, int NC) {
+  pdl_enter();
+  __shared__ float Ss[32][33];
+  __shared__ float Dd[32][64];
+  const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 64;
+  const int jj = threadIdx.x & 63, kg = threadIdx.x >> 6;      // 64 columns x 4 groups of 8 kernel rows
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float bsum = 0.f;
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int r = e >> 5, k = e & 31;
+      Ss[r][k] = (r0 + r < R && k0 + k < ld) ? __ldg(states + (long long)(r0 + r) * ld + k0 + k) : 0.f;
+    }
+    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
+      const int r = e >> 6, c = e & 63;
+      Dd[r][c] = (r0 + r < R && j0 + c < NC) ? __ldg(dgates + (long long)(r0 + r) * NC + j0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float dv = Dd[r][jj];
+      bsum += dv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(Ss[r][kg * 8 + i], dv, acc[i]);
+    }
+    __syncthreads();
+  }
+  if (j0 + jj < NC) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = k0 + kg * 8 + i;
+      if (k < ld) dW[(long long)k * NC + j0 + jj] = acc[i];
+    }
+    if (blockIdx.x == 0 && kg == 0) db[j0 + jj] = bsum;
+  }
+}
+int launch_lstm_wgrad(const float* states, const float* dgates, float* dW, float* db, int R, int ld, int ncols, cudaStream_t st) {
+  GEECO_LAUNCH((lstm_wgrad_kernel), dim3((ld + 31) / 32, (ncols + 63) / 64), 256, 0, st, states, dgates, dW, db, R, ld, ncols);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
@@ -630,7 +790,7 @@ long long lstm_gates_partial_floats(int N, int K, int Ncols) {
   return (long long)((K + GK_SLICE - 1) / GK_SLICE) * N * Ncols;
 }
 int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias, float* gates, float* partial, int N,
-                      int K, int Ncols, cudaStream_t st) {
+                      int K, int Ncols, cudaStream_t st, int* slices_out) {
   if (Ncols > 1024) { geeco_set_error("lstm gates: 4*dim_h_lstm = %d > 1024 not supported", Ncols); return GEECO_ERR_INVALID; }
   const int slices = (K + GK_SLICE - 1) / GK_SLICE;
   dim3 grid(slices, (N + 31) / 32);
@@ -639,8 +799,9 @@ int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias
   else if (cpt == 2) GEECO_LAUNCH((gates_splitk_kernel<2>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
   else if (cpt == 3) GEECO_LAUNCH((gates_splitk_kernel<3>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
   else GEECO_LAUNCH((gates_splitk_kernel<4>), grid, 256, 0, st, x, W, partial, N, K, ldx, Ncols);
-  GEECO_LAUNCH((gates_reduce_kernel), ceil_div((long long)N * Ncols, 256), 256, 0, st, partial, bias, gates, slices, N, Ncols);
-  geeco_count_launch(2);
+  if (slices_out) *slices_out = slices;         // the caller's next kernel reduces the partials itself
+  else GEECO_LAUNCH((gates_reduce_kernel), ceil_div((long long)N * Ncols, 256), 256, 0, st, partial, bias, gates, slices, N, Ncols);
+  geeco_count_launch(slices_out ? 1 : 2);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }

@@ -46,10 +46,20 @@ int launch_lstm_cell(int N, int Hl, const float* gates, const float* c_prev, con
                      float* c_out, float* m_out, float* state_out, float* m_next, int ld_next, cudaStream_t st);
 int launch_lstm_cell_bwd(int N, int Hl, const float* gates, const float* c_prev, const unsigned char* reset_mask,
                          const float* dm, int ld_dm, const float* dc_in, float* dgates, float* dc_prev, cudaStream_t st);
+// heads_out / fc1_out / losses_out / state_out2: the caller's copies (geeco_outputs), NULL = not wanted
 int launch_tail_fwd(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1, const float* m,
-                    float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, cudaStream_t st);
+                    float* fc1, float* heads, float* loss_parts, float* dheads, int with_loss, float* heads_out,
+                    float* fc1_out, cudaStream_t st);
+int launch_tail_fwd_fused(const TailDims& d, const TailHeads& th, const float* w_fc1, const float* b_fc1,
+                          const float* partial, int slices, const float* lstm_bias, float* gates, const float* c_prev,
+                          const unsigned char* reset_mask, float* c_out, float* m_out, float* state_out, float* fc1,
+                          float* heads, float* loss_parts, float* dheads, int with_loss, float* heads_out, float* fc1_out,
+                          float* state_out2, cudaStream_t st);
 int launch_loss_reduce(const TailDims& d, const TailHeads& th, const float* loss_parts, const float* reg_term,
-                       float* losses, cudaStream_t st);
+                       float* losses, float* losses_out, cudaStream_t st);
+int launch_lstm_dstate_scatter(const float* dgates, const float* W, const StateMap& sm, __nv_bfloat16* const* g_bf16, int ncols,
+                               cudaStream_t st);
+int launch_lstm_wgrad(const float* states, const float* dgates, float* dW, float* db, int R, int ld, int ncols, cudaStream_t st);
 // dm_out == NULL: one-step graphs, the LSTM cell backward is fused (writes dgates); else writes dL/dm_T [N][Hl]
 int launch_tail_bwd(const TailDims& d, const TailHeads& th, const float* w_fc1, float* gw_fc1, float* gb_fc1,
                     const float* m, const float* fc1, const float* dheads, const float* gates, const float* c_prev,
@@ -63,8 +73,9 @@ int launch_lstm_dstate(const float* dgates, const float* W, float* dstate, int N
                        cudaStream_t st);
 // up to four device-to-device output copies in one launch (dst[i] == NULL skips one)
 int launch_copy_outputs(const float* const* src, float* const* dst, const long long* n, cudaStream_t st);
+// slices_out != NULL: only the split-K partials are produced (the caller's next kernel reduces them)
 int launch_lstm_gates(const float* x, int ldx, const float* W, const float* bias, float* gates, float* partial, int N,
-                      int K, int Ncols, cudaStream_t st);
+                      int K, int Ncols, cudaStream_t st, int* slices_out = nullptr);
 int launch_ring_push(void* ring, const void* frame, const unsigned char* fresh, int N, int K, long long row_bytes,
                      int slot, cudaStream_t st);
 

@@ -112,3 +112,15 @@ def pin_to_gpu_numa_node(local_rank, local_world=1):
     return allowed
   except Exception:      # noqa: BLE001  (sysfs layout, permissions, cpusets: never fatal)
     return None
+
+
+def tune_for_data_parallel(world):
+  """Environment defaults for one-process-per-GPU training, set before NCCL and the CUDA library initialise.  The
+  backward kernels are persistent grids sized for every SM; NCCL's all-reduce CTAs (up to 32 by default) share the
+  SMs with them for ~0.2 ms per step.  Measured on 8 x B200 (profiles/r02_scaling_notes.md): NCCL capped at 4 CTAs
+  and the grids sized for 144 of the 148 SMs: 2.463 ms per step against 2.505 ms with the defaults (8 CTAs / 140 SMs,
+  16 / 132 and 8 / 148 were all slower: the 30 MB all-reduce hides behind the backward even at 4 CTAs)."""
+  import os
+  if world > 1:
+    os.environ.setdefault('NCCL_MAX_CTAS', '4')
+    os.environ.setdefault('GEECO_NUM_SMS', '144')

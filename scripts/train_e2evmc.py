@@ -187,6 +187,7 @@ def main(args, argv=None):
   import torch.distributed as dist
   if not torch.cuda.is_available():
     raise RuntimeError("geeco_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+  parallel.tune_for_data_parallel(int(os.environ.get('WORLD_SIZE', '1')))
   if int(os.environ.get('WORLD_SIZE', '1')) > 1 and not dist.is_initialized():
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     parallel.pin_to_gpu_numa_node(int(os.environ.get('LOCAL_RANK', '0')), int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
