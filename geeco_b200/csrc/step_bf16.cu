@@ -123,7 +123,11 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   bp->jobs_uploaded = false;
   if (!ws_base) return GEECO_OK;
   if (!bp->side) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&bp->side, cudaStreamNonBlocking));
+    // lowest priority: the repack's many short blocks must not hold up the CTAs of the step's own kernels (conv1
+    // started 25 us late behind the tail of the late repack, r02 timeline)
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&bp->side, cudaStreamNonBlocking, prio_lo));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join_late, cudaEventDisableTiming));
