@@ -67,6 +67,7 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 bool geeco_pdl_enabled();
+void geeco_pdl_suspend(int on);      // launches made while suspended are plain stream-ordered launches
 template <typename... KArgs, typename... Args>
 static inline void geeco_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                     Args&&... args) {

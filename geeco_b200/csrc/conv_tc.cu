@@ -1026,30 +1026,34 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
                                                                    long long grand_total) {
   pdl_enter();
   __shared__ int s_job;
-  const long long v0 = (long long)blockIdx.x * PACK_CHUNK;
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].start <= v0) lo = mid; else hi = mid - 1; }
-    s_job = lo;
-  }
-  __syncthreads();
-  const PackJob& jb = jobs[s_job];
-  const uint32_t total = (uint32_t)jb.total, Kp = (uint32_t)jb.Kpad, rows = (uint32_t)jb.rows;
-  const int mode = jb.mode, Cin = jb.Cin, Cout = jb.Cout, Cs = jb.Cs, ntaps = jb.ntaps, Kt = jb.Kt;
-  const float* W = jb.W;
-  const float* bias = jb.bias;
-  const int bias_col = jb.bias_col;
-  const long long wgs = jb.w_group_stride, bgs = jb.b_group_stride;
-  __nv_bfloat16* out = jb.out;
-  uint32_t i = (uint32_t)(v0 - jb.start) + threadIdx.x;
+  // grid-stride over PACK_CHUNK-sized chunks: a launch with few blocks (see launch_pack_weights_batched) keeps at
+  // most a block or two per SM resident, so the step's own CTAs always find room next to it
+  for (long long v0 = (long long)blockIdx.x * PACK_CHUNK; v0 < grand_total; v0 += (long long)gridDim.x * PACK_CHUNK) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = njobs - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].start <= v0) lo = mid; else hi = mid - 1; }
+      s_job = lo;
+    }
+    __syncthreads();
+    const PackJob& jb = jobs[s_job];
+    const uint32_t total = (uint32_t)jb.total, Kp = (uint32_t)jb.Kpad, rows = (uint32_t)jb.rows;
+    const int mode = jb.mode, Cin = jb.Cin, Cout = jb.Cout, Cs = jb.Cs, ntaps = jb.ntaps, Kt = jb.Kt;
+    const float* W = jb.W;
+    const float* bias = jb.bias;
+    const int bias_col = jb.bias_col;
+    const long long wgs = jb.w_group_stride, bgs = jb.b_group_stride;
+    __nv_bfloat16* out = jb.out;
+    uint32_t i = (uint32_t)(v0 - jb.start) + threadIdx.x;
 #pragma unroll 1
-  for (int e = 0; e < PACK_CHUNK / 256; ++e, i += 256) {
-    if (i >= total) break;
-    const uint32_t rr = i / Kp, k = i - rr * Kp;
-    const uint32_t grp = rr / rows, r = rr - grp * rows;
-    float v = pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k);
-    if ((int)k == bias_col && (int)r < Cout) v = bias[(long long)grp * bgs + r];
-    out[i] = __float2bfloat16_rn(v);
+    for (int e = 0; e < PACK_CHUNK / 256; ++e, i += 256) {
+      if (i >= total) break;
+      const uint32_t rr = i / Kp, k = i - rr * Kp;
+      const uint32_t grp = rr / rows, r = rr - grp * rows;
+      float v = pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k);
+      if ((int)k == bias_col && (int)r < Cout) v = bias[(long long)grp * bgs + r];
+      out[i] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -1723,11 +1727,24 @@ int launch_pack_weights(const float* W, __nv_bfloat16* out, int mode, int groups
   return GEECO_OK;
 }
 
-int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st) {
+// max_blocks > 0: a persistent launch of at most that many blocks (the repack that runs next to the step's first
+// kernels on the side stream: thousands of short blocks kept every SM's registers fragmented and conv1's CTAs, which
+// need 29 K registers each, could not start until the repack grid was exhausted -- r02 timeline: conv1 began 25 us
+// after its input was ready, exactly when the repack ended)
+int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st, int max_blocks) {
   if (njobs <= 0 || grand_total <= 0) return GEECO_OK;
   if (njobs > 64) { geeco_set_error("pack_weights_batched: %d jobs > 64", njobs); return GEECO_ERR_INVALID; }
   if (grand_total % PACK_CHUNK) { geeco_set_error("pack_weights_batched: jobs must start on PACK_CHUNK boundaries"); return GEECO_ERR_INVALID; }
-  GEECO_LAUNCH((pack_weights_batched_kernel), (unsigned)(grand_total / PACK_CHUNK), 256, 0, st, jobs_dev, njobs, grand_total);
+  long long blocks = grand_total / PACK_CHUNK;
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
+  // same shared-memory carve-out as the tcgen05 kernels it runs next to: an SM switches its L1 / shared split only
+  // when it is empty, and with repack blocks always resident it never was -- conv1's CTAs waited for the whole repack
+  static bool carve_set = false;
+  if (!carve_set) {
+    CUDA_TRY(cudaFuncSetAttribute(pack_weights_batched_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_set = true;
+  }
+  GEECO_LAUNCH((pack_weights_batched_kernel), (unsigned)blocks, 256, 0, st, jobs_dev, njobs, grand_total);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

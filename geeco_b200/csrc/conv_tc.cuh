@@ -93,7 +93,7 @@ struct PackJob {
 // jobs occupy [start, start + total) of a virtual index space; every start is a multiple of PACK_CHUNK and
 // grand_total is the end of the last job rounded up to PACK_CHUNK (total < 2^31 per job)
 constexpr int PACK_CHUNK = 2048;
-int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st);
+int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st, int max_blocks = 0);
 // 1-bit ReLU mask (layout of TC_EPI_MASKBITS) of a bf16 tensor: one uint16 per 16 consecutive values
 int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long long chunks, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);

@@ -25,9 +25,11 @@ void geeco_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void geeco_count_launch(int n) { g_launches += n; }
+static int g_pdl_suspend = 0;
+void geeco_pdl_suspend(int on) { g_pdl_suspend = on; }
 bool geeco_pdl_enabled() {
   static const bool on = getenv("GEECO_NO_PDL") == nullptr;
-  return on;
+  return on && !g_pdl_suspend;
 }
 
 extern "C" const char* geeco_last_error(void) { return g_err; }
@@ -448,6 +450,7 @@ extern "C" int geeco_bind(geeco_ctx* c, float* theta, float* grad, float* m, flo
   c->bound = true;
   c->weights_dirty = true;
   c->fwd_done = false;
+  c->host_step = 0;
   return GEECO_OK;
 }
 
@@ -473,6 +476,7 @@ extern "C" int geeco_params_changed(geeco_ctx* c, void* stream) {
 
 extern "C" int geeco_set_step(geeco_ctx* c, int64_t t, void* stream) {
   if (!c || !c->bound) { geeco_set_error("set_step: context not bound"); return GEECO_ERR_STATE; }
+  c->host_step = (long long)t;
   c->host_sc[0] = (float)t; c->host_sc[1] = 0.f; c->host_sc[2] = 0.f; c->host_sc[3] = 0.f;
   CUDA_TRY(cudaMemcpyAsync(c->sc, c->host_sc, 4 * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
@@ -922,7 +926,8 @@ extern "C" int geeco_step_update(geeco_ctx* c, float grad_scale, void* stream) {
   if (!c || !c->bound || !c->fwd_done) { geeco_set_error("step_update: call geeco_step_forward/backward first"); return GEECO_ERR_STATE; }
   cudaStream_t st = (cudaStream_t)stream;
   const geeco_config& cfg = c->cfg;
-  int rc = launch_adam(c->theta, c->grad, c->m, c->v, c->arena_floats, c->sc, cfg.lr, cfg.adam_beta1, cfg.adam_beta2,
+  c->host_step += 1;
+  int rc = launch_adam(c->theta, c->grad, c->m, c->v, c->arena_floats, c->host_step, cfg.lr, cfg.adam_beta1, cfg.adam_beta2,
                        cfg.adam_eps, grad_scale, cfg.l2_regularizer, st);
   if (rc) return rc;
   c->weights_dirty = true;

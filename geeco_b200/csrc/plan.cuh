@@ -52,6 +52,7 @@ struct geeco_ctx {
   long long partial_cap = 0;
   const unsigned char* reset_mask = nullptr;   // of the batch of the last forward (carry_state)
   int ring_start = 0;
+  long long host_step = 0;                     // Adam updates applied so far (global_step of the reference's checkpoints)
   bool g8_bf16_ready = false;                  // bf16 mode: the tail already wrote layers[7].g as bf16
   // bf16 extras
   void* bf16_ws = nullptr;

@@ -28,18 +28,22 @@ struct Bf16Plan {
   Bf16Layer L[8];
   float* partial;
   long long partial_cap;
-  // weight-repack jobs in two tables (uploaded at the first repack after bind).  EARLY = forward operands of
-  // conv1-conv3, a few hundred KB that the first kernels of the step need; LATE = everything else (forward operands
-  // of conv4-conv8 and all data-gradient operands, 95 % of the elements), needed ~0.6 ms into the step
-  PackJob* jobs_dev[2];
-  std::vector<PackJob> jobs[2];
-  long long jobs_total[2];
+  // weight-repack jobs in three tables (uploaded at the first repack after bind), launched where the step has room:
+  //   0 EARLY  forward operands of conv1-conv3 (a few hundred KB): next to the pre-process kernel, joined before conv1
+  //   1 LATE   forward operands of conv4-conv8: same place, joined before conv4 (~0.6 ms later)
+  //   2 DGRAD  all data-gradient operands (60 % of the elements): forked after conv8's forward, runs next to the
+  //            LSTM / heads tail (a dozen small kernels that leave most SMs idle), joined before the first data gradient
+  // (a single table next to the pre-process kernel kept conv1 from starting: its CTAs need 29 K registers each and the
+  //  repack's blocks refill every slot they free -- r02 timelines)
+  PackJob* jobs_dev[3];
+  std::vector<PackJob> jobs[3];
+  long long jobs_total[3];
   bool jobs_uploaded;
   // the weight repack of a step does not depend on the batch: it runs on a side stream next to the rank-pooling
   // kernel (whose 16-CTA clusters leave a quarter of the SMs idle) and is joined before the first convolution
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_late = nullptr;
-  bool forked = false, late_pending = false;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_late = nullptr, ev_fork_dg = nullptr, ev_join_dg = nullptr;
+  bool forked = false, late_pending = false, dg_dirty = true, dg_pending = false;
 };
 
 // packed-K extent of a data-gradient class when the layer's output has `cout` channels (the planned geometry was
@@ -120,6 +124,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
   bp->jobs_dev[0] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_dev[1] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
+  bp->jobs_dev[2] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_uploaded = false;
   if (!ws_base) return GEECO_OK;
   if (!bp->side) {
@@ -131,6 +136,8 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join_late, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_fork_dg, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&bp->ev_join_dg, cudaEventDisableTiming));
   }
   // tensor maps (need the real addresses)
   for (int l = 0; l < 8; ++l) {
@@ -171,6 +178,8 @@ void free_bf16(geeco_ctx* c) {
     if (bp->ev_fork) cudaEventDestroy(bp->ev_fork);
     if (bp->ev_join) cudaEventDestroy(bp->ev_join);
     if (bp->ev_join_late) cudaEventDestroy(bp->ev_join_late);
+    if (bp->ev_fork_dg) cudaEventDestroy(bp->ev_fork_dg);
+    if (bp->ev_join_dg) cudaEventDestroy(bp->ev_join_dg);
     delete bp;
     c->bf16_ws = nullptr;
   }
@@ -194,12 +203,12 @@ static void add_job(Bf16Plan* bp, int table, const float* W, __nv_bfloat16* out,
 }
 
 // fp32 master weights -> packed bf16 operands of every conv layer (forward + the data-gradient classes): one launch
-// per job table.  which: 0 = EARLY table, 1 = LATE table, 2 = both
-static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 2) {
+// per job table.  which: 0 / 1 / 2 = one table, 3 = the two forward tables, 4 = all three
+static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 4, int max_blocks = 0) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   const int G = c->G;
   if (!bp->jobs_uploaded) {
-    for (int t = 0; t < 2; ++t) { bp->jobs[t].clear(); bp->jobs_total[t] = 0; }
+    for (int t = 0; t < 3; ++t) { bp->jobs[t].clear(); bp->jobs_total[t] = 0; }
     for (int l = 0; l < 8; ++l) {
       LayerPlan& L = c->layers[l];
       Bf16Layer& B = bp->L[l];
@@ -219,12 +228,12 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 2) {
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
-          add_job(bp, 1, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
+          add_job(bp, 2, W, B.w_dg[ci][e], 1, groups, wstride, L.Cin_real, L.Cout[e], L.Cout[e], B.dg[ci].ntaps, B.dg_taps[ci],
                   L.Cin_real, Kp, dgrad_kt(B.dg[ci], L.Cout[e]));
         }
       }
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < 3; ++t) {
       if (bp->jobs[t].size() > 64) { geeco_set_error("repack: %zu jobs > 64", bp->jobs[t].size()); return GEECO_ERR_INVALID; }
       for (const PackJob& pj : bp->jobs[t])
         if (pj.total >= (1ll << 31)) { geeco_set_error("repack: a job of %lld elements needs 64-bit indexing", pj.total); return GEECO_ERR_INVALID; }
@@ -234,12 +243,14 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 2) {
     CUDA_TRY(cudaStreamSynchronize(st));
     bp->jobs_uploaded = true;
   }
-  for (int t = 0; t < 2; ++t) {
-    if ((which != 2 && which != t) || bp->jobs[t].empty()) continue;
-    int rc = launch_pack_weights_batched(bp->jobs_dev[t], (int)bp->jobs[t].size(), bp->jobs_total[t], st);
+  for (int t = 0; t < 3; ++t) {
+    const bool sel = which == t || (which == 3 && t < 2) || which == 4;
+    if (!sel || bp->jobs[t].empty()) continue;
+    int rc = launch_pack_weights_batched(bp->jobs_dev[t], (int)bp->jobs[t].size(), bp->jobs_total[t], st, max_blocks);
     if (rc) return rc;
   }
-  if (which != 0) c->weights_dirty = false;
+  if (which == 1 || which == 3 || which == 4) c->weights_dirty = false;     // forward operands are current
+  if (which == 2 || which == 4) bp->dg_dirty = false;                        // data-gradient operands are current
   return GEECO_OK;
 }
 
@@ -250,12 +261,15 @@ int repack_fork_bf16(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   static const bool off = getenv("GEECO_NO_OVERLAP") != nullptr;
   if (!bp || !c->weights_dirty || !bp->side || !bp->jobs_uploaded || off) return GEECO_OK;   // first step: inline repack
+  bp->dg_dirty = true;                                  // the weights changed: every table is stale
   CUDA_TRY(cudaEventRecord(bp->ev_fork, st));
   CUDA_TRY(cudaStreamWaitEvent(bp->side, bp->ev_fork, 0));
+  geeco_pdl_suspend(1);                                 // plain launches on the side stream (events between them)
   int rc = repack_weights(c, bp->side, 0);
-  if (rc) return rc;
+  if (rc) { geeco_pdl_suspend(0); return rc; }
   CUDA_TRY(cudaEventRecord(bp->ev_join, bp->side));
   rc = repack_weights(c, bp->side, 1);
+  geeco_pdl_suspend(0);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(bp->ev_join_late, bp->side));
   bp->forked = true;
@@ -271,12 +285,29 @@ int repack_join_bf16(geeco_ctx* c, cudaStream_t st) {
   bp->forked = false;
   return GEECO_OK;
 }
+// data-gradient operands: forked behind the forward of conv8 (training contexts), joined before the first data gradient
+static int repack_dgrad_fork(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!c->cfg.training || !bp->dg_dirty || bp->dg_pending) return GEECO_OK;
+  static const bool off = getenv("GEECO_NO_OVERLAP") != nullptr;
+  if (off || !bp->side) return repack_weights(c, st, 2);
+  CUDA_TRY(cudaEventRecord(bp->ev_fork_dg, st));
+  CUDA_TRY(cudaStreamWaitEvent(bp->side, bp->ev_fork_dg, 0));
+  geeco_pdl_suspend(1);
+  int rc = repack_weights(c, bp->side, 2);
+  geeco_pdl_suspend(0);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(bp->ev_join_dg, bp->side));
+  bp->dg_pending = true;
+  return GEECO_OK;
+}
 
 int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
   if (c->weights_dirty) {
-    int rc = repack_weights(c, st);
+    bp->dg_dirty = true;
+    int rc = repack_weights(c, st, 3);
     if (rc) return rc;
   }
   const int N = c->M, G = c->G;
@@ -314,12 +345,19 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
     }
     src = (const __nv_bfloat16*)L.y;
   }
-  return GEECO_OK;
+  return repack_dgrad_fork(c, st);
 }
 
 int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
+  if (bp->dg_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(st, bp->ev_join_dg, 0));
+    bp->dg_pending = false;
+  } else if (bp->dg_dirty) {
+    int rc = repack_weights(c, st, 2);
+    if (rc) return rc;
+  }
   const int N = c->M, G = c->G;
   if (lhi == 7 && !c->g8_bf16_ready) {
     int rc = launch_f32_to_bf16(c->g8_f32, (__nv_bfloat16*)c->layers[7].g, c->layers[7].act_elems, st);

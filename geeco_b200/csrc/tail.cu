@@ -5,6 +5,7 @@
 // (lstm_decoder), :452-500 (losses); src/models/e2evmc/estimator.py:205-244 (targets, loss
 // composition, AdamOptimizer).  TF-1.15 semantics restated in oracle/geeco_oracle.py.
 #include "tail.cuh"
+#include <math.h>
 
 // ---------------------------------------------------------------------------------------
 // LSTM inputs of all T steps:  states[t][n] = [ flatten_hwc(concat_c[...]) | m_{t-1} ]       (graph.py:123-192)
@@ -403,21 +404,11 @@ __global__ void tail_wgrad_kernel(TailDims d, TailHeads th, float* __restrict__ 
 // v += (g*g-v)(1-b2); theta -= lr_t*m/(sqrt(v)+eps).   One launch over the flat arena.
 // sc[0] = t (as float), sc[1] = lr_t, sc[2] = 0.5*l2*sum(theta^2)
 // ---------------------------------------------------------------------------------------
-__global__ void adam_prep_kernel(float* sc, double lr, double b1, double b2) {
-  pdl_enter();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const double t = (double)sc[0] + 1.0;
-    sc[0] = (float)t;
-    sc[1] = (float)(lr * sqrt(1.0 - pow(b2, t)) / (1.0 - pow(b1, t)));
-  }
-}
-
+// lr_t comes from the host (the step counter lives in the context): one launch, nothing in front of it.
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ theta, const float4* __restrict__ grad,
                                                    float4* __restrict__ m, float4* __restrict__ v, long long n4,
-                                                   const float* __restrict__ sc, float b1, float b2, float eps,
-                                                   float gscale, float l2) {
+                                                   float lr_t, float b1, float b2, float eps, float gscale, float l2) {
   pdl_enter();
-  const float lr_t = sc[1];
   const float omb1 = 1.f - b1, omb2 = 1.f - b2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 th = theta[i], g = grad[i], mm = m[i], vv = v[i];
@@ -543,15 +534,16 @@ int launch_tail_bwd(const TailDims& d, const TailHeads& th, const float* w_fc1, 
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }
-int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, float* sc, double lr, double b1,
+int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, long long t, double lr, double b1,
                 double b2, double eps, float gscale, float l2, cudaStream_t st) {
-  GEECO_LAUNCH((adam_prep_kernel), 1, 32, 0, st, sc, lr, b1, b2);
+  // tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) for the t-th update (t >= 1), in double
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t)));
   const long long n4 = n / 4;
   int blocks = ceil_div(n4, 256); if (blocks > 148 * 8) blocks = 148 * 8;
   GEECO_LAUNCH((adam_kernel), blocks, 256, 0, st, reinterpret_cast<float4*>(theta), reinterpret_cast<const float4*>(grad),
-                                      reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4, sc, (float)b1,
-                                      (float)b2, (float)eps, gscale, l2);
-  geeco_count_launch(2);
+                                      reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), n4, lr_t, (float)b1, (float)b2,
+                                      (float)eps, gscale, l2);
+  geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
 }

@@ -64,7 +64,8 @@ int launch_lstm_wgrad(const float* states, const float* dgates, float* dW, float
 int launch_tail_bwd(const TailDims& d, const TailHeads& th, const float* w_fc1, float* gw_fc1, float* gb_fc1,
                     const float* m, const float* fc1, const float* dheads, const float* gates, const float* c_prev,
                     const unsigned char* reset_mask, float* dfc1, float* dgates, float* dm_out, cudaStream_t st);
-int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, float* sc, double lr, double b1,
+// t = index of this update (1 for the first step after global_step 0)
+int launch_adam(float* theta, const float* grad, float* m, float* v, long long n, long long t, double lr, double b1,
                 double b2, double eps, float gscale, float l2, cudaStream_t st);
 int launch_l2_term(const float* theta, long long n, float l2, float* sc, cudaStream_t st);
 long long lstm_gates_partial_floats(int N, int K, int Ncols);
