@@ -77,11 +77,12 @@ def load_peaks():
 
 
 def load_traffic():
-  """DRAM bytes per launch from the committed ncu --set full captures (profiles/r01_traffic.json)."""
-  path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-  if os.path.exists(path):
-    with open(path) as fp:
-      return json.load(fp)
+  """DRAM bytes per launch from the committed ncu --set full captures (profiles/r02_traffic.json, else round 1's)."""
+  for name in ('r02_traffic.json', 'r01_traffic.json'):
+    path = os.path.join(ROOT, 'profiles', name)
+    if os.path.exists(path):
+      with open(path) as fp:
+        return json.load(fp)
   return {}
 
 
