@@ -101,6 +101,13 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
   uint32_t buf = 0, bphase = 0;
   int turn = 0, group = 0, group_end = tiles_per_group;
   for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+    if (ncls == 1 && turn != set) {
+      // single-class launch whose tile belongs to another set: only the ring position moves (the per-tile decoding
+      // below was a quarter of conv1's instructions when every set ran it for every tile)
+      if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+      if (++turn == nsets) turn = 0;
+      continue;
+    }
     while (flat >= group_end) { ++group; group_end += tiles_per_group; }
     const uint32_t m = (uint32_t)(flat - (group_end - tiles_per_group)) * BM + row;
     const bool valid = m < Mg;
@@ -209,6 +216,92 @@ __device__ __forceinline__ void nn_epilogue(const TcGeom& g, const TcClasses& cl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lean epilogue of the two largest activations of the network (conv1 forward: ReLU + mask bits out; conv2 data
+// gradient: mask bits in), selected by TcGeom::fast32: N = Ntot = 32, power-of-two maps, every group a whole number of
+// tiles, < 2^31 destination pixels.  The generic epilogue above spent ~390 instructions per warp and item there (ncu:
+// conv1 forward at 72 % issue-slot use, 65 % of its instructions in the epilogue; conv2 data gradient stalled a third of
+// its samples on the second chunk's mask load).  Here: the warp walks ITS items only, a row is linear in
+// (flat tile, lane), the row's 32 mask bits are ONE 32-bit load issued before the accumulator wait, the accumulator is
+// read with one 32-column tcgen05.ld and released BEFORE the arithmetic and the stores, and the mask is applied to the
+// packed words (shift + byte-permute with sign replication + and: no predicates).
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_n32(const TcGeom& g, const TcClasses& cl, const unsigned short* __restrict__ mbits,
+                                             __nv_bfloat16* __restrict__ dst, int tiles_flat, int nbuf, uint32_t tmem_base,
+                                             uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane, int set, int nsets,
+                                             unsigned short* __restrict__ bits_out) {
+  static_assert(EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS, "epilogue_n32: ReLU (+ mask bits out) or mask bits in");
+  const int ncls = cl.ncls;
+  const uint32_t row = (uint32_t)(q * 32 + lane);
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  const uint32_t hw_shift = (uint32_t)g.hw_shift, w_shift = (uint32_t)g.w_shift;
+  const uint32_t hw_mask = (1u << hw_shift) - 1u, w_mask = (1u << w_shift) - 1u;
+  const uint32_t Hd = (uint32_t)g.Hd, Wd = (uint32_t)g.Wd, dsy = (uint32_t)g.dsy, dsx = (uint32_t)g.dsx;
+  const uint32_t* __restrict__ mb32 = reinterpret_cast<const uint32_t*>(mbits);
+  uint32_t* __restrict__ bo32 = reinterpret_cast<uint32_t*>(bits_out);
+  uint4* __restrict__ dst4 = reinterpret_cast<uint4*>(dst);
+  // item it = j * ncls + c (j-th tile of this CTA, class c); this warp's set serves it % nsets == set
+  int c = set, flat = blockIdx.x;
+  uint32_t buf = (uint32_t)set, bphase = 0;
+  while (c >= ncls) { c -= ncls; flat += gridDim.x; }
+  while (buf >= (uint32_t)nbuf) { buf -= (uint32_t)nbuf; bphase ^= 1u; }
+  while (flat < tiles_flat) {
+    const uint32_t L = (uint32_t)flat * BM + row;                     // row index over all groups
+    const uint32_t gimg = L >> hw_shift, rem = L & hw_mask;
+    const uint32_t y = rem >> w_shift, x = rem & w_mask;
+    const TcCls& kc = cl.c[c];
+    const uint32_t pix = (gimg * Hd + y * dsy + (uint32_t)kc.dy0) * Wd + x * dsx + (uint32_t)kc.dx0;
+    uint32_t bits = 0;
+    if (EPI == TC_EPI_MASKBITS) bits = __ldg(mb32 + pix);             // two 16-channel chunks = one word per pixel
+    mbar_wait(&tmem_full[buf], bphase);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(lane_addr + buf * 32u, v);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(&tmem_empty[buf]);                                    // the MMA warp may refill while we pack and store
+    uint32_t o[16];
+    if (EPI == TC_EPI_MASKBITS) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t bh = h ? bits >> 16 : bits;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // bit i (channel 2i) -> byte 0's sign, bit 8+i (channel 2i+1) -> byte 1's sign; 0x9988 replicates them
+          uint32_t keep;
+          asm("prmt.b32 %0, %1, 0, 0x9988;" : "=r"(keep) : "r"(bh << (7 - i)));
+          o[h * 8 + i] = pack_bf16x2(__uint_as_float(v[h * 16 + 2 * i]), __uint_as_float(v[h * 16 + 2 * i + 1])) & keep;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    }
+    uint4* d = dst4 + (size_t)pix * 4;                                // 32 channels = 64 bytes per pixel
+    stg256(d, o);
+    stg256(d + 2, o + 8);
+    if (EPI == TC_EPI_RELU && bits_out) {
+      // 1-bit ReLU mask of the stored values (layout of TC_EPI_MASKBITS): halfword h >= 0, h + 0x7fff has bit 15 set iff
+      // h != 0; shifting the accumulator right once per word leaves word i's flags at bits 8+i and 24+i
+      uint32_t w = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[h * 8 + i] + 0x7fff7fffu) & 0x80008000u);
+        const uint32_t b16 = ((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u);
+        w |= b16 << (16 * h);
+      }
+      bo32[pix] = w;
+    }
+    c += nsets;
+    while (c >= ncls) { c -= ncls; flat += gridDim.x; }
+    buf += (uint32_t)nsets;
+    while (buf >= (uint32_t)nbuf) { buf -= (uint32_t)nbuf; bphase ^= 1u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward / data-gradient kernel.  PIECE = bf16 elements per cp.async (8 -> 16 B, 4 -> 8 B)
 // ------------------------------------------------------------------------------------------------
 // NPW gather-producer warps and 12 - NPW epilogue warps (8/4 by default; 4/8 when the epilogue is the bottleneck:
@@ -295,35 +388,37 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     if (PIECE == 4 && NPW == 4 && g.rowwin) {
       // conv1 fast path: the tile is 128 consecutive pixels of one image row and K = 36 fits one k-block.
       // Producer thread t owns GEMM row t; a (row, ky) pair is 24 contiguous source bytes = three 8-byte copies.
-      // Only a handful of values stay live across tiles (the destination offsets are recomputed: two ALU ops each).
+      // Source and map have the same size (stride 1) and every group is a whole number of tiles, so the source pixel of
+      // a row is LINEAR in (flat tile, thread): one 64-bit base per tile, +Ws pixels per ky, immediates per kx.  A tap
+      // outside the image keeps its (unread) address and copies zero bytes (cp.async zero-fill).
       const TcCls& k0 = cl.c[0];
       const int dx0 = k0.dx[0], dy0 = k0.dy[0];                   // taps are dy0 + ky, dx0 + kx
-      const int Hs = g.Hs, Ws = g.Ws, ipg = g.imgs_per_group, hw_shift = g.hw_shift, w_shift = g.w_shift;
-      const uint32_t row = threadIdx.x, rsw = row & 7u, rbase = row * 128u;
+      const int Hs = g.Hs, Ws = g.Ws;
+      const uint32_t hw_mask = (1u << g.hw_shift) - 1u, w_mask = (1u << g.w_shift) - 1u, w_shift = (uint32_t)g.w_shift;
+      const uint32_t row = threadIdx.x, rsw4 = (row & 7u) << 4;
+      const uint32_t a_row0 = smem_u32(a_base) + row * 128u;
+      const char* const srcb = reinterpret_cast<const char*>(src) + ((long long)dy0 * Ws + dx0 + (long long)row) * 8;
+      const long long row_bytes = (long long)Ws * 8;
+      (void)group; (void)group_end;
       for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-        while (flat >= group_end) { ++group; group_end += tiles_per_group; }
-        const uint32_t m0 = (uint32_t)(flat - (group_end - tiles_per_group)) * BM;
-        const int img = (int)(m0 >> hw_shift);
-        const uint32_t rem = m0 & ((1u << hw_shift) - 1u);
-        const int y = (int)(rem >> w_shift), x0 = (int)(rem & ((1u << w_shift) - 1u));
-        mbar_wait(&empty[s], sphase ^ 1u);
-        const uint32_t a_row = smem_u32(a_base + s * A_STAGE_BYTES) + rbase;
-        const int xl = x0 + (int)row + dx0;                         // leftmost source column of this row's window
+        const uint32_t L = (uint32_t)flat * BM + row;
+        const uint32_t rem = L & hw_mask;
+        const int yt = (int)(rem >> w_shift) + dy0, xl = (int)(rem & w_mask) + dx0;   // top-left source pixel
         const bool in0 = xl >= 0, in2 = xl + 2 < Ws;                // kx = 1 is always inside (Ws >= 2)
-        // pointer to source pixel (y + dy0, xl)
-        const __nv_bfloat16* sp = src + ((long long)((group * ipg + img) * Hs + (y + dy0)) * Ws + xl) * 4;
+        const char* sp = srcb + (long long)flat * (BM * 8);
+        mbar_wait(&empty[s], sphase ^ 1u);
+        const uint32_t a_row = a_row0 + s * (uint32_t)A_STAGE_BYTES;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const bool okr = (unsigned)(y + dy0 + ky) < (unsigned)Hs;
-          const bool ok0 = okr && in0, ok2 = okr && in2;
+          const bool okr = (unsigned)(yt + ky) < (unsigned)Hs;
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const uint32_t bb = (uint32_t)(ky * 24 + kx * 8);       // byte of (ky, kx) in the 128-byte im2col row
-            const uint32_t d = a_row + (((bb >> 4) ^ rsw) << 4) + (bb & 15u);
-            const bool ok = kx == 0 ? ok0 : (kx == 1 ? okr : ok2);
-            cp_async8(d, ok ? (const void*)(sp + kx * 4) : (const void*)src, ok ? 8u : 0u);
+            const uint32_t d = a_row + (((bb >> 4) << 4) ^ rsw4) + (bb & 15u);
+            const bool ok = okr && (kx == 0 ? in0 : (kx == 1 ? true : in2));
+            cp_async8(d, sp + kx * 8, ok ? 8u : 0u);
           }
-          sp += (long long)Ws * 4;
+          sp += row_bytes;
         }
         cp_async_mbar_arrive_noinc(&full[s]);
         if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
@@ -376,9 +471,19 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     }
    }
   } else if (warp < 12) {
-    nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                             tmem_empty, Mg, warp & 3, ((warp - NPW) >> 2) % NHALF, lane, ((warp - NPW) >> 2) / NHALF, ESETS,
-                             bits_out);
+    if constexpr (NHALF == 1 && (EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS)) {
+      if (g.fast32) {
+        epilogue_n32<EPI>(g, cl, reinterpret_cast<const unsigned short*>(mask), dst, tiles_flat, nbuf, tmem_base, tmem_full,
+                          tmem_empty, warp & 3, lane, (warp - NPW) >> 2, ESETS, bits_out);
+      } else {
+        nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                                 tmem_empty, Mg, warp & 3, 0, lane, (warp - NPW) >> 2, ESETS, bits_out);
+      }
+    } else {
+      nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                               tmem_empty, Mg, warp & 3, ((warp - NPW) >> 2) % NHALF, lane, ((warp - NPW) >> 2) / NHALF, ESETS,
+                               bits_out);
+    }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
     // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
@@ -516,8 +621,18 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
 
   if (warp < W_MMA) {
     const int set = warp / SETW, ws = warp - set * SETW;
-    nn_epilogue<SETW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
-                               tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS * SUBSETS, bits_out);
+    if constexpr (SETW == 4 && (EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS)) {
+      if (g.fast32) {
+        epilogue_n32<EPI>(g, cl, reinterpret_cast<const unsigned short*>(mask), dst, tiles_flat, nbuf, tmem_base, tmem_full,
+                          tmem_empty, ws & 3, lane, set, SETS * SUBSETS, bits_out);
+      } else {
+        nn_epilogue<1, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                            tmem_empty, Mg, ws & 3, 0, lane, set, SETS * SUBSETS, bits_out);
+      }
+    } else {
+      nn_epilogue<SETW / 4, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
+                                 tmem_empty, Mg, ws & 3, ws >> 2, lane, set, SETS * SUBSETS, bits_out);
+    }
   } else if (warp == W_MMA) {
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
     // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
@@ -1364,6 +1479,16 @@ static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f
   return EPI_GENERIC;
 }
 
+// lean N = 32 epilogue (epilogue_n32): every condition it relies on, checked on the host
+static int tc_fast32(const TcGeom& g, int epi_t) {
+  static const bool off = getenv("GEECO_TC_NO_FAST32") != nullptr;
+  if (off || (epi_t != TC_EPI_RELU && epi_t != TC_EPI_MASKBITS)) return 0;
+  const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
+  const long long dst_pixels = (long long)g.groups * g.imgs_per_group * g.Hd * g.Wd;
+  return g.Nn == 32 && g.Ntot == 32 && g.nsplit == 1 && g.hw_shift >= 0 && g.w_shift >= 0 && Mg % BM == 0 &&
+         dst_pixels < (1ll << 31) && (long long)g.groups * Mg < (1ll << 31);
+}
+
 // builds the row program of a row-resident launch (see tc_rows_kernel) and runs it
 static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const TcMaps& maps, const __nv_bfloat16* src,
                           const float* bias, const __nv_bfloat16* mask, __nv_bfloat16* dst, float* dst_f32, int epi,
@@ -1440,12 +1565,14 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
     auto kern = tc_rows_kernel<SETS_, EPW_, MASK_>;                                                                     \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
-    GEECO_LAUNCH((kern), ctas, SETS_ * EPW_ * 32 + 64, smem, st, g, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,                \
+    GEECO_LAUNCH((kern), ctas, SETS_ * EPW_ * 32 + 64, smem, st, gk, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,               \
                                                      tiles_per_group, tiles_flat, tmem_cols, stages, nbuf, bits_out);   \
   } while (0)
 #define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
 #define ROWS_LAUNCH_S(MASK_) do { if (per_sm == 2) ROWS_LAUNCH_E(1, MASK_); else ROWS_LAUNCH_E(2, MASK_); } while (0)
   const int epi_t = tc_epi_template(epi, dst, dst_f32);
+  TcGeom gk = g;
+  gk.fast32 = tc_fast32(g, epi_t);
   if (epi_t == TC_EPI_MASK) ROWS_LAUNCH_S(TC_EPI_MASK);
   else if (epi_t == TC_EPI_MASKBITS) ROWS_LAUNCH_S(TC_EPI_MASKBITS);
   else if (epi_t == TC_EPI_BIAS_RELU) ROWS_LAUNCH_S(TC_EPI_BIAS_RELU);
@@ -1566,6 +1693,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     else NN_LAUNCH_M(PIECE_, NPW_, EPI_GENERIC);                                                                       \
   } while (0)
   const int epi_t = tc_epi_template(epi, dst, dst_f32);
+  g.fast32 = tc_fast32(g, epi_t);
   if (npw == 0) NN_LAUNCH(8, 0);
   else if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
   else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }

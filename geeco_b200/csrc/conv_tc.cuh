@@ -27,6 +27,7 @@ struct TcGeom {
   int Hd, Wd;                 // destination tensor [imgs, Hd, Wd, Nn]
   int dsy, dsx, dy0, dx0;
   int imgs_per_group, groups;
+  int fast32;                 // set by the launchers: the lean N = 32 epilogue applies (see epilogue_n32 in conv_tc.cu)
   int b_rows_per_group;       // rows of the packed weight matrix per group (tensor-map row offset)
   long long bias_group_stride;
 };
