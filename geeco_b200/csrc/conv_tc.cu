@@ -229,8 +229,15 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_n32(const TcGeom& g, const TcClasses& cl, const unsigned short* __restrict__ mbits,
                                              __nv_bfloat16* __restrict__ dst, int tiles_flat, int nbuf, uint32_t tmem_base,
                                              uint64_t* tmem_full, uint64_t* tmem_empty, int q, int lane, int set, int nsets,
-                                             unsigned short* __restrict__ bits_out) {
+                                             unsigned short* __restrict__ bits_out, const CUtensorMap* omap, uint8_t* stage) {
   static_assert(EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS, "epilogue_n32: ReLU (+ mask bits out) or mask bits in");
+  // stage != nullptr: the warp's 32 rows x 64 bytes go through a private 2 KB staging tile (SWIZZLE_64B: conflict-free
+  // 128-bit shared stores with a fixed register group per instruction) and ONE TMA tensor store instead of 64 per-lane
+  // 32-byte sectors: the LSU wavefronts of the row-per-lane stores were the busiest unit of these kernels (ncu:
+  // l1tex__data_pipe_lsu_wavefronts 75-81 %).  No CTA-level barrier is involved (round 1's staged epilogue lost to two
+  // named barriers per tile): lane 0 owns the bulk group, the warp synchronises with __syncwarp.
+  const uint32_t stage_u32 = stage ? smem_u32(stage) : 0u;
+  const uint32_t dshift = g.dsx == 2 ? 1u : 0u;
   const int ncls = cl.ncls;
   const uint32_t row = (uint32_t)(q * 32 + lane);
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -277,9 +284,24 @@ __device__ __forceinline__ void epilogue_n32(const TcGeom& g, const TcClasses& c
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
     }
-    uint4* d = dst4 + (size_t)pix * 4;                                // 32 channels = 64 bytes per pixel
-    stg256(d, o);
-    stg256(d + 2, o + 8);
+    if (stage) {
+      if (lane == 0) bulk_wait_read0();                               // the previous store has read the staging tile
+      __syncwarp();
+      const uint32_t sw = ((uint32_t)lane >> 1) & 3u, srow = stage_u32 + (uint32_t)lane * 64u;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        st_shared_v4(srow + (((uint32_t)ch ^ sw) << 4), o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {                                                // lane 0's row is the first of the warp's 32
+        tma_store_3d(omap, stage_u32, 0, (int)(pix & ((1u << dshift) - 1u)), (int)(pix >> dshift));
+        bulk_commit();
+      }
+    } else {
+      uint4* d = dst4 + (size_t)pix * 4;                              // 32 channels = 64 bytes per pixel
+      stg256(d, o);
+      stg256(d + 2, o + 8);
+    }
     if (EPI == TC_EPI_RELU && bits_out) {
       // 1-bit ReLU mask of the stored values (layout of TC_EPI_MASKBITS): halfword h >= 0, h + 0x7fff has bit 15 set iff
       // h != 0; shifting the accumulator right once per word leaves word i's flags at bits 8+i and 24+i
@@ -299,6 +321,90 @@ __device__ __forceinline__ void epilogue_n32(const TcGeom& g, const TcClasses& c
     buf += (uint32_t)nsets;
     while (buf >= (uint32_t)nbuf) { buf -= (uint32_t)nbuf; bphase ^= 1u; }
   }
+  if (stage && lane == 0) bulk_wait0();                               // global writes performed before the CTA retires
+}
+
+// MMA issue loop of tc_nn_kernel.  The whole warp runs it (warp-uniform control flow keeps the descriptors in uniform
+// registers), one elected lane issues; ring positions and phases are carried incrementally.  KSTEPS = K = 16 steps
+// per 64-wide k-block that hold data.
+template <int KSTEPS>
+__device__ __forceinline__ void nn_mma_loop(const TcClasses& cl, int ncls, int tiles_flat, int stages, int nbuf, int BN,
+                                            uint32_t tmem_base, uint32_t a_base_u32, uint32_t b_base_u32, int b_stage_bytes,
+                                            uint64_t* full, uint64_t* empty, uint64_t* tmem_full, uint64_t* tmem_empty) {
+  const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+  const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+  const uint32_t a_base16 = a_base_u32 >> 4, b_base16 = b_base_u32 >> 4;
+  const uint32_t bstage16 = (uint32_t)b_stage_bytes >> 4;
+  uint32_t s = 0, sphase = 0, buf = 0, bphase = 0;
+  for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+    for (int c = 0; c < ncls; ++c) {
+      const int nkb = cl.c[c].Kpad / BK;
+      mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * (uint32_t)BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], sphase);
+        tc_fence_after();
+        const uint32_t a16 = a_base16 + s * (uint32_t)(A_STAGE_BYTES >> 4);
+        const uint32_t b16 = b_base16 + s * bstage16;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KSTEPS; ++j)
+            tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
+          tc_commit(&empty[s]);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
+      }
+      if (elect_one()) tc_commit(&tmem_full[buf]);
+      __syncwarp();
+      if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+    }
+  }
+}
+
+// MMA issue loop of tc_rows_kernel (see there): per tile one stage of source rows, per class `nsteps` shifted-window
+// MMAs of KSTEPS K = 16 steps against resident weight k-blocks.
+template <int KSTEPS>
+__device__ __forceinline__ void rows_mma_loop(const TcRowProg& rp, int ncls, int tiles_per_group, int tiles_flat, int stages,
+                                              int nbuf, int BN, uint32_t tmem_base, uint32_t a_base_u32, uint32_t b_base_u32,
+                                              int stage_bytes, int b_slot_bytes, uint64_t* full, uint64_t* empty,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty, uint64_t* wfull) {
+  const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+  const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+  const uint32_t a_base16 = a_base_u32 >> 4, b_base16 = b_base_u32 >> 4;
+  const uint32_t stage16 = (uint32_t)stage_bytes >> 4, slot16 = (uint32_t)b_slot_bytes >> 4;
+  uint32_t wphase = 0, s = 0, sphase = 0, buf = 0, bphase = 0;
+  int group = 0, group_end = tiles_per_group, cur_group = -1;
+  for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
+    while (flat >= group_end) { ++group; group_end += tiles_per_group; }
+    if (group != cur_group) { mbar_wait(wfull, wphase); wphase ^= 1u; cur_group = group; }
+    mbar_wait(&full[s], sphase);
+    tc_fence_after();
+    const uint32_t a_stage16 = a_base16 + s * stage16;
+    for (int c = 0; c < ncls; ++c) {
+      mbar_wait(&tmem_empty[buf], bphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * (uint32_t)BN;
+      const int ns = rp.nsteps[c];
+      for (int st = 0; st < ns; ++st) {
+        const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
+        const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < KSTEPS; ++j)
+            tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&tmem_full[buf]);
+      __syncwarp();
+      if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
+    }
+    if (elect_one()) tc_commit(&empty[s]);
+    __syncwarp();
+    if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,7 +418,8 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
              const __grid_constant__ CUtensorMap amap, const __nv_bfloat16* __restrict__ src,
              const float* __restrict__ bias_all, const __nv_bfloat16* __restrict__ mask,
              __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi, int tiles_per_group,
-             int tiles_flat, int tmem_cols, int stages, int nbuf, unsigned short* __restrict__ bits_out) {
+             int tiles_flat, int tmem_cols, int stages, int nbuf, unsigned short* __restrict__ bits_out,
+             const __grid_constant__ CUtensorMap omap) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -473,8 +580,12 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
   } else if (warp < 12) {
     if constexpr (NHALF == 1 && (EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS)) {
       if (g.fast32) {
+        // fast32 == 2: staged TMA-store epilogue, 2 KB per epilogue warp behind the barriers / bias (1024-aligned)
+        uint8_t* epi_stage = nullptr;
+        if (g.fast32 == 2)
+          epi_stage = smem + ((stages * (A_STAGE_BYTES + b_stage_bytes) + 512 + g.groups * BN * 4 + 1023) & ~1023) + (warp - NPW) * 2048;
         epilogue_n32<EPI>(g, cl, reinterpret_cast<const unsigned short*>(mask), dst, tiles_flat, nbuf, tmem_base, tmem_full,
-                          tmem_empty, warp & 3, lane, (warp - NPW) >> 2, ESETS, bits_out);
+                          tmem_empty, warp & 3, lane, (warp - NPW) >> 2, ESETS, bits_out, &omap, epi_stage);
       } else {
         nn_epilogue<NHALF, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
                                  tmem_empty, Mg, warp & 3, 0, lane, (warp - NPW) >> 2, ESETS, bits_out);
@@ -486,38 +597,16 @@ tc_nn_kernel(const TcGeom g, const TcClasses cl, const __grid_constant__ TcMaps 
     }
   } else if (warp == 12) {
     // ===================== MMA issuer =====================
-    // the whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers), one
-    // elected lane issues; ring positions and phases are carried incrementally
-    const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
-    const uint32_t a_base16 = smem_u32(a_base) >> 4, b_base16 = smem_u32(b_base) >> 4;
-    const uint32_t bstage16 = (uint32_t)b_stage_bytes >> 4;
-    uint32_t s = 0, sphase = 0, buf = 0, bphase = 0;
-    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-      for (int c = 0; c < ncls; ++c) {
-        const int nkb = cl.c[c].Kpad / BK;
-        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d = tmem_base + buf * (uint32_t)BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[s], sphase);
-          tc_fence_after();
-          const uint32_t a16 = a_base16 + s * (uint32_t)(A_STAGE_BYTES >> 4);
-          const uint32_t b16 = b_base16 + s * bstage16;
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < BK / 16; ++j)
-              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (kb | j) != 0 ? 1u : 0u);
-            tc_commit(&empty[s]);
-          }
-          __syncwarp();
-          if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
-        }
-        if (elect_one()) tc_commit(&tmem_full[buf]);
-        __syncwarp();
-        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
-      }
-    }
+    // TMA-fed A with one 64-channel chunk per tap: the chunk holds only the channels the source really has (48 ->
+    // three K = 16 steps; the fourth would multiply zero-filled columns by zero weights).  The step count is a
+    // template argument of the loop: a runtime bound inside the issue loop cost conv2's forward 20 % (measured).
+    const int ksteps = (A_TMA && g.Kt == BK) ? (((g.Cs - 1) & 63) >> 4) + 1 : BK / 16;
+    if (ksteps == 3)
+      nn_mma_loop<3>(cl, ncls, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base), smem_u32(b_base), b_stage_bytes, full,
+                     empty, tmem_full, tmem_empty);
+    else
+      nn_mma_loop<BK / 16>(cl, ncls, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base), smem_u32(b_base), b_stage_bytes,
+                           full, empty, tmem_full, tmem_empty);
   } else {
     // ===================== weight tiles (and, A_TMA, activation tiles) by TMA (one thread) =====================
     if (lane == 0) {
@@ -576,7 +665,7 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
                const __grid_constant__ CUtensorMap amap, const float* __restrict__ bias_all,
                const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dst, float* __restrict__ dst_f32, int epi,
                int tiles_per_group, int tiles_flat, int tmem_cols, int stages, int nbuf,
-               unsigned short* __restrict__ bits_out) {
+               unsigned short* __restrict__ bits_out, const __grid_constant__ CUtensorMap omap) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -623,8 +712,11 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
     const int set = warp / SETW, ws = warp - set * SETW;
     if constexpr (SETW == 4 && (EPI == TC_EPI_RELU || EPI == TC_EPI_MASKBITS)) {
       if (g.fast32) {
+        uint8_t* epi_stage = nullptr;
+        if (g.fast32 == 2)
+          epi_stage = smem + ((rp.b_slots * b_slot_bytes + stages * stage_bytes + 512 + g.groups * BN * 4 + 1023) & ~1023) + warp * 2048;
         epilogue_n32<EPI>(g, cl, reinterpret_cast<const unsigned short*>(mask), dst, tiles_flat, nbuf, tmem_base, tmem_full,
-                          tmem_empty, ws & 3, lane, set, SETS * SUBSETS, bits_out);
+                          tmem_empty, ws & 3, lane, set, SETS * SUBSETS, bits_out, &omap, epi_stage);
       } else {
         nn_epilogue<1, EPI>(g, cl, bias_s, mask, dst, dst_f32, epi, tiles_per_group, tiles_flat, nbuf, tmem_base, tmem_full,
                             tmem_empty, Mg, ws & 3, 0, lane, set, SETS * SUBSETS, bits_out);
@@ -637,41 +729,15 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
     // The whole warp runs the issue loop (warp-uniform control flow -> descriptors live in uniform registers); one
     // elected lane issues.  No divisions: ring positions and phases are carried incrementally.  A single thread
     // issuing ~25 instructions per MMA was what bounded the earlier kernels (profiles/r01_ncu_notes.md).
-    const uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
-    const uint32_t a_base16 = smem_u32(a_base) >> 4, b_base16 = smem_u32(b_base) >> 4;
-    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, slot16 = (uint32_t)b_slot_bytes >> 4;
-    uint32_t wphase = 0, s = 0, sphase = 0, buf = 0, bphase = 0;
-    int group = 0, group_end = tiles_per_group, cur_group = -1;
-    for (int flat = blockIdx.x; flat < tiles_flat; flat += gridDim.x) {
-      while (flat >= group_end) { ++group; group_end += tiles_per_group; }
-      if (group != cur_group) { mbar_wait(wfull, wphase); wphase ^= 1u; cur_group = group; }
-      mbar_wait(&full[s], sphase);
-      tc_fence_after();
-      const uint32_t a_stage16 = a_base16 + s * stage16;
-      for (int c = 0; c < ncls; ++c) {
-        mbar_wait(&tmem_empty[buf], bphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d = tmem_base + buf * (uint32_t)BN;
-        const int ns = rp.nsteps[c];
-        for (int st = 0; st < ns; ++st) {
-          const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
-          const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < BK / 16; ++j)
-              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) tc_commit(&tmem_full[buf]);
-        __syncwarp();
-        if (++buf == (uint32_t)nbuf) { buf = 0; bphase ^= 1u; }
-      }
-      if (elect_one()) tc_commit(&empty[s]);
-      __syncwarp();
-      if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
-    }
+    // Unit-stride source: a window row holds the Cs real channels of one pixel, zero-filled to 64 (48 -> three K = 16
+    // steps); the step count is a template argument of the loop (a runtime bound inside it cost 20 %).
+    const int ksteps = g.rows == 1 ? (((g.Cs - 1) & 63) >> 4) + 1 : BK / 16;
+    if (ksteps == 3)
+      rows_mma_loop<3>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base), smem_u32(b_base),
+                       stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
+    else
+      rows_mma_loop<BK / 16>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base),
+                             smem_u32(b_base), stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
   } else {
     if (lane == 0) {
       uint32_t it = 0;
@@ -1479,6 +1545,21 @@ static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f
   return EPI_GENERIC;
 }
 
+// 3-D tensor map over a 32-channel bf16 destination viewed as [pixels / dsx][dsx][32]: one box = 32 pixels of one
+// column parity x 64 bytes, SWIZZLE_64B staging tile (epilogue_n32's TMA store)
+static int make_out32_tensor_map(CUtensorMap* map, void* base, long long pixels, int dsx) {
+  PFN_encodeTiled fn = encode_tiled_fn();
+  if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
+  cuuint64_t gdim[3] = {32u, (cuuint64_t)dsx, (cuuint64_t)(pixels / dsx)};
+  cuuint64_t gstr[2] = {64u, (cuuint64_t)64 * dsx};
+  cuuint32_t box[3] = {32u, 1u, 32u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { geeco_set_error("cuTensorMapEncodeTiled (32-channel destination) failed with CUresult %d", (int)r); return GEECO_ERR_CUDA; }
+  return GEECO_OK;
+}
+
 // lean N = 32 epilogue (epilogue_n32): every condition it relies on, checked on the host
 static int tc_fast32(const TcGeom& g, int epi_t) {
   static const bool off = getenv("GEECO_TC_NO_FAST32") != nullptr;
@@ -1548,16 +1629,31 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
   const int stage_bytes = rp.nrows * rp.pitch;
   const int b_bytes = rp.b_slots * g.Nn * BK * 2;
   const int tail_bytes = 512 + g.groups * g.Nn * 4;
+  const int epi_t = tc_epi_template(epi, dst, dst_f32);
+  TcGeom gk = g;
+  gk.fast32 = tc_fast32(g, epi_t);
+  // staged TMA-store epilogue (epilogue_n32): 2 KB per epilogue warp; experiment switch, off unless asked for
+  // (the conv2 data gradient then no longer fits two CTAs per SM)
+  static const bool rows_tmastore = getenv("GEECO_TC_ROWS_TMASTORE") != nullptr;
+  const bool want_stage = gk.fast32 && rows_tmastore;
   // two co-resident CTAs with one epilogue set each when two stages fit twice, else one CTA with two sets
-  int per_sm = 2 * (1024 + b_bytes + 2 * stage_bytes + tail_bytes) <= (int)SMEM_BUDGET ? 2 : 1;
+  int per_sm = 2 * (1024 + b_bytes + 2 * stage_bytes + tail_bytes + (want_stage ? 1024 + 8 * 2048 : 0)) <= (int)SMEM_BUDGET ? 2 : 1;
   if (const char* e = getenv("GEECO_TC_ROWS_PERSM")) { const int v = atoi(e); if (v == 1 || (v == 2 && per_sm == 2)) per_sm = v; }
-  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - b_bytes - tail_bytes) / stage_bytes);
+  const int epi_stage_bytes = want_stage ? 1024 + (per_sm == 2 ? 8 : 16) * 2048 : 0;
+  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - b_bytes - tail_bytes - epi_stage_bytes) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) { geeco_set_error("tc_rows: stage of %d bytes does not fit twice", stage_bytes); return GEECO_ERR_INVALID; }
   int nbuf = 2;
   while (nbuf < 8 && 2 * nbuf * g.Nn <= 512 / per_sm) nbuf *= 2;
   const int tmem_cols = next_pow2_cols(nbuf * g.Nn);
-  const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * stage_bytes + tail_bytes;
+  const size_t smem = 1024 + (size_t)b_bytes + (size_t)stages * stage_bytes + tail_bytes + epi_stage_bytes;
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  if (want_stage) {
+    rc = make_out32_tensor_map(&omap, dst, (long long)g.groups * g.imgs_per_group * g.Hd * g.Wd, g.dsx);
+    if (rc) return rc;
+    gk.fast32 = 2;
+  }
   int ctas = num_sms() * per_sm;
   if (ctas > tiles_flat) ctas = tiles_flat;
 #define ROWS_LAUNCH(SETS_, EPW_, MASK_)                                                                                 \
@@ -1566,13 +1662,10 @@ static int launch_tc_rows(const TcGeom* gs, int ncls, const TcClasses& cl, const
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                       \
     GEECO_LAUNCH((kern), ctas, SETS_ * EPW_ * 32 + 64, smem, st, gk, cl, rp, maps, amap, bias, mask, dst, dst_f32, epi,               \
-                                                     tiles_per_group, tiles_flat, tmem_cols, stages, nbuf, bits_out);   \
+                                                     tiles_per_group, tiles_flat, tmem_cols, stages, nbuf, bits_out, omap); \
   } while (0)
 #define ROWS_LAUNCH_E(SETS_, MASK_) do { if (g.Nn <= 32) ROWS_LAUNCH(SETS_, 8, MASK_); else ROWS_LAUNCH(SETS_, 12, MASK_); } while (0)
 #define ROWS_LAUNCH_S(MASK_) do { if (per_sm == 2) ROWS_LAUNCH_E(1, MASK_); else ROWS_LAUNCH_E(2, MASK_); } while (0)
-  const int epi_t = tc_epi_template(epi, dst, dst_f32);
-  TcGeom gk = g;
-  gk.fast32 = tc_fast32(g, epi_t);
   if (epi_t == TC_EPI_MASK) ROWS_LAUNCH_S(TC_EPI_MASK);
   else if (epi_t == TC_EPI_MASKBITS) ROWS_LAUNCH_S(TC_EPI_MASKBITS);
   else if (epi_t == TC_EPI_BIAS_RELU) ROWS_LAUNCH_S(TC_EPI_BIAS_RELU);
@@ -1654,11 +1747,24 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
   if (const char* e = getenv("GEECO_TC_PERSM")) { const int v = atoi(e); if (v == 1 || v == 2) per_sm = v; }
   if (const char* e = getenv("GEECO_TC_NBUF")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v * g.Nn <= 512 / per_sm) nbuf = v; }
   const int tmem_cols = next_pow2_cols(nbuf * g.Nn);
-  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - tail_bytes) / stage_bytes);
+  const int epi_t = tc_epi_template(epi, dst, dst_f32);
+  g.fast32 = tc_fast32(g, epi_t);
+  // staged TMA-store epilogue (epilogue_n32): 2 KB per epilogue warp behind the barriers
+  static const bool no_tmastore = getenv("GEECO_TC_NO_TMASTORE") != nullptr;
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  int epi_stage_bytes = 0;
+  if (g.fast32 && !no_tmastore) {
+    int rc = make_out32_tensor_map(&omap, dst, (long long)g.groups * g.imgs_per_group * g.Hd * g.Wd, g.dsx);
+    if (rc) return rc;
+    g.fast32 = 2;
+    epi_stage_bytes = 1024 + 8 * 2048;
+  }
+  int stages = (int)((SMEM_BUDGET / per_sm - 1024 - tail_bytes - epi_stage_bytes) / stage_bytes);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (const char* e = getenv("GEECO_TC_STAGES")) { const int v = atoi(e); if (v >= 3 && v <= stages) stages = v; }
   if (stages < 3) { geeco_set_error("tc_nn: stage of %d bytes does not fit 3 times", stage_bytes); return GEECO_ERR_INVALID; }
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes + epi_stage_bytes;
   int ctas = num_sms() * per_sm;
   if (const char* e = getenv("GEECO_TC_CTAS")) { const int v = atoi(e); if (v > 0) ctas = v; }
   if (max_ctas > 0 && ctas > max_ctas) ctas = max_ctas;
@@ -1682,7 +1788,7 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                      \
     GEECO_LAUNCH((kern), ctas, NN_THREADS, smem, st, g, cl, maps, amap, src, bias, mask, dst, dst_f32, epi, tiles_per_group,        \
-                                         tiles_flat, tmem_cols, stages, nbuf, bits_out);                               \
+                                         tiles_flat, tmem_cols, stages, nbuf, bits_out, omap);                         \
   } while (0)
 #define NN_LAUNCH(PIECE_, NPW_)                                                                                        \
   do {                                                                                                                 \
@@ -1692,8 +1798,6 @@ int launch_tc_nn_multi(const TcGeom* gs, const CUtensorMap* const* wmaps, int nc
     else if (epi_t == TC_EPI_RELU) NN_LAUNCH_M(PIECE_, NPW_, TC_EPI_RELU);                                             \
     else NN_LAUNCH_M(PIECE_, NPW_, EPI_GENERIC);                                                                       \
   } while (0)
-  const int epi_t = tc_epi_template(epi, dst, dst_f32);
-  g.fast32 = tc_fast32(g, epi_t);
   if (npw == 0) NN_LAUNCH(8, 0);
   else if (g.Cs == 4) { if (npw == 4) NN_LAUNCH(4, 4); else NN_LAUNCH(4, 8); }
   else { if (npw == 4) NN_LAUNCH(8, 4); else NN_LAUNCH(8, 8); }
