@@ -365,7 +365,10 @@ __device__ __forceinline__ void nn_mma_loop(const TcClasses& cl, int ncls, int t
 
 // MMA issue loop of tc_rows_kernel (see there): per tile one stage of source rows, per class `nsteps` shifted-window
 // MMAs of KSTEPS K = 16 steps against resident weight k-blocks.
-template <int KSTEPS>
+// PAIRS (forward stride-2 layer on pixel pairs): steps alternate between a full pair (kx = 0, 1: four K = 16 steps)
+// and the first pixel of the next pair (kx = 2: its 32 channels = two steps, the other half of the k-block meets zero
+// weights) -> 18 instead of 24 MMAs per tile.
+template <int KSTEPS, bool PAIRS>
 __device__ __forceinline__ void rows_mma_loop(const TcRowProg& rp, int ncls, int tiles_per_group, int tiles_flat, int stages,
                                               int nbuf, int BN, uint32_t tmem_base, uint32_t a_base_u32, uint32_t b_base_u32,
                                               int stage_bytes, int b_slot_bytes, uint64_t* full, uint64_t* empty,
@@ -387,15 +390,33 @@ __device__ __forceinline__ void rows_mma_loop(const TcRowProg& rp, int ncls, int
       tc_fence_after();
       const uint32_t d = tmem_base + buf * (uint32_t)BN;
       const int ns = rp.nsteps[c];
-      for (int st = 0; st < ns; ++st) {
-        const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
-        const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
-        if (elect_one()) {
+      if constexpr (PAIRS) {
+        for (int st = 0; st < ns; st += 2) {
+          const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
+          const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
+          const uint32_t a16n = a_stage16 + ((uint32_t)rp.a_off[c][st + 1] >> 4);
+          const uint32_t b16n = b_base16 + (uint32_t)rp.b_slot[c][st + 1] * slot16;
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < KSTEPS; ++j)
-            tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < 4; ++j)
+              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tc_mma(d, dtempl | (uint64_t)(a16n + 2 * j), dtempl | (uint64_t)(b16n + 2 * j), idesc, 1u);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+      } else {
+        for (int st = 0; st < ns; ++st) {
+          const uint32_t a16 = a_stage16 + ((uint32_t)rp.a_off[c][st] >> 4);
+          const uint32_t b16 = b_base16 + (uint32_t)rp.b_slot[c][st] * slot16;
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < KSTEPS; ++j)
+              tc_mma(d, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b16 + 2 * j), idesc, (st | j) != 0 ? 1u : 0u);
+          }
+          __syncwarp();
+        }
       }
       if (elect_one()) tc_commit(&tmem_full[buf]);
       __syncwarp();
@@ -732,12 +753,15 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
     // Unit-stride source: a window row holds the Cs real channels of one pixel, zero-filled to 64 (48 -> three K = 16
     // steps); the step count is a template argument of the loop (a runtime bound inside it cost 20 %).
     const int ksteps = g.rows == 1 ? (((g.Cs - 1) & 63) >> 4) + 1 : BK / 16;
-    if (ksteps == 3)
-      rows_mma_loop<3>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base), smem_u32(b_base),
-                       stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
+    if (g.rows == 2 && g.Cs == 32 && !(rp.nsteps[0] & 1))
+      rows_mma_loop<BK / 16, true>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base),
+                                   smem_u32(b_base), stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
+    else if (ksteps == 3)
+      rows_mma_loop<3, false>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base),
+                              smem_u32(b_base), stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
     else
-      rows_mma_loop<BK / 16>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base),
-                             smem_u32(b_base), stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
+      rows_mma_loop<BK / 16, false>(rp, ncls, tiles_per_group, tiles_flat, stages, nbuf, BN, tmem_base, smem_u32(a_base),
+                                    smem_u32(b_base), stage_bytes, b_slot_bytes, full, empty, tmem_full, tmem_empty, wfull);
   } else {
     if (lane == 0) {
       uint32_t it = 0;
@@ -1543,6 +1567,22 @@ static void fill_class(TcCls* c, const TcGeom& g) {
 static int tc_epi_template(int epi, const __nv_bfloat16* dst, const float* dst_f32) {
   if (dst && !dst_f32 && (epi == TC_EPI_MASK || epi == TC_EPI_BIAS_RELU || epi == TC_EPI_MASKBITS || epi == TC_EPI_RELU)) return epi;
   return EPI_GENERIC;
+}
+
+int tc_num_sms() { return num_sms(); }
+
+int make_tensor_map_2d_sw128(CUtensorMap* map, void* base, int inner, long long rows, long long row_stride_bytes, int box_inner,
+                             int box_rows) {
+  PFN_encodeTiled fn = encode_tiled_fn();
+  if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)row_stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { geeco_set_error("cuTensorMapEncodeTiled (2-D, %d x %lld) failed with CUresult %d", inner, rows, (int)r); return GEECO_ERR_CUDA; }
+  return GEECO_OK;
 }
 
 // 3-D tensor map over a 32-channel bf16 destination viewed as [pixels / dsx][dsx][32]: one box = 32 pixels of one

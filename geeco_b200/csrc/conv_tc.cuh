@@ -102,6 +102,17 @@ int launch_bf16_to_f32(const __nv_bfloat16* in, float* out, long long n, cudaStr
 // 2-D tensor map over a packed weight matrix [rows_total][Kpad] bf16, box = 64 x box_rows, SWIZZLE_128B
 int make_weight_tensor_map(CUtensorMap* map, const void* base, long long rows_total, int Kpad, int box_rows);
 
+// 2-D bf16 tensor map [rows][inner] with SWIZZLE_128B (inner box of 64 elements = 128 bytes)
+int make_tensor_map_2d_sw128(CUtensorMap* map, void* base, int inner, long long rows, long long row_stride_bytes, int box_inner,
+                             int box_rows);
+int tc_num_sms();             // SM count the persistent grids are sized for (honours GEECO_NUM_SMS)
+// conv1 -> conv2 forward as one kernel (conv12_fused.cu): y1 stays on chip between the layers; y1 / bits1 / bits2 may be
+// nullptr (inference writes neither y1 nor the ReLU masks)
+bool tc_conv12_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int stride1, int stride2, const TcGeom& g1);
+int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CUtensorMap* w2map, const float* bias2,
+                     long long bias2_group_stride, __nv_bfloat16* y1, unsigned short* bits1, __nv_bfloat16* y2,
+                     unsigned short* bits2, int G, int M, cudaStream_t st);
+
 TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_group, int groups);
 bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, int groups,
                    TcGeom* out, int* taps_out);

@@ -319,6 +319,18 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
       CUDA_TRY(cudaStreamWaitEvent(st, bp->ev_join_late, 0));
       bp->late_pending = false;
     }
+    if (l == 0 && !B.pair && L.grouped && c->layers[1].grouped && bp->L[1].fwd.rows == 2 && bp->L[1].fwd.wpack == 4 &&
+        tc_conv12_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], c->layers[1].Cout[0], L.stride, c->layers[1].stride, B.fwd)) {
+      // conv1 -> conv2 in one kernel: y1 stays on chip between the layers; inference does not write it at all
+      LayerPlan& L1 = c->layers[1];
+      int rc = launch_tc_conv12(src, &B.fwd_map[0], &bp->L[1].fwd_map[0], c->theta + c->params[L1.p_b[0]].offset,
+                                b_group_stride(c, L1), c->cfg.training ? (__nv_bfloat16*)L.y : nullptr,
+                                (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y, (unsigned short*)L1.mbits, G, N, st);
+      if (rc) return rc;
+      src = (const __nv_bfloat16*)L1.y;
+      l = 1;
+      continue;
+    }
     if (B.pair) {
       TcGeom pg[2] = {B.pg[0], B.pg[1]};
       pg[0].bias_group_stride = pg[1].bias_group_stride = b_group_stride(c, L);
