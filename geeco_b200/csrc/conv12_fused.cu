@@ -14,9 +14,9 @@
 //   warps 4-11   conv1 epilogue, thread = pixel of the y1 row: TMEM -> ReLU -> bf16 -> the y1 ring in shared memory in
 //                conv2's own operand layout (pixel pairs x 64 channels, SWIZZLE_128B), + the 1-bit ReLU mask (training)
 //   warps 12-15  conv2 epilogue: TMEM -> bias + ReLU -> bf16 -> y2 (+ mask bits)
-//   warp 16      MMA issuer for both layers, software-pipelined: conv1 of unit i+1 is issued before conv2 of unit i
-//   warp 17      TMA: the packed weights of both layers, once (a CTA never crosses an encoder group)
-//   warp 18      training only: one TMA tensor store per finished y1 row, ring slot -> y1 in HBM (the backward needs it)
+//   warp 16/17   MMA issuers, one per layer (independent instruction streams; the tensor pipe interleaves them)
+//   warp 18      TMA: the packed weights of both layers, once (a CTA never crosses an encoder group); training only:
+//                one TMA tensor store per finished y1 row, ring slot -> y1 in HBM (the backward needs it)
 //
 // Inference never writes y1: per unit 4 KB of x0 in, 12 KB of y2 out instead of 32 KB + 32 KB + 12 KB.
 #include "conv_tc.cuh"
@@ -40,7 +40,7 @@ constexpr int B2_BYTES = 6 * B2_SLOT;
 constexpr int S1 = 4;                          // im2col stages
 constexpr int RING = 6;                        // y1 row slots
 constexpr int NB1 = 8, NB2 = 2;                // accumulator buffers: conv1 (32 columns each), conv2 (64-column stride)
-constexpr int THREADS = 19 * 32;
+constexpr int THREADS = 19 * 32;                // 4 producer, 8 + 4 epilogue, 2 MMA warps, 1 TMA warp
 constexpr int SMEM_BYTES = 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024;
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
@@ -122,7 +122,7 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   }
   fence_proxy_async();
   if (warp == 16) tmem_alloc(tmem_ptr_s, 512);
-  if (warp == 17 && lane == 0) { tma_prefetch_desc(&w1map); tma_prefetch_desc(&w2map); if (store_y1) tma_prefetch_desc(&y1map); }
+  if (warp == 18 && lane == 0) { tma_prefetch_desc(&w1map); tma_prefetch_desc(&w2map); if (store_y1) tma_prefetch_desc(&y1map); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -248,89 +248,93 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
       }
     }
   } else if (warp == 16) {
-    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
-    const uint32_t idesc1 = make_idesc_bf16(128, C1, 0, 0), idesc2 = make_idesc_bf16(128, C2, 0, 0);
+    // ===================== conv1 MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    // Two issuing warps, one per layer: a single warp issuing both layers was the bound of the first version (ncu: every
+    // other role waiting on it, the tensor pipe 38 % busy, ~400 dependent instructions per unit in one warp).
+    const uint32_t idesc1 = make_idesc_bf16(128, C1, 0, 0);
     const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
-    const uint32_t a1_16 = smem_u32(a1) >> 4, b1_16 = smem_u32(b1) >> 4, b2_16 = smem_u32(b2) >> 4, ring16 = smem_u32(ring) >> 4;
+    const uint32_t a1_16 = smem_u32(a1) >> 4, b1_16 = smem_u32(b1) >> 4;
     mbar_wait(w_full, 0);
     tc_fence_after();
-    uint32_t s = 0, sphase = 0, tile = 0, q = 0, i2 = 0;
-    int pq0 = -1, pq1 = -1, pq2 = -1, last_q2 = -1;               // ring rows of the unit whose conv2 is pending
-    for (int u = u_lo; u <= u_hi; ++u) {
-      int nq0 = -1, nq1 = -1, nq2 = -1;
-      if (u < u_hi) {
-        // ---- conv1 of the rows unit u adds
-        int r_begin, r_end;
-        unit_rows(u, u_lo, r_begin, r_end);
-        const bool first = r_begin == 2 * (u & 127);
-        const int nrows = r_end - r_begin + 1;
-        if (first) { nq0 = (int)q; nq1 = (int)q + 1; nq2 = nrows == 3 ? (int)q + 2 : -1; }
-        else { nq0 = last_q2; nq1 = (int)q; nq2 = nrows == 2 ? (int)q + 1 : -1; }
-        last_q2 = nq2;
-        q += (uint32_t)nrows;
-        for (int tl = 0; tl < 2 * nrows; ++tl, ++tile) {
-          const uint32_t buf = tile % NB1, tuse = tile / NB1;
-          mbar_wait(&t1_empty[buf], (tuse & 1u) ^ 1u);
-          mbar_wait(&a_full[s], sphase);
-          tc_fence_after();
-          const uint32_t a16 = a1_16 + s * (uint32_t)(A1_BYTES >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j)      // K = 36 taps x channels + the bias column: three K = 16 steps
-              tc_mma(tmem_base + buf * 32u, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b1_16 + 2 * j), idesc1, j != 0 ? 1u : 0u);
-            tc_commit(&a_empty[s]);
-            tc_commit(&t1_full[buf]);
-          }
-          __syncwarp();
-          if (++s == S1) { s = 0; sphase ^= 1u; }
-        }
-      }
-      if (u > u_lo) {
-        // ---- conv2 of unit u - 1 on the ring rows pq0, pq1, pq2
-        const uint32_t buf = i2 % NB2, use = i2 / NB2;
-        const int nky = pq2 >= 0 ? 3 : 2;
-        mbar_wait(&t2_empty[buf], (use & 1u) ^ 1u);
-        for (int ky = 0; ky < nky; ++ky) {
-          const uint32_t qq = (uint32_t)(ky == 0 ? pq0 : (ky == 1 ? pq1 : pq2));
-          mbar_wait(&y_full[qq % RING], (qq / RING) & 1u);
-        }
+    uint32_t s = 0, sphase = 0, buf = 0, bphase = 0;
+    for (int u = u_lo; u < u_hi; ++u) {
+      int r_begin, r_end;
+      unit_rows(u, u_lo, r_begin, r_end);
+      const int ntiles = 2 * (r_end - r_begin + 1);
+      for (int tl = 0; tl < ntiles; ++tl) {
+        mbar_wait(&t1_empty[buf], bphase ^ 1u);
+        mbar_wait(&a_full[s], sphase);
         tc_fence_after();
-        const uint32_t d = tmem_base + 256u + buf * 64u;
-        for (int ky = 0; ky < nky; ++ky) {
-          const uint32_t qq = (uint32_t)(ky == 0 ? pq0 : (ky == 1 ? pq1 : pq2));
-          const uint32_t sa16 = ring16 + (qq % RING) * (uint32_t)(SLOT_BYTES >> 4);
-          const uint32_t bb16 = b2_16 + (uint32_t)(ky * 2) * (uint32_t)(B2_SLOT >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)      // pixel pair ox: kx = 0, 1 (64 channels of the pair)
-              tc_mma(d, dtempl | (uint64_t)(sa16 + 2 * j), dtempl | (uint64_t)(bb16 + 2 * j), idesc2, (ky | j) != 0 ? 1u : 0u);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)      // first pixel of pair ox + 1: kx = 2 (its 32 channels)
-              tc_mma(d, dtempl | (uint64_t)(sa16 + 8 + 2 * j), dtempl | (uint64_t)(bb16 + (B2_SLOT >> 4) + 2 * j), idesc2, 1u);
-          }
-          __syncwarp();
-        }
+        const uint32_t a16 = a1_16 + s * (uint32_t)(A1_BYTES >> 4);
         if (elect_one()) {
-          tc_commit(&t2_full[buf]);
-          tc_commit(&y_empty[(uint32_t)pq0 % RING]);
-          tc_commit(&y_empty[(uint32_t)pq1 % RING]);
-          // the third row is the next unit's first unless the range ends here (a new image starts with its own row 0,
-          // and then this unit had no third row)
-          if (pq2 >= 0 && u == u_hi) tc_commit(&y_empty[(uint32_t)pq2 % RING]);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)      // K = 36 taps x channels + the bias column: three K = 16 steps
+            tc_mma(tmem_base + buf * 32u, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b1_16 + 2 * j), idesc1, j != 0 ? 1u : 0u);
+          tc_commit(&a_empty[s]);
+          tc_commit(&t1_full[buf]);
         }
         __syncwarp();
-        ++i2;
+        if (++s == S1) { s = 0; sphase ^= 1u; }
+        if (++buf == NB1) { buf = 0; bphase ^= 1u; }
       }
-      pq0 = nq0; pq1 = nq1; pq2 = nq2;
     }
   } else if (warp == 17) {
+    // ===================== conv2 MMA issuer: unit u on the ring rows q0, q1, q2 =====================
+    const uint32_t idesc2 = make_idesc_bf16(128, C2, 0, 0);
+    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+    const uint32_t b2_16 = smem_u32(b2) >> 4, ring16 = smem_u32(ring) >> 4;
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    uint32_t q = 0, buf = 0, bphase = 0;
+    int last_q2 = -1;
+    for (int u = u_lo; u < u_hi; ++u) {
+      int r_begin, r_end;
+      unit_rows(u, u_lo, r_begin, r_end);
+      const bool first = r_begin == 2 * (u & 127);
+      const int nrows = r_end - r_begin + 1;
+      int q0, q1, q2;
+      if (first) { q0 = (int)q; q1 = (int)q + 1; q2 = nrows == 3 ? (int)q + 2 : -1; }
+      else { q0 = last_q2; q1 = (int)q; q2 = nrows == 2 ? (int)q + 1 : -1; }
+      last_q2 = q2;
+      q += (uint32_t)nrows;
+      const int nky = q2 >= 0 ? 3 : 2;
+      mbar_wait(&t2_empty[buf], bphase ^ 1u);
+      const uint32_t d = tmem_base + 256u + buf * 64u;
+      for (int ky = 0; ky < nky; ++ky) {
+        const uint32_t qq = (uint32_t)(ky == 0 ? q0 : (ky == 1 ? q1 : q2));
+        mbar_wait(&y_full[qq % RING], (qq / RING) & 1u);
+        tc_fence_after();
+        const uint32_t sa16 = ring16 + (qq % RING) * (uint32_t)(SLOT_BYTES >> 4);
+        const uint32_t bb16 = b2_16 + (uint32_t)(ky * 2) * (uint32_t)(B2_SLOT >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)      // pixel pair ox: kx = 0, 1 (64 channels of the pair)
+            tc_mma(d, dtempl | (uint64_t)(sa16 + 2 * j), dtempl | (uint64_t)(bb16 + 2 * j), idesc2, (ky | j) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)      // first pixel of pair ox + 1: kx = 2 (its 32 channels)
+            tc_mma(d, dtempl | (uint64_t)(sa16 + 8 + 2 * j), dtempl | (uint64_t)(bb16 + (B2_SLOT >> 4) + 2 * j), idesc2, 1u);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        tc_commit(&t2_full[buf]);
+        tc_commit(&y_empty[(uint32_t)q0 % RING]);
+        tc_commit(&y_empty[(uint32_t)q1 % RING]);
+        // the third row is the next unit's first unless the range ends here (a new image starts with its own row 0,
+        // and then this unit had no third row)
+        if (q2 >= 0 && u + 1 == u_hi) tc_commit(&y_empty[(uint32_t)q2 % RING]);
+      }
+      __syncwarp();
+      if (++buf == NB2) { buf = 0; bphase ^= 1u; }
+    }
+  } else {
+    // ===================== TMA warp: the weights of both layers once, then (training) the y1 stores =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(w_full, (uint32_t)(B1_BYTES + B2_BYTES));
       tma_load_2d(smem_u32(b1), &w1map, w_full, 0, group * C1);
       for (int sl = 0; sl < 6; ++sl) tma_load_2d(smem_u32(b2 + sl * B2_SLOT), &w2map, w_full, sl * 64, group * C2);
     }
-  } else {
-    // ===================== y1 store warp (training): ring slot -> HBM, one TMA tensor store per row =====================
+    // ring slot -> y1 in HBM, one TMA tensor store per finished row
     if (store_y1 && lane == 0) {
       uint32_t q = 0;
       int prev_slot = -1;
