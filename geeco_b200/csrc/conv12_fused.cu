@@ -14,7 +14,8 @@
 //   warps 4-11   conv1 epilogue, thread = pixel of the y1 row: TMEM -> ReLU -> bf16 -> the y1 ring in shared memory in
 //                conv2's own operand layout (pixel pairs x 64 channels, SWIZZLE_128B), + the 1-bit ReLU mask (training)
 //   warps 12-15  conv2 epilogue: TMEM -> bias + ReLU -> bf16 -> y2 (+ mask bits)
-//   warp 16/17   MMA issuers, one per layer (independent instruction streams; the tensor pipe interleaves them)
+//   warp 16/19   conv1 MMA issuers (left / right half rows), warp 17 conv2 MMA issuer: independent instruction streams,
+//                the tensor pipe interleaves them
 //   warp 18      TMA: the packed weights of both layers, once (a CTA never crosses an encoder group); training only:
 //                one TMA tensor store per finished y1 row, ring slot -> y1 in HBM (the backward needs it)
 //
@@ -40,8 +41,9 @@ constexpr int B2_BYTES = 6 * B2_SLOT;
 constexpr int S1 = 4;                          // im2col stages
 constexpr int RING = 6;                        // y1 row slots
 constexpr int NB1 = 8, NB2 = 2;                // accumulator buffers: conv1 (32 columns each), conv2 (64-column stride)
-constexpr int THREADS = 19 * 32;                // 4 producer, 8 + 4 epilogue, 2 MMA warps, 1 TMA warp
-constexpr int SMEM_BYTES = 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024;
+constexpr int THREADS = 20 * 32;                // 4 producer, 8 + 4 epilogue, 3 MMA warps, 1 TMA warp
+constexpr int Y2_STAGE = 32 * C2 * 2;           // 3 KB: the 32 pixels x 48 channels one conv2-epilogue warp stores per unit
+constexpr int SMEM_BYTES = 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024 + 4 * Y2_STAGE;
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -51,6 +53,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                    reinterpret_cast<uint64_t>(map)),
                "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
+}
+// contiguous shared -> global bulk copy (bulk async group of the issuing thread)
+__device__ __forceinline__ void bulk_store(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
@@ -95,6 +101,7 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   uint64_t* w_full = t2_empty + NB2;       // [1]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(w_full + 1);
   float* bias2_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  uint8_t* y2_stage = reinterpret_cast<uint8_t*>(bars) + 1024;     // [4 warps][3 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = blockIdx.x / a.cpg, lb = blockIdx.x - group * a.cpg;
@@ -217,6 +224,7 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
     const int quad = warp & 3;
     const int ox = quad * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + 256u;
+    const uint32_t stage_u32 = smem_u32(y2_stage + quad * Y2_STAGE);
     uint32_t i2 = 0;
     for (int u = u_lo; u < u_hi; ++u, ++i2) {
       const uint32_t buf = i2 % NB2, use = i2 / NB2;
@@ -233,10 +241,18 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
       for (int i = 0; i < 24; ++i)
         o[i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]) + bias2_s[2 * i], __uint_as_float(v[2 * i + 1]) + bias2_s[2 * i + 1]);
       const long long p2 = ((gimg0 + (u >> 7)) * 128 + (u & 127)) * 128 + ox;
-      __nv_bfloat16* d = a.y2 + p2 * C2;
-      stg256(d, o);
-      stg256(d + 16, o + 8);
-      stg256(d + 32, o + 16);
+      // the warp's 32 pixels are 3 KB of contiguous y2: staged in shared memory (linear) and written by ONE bulk copy
+      // instead of 96 per-lane 32-byte sectors (the LSU wavefronts were the busiest unit of this kernel: 70 %)
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 6; ++j) st_shared_v4(stage_u32 + (uint32_t)lane * 96u + (uint32_t)j * 16u, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(a.y2 + (p2 - lane) * C2, stage_u32, (uint32_t)Y2_STAGE);
+        bulk_commit();
+      }
       if (a.bits2) {
 #pragma unroll
         for (int ck = 0; ck < 3; ++ck) {
@@ -247,8 +263,11 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
         }
       }
     }
-  } else if (warp == 16) {
-    // ===================== conv1 MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    if (lane == 0) bulk_wait0();                                   // global writes performed before the CTA retires
+  } else if (warp == 16 || warp == 19) {
+    // ===================== conv1 MMA issuers (whole warp runs the loop, one elected lane issues) =====================
+    // warp 16 issues the left half rows (even tiles), warp 19 the right ones: one warp spent ~2000 of the 2550 cycles
+    // of a unit on its four tiles (dependent uniform-datapath instructions, ~9 cycles each)
     // Two issuing warps, one per layer: a single warp issuing both layers was the bound of the first version (ncu: every
     // other role waiting on it, the tensor pipe 38 % busy, ~400 dependent instructions per unit in one warp).
     const uint32_t idesc1 = make_idesc_bf16(128, C1, 0, 0);
@@ -256,11 +275,13 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
     const uint32_t a1_16 = smem_u32(a1) >> 4, b1_16 = smem_u32(b1) >> 4;
     mbar_wait(w_full, 0);
     tc_fence_after();
-    uint32_t s = 0, sphase = 0, buf = 0, bphase = 0;
+    // tile i uses stage i % S1 and buffer i % NB1 (both even counts): this warp's tiles are i = par, par + 2, ...
+    const uint32_t par = warp == 16 ? 0u : 1u;
+    uint32_t s = par, sphase = 0, buf = par, bphase = 0;
     for (int u = u_lo; u < u_hi; ++u) {
       int r_begin, r_end;
       unit_rows(u, u_lo, r_begin, r_end);
-      const int ntiles = 2 * (r_end - r_begin + 1);
+      const int ntiles = r_end - r_begin + 1;                    // of this warp: one per row
       for (int tl = 0; tl < ntiles; ++tl) {
         mbar_wait(&t1_empty[buf], bphase ^ 1u);
         mbar_wait(&a_full[s], sphase);
@@ -274,8 +295,8 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
           tc_commit(&t1_full[buf]);
         }
         __syncwarp();
-        if (++s == S1) { s = 0; sphase ^= 1u; }
-        if (++buf == NB1) { buf = 0; bphase ^= 1u; }
+        if ((s += 2) >= S1) { s -= S1; sphase ^= 1u; }
+        if ((buf += 2) >= NB1) { buf -= NB1; bphase ^= 1u; }
       }
     }
   } else if (warp == 17) {
