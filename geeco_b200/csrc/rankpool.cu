@@ -239,6 +239,9 @@ __device__ __forceinline__ void store_unit(OutT* dst, const float* e) {
 // division; a lookup per byte replaces ~60 divisions per 4-pixel unit (the uint8 kernel was compute-bound on them).
 template <typename InT> struct FrameLoad;
 template <> struct FrameLoad<float> {
+  typedef float4 raw_t;
+  static __device__ __forceinline__ raw_t raw(const float* base, long long i4) { return ldg_stream(reinterpret_cast<const float4*>(base) + i4); }
+  static __device__ __forceinline__ float4 cvt(const raw_t& r) { return r; }
   static __device__ __forceinline__ float4 at(const float* base, long long i4, const float*) {
     return ldg_stream(reinterpret_cast<const float4*>(base) + i4);
   }
@@ -248,10 +251,24 @@ template <> struct FrameLoad<float> {
     return __ldg(reinterpret_cast<const float4*>(base) + i4);
   }
 };
+// float(b) / 255.0f, correctly rounded, without a division or a table: q = b * fl(1/255), then one exact-residual
+// correction step q + (b - 255 q) * fl(1/255).  Checked exhaustively against the IEEE division for b = 0..255 (all equal;
+// the bare product differs for 126 of them).  The 256-entry shared-memory table this replaces made the uint8 kernel
+// LDS-bound: 1.4 M random lookups per sample, 3-4-way bank conflicts (1.07 ms per 1024-environment policy chunk).
+__device__ __forceinline__ float u8_unit(unsigned int b) {
+  const float f = (float)b, rc = 0x1.010102p-8f;
+  const float q = __fmul_rn(f, rc);
+  return __fmaf_rn(__fmaf_rn(-q, 255.f, f), rc, q);
+}
 template <> struct FrameLoad<unsigned char> {
-  static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4, const float* lut) {
+  typedef unsigned int raw_t;
+  static __device__ __forceinline__ raw_t raw(const unsigned char* base, long long i4) { return __ldg(reinterpret_cast<const unsigned int*>(base) + i4); }
+  static __device__ __forceinline__ float4 cvt(const raw_t& w) {
+    return make_float4(u8_unit(w & 255u), u8_unit((w >> 8) & 255u), u8_unit((w >> 16) & 255u), u8_unit(w >> 24));
+  }
+  static __device__ __forceinline__ float4 at(const unsigned char* base, long long i4, const float*) {
     const unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(base) + i4);
-    return make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
+    return make_float4(u8_unit(w & 255u), u8_unit((w >> 8) & 255u), u8_unit((w >> 16) & 255u), u8_unit(w >> 24));
   }
   static __device__ __forceinline__ float4 at_l1(const unsigned char* base, long long i4, const float* lut) { return at(base, i4, lut); }
 };
@@ -299,26 +316,30 @@ __global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
   // channel-padded copy of the current frame needs whole pixels and is written in pass 2, which re-reads cur anyway.
   {
     const long long f_lo = lo * C, f_hi = hi * C;
-    constexpr int U = K >= 6 ? 1 : 2;                      // float4 positions per thread in flight
+    // float4 positions per thread in flight (six raw uint8 words per stream instead of two were measured slower:
+    // 1.26 vs 0.97 ms per 1024-environment chunk)
+    constexpr int U = K >= 6 ? 1 : 2;
+    typedef typename FrameLoad<InT>::raw_t raw_t;
     for (long long f0 = f_lo + threadIdx.x; f0 < f_hi; f0 += (long long)U * RP_THREADS) {
-      float4 v[U][K], t[U];
+      raw_t v[U][K], t[U];
 #pragma unroll
       for (int q = 0; q < U; ++q) {
         const long long f = f0 + (long long)q * RP_THREADS;
         if (f < f_hi) {
 #pragma unroll
-          for (int k = 0; k < K; ++k) v[q][k] = FrameLoad<InT>::at(fk[k], f, s_lut);
-          t[q] = FrameLoad<InT>::at(tbase, f, s_lut);
+          for (int k = 0; k < K; ++k) v[q][k] = FrameLoad<InT>::raw(fk[k], f);
+          t[q] = FrameLoad<InT>::raw(tbase, f);
         }
       }
 #pragma unroll
       for (int q = 0; q < U; ++q) {
         const long long f = f0 + (long long)q * RP_THREADS;
         if (f < f_hi) {
-          float4 acc = f4_scale(al.a[0], v[q][0]);
+          float4 acc = f4_scale(al.a[0], FrameLoad<InT>::cvt(v[q][0]));
+          float4 last = FrameLoad<InT>::cvt(v[q][K - 1]);
 #pragma unroll
-          for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], v[q][k]);
-          const float4 dd = f4_axpy(f4_scale(-0.5f, v[q][K - 1]), 0.5f, t[q]);
+          for (int k = 1; k < K; ++k) acc = f4_axpy(acc, al.a[k], k == K - 1 ? last : FrameLoad<InT>::cvt(v[q][k]));
+          const float4 dd = f4_axpy(f4_scale(-0.5f, last), 0.5f, FrameLoad<InT>::cvt(t[q]));
           sd0[f - f_lo] = acc;
           f4_minmax(acc, mn0, mx0);
           f4_minmax(dd, mn1, mx1);
