@@ -957,6 +957,12 @@ extern "C" int geeco_ring_push(void* ring, const void* frame, const uint8_t* fre
   return launch_ring_push(ring, frame, fresh, N, K, row_bytes, slot, (cudaStream_t)stream);
 }
 
+extern "C" int geeco_profile_kernel(geeco_ctx* c, const char* name, void* stream) {
+  if (!c || !c->bound || !name) { geeco_set_error("profile_kernel: bad arguments"); return GEECO_ERR_INVALID; }
+  if (c->cfg.precision != GEECO_BF16) { geeco_set_error("profile_kernel: bf16 contexts only"); return GEECO_ERR_INVALID; }
+  return profile_kernel_bf16(c, name, (cudaStream_t)stream);
+}
+
 extern "C" int geeco_debug_buffer(const geeco_ctx* c, const char* name, void** ptr, int64_t* numel, int32_t* dtype) {
   if (!c || !c->bound || !name || !ptr || !numel || !dtype) { geeco_set_error("debug_buffer: bad arguments"); return GEECO_ERR_INVALID; }
   const geeco_config& cfg = c->cfg;

@@ -78,4 +78,5 @@ void free_bf16(geeco_ctx* c);
 int repack_fork_bf16(geeco_ctx* c, cudaStream_t st);     // weight repack on a side stream, ordered after `st` so far
 int repack_join_bf16(geeco_ctx* c, cudaStream_t st);     // `st` waits for it
 int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st);
+int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st);
 int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st);

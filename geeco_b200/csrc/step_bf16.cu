@@ -302,6 +302,36 @@ static int repack_dgrad_fork(geeco_ctx* c, cudaStream_t st) {
   return GEECO_OK;
 }
 
+// conv1 -> conv2 as one kernel when the two layers have the shape it is written for; returns 1 if it ran, 0 if the
+// separate kernels have to, < 0 on error
+static int try_conv12(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
+  LayerPlan& L = c->layers[0];
+  LayerPlan& L1 = c->layers[1];
+  Bf16Layer& B = bp->L[0];
+  if (B.pair || !L.grouped || !L1.grouped || bp->L[1].fwd.rows != 2 || bp->L[1].fwd.wpack != 4 ||
+      !tc_conv12_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L1.Cout[0], L.stride, L1.stride, B.fwd))
+    return 0;
+  // y1 stays on chip between the layers; inference does not write it at all
+  int rc = launch_tc_conv12((const __nv_bfloat16*)c->x0, &B.fwd_map[0], &bp->L[1].fwd_map[0],
+                            c->theta + c->params[L1.p_b[0]].offset, b_group_stride(c, L1),
+                            c->cfg.training ? (__nv_bfloat16*)L.y : nullptr, (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y,
+                            (unsigned short*)L1.mbits, c->G, c->M, st);
+  return rc ? -rc : 1;
+}
+
+// profiling entry (geeco_profile_kernel): one kernel of the bf16 step on the buffers the last step left behind
+int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!bp) { geeco_set_error("profile_kernel: bf16 plan missing"); return GEECO_ERR_STATE; }
+  if (!strcmp(name, "conv12")) {
+    const int r = try_conv12(c, bp, st);
+    if (r == 0) { geeco_set_error("profile_kernel: the fused conv1->conv2 kernel does not cover this configuration"); return GEECO_ERR_INVALID; }
+    return r < 0 ? -r : GEECO_OK;
+  }
+  geeco_set_error("profile_kernel: unknown kernel '%s'", name);
+  return GEECO_ERR_INVALID;
+}
+
 int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
   if (!bp) { geeco_set_error("bf16 plan missing"); return GEECO_ERR_STATE; }
@@ -319,17 +349,10 @@ int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st) {
       CUDA_TRY(cudaStreamWaitEvent(st, bp->ev_join_late, 0));
       bp->late_pending = false;
     }
-    if (l == 0 && !B.pair && L.grouped && c->layers[1].grouped && bp->L[1].fwd.rows == 2 && bp->L[1].fwd.wpack == 4 &&
-        tc_conv12_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], c->layers[1].Cout[0], L.stride, c->layers[1].stride, B.fwd)) {
-      // conv1 -> conv2 in one kernel: y1 stays on chip between the layers; inference does not write it at all
-      LayerPlan& L1 = c->layers[1];
-      int rc = launch_tc_conv12(src, &B.fwd_map[0], &bp->L[1].fwd_map[0], c->theta + c->params[L1.p_b[0]].offset,
-                                b_group_stride(c, L1), c->cfg.training ? (__nv_bfloat16*)L.y : nullptr,
-                                (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y, (unsigned short*)L1.mbits, G, N, st);
-      if (rc) return rc;
-      src = (const __nv_bfloat16*)L1.y;
-      l = 1;
-      continue;
+    if (l == 0) {
+      const int r = try_conv12(c, bp, st);
+      if (r < 0) return -r;
+      if (r > 0) { src = (const __nv_bfloat16*)c->layers[1].y; l = 1; continue; }
     }
     if (B.pair) {
       TcGeom pg[2] = {B.pg[0], B.pg[1]};

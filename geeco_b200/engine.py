@@ -462,6 +462,10 @@ class Engine(object):
     return d
 
   # ------------------------------------------------------------------ debugging
+  def profile_kernel(self, name):
+    """Runs one kernel of the bf16 step again on the buffers of the last step ('conv12': fused conv1 -> conv2)."""
+    _lib.check(self.lib.geeco_profile_kernel(self._ctx, name.encode(), self._stream()))
+
   def debug_buffer(self, name):
     ptr, cnt, dt = C.c_void_p(), C.c_int64(), C.c_int32()
     _lib.check(self.lib.geeco_debug_buffer(self._ctx, name.encode(), C.byref(ptr), C.byref(cnt), C.byref(dt)))

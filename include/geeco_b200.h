@@ -235,6 +235,10 @@ int geeco_ring_push(void* ring, const void* frame, const uint8_t* fresh, int32_t
 /* internal activation buffers by name ("x0", "y1".."y8", "g1".."g8", "state", "gates", "dstate", ...);
  * dtype: 0 = f32, 1 = bf16 */
 int geeco_debug_buffer(const geeco_ctx* ctx, const char* name, void** ptr, int64_t* numel, int32_t* dtype);
+/* runs ONE kernel of the bf16 step again on the buffers the last geeco_forward / geeco_train_step left behind, so that a
+ * benchmark can time it alone with events on `stream`.  name: "conv12" = the fused conv1 -> conv2 forward
+ * (graph.py:76-115, first two layers of conv_encoder). */
+int geeco_profile_kernel(geeco_ctx* ctx, const char* name, void* stream);
 /* number of kernel launches enqueued by this library since the last call with reset != 0 */
 int64_t geeco_launch_count(int32_t reset);
 
