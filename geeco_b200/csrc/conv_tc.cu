@@ -1445,6 +1445,8 @@ static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom&
   return GEECO_OK;
 }
 
+int tc_make_row_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int pw) { return make_act_tensor_map(map, base, g, pw); }
+
 static void same_pad_tc(int in, int s, int* out, int* before) {
   *out = (in + s - 1) / s;
   int total = (*out - 1) * s + 3 - in;

@@ -113,6 +113,16 @@ int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CU
                      long long bias2_group_stride, __nv_bfloat16* y1, unsigned short* bits1, __nv_bfloat16* y2,
                      unsigned short* bits2, int G, int M, cudaStream_t st);
 
+// conv2 data gradient -> conv1 weight gradient as one kernel (conv21_bwd_fused.cu): dL/d(pre-activation of conv1) stays
+// on chip.  dg = the four parity classes of the stride-2 layer in (py, px) order, wmaps their packed-weight maps.
+bool tc_bwd21_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int stride1, int stride2, const TcGeom* dg, int ncls);
+long long tc_bwd21_partial_floats();
+int launch_tc_bwd21(const __nv_bfloat16* G2, const TcGeom* dg, const CUtensorMap* const* wmaps, const unsigned short* bits1,
+                    const __nv_bfloat16* x0, float* partial, long long partial_cap, float* dW1, float* dbias1, int Cw,
+                    long long dw_group_stride, long long dbias_group_stride, int G, int M, cudaStream_t st);
+// 5-D tensor map over the source of geometry g whose box is one row of `pw` pixels x 64 channels (row-resident kernels)
+int tc_make_row_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int pw);
+
 TcGeom tc_fwd_geom(int H, int W, int Cs, int Cout, int stride, int imgs_per_group, int groups);
 bool tc_dgrad_geom(int H, int W, int Cin, int Cout, int stride, int py, int px, int imgs_per_group, int groups,
                    TcGeom* out, int* taps_out);

@@ -120,6 +120,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
       }
     }
   }
+  if (tc_bwd21_partial_floats() > cap) cap = tc_bwd21_partial_floats();
   bp->partial_cap = cap;
   bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
   bp->jobs_dev[0] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
@@ -319,6 +320,25 @@ static int try_conv12(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
   return rc ? -rc : 1;
 }
 
+// conv2 data gradient -> conv1 weight gradient as one kernel when the two layers have the shape it is written for (G1 is
+// then never written); returns 1 if it ran, 0 if the separate kernels have to, < 0 on error
+static int try_bwd21(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
+  LayerPlan& L0 = c->layers[0];
+  LayerPlan& L1 = c->layers[1];
+  Bf16Layer& B0 = bp->L[0];
+  Bf16Layer& B1 = bp->L[1];
+  if (B0.pair || !L0.grouped || !L1.grouped || !L0.mbits || L0.Cin_real > 4 ||
+      !tc_bwd21_supported(L0.Hin, L0.Hin, L0.Cin_pad, L0.Cout[0], L1.Cout[0], L0.stride, L1.stride, B1.dg, B1.n_classes))
+    return 0;
+  const CUtensorMap* dmaps[4];
+  for (int ci = 0; ci < 4; ++ci) dmaps[ci] = &B1.dg_map[ci][0];
+  int rc = launch_tc_bwd21((const __nv_bfloat16*)L1.g, B1.dg, dmaps, (const unsigned short*)L0.mbits, (const __nv_bfloat16*)c->x0,
+                           bp->partial, bp->partial_cap, c->grad + c->params[L0.p_w[0]].offset,
+                           c->grad + c->params[L0.p_b[0]].offset, L0.Cin_real, w_group_stride(c, L0), b_group_stride(c, L0),
+                           c->G, c->M, st);
+  return rc ? -rc : 1;
+}
+
 // profiling entry (geeco_profile_kernel): one kernel of the bf16 step on the buffers the last step left behind
 int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st) {
   Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
@@ -326,6 +346,11 @@ int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st) {
   if (!strcmp(name, "conv12")) {
     const int r = try_conv12(c, bp, st);
     if (r == 0) { geeco_set_error("profile_kernel: the fused conv1->conv2 kernel does not cover this configuration"); return GEECO_ERR_INVALID; }
+    return r < 0 ? -r : GEECO_OK;
+  }
+  if (!strcmp(name, "bwd21")) {
+    const int r = try_bwd21(c, bp, st);
+    if (r == 0) { geeco_set_error("profile_kernel: the fused conv2-dgrad -> conv1-wgrad kernel does not cover this configuration"); return GEECO_ERR_INVALID; }
     return r < 0 ? -r : GEECO_OK;
   }
   geeco_set_error("profile_kernel: unknown kernel '%s'", name);
@@ -428,6 +453,12 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
                                c->grad + c->params[L.p_b[e]].offset, bp->partial, bp->partial_cap, wstride, bstride, st);
       if (rc) return rc;
       if (l == 0) continue;
+      if (l == 1 && llo == 0) {
+        // conv2's data gradient feeds conv1's weight gradient on chip; layer 0 is then done
+        const int r = try_bwd21(c, bp, st);
+        if (r < 0) return -r;
+        if (r > 0) { llo = 1; continue; }
+      }
       {
         TcGeom dgs[4];
         const CUtensorMap* dmaps[4];
