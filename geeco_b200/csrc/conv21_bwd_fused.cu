@@ -19,12 +19,15 @@
 //   epilogue        thread = ox; set py (4 warps) owns the classes (py, 0) and (py, 1): TMEM -> ReLU mask of y1 (1 bit
 //                   per value, written by the forward) -> bf16 -> the G1 tile of G1 row 2q+py: row ox = the pixel pair
 //                   (2ox, 2ox+1) x 32 channels = 128 bytes, SWIZZLE_128B, i.e. the MN-major A operand of the
-//                   weight-gradient GEMM (M = 64 = (px, co)).
-//   producers       im2col of x0 on pixel pairs for the same G1 row: row ox = the 3 x 4 pixel window around the pair
-//                   (48 values + a constant 1.0 for the bias gradient), 3 cp.async per window row (16 + 8 + 8 bytes).
-//   weight gradient D2[(px, co)][(ky, cx, ch)] += G1tile^T x window tile, M = 64, N = 64, K = 128 pairs = 8 MMAs per G1
-//                   row; kx = cx - px.  One accumulator for the whole CTA, written once at the end as a 16 KB partial;
-//                   a small kernel sums the partials of a group in a fixed order (deterministic).
+//                   weight-gradient GEMM; the tiles of py = 0 and py = 1 are its two 64-row M atoms.
+//   producers       im2col of x0 for BOTH G1 rows of the unit: row ox = the 4 x 4 pixel window (x0 rows 2q-1 .. 2q+2,
+//                   columns 2ox-1 .. 2ox+2) x 4 channels = 64 values = 128 bytes, 3 cp.async per window row (16 + 8 + 8
+//                   bytes): every tap of every class is one of its columns.
+//   weight gradient D2[(py, px, co)][(wy, cx, ch)] += [G1 tile py=0 | G1 tile py=1]^T x window tile: M = 128, N = 64,
+//                   K = 128 pairs = 8 MMAs per unit; ky = wy - py, kx = cx - px.  The bias gradient is a second MMA of the
+//                   same A against a constant tile whose first column is 1.0 (N = 16).  One accumulator for the whole
+//                   CTA, written once at the end as a 33 KB partial; a small kernel sums the partials of a group in a
+//                   fixed order (deterministic).
 //
 //   warps 0-3 producers, 4-11 epilogue (two sets), 12 data-gradient MMA issuer (+ TMEM), 13 weight-gradient MMA issuer,
 //   14 TMA (weights once, one G2 row per unit).
@@ -46,12 +49,14 @@ constexpr int RG = 4;                          // G2 row ring
 constexpr int W_SLOT = C1 * 128;               // one (class, tap) k-block of the packed data-gradient weights: 32 x 64
 constexpr int W_BYTES = 9 * W_SLOT;
 constexpr int TILE = 128 * 128;                // G1 tile / window tile: 128 pixel pairs x 128 bytes
-constexpr int NG1 = 2;                         // G1 tiles: one per epilogue set
-constexpr int NX = 4;                          // window tiles in flight
+constexpr int NG1 = 2;                         // G1 buffers: [py = 0 | py = 1] tile pairs (the two M atoms of one A operand)
+constexpr int NX = 3;                          // window tiles in flight
 constexpr int NB = 2;                          // data-gradient accumulators (128 columns each)
 constexpr int THREADS = 15 * 32;
-constexpr int ACC_COL = 256;                   // weight-gradient accumulator: TMEM columns [256, 320)
-constexpr int SMEM_BYTES = 1024 + W_BYTES + RG * ROW_BYTES + NG1 * TILE + NX * TILE + 1024;
+constexpr int ACC_COL = 256;                   // weight-gradient accumulator: TMEM columns [256, 320), bias gradient [320, 336)
+constexpr int ONES_BYTES = 16 * 128;           // constant B tile of the bias-gradient MMA: 16 K rows, column 0 = 1.0
+constexpr int PART_FLOATS = 128 * 64 + 128;    // per-CTA partial: D2 and the bias column
+constexpr int SMEM_BYTES = 1024 + W_BYTES + RG * ROW_BYTES + NG1 * 2 * TILE + NX * TILE + ONES_BYTES + 1024;
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -60,7 +65,7 @@ __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, ui
 struct B21Args {
   const __nv_bfloat16* x0;        // [G*M][256][256][4]
   const uint2* bits1;             // ReLU mask of y1: one 32-bit word per pixel, read as pixel pairs
-  float* partial;                 // [CTAs][64][64]
+  float* partial;                 // [CTAs][PART_FLOATS]
   int M;                          // images per encoder group
   int cpg;                        // CTAs per encoder group
   short slot_cls[9], slot_tap[9]; // shared-memory weight slot -> (class map, k-block) it is loaded from
@@ -78,8 +83,9 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
   uint8_t* wsm = smem;
   uint8_t* ring = wsm + W_BYTES;
   uint8_t* g1t = ring + RG * ROW_BYTES;
-  uint8_t* xt = g1t + NG1 * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xt + NX * TILE);
+  uint8_t* xt = g1t + NG1 * 2 * TILE;
+  uint8_t* ones = xt + NX * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + ONES_BYTES);
   uint64_t* r_full = bars;                 // [RG]
   uint64_t* r_empty = r_full + RG;         // [RG]
   uint64_t* tm_full = r_empty + RG;        // [NB]
@@ -101,19 +107,16 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
   if (threadIdx.x == 0) {
     for (int s = 0; s < RG; ++s) { mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 1); }
     for (int b = 0; b < NB; ++b) { mbar_init(&tm_full[b], 1); mbar_init(&tm_empty[b], 256); }
-    for (int s = 0; s < NG1; ++s) { mbar_init(&g1_full[s], 128); mbar_init(&g1_empty[s], 1); }
+    for (int s = 0; s < NG1; ++s) { mbar_init(&g1_full[s], 256); mbar_init(&g1_empty[s], 1); }
     for (int s = 0; s < NX; ++s) { mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], 1); }
     mbar_init(w_full, 1);
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  // window-tile columns >= 48 are never written by the producers: zero once, then the constant 1.0 of the bias gradient
-  for (int i = threadIdx.x * 16; i < NX * TILE; i += THREADS * 16) *reinterpret_cast<uint4*>(xt + i) = make_uint4(0, 0, 0, 0);
+  // constant operand of the bias gradient: column 0 of every K row is 1.0 (bf16 0x3f80), the rest zero
+  for (int i = threadIdx.x * 16; i < ONES_BYTES; i += THREADS * 16) *reinterpret_cast<uint4*>(ones + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int i = threadIdx.x; i < NX * 128; i += THREADS) {
-    const int s = i >> 7, r = i & 127;
-    *reinterpret_cast<uint16_t*>(xt + s * TILE + r * 128 + ((6 ^ (r & 7)) << 4)) = 0x3f80;   // column 48
-  }
+  if (threadIdx.x < 16) *reinterpret_cast<uint16_t*>(ones + threadIdx.x * 128 + ((threadIdx.x & 7) << 4)) = 0x3f80;
   fence_proxy_async();
   if (warp == 12) tmem_alloc(tmem_ptr_s, 512);
   if (warp == 14 && lane == 0) {
@@ -126,7 +129,7 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
   const uint32_t tmem_base = *tmem_ptr_s;
 
   if (warp < 4) {
-    // ===================== producers: pixel-pair windows of x0 for G1 row r = 2q + py =====================
+    // ===================== producers: 4 x 4 pixel windows of x0 around the pixel pairs of G1 rows 2q, 2q+1 =====================
     const int ox = threadIdx.x;
     const uint32_t sw = (uint32_t)ox & 7u;
     const uint32_t row_u32 = smem_u32(xt) + (uint32_t)ox * 128u;
@@ -135,26 +138,22 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
     for (int u = u_lo; u < u_hi; ++u) {
       const long long gi = gimg0 + (u >> 7);
       const int q = u & 127;
-#pragma unroll 1
-      for (int py = 0; py < 2; ++py) {
-        const int r = 2 * q + py;
-        // pixel (r - 1, 2ox) of the image
-        const char* sp = reinterpret_cast<const char*>(a.x0) + (((gi * HW + (r - 1)) * HW) + 2 * ox) * 8;
-        mbar_wait(&x_empty[s], sphase ^ 1u);
-        const uint32_t d0 = row_u32 + s * (uint32_t)TILE;
+      // pixel (2q - 1, 2ox) of the image
+      const char* sp = reinterpret_cast<const char*>(a.x0) + (((gi * HW + (2 * q - 1)) * HW) + 2 * ox) * 8;
+      mbar_wait(&x_empty[s], sphase ^ 1u);
+      const uint32_t d0 = row_u32 + s * (uint32_t)TILE;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const bool ok = (unsigned)(r - 1 + ky) < (unsigned)HW;
-          const uint32_t ca = d0 + (((uint32_t)(2 * ky) ^ sw) << 4), cb = d0 + (((uint32_t)(2 * ky + 1) ^ sw) << 4);
-          const char* p = ok ? sp : reinterpret_cast<const char*>(a.x0) + 8;
-          cp_async16(ca, p, ok ? 16u : 0u);                                   // pixels 2ox, 2ox+1
-          cp_async8(cb, p - 8, (ok && okl) ? 8u : 0u);                         // pixel 2ox-1
-          cp_async8(cb + 8, ok && okr ? p + 16 : p, (ok && okr) ? 8u : 0u);    // pixel 2ox+2
-          sp += HW * 8;
-        }
-        cp_async_mbar_arrive_noinc(&x_full[s]);
-        if (++s == NX) { s = 0; sphase ^= 1u; }
+      for (int wy = 0; wy < 4; ++wy) {
+        const bool ok = (unsigned)(2 * q - 1 + wy) < (unsigned)HW;
+        const uint32_t ca = d0 + (((uint32_t)(2 * wy) ^ sw) << 4), cb = d0 + (((uint32_t)(2 * wy + 1) ^ sw) << 4);
+        const char* p = ok ? sp : reinterpret_cast<const char*>(a.x0) + 8;
+        cp_async16(ca, p, ok ? 16u : 0u);                                   // pixels 2ox, 2ox+1
+        cp_async8(cb, p - 8, (ok && okl) ? 8u : 0u);                         // pixel 2ox-1
+        cp_async8(cb + 8, ok && okr ? p + 16 : p, (ok && okr) ? 8u : 0u);    // pixel 2ox+2
+        sp += HW * 8;
       }
+      cp_async_mbar_arrive_noinc(&x_full[s]);
+      if (++s == NX) { s = 0; sphase ^= 1u; }
     }
   } else if (warp < 12) {
     // ===================== epilogue: set py, thread = ox =====================
@@ -165,11 +164,17 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
     const uint32_t col0 = py == 0 ? 32u : 0u, col1 = py == 0 ? 64u : 96u;
     const uint32_t sw = (uint32_t)ox & 7u;
     const uint32_t trow = smem_u32(g1t) + (uint32_t)py * (uint32_t)TILE + (uint32_t)ox * 128u;
-    uint32_t buf = 0, bphase = 0, gphase = 0;
+    uint32_t buf = 0, bphase = 0, gb = 0, gphase = 0;
+    // mask words of pixels 2ox, 2ox+1 of G1 row 2q+py, fetched two units ahead: the load's latency sat on the critical
+    // path of every unit (ncu: 22 % of all stall samples on its first use)
+    const uint2* bp = a.bits1 + (((gimg0 + (u_lo >> 7)) * HW + 2 * (u_lo & 127) + py) * HW) / 2 + ox;
+    uint2 bits0 = __ldg(bp), bits1 = make_uint2(0u, 0u);
+    if (u_lo + 1 < u_hi) bits1 = __ldg(bp + HW);
     for (int u = u_lo; u < u_hi; ++u) {
-      const long long gi = gimg0 + (u >> 7);
-      const int r = 2 * (u & 127) + py;
-      const uint2 bits = __ldg(a.bits1 + ((gi * HW + r) * HW) / 2 + ox);      // mask words of pixels 2ox, 2ox+1
+      const uint2 bits = bits0;
+      bits0 = bits1;
+      if (u + 2 < u_hi) bits1 = __ldg(bp + 2 * HW);     // consecutive units are two G1 rows apart, also across images
+      bp += HW;
       mbar_wait(&tm_full[buf], bphase);
       tc_fence_after();
       uint32_t o[32];
@@ -178,6 +183,10 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
         uint32_t v[32];
         tmem_ld32(lane_addr + buf * 128u + (px ? col1 : col0), v);
         tmem_ld_wait();
+        if (px == 1) {
+          tc_fence_before();
+          mbar_arrive(&tm_empty[buf]);
+        }
         const uint32_t bw = px ? bits.y : bits.x;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -191,33 +200,35 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tm_empty[buf]);
       if (++buf == NB) { buf = 0; bphase ^= 1u; }
-      // the set's tile has been consumed by the weight-gradient MMAs of the previous unit
-      mbar_wait(&g1_empty[py], gphase ^ 1u);
+      // the buffer's tile pair has been consumed by the weight-gradient MMAs of NG1 units ago
+      mbar_wait(&g1_empty[gb], gphase ^ 1u);
+      const uint32_t tr = trow + gb * (uint32_t)(2 * TILE);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        st_shared_v4(trow + (((uint32_t)c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        st_shared_v4(tr + (((uint32_t)c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
       fence_proxy_async();
-      mbar_arrive(&g1_full[py]);
-      gphase ^= 1u;
+      mbar_arrive(&g1_full[gb]);
+      if (++gb == NG1) { gb = 0; gphase ^= 1u; }
     }
     if (py == 0) {
-      // the CTA's weight-gradient accumulator (M = 64: row m sits in lane (m % 16) + 32 * (m / 16)) -> its partial
+      // the CTA's weight-gradient accumulator (M = 128: TMEM lane = row (py, px, co)) -> its partial
       mbar_wait(acc_full, 0);
       tc_fence_after();
-      float* P = a.partial + ((long long)blockIdx.x * 64 + quad * 16 + (lane & 15)) * 64;
+      float* P = a.partial + (long long)blockIdx.x * PART_FLOATS;
+      float* Pr = P + (quad * 32 + lane) * 64;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+      for (int c0 = 0; c0 < 80; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(lane_addr + (uint32_t)ACC_COL + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (lane < 16) {
+        if (c0 < 64) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(P + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            *reinterpret_cast<float4*>(Pr + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        } else {
+          P[128 * 64 + quad * 32 + lane] = __uint_as_float(v[0]);
         }
       }
     }
@@ -266,32 +277,31 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
       if (++buf == NB) { buf = 0; bphase ^= 1u; }
     }
   } else if (warp == 13) {
-    // ===================== weight-gradient MMA issuer: item = (unit, py) =====================
-    const uint32_t idw = make_idesc_bf16(64, 64, 1, 1);
-    const uint64_t dtempl = make_desc_sw128(0, 8192, 1024);
-    const uint32_t g16 = smem_u32(g1t) >> 4, x16 = smem_u32(xt) >> 4;
+    // ===================== weight-gradient MMA issuer: one item per unit =====================
+    const uint32_t idw = make_idesc_bf16(128, 64, 1, 1), idb = make_idesc_bf16(128, 16, 1, 1);
+    const uint64_t adesc = make_desc_sw128(0, TILE, 1024);        // two M atoms (py = 0, 1), TILE bytes apart
+    const uint64_t bdesc = make_desc_sw128(0, 8192, 1024);
+    const uint32_t g16 = smem_u32(g1t) >> 4, x16 = smem_u32(xt) >> 4, ones16 = smem_u32(ones) >> 4;
     const uint32_t dacc = tmem_base + (uint32_t)ACC_COL;
-    uint32_t s = 0, sphase = 0, gphase = 0;
-    bool first = true;
+    uint32_t s = 0, sphase = 0, gb = 0, gphase = 0;
     for (int u = u_lo; u < u_hi; ++u) {
-#pragma unroll 1
-      for (int py = 0; py < 2; ++py) {
-        mbar_wait(&x_full[s], sphase);
-        mbar_wait(&g1_full[py], gphase);
-        tc_fence_after();
-        const uint32_t a16 = g16 + (uint32_t)py * (uint32_t)(TILE >> 4), b16 = x16 + s * (uint32_t)(TILE >> 4);
-        if (elect_one()) {
+      mbar_wait(&x_full[s], sphase);
+      mbar_wait(&g1_full[gb], gphase);
+      tc_fence_after();
+      const uint32_t a16 = g16 + gb * (uint32_t)(2 * TILE >> 4), b16 = x16 + s * (uint32_t)(TILE >> 4);
+      const uint32_t acc = u != u_lo ? 1u : 0u;
+      if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)      // 8 x 16 pixel pairs
-            tc_mma(dacc, dtempl | (uint64_t)(a16 + j * 128), dtempl | (uint64_t)(b16 + j * 128), idw, (first && j == 0) ? 0u : 1u);
-          tc_commit(&g1_empty[py]);
-          tc_commit(&x_empty[s]);
+        for (int j = 0; j < 8; ++j) {      // 8 x 16 pixel pairs
+          tc_mma(dacc, adesc | (uint64_t)(a16 + j * 128), bdesc | (uint64_t)(b16 + j * 128), idw, j != 0 ? 1u : acc);
+          tc_mma(dacc + 64, adesc | (uint64_t)(a16 + j * 128), bdesc | (uint64_t)ones16, idb, j != 0 ? 1u : acc);
         }
-        __syncwarp();
-        first = false;
-        if (++s == NX) { s = 0; sphase ^= 1u; }
+        tc_commit(&g1_empty[gb]);
+        tc_commit(&x_empty[s]);
       }
-      gphase ^= 1u;
+      __syncwarp();
+      if (++s == NX) { s = 0; sphase ^= 1u; }
+      if (++gb == NG1) { gb = 0; gphase ^= 1u; }
     }
     if (elect_one()) tc_commit(acc_full);
     __syncwarp();
@@ -319,34 +329,41 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
   if (warp == 12) tmem_dealloc(tmem_base, 512);
 }
 
-// dW1[g][(ky*3 + kx)*Cw + ch][co] = sum over the group's CTAs and both column parities px of
-// P[cta][px*32 + co][ky*16 + slot(px + kx)*4 + ch]; the bias gradient sits in window column 48.  Window slot of
-// pair-relative column cx = -1 .. 2 (cx + 1 = px + kx): the two pixels of the pair first, then the left and right neighbour.
-__global__ void conv21_bwd_reduce_kernel(const float* __restrict__ P, float* __restrict__ dW, float* __restrict__ dbias, int cpg,
-                                         int Cw, long long dw_group_stride, long long dbias_group_stride) {
+// dW1[g][(ky*3 + kx)*Cw + ch][co] = sum over the group's CTAs and the four classes (py, px) of
+// P[cta][(py*2 + px)*32 + co][(ky + py)*16 + slot(px + kx)*4 + ch]; the bias gradient is the extra column.  Window slot of
+// pair-relative column cx = px + kx (0: pixel 2ox-1 .. 3: pixel 2ox+2): the two pixels of the pair first, then the left and
+// the right neighbour.  One block per (group, k): thread (co, j) sums the CTAs j, j + 8, ..; fixed order throughout.
+__global__ void __launch_bounds__(256) conv21_bwd_reduce_kernel(const float* __restrict__ P, float* __restrict__ dW,
+                                                                float* __restrict__ dbias, int cpg, int Cw,
+                                                                long long dw_group_stride, long long dbias_group_stride) {
   pdl_enter();
-  const int g = blockIdx.x;
-  const int per_group = (9 * Cw + 1) * C1;
-  for (int e = threadIdx.x; e < per_group; e += blockDim.x) {
-    const int k = e / C1, co = e - k * C1;
-    int col[2];
-    if (k < 9 * Cw) {
-      const int tap = k / Cw, ch = k - tap * Cw, ky = tap / 3, kx = tap - ky * 3;
-      for (int px = 0; px < 2; ++px) {
-        const int cx = px + kx;                        // 0: pixel 2ox-1, 1: 2ox, 2: 2ox+1, 3: 2ox+2
-        const int slot = cx == 0 ? 2 : (cx == 1 ? 0 : (cx == 2 ? 1 : 3));
-        col[px] = ky * 16 + slot * 4 + ch;
-      }
-    } else {
-      col[0] = col[1] = 48;
+  __shared__ float red[8][C1];
+  const int nk = 9 * Cw + 1;
+  const int g = blockIdx.x / nk, k = blockIdx.x - g * nk;
+  const int co = threadIdx.x & 31, j = threadIdx.x >> 5;
+  int off[4];
+  if (k < 9 * Cw) {
+    const int tap = k / Cw, ch = k - tap * Cw, ky = tap / 3, kx = tap - ky * 3;
+    for (int c = 0; c < 4; ++c) {
+      const int py = c >> 1, px = c & 1, cx = px + kx;
+      const int slot = cx == 0 ? 2 : (cx == 1 ? 0 : (cx == 2 ? 1 : 3));
+      off[c] = (c * C1 + co) * 64 + (ky + py) * 16 + slot * 4 + ch;
     }
-    float s = 0.f;
-    for (int cta = g * cpg; cta < (g + 1) * cpg; ++cta) {
-      const float* p = P + (long long)cta * 4096;
-      s += p[co * 64 + col[0]] + p[(C1 + co) * 64 + col[1]];
-    }
-    if (k < 9 * Cw) dW[(long long)g * dw_group_stride + (long long)k * C1 + co] = s;
-    else if (dbias) dbias[(long long)g * dbias_group_stride + co] = s;
+  } else {
+    for (int c = 0; c < 4; ++c) off[c] = 128 * 64 + c * C1 + co;
+  }
+  float s = 0.f;
+  for (int cta = g * cpg + j; cta < (g + 1) * cpg; cta += 8) {
+    const float* p = P + (long long)cta * PART_FLOATS;
+    s += (p[off[0]] + p[off[1]]) + (p[off[2]] + p[off[3]]);
+  }
+  red[j][co] = s;
+  __syncthreads();
+  if (j == 0) {
+    float t = red[0][co];
+    for (int i = 1; i < 8; ++i) t += red[i][co];
+    if (k < 9 * Cw) dW[(long long)g * dw_group_stride + (long long)k * C1 + co] = t;
+    else if (dbias) dbias[(long long)g * dbias_group_stride + co] = t;
   }
 }
 
@@ -383,7 +400,7 @@ bool tc_bwd21_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int str
          bwd21_slots(dg, ncls, sc, stp);
 }
 
-long long tc_bwd21_partial_floats() { return (long long)tc_num_sms() * 4096; }
+long long tc_bwd21_partial_floats() { return (long long)tc_num_sms() * PART_FLOATS; }
 
 int launch_tc_bwd21(const __nv_bfloat16* G2, const TcGeom* dg, const CUtensorMap* const* wmaps, const unsigned short* bits1,
                     const __nv_bfloat16* x0, float* partial, long long partial_cap, float* dW1, float* dbias1, int Cw,
@@ -397,7 +414,7 @@ int launch_tc_bwd21(const __nv_bfloat16* G2, const TcGeom* dg, const CUtensorMap
   int cpg = tc_num_sms() / G;
   if (cpg < 1) cpg = 1;
   if ((long long)cpg > (long long)M * 128) cpg = M * 128;
-  if ((long long)cpg * G * 4096 > partial_cap) { geeco_set_error("bwd21: partial buffer too small"); return GEECO_ERR_WORKSPACE; }
+  if ((long long)cpg * G * PART_FLOATS > partial_cap) { geeco_set_error("bwd21: partial buffer too small"); return GEECO_ERR_WORKSPACE; }
   B21Maps maps;
   for (int c = 0; c < 4; ++c) maps.m[c] = *wmaps[c];
   CUtensorMap g2map;
@@ -409,7 +426,7 @@ int launch_tc_bwd21(const __nv_bfloat16* G2, const TcGeom* dg, const CUtensorMap
   GEECO_LAUNCH((conv21_bwd_fused_kernel), cpg * G, THREADS, SMEM_BYTES, st, a, maps, g2map);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
-  GEECO_LAUNCH((conv21_bwd_reduce_kernel), G, 256, 0, st, (const float*)partial, dW1, dbias1, cpg, Cw, dw_group_stride, dbias_group_stride);
+  GEECO_LAUNCH((conv21_bwd_reduce_kernel), G * (9 * Cw + 1), 256, 0, st, (const float*)partial, dW1, dbias1, cpg, Cw, dw_group_stride, dbias_group_stride);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
