@@ -476,6 +476,16 @@ def kernel_rooflines(eng, dev, peaks, args):
                   2.0 * P1 * 32 * 27 + 2.0 * P2 * 48 * 288, launches=1)
   except Exception as exc:                      # GEECO_NO_FUSE12=1 or another image size: the separate kernels ran
     sys.stderr.write('fused conv1->conv2 kernel not timed: %s\n' % exc)
+  # the step's conv2 data gradient + conv1 weight gradient: ONE fused kernel (conv21_bwd_fused.cu) + its partial reduce.
+  # Algorithmic bytes: G2 in, the 1-bit ReLU mask of y1 in, x0 in; dL/d(pre-activation of conv1) (0.8 GB) never exists.
+  fused_bwd = None
+  try:
+    sec = _timed(dev, lambda: eng.profile_kernel('bwd21'), flush=flush)
+    fused_bwd = entry('conv21_bwd_fused_kernel conv2 dgrad + conv1 wgrad', sec, P2 * 48 * 2 + P1 * 4 + P1 * 4 * 2,
+                      2.0 * P2 * 48 * 288 + 2.0 * P1 * 32 * 27, launches=2)
+    fused_bwd['limiter'] = 'shared-memory data pipe (MMA operand reads + staging stores), see profiles/r02_ncu_notes.md'
+  except Exception as exc:                      # GEECO_NO_FUSE_BWD21=1 or another image size
+    sys.stderr.write('fused conv2-dgrad -> conv1-wgrad kernel not timed: %s\n' % exc)
   sec = _timed(dev, lambda: ops.conv2d_same_bf16(x1, w1, b1, stride=1), flush=flush)
   entry('tc_nn_kernel<4,4> conv1 fwd', sec, P1 * (4 + 32) * 2, 2.0 * P1 * 32 * 27, launches=2)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x1, w1, g1, stride=1, need_dx=False), flush=flush)
@@ -487,8 +497,9 @@ def kernel_rooflines(eng, dev, peaks, args):
   entry('tc_rows_kernel<2,12> conv2 fwd', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
   g2 = (torch.rand((N3, 128, 128, 48), device=dev) - 0.5).to(torch.bfloat16)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, need_dx=False), flush=flush)
-  entry('tc_wgrad_kernel<8,512> conv2 wgrad', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
-  # the longest kernel of the step: conv2 data gradient = G2 in, 1-bit ReLU mask of y1 in (as in the step), G1 out
+  wg2 = entry('tc_wgrad_kernel<8,512> conv2 wgrad', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
+  # conv2 data gradient as a separate kernel (what the fused backward replaces; other image sizes still run it):
+  # G2 in, 1-bit ReLU mask of y1 in, G1 out
   bits1 = ops.relu_mask_bits(x2)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x2, w2, g2, stride=2, relu_mask_bits=bits1, need_dx=True, need_dw=False),
                flush=flush)
@@ -529,9 +540,10 @@ def kernel_rooflines(eng, dev, peaks, args):
       e['bound'] = 'tensor'
     del x, w, b, g, bits
     Hin, Cin = Ho, Cout
-  # `roofline` = the longest kernel of the step: the fused conv1 -> conv2 forward or conv2's data gradient
-  if fused is not None and fused['ms'] > dom['ms']:
-    dom = fused
+  # `roofline` = the longest kernel the step actually runs: the fused conv1 -> conv2 forward, conv2's weight gradient or
+  # the fused backward (the separate conv2 data gradient only where the fused kernels do not apply)
+  if fused is not None:
+    dom = max([e for e in (fused, wg2, fused_bwd) if e is not None], key=lambda e: e['ms'])
   return dom, out
 
 

@@ -802,12 +802,17 @@ tc_rows_kernel(const TcGeom g, const TcClasses cl, const TcRowProg rp, const __g
 // ------------------------------------------------------------------------------------------------
 __device__ int g_wgrad_m128 = 0;       // experiment switch (GEECO_TC_WGRAD_M128=1): keep M = 128 for Cout <= 64
 
+// Single-split launches (the pixel range of a group fits one CTA column: conv7, conv8) write the gradient itself instead
+// of a partial: lane = output channel, so for a fixed reduction index the warp's 32 stores are consecutive floats of
+// dW[k][co] -- better coalesced than the row-per-lane partial, and the reduce launch disappears.
+struct WgDirect { float* dW; float* dbias; long long dw_group_stride, dbias_group_stride; };
+
 // NPROD producer threads: 512 (one CTA per SM, big stages) or 256 (two CTAs per SM when the stage is small)
 template <int PIECE, int NPROD>
 __global__ void __launch_bounds__(NPROD + 160, NPROD == 256 ? 2 : 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
-                int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk) {
+                int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk, const WgDirect direct) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1022,10 +1027,20 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
       if (co < Cout) {
+        if (direct.dW) {
+          float* dw = direct.dW + (long long)group * direct.dw_group_stride + co;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<float4*>(P + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          for (int i = 0; i < 16; ++i) {
+            const int k = col0 + c0 + i;
+            if (k < g.Ktot) dw[(long long)k * Cout] = __uint_as_float(v[i]);
+            else if (k == ones_col && direct.dbias) direct.dbias[(long long)group * direct.dbias_group_stride + co] = __uint_as_float(v[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(P + c0 + 4 * i) = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
       }
     }
   } else {
@@ -1258,6 +1273,36 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
       float v = pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k);
       if ((int)k == bias_col && (int)r < Cout) v = bias[(long long)grp * bgs + r];
       out[i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// One 32 x 32 tile of one tap per block (see PackTile): 256 threads = 32 x 8.  The element-wise kernel above spends
+// ~60 instructions per element on index arithmetic (three divisions by runtime values) and, in mode 0, reads W with a
+// stride of Cout floats: 55 + 36 us per step for the conv4-conv8 forward and the data-gradient operands when run alone,
+// and its thousands of short blocks kept the tail's small kernels waiting for SM slots (r02 timelines).
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const PackTile* __restrict__ tiles) {
+  pdl_enter();
+  __shared__ float t[32][33];
+  const PackTile pt = tiles[blockIdx.x];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (pt.transpose) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      t[r][tx] = (r < pt.rows && tx < pt.cols) ? pt.S[(long long)r * pt.s_ld + tx] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = ty + 8 * i;                 // source column = destination row
+      if (c < pt.cols && tx < pt.rows) pt.D[(long long)c * pt.d_ld + tx] = __float2bfloat16_rn(t[tx][c]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 8 * i;
+      if (r < pt.rows && tx < pt.cols) pt.D[(long long)r * pt.d_ld + tx] = __float2bfloat16_rn(pt.S[(long long)r * pt.s_ld + tx]);
     }
   }
 }
@@ -1868,6 +1913,16 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   // up to 8 sub-tiles (N = 512 TMEM columns) per CTA; the ring must hold at least 3 stages
   int cap = 8;
   while (cap > 1 && 3 * (2 + cap) * SUB + 1536 > (int)SMEM_BUDGET) --cap;
+  static const int env_cap = getenv("GEECO_TC_WGRAD_NSUB") ? atoi(getenv("GEECO_TC_WGRAD_NSUB")) : 0;
+  static const int env_minkb = getenv("GEECO_TC_WGRAD_MINKB") ? atoi(getenv("GEECO_TC_WGRAD_MINKB")) : 8;
+  if (env_cap > 0 && cap > env_cap) cap = env_cap;
+  // few pixels per group (conv6-conv8: 4-64 k-blocks): narrow column chunks = more CTAs, shorter epilogues and fewer
+  // (or no) splits; measured in situ (tools/sweep_wgrad.sh): conv8 30 -> 20 us, conv7 35 -> 28 us, conv6 47 -> 40 us
+  if (env_cap == 0) {
+    const long long kb = (Mg + 63) / 64;
+    const int small_cap = kb <= 16 ? 2 : (kb <= 64 ? 4 : cap);
+    if (cap > small_cap) cap = small_cap;
+  }
   p.n_chunks = (total_sub + cap - 1) / cap;
   p.nsub_chunk = (total_sub + p.n_chunks - 1) / p.n_chunks;
   p.total_kb = (int)((Mg + 63) / 64);
@@ -1883,7 +1938,7 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
   // one wave: never more CTAs than can be resident at once (a 149th CTA on 148 SMs doubles the kernel time)
   int want = (num_sms() * p.per_sm) / base;
   if (want < 1) want = 1;
-  if (want > p.total_kb / 8) want = p.total_kb / 8 > 0 ? p.total_kb / 8 : 1;     // >= 8 k-blocks per split
+  if (want > p.total_kb / env_minkb) want = p.total_kb / env_minkb > 0 ? p.total_kb / env_minkb : 1;     // >= 8 k-blocks per split
   p.kb_per_split = (p.total_kb + want - 1) / want;
   p.splits = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.Mrows_pad = p.m_tiles * 128;
@@ -1899,7 +1954,8 @@ long long tc_wgrad_partial_floats(const TcGeom& g_in, int Cout) {
 
 // runs the weight-gradient GEMM into `partial` ([splits][groups][Mrows_pad][Kpad] fp32)
 static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
-                      long long partial_cap, bool want_ones, WgradPlan* plan_out, cudaStream_t st) {
+                      long long partial_cap, bool want_ones, WgradPlan* plan_out, cudaStream_t st,
+                      const WgDirect* direct_in = nullptr) {
   if (Cout % 8 || Cout > 256 * 8) { geeco_set_error("tc_wgrad: unsupported Cout=%d", Cout); return GEECO_ERR_INVALID; }
   int rc = check_geom(g, "tc_wgrad");
   if (rc) return rc;
@@ -1912,6 +1968,8 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
   if (p.stages < 3) { geeco_set_error("tc_wgrad: stage does not fit 3 times"); return GEECO_ERR_INVALID; }
   const size_t smem = 1024 + (size_t)p.stages * (2 + p.nsub_chunk) * SUB + 512;
   const int ones = want_ones ? p.ones_col : -1;
+  WgDirect direct = {nullptr, nullptr, 0, 0};
+  if (direct_in && p.splits == 1) direct = *direct_in;
   dim3 grid(p.m_tiles * p.n_chunks, p.splits, g.groups);
   {
     static int flag_set = -1;
@@ -1929,7 +1987,7 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
                                   (int)smem));                                                                      \
     GEECO_LAUNCH((tc_wgrad_kernel<PIECE_, NPROD_>), grid, NPROD_ + 160, smem, st, g, src, G, partial, Cout, p.n_chunks,          \
                                                                       p.kb_per_split, p.total_kb, p.Mrows_pad, ones, \
-                                                                      p.tmem_cols, p.stages, p.gsub, p.nsub_chunk);  \
+                                                                      p.tmem_cols, p.stages, p.gsub, p.nsub_chunk, direct);  \
   } while (0)
   if (g.Cs == 4) { if (p.per_sm == 2) WG_LAUNCH(4, 256); else WG_LAUNCH(4, 512); }
   else { if (p.per_sm == 2) WG_LAUNCH(8, 256); else WG_LAUNCH(8, 512); }
@@ -1959,8 +2017,14 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
   WgradPlan p;
-  int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st);
+  static const bool no_direct = getenv("GEECO_TC_WGRAD_NO_DIRECT") != nullptr;
+  // a single split needs no reduction when the stored channels are the real ones (reduction index = dW row)
+  WgDirect direct = {dW, dbias, dw_group_stride, dbias_group_stride};
+  const bool can_direct = !no_direct && g.Cs == Cw;
+  int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st, can_direct ? &direct : nullptr);
   if (rc) return rc;
+  if (dbias && p.ones_col < 0) { geeco_set_error("tc_wgrad: no padding column for the bias gradient"); return GEECO_ERR_INVALID; }
+  if (can_direct && p.splits == 1) return GEECO_OK;
   const int ones = dbias ? p.ones_col : -1;
   const dim3 tgrid(ceil_div(g.Ktot + 1, 32), ceil_div(Cout, 32), g.groups);
   const int tiles = (int)(tgrid.x * tgrid.y * tgrid.z);
@@ -2019,6 +2083,42 @@ int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long gr
     carve_set = true;
   }
   GEECO_LAUNCH((pack_weights_batched_kernel), (unsigned)blocks, 256, 0, st, jobs_dev, njobs, grand_total);
+  geeco_count_launch(1);
+  CUDA_TRY(cudaGetLastError());
+  return GEECO_OK;
+}
+
+bool pack_job_is_plain(const PackJob& j) { return (j.mode == 0 || j.mode == 1) && j.bias_col < 0; }
+
+// tiles of a plain job: per group and tap the [Cin][Cout] matrix of that tap, cut into 32 x 32 tiles
+void pack_job_tiles(const PackJob& j, std::vector<PackTile>* out) {
+  const int per_tap = j.Kt > 0 ? j.Kt : (j.mode == 0 ? j.Cs : j.Cout);
+  for (int g = 0; g < j.groups; ++g)
+    for (int t = 0; t < j.ntaps; ++t) {
+      const float* S = j.W + (long long)g * j.w_group_stride + (long long)j.taps[t] * j.Cin * j.Cout;
+      __nv_bfloat16* D = j.out + (long long)g * j.rows * j.Kpad + (long long)t * per_tap;
+      for (int r0 = 0; r0 < j.Cin; r0 += 32)
+        for (int c0 = 0; c0 < j.Cout; c0 += 32) {
+          PackTile pt;
+          pt.S = S + (long long)r0 * j.Cout + c0;
+          pt.D = j.mode == 0 ? D + (long long)c0 * j.Kpad + r0 : D + (long long)r0 * j.Kpad + c0;
+          pt.s_ld = j.Cout; pt.d_ld = j.Kpad;
+          pt.rows = (short)(j.Cin - r0 < 32 ? j.Cin - r0 : 32);
+          pt.cols = (short)(j.Cout - c0 < 32 ? j.Cout - c0 : 32);
+          pt.transpose = j.mode == 0 ? 1 : 0; pt.pad_ = 0;
+          out->push_back(pt);
+        }
+    }
+}
+
+int launch_pack_tiles(const PackTile* tiles_dev, int ntiles, cudaStream_t st) {
+  if (ntiles <= 0) return GEECO_OK;
+  static bool carve_set = false;
+  if (!carve_set) {
+    CUDA_TRY(cudaFuncSetAttribute(pack_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_set = true;
+  }
+  GEECO_LAUNCH((pack_tiles_kernel), (unsigned)ntiles, 256, 0, st, tiles_dev);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

@@ -1,6 +1,7 @@
 // bf16 tensor-core (tcgen05) gather-GEMM kernels: declarations shared with step_bf16.cu / geeco_api.cu
 #pragma once
 #include <cuda.h>
+#include <vector>
 #include "common.cuh"
 
 // Geometry of one tensor-core gather GEMM (bf16 NHWC source, implicit im2col).
@@ -95,6 +96,14 @@ struct PackJob {
 // grand_total is the end of the last job rounded up to PACK_CHUNK (total < 2^31 per job)
 constexpr int PACK_CHUNK = 2048;
 int launch_pack_weights_batched(const PackJob* jobs_dev, int njobs, long long grand_total, cudaStream_t st, int max_blocks = 0);
+// Tile form of the plain repack jobs (mode 0 / 1, no bias column): one 32 x 32 tile of one tap's [Cin][Cout] matrix per
+// block, every index computed once per block.  Writes only real elements: the padding of the packed matrices must have
+// been written once by launch_pack_weights_batched (it is never touched again).
+//   transpose (mode 0): D[c * d_ld + r] = S[r * s_ld + c]      copy (mode 1): D[r * d_ld + c] = S[r * s_ld + c]
+struct PackTile { const float* S; __nv_bfloat16* D; int s_ld, d_ld; short rows, cols, transpose, pad_; };
+bool pack_job_is_plain(const PackJob& j);
+void pack_job_tiles(const PackJob& j, std::vector<PackTile>* out);
+int launch_pack_tiles(const PackTile* tiles_dev, int ntiles, cudaStream_t st);
 // 1-bit ReLU mask (layout of TC_EPI_MASKBITS) of a bf16 tensor: one uint16 per 16 consecutive values
 int launch_relu_mask_bits(const __nv_bfloat16* y, unsigned short* bits, long long chunks, cudaStream_t st);
 int launch_f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);

@@ -39,6 +39,11 @@ struct Bf16Plan {
   std::vector<PackJob> jobs[3];
   long long jobs_total[3];
   bool jobs_uploaded;
+  // tables 1 and 2 again as 32 x 32 tiles (pack_tiles_kernel): used from a table's second repack on, after the
+  // element-wise kernel has written the zero padding of the packed matrices once
+  PackTile* tiles_dev[3] = {nullptr, nullptr, nullptr};
+  int tiles_cap[3] = {0, 0, 0}, ntiles[3] = {0, 0, 0};
+  bool table_init[3] = {false, false, false};
   // the weight repack of a step does not depend on the batch: it runs on a side stream next to the rank-pooling
   // kernel (whose 16-CTA clusters leave a quarter of the SMs idle) and is joined before the first convolution
   cudaStream_t side = nullptr;
@@ -127,6 +132,18 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
   bp->jobs_dev[1] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_dev[2] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
   bp->jobs_uploaded = false;
+  for (int t = 1; t < 3; ++t) {
+    long long n = 0;
+    for (int l = (t == 1 ? 3 : 1); l < 8; ++l) {
+      const LayerPlan& L = c->layers[l];
+      for (int e = 0; e < G; ++e) n += 9ll * ((L.Cin_real + 31) / 32) * ((L.Cout[L.grouped ? 0 : e] + 31) / 32);
+    }
+    bp->tiles_cap[t] = (int)n;
+    bp->tiles_dev[t] = (PackTile*)carve(ws_off, ws_base, (size_t)n * sizeof(PackTile));
+    bp->ntiles[t] = 0;
+    bp->table_init[t] = false;
+  }
+  bp->table_init[0] = false;
   if (!ws_base) return GEECO_OK;
   if (!bp->side) {
     // lowest priority: the repack's many short blocks must not hold up the CTAs of the step's own kernels (conv1
@@ -241,13 +258,33 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 4, int max_
       if (!bp->jobs[t].empty())
         CUDA_TRY(cudaMemcpyAsync(bp->jobs_dev[t], bp->jobs[t].data(), bp->jobs[t].size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
     }
+    const bool no_tiles = getenv("GEECO_PACK_NO_TILES") != nullptr;     // read per context: the parity test toggles it
+    std::vector<PackTile> tiles;
+    for (int t = 1; t < 3; ++t) {
+      bp->ntiles[t] = 0;
+      bool plain = !no_tiles && bp->tiles_dev[t] != nullptr;
+      for (const PackJob& pj : bp->jobs[t]) plain = plain && pack_job_is_plain(pj);
+      if (!plain) continue;
+      tiles.clear();
+      for (const PackJob& pj : bp->jobs[t]) pack_job_tiles(pj, &tiles);
+      if ((int)tiles.size() > bp->tiles_cap[t]) continue;         // keeps the element-wise kernel
+      CUDA_TRY(cudaMemcpyAsync(bp->tiles_dev[t], tiles.data(), tiles.size() * sizeof(PackTile), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));                         // `tiles` is reused / freed
+      bp->ntiles[t] = (int)tiles.size();
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     bp->jobs_uploaded = true;
   }
   for (int t = 0; t < 3; ++t) {
     const bool sel = which == t || (which == 3 && t < 2) || which == 4;
     if (!sel || bp->jobs[t].empty()) continue;
-    int rc = launch_pack_weights_batched(bp->jobs_dev[t], (int)bp->jobs[t].size(), bp->jobs_total[t], st, max_blocks);
+    int rc;
+    if (bp->table_init[t] && bp->ntiles[t] > 0) {
+      rc = launch_pack_tiles(bp->tiles_dev[t], bp->ntiles[t], st);
+    } else {
+      rc = launch_pack_weights_batched(bp->jobs_dev[t], (int)bp->jobs[t].size(), bp->jobs_total[t], st, max_blocks);
+      bp->table_init[t] = true;
+    }
     if (rc) return rc;
   }
   if (which == 1 || which == 3 || which == 4) c->weights_dirty = false;     // forward operands are current
@@ -295,7 +332,9 @@ static int repack_dgrad_fork(geeco_ctx* c, cudaStream_t st) {
   CUDA_TRY(cudaEventRecord(bp->ev_fork_dg, st));
   CUDA_TRY(cudaStreamWaitEvent(bp->side, bp->ev_fork_dg, 0));
   geeco_pdl_suspend(1);
-  int rc = repack_weights(c, bp->side, 2);
+  // few resident blocks (grid-stride): the tail's small kernels must find free SM slots while this runs next to them
+  static const int dg_blocks = getenv("GEECO_PACK_DG_BLOCKS") ? atoi(getenv("GEECO_PACK_DG_BLOCKS")) : 0;
+  int rc = repack_weights(c, bp->side, 2, dg_blocks);
   geeco_pdl_suspend(0);
   if (rc) return rc;
   CUDA_TRY(cudaEventRecord(bp->ev_join_dg, bp->side));

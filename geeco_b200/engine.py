@@ -463,7 +463,7 @@ class Engine(object):
 
   # ------------------------------------------------------------------ debugging
   def profile_kernel(self, name):
-    """Runs one kernel of the bf16 step again on the buffers of the last step ('conv12': fused conv1 -> conv2)."""
+    """Runs one kernel of the bf16 step again on the buffers of the last step ('conv12': fused conv1 -> conv2 forward; 'bwd21': fused conv2 data gradient -> conv1 weight gradient)."""
     _lib.check(self.lib.geeco_profile_kernel(self._ctx, name.encode(), self._stream()))
 
   def debug_buffer(self, name):

@@ -71,3 +71,16 @@ def test_fused_backward_is_reproducible_and_trains(cuda_device, monkeypatch):
   assert np.isfinite(la).all()
   # four Adam steps later the two paths are still the same model to fp32 rounding of conv1's update
   np.testing.assert_allclose(la, lc, rtol=2e-4, atol=1e-6)
+
+
+def test_tile_repack_is_bit_identical(cuda_device, monkeypatch):
+  """From a context's second step on, the conv4-conv8 forward operands and all data-gradient operands are repacked by
+  pack_tiles_kernel (one 32 x 32 tile per block) instead of the element-wise kernel: same values, same rounding."""
+  la, ga, ta, _ = _run(2, monkeypatch, fused=True, steps=4)
+  monkeypatch.setenv('GEECO_PACK_NO_TILES', '1')
+  lb, gb, tb, _ = _run(2, monkeypatch, fused=True, steps=4)
+  assert np.array_equal(la, lb)
+  for k in ta:
+    assert np.array_equal(ta[k], tb[k]), 'tile repack changed %s' % k
+  for k in ga:
+    assert np.array_equal(ga[k], gb[k]), 'tile repack changed the gradient of %s' % k
