@@ -129,6 +129,13 @@ long long tc_bwd21_partial_floats();
 int launch_tc_bwd21(const __nv_bfloat16* G2, const TcGeom* dg, const CUtensorMap* const* wmaps, const unsigned short* bits1,
                     const __nv_bfloat16* x0, float* partial, long long partial_cap, float* dW1, float* dbias1, int Cw,
                     long long dw_group_stride, long long dbias_group_stride, int G, int M, cudaStream_t st);
+// conv2 weight gradient on whole y1 rows (conv2_wgrad_fused.cu): y1 != nullptr loads the rows by TMA, y1 == nullptr
+// recomputes them from x0 on chip (the forward then need not store y1)
+bool tc_wgrad2_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int stride1, int stride2, const TcGeom& g1);
+long long tc_wgrad2_partial_floats();
+int launch_tc_wgrad2(const __nv_bfloat16* x0, const CUtensorMap* w1map, const __nv_bfloat16* y1, const __nv_bfloat16* G2,
+                     float* partial, long long partial_cap, float* dW2, float* dbias2, long long dw_group_stride,
+                     long long dbias_group_stride, int G, int M, cudaStream_t st);
 // 5-D tensor map over the source of geometry g whose box is one row of `pw` pixels x 64 channels (row-resident kernels)
 int tc_make_row_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int pw);
 

@@ -973,6 +973,14 @@ extern "C" int geeco_debug_buffer(const geeco_ctx* c, const char* name, void** p
   if (s == "x0") { *ptr = c->x0; *numel = (long long)c->G * c->M * cfg.img_height * cfg.img_width * c->CP; *dtype = act_dt; return GEECO_OK; }
   if (s.size() == 2 && (s[0] == 'y' || s[0] == 'g') && s[1] >= '1' && s[1] <= '8') {
     const LayerPlan& L = c->layers[s[1] - '1'];
+    if (s == "y1" && c->y1_stale) {
+      // the last training forward kept y1 on chip: rebuild it (debug only; default stream, synchronous)
+      geeco_ctx* cm = const_cast<geeco_ctx*>(c);
+      if (cudaDeviceSynchronize() != cudaSuccess) { geeco_set_error("debug_buffer: device error before rebuilding y1"); return GEECO_ERR_CUDA; }
+      int rc = recompute_y1_bf16(cm, nullptr);
+      if (rc) return rc;
+      if (cudaDeviceSynchronize() != cudaSuccess) { geeco_set_error("debug_buffer: rebuilding y1 failed"); return GEECO_ERR_CUDA; }
+    }
     *ptr = s[0] == 'y' ? L.y : L.g; *numel = L.act_elems; *dtype = act_dt;
     if (!*ptr) { geeco_set_error("debug_buffer: %s not allocated", name); return GEECO_ERR_INVALID; }
     return GEECO_OK;

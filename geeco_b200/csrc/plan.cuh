@@ -53,6 +53,8 @@ struct geeco_ctx {
   const unsigned char* reset_mask = nullptr;   // of the batch of the last forward (carry_state)
   int ring_start = 0;
   long long host_step = 0;                     // Adam updates applied so far (global_step of the reference's checkpoints)
+  bool y1_stale = false;                       // bf16 training: the last forward did not store y1 (conv2's weight gradient
+                                               // recomputes it on chip); geeco_debug_buffer("y1") rebuilds it on demand
   bool g8_bf16_ready = false;                  // bf16 mode: the tail already wrote layers[7].g as bf16
   // bf16 extras
   void* bf16_ws = nullptr;
@@ -79,4 +81,5 @@ int repack_fork_bf16(geeco_ctx* c, cudaStream_t st);     // weight repack on a s
 int repack_join_bf16(geeco_ctx* c, cudaStream_t st);     // `st` waits for it
 int encoders_fwd_bf16(geeco_ctx* c, cudaStream_t st);
 int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st);
+int recompute_y1_bf16(geeco_ctx* c, cudaStream_t st);      // debug: conv1's activation of the last forward into layers[0].y
 int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st);

@@ -126,6 +126,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     }
   }
   if (tc_bwd21_partial_floats() > cap) cap = tc_bwd21_partial_floats();
+  if (tc_wgrad2_partial_floats() > cap) cap = tc_wgrad2_partial_floats();
   bp->partial_cap = cap;
   bp->partial = (float*)carve(ws_off, ws_base, (size_t)cap * sizeof(float));
   bp->jobs_dev[0] = (PackJob*)carve(ws_off, ws_base, 64 * sizeof(PackJob));
@@ -342,20 +343,72 @@ static int repack_dgrad_fork(geeco_ctx* c, cudaStream_t st) {
   return GEECO_OK;
 }
 
+static bool conv12_applies(geeco_ctx* c, Bf16Plan* bp) {
+  LayerPlan& L = c->layers[0];
+  LayerPlan& L1 = c->layers[1];
+  Bf16Layer& B = bp->L[0];
+  return !(B.pair || !L.grouped || !L1.grouped || bp->L[1].fwd.rows != 2 || bp->L[1].fwd.wpack != 4 ||
+           !tc_conv12_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L1.Cout[0], L.stride, L1.stride, B.fwd));
+}
+
+// conv2's weight gradient on whole y1 rows (conv2_wgrad_fused.cu) when the two layers have the shape it is written for
+static bool wgrad2_active(geeco_ctx* c, Bf16Plan* bp) {
+  LayerPlan& L = c->layers[0];
+  LayerPlan& L1 = c->layers[1];
+  return c->cfg.training && conv12_applies(c, bp) && L.mbits != nullptr && L1.Cin_real == L.Cout[0] &&
+         tc_wgrad2_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L1.Cout[0], L.stride, L1.stride, bp->L[0].fwd);
+}
+
+// GEECO_WG2_RECOMPUTE=1: that kernel rebuilds the y1 rows from x0 instead of loading them; the data gradient takes its
+// ReLU mask from the 1-bit copy, so no kernel reads y1 from HBM then and the fused forward does not store it (measured
+// slower than loading: 248 + 301 us vs 275 + ~200 us for the forward + this gradient; it frees 805 MB and 1.6 GB of DRAM
+// traffic per step)
+static bool wgrad2_recompute(geeco_ctx* c, Bf16Plan* bp) {
+  return wgrad2_active(c, bp) && getenv("GEECO_WG2_RECOMPUTE") != nullptr && getenv("GEECO_KEEP_Y1") == nullptr;
+}
+
 // conv1 -> conv2 as one kernel when the two layers have the shape it is written for; returns 1 if it ran, 0 if the
 // separate kernels have to, < 0 on error
 static int try_conv12(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
   LayerPlan& L = c->layers[0];
   LayerPlan& L1 = c->layers[1];
   Bf16Layer& B = bp->L[0];
-  if (B.pair || !L.grouped || !L1.grouped || bp->L[1].fwd.rows != 2 || bp->L[1].fwd.wpack != 4 ||
-      !tc_conv12_supported(L.Hin, L.Hin, L.Cin_pad, L.Cout[0], L1.Cout[0], L.stride, L1.stride, B.fwd))
-    return 0;
-  // y1 stays on chip between the layers; inference does not write it at all
+  if (!conv12_applies(c, bp)) return 0;
+  // y1 stays on chip between the layers; inference does not write it at all, training only when a kernel will read it
+  const bool store_y1 = c->cfg.training && !wgrad2_recompute(c, bp);
   int rc = launch_tc_conv12((const __nv_bfloat16*)c->x0, &B.fwd_map[0], &bp->L[1].fwd_map[0],
                             c->theta + c->params[L1.p_b[0]].offset, b_group_stride(c, L1),
-                            c->cfg.training ? (__nv_bfloat16*)L.y : nullptr, (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y,
+                            store_y1 ? (__nv_bfloat16*)L.y : nullptr, (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y,
                             (unsigned short*)L1.mbits, c->G, c->M, st);
+  c->y1_stale = c->cfg.training && !store_y1;
+  return rc ? -rc : 1;
+}
+
+// debug (geeco_debug_buffer("y1")): conv1's activation of the last forward, rebuilt by the stand-alone conv1 kernel
+// (bit-identical to what the fused kernels compute, tests/test_gpu_fused12.py)
+int recompute_y1_bf16(geeco_ctx* c, cudaStream_t st) {
+  Bf16Plan* bp = (Bf16Plan*)c->bf16_ws;
+  if (!bp || !c->y1_stale) return GEECO_OK;
+  LayerPlan& L = c->layers[0];
+  TcGeom g = bp->L[0].fwd;
+  g.bias_group_stride = b_group_stride(c, L);
+  geeco_pdl_suspend(1);
+  int rc = launch_tc_nn(g, &bp->L[0].fwd_map[0], (const __nv_bfloat16*)c->x0, c->theta + c->params[L.p_b[0]].offset, nullptr,
+                        (__nv_bfloat16*)L.y, nullptr, TC_EPI_BIAS_RELU, 0, st, nullptr, bp->L[0].w_fwd[0]);
+  geeco_pdl_suspend(0);
+  if (rc) return rc;
+  c->y1_stale = false;
+  return GEECO_OK;
+}
+
+static int try_wgrad2(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
+  if (!wgrad2_active(c, bp)) return 0;
+  LayerPlan& L1 = c->layers[1];
+  // y1 rows are loaded unless the forward kept them on chip (then they are rebuilt from x0)
+  const __nv_bfloat16* y1 = c->y1_stale ? nullptr : (const __nv_bfloat16*)c->layers[0].y;
+  int rc = launch_tc_wgrad2((const __nv_bfloat16*)c->x0, &bp->L[0].fwd_map[0], y1, (const __nv_bfloat16*)L1.g, bp->partial,
+                            bp->partial_cap, c->grad + c->params[L1.p_w[0]].offset, c->grad + c->params[L1.p_b[0]].offset,
+                            w_group_stride(c, L1), b_group_stride(c, L1), c->G, c->M, st);
   return rc ? -rc : 1;
 }
 
@@ -385,6 +438,11 @@ int profile_kernel_bf16(geeco_ctx* c, const char* name, cudaStream_t st) {
   if (!strcmp(name, "conv12")) {
     const int r = try_conv12(c, bp, st);
     if (r == 0) { geeco_set_error("profile_kernel: the fused conv1->conv2 kernel does not cover this configuration"); return GEECO_ERR_INVALID; }
+    return r < 0 ? -r : GEECO_OK;
+  }
+  if (!strcmp(name, "wgrad2")) {
+    const int r = try_wgrad2(c, bp, st);
+    if (r == 0) { geeco_set_error("profile_kernel: the fused conv2 weight gradient does not cover this configuration"); return GEECO_ERR_INVALID; }
     return r < 0 ? -r : GEECO_OK;
   }
   if (!strcmp(name, "bwd21")) {
@@ -488,8 +546,13 @@ int encoders_bwd_bf16(geeco_ctx* c, int lhi, int llo, cudaStream_t st) {
       const long long in_off = L.grouped ? 0 : (long long)e * N * L.Hin * L.Hin * L.Cin_pad;
       const __nv_bfloat16* gy = (const __nv_bfloat16*)L.g + (L.grouped ? 0 : L.act_off[e]);
       TcGeom g = L.grouped ? B.fwd : tc_fwd_geom(L.Hin, L.Hin, L.Cin_pad, L.Cout[e], L.stride, N, 1);
-      int rc = launch_tc_wgrad(g, L.Cout[e], L.Cin_real, xin + in_off, gy, c->grad + c->params[L.p_w[e]].offset,
-                               c->grad + c->params[L.p_b[e]].offset, bp->partial, bp->partial_cap, wstride, bstride, st);
+      int rc = 0;
+      // conv2: y1 is recomputed on chip instead of read (it was not stored)
+      const int fused_wg = l == 1 ? try_wgrad2(c, bp, st) : 0;
+      if (fused_wg < 0) return -fused_wg;
+      if (fused_wg == 0)
+        rc = launch_tc_wgrad(g, L.Cout[e], L.Cin_real, xin + in_off, gy, c->grad + c->params[L.p_w[e]].offset,
+                             c->grad + c->params[L.p_b[e]].offset, bp->partial, bp->partial_cap, wstride, bstride, st);
       if (rc) return rc;
       if (l == 0) continue;
       if (l == 1 && llo == 0) {
