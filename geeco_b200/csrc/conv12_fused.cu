@@ -35,12 +35,13 @@ constexpr int C1 = 32, C2 = 48;
 constexpr int SLOT_PAIRS = 136;                // 128 pixel pairs of a y1 row + zero pairs (the kx = 2 window reads pair 128)
 constexpr int SLOT_BYTES = SLOT_PAIRS * 128;   // 17408 = 17 swizzle atoms
 constexpr int A1_BYTES = 128 * 128;            // conv1 im2col tile: 128 pixels x 64 K (bf16)
-constexpr int B1_BYTES = C1 * 128;
+constexpr int B1_BYTES = 2 * C1 * 128;         // conv1's packed weights: 32 rows (per pixel) or 64 rows (per pixel pair)
 constexpr int B2_SLOT = C2 * 128;              // one (ky, pair) k-block of conv2's packed weights
 constexpr int B2_BYTES = 6 * B2_SLOT;
 constexpr int S1 = 4;                          // im2col stages
 constexpr int RING = 6;                        // y1 row slots
 constexpr int NB1 = 8, NB2 = 2;                // accumulator buffers: conv1 (32 columns each), conv2 (64-column stride)
+constexpr int NB1P = 4;                        // pixel-pair conv1: 64 columns per buffer (the same TMEM columns [0, 256))
 constexpr int THREADS = 20 * 32;                // 4 producer, 8 + 4 epilogue, 3 MMA warps, 1 TMA warp
 constexpr int Y2_STAGE = 32 * C2 * 2;           // 3 KB: the 32 pixels x 48 channels one conv2-epilogue warp stores per unit
 constexpr int SMEM_BYTES = 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024 + 4 * Y2_STAGE;
@@ -79,6 +80,14 @@ __device__ __forceinline__ void unit_rows(int u, int u_lo, int& r_begin, int& r_
   r_end = oy < 127 ? 2 * oy + 2 : 2 * oy + 1;
 }
 
+// PAIR: conv1 runs on pixel pairs.  A GEMM row is the pair (2t, 2t+1) of a y1 row, its K the 3 x 4 pixel window around
+// the pair (k = ky*16 + slot*4 + ch, slots = pixels 2t, 2t+1, 2t-1, 2t+2: 16 + 8 + 8 byte copies per window row, half the
+// copies and shared-memory wavefronts of the per-pixel im2col), its N the 64 values (p, co) -- which is exactly the ring
+// row conv2 consumes, so one thread writes one whole ring row.  One MMA tile = one y1 row (4 K = 16 steps of N = 64)
+// instead of two half rows (3 steps of N = 32 each).  The packed weights are the mode-5 copy (pack_value).  Same
+// products as the per-pixel form, summed in a different order inside the tensor core: y1 agrees to fp32 rounding, not
+// bit for bit (tests/test_gpu_fused12.py holds the per-pixel form to bit-identity with the separate kernels).
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, const __grid_constant__ CUtensorMap w2map,
                     const __grid_constant__ CUtensorMap y1map) {
@@ -112,7 +121,7 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S1; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
     for (int b = 0; b < NB1; ++b) { mbar_init(&t1_full[b], 1); mbar_init(&t1_empty[b], 128); }
-    for (int r = 0; r < RING; ++r) { mbar_init(&y_full[r], 256); mbar_init(&y_empty[r], store_y1 ? 2 : 1); }
+    for (int r = 0; r < RING; ++r) { mbar_init(&y_full[r], PAIR ? 128 : 256); mbar_init(&y_empty[r], store_y1 ? 2 : 1); }
     for (int b = 0; b < NB2; ++b) { mbar_init(&t2_full[b], 1); mbar_init(&t2_empty[b], 128); }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -122,10 +131,12 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   for (int i = threadIdx.x * 16; i < RING * SLOT_BYTES; i += THREADS * 16) *reinterpret_cast<uint4*>(ring + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x < C2) bias2_s[threadIdx.x] = a.bias2[(long long)group * a.bias2_group_stride + threadIdx.x];
   __syncthreads();
-  // conv1's bias rides in the GEMM: im2col column 36 is a constant 1.0 (the packed weights hold the bias there)
+  // conv1's bias rides in the GEMM: im2col column 36 (pixel pairs: 48) is a constant 1.0 (the packed weights hold the
+  // bias there)
   for (int i = threadIdx.x; i < S1 * 128; i += THREADS) {
     const int st_i = i >> 7, r = i & 127;
-    *reinterpret_cast<uint16_t*>(a1 + st_i * A1_BYTES + r * 128 + ((4 ^ (r & 7)) << 4) + 8) = 0x3f80;
+    if (PAIR) *reinterpret_cast<uint16_t*>(a1 + st_i * A1_BYTES + r * 128 + ((6 ^ (r & 7)) << 4)) = 0x3f80;
+    else *reinterpret_cast<uint16_t*>(a1 + st_i * A1_BYTES + r * 128 + ((4 ^ (r & 7)) << 4) + 8) = 0x3f80;
   }
   fence_proxy_async();
   if (warp == 16) tmem_alloc(tmem_ptr_s, 512);
@@ -136,7 +147,37 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   const uint32_t tmem_base = *tmem_ptr_s;
   const long long gimg0 = (long long)group * a.M;               // first image of this encoder group
 
-  if (warp < 4) {
+  if (PAIR && warp < 4) {
+    // ===================== conv1 producers on pixel pairs: one y1 row (128 pairs) per stage =====================
+    const int t = threadIdx.x;
+    const uint32_t sw = (uint32_t)t & 7u;
+    const uint32_t a_row0 = smem_u32(a1) + (uint32_t)t * 128u;
+    const bool okl = t >= 1, okr = t <= 126;
+    uint32_t s = 0, sphase = 0;
+    for (int u = u_lo; u < u_hi; ++u) {
+      int r_begin, r_end;
+      unit_rows(u, u_lo, r_begin, r_end);
+      const long long gi = gimg0 + (u >> 7);
+      for (int r = r_begin; r <= r_end; ++r) {
+        // pixel (r - 1, 2t) of the image; a window row / pixel outside the image copies zero bytes
+        const char* sp = reinterpret_cast<const char*>(a.x0) + (((gi * HW + (r - 1)) * HW) + 2 * t) * 8;
+        mbar_wait(&a_empty[s], sphase ^ 1u);
+        const uint32_t d0 = a_row0 + s * (uint32_t)A1_BYTES;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const bool ok = (unsigned)(r - 1 + ky) < (unsigned)HW;
+          const uint32_t ca = d0 + (((uint32_t)(2 * ky) ^ sw) << 4), cb = d0 + (((uint32_t)(2 * ky + 1) ^ sw) << 4);
+          const char* p = ok ? sp : reinterpret_cast<const char*>(a.x0) + 8;
+          cp_async16(ca, p, ok ? 16u : 0u);                                   // pixels 2t, 2t+1
+          cp_async8(cb, p - 8, (ok && okl) ? 8u : 0u);                         // pixel 2t-1
+          cp_async8(cb + 8, ok && okr ? p + 16 : p, (ok && okr) ? 8u : 0u);    // pixel 2t+2
+          sp += HW * 8;
+        }
+        cp_async_mbar_arrive_noinc(&a_full[s]);
+        if (++s == S1) { s = 0; sphase ^= 1u; }
+      }
+    }
+  } else if (warp < 4) {
     // ===================== conv1 producers: one half row (128 pixels) per stage =====================
     const int t = threadIdx.x;
     const uint32_t rsw4 = ((uint32_t)t & 7u) << 4;
@@ -170,6 +211,64 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
           cp_async_mbar_arrive_noinc(&a_full[s]);
           if (++s == S1) { s = 0; sphase ^= 1u; }
         }
+      }
+    }
+  } else if (PAIR && warp < 12) {
+    // ===================== conv1 epilogue on pixel pairs: thread = pair of the y1 row, set h takes every other row ==========
+    const int we = warp - 4, h = we >> 2, quad = we & 3;
+    const uint32_t pair = (uint32_t)(quad * 32 + lane);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t slot_off = pair * 128u, psw = pair & 7u;
+    const uint32_t ring_u32 = smem_u32(ring);
+    uint2* bits2 = reinterpret_cast<uint2*>(a.bits1);
+    uint32_t q = 0;                                             // y1 rows produced so far by this CTA
+    for (int u = u_lo; u < u_hi; ++u) {
+      int r_begin, r_end;
+      unit_rows(u, u_lo, r_begin, r_end);
+      const long long gi = gimg0 + (u >> 7);
+      for (int r = r_begin; r <= r_end; ++r, ++q) {
+        if ((q & 1u) != (uint32_t)h) continue;
+        const uint32_t slot = q % RING, use = q / RING;
+        const uint32_t buf = q % NB1P, tuse = q / NB1P;
+        mbar_wait(&t1_full[buf], tuse & 1u);
+        tc_fence_after();
+        uint32_t o[32];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + buf * 64u + (uint32_t)pp * 32u, v);
+          tmem_ld_wait();
+          if (pp == 1) {
+            tc_fence_before();
+            mbar_arrive(&t1_empty[buf]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[pp * 16 + i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+        }
+        if (a.bits1) {
+          uint32_t w2[2];
+#pragma unroll
+          for (int pp = 0; pp < 2; ++pp) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t acc = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[pp * 16 + hh * 8 + i] + 0x7fff7fffu) & 0x80008000u);
+              w |= (((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u)) << (16 * hh);
+            }
+            w2[pp] = w;
+          }
+          bits2[((gi * HW + r) * HW) / 2 + pair] = make_uint2(w2[0], w2[1]);
+        }
+        // the slot's previous row has been consumed by conv2 (and read by the y1 store)
+        mbar_wait(&y_empty[slot], (use & 1u) ^ 1u);
+        const uint32_t srow = ring_u32 + slot * (uint32_t)SLOT_BYTES + slot_off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          st_shared_v4(srow + (((uint32_t)c ^ psw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        fence_proxy_async();
+        mbar_arrive(&y_full[slot]);
       }
     }
   } else if (warp < 12) {
@@ -264,6 +363,35 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
       }
     }
     if (lane == 0) bulk_wait0();                                   // global writes performed before the CTA retires
+  } else if (PAIR && (warp == 16 || warp == 19)) {
+    // ===================== conv1 MMA issuers on pixel pairs: warp 16 takes the even rows q, warp 19 the odd ones ==========
+    const uint32_t idesc1 = make_idesc_bf16(128, 2 * C1, 0, 0);
+    const uint64_t dtempl = make_desc_sw128(0, 16, 1024);
+    const uint32_t a1_16 = smem_u32(a1) >> 4, b1_16 = smem_u32(b1) >> 4;
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    const uint32_t par = warp == 16 ? 0u : 1u;
+    uint32_t q = 0;
+    for (int u = u_lo; u < u_hi; ++u) {
+      int r_begin, r_end;
+      unit_rows(u, u_lo, r_begin, r_end);
+      for (int r = r_begin; r <= r_end; ++r, ++q) {
+        if ((q & 1u) != par) continue;
+        const uint32_t s = q % S1, sphase = (q / S1) & 1u, buf = q % NB1P, bphase = (q / NB1P) & 1u;
+        mbar_wait(&t1_empty[buf], bphase ^ 1u);
+        mbar_wait(&a_full[s], sphase);
+        tc_fence_after();
+        const uint32_t a16 = a1_16 + s * (uint32_t)(A1_BYTES >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)      // K = 3 window rows x 16 + the bias column: four K = 16 steps
+            tc_mma(tmem_base + buf * 64u, dtempl | (uint64_t)(a16 + 2 * j), dtempl | (uint64_t)(b1_16 + 2 * j), idesc1, j != 0 ? 1u : 0u);
+          tc_commit(&a_empty[s]);
+          tc_commit(&t1_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 16 || warp == 19) {
     // ===================== conv1 MMA issuers (whole warp runs the loop, one elected lane issues) =====================
     // warp 16 issues the left half rows (even tiles), warp 19 the right ones: one warp spent ~2000 of the 2550 cycles
@@ -351,8 +479,8 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
   } else {
     // ===================== TMA warp: the weights of both layers once, then (training) the y1 stores =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, (uint32_t)(B1_BYTES + B2_BYTES));
-      tma_load_2d(smem_u32(b1), &w1map, w_full, 0, group * C1);
+      mbar_arrive_expect_tx(w_full, (uint32_t)((PAIR ? 2 : 1) * C1 * 128 + B2_BYTES));
+      tma_load_2d(smem_u32(b1), &w1map, w_full, 0, group * (PAIR ? 2 * C1 : C1));
       for (int sl = 0; sl < 6; ++sl) tma_load_2d(smem_u32(b2 + sl * B2_SLOT), &w2map, w_full, sl * 64, group * C2);
     }
     // ring slot -> y1 in HBM, one TMA tensor store per finished row
@@ -393,7 +521,7 @@ bool tc_conv12_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int st
 
 int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CUtensorMap* w2map, const float* bias2,
                      long long bias2_group_stride, __nv_bfloat16* y1, unsigned short* bits1, __nv_bfloat16* y2,
-                     unsigned short* bits2, int G, int M, cudaStream_t st) {
+                     unsigned short* bits2, int G, int M, cudaStream_t st, const CUtensorMap* w1pair_map) {
   if (G < 1 || M < 1) return GEECO_OK;
   const long long pairs = (long long)G * M * HW * 128;
   if (pairs >= (1ll << 31)) { geeco_set_error("conv12: %lld pixel pairs exceed the 2^31 the store coordinates hold", pairs); return GEECO_ERR_INVALID; }
@@ -409,9 +537,11 @@ int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CU
   C12Args a;
   a.x0 = x0; a.y1 = y1; a.bits1 = reinterpret_cast<unsigned int*>(bits1); a.y2 = y2; a.bits2 = bits2; a.bias2 = bias2;
   a.bias2_group_stride = bias2_group_stride; a.M = M; a.cpg = cpg;
-  CUDA_TRY(cudaFuncSetAttribute(conv12_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(cudaFuncSetAttribute(conv12_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GEECO_LAUNCH((conv12_fused_kernel), cpg * G, THREADS, SMEM_BYTES, st, a, *w1map, *w2map, y1map);
+  // w1pair_map: the pixel-pair copy of conv1's packed weights (mode 5) -> conv1 on pixel pairs
+  auto kern = w1pair_map ? conv12_fused_kernel<true> : conv12_fused_kernel<false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GEECO_LAUNCH((kern), cpg * G, THREADS, SMEM_BYTES, st, a, w1pair_map ? *w1pair_map : *w1map, *w2map, y1map);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;

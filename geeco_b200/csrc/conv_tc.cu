@@ -1208,6 +1208,18 @@ __device__ __forceinline__ float pack_value(const float* __restrict__ Wg0, int m
     if (kx < 0 || kx > 2 || c >= Cin) return 0.f;
     return Wg0[((long long)(ky * 3 + kx) * Cin + c) * Cout + r];
   }
+  if (mode == 5) {
+    // conv1 on pixel pairs inside the fused conv1 -> conv2 kernel (conv12_fused.cu): row r = p*Cout + co, column
+    // k = ky*16 + slot*4 + ch with the window slots = pixels 2t, 2t+1, 2t-1, 2t+2 of the pair's row (pair-relative
+    // column cx = 1, 2, 0, 3); output pixel p meets window column cx through tap kx = cx - p
+    if (k >= 48 || r >= 2 * Cout) return 0.f;
+    const int pp = r / Cout, co = r - pp * Cout;
+    const int ky = k >> 4, slot = (k >> 2) & 3, ch = k & 3;
+    const int cx = slot == 0 ? 1 : (slot == 1 ? 2 : (slot == 2 ? 0 : 3));
+    const int kx = cx - pp;
+    if (kx < 0 || kx > 2 || ch >= Cin) return 0.f;
+    return Wg0[((long long)(ky * 3 + kx) * Cin + ch) * Cout + co];
+  }
   if (mode == 4) {
     // forward stride-2 layer on pixel pairs (2*Cs == 64): k-block (ky, j) holds columns kx = 2j, 2j+1 of kernel row ky
     const int blk = k >> 6, e = k & 63, ky = blk >> 1, j = blk & 1, pp = e / Cs, c = e - pp * Cs;
@@ -1235,7 +1247,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W, __nv_bfloat16* 
     const long long rr = i / Kpad;
     const int r = (int)(rr % rows), grp = (int)(rr / rows);
     float v = pack_value(W + (long long)grp * w_group_stride, mode, Cin, Cout, Cs, ntaps, taps, Kt, r, k);
-    if (k == bias_col && r < Cout) v = bias[r];
+    if (k == bias_col && r < (mode == 5 ? 2 * Cout : Cout)) v = bias[mode == 5 ? r % Cout : r];
     out[i] = __float2bfloat16_rn(v);
   }
 }
@@ -1271,7 +1283,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackJob
       const uint32_t rr = i / Kp, k = i - rr * Kp;
       const uint32_t grp = rr / rows, r = rr - grp * rows;
       float v = pack_value(W + (long long)grp * wgs, mode, Cin, Cout, Cs, ntaps, jb.taps, Kt, (int)r, (int)k);
-      if ((int)k == bias_col && (int)r < Cout) v = bias[(long long)grp * bgs + r];
+      if ((int)k == bias_col && (int)r < (mode == 5 ? 2 * Cout : Cout)) v = bias[(long long)grp * bgs + (mode == 5 ? (int)r % Cout : (int)r)];
       out[i] = __float2bfloat16_rn(v);
     }
   }

@@ -120,7 +120,7 @@ int tc_num_sms();             // SM count the persistent grids are sized for (ho
 bool tc_conv12_supported(int H, int W, int Cin_pad, int Cout1, int Cout2, int stride1, int stride2, const TcGeom& g1);
 int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CUtensorMap* w2map, const float* bias2,
                      long long bias2_group_stride, __nv_bfloat16* y1, unsigned short* bits1, __nv_bfloat16* y2,
-                     unsigned short* bits2, int G, int M, cudaStream_t st);
+                     unsigned short* bits2, int G, int M, cudaStream_t st, const CUtensorMap* w1pair_map = nullptr);
 
 // conv2 data gradient -> conv1 weight gradient as one kernel (conv21_bwd_fused.cu): dL/d(pre-activation of conv1) stays
 // on chip.  dg = the four parity classes of the stride-2 layer in (py, px) order, wmaps their packed-weight maps.

@@ -22,6 +22,9 @@ struct Bf16Layer {
   TcGeom pg[2];
   __nv_bfloat16* w_pair[2];
   CUtensorMap pair_map[2];
+  // conv1 on pixel pairs inside the fused forward kernel: [G][64 rows (p, co)][64] (pack mode 5)
+  __nv_bfloat16* w_c12pair = nullptr;
+  CUtensorMap c12pair_map;
 };
 
 struct Bf16Plan {
@@ -114,6 +117,7 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
     for (int e = 0; e < G; ++e) { B.w_fwd[e] = base ? base + o : nullptr; o += (size_t)L.Cout[e] * B.fwd.Kpad; }
     for (int par = 0; par < 2; ++par)
       B.w_pair[par] = B.pair ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)G * L.Cout[0] * 64 * 2) : nullptr;
+    B.w_c12pair = (l == 0 && L.grouped && L.Cin_pad == 4 && L.Cout[0] == 32) ? (__nv_bfloat16*)carve(ws_off, ws_base, (size_t)G * 64 * 64 * 2) : nullptr;
     for (int ci = 0; ci < B.n_classes; ++ci) {
       size_t t2 = 0;
       for (int e = 0; e < G; ++e) t2 += (size_t)L.Cin_real * dgrad_kpad(B.dg[ci], L.Cout[e]);
@@ -167,6 +171,10 @@ int plan_bf16(geeco_ctx* c, size_t* ws_off, char* ws_base) {
         int rc = make_weight_tensor_map(&B.pair_map[par], B.w_pair[par], (long long)G * L.Cout[0], 64, L.Cout[0]);
         if (rc) return rc;
       }
+    }
+    if (B.w_c12pair) {
+      int rc = make_weight_tensor_map(&B.c12pair_map, B.w_c12pair, (long long)G * 64, 64, 64);
+      if (rc) return rc;
     }
     if (L.grouped) {
       int rc = make_weight_tensor_map(&B.fwd_map[0], B.w_fwd[0], (long long)G * L.Cout[0], B.fwd.Kpad, L.Cout[0]);
@@ -244,6 +252,9 @@ static int repack_weights(geeco_ctx* c, cudaStream_t st, int which = 4, int max_
           const long long bstride = b_group_stride(c, L);
           add_job(bp, fwd_table, W, B.w_fwd[e], B.fwd.wpack, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, L.Cout[e],
                   B.fwd.Kpad, B.fwd.Kt, B.fwd.bias_in_k ? c->theta + c->params[L.p_b[e]].offset : nullptr, bstride, B.fwd.Ktot);
+          if (B.w_c12pair && e == 0)
+            add_job(bp, fwd_table, W, B.w_c12pair, 5, groups, wstride, L.Cin_real, L.Cout[e], L.Cin_pad, 9, kAllTaps, 64, 64, 0,
+                    c->theta + c->params[L.p_b[e]].offset, bstride, 48);
         }
         for (int ci = 0; ci < B.n_classes; ++ci) {
           const int Kp = dgrad_kpad(B.dg[ci], L.Cout[e]);
@@ -376,10 +387,15 @@ static int try_conv12(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
   if (!conv12_applies(c, bp)) return 0;
   // y1 stays on chip between the layers; inference does not write it at all, training only when a kernel will read it
   const bool store_y1 = c->cfg.training && !wgrad2_recompute(c, bp);
+  // conv1 on pixel pairs: opt-in experiment (GEECO_CONV12_PAIR=1).  Half the im2col copies and a third fewer operand
+  // reads, but measured SLOWER on B200 (315 vs 275 us at batch 64: no unit saturated, the longer per-row chain of one
+  // epilogue set per row stalls the ring; profiles/r02_ncu_notes.md).  Never together with the y1-rebuilding weight
+  // gradient: the two forms sum the same products in a different order, and the rebuilt rows must be the forward's.
+  const bool pair = B.w_c12pair != nullptr && !wgrad2_recompute(c, bp) && getenv("GEECO_CONV12_PAIR") != nullptr;
   int rc = launch_tc_conv12((const __nv_bfloat16*)c->x0, &B.fwd_map[0], &bp->L[1].fwd_map[0],
                             c->theta + c->params[L1.p_b[0]].offset, b_group_stride(c, L1),
                             store_y1 ? (__nv_bfloat16*)L.y : nullptr, (unsigned short*)L.mbits, (__nv_bfloat16*)L1.y,
-                            (unsigned short*)L1.mbits, c->G, c->M, st);
+                            (unsigned short*)L1.mbits, c->G, c->M, st, pair ? &B.c12pair_map : nullptr);
   c->y1_stale = c->cfg.training && !store_y1;
   return rc ? -rc : 1;
 }
