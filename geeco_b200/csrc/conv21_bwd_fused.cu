@@ -24,8 +24,9 @@
 //                   columns 2ox-1 .. 2ox+2) x 4 channels = 64 values = 128 bytes, 3 cp.async per window row (16 + 8 + 8
 //                   bytes): every tap of every class is one of its columns.
 //   weight gradient D2[(py, px, co)][(wy, cx, ch)] += [G1 tile py=0 | G1 tile py=1]^T x window tile: M = 128, N = 64,
-//                   K = 128 pairs = 8 MMAs per unit; ky = wy - py, kx = cx - px.  The bias gradient is a second MMA of the
-//                   same A against a constant tile whose first column is 1.0 (N = 16).  One accumulator for the whole
+//                   K = 128 pairs = 8 MMAs per unit; ky = wy - py, kx = cx - px.  The bias gradient rides in the same MMAs:
+//                   N = 80, whose second 64-column atom is a constant tile with 1.0 in its first column (a separate
+//                   N = 16 MMA re-read the whole A operand: a fifth of all operand reads).  One accumulator for the whole
 //                   CTA, written once at the end as a 33 KB partial; a small kernel sums the partials of a group in a
 //                   fixed order (deterministic).
 //
@@ -45,7 +46,7 @@ constexpr int HW = 256;                        // height = width of x0 / y1 / G1
 constexpr int C1 = 32, C2 = 48;
 constexpr int ROW_PIX = 136;                   // G2 row box: pixels -1 .. 134 (zero-filled outside 0 .. 127)
 constexpr int ROW_BYTES = ROW_PIX * 128;       // 64-channel (48 real) rows of 128 bytes
-constexpr int RG = 4;                          // G2 row ring
+constexpr int RG = 3;                          // G2 row ring
 constexpr int W_SLOT = C1 * 128;               // one (class, tap) k-block of the packed data-gradient weights: 32 x 64
 constexpr int W_BYTES = 9 * W_SLOT;
 constexpr int TILE = 128 * 128;                // G1 tile / window tile: 128 pixel pairs x 128 bytes
@@ -54,7 +55,7 @@ constexpr int NX = 3;                          // window tiles in flight
 constexpr int NB = 2;                          // data-gradient accumulators (128 columns each)
 constexpr int THREADS = 15 * 32;
 constexpr int ACC_COL = 256;                   // weight-gradient accumulator: TMEM columns [256, 320), bias gradient [320, 336)
-constexpr int ONES_BYTES = 16 * 128;           // constant B tile of the bias-gradient MMA: 16 K rows, column 0 = 1.0
+constexpr int ONES_BYTES = 128 * 128;          // constant second N atom of the weight-gradient B operand: column 0 = 1.0
 constexpr int PART_FLOATS = 128 * 64 + 128;    // per-CTA partial: D2 and the bias column
 constexpr int SMEM_BYTES = 1024 + W_BYTES + RG * ROW_BYTES + NG1 * 2 * TILE + NX * TILE + ONES_BYTES + 1024;
 
@@ -116,7 +117,7 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
   // constant operand of the bias gradient: column 0 of every K row is 1.0 (bf16 0x3f80), the rest zero
   for (int i = threadIdx.x * 16; i < ONES_BYTES; i += THREADS * 16) *reinterpret_cast<uint4*>(ones + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (threadIdx.x < 16) *reinterpret_cast<uint16_t*>(ones + threadIdx.x * 128 + ((threadIdx.x & 7) << 4)) = 0x3f80;
+  if (threadIdx.x < 128) *reinterpret_cast<uint16_t*>(ones + threadIdx.x * 128 + ((threadIdx.x & 7) << 4)) = 0x3f80;
   fence_proxy_async();
   if (warp == 12) tmem_alloc(tmem_ptr_s, 512);
   if (warp == 14 && lane == 0) {
@@ -278,9 +279,8 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
     }
   } else if (warp == 13) {
     // ===================== weight-gradient MMA issuer: one item per unit =====================
-    const uint32_t idw = make_idesc_bf16(128, 64, 1, 1), idb = make_idesc_bf16(128, 16, 1, 1);
+    const uint32_t idw = make_idesc_bf16(128, 80, 1, 1);
     const uint64_t adesc = make_desc_sw128(0, TILE, 1024);        // two M atoms (py = 0, 1), TILE bytes apart
-    const uint64_t bdesc = make_desc_sw128(0, 8192, 1024);
     const uint32_t g16 = smem_u32(g1t) >> 4, x16 = smem_u32(xt) >> 4, ones16 = smem_u32(ones) >> 4;
     const uint32_t dacc = tmem_base + (uint32_t)ACC_COL;
     uint32_t s = 0, sphase = 0, gb = 0, gphase = 0;
@@ -290,12 +290,12 @@ conv21_bwd_fused_kernel(const B21Args a, const __grid_constant__ B21Maps wmaps, 
       tc_fence_after();
       const uint32_t a16 = g16 + gb * (uint32_t)(2 * TILE >> 4), b16 = x16 + s * (uint32_t)(TILE >> 4);
       const uint32_t acc = u != u_lo ? 1u : 0u;
+      // B = [window tile | ones tile]: the second N atom sits (ones - tile) bytes after the first
+      const uint64_t bdesc = make_desc_sw128(0, (ones16 - b16) << 4, 1024);
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {      // 8 x 16 pixel pairs
+        for (int j = 0; j < 8; ++j)        // 8 x 16 pixel pairs
           tc_mma(dacc, adesc | (uint64_t)(a16 + j * 128), bdesc | (uint64_t)(b16 + j * 128), idw, j != 0 ? 1u : acc);
-          tc_mma(dacc + 64, adesc | (uint64_t)(a16 + j * 128), bdesc | (uint64_t)ones16, idb, j != 0 ? 1u : acc);
-        }
         tc_commit(&g1_empty[gb]);
         tc_commit(&x_empty[s]);
       }
