@@ -486,6 +486,13 @@ def kernel_rooflines(eng, dev, peaks, args):
     fused_bwd['limiter'] = 'shared-memory data pipe (MMA operand reads + staging stores), see profiles/r02_ncu_notes.md'
   except Exception as exc:                      # GEECO_NO_FUSE_BWD21=1 or another image size
     sys.stderr.write('fused conv2-dgrad -> conv1-wgrad kernel not timed: %s\n' % exc)
+  # the step's conv2 weight gradient: whole y1 rows by TMA into a ring, windows stacked into M = 128 (conv2_wgrad_fused.cu)
+  rows_wg = None
+  try:
+    sec = _timed(dev, lambda: eng.profile_kernel('wgrad2'), flush=flush)
+    rows_wg = entry('conv2_wgrad_rows_kernel conv2 wgrad', sec, (P1 * 32 + P2 * 48) * 2, 2.0 * P2 * 48 * 288, launches=2)
+  except Exception as exc:
+    sys.stderr.write('row-wise conv2 weight gradient not timed: %s\n' % exc)
   sec = _timed(dev, lambda: ops.conv2d_same_bf16(x1, w1, b1, stride=1), flush=flush)
   entry('tc_nn_kernel<4,4> conv1 fwd', sec, P1 * (4 + 32) * 2, 2.0 * P1 * 32 * 27, launches=2)
   sec = _timed(dev, lambda: ops.conv2d_same_bwd_bf16(x1, w1, g1, stride=1, need_dx=False), flush=flush)
@@ -540,10 +547,10 @@ def kernel_rooflines(eng, dev, peaks, args):
       e['bound'] = 'tensor'
     del x, w, b, g, bits
     Hin, Cin = Ho, Cout
-  # `roofline` = the longest kernel the step actually runs: the fused conv1 -> conv2 forward, conv2's weight gradient or
-  # the fused backward (the separate conv2 data gradient only where the fused kernels do not apply)
+  # `roofline` = the longest kernel the step actually runs: the fused conv1 -> conv2 forward, conv2's (row-wise) weight
+  # gradient or the fused backward (the separate kernels only where the fused ones do not apply)
   if fused is not None:
-    dom = max([e for e in (fused, wg2, fused_bwd) if e is not None], key=lambda e: e['ms'])
+    dom = max([e for e in (fused, rows_wg if rows_wg is not None else wg2, fused_bwd) if e is not None], key=lambda e: e['ms'])
   return dom, out
 
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libgeeco_b200.so')
 SOURCES = ['geeco_api.cu', 'rankpool.cu', 'conv_fp32.cu', 'tail.cu', 'step_bf16.cu', 'conv_tc.cu', 'conv12_fused.cu', 'conv21_bwd_fused.cu', 'conv2_wgrad_fused.cu', 'lstm_seq.cu', 'lstm_persistent.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+NVCC_FLAGS = (os.environ.get('GEECO_NVCC_EXTRA', '').split()) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
 

@@ -38,13 +38,14 @@ constexpr int A1_BYTES = 128 * 128;            // conv1 im2col tile: 128 pixels 
 constexpr int B1_BYTES = 2 * C1 * 128;         // conv1's packed weights: 32 rows (per pixel) or 64 rows (per pixel pair)
 constexpr int B2_SLOT = C2 * 128;              // one (ky, pair) k-block of conv2's packed weights
 constexpr int B2_BYTES = 6 * B2_SLOT;
-constexpr int S1 = 4;                          // im2col stages
-constexpr int RING = 6;                        // y1 row slots
+// im2col stages S1 and y1 row slots RING are template arguments of the kernel: training (the y1 store holds ring slots
+// longer, the producers are the critical path) runs best with 6 stages / 4 slots (263 vs 275 us), inference with 4 / 6
+// (3.42 vs 3.57 ms per 3072 images); both fill the 227 KB
 constexpr int NB1 = 8, NB2 = 2;                // accumulator buffers: conv1 (32 columns each), conv2 (64-column stride)
 constexpr int NB1P = 4;                        // pixel-pair conv1: 64 columns per buffer (the same TMEM columns [0, 256))
 constexpr int THREADS = 20 * 32;                // 4 producer, 8 + 4 epilogue, 3 MMA warps, 1 TMA warp
 constexpr int Y2_STAGE = 32 * C2 * 2;           // 3 KB: the 32 pixels x 48 channels one conv2-epilogue warp stores per unit
-constexpr int SMEM_BYTES = 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024 + 4 * Y2_STAGE;
+constexpr int smem_bytes(int S1, int RING) { return 1024 + S1 * A1_BYTES + B1_BYTES + B2_BYTES + RING * SLOT_BYTES + 1024 + 4 * Y2_STAGE; }
 
 __device__ __forceinline__ void cp_async8(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -87,7 +88,7 @@ __device__ __forceinline__ void unit_rows(int u, int u_lo, int& r_begin, int& r_
 // instead of two half rows (3 steps of N = 32 each).  The packed weights are the mode-5 copy (pack_value).  Same
 // products as the per-pixel form, summed in a different order inside the tensor core: y1 agrees to fp32 rounding, not
 // bit for bit (tests/test_gpu_fused12.py holds the per-pixel form to bit-identity with the separate kernels).
-template <bool PAIR>
+template <bool PAIR, int S1, int RING>
 __global__ void __launch_bounds__(THREADS, 1)
 conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, const __grid_constant__ CUtensorMap w2map,
                     const __grid_constant__ CUtensorMap y1map) {
@@ -538,10 +539,12 @@ int launch_tc_conv12(const __nv_bfloat16* x0, const CUtensorMap* w1map, const CU
   a.x0 = x0; a.y1 = y1; a.bits1 = reinterpret_cast<unsigned int*>(bits1); a.y2 = y2; a.bits2 = bits2; a.bias2 = bias2;
   a.bias2_group_stride = bias2_group_stride; a.M = M; a.cpg = cpg;
   // w1pair_map: the pixel-pair copy of conv1's packed weights (mode 5) -> conv1 on pixel pairs
-  auto kern = w1pair_map ? conv12_fused_kernel<true> : conv12_fused_kernel<false>;
+  const bool deep = y1 != nullptr && !w1pair_map && getenv("GEECO_CONV12_SHALLOW") == nullptr;   // training: 6 stages, 4 slots
+  auto kern = w1pair_map ? conv12_fused_kernel<true, 4, 6> : (deep ? conv12_fused_kernel<false, 6, 4> : conv12_fused_kernel<false, 4, 6>);
+  const int smem = deep ? smem_bytes(6, 4) : smem_bytes(4, 6);
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  GEECO_LAUNCH((kern), cpg * G, THREADS, SMEM_BYTES, st, a, w1pair_map ? *w1pair_map : *w1map, *w2map, y1map);
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  GEECO_LAUNCH((kern), cpg * G, THREADS, smem, st, a, w1pair_map ? *w1pair_map : *w1map, *w2map, y1map);
   geeco_count_launch(1);
   CUDA_TRY(cudaGetLastError());
   return GEECO_OK;
