@@ -88,6 +88,8 @@ __device__ __forceinline__ void unit_rows(int u, int u_lo, int& r_begin, int& r_
 // instead of two half rows (3 steps of N = 32 each).  The packed weights are the mode-5 copy (pack_value).  Same
 // products as the per-pixel form, summed in a different order inside the tensor core: y1 agrees to fp32 rounding, not
 // bit for bit (tests/test_gpu_fused12.py holds the per-pixel form to bit-identity with the separate kernels).
+// Opt-in (GEECO_CONV12_PAIR=1): the LSU wavefronts drop from 78 % to 43 %, but training is slower (322 vs 266 us: the
+// epilogue waits for ring slots the y1 store still holds) and inference gains only 2.4 % (3.38 vs 3.46 ms per 3072 images).
 template <bool PAIR, int S1, int RING>
 __global__ void __launch_bounds__(THREADS, 1)
 conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, const __grid_constant__ CUtensorMap w2map,
@@ -121,8 +123,8 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S1; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
-    for (int b = 0; b < NB1; ++b) { mbar_init(&t1_full[b], 1); mbar_init(&t1_empty[b], 128); }
-    for (int r = 0; r < RING; ++r) { mbar_init(&y_full[r], PAIR ? 128 : 256); mbar_init(&y_empty[r], store_y1 ? 2 : 1); }
+    for (int b = 0; b < NB1; ++b) { mbar_init(&t1_full[b], 1); mbar_init(&t1_empty[b], PAIR ? 256 : 128); }
+    for (int r = 0; r < RING; ++r) { mbar_init(&y_full[r], 256); mbar_init(&y_empty[r], store_y1 ? 2 : 1); }
     for (int b = 0; b < NB2; ++b) { mbar_init(&t2_full[b], 1); mbar_init(&t2_empty[b], 128); }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -215,59 +217,49 @@ conv12_fused_kernel(const C12Args a, const __grid_constant__ CUtensorMap w1map, 
       }
     }
   } else if (PAIR && warp < 12) {
-    // ===================== conv1 epilogue on pixel pairs: thread = pair of the y1 row, set h takes every other row ==========
+    // ===================== conv1 epilogue on pixel pairs: thread = (pair, pixel h of the pair) of the y1 row =====================
+    // (one set of 4 warps per row with both pixels per thread was the first version: twice the per-row latency, the
+    //  ring ran dry)
     const int we = warp - 4, h = we >> 2, quad = we & 3;
     const uint32_t pair = (uint32_t)(quad * 32 + lane);
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)h * 32u;
     const uint32_t slot_off = pair * 128u, psw = pair & 7u;
     const uint32_t ring_u32 = smem_u32(ring);
-    uint2* bits2 = reinterpret_cast<uint2*>(a.bits1);
     uint32_t q = 0;                                             // y1 rows produced so far by this CTA
     for (int u = u_lo; u < u_hi; ++u) {
       int r_begin, r_end;
       unit_rows(u, u_lo, r_begin, r_end);
       const long long gi = gimg0 + (u >> 7);
       for (int r = r_begin; r <= r_end; ++r, ++q) {
-        if ((q & 1u) != (uint32_t)h) continue;
         const uint32_t slot = q % RING, use = q / RING;
         const uint32_t buf = q % NB1P, tuse = q / NB1P;
         mbar_wait(&t1_full[buf], tuse & 1u);
         tc_fence_after();
-        uint32_t o[32];
+        uint32_t v[32];
+        tmem_ld32(lane_addr + buf * 64u, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&t1_empty[buf]);
+        uint32_t o[16];
 #pragma unroll
-        for (int pp = 0; pp < 2; ++pp) {
-          uint32_t v[32];
-          tmem_ld32(lane_addr + buf * 64u + (uint32_t)pp * 32u, v);
-          tmem_ld_wait();
-          if (pp == 1) {
-            tc_fence_before();
-            mbar_arrive(&t1_empty[buf]);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[pp * 16 + i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        }
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
         if (a.bits1) {
-          uint32_t w2[2];
+          uint32_t w = 0;
 #pragma unroll
-          for (int pp = 0; pp < 2; ++pp) {
-            uint32_t w = 0;
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t acc = 0;
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint32_t acc = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[pp * 16 + hh * 8 + i] + 0x7fff7fffu) & 0x80008000u);
-              w |= (((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u)) << (16 * hh);
-            }
-            w2[pp] = w;
+            for (int i = 0; i < 8; ++i) acc = (acc >> 1) | ((o[hh * 8 + i] + 0x7fff7fffu) & 0x80008000u);
+            w |= (((acc >> 8) & 0xffu) | ((acc >> 16) & 0xff00u)) << (16 * hh);
           }
-          bits2[((gi * HW + r) * HW) / 2 + pair] = make_uint2(w2[0], w2[1]);
+          a.bits1[(gi * HW + r) * HW + 2 * pair + (uint32_t)h] = w;
         }
         // the slot's previous row has been consumed by conv2 (and read by the y1 store)
         mbar_wait(&y_empty[slot], (use & 1u) ^ 1u);
         const uint32_t srow = ring_u32 + slot * (uint32_t)SLOT_BYTES + slot_off;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          st_shared_v4(srow + (((uint32_t)c ^ psw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        for (int j = 0; j < 4; ++j)
+          st_shared_v4(srow + ((((uint32_t)h * 4u + (uint32_t)j) ^ psw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         fence_proxy_async();
         mbar_arrive(&y_full[slot]);
       }

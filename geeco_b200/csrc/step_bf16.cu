@@ -388,8 +388,8 @@ static int try_conv12(geeco_ctx* c, Bf16Plan* bp, cudaStream_t st) {
   // y1 stays on chip between the layers; inference does not write it at all, training only when a kernel will read it
   const bool store_y1 = c->cfg.training && !wgrad2_recompute(c, bp);
   // conv1 on pixel pairs: opt-in experiment (GEECO_CONV12_PAIR=1).  Half the im2col copies and a third fewer operand
-  // reads, but measured SLOWER on B200 (315 vs 275 us at batch 64: no unit saturated, the longer per-row chain of one
-  // epilogue set per row stalls the ring; profiles/r02_ncu_notes.md).  Never together with the y1-rebuilding weight
+  // reads, but measured SLOWER in training on B200 (322 vs 266 us at batch 64; inference 2.4 % faster;
+  // profiles/r02_ncu_notes.md).  Never together with the y1-rebuilding weight
   // gradient: the two forms sum the same products in a different order, and the rebuilt rows must be the forward's.
   const bool pair = B.w_c12pair != nullptr && !wgrad2_recompute(c, bp) && getenv("GEECO_CONV12_PAIR") != nullptr;
   int rc = launch_tc_conv12((const __nv_bfloat16*)c->x0, &B.fwd_map[0], &bp->L[1].fwd_map[0],
