@@ -812,7 +812,8 @@ template <int PIECE, int NPROD>
 __global__ void __launch_bounds__(NPROD + 160, NPROD == 256 ? 2 : 1)
 tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ G,
                 float* __restrict__ partial, int Cout, int n_chunks, int kb_per_split, int total_kb, int Mrows_pad,
-                int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk, const WgDirect direct) {
+                int ones_col, int tmem_cols, int stages, int gsub, int nsub_chunk, const WgDirect direct,
+                const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap amap, const TcCls kc, int cpt) {
   pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -833,7 +834,7 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int EPI_WARP0 = NPROD / 32, MMA_WARP = EPI_WARP0 + 4;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < stages; ++s) { mbar_init(&full[s], NPROD == 32 ? 1 : NPROD); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
@@ -863,7 +864,41 @@ tc_wgrad_kernel(const TcGeom g, const __nv_bfloat16* __restrict__ src, const __n
   if (kb_hi > total_kb) kb_hi = total_kb;
   const int nkb = kb_hi - kb_lo;
 
-  if (warp < EPI_WARP0 && PIECE == 4 && NPROD == 256 && g.rowwin && Cout == 32 && (Mg & 63u) == 0 && g.dsx == 1 && g.dsy == 1) {
+  if (NPROD == 32 && warp < EPI_WARP0) {
+    // ---- TMA-fed operands (stride-2 layers with >= 48 stored channels: conv3-conv8): no gather arithmetic at all.  A
+    // k-block is 64 consecutive GEMM rows = a (bw x bh x bn) block of output pixels; the G sub-tiles are 2-D boxes of
+    // G [pixels][Cout], an im2col sub-tile (tap, 64-channel chunk) is ONE 5-D box of the source (hardware zero-fill =
+    // SAME padding), exactly what tc_nn_kernel loads as its K-major A tile -- the same bytes are the MN-major B operand
+    // here.  The software gather spent ~290 instructions per thread and k-block and was issue-bound (r02 notes).
+    if (lane == 0) {
+      tma_prefetch_desc(&gmap);
+      tma_prefetch_desc(&amap);
+      const int sub0 = col0 >> 6;
+      int ng = 0;
+      for (int j = 0; j < gsub; ++j) ng += (mtile * 128 + j * 64) < Cout ? 1 : 0;
+      int nreal = 0;
+      for (int j = 0; j < nsub; ++j) nreal += (sub0 + j) * 64 < g.Ktot ? 1 : 0;
+      uint32_t s = 0, sphase = 0;
+      for (int it = 0; it < nkb; ++it) {
+        const uint32_t m0 = (uint32_t)(kb_lo + it) * 64;
+        int img0, y0, x0;
+        decode_pixel(g, m0, img0, y0, x0);
+        img0 += group * g.imgs_per_group;
+        mbar_wait(&empty[s], sphase ^ 1u);
+        uint8_t* st_p = st_base + s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], (uint32_t)((ng + nreal) * SUB));
+        for (int j = 0; j < ng; ++j)
+          tma_load_2d(smem_u32(st_p + j * SUB), &gmap, &full[s], mtile * 128 + j * 64, (int)((long long)group * Mg + m0));
+        int tap = sub0 / cpt, chunk = sub0 - tap * cpt;
+        for (int j = 0; j < nreal; ++j) {
+          tma_load_5d(smem_u32(st_p + (2 + j) * SUB), &amap, &full[s], kc.tc0[tap] + chunk * 64, x0 + kc.twq[tap], kc.thp[tap],
+                      y0 + kc.thq[tap], img0);
+          if (++chunk == cpt) { chunk = 0; ++tap; }
+        }
+        if (++s == (uint32_t)stages) { s = 0; sphase ^= 1u; }
+      }
+    }
+  } else if (warp < EPI_WARP0 && PIECE == 4 && NPROD == 256 && g.rowwin && Cout == 32 && (Mg & 63u) == 0 && g.dsx == 1 && g.dsy == 1) {
     // ---- conv1 (3/4 input channels, 32 filters): a k-block is 64 consecutive pixels of one image row.  Everything
     // that does not change from k-block to k-block is hoisted; per k-block a thread issues one 16-byte G copy
     // (thread = (row, 16-byte chunk of the 64-byte G row)) and, threads 0..191, the three 8-byte copies of one
@@ -1451,10 +1486,10 @@ static bool tc_rows_enabled() {
   static const bool off = getenv("GEECO_TC_NO_ROWS") != nullptr || getenv("GEECO_TC_NO_TMA") != nullptr;
   return !off;
 }
-static void tc_tile_block(const TcGeom& g, int* bw, int* bh, int* bn) {
-  *bw = g.Wm < 128 ? g.Wm : 128;
-  *bh = g.Hm < 128 / *bw ? g.Hm : 128 / *bw;
-  *bn = 128 / (*bw * *bh);
+static void tc_tile_block(const TcGeom& g, int* bw, int* bh, int* bn, int tile_px = 128) {
+  *bw = g.Wm < tile_px ? g.Wm : tile_px;
+  *bh = g.Hm < tile_px / *bw ? g.Hm : tile_px / *bw;
+  *bn = tile_px / (*bw * *bh);
 }
 // K layout of the packed weights for this geometry: per-tap extent Kt (Cs, or Cs rounded up to 64 for TMA)
 static void finish_k(TcGeom* g) {
@@ -1473,11 +1508,11 @@ static TcGeom gather_view(const TcGeom& g) {
 }
 
 // 5-D tensor map over a bf16 NHWC activation for the tile blocks of geometry g (see tc_use_tma)
-static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int row_box_pw = 0) {
+static int make_act_tensor_map(CUtensorMap* map, const void* base, const TcGeom& g, int row_box_pw = 0, int tile_px = 128) {
   PFN_encodeTiled fn = encode_tiled_fn();
   if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
   int bw, bh, bn;
-  tc_tile_block(g, &bw, &bh, &bn);
+  tc_tile_block(g, &bw, &bh, &bn, tile_px);
   if (row_box_pw > 0) { bw = row_box_pw; bh = 1; bn = 1; }       // row-resident kernel: one row of pw pixels per box
   const cuuint64_t imgs = (cuuint64_t)g.imgs_per_group * g.groups;
   const cuuint64_t row = (cuuint64_t)g.Ws * g.Cs * 2, img = row * g.Hs;
@@ -1915,6 +1950,30 @@ int launch_tc_nn(const TcGeom& g, const CUtensorMap* wmap, const __nv_bfloat16* 
   return launch_tc_nn_multi(&g, maps, 1, src, bias, mask, dst, dst_f32, epi, max_ctas, st, bits_out, wptr ? wp : nullptr);
 }
 
+// TMA-fed weight gradient (see tc_wgrad_kernel, NPROD == 32): stride-2 layers whose source tc_nn_kernel can box, whole
+// 64-channel blocks of G, k-blocks of 64 pixels that never straddle an encoder group.  OPT-IN (GEECO_TC_WGRAD_TMA=1):
+// correct (tests pass with it) but measured slower in situ -- conv3 132 vs 89 us, conv5 44 vs 39 us, conv4 / conv6-8
+// unchanged: every tap's box comes from L2 (9 x the source per k-block, ~11 TB/s aggregate = the L2 -> SM limit), while
+// the software gather's cp.async.ca copies find the overlapping taps of a k-block in L1.
+static bool wgrad_use_tma(const TcGeom& g_in, int Cout) {
+  static const bool on = getenv("GEECO_TC_WGRAD_TMA") != nullptr;
+  if (!on || g_in.sx != 2 || Cout % 64) return false;
+  TcGeom t = g_in;
+  t.rows = 0;
+  if (!tc_use_tma(t)) return false;
+  const long long Mg = (long long)g_in.imgs_per_group * g_in.Hm * g_in.Wm;
+  if (Mg % 64 || g_in.hw_shift < 0) return false;
+  return true;
+}
+// the geometry as the TMA-fed kernel sees it: every tap padded to whole 64-channel chunks, one more sub-tile for the
+// bias gradient's ones column
+static TcGeom wgrad_tma_view(const TcGeom& g) {
+  TcGeom v = g;
+  v.a_tma = 1; v.rows = 0; v.wpack = 0; v.bias_in_k = 0; v.Kt = (v.Cs + 63) / 64 * 64; v.Ktot = v.ntaps * v.Kt; v.Kpad = v.Ktot + 64;
+  return v;
+}
+static TcGeom wgrad_view(const TcGeom& g, int Cout) { return wgrad_use_tma(g, Cout) ? wgrad_tma_view(g) : gather_view(g); }
+
 struct WgradPlan { int m_tiles, n_chunks, nsub_chunk, splits, kb_per_split, total_kb, Mrows_pad, ones_col, gsub, stages, tmem_cols, per_sm; };
 
 static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
@@ -1959,7 +2018,7 @@ static WgradPlan wgrad_plan(const TcGeom& g, int Cout) {
 }
 
 long long tc_wgrad_partial_floats(const TcGeom& g_in, int Cout) {
-  const TcGeom g = gather_view(g_in);
+  const TcGeom g = wgrad_view(g_in, Cout);
   WgradPlan p = wgrad_plan(g, Cout);
   return (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad + 64;
 }
@@ -1973,8 +2032,9 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
   if (rc) return rc;
   WgradPlan p = wgrad_plan(g, Cout);
   *plan_out = p;
-  if (!partial || tc_wgrad_partial_floats(g, Cout) > partial_cap) {
-    geeco_set_error("tc_wgrad: partial buffer too small (%lld floats needed, %lld given)", tc_wgrad_partial_floats(g, Cout), partial_cap);
+  const long long need_floats = (long long)p.splits * g.groups * p.Mrows_pad * g.Kpad + 64;
+  if (!partial || need_floats > partial_cap) {
+    geeco_set_error("tc_wgrad: partial buffer too small (%lld floats needed, %lld given)", need_floats, partial_cap);
     return GEECO_ERR_WORKSPACE;
   }
   if (p.stages < 3) { geeco_set_error("tc_wgrad: stage does not fit 3 times"); return GEECO_ERR_INVALID; }
@@ -1991,6 +2051,29 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
       flag_set = v;
     }
   }
+  CUtensorMap gmap, amap;
+  memset(&gmap, 0, sizeof(gmap));
+  memset(&amap, 0, sizeof(amap));
+  TcCls kc;
+  memset(&kc, 0, sizeof(kc));
+  const bool tma = g.a_tma != 0;
+  const int cpt = tma ? g.Kt / 64 : 1;
+  if (tma) {
+    const long long Mg_ = (long long)g.imgs_per_group * g.Hm * g.Wm;
+    PFN_encodeTiled fn = encode_tiled_fn();
+    if (!fn) { geeco_set_error("cuTensorMapEncodeTiled not available from the driver"); return GEECO_ERR_CUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)Cout, (cuuint64_t)(Mg_ * g.groups)};
+    cuuint64_t gstr[1] = {(cuuint64_t)Cout * 2};
+    cuuint32_t box[2] = {64u, 64u};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(&gmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(G), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { geeco_set_error("cuTensorMapEncodeTiled (weight-gradient G, %d channels) failed with CUresult %d", Cout, (int)r); return GEECO_ERR_CUDA; }
+    rc = make_act_tensor_map(&amap, src, g, 0, 64);
+    if (rc) return rc;
+    fill_class(&kc, g);
+  }
 #define WG_LAUNCH(PIECE_, NPROD_)                                                                                   \
   do {                                                                                                              \
     CUDA_TRY(cudaFuncSetAttribute(tc_wgrad_kernel<PIECE_, NPROD_>, cudaFuncAttributePreferredSharedMemoryCarveout,  \
@@ -1999,9 +2082,10 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
                                   (int)smem));                                                                      \
     GEECO_LAUNCH((tc_wgrad_kernel<PIECE_, NPROD_>), grid, NPROD_ + 160, smem, st, g, src, G, partial, Cout, p.n_chunks,          \
                                                                       p.kb_per_split, p.total_kb, p.Mrows_pad, ones, \
-                                                                      p.tmem_cols, p.stages, p.gsub, p.nsub_chunk, direct);  \
+                                                                      p.tmem_cols, p.stages, p.gsub, p.nsub_chunk, direct, gmap, amap, kc, cpt);  \
   } while (0)
-  if (g.Cs == 4) { if (p.per_sm == 2) WG_LAUNCH(4, 256); else WG_LAUNCH(4, 512); }
+  if (tma) WG_LAUNCH(8, 32);
+  else if (g.Cs == 4) { if (p.per_sm == 2) WG_LAUNCH(4, 256); else WG_LAUNCH(4, 512); }
   else { if (p.per_sm == 2) WG_LAUNCH(8, 256); else WG_LAUNCH(8, 512); }
 #undef WG_LAUNCH
   geeco_count_launch(1);
@@ -2012,7 +2096,7 @@ static int wgrad_gemm(const TcGeom& g, int Cout, const __nv_bfloat16* src, const
 // partial-only variant: the caller performs the reduction (conv1 pixel-pair classes)
 int launch_tc_wgrad_partial(const TcGeom& g_in, int Cout, const __nv_bfloat16* src, const __nv_bfloat16* G, float* partial,
                             long long partial_cap, int want_ones, int* splits_out, int* mrows_out, cudaStream_t st) {
-  const TcGeom g = gather_view(g_in);
+  const TcGeom g = gather_view(g_in);       // (the pixel-pair classes of conv1: software gather)
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) { geeco_set_error("tc_wgrad_partial: empty problem"); return GEECO_ERR_INVALID; }
   WgradPlan p;
@@ -2025,14 +2109,15 @@ int launch_tc_wgrad_partial(const TcGeom& g_in, int Cout, const __nv_bfloat16* s
 int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* src, const __nv_bfloat16* G, float* dW,
                     float* dbias, float* partial, long long partial_cap, long long dw_group_stride,
                     long long dbias_group_stride, cudaStream_t st) {
-  const TcGeom g = gather_view(g_in);       // the weight-gradient kernel gathers its operands itself (dense K)
+  // software gather (dense K) or TMA-fed operands (every tap padded to whole 64-channel chunks)
+  const TcGeom g = wgrad_view(g_in, Cout);
   const long long Mg = (long long)g.imgs_per_group * g.Hm * g.Wm;
   if (Mg <= 0) return GEECO_OK;
   WgradPlan p;
   static const bool no_direct = getenv("GEECO_TC_WGRAD_NO_DIRECT") != nullptr;
   // a single split needs no reduction when the stored channels are the real ones (reduction index = dW row)
   WgDirect direct = {dW, dbias, dw_group_stride, dbias_group_stride};
-  const bool can_direct = !no_direct && g.Cs == Cw;
+  const bool can_direct = !no_direct && g.Kt == Cw;
   int rc = wgrad_gemm(g, Cout, src, G, partial, partial_cap, dbias != nullptr, &p, st, can_direct ? &direct : nullptr);
   if (rc) return rc;
   if (dbias && p.ones_col < 0) { geeco_set_error("tc_wgrad: no padding column for the bias gradient"); return GEECO_ERR_INVALID; }
@@ -2043,16 +2128,16 @@ int launch_tc_wgrad(const TcGeom& g_in, int Cout, int Cw, const __nv_bfloat16* s
   if (p.splits <= 12 && tiles >= 2 * num_sms()) {
     // few splits, many outputs (conv5-conv8)
     GEECO_LAUNCH((wgrad_reduce_t_kernel<4>), tgrid, dim3(32, 8), 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
-                                                           g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
+                                                           g.Kt, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
   } else if (tiles >= 64) {
     // more splits (conv3, conv4): one output channel per thread, 1024 threads per tile
     GEECO_LAUNCH((wgrad_reduce_t_kernel<1>), tgrid, dim3(32, 32), 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout,
-                                                            g.Cs, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
+                                                            g.Kt, Cw, g.Ktot, ones, dw_group_stride, dbias_group_stride);
   } else {
     // many splits, few outputs (conv1, conv2): one thread per output, no transpose
     const long long total = (long long)(g.Ktot + 1) * Cout * g.groups;
     int rb = ceil_div(total, 256); if (rb > 148 * 8) rb = 148 * 8;
-    GEECO_LAUNCH((wgrad_reduce_kernel), rb, 256, 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Cs, Cw,
+    GEECO_LAUNCH((wgrad_reduce_kernel), rb, 256, 0, st, partial, dW, dbias, p.splits, g.groups, p.Mrows_pad, g.Kpad, Cout, g.Kt, Cw,
                                             g.Ktot, ones, dw_group_stride, dbias_group_stride);
   }
   geeco_count_launch(1);
