@@ -273,8 +273,10 @@ template <> struct FrameLoad<unsigned char> {
   static __device__ __forceinline__ float4 at_l1(const unsigned char* base, long long i4, const float* lut) { return at(base, i4, lut); }
 };
 
+// uint8 frames: two CTAs per SM (64 registers per thread).  The kernel is latency-bound; at 80 registers only one
+// 512-thread CTA fitted (ncu: 25 % of the warp slots, 15 clusters of 8 resident, 1.6 TB/s).
 template <typename InT, typename OutT, int CP, int C, int K>
-__global__ void __launch_bounds__(RP_THREADS) preprocess_geecof_kernel(
+__global__ void __launch_bounds__(RP_THREADS, sizeof(InT) == 1 ? 2 : 1) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
     AlphaTab al, int ring_start, const int* __restrict__ frame_index, const int* __restrict__ target_index, int dbg) {
