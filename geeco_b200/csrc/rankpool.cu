@@ -273,10 +273,10 @@ template <> struct FrameLoad<unsigned char> {
   static __device__ __forceinline__ float4 at_l1(const unsigned char* base, long long i4, const float* lut) { return at(base, i4, lut); }
 };
 
-// uint8 frames: two CTAs per SM (64 registers per thread).  The kernel is latency-bound; at 80 registers only one
-// 512-thread CTA fitted (ncu: 25 % of the warp slots, 15 clusters of 8 resident, 1.6 TB/s).
+// Two CTAs per SM (64 registers per thread).  The kernel is latency-bound; at 80 registers only one 512-thread CTA
+// fitted (ncu, uint8 frames: 25 % of the warp slots, 15 clusters of 8 resident, 1.6 TB/s).
 template <typename InT, typename OutT, int CP, int C, int K>
-__global__ void __launch_bounds__(RP_THREADS, sizeof(InT) == 1 ? 2 : 1) preprocess_geecof_kernel(
+__global__ void __launch_bounds__(RP_THREADS, 2) preprocess_geecof_kernel(
     const InT* __restrict__ rgb, const InT* __restrict__ tgt, OutT* __restrict__ x0,
     float* __restrict__ dynbuff_f32, float* __restrict__ dyndiff_f32, int N, long long units, long long per_units,
     AlphaTab al, int ring_start, const int* __restrict__ frame_index, const int* __restrict__ target_index, int dbg) {
@@ -471,10 +471,9 @@ static int launch_pre_t(const InT* rgb, const InT* tgt, void* x0, float* db, flo
   long long units = (long long)H * W / 4;
   if (cluster_hint <= 0) { if (const char* e = getenv("GEECO_PRE_CLUSTER")) cluster_hint = atoi(e); }
   int cl = pick_cluster((long long)H * W * C * 4, cluster_hint);
-  // float32 frames: one CTA per SM with a 2x larger slice beats two co-resident CTAs (measured r02, batch 64: 91 vs
-  // 111 us: half as many cluster barriers and second-pass ramps per byte); uint8 frames are LUT-bound and prefer
-  // the occupancy (75 vs 91 us)
-  if (cluster_hint <= 0 && sizeof(InT) == 4 && cl > 1 && (size_t)((units + cl / 2 - 1) / (cl / 2)) * C * 16 <= RP_SMEM_CAP) cl /= 2;
+  // two co-resident CTAs of a 98 KB slice each (the kernel is compiled for 64 registers): float32 frames 84 us at
+  // batch 64 against 92-94 us for one CTA per SM with a slice twice as large (GEECO_PRE_CLUSTER=4), uint8 frames 65 us
+  // against 104 us when 80 registers kept the second CTA out
   long long per_units = (units + cl - 1) / cl;
   size_t smem = (size_t)per_units * C * 16;
   if (smem > RP_SMEM_CAP) {
