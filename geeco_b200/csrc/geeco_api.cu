@@ -304,6 +304,10 @@ static int plan(geeco_ctx* c, char* ws_base) {
     hp.p_b = add_param(c, dsc + hp.name + "/bias", {hp.width});
     c->NH += hp.width;
   }
+  // bucket 0 = LSTM + fc1 + heads (98 % of the bytes): complete as soon as the tail's backward is, before any encoder
+  // gradient -- its all-reduce then has the whole encoder backward to hide behind
+  c->arena_floats = (c->arena_floats + 3) & ~3ll;
+  c->bucket_end[0] = c->arena_floats;
   for (int l = 7; l >= 0; --l) {
     LayerPlan& L = c->layers[l];
     char nm[128];
@@ -315,11 +319,11 @@ static int plan(geeco_ctx* c, char* ws_base) {
       snprintf(nm, sizeof(nm), "%s/conv%d/bias", c->enc_scope[e], l + 1);
       L.p_b[e] = add_param(c, nm, {L.Cout[e]});
     }
-    if (l == 4) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[0] = c->arena_floats; }
-    if (l == 2) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[1] = c->arena_floats; }
+    if (l == 4) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[1] = c->arena_floats; }
+    if (l == 2) { c->arena_floats = (c->arena_floats + 3) & ~3ll; c->bucket_end[2] = c->arena_floats; }
   }
   c->arena_floats = (c->arena_floats + 3) & ~3ll;
-  c->bucket_end[2] = c->arena_floats;
+  c->bucket_end[3] = c->arena_floats;
 
   // ---- workspace
   Carver cv{ws_base, 0};
@@ -401,7 +405,7 @@ extern "C" int geeco_query_sizes(const geeco_config* cfg, geeco_sizes* out) {
   out->arena_floats = tmp.arena_floats;
   out->workspace_bytes = (int64_t)tmp.workspace_bytes;
   out->num_params = (int32_t)tmp.params.size();
-  out->num_buckets = 3;
+  out->num_buckets = 4;
   return GEECO_OK;
 }
 
@@ -461,7 +465,7 @@ extern "C" int geeco_param_info(const geeco_ctx* c, int32_t index, geeco_param_d
 }
 
 extern "C" int geeco_grad_bucket(const geeco_ctx* c, int32_t b, int64_t* offset, int64_t* numel) {
-  if (!c || b < 0 || b > 2 || !offset || !numel) { geeco_set_error("grad_bucket: bad arguments"); return GEECO_ERR_INVALID; }
+  if (!c || b < 0 || b > 3 || !offset || !numel) { geeco_set_error("grad_bucket: bad arguments"); return GEECO_ERR_INVALID; }
   const long long lo = b == 0 ? 0 : c->bucket_end[b - 1];
   *offset = lo; *numel = c->bucket_end[b] - lo;
   return GEECO_OK;
@@ -904,16 +908,14 @@ static int tail_backward(geeco_ctx* c, cudaStream_t st) {
 
 extern "C" int geeco_step_backward(geeco_ctx* c, int32_t bucket, void* stream) {
   if (!c || !c->bound || !c->fwd_done) { geeco_set_error("step_backward: call geeco_step_forward first"); return GEECO_ERR_STATE; }
-  if (bucket < 0 || bucket > 2) { geeco_set_error("step_backward: bucket %d outside [0,2]", bucket); return GEECO_ERR_INVALID; }
+  if (bucket < 0 || bucket > 3) { geeco_set_error("step_backward: bucket %d outside [0,3]", bucket); return GEECO_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
   const bool bf16 = c->cfg.precision == GEECO_BF16;
   int rc;
-  if (bucket == 0) {
-    rc = tail_backward(c, st);
-    if (rc) return rc;
-  }
-  const int lhi = bucket == 0 ? 7 : (bucket == 1 ? 3 : 1);
-  const int llo = bucket == 0 ? 4 : (bucket == 1 ? 2 : 0);
+  // bucket 0: LSTM + fc1 + heads; 1: conv8..conv5; 2: conv4, conv3; 3: conv2, conv1
+  if (bucket == 0) return tail_backward(c, st);
+  const int lhi = bucket == 1 ? 7 : (bucket == 2 ? 3 : 1);
+  const int llo = bucket == 1 ? 4 : (bucket == 2 ? 2 : 0);
   if (bf16) return encoders_bwd_bf16(c, lhi, llo, st);
   for (int l = lhi; l >= llo; --l) {
     rc = conv_layer_bwd_f32(c, l, st);
@@ -941,7 +943,7 @@ extern "C" int geeco_train_step(geeco_ctx* c, const geeco_batch* b, const geeco_
   // kernel drain + launch latency, not host enqueue, so the step stays a plain launch sequence.)
   int rc = geeco_step_forward(c, b, out, stream);
   if (rc) return rc;
-  for (int bucket = 0; bucket < 3; ++bucket) {
+  for (int bucket = 0; bucket < 4; ++bucket) {
     rc = geeco_step_backward(c, bucket, stream);
     if (rc) return rc;
   }

@@ -27,7 +27,7 @@ struct geeco_ctx {
   geeco_config cfg;
   std::vector<geeco_param_desc> params;
   long long arena_floats = 0;
-  long long bucket_end[3] = {0, 0, 0};
+  long long bucket_end[4] = {0, 0, 0, 0};
   size_t workspace_bytes = 0;
   bool bound = false, weights_dirty = true, fwd_done = false, uniform8 = true;
   // graph variant (tail.cuh: VAR_*): G encoder weight sets ("groups") of M images each, T LSTM steps

@@ -123,7 +123,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
     setattr(c, k, v)
   s = _lib.GeecoSizes()
   _lib.check(lib.geeco_query_sizes(ctypes.byref(c), ctypes.byref(s)))
-  assert s.num_params == 60 and s.num_buckets == 3 and 7552796 <= s.arena_floats < 7552796 + 4 * 60
+  assert s.num_params == 60 and s.num_buckets == 4 and 7552796 <= s.arena_floats < 7552796 + 4 * 60
   assert s.workspace_bytes > 2 ** 30
   c.img_channels = 5
   with pytest.raises(ValueError):
