@@ -10,7 +10,7 @@
 // Work unit = one row q of G2 = dL/d(pre-activation of conv2) of one image (128 pixels x 48 channels).  It yields the rows
 // 2q and 2q+1 of G1 (256 pixels x 32 channels each) as four input-pixel parity classes (py, px): G1[2q+py][2ox+px] for
 // ox = 0..127, from the G2 rows q-1 and q (TF SAME of an even-sized stride-2 layer pads only after).  A CTA walks a
-// contiguous range of units, so consecutive units share a G2 row and every row is loaded once (ring of 4 rows).
+// contiguous range of units, so consecutive units share a G2 row and every row is loaded once (ring of 3 rows).
 //
 //   data gradient   D[ox][(class, ci)] = sum over the 4 shifted windows (dy, dx) in {0,-1}^2 of G2 window x W2 taps.  The
 //                   classes that use a window are adjacent accumulator columns (order c2 c0 c1 c3), so a window is ONE
