@@ -87,6 +87,7 @@ SYMBOLS = {
     'geeco_step_forward': (C.c_int, [_P, C.POINTER(GeecoBatch), C.POINTER(GeecoOutputs), _P]),
     'geeco_step_backward': (C.c_int, [_P, _I32, _P]),
     'geeco_step_update': (C.c_int, [_P, _F, _P]),
+    'geeco_step_update_buckets': (C.c_int, [_P, _F, _I32, _I32, _P]),
     'geeco_ring_push': (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _I32, _P]),
     'geeco_debug_buffer': (C.c_int, [_P, C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I32)]),
     'geeco_profile_kernel': (C.c_int, [_P, C.c_char_p, _P]),

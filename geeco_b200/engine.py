@@ -440,6 +440,12 @@ class Engine(object):
     _lib.check(self.lib.geeco_step_update(self._ctx, float(grad_scale), self._stream()))
     self.global_step += 1
 
+  def step_update_buckets(self, grad_scale, first, last):
+    """Adam over gradient buckets [first, last] only; the call that includes the last bucket closes the step."""
+    _lib.check(self.lib.geeco_step_update_buckets(self._ctx, float(grad_scale), int(first), int(last), self._stream()))
+    if last == len(self.buckets) - 1:
+      self.global_step += 1
+
   def set_lstm_state(self, state_cm=None):
     p = C.c_void_p(state_cm.data_ptr()) if state_cm is not None else None
     _lib.check(self.lib.geeco_set_lstm_state(self._ctx, p, self._stream()))

@@ -51,10 +51,23 @@ def data_parallel_step(engine, features, labels):
   for b in range(len(engine.buckets)):
     engine.step_backward(b)
     works.append(allreduce_bucket(engine.grad, engine.buckets[b], async_op=True))
-  for w in works:
+  nb = len(works)
+  split = getattr(engine, 'step_update_buckets', None)
+  if split is None or nb < 2:
+    for w in works:
+      if w is not None:
+        w.wait()
+    engine.step_update(1.0 / world)
+    return engine.out_losses
+  # the last bucket (conv2 + conv1) can only be reduced after the last backward kernel: update every other bucket while
+  # its small all-reduce is in flight instead of leaving it exposed in front of the whole optimizer step
+  for w in works[:-1]:
     if w is not None:
       w.wait()
-  engine.step_update(1.0 / world)
+  split(1.0 / world, 0, nb - 2)
+  if works[-1] is not None:
+    works[-1].wait()
+  split(1.0 / world, nb - 1, nb - 1)
   return engine.out_losses
 
 

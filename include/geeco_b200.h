@@ -222,6 +222,11 @@ int geeco_train_step(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outpu
 int geeco_step_forward(geeco_ctx* ctx, const geeco_batch* batch, const geeco_outputs* out, void* stream);
 int geeco_step_backward(geeco_ctx* ctx, int32_t bucket, void* stream);
 int geeco_step_update(geeco_ctx* ctx, float grad_scale, void* stream);
+/* the optimizer step over gradient buckets [first, last] only (0 <= first <= last < num_buckets): lets the host update
+ * the buckets whose all-reduce has finished while a later bucket's is still in flight.  Every bucket exactly once per
+ * step; the call that includes the last bucket closes the step (same arithmetic as geeco_step_update: the reference's
+ * single AdamOptimizer.minimize, estimator.py:243-244, is element-wise). */
+int geeco_step_update_buckets(geeco_ctx* ctx, float grad_scale, int32_t first, int32_t last, void* stream);
 
 /* ---- K-frame history of many environments as a device ring (BASELINE config 4) ------------------------------------
  * The FIFO of predictor.py:140-146 without shifting: writes frame[n] ([N][row_bytes]) into slot `slot` of

@@ -105,6 +105,21 @@ def test_phased_step_equals_fused_step(cuda_device):
     eng.step_backward(b)
   eng.step_update(1.0)
   assert torch.equal(th_fused, eng.theta)
+  # ... and with the optimizer step cut at a bucket boundary (what the data-parallel step does while the last
+  # bucket's all-reduce is in flight); two steps, so that the step counter / bias correction is covered too
+  eng.train_step(feats, labels)
+  th2 = eng.theta.clone()
+  eng.set_params({k: v.float() for k, v in P.items()})
+  eng.adam_m.zero_(); eng.adam_v.zero_(); eng.set_global_step(0)
+  nb = len(eng.buckets)
+  for _ in range(2):
+    eng.step_forward(feats, labels)
+    for b in range(nb):
+      eng.step_backward(b)
+    eng.step_update_buckets(1.0, 0, nb - 2)
+    eng.step_update_buckets(1.0, nb - 1, nb - 1)
+  assert torch.equal(th2, eng.theta)
+  assert eng.global_step == 2
 
 
 def test_three_steps_track_oracle(cuda_device):
