@@ -176,6 +176,17 @@ parallel.data_parallel_step(e, None, None)
 exp = torch.tensor([1.5] * 4 + [3.0] * 4 + [4.5] * 2)      # mean over ranks of (rank+1)*(b+1)
 assert torch.allclose(-e.theta, exp), e.theta
 assert e.log == ['fwd', 'bwd0', 'bwd1', 'bwd2', 'upd']
+# engines with a per-bucket optimizer step (geeco_step_update_buckets): buckets 0 .. n-2 are updated while the last
+# bucket's all-reduce is in flight, then the last one; same result, every bucket exactly once
+class SplitEngine(FakeEngine):
+  def step_update_buckets(self, scale, first, last):
+    lo, hi = self.buckets[first][0], self.buckets[last][0] + self.buckets[last][1]
+    self.theta[lo:hi] -= self.grad[lo:hi] * scale; self.log.append('upd%%d-%%d' %% (first, last))
+  def step_update(self, scale): raise AssertionError('the split engine must be updated per bucket')
+e2 = SplitEngine()
+parallel.data_parallel_step(e2, None, None)
+assert torch.allclose(-e2.theta, exp), e2.theta
+assert e2.log == ['fwd', 'bwd0', 'bwd1', 'bwd2', 'upd0-1', 'upd2-2']
 e.theta = torch.full((10,), float(rank))
 parallel.broadcast_parameters(e, src=0)
 assert float(e.theta.abs().max()) == 0.0
